@@ -1,0 +1,242 @@
+/*
+ * b200audio.h -- C ABI of libb200audio.so: the B200-native (sm_100a) hot path behind
+ * MLXAudio's Swift protocols.  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the
+ * Blaizzy/mlx-audio-swift checkout).  INTEGRATION.md shows the Swift-side binding.
+ *
+ * Conventions
+ *   - every function returns an int32 status (B2A_OK == 0).  Codes 1..5 map 1:1 onto the cases
+ *     of AudioGenerationError (Sources/MLXAudioCore/Generation/GenerationTypes.swift:66-87);
+ *     the library never aborts the process.  b2a_last_error() returns the message of the last
+ *     failure on the calling thread.
+ *   - handles are opaque, own their device memory and CUDA stream, and are NOT thread-safe:
+ *     one in-flight call per handle ("Threading").
+ *   - the caller owns every host buffer.  `_dev` variants take DEVICE pointers (already resident
+ *     in HBM) plus a cudaStream_t passed as void*; all other variants take HOST pointers and do
+ *     the host<->device copies themselves.
+ *   - there is NO CPU fallback: with no usable CUDA device every create/compute call fails with
+ *     B2A_ERR_CUDA.
+ */
+#ifndef B200AUDIO_H
+#define B200AUDIO_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2A_OK 0
+#define B2A_ERR_MODEL_NOT_INITIALIZED 1 /* AudioGenerationError.modelNotInitialized */
+#define B2A_ERR_GENERATION_FAILED 2     /* .generationFailed   */
+#define B2A_ERR_INVALID_INPUT 3         /* .invalidInput       */
+#define B2A_ERR_AUDIO_DECODING_FAILED 4 /* .audioDecodingFailed */
+#define B2A_ERR_AUDIO_ENCODING_FAILED 5 /* .audioEncodingFailed */
+#define B2A_ERR_CANCELLED 6             /* Task.checkCancellation (LlamaTTS.swift:715) */
+#define B2A_ERR_CUDA 7                  /* no device / CUDA runtime failure */
+
+#define B2A_DTYPE_F32 0
+#define B2A_DTYPE_BF16 1
+#define B2A_DTYPE_I32 2
+
+/* One named host tensor (row-major).  Names follow the reference's safetensors keys. */
+typedef struct b2a_tensor {
+    const char* name;
+    int32_t dtype;
+    int32_t ndim;
+    int64_t shape[4];
+    const void* data;
+} b2a_tensor;
+
+const char* b2a_last_error(void);
+const char* b2a_version(void);
+/* number of visible CUDA devices (0 when none); never fails */
+int32_t b2a_device_count(void);
+/* kernels launched by this library on the calling process so far (for bench.py's gpu_launches) */
+int64_t b2a_launch_count(void);
+
+/* ------------------------------------------------------------------ DSP tables (host math)
+ * hanningWindow  Sources/MLXAudioCore/DSP.swift:15-22  (symmetric; periodic!=0 gives the
+ *                WhisperAudio.swift:42-43 window)
+ * melFilters     Sources/MLXAudioCore/DSP.swift:76-168 ; out is [n_fft/2+1, n_mels] row-major;
+ *                f_max < 0 means sample_rate/2; mel_scale 0 = htk, 1 = slaney; norm_slaney 0/1. */
+int32_t b2a_hanning_window(int32_t size, int32_t periodic, float* out);
+int32_t b2a_mel_filters(int32_t sample_rate, int32_t n_fft, int32_t n_mels, float f_min, float f_max,
+                        int32_t norm_slaney, int32_t mel_scale, float* out);
+
+/* ------------------------------------------------------------------ streaming log-mel
+ * Replaces class IncrementalMelSpectrogram
+ *   (Sources/MLXAudioSTT/Streaming/IncrementalMelSpectrogram.swift:18-208):
+ *   init(sampleRate:nFft:hopLength:nMels:) :43-62 -> b2a_mel_create
+ *   process(samples:) :68-147 -> b2a_mel_process   (*n_frames == 0  <=>  reference returns nil)
+ *   flush() :151-200          -> b2a_mel_flush
+ *   reset() :203-208          -> b2a_mel_reset
+ *   totalFrames :41           -> b2a_mel_total_frames
+ * `out` receives [n_frames, n_mels] float32; out_cap_frames is its capacity in frames
+ * (B2A_ERR_INVALID_INPUT if too small; b2a_mel_max_frames() gives a safe bound).           */
+typedef struct b2a_mel b2a_mel;
+int32_t b2a_mel_create(int32_t device, int32_t sample_rate, int32_t n_fft, int32_t hop_length,
+                       int32_t n_mels, b2a_mel** out);
+int64_t b2a_mel_max_frames(const b2a_mel* h, int64_t n_samples);
+int32_t b2a_mel_process(b2a_mel* h, const float* samples, int64_t n_samples, float* out,
+                        int64_t out_cap_frames, int64_t* n_frames);
+int32_t b2a_mel_flush(b2a_mel* h, float* out, int64_t out_cap_frames, int64_t* n_frames);
+int32_t b2a_mel_reset(b2a_mel* h);
+int64_t b2a_mel_total_frames(const b2a_mel* h);
+void b2a_mel_destroy(b2a_mel* h);
+
+/* ------------------------------------------------------------------ offline / batched log-mel
+ * kind 0: computeMelSpectrogram (Sources/MLXAudioCore/DSP.swift:230-273): symmetric Hann, HTK
+ *         scale, reflect pad both sides, global max-8 clamp, out [B, 1+n/hop, n_mels].
+ * kind 1: WhisperAudio.encoderFeatures (Sources/MLXAudioSTT/Models/Whisper/WhisperAudio.swift:
+ *         7-13,38-87): pad/trim each clip to 480000, periodic Hann, Slaney scale, last frame
+ *         dropped, per-clip max-8 clamp, out [B, 3000, n_mels].
+ * pcm is [B, n_samples] (every clip the same length); b2a_logmel_frames gives frames per clip. */
+typedef struct b2a_logmel b2a_logmel;
+int32_t b2a_logmel_create(int32_t device, int32_t kind, int32_t sample_rate, int32_t n_fft,
+                          int32_t hop_length, int32_t n_mels, b2a_logmel** out);
+int64_t b2a_logmel_frames(const b2a_logmel* h, int64_t n_samples);
+int32_t b2a_logmel_compute(b2a_logmel* h, const float* pcm, int32_t batch, int64_t n_samples, float* out);
+int32_t b2a_logmel_compute_dev(b2a_logmel* h, const float* d_pcm, int32_t batch, int64_t n_samples,
+                               float* d_out, void* stream);
+void b2a_logmel_destroy(b2a_logmel* h);
+
+/* ------------------------------------------------------------------ SNAC codec
+ * Replaces class SNAC (Sources/MLXAudioCodecs/SNAC/SNACDecoder.swift:12-131) behind the
+ * AudioCodecModel protocol (Sources/MLXAudioCodecs/AudioCodecModel.swift:4-27):
+ *   SNAC.fromConfig/fromModelDirectory :135-189 -> b2a_snac_create (config + named tensors)
+ *   decode(_ codes:) :127-131 / decodeAudio :199 -> b2a_snac_decode
+ *   quantizer(z) (ResidualVectorQuantize.callAsFunction, SNAC/VQ.swift:150-163), the
+ *   encode-side code search                      -> b2a_snac_quantize
+ * codes[i] is [B, T_i] int32 with T_i = t_latent / vq_strides[i]; wave is [B, 1, t_latent*hop].
+ * noise[i] (nullable array of nullable pointers) is the [B, 1, T] Gaussian draw of decoder
+ * block i's NoiseBlock (Layers.swift:263-279); NULL = draw on device from `seed`
+ * (noise_mode 0) or use zero noise (noise_mode 1).                                          */
+typedef struct b2a_snac_config {
+    int32_t sampling_rate;
+    int32_t encoder_dim;
+    int32_t n_encoder_rates;
+    int32_t encoder_rates[8];
+    int32_t latent_dim; /* 0 => encoder_dim * 2^n_encoder_rates */
+    int32_t decoder_dim;
+    int32_t n_decoder_rates;
+    int32_t decoder_rates[8];
+    int32_t attn_window_size; /* 0 => none (only value supported) */
+    int32_t codebook_size;
+    int32_t codebook_dim;
+    int32_t n_vq_strides;
+    int32_t vq_strides[8];
+    int32_t noise;
+    int32_t depthwise;
+} b2a_snac_config;
+
+typedef struct b2a_snac b2a_snac;
+int32_t b2a_snac_create(int32_t device, const b2a_snac_config* cfg, const b2a_tensor* tensors,
+                        int32_t n_tensors, b2a_snac** out);
+int64_t b2a_snac_hop_length(const b2a_snac* h);
+int32_t b2a_snac_decode(b2a_snac* h, const int32_t* const* codes, int32_t batch, int64_t t_latent,
+                        const float* const* noise, int32_t noise_mode, uint64_t seed, float* wave);
+int32_t b2a_snac_decode_dev(b2a_snac* h, const int32_t* const* d_codes, int32_t batch, int64_t t_latent,
+                            const float* const* d_noise, int32_t noise_mode, uint64_t seed,
+                            float* d_wave, void* stream);
+/* z [B, latent_dim, T] float32 -> codes[i] [B, T/stride_i] int32 (+ optional z_q [B, latent, T]) */
+int32_t b2a_snac_quantize(b2a_snac* h, const float* z, int32_t batch, int64_t t_latent,
+                          int32_t* const* codes, float* z_q);
+void b2a_snac_destroy(b2a_snac* h);
+
+/* ------------------------------------------------------------------ Orpheus / Llama TTS
+ * Replaces class LlamaTTSModel (Sources/MLXAudioTTS/Models/Llama/LlamaTTS.swift:354-977) behind
+ * SpeechGenerationModel (Sources/MLXAudioTTS/Generation.swift:8-39):
+ *   fromModelDirectory :942-977 (weights + config)   -> b2a_tts_create
+ *   callAsFunction(_:cache:) :557-567                -> b2a_tts_forward_logits (parity hook)
+ *   generate(text:voice:...) :658-765                -> b2a_tts_generate
+ *   generateStream :777-913 (.token/.info/.audio)    -> b2a_tts_generate + on_token callback
+ *   Task cancellation :715,911                       -> b2a_tts_cancel
+ * Tokenisation stays host-side: the ABI takes token ids already framed by prepareInputIds
+ * (:446-553; b2a_tts_prepare_input_ids does the framing for raw text-token ids).
+ * A batch is B independent utterances ("batched == serial"; the reference itself is batch-1). */
+typedef struct b2a_llama_config {
+    int32_t hidden_size;
+    int32_t num_hidden_layers;
+    int32_t intermediate_size;
+    int32_t num_attention_heads;
+    int32_t num_key_value_heads;
+    int32_t head_dim;
+    int32_t vocab_size;
+    float rms_norm_eps;
+    float rope_theta;
+    float rope_factor; /* llama3 rope_scaling (LlamaTTS.swift:114-118) */
+    float rope_low_freq_factor;
+    float rope_high_freq_factor;
+    float rope_old_context_len;
+    int32_t tie_word_embeddings;
+    int32_t max_batch;   /* KV-cache rows */
+    int32_t max_context; /* KV-cache positions per row */
+} b2a_llama_config;
+
+/* GenerateParameters as used at LlamaTTS.swift:573-581 (defaults 1200 / 0.6 / 0.8 / 1.3 / 20) */
+typedef struct b2a_gen_params {
+    int32_t max_tokens;
+    float temperature; /* 0 => greedy argmax, lowest index wins ties */
+    float top_p;
+    float repetition_penalty;
+    int32_t repetition_context_size;
+    uint64_t seed;
+    int32_t mask_eos;   /* benchmark only: never stop on 128258 (fixed work) */
+    int32_t wrap_codes; /* benchmark only: codes taken mod 4096 so random-init tokens index the codebook */
+} b2a_gen_params;
+
+/* AudioGenerationInfo (GenerationTypes.swift:14-45) */
+typedef struct b2a_gen_info {
+    int32_t prompt_token_count;
+    int32_t generation_token_count;
+    double prefill_time;
+    double generate_time;
+    double tokens_per_second;
+    double codec_time;
+    double peak_memory_gb;
+} b2a_gen_info;
+
+typedef struct b2a_tts b2a_tts;
+/* on_token(user, utterance, step, token): the .token(Int) events of generateStream (:862) */
+typedef void (*b2a_token_cb)(void* user, int32_t utterance, int32_t step, int32_t token);
+
+int32_t b2a_tts_create(int32_t device, const b2a_llama_config* cfg, const b2a_tensor* tensors,
+                       int32_t n_tensors, b2a_snac* snac /* borrowed, may be NULL */, b2a_tts** out);
+/* [SOH] ids [EOT, EOH], left-padded with 128263 to the longest prompt; out is [B, max_len+3] */
+int32_t b2a_tts_prepare_input_ids(const int32_t* const* prompt_ids, const int32_t* lens, int32_t batch,
+                                  int32_t* out, int32_t* out_len);
+/* One forward over ids [B, L] appended at the cache's current offset (reset_cache != 0 clears
+ * it first); logits_out [B, L, vocab] float32 (host). */
+int32_t b2a_tts_forward_logits(b2a_tts* h, const int32_t* ids, int32_t batch, int32_t len,
+                               int32_t reset_cache, float* logits_out);
+/* Full text-token-ids -> tokens -> (parseOutput, 7-token de-interleave, SNAC decode) -> waveform.
+ * input_ids [B, L] (all rows length L, as produced by b2a_tts_prepare_input_ids or the host).
+ * tokens_out [B, max_tokens] (nullable) receives generated ids, n_tokens_out[B] their counts.
+ * wave_out [B, wave_cap] (nullable => skip the codec) receives each waveform, wave_len[B] its
+ * sample count.  Rows that yield no audio codes report wave_len 0; if every row does the call
+ * fails with B2A_ERR_GENERATION_FAILED ("No audio codes generated", LlamaTTS.swift:752-754).  */
+int32_t b2a_tts_generate(b2a_tts* h, const int32_t* input_ids, int32_t batch, int32_t len,
+                         const b2a_gen_params* params, int32_t* tokens_out, int32_t* n_tokens_out,
+                         float* wave_out, int64_t wave_cap, int64_t* wave_len, b2a_gen_info* info,
+                         b2a_token_cb on_token, void* user);
+/* Device-resident variant for bench.py's `value`: ids already in HBM, waveform left in HBM. */
+int32_t b2a_tts_generate_dev(b2a_tts* h, const int32_t* d_input_ids, int32_t batch, int32_t len,
+                             const b2a_gen_params* params, float* d_wave_out, int64_t wave_cap,
+                             int64_t* wave_len, b2a_gen_info* info);
+int32_t b2a_tts_cancel(b2a_tts* h);
+/* parseOutput (:383-434) and llamaDecodeAudioFromCodes' de-interleave (:41-63), host-side ints.
+ * tokens [B, n]; code_lists_out [B, n] / code_lens[B]; then per row codes0/1/2 sized n/7, 2n/7, 4n/7 */
+int32_t b2a_tts_parse_output(const int32_t* tokens, int32_t batch, int32_t n, int32_t* code_lists_out,
+                             int32_t* code_lens);
+int32_t b2a_tts_deinterleave(const int32_t* code_list, int32_t n, int32_t* codes0, int32_t* codes1,
+                             int32_t* codes2, int32_t* n_frames);
+int32_t b2a_tts_interleave(const int32_t* codes0, const int32_t* codes1, const int32_t* codes2,
+                           int32_t n_frames, int32_t* code_list);
+void b2a_tts_destroy(b2a_tts* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200AUDIO_H */

@@ -1,0 +1,21 @@
+"""mlx-audio-swift_b200: B200-native (sm_100a) speech-inference hot path behind MLXAudio's protocols.
+
+Everything numeric runs in `lib/libb200audio.so` (hand-written CUDA, C ABI in include/b200audio.h);
+this package is the host-side mirror of the reference interface for that path.  No CPU fallback."""
+from . import _ffi
+from ._ffi import AudioGenerationError
+from .dsp import IncrementalMelSpectrogram, LogMel, compute_mel_spectrogram, hanning_window, mel_filters, whisper_encoder_features
+from .snac import SNAC
+from .llama_tts import AudioGenerationInfo, GenerateParameters, LlamaTTSModel
+
+__all__ = ["AudioGenerationError", "IncrementalMelSpectrogram", "LogMel", "compute_mel_spectrogram", "hanning_window",
+           "mel_filters", "whisper_encoder_features", "SNAC", "LlamaTTSModel", "GenerateParameters",
+           "AudioGenerationInfo"]
+
+
+def device_count() -> int:
+    return int(_ffi.lib().b2a_device_count())
+
+
+def launch_count() -> int:
+    return int(_ffi.lib().b2a_launch_count())

@@ -1,0 +1,1103 @@
+// Orpheus / Llama-3 autoregressive step for sm_100a.  Replaces (reference paths):
+//   Sources/MLXAudioTTS/Models/Llama/LlamaTTS.swift:104-202  Llama3ScaledRoPE
+//   Sources/MLXAudioTTS/Models/Llama/LlamaTTS.swift:206-346  attention / MLP / block / inner model
+//   Sources/MLXAudioTTS/Models/Llama/LlamaTTS.swift:557-567  tied lm head
+//   Sources/MLXAudioTTS/Models/Llama/LlamaTTS.swift:658-765  generate loop (+ :383-434 parseOutput,
+//                                                            :41-98 SNAC frame (de)interleave)
+//   mlx-swift-lm 3.31.4 (un-vendored): TopPSampler / RepetitionContext (call sites :691-692)
+//
+// HBM layout: weights bf16 [out, in] row-major (q|k|v fused into one matrix, gate/up row-
+// interleaved so SwiGLU is a GEMV epilogue); KV cache bf16 [layer][B][kv_head][ctx][128];
+// residual stream fp32 [B, H]; GEMV inputs bf16 [B, K] (staged in shared memory per CTA).
+// The whole decode step (embed -> 28 layers -> lm head -> logits processors -> sampler ->
+// bookkeeping) is captured in one CUDA graph and replayed per token; nothing syncs with the
+// host inside the loop except a poll of the "all rows finished" flag every few steps.
+#include "common.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+
+namespace b2a {
+
+typedef __nv_bfloat16 bf16;
+
+constexpr int TOK_START_OF_HUMAN = 128259, TOK_END_OF_HUMAN = 128260, TOK_END_OF_TEXT = 128009;
+constexpr int TOK_START_OF_SPEECH = 128257, TOK_END_OF_SPEECH = 128258, TOK_PAD = 128263;
+constexpr int TOK_AUDIO_OFFSET = 128266;
+
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+__device__ __forceinline__ float bf_lo(unsigned u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf_hi(unsigned u) { return __uint_as_float(u & 0xffff0000u); }
+
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// embed + RMSNorm
+// ------------------------------------------------------------------------------------------------
+// x[b,:] = embed[token[b]]  (fp32 residual stream)
+__global__ void embed_kernel(const int* __restrict__ tokens, const bf16* __restrict__ embed, float* __restrict__ x,
+                             int H, int V) {
+    const int b = blockIdx.x;
+    int tok = tokens[b];
+    tok = min(max(tok, 0), V - 1);
+    for (int i = threadIdx.x; i < H; i += blockDim.x) x[(long long)b * H + i] = __bfloat162float(embed[(long long)tok * H + i]);
+}
+
+// x += delta (optional);  xn = bf16( x * rsqrt(mean(x^2) + eps) * w )
+__global__ void __launch_bounds__(256)
+add_rmsnorm_kernel(float* __restrict__ x, float* __restrict__ delta, const float* __restrict__ w,
+                   bf16* __restrict__ xn, int H, float eps) {
+    __shared__ float red[8];
+    const int b = blockIdx.x;
+    float* xr = x + (long long)b * H;
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < H; i += 256) {
+        float v = xr[i];
+        if (delta) { v += delta[(long long)b * H + i]; xr[i] = v; delta[(long long)b * H + i] = 0.f; }
+        ss += v * v;
+    }
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += red[i];
+    const float r = rsqrtf(tot / (float)H + eps);
+    for (int i = threadIdx.x; i < H; i += 256) xn[(long long)b * H + i] = __float2bfloat16_rn(xr[i] * r * w[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight-streaming GEMV: y[b, n] = sum_k W[n,k] * x[b,k],  NB rows of x in shared memory (bf16),
+// each warp owns ROWS consecutive weight rows and streams them with 16-byte no-allocate loads.
+// ------------------------------------------------------------------------------------------------
+constexpr int GV_MAX_THREADS = 512;
+enum : int { GV_F32 = 0, GV_SWIGLU = 1, GV_F32_ATOMIC = 2 };
+
+// grid = (row tiles, K splits).  blockDim.x = 32 * warps.  With gridDim.y == 2 (GV_F32_ATOMIC) the two
+// K halves are combined with atomicAdd into a zeroed y: a + b is commutative, so the result does not
+// depend on arrival order.
+template <int NB, int ROWS, int EPI>
+__global__ void __launch_bounds__(GV_MAX_THREADS)
+gemv_bf16_kernel(const bf16* __restrict__ W, const bf16* __restrict__ xin, float* __restrict__ y,
+                 bf16* __restrict__ act, int N, int K) {
+    extern __shared__ uint4 sx[];  // [NB][Kc/8]
+    const int K8 = K >> 3;
+    const int Kc8 = K8 / gridDim.y, kbase = blockIdx.y * Kc8;
+    for (int i = threadIdx.x; i < NB * Kc8; i += blockDim.x) {
+        const int b = i / Kc8, k = i - b * Kc8;
+        sx[i] = reinterpret_cast<const uint4*>(xin)[(long long)b * K8 + kbase + k];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row0 = (blockIdx.x * (blockDim.x >> 5) + warp) * ROWS;
+    if (row0 >= N) return;
+    const uint4* Wr[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+        Wr[r] = reinterpret_cast<const uint4*>(W) + (long long)min(row0 + r, N - 1) * K8 + kbase;
+
+    float acc[ROWS][NB];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+        for (int b = 0; b < NB; ++b) acc[r][b] = 0.f;
+
+#pragma unroll 2
+    for (int k8 = lane; k8 < Kc8; k8 += 32) {
+        uint4 wv[ROWS];
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) wv[r] = ldg_stream(Wr[r] + k8);
+        float wf[ROWS][8];
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            wf[r][0] = bf_lo(wv[r].x); wf[r][1] = bf_hi(wv[r].x); wf[r][2] = bf_lo(wv[r].y); wf[r][3] = bf_hi(wv[r].y);
+            wf[r][4] = bf_lo(wv[r].z); wf[r][5] = bf_hi(wv[r].z); wf[r][6] = bf_lo(wv[r].w); wf[r][7] = bf_hi(wv[r].w);
+        }
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const uint4 xv = sx[b * Kc8 + k8];
+            const float xf[8] = {bf_lo(xv.x), bf_hi(xv.x), bf_lo(xv.y), bf_hi(xv.y),
+                                 bf_lo(xv.z), bf_hi(xv.z), bf_lo(xv.w), bf_hi(xv.w)};
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[r][b] = fmaf(wf[r][j], xf[j], acc[r][b]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+        for (int b = 0; b < NB; ++b) acc[r][b] = warp_sum(acc[r][b]);
+    if (lane == 0) {
+        if (EPI == GV_F32) {
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r)
+                if (row0 + r < N)
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) y[(long long)b * N + row0 + r] = acc[r][b];
+        } else if (EPI == GV_F32_ATOMIC) {
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r)
+                if (row0 + r < N)
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) atomicAdd(&y[(long long)b * N + row0 + r], acc[r][b]);
+        } else {  // rows are (gate, up) pairs: act[b, n/2] = bf16(silu(gate) * up)   (LlamaTTS.swift:282-284)
+#pragma unroll
+            for (int r = 0; r < ROWS; r += 2)
+                if (row0 + r + 1 < N)
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) {
+                        const float g = acc[r][b], u = acc[r + 1][b];
+                        act[(long long)b * (N / 2) + (row0 + r) / 2] = __float2bfloat16_rn(g / (1.0f + __expf(-g)) * u);
+                    }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Decode attention for one (kv head, row): RoPE on q/k, append k/v to the cache, softmax(qK^T)V
+// over positions 0..pos.  G = q heads per kv head.  (LlamaTTS.swift:235-266)
+// ------------------------------------------------------------------------------------------------
+constexpr int HD = 128, AT_THREADS = 128, MAXG = 8;
+
+__global__ void __launch_bounds__(AT_THREADS)
+attn_decode_kernel(const float* __restrict__ qkv, const int* __restrict__ pos_arr, const float* __restrict__ freqs,
+                   bf16* __restrict__ kcache, bf16* __restrict__ vcache, bf16* __restrict__ out, int nq, int nkv,
+                   int max_ctx, int max_batch_stride, float scale) {
+    extern __shared__ float sm[];  // q [G][HD] | scores [G][max_ctx]
+    const int G = nq / nkv;
+    float* sq = sm;
+    float* sc = sm + G * HD;
+    __shared__ float red[AT_THREADS / 32][MAXG];
+    __shared__ float stat[2][MAXG];
+
+    const int h = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
+    const int p = pos_arr[b];
+    if (p < 0 || p >= max_ctx) return;
+    const int qkv_ld = (nq + 2 * nkv) * HD;
+    const float* row = qkv + (long long)b * qkv_ld;
+    bf16* kc = kcache + (((long long)b * nkv + h) * max_ctx) * HD;
+    bf16* vc = vcache + (((long long)b * nkv + h) * max_ctx) * HD;
+    (void)max_batch_stride;
+
+    if (d < HD / 2) {  // MLXFast.RoPE(traditional:false, freqs:): angle = pos / freqs[i], pairs (i, i+64)
+        float s, c;
+        sincosf((float)p / freqs[d], &s, &c);
+        for (int g = 0; g < G; ++g) {
+            const float* q = row + (h * G + g) * HD;
+            const float x1 = q[d], x2 = q[d + HD / 2];
+            sq[g * HD + d] = bf16_round(x1 * c - x2 * s);
+            sq[g * HD + d + HD / 2] = bf16_round(x2 * c + x1 * s);
+        }
+        const float* k = row + (nq + h) * HD;
+        const float x1 = k[d], x2 = k[d + HD / 2];
+        kc[(long long)p * HD + d] = __float2bfloat16_rn(x1 * c - x2 * s);
+        kc[(long long)p * HD + d + HD / 2] = __float2bfloat16_rn(x2 * c + x1 * s);
+    }
+    vc[(long long)p * HD + d] = __float2bfloat16_rn(row[(nq + nkv + h) * HD + d]);
+    __syncthreads();
+
+    // scores: one key per thread
+    float lmax[MAXG];
+    for (int g = 0; g < G; ++g) lmax[g] = -INFINITY;
+    for (int t = d; t <= p; t += AT_THREADS) {
+        const uint4* kr = reinterpret_cast<const uint4*>(kc + (long long)t * HD);
+        float acc[MAXG];
+        for (int g = 0; g < G; ++g) acc[g] = 0.f;
+#pragma unroll 4
+        for (int c8 = 0; c8 < HD / 8; ++c8) {
+            const uint4 kv = kr[c8];
+            const float kf[8] = {bf_lo(kv.x), bf_hi(kv.x), bf_lo(kv.y), bf_hi(kv.y),
+                                 bf_lo(kv.z), bf_hi(kv.z), bf_lo(kv.w), bf_hi(kv.w)};
+            for (int g = 0; g < G; ++g) {
+                const float* q = sq + g * HD + c8 * 8;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[g] = fmaf(q[j], kf[j], acc[g]);
+            }
+        }
+        for (int g = 0; g < G; ++g) {
+            const float s = acc[g] * scale;
+            sc[g * max_ctx + t] = s;
+            lmax[g] = fmaxf(lmax[g], s);
+        }
+    }
+    for (int g = 0; g < G; ++g) {
+        float m = lmax[g];
+        for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if ((d & 31) == 0) red[d >> 5][g] = m;
+    }
+    __syncthreads();
+    if (d < G) {
+        float m = red[0][d];
+        for (int i = 1; i < AT_THREADS / 32; ++i) m = fmaxf(m, red[i][d]);
+        stat[0][d] = m;
+    }
+    __syncthreads();
+    float lsum[MAXG];
+    for (int g = 0; g < G; ++g) lsum[g] = 0.f;
+    for (int t = d; t <= p; t += AT_THREADS)
+        for (int g = 0; g < G; ++g) {
+            const float e = __expf(sc[g * max_ctx + t] - stat[0][g]);
+            sc[g * max_ctx + t] = e;
+            lsum[g] += e;
+        }
+    __syncthreads();
+    for (int g = 0; g < G; ++g) {
+        const float s = warp_sum(lsum[g]);
+        if ((d & 31) == 0) red[d >> 5][g] = s;
+    }
+    __syncthreads();
+    if (d < G) {
+        float s = 0.f;
+        for (int i = 0; i < AT_THREADS / 32; ++i) s += red[i][d];
+        stat[1][d] = s;
+    }
+    __syncthreads();
+    // PV: one output dim per thread
+    float o[MAXG];
+    for (int g = 0; g < G; ++g) o[g] = 0.f;
+    for (int t = 0; t <= p; ++t) {
+        const float v = __bfloat162float(vc[(long long)t * HD + d]);
+        for (int g = 0; g < G; ++g) o[g] = fmaf(sc[g * max_ctx + t], v, o[g]);
+    }
+    for (int g = 0; g < G; ++g)
+        out[(long long)b * nq * HD + (h * G + g) * HD + d] = __float2bfloat16_rn(o[g] / stat[1][g]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Logits processors + sampler + bookkeeping: one CTA per row.
+// ------------------------------------------------------------------------------------------------
+constexpr int SM_THREADS = 1024, SM_BINS = 2048;
+
+struct SampleArgs {
+    float* logits;        // [B, V]  (modified in place: penalty, EOS mask)
+    float* probs;         // [B, V]  scratch
+    int* tokens;          // [B] next input token (written)
+    int* pos;             // [B] position of the NEXT input token (incremented)
+    int* recent;          // [B, R] ring of the last R tokens (prompt + generated)
+    int* recent_n;        // [B] total tokens pushed so far
+    int* out_tokens;      // [B, max_tokens]
+    int* n_gen;           // [B]
+    int* done;            // [B]
+    int* n_active;        // [1] rows not yet finished (decremented when a row emits EOS)
+    const int* forced;    // nullable [B]: if set, ignore the sampler and emit forced[b] (prefill)
+    int V, R, max_tokens;
+    float temperature, top_p, rep_penalty;
+    unsigned long long seed;
+    int mask_eos;
+};
+
+__device__ __forceinline__ float block_sum_1024(float v, float* sred) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < SM_THREADS / 32; ++i) t += sred[i];
+    return t;
+}
+
+// crossing bin of a histogram scanned from the top: max{i : sum_{j>=i} hist[j] >= target}
+__device__ int find_crossing_bin(const float* hist, int nbins, float target, float* above_out, float* sred,
+                                 int* sres) {
+    // each thread owns bins [2t, 2t+1]; suffix sums via warp shuffles
+    const int t = threadIdx.x;
+    const float h0 = (2 * t < nbins) ? hist[2 * t] : 0.f, h1 = (2 * t + 1 < nbins) ? hist[2 * t + 1] : 0.f;
+    float s = h0 + h1;  // inclusive suffix over threads >= t
+    const int lane = t & 31, warp = t >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float n = __shfl_down_sync(0xffffffffu, s, o);
+        if (lane + o < 32) s += n;
+    }
+    __syncthreads();
+    if (lane == 0) sred[warp] = s;
+    if (t == 0) *sres = -1;
+    __syncthreads();
+    float higher = 0.f;
+    for (int w = warp + 1; w < SM_THREADS / 32; ++w) higher += sred[w];
+    s += higher;                      // sum over bins >= 2t
+    const float s1 = s - h0;          // sum over bins >= 2t+1
+    int cand = -1;
+    if (2 * t + 1 < nbins && s1 >= target) cand = 2 * t + 1;
+    else if (2 * t < nbins && s >= target) cand = 2 * t;
+    if (cand >= 0) atomicMax(sres, cand);
+    __syncthreads();
+    int r = *sres;
+    if (r < 0) r = 0;
+    __syncthreads();
+    if (t == r / 2) *above_out = (r & 1) ? (s1 - h1) : s1;  // mass strictly above bin r
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(SM_THREADS)
+sample_kernel(SampleArgs a) {
+    __shared__ float hist[SM_BINS];
+    __shared__ float sred[SM_THREADS / 32];
+    __shared__ int sres;
+    __shared__ float sabove;
+    __shared__ int s_tok;
+    __shared__ float s_val[SM_THREADS / 32];
+    __shared__ int s_idx[SM_THREADS / 32];
+    const int b = blockIdx.x, t = threadIdx.x;
+    float* lg = a.logits + (long long)b * a.V;
+    float* pr = a.probs + (long long)b * a.V;
+    const int nrec = min(a.recent_n[b], a.R);
+
+    if (a.forced == nullptr) {
+        // RepetitionContext.process: once per unique token among the last R
+        if (a.rep_penalty != 1.0f && t < nrec) {
+            const int tok = a.recent[b * a.R + t];
+            bool dup = false;
+            for (int j = 0; j < t; ++j) dup |= (a.recent[b * a.R + j] == tok);
+            if (!dup && tok >= 0 && tok < a.V) {
+                const float l = lg[tok];
+                lg[tok] = l < 0.f ? l * a.rep_penalty : l / a.rep_penalty;
+            }
+        }
+        if (a.mask_eos && t == 0 && TOK_END_OF_SPEECH < a.V) lg[TOK_END_OF_SPEECH] = -INFINITY;
+        __syncthreads();
+
+        // max (and argmax, lowest index wins ties)
+        float best = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int i = t; i < a.V; i += SM_THREADS) {
+            const float v = lg[i];
+            if (v > best) { best = v; bi = i; }
+        }
+        for (int o = 16; o; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if ((t & 31) == 0) { s_val[t >> 5] = best; s_idx[t >> 5] = bi; }
+        __syncthreads();
+        if (t == 0) {
+            for (int i = 1; i < SM_THREADS / 32; ++i)
+                if (s_val[i] > best || (s_val[i] == best && s_idx[i] < bi)) { best = s_val[i]; bi = s_idx[i]; }
+            s_val[0] = best; s_tok = bi;
+        }
+        __syncthreads();
+        const float mx = s_val[0];
+
+        if (a.temperature > 0.f) {
+            // TopPSampler: p = softmax(l / T); keep the smallest top set whose mass reaches top_p
+            const float inv_t = 1.0f / a.temperature;
+            float z = 0.f;
+            for (int i = t; i < a.V; i += SM_THREADS) {
+                const float e = __expf((lg[i] - mx) * inv_t);
+                pr[i] = e;
+                z += e;
+            }
+            z = block_sum_1024(z, sred);
+            unsigned prefix = 0, pmask = 0;
+            float above = 0.f;
+            if (a.top_p < 1.0f) {
+                const float target = a.top_p * z;
+                const int shifts[3] = {22, 11, 0}, nb[3] = {1024, 2048, 2048};
+                for (int lv = 0; lv < 3; ++lv) {
+                    for (int i = t; i < SM_BINS; i += SM_THREADS) hist[i] = 0.f;
+                    __syncthreads();
+                    for (int i = t; i < a.V; i += SM_THREADS) {
+                        const unsigned u = __float_as_uint(pr[i]);
+                        if ((u & pmask) == prefix) atomicAdd(&hist[(u >> shifts[lv]) & (nb[lv] - 1)], pr[i]);
+                    }
+                    __syncthreads();
+                    float ab;
+                    const int bin = find_crossing_bin(hist, nb[lv], target - above, &sabove, sred, &sres);
+                    ab = sabove;
+                    above += ab;
+                    prefix |= ((unsigned)bin) << shifts[lv];
+                    pmask |= ((unsigned)(nb[lv] - 1)) << shifts[lv];
+                }
+            }
+            const float thr = __uint_as_float(prefix);  // smallest kept probability (0 when top_p >= 1)
+            // inverse-CDF draw over the kept set in index order
+            const int chunk = (a.V + SM_THREADS - 1) / SM_THREADS;
+            const int i0 = t * chunk, i1 = min(a.V, i0 + chunk);
+            float part = 0.f;
+            for (int i = i0; i < i1; ++i) { const float p = pr[i]; if (p >= thr) part += p; }
+            // exclusive prefix over threads
+            float incl = part;
+            const int lane = t & 31, warp = t >> 5;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const float n = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += n;
+            }
+            __syncthreads();
+            if (lane == 31) sred[warp] = incl;
+            if (t == 0) sres = 0x7fffffff;
+            __syncthreads();
+            float wbase = 0.f, total = 0.f;
+            for (int w = 0; w < SM_THREADS / 32; ++w) { if (w < warp) wbase += sred[w]; total += sred[w]; }
+            incl += wbase;
+            const float excl = incl - part;
+            // uniform in [0,1) from (seed, row, step)
+            unsigned long long zz = a.seed + 0x9E3779B97F4A7C15ull * ((unsigned long long)b * 1000003ull + (unsigned long long)a.n_gen[b] + 1ull);
+            zz = (zz ^ (zz >> 30)) * 0xBF58476D1CE4E5B9ull;
+            zz = (zz ^ (zz >> 27)) * 0x94D049BB133111EBull;
+            zz ^= zz >> 31;
+            const float u01 = (float)(zz >> 40) * (1.0f / 16777216.0f);
+            const float r = u01 * total;
+            if (part > 0.f && r >= excl && r < incl) {
+                float run = excl;
+                int pick = -1;
+                for (int i = i0; i < i1; ++i) {
+                    const float p = pr[i];
+                    if (p >= thr) { run += p; pick = i; if (run > r) break; }
+                }
+                if (pick >= 0) atomicMin(&sres, pick);
+            }
+            __syncthreads();
+            if (t == 0 && sres != 0x7fffffff) s_tok = sres;   // else keep the argmax (numerical corner)
+            __syncthreads();
+        }
+    } else {
+        if (t == 0) s_tok = a.forced[b];
+        __syncthreads();
+    }
+
+    if (t == 0) {
+        const int tok = s_tok;
+        a.tokens[b] = tok;
+        a.pos[b] += 1;
+        const int rn = a.recent_n[b];
+        if (a.R > 0) {
+            // keep `recent` as "last R tokens" in arrival order: shift when full
+            if (rn < a.R) a.recent[b * a.R + rn] = tok;
+            else {
+                for (int j = 1; j < a.R; ++j) a.recent[b * a.R + j - 1] = a.recent[b * a.R + j];
+                a.recent[b * a.R + a.R - 1] = tok;
+            }
+            a.recent_n[b] = rn + 1;
+        }
+        if (a.forced == nullptr && !a.done[b]) {
+            if (tok == TOK_END_OF_SPEECH) {      // LlamaTTS.swift:734-736: stop, token not appended
+                a.done[b] = 1;
+                atomicSub(a.n_active, 1);
+            } else {
+                const int n = a.n_gen[b];
+                if (n < a.max_tokens) a.out_tokens[b * a.max_tokens + n] = tok;
+                a.n_gen[b] = n + 1;
+                if (n + 1 >= a.max_tokens) { a.done[b] = 1; atomicSub(a.n_active, 1); }
+            }
+        }
+    }
+}
+
+// prefill bookkeeping for positions that do not need logits: next token = ids[b, pos+1]
+__global__ void prefill_advance_kernel(const int* __restrict__ ids, int L, int* tokens, int* pos, int B) {
+    const int b = threadIdx.x;
+    if (b >= B) return;
+    const int p = pos[b] + 1;
+    pos[b] = p;
+    if (p < L) tokens[b] = ids[b * L + p];
+}
+
+__global__ void init_rows_kernel(const int* __restrict__ ids, int L, int B, int R, int* tokens, int* pos, int* recent,
+                                 int* recent_n, int* n_gen, int* done, int* n_active, int start_pos) {
+    const int b = threadIdx.x;
+    if (b == 0) *n_active = B;
+    if (b >= B) return;
+    tokens[b] = ids[b * L];
+    pos[b] = start_pos;
+    n_gen[b] = 0;
+    done[b] = 0;
+    // processor.prompt(promptTokens): the ring starts with the last R prompt tokens
+    const int n = min(R, L);
+    for (int j = 0; j < n; ++j) recent[b * R + j] = ids[b * L + L - n + j];
+    recent_n[b] = n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+static std::vector<float> llama3_freqs(const b2a_llama_config& c) {
+    // LlamaTTS.swift:121-156 in Float
+    const int d = c.head_dim;
+    std::vector<float> f(d / 2);
+    const float low_wl = c.rope_old_context_len / c.rope_low_freq_factor;
+    const float high_wl = c.rope_old_context_len / c.rope_high_freq_factor;
+    for (int i = 0; i < d / 2; ++i) {
+        float fr = powf(c.rope_theta, (float)(2 * i) / (float)d);
+        const float wl = 2.0f * (float)M_PI * fr;
+        const float base = fr;
+        if (wl > low_wl) fr = fr * c.rope_factor;
+        const bool med = wl > high_wl && wl < low_wl;
+        if (med) {
+            const float smooth = (c.rope_old_context_len / wl - c.rope_low_freq_factor) /
+                                 (c.rope_high_freq_factor - c.rope_low_freq_factor);
+            fr = base / ((1.0f - smooth) / c.rope_factor + smooth);
+        }
+        f[i] = fr;
+    }
+    return f;
+}
+
+struct LayerW {
+    DBuf<bf16> wqkv, wo, wgu, wdown;
+    DBuf<float> ln1, ln2;
+};
+
+}  // namespace b2a
+
+using namespace b2a;
+
+struct b2a_tts {
+    int device;
+    b2a_llama_config cfg;
+    b2a_snac* snac;
+    cudaStream_t stream = nullptr;
+    std::vector<LayerW> layers;
+    DBuf<bf16> embed, lm_head_w;
+    const bf16* lm_head = nullptr;
+    DBuf<float> final_ln, freqs;
+    DBuf<bf16> kcache, vcache;   // [layer][B][nkv][ctx][hd]
+    // activations
+    DBuf<float> x, y, qkv, logits, probs;
+    DBuf<bf16> xn, attn, act;
+    DBuf<int> tokens, pos, recent, recent_n, out_tokens, n_gen, done, n_active, ids, forced;
+    HBuf<int> h_flag;
+    std::atomic<int> cancel{0};
+    int nb_pad = 0;   // rows rounded up to 1/2/4/8
+    // CUDA graphs for the two step flavours (captured per (nb_pad, params) configuration)
+    cudaGraphExec_t g_step = nullptr, g_prefill = nullptr;
+    SampleArgs g_args{};
+    int g_nb = 0;
+    // codec workspaces
+    DBuf<int> d_codes[3];
+    DBuf<float> d_wave;
+
+    ~b2a_tts() {
+        if (g_step) cudaGraphExecDestroy(g_step);
+        if (g_prefill) cudaGraphExecDestroy(g_prefill);
+        if (stream) cudaStreamDestroy(stream);
+    }
+
+    static void upload_bf16(const TensorTable& tt, const std::string& name, int64_t expect, DBuf<bf16>& dst, size_t offset_elems,
+                            size_t total_elems) {
+        const b2a_tensor& t = tt.get(name);
+        B2A_CHECK(t.dtype == B2A_DTYPE_BF16, B2A_ERR_MODEL_NOT_INITIALIZED, "tensor must be bf16: " + name);
+        B2A_CHECK(TensorTable::numel(t) == expect, B2A_ERR_MODEL_NOT_INITIALIZED, "bad shape for tensor: " + name);
+        dst.alloc(total_elems);
+        B2A_CUDA(cudaMemcpy(dst.p + offset_elems, t.data, expect * sizeof(bf16), cudaMemcpyHostToDevice));
+    }
+
+    b2a_tts(int dev, const b2a_llama_config& c, const TensorTable& tt, b2a_snac* sn) : device(dev), cfg(c), snac(sn) {
+        B2A_CHECK(c.head_dim == HD, B2A_ERR_INVALID_INPUT, "llama: head_dim must be 128");
+        B2A_CHECK(c.hidden_size % 8 == 0 && c.intermediate_size % 8 == 0, B2A_ERR_INVALID_INPUT, "llama: sizes must be multiples of 8");
+        B2A_CHECK(c.num_attention_heads % c.num_key_value_heads == 0 && c.num_attention_heads / c.num_key_value_heads <= MAXG,
+                  B2A_ERR_INVALID_INPUT, "llama: unsupported GQA ratio");
+        B2A_CHECK(c.max_batch >= 1 && c.max_batch <= 8, B2A_ERR_INVALID_INPUT, "llama: max_batch must be in 1..8");
+        B2A_CHECK(c.max_context >= 8, B2A_ERR_INVALID_INPUT, "llama: max_context too small");
+        require_device(dev);
+        B2A_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        const int H = c.hidden_size, I = c.intermediate_size, nq = c.num_attention_heads, nkv = c.num_key_value_heads;
+        const int NQ = nq * HD, NKV = nkv * HD;
+        upload_bf16(tt, "model.embed_tokens.weight", (int64_t)c.vocab_size * H, embed, 0, (size_t)c.vocab_size * H);
+        if (c.tie_word_embeddings) lm_head = embed.p;   // embedTokens.asLinear (LlamaTTS.swift:563)
+        else { upload_bf16(tt, "lm_head.weight", (int64_t)c.vocab_size * H, lm_head_w, 0, (size_t)c.vocab_size * H); lm_head = lm_head_w.p; }
+        layers.resize(c.num_hidden_layers);
+        std::vector<bf16> tmp;
+        for (int l = 0; l < c.num_hidden_layers; ++l) {
+            const std::string p = "model.layers." + std::to_string(l) + ".";
+            LayerW& L = layers[l];
+            const size_t qkv_n = (size_t)(NQ + 2 * NKV) * H;
+            upload_bf16(tt, p + "self_attn.q_proj.weight", (int64_t)NQ * H, L.wqkv, 0, qkv_n);
+            upload_bf16(tt, p + "self_attn.k_proj.weight", (int64_t)NKV * H, L.wqkv, (size_t)NQ * H, qkv_n);
+            upload_bf16(tt, p + "self_attn.v_proj.weight", (int64_t)NKV * H, L.wqkv, (size_t)(NQ + NKV) * H, qkv_n);
+            upload_bf16(tt, p + "self_attn.o_proj.weight", (int64_t)H * NQ, L.wo, 0, (size_t)H * NQ);
+            upload_bf16(tt, p + "mlp.down_proj.weight", (int64_t)H * I, L.wdown, 0, (size_t)H * I);
+            // gate / up rows interleaved: row 2n = gate_n, row 2n+1 = up_n
+            const b2a_tensor& tg = tt.get(p + "mlp.gate_proj.weight");
+            const b2a_tensor& tu = tt.get(p + "mlp.up_proj.weight");
+            B2A_CHECK(tg.dtype == B2A_DTYPE_BF16 && tu.dtype == B2A_DTYPE_BF16 && TensorTable::numel(tg) == (int64_t)I * H &&
+                          TensorTable::numel(tu) == (int64_t)I * H,
+                      B2A_ERR_MODEL_NOT_INITIALIZED, "bad gate/up projection: " + p);
+            tmp.resize((size_t)2 * I * H);
+            for (int n = 0; n < I; ++n) {
+                memcpy(&tmp[(size_t)(2 * n) * H], (const bf16*)tg.data + (size_t)n * H, H * sizeof(bf16));
+                memcpy(&tmp[(size_t)(2 * n + 1) * H], (const bf16*)tu.data + (size_t)n * H, H * sizeof(bf16));
+            }
+            L.wgu.alloc(tmp.size());
+            B2A_CUDA(cudaMemcpy(L.wgu.p, tmp.data(), tmp.size() * sizeof(bf16), cudaMemcpyHostToDevice));
+            std::vector<float> g1 = tt.f32(p + "input_layernorm.weight", H), g2 = tt.f32(p + "post_attention_layernorm.weight", H);
+            L.ln1.upload(g1.data(), H);
+            L.ln2.upload(g2.data(), H);
+        }
+        std::vector<float> gf = tt.f32("model.norm.weight", H);
+        final_ln.upload(gf.data(), H);
+        std::vector<float> fr = llama3_freqs(c);
+        freqs.upload(fr.data(), fr.size());
+        const size_t kv = (size_t)c.num_hidden_layers * c.max_batch * nkv * c.max_context * HD;
+        kcache.alloc(kv);
+        vcache.alloc(kv);
+        const int B = 8;
+        x.alloc((size_t)B * H); y.alloc((size_t)B * H); qkv.alloc((size_t)B * (NQ + 2 * NKV));
+        logits.alloc((size_t)B * c.vocab_size); probs.alloc((size_t)B * c.vocab_size);
+        xn.alloc((size_t)B * H); attn.alloc((size_t)B * NQ); act.alloc((size_t)B * I);
+        B2A_CUDA(cudaMemset(xn.p, 0, (size_t)B * H * sizeof(bf16)));
+        B2A_CUDA(cudaMemset(attn.p, 0, (size_t)B * NQ * sizeof(bf16)));
+        B2A_CUDA(cudaMemset(act.p, 0, (size_t)B * I * sizeof(bf16)));
+        B2A_CUDA(cudaMemset(x.p, 0, (size_t)B * H * sizeof(float)));
+        tokens.alloc(B); pos.alloc(B); recent.alloc(B * 64); recent_n.alloc(B); n_gen.alloc(B); done.alloc(B);
+        n_active.alloc(1); forced.alloc(B);
+        B2A_CUDA(cudaMemset(tokens.p, 0, B * sizeof(int)));
+        h_flag.alloc(16);
+        gemv_attrs<1>(); gemv_attrs<2>(); gemv_attrs<4>(); gemv_attrs<8>();
+        const size_t at_sm = (size_t)(nq / nkv) * (HD + c.max_context) * sizeof(float);
+        B2A_CHECK(at_sm <= 200 * 1024, B2A_ERR_INVALID_INPUT, "llama: max_context too large for the attention score tile");
+        B2A_CUDA(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)at_sm));
+        B2A_CUDA(cudaMemset(y.p, 0, (size_t)B * H * sizeof(float)));
+        B2A_CUDA(cudaDeviceSynchronize());
+    }
+
+    template <int NB, int ROWS, int EPI>
+    void gemv_launch(const bf16* W, const bf16* xin, float* yout, bf16* actout, int N, int K, int warps, int ksplit,
+                     cudaStream_t s) {
+        const size_t sm = (size_t)NB * (K / ksplit) * sizeof(bf16);
+        dim3 grid(cdiv(N, warps * ROWS), ksplit);
+        gemv_bf16_kernel<NB, ROWS, EPI><<<grid, warps * 32, sm, s>>>(W, xin, yout, actout, N, K);
+        count_launch();
+    }
+    template <int NB, int ROWS, int EPI>
+    static void gemv_attr() {
+        B2A_CUDA(cudaFuncSetAttribute(gemv_bf16_kernel<NB, ROWS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    }
+    template <int NB>
+    static void gemv_attrs() {
+        gemv_attr<NB, 2, GV_F32>(); gemv_attr<NB, 4, GV_F32>(); gemv_attr<NB, 4, GV_SWIGLU>(); gemv_attr<NB, 2, GV_F32_ATOMIC>();
+    }
+    enum { OP_QKV, OP_O, OP_GU, OP_DOWN, OP_LM };
+    template <int NB>
+    void gemv_op(int op, const bf16* W, const bf16* xin, float* yout, bf16* actout, int N, int K, cudaStream_t s) {
+        switch (op) {
+            case OP_QKV: gemv_launch<NB, 2, GV_F32>(W, xin, yout, actout, N, K, 8, 1, s); break;
+            case OP_O: gemv_launch<NB, 2, GV_F32>(W, xin, yout, actout, N, K, 4, 1, s); break;
+            case OP_GU: gemv_launch<NB, 4, GV_SWIGLU>(W, xin, yout, actout, N, K, 8, 1, s); break;
+            case OP_DOWN:
+                if ((K / 8) % 2 == 0) gemv_launch<NB, 2, GV_F32_ATOMIC>(W, xin, yout, actout, N, K, 4, 2, s);
+                else gemv_launch<NB, 2, GV_F32>(W, xin, yout, actout, N, K, 4, 1, s);
+                break;
+            default: gemv_launch<NB, 4, GV_F32>(W, xin, yout, actout, N, K, 8, 1, s); break;
+        }
+    }
+    void gemv_nb(int op, const bf16* W, const bf16* xin, float* yout, bf16* actout, int N, int K, cudaStream_t s) {
+        B2A_CHECK((size_t)nb_pad * K * sizeof(bf16) <= 160 * 1024 * (op == OP_DOWN ? 2 : 1), B2A_ERR_INVALID_INPUT,
+                  "llama: layer too wide for the shared-memory activation tile");
+        switch (nb_pad) {
+            case 1: gemv_op<1>(op, W, xin, yout, actout, N, K, s); break;
+            case 2: gemv_op<2>(op, W, xin, yout, actout, N, K, s); break;
+            case 4: gemv_op<4>(op, W, xin, yout, actout, N, K, s); break;
+            default: gemv_op<8>(op, W, xin, yout, actout, N, K, s); break;
+        }
+    }
+
+    // embed(tokens) -> all layers; leaves the residual stream in x and the last MLP output in y
+    void run_layers(int B, cudaStream_t s) {
+        const int H = cfg.hidden_size, I = cfg.intermediate_size, nq = cfg.num_attention_heads, nkv = cfg.num_key_value_heads;
+        const int NQ = nq * HD, NKV = nkv * HD, G = nq / nkv;
+        embed_kernel<<<B, 256, 0, s>>>(tokens.p, embed.p, x.p, H, cfg.vocab_size);
+        count_launch();
+        const size_t kv_layer = (size_t)cfg.max_batch * nkv * cfg.max_context * HD;
+        const size_t at_sm = (size_t)(G * HD + G * cfg.max_context) * sizeof(float);
+        for (int l = 0; l < cfg.num_hidden_layers; ++l) {
+            LayerW& L = layers[l];
+            add_rmsnorm_kernel<<<B, 256, 0, s>>>(x.p, l == 0 ? nullptr : y.p, L.ln1.p, xn.p, H, cfg.rms_norm_eps);
+            count_launch();
+            gemv_nb(OP_QKV, L.wqkv.p, xn.p, qkv.p, nullptr, NQ + 2 * NKV, H, s);
+            attn_decode_kernel<<<dim3(nkv, B), AT_THREADS, at_sm, s>>>(qkv.p, pos.p, freqs.p, kcache.p + l * kv_layer,
+                                                                       vcache.p + l * kv_layer, attn.p, nq, nkv, cfg.max_context,
+                                                                       0, 1.0f / sqrtf((float)HD));
+            count_launch();
+            gemv_nb(OP_O, L.wo.p, attn.p, y.p, nullptr, H, NQ, s);
+            add_rmsnorm_kernel<<<B, 256, 0, s>>>(x.p, y.p, L.ln2.p, xn.p, H, cfg.rms_norm_eps);
+            count_launch();
+            gemv_nb(OP_GU, L.wgu.p, xn.p, nullptr, act.p, 2 * I, H, s);
+            gemv_nb(OP_DOWN, L.wdown.p, act.p, y.p, nullptr, H, I, s);
+        }
+    }
+
+    void run_lm_head(int B, cudaStream_t s) {
+        add_rmsnorm_kernel<<<B, 256, 0, s>>>(x.p, y.p, final_ln.p, xn.p, cfg.hidden_size, cfg.rms_norm_eps);
+        count_launch();
+        gemv_nb(OP_LM, lm_head, xn.p, logits.p, nullptr, cfg.vocab_size, cfg.hidden_size, s);
+    }
+    // NOTE: gemv writes y[b*N + n] with N = vocab: logits are [nb_pad, V] row-major.
+
+    void set_batch(int B) {
+        nb_pad = B <= 1 ? 1 : B <= 2 ? 2 : B <= 4 ? 4 : 8;
+    }
+
+    void drop_graphs() {
+        if (g_step) { cudaGraphExecDestroy(g_step); g_step = nullptr; }
+        if (g_prefill) { cudaGraphExecDestroy(g_prefill); g_prefill = nullptr; }
+    }
+
+    static bool same_args(const SampleArgs& a, const SampleArgs& b) {
+        return a.V == b.V && a.R == b.R && a.max_tokens == b.max_tokens && a.temperature == b.temperature &&
+               a.top_p == b.top_p && a.rep_penalty == b.rep_penalty && a.seed == b.seed && a.mask_eos == b.mask_eos &&
+               a.out_tokens == b.out_tokens;
+    }
+
+    void capture(int B, const SampleArgs& sa, int L) {
+        if (g_step && g_nb == B && same_args(sa, g_args) && g_L == L) return;
+        drop_graphs();
+        cudaGraph_t g;
+        B2A_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+        run_layers(B, stream);
+        run_lm_head(B, stream);
+        sample_kernel<<<B, SM_THREADS, 0, stream>>>(sa);
+        count_launch();
+        B2A_CUDA(cudaStreamEndCapture(stream, &g));
+        B2A_CUDA(cudaGraphInstantiate(&g_step, g, 0));
+        cudaGraphDestroy(g);
+        B2A_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+        run_layers(B, stream);
+        prefill_advance_kernel<<<1, 32, 0, stream>>>(ids.p, L, tokens.p, pos.p, B);
+        count_launch();
+        B2A_CUDA(cudaStreamEndCapture(stream, &g));
+        B2A_CUDA(cudaGraphInstantiate(&g_prefill, g, 0));
+        cudaGraphDestroy(g);
+        g_nb = B; g_args = sa; g_L = L;
+        launches_step = 1 + cfg.num_hidden_layers * 7 + 2 + 1;
+        launches_prefill = 1 + cfg.num_hidden_layers * 7 + 1;
+    }
+    int g_L = 0, launches_step = 0, launches_prefill = 0;
+};
+
+// ------------------------------------------------------------------------------------------------
+// host-side token plumbing (ints; the reference does these on the host too)
+// ------------------------------------------------------------------------------------------------
+static std::vector<int> parse_row(const int* row, int n, int crop_after) {
+    // LlamaTTS.swift:400-431 for one row: crop, drop 128258, trim to a multiple of 7, subtract 128266
+    std::vector<int> r;
+    for (int j = crop_after + 1; j < n; ++j)
+        if (row[j] != TOK_END_OF_SPEECH) r.push_back(row[j]);
+    r.resize((r.size() / 7) * 7);
+    for (auto& t : r) t -= TOK_AUDIO_OFFSET;
+    return r;
+}
+
+static void deinterleave(const int* cl, int n, std::vector<int>& l1, std::vector<int>& l2, std::vector<int>& l3) {
+    // llamaDecodeAudioFromCodes, LlamaTTS.swift:46-58
+    const int groups = (n + 1) / 7;
+    for (int i = 0; i < groups; ++i) {
+        const int b = 7 * i;
+        l1.push_back(cl[b]);
+        l2.push_back(cl[b + 1] - 4096);
+        l3.push_back(cl[b + 2] - 2 * 4096);
+        l3.push_back(cl[b + 3] - 3 * 4096);
+        l2.push_back(cl[b + 4] - 4 * 4096);
+        l3.push_back(cl[b + 5] - 5 * 4096);
+        l3.push_back(cl[b + 6] - 6 * 4096);
+    }
+}
+
+static double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// shared body of b2a_tts_generate / _dev.  ids_on_device: input ids pointer is a device pointer.
+static void tts_generate_impl(b2a_tts* h, const int32_t* input_ids, bool ids_on_device, int32_t B, int32_t L,
+                              const b2a_gen_params* gp, int32_t* tokens_out, int32_t* n_tokens_out, float* wave_out,
+                              bool wave_on_device, int64_t wave_cap, int64_t* wave_len, b2a_gen_info* info,
+                              b2a_token_cb on_token, void* user) {
+    B2A_CHECK(h && input_ids && gp, B2A_ERR_INVALID_INPUT, "tts generate: null argument");
+    B2A_CHECK(B >= 1 && B <= h->cfg.max_batch, B2A_ERR_INVALID_INPUT, "tts generate: batch exceeds max_batch");
+    B2A_CHECK(L >= 1, B2A_ERR_INVALID_INPUT, "tts generate: empty prompt");
+    B2A_CHECK(gp->max_tokens >= 1, B2A_ERR_INVALID_INPUT, "tts generate: max_tokens must be positive");
+    B2A_CHECK(L + gp->max_tokens <= h->cfg.max_context, B2A_ERR_INVALID_INPUT, "tts generate: prompt + max_tokens exceeds max_context");
+    B2A_CHECK(gp->repetition_context_size >= 0 && gp->repetition_context_size <= 64, B2A_ERR_INVALID_INPUT,
+              "tts generate: repetition_context_size must be in 0..64");
+    B2A_CHECK(gp->temperature >= 0.f && gp->top_p > 0.f, B2A_ERR_INVALID_INPUT, "tts generate: bad sampling parameters");
+    if (wave_out) B2A_CHECK(h->snac, B2A_ERR_MODEL_NOT_INITIALIZED, "SNAC model not loaded");   // LlamaTTS.swift:672-674
+    B2A_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    h->cancel.store(0);
+    h->set_batch(B);
+    const int MT = gp->max_tokens, R = std::max(1, gp->repetition_context_size);
+    h->ids.alloc((size_t)B * L);
+    h->out_tokens.alloc((size_t)B * MT);
+    h->recent.alloc((size_t)8 * R);
+    B2A_CUDA(cudaMemcpyAsync(h->ids.p, input_ids, (size_t)B * L * sizeof(int),
+                             ids_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+    SampleArgs sa{};
+    sa.logits = h->logits.p; sa.probs = h->probs.p; sa.tokens = h->tokens.p; sa.pos = h->pos.p; sa.recent = h->recent.p;
+    sa.recent_n = h->recent_n.p; sa.out_tokens = h->out_tokens.p; sa.n_gen = h->n_gen.p; sa.done = h->done.p;
+    sa.n_active = h->n_active.p; sa.forced = nullptr; sa.V = h->cfg.vocab_size; sa.R = gp->repetition_context_size > 0 ? R : 0;
+    sa.max_tokens = MT; sa.temperature = gp->temperature; sa.top_p = gp->top_p;
+    sa.rep_penalty = gp->repetition_context_size > 0 ? gp->repetition_penalty : 1.0f;
+    sa.seed = gp->seed; sa.mask_eos = gp->mask_eos;
+    if (sa.R == 0) { sa.R = 1; }
+    h->capture(B, sa, L);
+
+    const double t0 = now_s();
+    init_rows_kernel<<<1, 32, 0, s>>>(h->ids.p, L, B, gp->repetition_context_size > 0 ? R : 0, h->tokens.p, h->pos.p, h->recent.p,
+                                      h->recent_n.p, h->n_gen.p, h->done.p, h->n_active.p, 0);
+    count_launch();
+    // prefill: positions 0..L-2 need no logits; position L-1 runs the full step (logits -> first token)
+    for (int p = 0; p < L - 1; ++p) {
+        B2A_CUDA(cudaGraphLaunch(h->g_prefill, s));
+        count_launch(h->launches_prefill);
+    }
+    B2A_CUDA(cudaStreamSynchronize(s));
+    const double t1 = now_s();
+    int steps = 0;
+    bool cancelled = false;
+    int streamed = 0;
+    std::vector<int> h_tok;
+    while (steps < MT) {
+        const int burst = on_token ? 1 : std::min(16, MT - steps);
+        for (int i = 0; i < burst; ++i) {
+            B2A_CUDA(cudaGraphLaunch(h->g_step, s));
+            count_launch(h->launches_step);
+        }
+        steps += burst;
+        B2A_CUDA(cudaMemcpyAsync(h->h_flag.p, h->n_active.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+        B2A_CUDA(cudaStreamSynchronize(s));
+        if (on_token) {   // .token events (LlamaTTS.swift:862), row-major per step
+            h_tok.resize((size_t)B * MT);
+            std::vector<int> ng(B);
+            B2A_CUDA(cudaMemcpy(ng.data(), h->n_gen.p, B * sizeof(int), cudaMemcpyDeviceToHost));
+            B2A_CUDA(cudaMemcpy(h_tok.data(), h->out_tokens.p, (size_t)B * MT * sizeof(int), cudaMemcpyDeviceToHost));
+            for (int b = 0; b < B; ++b)
+                if (ng[b] > streamed) on_token(user, b, streamed, h_tok[(size_t)b * MT + streamed]);
+            ++streamed;
+        }
+        if (h->cancel.load()) { cancelled = true; break; }
+        if (h->h_flag.p[0] <= 0) break;
+    }
+    const double t2 = now_s();
+    B2A_CHECK(!cancelled, B2A_ERR_CANCELLED, "generation cancelled");
+
+    std::vector<int> ng(B), toks((size_t)B * MT), prompt((size_t)B * L);
+    B2A_CUDA(cudaMemcpyAsync(ng.data(), h->n_gen.p, B * sizeof(int), cudaMemcpyDeviceToHost, s));
+    B2A_CUDA(cudaMemcpyAsync(toks.data(), h->out_tokens.p, (size_t)B * MT * sizeof(int), cudaMemcpyDeviceToHost, s));
+    B2A_CUDA(cudaMemcpyAsync(prompt.data(), h->ids.p, (size_t)B * L * sizeof(int), cudaMemcpyDeviceToHost, s));
+    B2A_CUDA(cudaStreamSynchronize(s));
+    int total_gen = 0;
+    for (int b = 0; b < B; ++b) {
+        ng[b] = std::min(ng[b], MT);
+        total_gen += ng[b];
+        if (n_tokens_out) n_tokens_out[b] = ng[b];
+        if (tokens_out) memcpy(tokens_out + (size_t)b * MT, toks.data() + (size_t)b * MT, ng[b] * sizeof(int));
+    }
+
+    double codec_t = 0;
+    if (wave_out) {
+        const double c0 = now_s();
+        // per row: generatedTokens = prompt + generated (LlamaTTS.swift:705-707,738) -> parseOutput -> frames
+        std::vector<std::vector<int>> l1(B), l2(B), l3(B);
+        std::vector<int> frames(B, 0);
+        bool any = false;
+        for (int b = 0; b < B; ++b) {
+            std::vector<int> all(prompt.begin() + (size_t)b * L, prompt.begin() + (size_t)(b + 1) * L);
+            all.insert(all.end(), toks.begin() + (size_t)b * MT, toks.begin() + (size_t)b * MT + ng[b]);
+            int last = -1;
+            for (int j = 0; j < (int)all.size(); ++j) if (all[j] == TOK_START_OF_SPEECH) last = j;
+            std::vector<int> cl = parse_row(all.data(), (int)all.size(), last);
+            if (gp->wrap_codes)   // benchmark only: fold random-init tokens into each slot's 4096-code range
+                for (size_t i = 0; i < cl.size(); ++i) cl[i] = ((cl[i] % 4096) + 4096) % 4096 + 4096 * (int)(i % 7);
+            deinterleave(cl.data(), (int)cl.size(), l1[b], l2[b], l3[b]);
+            frames[b] = (int)l1[b].size();
+            any |= frames[b] > 0;
+            if (wave_len) wave_len[b] = 0;
+        }
+        B2A_CHECK(any, B2A_ERR_GENERATION_FAILED, "No audio codes generated");   // LlamaTTS.swift:752-754
+        const int64_t hop = b2a_snac_hop_length(h->snac);
+        // group rows with equal frame counts into one batched codec call
+        std::vector<bool> used(B, false);
+        for (int b = 0; b < B; ++b) {
+            if (used[b] || frames[b] == 0) continue;
+            std::vector<int> grp;
+            for (int c = b; c < B; ++c) if (!used[c] && frames[c] == frames[b]) { grp.push_back(c); used[c] = true; }
+            const int F = frames[b], nb = (int)grp.size();
+            const int64_t T = 4ll * F, wl = T * hop;
+            B2A_CHECK(wl <= wave_cap, B2A_ERR_INVALID_INPUT, "tts generate: wave buffer too small");
+            std::vector<int> c0v, c1v, c2v;
+            for (int r : grp) { c0v.insert(c0v.end(), l1[r].begin(), l1[r].end()); c1v.insert(c1v.end(), l2[r].begin(), l2[r].end());
+                                c2v.insert(c2v.end(), l3[r].begin(), l3[r].end()); }
+            h->d_codes[0].upload(c0v.data(), c0v.size(), s);
+            h->d_codes[1].upload(c1v.data(), c1v.size(), s);
+            h->d_codes[2].upload(c2v.data(), c2v.size(), s);
+            h->d_wave.alloc((size_t)nb * wl);
+            const int* dc[3] = {h->d_codes[0].p, h->d_codes[1].p, h->d_codes[2].p};
+            B2A_CUDA(cudaStreamSynchronize(s));   // host vectors above go out of scope after the copy
+            const int32_t st = b2a_snac_decode_dev(h->snac, dc, nb, T, nullptr, 0, gp->seed, h->d_wave.p, s);
+            B2A_CHECK(st == B2A_OK, B2A_ERR_AUDIO_DECODING_FAILED, std::string("SNAC decode failed: ") + b2a_last_error());
+            for (int i = 0; i < nb; ++i) {
+                const int r = grp[i];
+                B2A_CUDA(cudaMemcpyAsync(wave_out + (size_t)r * wave_cap, h->d_wave.p + (size_t)i * wl, wl * sizeof(float),
+                                         wave_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+                if (wave_len) wave_len[r] = wl;
+            }
+            B2A_CUDA(cudaStreamSynchronize(s));
+        }
+        codec_t = now_s() - c0;
+    }
+    if (info) {
+        info->prompt_token_count = L;
+        info->generation_token_count = total_gen;
+        info->prefill_time = t1 - t0;
+        info->generate_time = t2 - t1;
+        info->tokens_per_second = total_gen / std::max(1e-9, t2 - t1);
+        info->codec_time = codec_t;
+        size_t fr = 0, tot = 0;
+        cudaMemGetInfo(&fr, &tot);
+        info->peak_memory_gb = (double)(tot - fr) / 1e9;
+    }
+}
+
+extern "C" {
+
+int32_t b2a_tts_create(int32_t device, const b2a_llama_config* cfg, const b2a_tensor* tensors, int32_t n, b2a_snac* snac,
+                       b2a_tts** out) {
+    return guarded([&] {
+        B2A_CHECK(out, B2A_ERR_INVALID_INPUT, "b2a_tts_create: null out");
+        *out = nullptr;
+        B2A_CHECK(cfg && tensors && n > 0, B2A_ERR_MODEL_NOT_INITIALIZED, "b2a_tts_create: missing config or weights");
+        TensorTable tt(tensors, n);
+        *out = new b2a_tts(device, *cfg, tt, snac);
+    });
+}
+
+int32_t b2a_tts_prepare_input_ids(const int32_t* const* prompt_ids, const int32_t* lens, int32_t batch, int32_t* out,
+                                  int32_t* out_len) {
+    return guarded([&] {
+        B2A_CHECK(prompt_ids && lens && out_len && batch > 0, B2A_ERR_INVALID_INPUT, "b2a_tts_prepare_input_ids: null argument");
+        int mx = 0;
+        for (int b = 0; b < batch; ++b) mx = std::max(mx, lens[b]);
+        *out_len = mx + 3;
+        if (!out) return;
+        for (int b = 0; b < batch; ++b) {   // LlamaTTS.swift:499-543
+            int32_t* r = out + (size_t)b * (mx + 3);
+            int j = 0;
+            for (; j < mx - lens[b]; ++j) r[j] = TOK_PAD;
+            r[j++] = TOK_START_OF_HUMAN;
+            for (int i = 0; i < lens[b]; ++i) r[j++] = prompt_ids[b][i];
+            r[j++] = TOK_END_OF_TEXT;
+            r[j++] = TOK_END_OF_HUMAN;
+        }
+    });
+}
+
+int32_t b2a_tts_forward_logits(b2a_tts* h, const int32_t* ids, int32_t B, int32_t L, int32_t reset_cache, float* logits_out) {
+    return guarded([&] {
+        B2A_CHECK(h && ids && logits_out, B2A_ERR_INVALID_INPUT, "b2a_tts_forward_logits: null argument");
+        B2A_CHECK(B >= 1 && B <= h->cfg.max_batch && L >= 1, B2A_ERR_INVALID_INPUT, "b2a_tts_forward_logits: bad batch / length");
+        B2A_CUDA(cudaSetDevice(h->device));
+        cudaStream_t s = h->stream;
+        h->set_batch(B);
+        h->drop_graphs();
+        std::vector<int> hp(8, 0);
+        if (!reset_cache) B2A_CUDA(cudaMemcpy(hp.data(), h->pos.p, 8 * sizeof(int), cudaMemcpyDeviceToHost));
+        const int start = reset_cache ? 0 : hp[0];
+        B2A_CHECK(start + L <= h->cfg.max_context, B2A_ERR_INVALID_INPUT, "b2a_tts_forward_logits: context overflow");
+        h->ids.alloc((size_t)B * L);
+        B2A_CUDA(cudaMemcpyAsync(h->ids.p, ids, (size_t)B * L * sizeof(int), cudaMemcpyHostToDevice, s));
+        const int V = h->cfg.vocab_size;
+        std::vector<int> tk(8, 0), ps(8, -1);
+        for (int p = 0; p < L; ++p) {
+            for (int b = 0; b < B; ++b) { tk[b] = ids[(size_t)b * L + p]; ps[b] = start + p; }
+            B2A_CUDA(cudaMemcpyAsync(h->tokens.p, tk.data(), 8 * sizeof(int), cudaMemcpyHostToDevice, s));
+            B2A_CUDA(cudaMemcpyAsync(h->pos.p, ps.data(), 8 * sizeof(int), cudaMemcpyHostToDevice, s));
+            h->run_layers(B, s);
+            h->run_lm_head(B, s);
+            for (int b = 0; b < B; ++b)
+                B2A_CUDA(cudaMemcpyAsync(logits_out + ((size_t)b * L + p) * V, h->logits.p + (size_t)b * V, V * sizeof(float),
+                                         cudaMemcpyDeviceToHost, s));
+            B2A_CUDA(cudaStreamSynchronize(s));
+        }
+        for (int b = 0; b < B; ++b) ps[b] = start + L;
+        B2A_CUDA(cudaMemcpy(h->pos.p, ps.data(), 8 * sizeof(int), cudaMemcpyHostToDevice));
+        B2A_CUDA(cudaGetLastError());
+    });
+}
+
+int32_t b2a_tts_generate(b2a_tts* h, const int32_t* input_ids, int32_t B, int32_t L, const b2a_gen_params* gp,
+                         int32_t* tokens_out, int32_t* n_tokens_out, float* wave_out, int64_t wave_cap, int64_t* wave_len,
+                         b2a_gen_info* info, b2a_token_cb on_token, void* user) {
+    return guarded([&] {
+        tts_generate_impl(h, input_ids, false, B, L, gp, tokens_out, n_tokens_out, wave_out, false, wave_cap, wave_len, info,
+                          on_token, user);
+    });
+}
+
+int32_t b2a_tts_generate_dev(b2a_tts* h, const int32_t* d_input_ids, int32_t B, int32_t L, const b2a_gen_params* gp,
+                             float* d_wave_out, int64_t wave_cap, int64_t* wave_len, b2a_gen_info* info) {
+    return guarded([&] {
+        tts_generate_impl(h, d_input_ids, true, B, L, gp, nullptr, nullptr, d_wave_out, true, wave_cap, wave_len, info, nullptr,
+                          nullptr);
+    });
+}
+
+int32_t b2a_tts_cancel(b2a_tts* h) {
+    if (!h) return B2A_ERR_INVALID_INPUT;
+    h->cancel.store(1);
+    return B2A_OK;
+}
+
+int32_t b2a_tts_parse_output(const int32_t* tokens, int32_t batch, int32_t n, int32_t* code_lists_out, int32_t* code_lens) {
+    return guarded([&] {
+        B2A_CHECK(tokens && code_lists_out && code_lens && batch > 0 && n >= 0, B2A_ERR_INVALID_INPUT, "b2a_tts_parse_output: bad argument");
+        int last = -1;   // LlamaTTS.swift:391-398: last match in row-major visiting order
+        for (int i = 0; i < batch; ++i)
+            for (int j = 0; j < n; ++j)
+                if (tokens[(size_t)i * n + j] == TOK_START_OF_SPEECH) last = j;
+        for (int i = 0; i < batch; ++i) {
+            std::vector<int> r = parse_row(tokens + (size_t)i * n, n, last);
+            code_lens[i] = (int)r.size();
+            memcpy(code_lists_out + (size_t)i * n, r.data(), r.size() * sizeof(int));
+        }
+    });
+}
+
+int32_t b2a_tts_deinterleave(const int32_t* code_list, int32_t n, int32_t* c0, int32_t* c1, int32_t* c2, int32_t* n_frames) {
+    return guarded([&] {
+        B2A_CHECK(code_list && c0 && c1 && c2 && n_frames && n >= 0, B2A_ERR_INVALID_INPUT, "b2a_tts_deinterleave: bad argument");
+        const int groups = (n + 1) / 7;
+        B2A_CHECK(groups * 7 <= n, B2A_ERR_INVALID_INPUT, "b2a_tts_deinterleave: code list must hold whole 7-token frames");
+        std::vector<int> l1, l2, l3;
+        deinterleave(code_list, n, l1, l2, l3);
+        memcpy(c0, l1.data(), l1.size() * sizeof(int));
+        memcpy(c1, l2.data(), l2.size() * sizeof(int));
+        memcpy(c2, l3.data(), l3.size() * sizeof(int));
+        *n_frames = groups;
+    });
+}
+
+int32_t b2a_tts_interleave(const int32_t* c0, const int32_t* c1, const int32_t* c2, int32_t n_frames, int32_t* cl) {
+    return guarded([&] {   // llamaEncodeAudioToCodes, LlamaTTS.swift:85-95
+        B2A_CHECK(c0 && c1 && c2 && cl && n_frames >= 0, B2A_ERR_INVALID_INPUT, "b2a_tts_interleave: bad argument");
+        for (int i = 0; i < n_frames; ++i) {
+            int32_t* o = cl + 7 * i;
+            o[0] = c0[i];
+            o[1] = c1[2 * i] + 4096;
+            o[2] = c2[4 * i] + 2 * 4096;
+            o[3] = c2[4 * i + 1] + 3 * 4096;
+            o[4] = c1[2 * i + 1] + 4 * 4096;
+            o[5] = c2[4 * i + 2] + 5 * 4096;
+            o[6] = c2[4 * i + 3] + 6 * 4096;
+        }
+    });
+}
+
+void b2a_tts_destroy(b2a_tts* h) { delete h; }
+
+}  // extern "C"

@@ -1,0 +1,25 @@
+"""CPU oracle: a restatement of the reference's algorithm for the hot path.
+
+THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl
+reference`` legs may import anything from this package.  The product path
+(``mlx-audio-swift_b200``) never imports it and fails loudly when its CUDA
+library is missing.
+
+PARITY UNPINNED.  The reference (Blaizzy/mlx-audio-swift @ 4266f988) is pure
+Swift on top of the un-vendored ``mlx-swift 0.31.4`` / ``mlx-swift-lm 3.31.4``
+packages (``Package.resolved``); neither can be compiled or imported in this
+container (no Swift toolchain, macOS/iOS-only package, no ``mlx`` Python
+module), and the reference's own tests hold no numeric golden vectors for this
+path -- only two "returns nil" robustness cases for
+``IncrementalMelSpectrogram`` (``Tests/IncrementalMelSpectrogramTests.swift:7-17``),
+shape checks for Whisper features (``Tests/MLXAudioSTTTests.swift:4416-4422``)
+and closed-form window values.  Those are all reproduced in
+``tests/test_oracle_*.py``.  Beyond that the oracle is cross-checked against
+independent implementations available offline (``torch.stft``,
+``torch.nn.functional.conv1d/conv_transpose1d``, ``transformers`` Llama/Whisper
+with random init), see ``tests/test_oracle_crosscheck.py``.
+
+Every function cites the reference ``file:line`` it follows (paths relative
+to the reference checkout root).
+"""

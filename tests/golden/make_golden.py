@@ -1,0 +1,79 @@
+"""Generates the committed golden fixtures from the CPU oracle (run from the repo root:
+`python tests/golden/make_golden.py`).  The reference itself cannot run here, so
+these pin the ORACLE; the oracle in turn is cross-checked against independent implementations in
+tests/test_oracle_*.py.  Style follows the reference's own Python-parity goldens: first-N samples +
+mean / abs-mean / min / max (Tests/MLXAudioCodecsTests.swift:207-241), plus small full arrays."""
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+from oracle import dsp, llama, snac  # noqa: E402
+
+OUT = Path(__file__).resolve().parent
+
+
+def stats(x):
+    x = np.asarray(x, dtype=np.float64).reshape(-1)
+    return np.array([x.mean(), np.abs(x).mean(), x.min(), x.max()])
+
+
+def mel():
+    x = dsp.synth_audio(160000, 0)
+    m = dsp.IncrementalMelSpectrogram(16000, 400, 160, 80)
+    a, b = m.process(x), m.flush()
+    full = np.concatenate([a, b])
+    # irregular chunking (the reference's streaming==offline test style)
+    m2 = dsp.IncrementalMelSpectrogram(16000, 400, 160, 80)
+    cuts = [0, 1, 3, 150, 700, 5000, 5160, 40000, 160000]
+    chunks = []
+    for i in range(len(cuts) - 1):
+        o = m2.process(x[cuts[i]:cuts[i + 1]])
+        if o is not None:
+            chunks.append(o)
+    chunks.append(m2.flush())
+    irr = np.concatenate(chunks)
+    w = dsp.whisper_encoder_features(x, 80)[0]
+    off = dsp.compute_mel_spectrogram(x, 16000, 400, 160, 80)
+    np.savez_compressed(OUT / "mel.npz", inc_first=full[:4].astype(np.float32), inc_last=full[-3:].astype(np.float32),
+                        inc_stats=stats(full), inc_shape=np.array(full.shape), irr_stats=stats(irr),
+                        irr_shape=np.array(irr.shape), irr_rows=irr[[0, 5, 30, 500, 1000]].astype(np.float32),
+                        whisper_stats=stats(w), whisper_rows=w[[0, 1, 999, 1000, 2999]].astype(np.float32),
+                        core_stats=stats(off), core_rows=off[[0, 1, 500, 1000]].astype(np.float32))
+
+
+def snac_small():
+    cfg = snac.SNACConfig()
+    W = snac.init_weights(cfg, 1234)
+    codes = snac.synth_codes(cfg, 2, 16, seed=2)
+    rng = np.random.default_rng(7)
+    noise = [rng.standard_normal(s).astype(np.float32) for s in snac.noise_shapes(cfg, 2, 16)]
+    y = snac.decode(cfg, W, codes, noise)
+    y0 = snac.decode(cfg, W, codes, None)
+    z = (rng.standard_normal((2, cfg.latent, 16)) * 0.5).astype(np.float32)
+    zq, qc = snac.quantize(cfg, W, z)
+    np.savez_compressed(OUT / "snac.npz", wave=y.astype(np.float32), wave_nonoise=y0.astype(np.float32),
+                        wave_stats=stats(y), q_codes0=qc[0], q_codes1=qc[1], q_codes2=qc[2], zq_stats=stats(zq))
+
+
+def llama_tiny():
+    cfg = llama.LlamaConfig(hidden_size=256, num_hidden_layers=2, intermediate_size=512, num_attention_heads=2,
+                            num_key_value_heads=1, head_dim=128, vocab_size=2048)
+    W = llama.init_weights(cfg, 1234, std=0.08)
+    ids = np.random.default_rng(3).integers(0, 2048, size=(2, 12))
+    mo = llama.LlamaOracle(cfg, W, round_acts=True)
+    lg = mo.forward(torch.as_tensor(ids)).numpy()
+    gen = llama.generate_tokens(llama.LlamaOracle(cfg, W, True), ids, max_tokens=24, temperature=0.0,
+                                rep_penalty=1.3, rep_context=20)
+    np.savez_compressed(OUT / "llama_tiny.npz", ids=ids, logits_last=lg[:, -1].astype(np.float32),
+                        logits_stats=stats(lg), greedy=np.asarray(gen, dtype=np.int32),
+                        freqs=llama.llama3_rope_freqs(llama.LlamaConfig()))
+
+
+if __name__ == "__main__":
+    mel(); snac_small(); llama_tiny()
+    for f in sorted(OUT.glob("*.npz")):
+        print(f.name, f.stat().st_size)

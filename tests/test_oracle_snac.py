@@ -1,0 +1,91 @@
+"""Oracle SNAC restatement vs independent formulations (explicit scatter loop for the transposed conv,
+torch weight_norm, float64 code search) and the committed goldens.  CPU only."""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from conftest import GOLDEN, rel_err
+from oracle import snac
+
+
+def test_conv_transpose_scatter_semantics():
+    # y[t*s + k - pad, o] += x[t, i] * w[o, k, i]  (SURVEY 8c trap 7; EncodecLayers.swift:422-438 spells it out)
+    rng = np.random.default_rng(0)
+    cin, cout, s, T = 3, 2, 4, 5
+    k, pad = 2 * s, 2
+    w = {"p.weight_v": rng.standard_normal((cin, k, cout)).astype(np.float32),
+         "p.weight_g": rng.uniform(0.5, 1.5, (cin, 1, 1)).astype(np.float32),
+         "p.bias": rng.standard_normal(cout).astype(np.float32)}
+    x = rng.standard_normal((1, cin, T))
+    y = snac.wn_conv_transpose1d(w, "p", torch.as_tensor(x), stride=s, padding=pad).numpy()[0]
+    v = w["p.weight_v"].astype(np.float64)
+    wn = w["p.weight_g"].astype(np.float64) * v / np.sqrt((v ** 2).sum(axis=(1, 2), keepdims=True))   # [in,k,out]
+    ref = np.zeros((cout, T * s))
+    for t in range(T):
+        for kk in range(k):
+            to = t * s + kk - pad
+            if 0 <= to < T * s:
+                for o in range(cout):
+                    ref[o, to] += (x[0, :, t] * wn[:, kk, o]).sum()
+    ref += w["p.bias"][:, None]
+    assert y.shape == ref.shape and rel_err(y, ref) < 1e-12
+
+
+def test_weight_norm_matches_torch_parametrization():
+    rng = np.random.default_rng(1)
+    v = rng.standard_normal((6, 7, 4)).astype(np.float32)          # MLX [out, k, in]
+    g = rng.uniform(0.5, 1.5, (6, 1, 1)).astype(np.float32)
+    ours = snac.wn_conv_weight({"c.weight_v": v, "c.weight_g": g}, "c")
+    conv = torch.nn.utils.parametrizations.weight_norm(torch.nn.Conv1d(4, 6, 7).double())
+    with torch.no_grad():
+        conv.parametrizations.weight.original1.copy_(torch.as_tensor(v).permute(0, 2, 1))
+        conv.parametrizations.weight.original0.copy_(torch.as_tensor(g))
+    assert rel_err(ours.numpy(), conv.weight.detach().numpy()) < 1e-6
+
+
+def test_from_codes_repeat_interleave_and_shapes():
+    cfg = snac.SNACConfig()
+    W = snac.init_weights(cfg, 1234)
+    codes = snac.synth_codes(cfg, 2, 8, seed=2)
+    assert [c.shape for c in codes] == [(2, 2), (2, 4), (2, 8)]
+    z = snac.from_codes(cfg, W, codes).numpy()
+    assert z.shape == (2, 768, 8)
+    # level 0 contributes a value constant over each group of 4 latent steps
+    z0 = snac.from_codes(cfg, W, [codes[0], np.zeros_like(codes[1]), np.zeros_like(codes[2])]).numpy()
+    zb = snac.from_codes(cfg, W, [np.zeros_like(codes[0]), np.zeros_like(codes[1]), np.zeros_like(codes[2])]).numpy()
+    d = z0 - zb
+    assert np.abs(d[:, :, 0:4] - d[:, :, 0:1]).max() < 1e-12 and np.abs(d[:, :, 4:8] - d[:, :, 4:5]).max() < 1e-12
+
+
+def test_decode_shape_and_batch_equals_serial():
+    cfg = snac.SNACConfig()
+    W = snac.init_weights(cfg, 1234)
+    codes = snac.synth_codes(cfg, 2, 8, seed=5)
+    y = snac.decode(cfg, W, codes)
+    assert y.shape == (2, 1, 8 * 512) and np.abs(y).max() <= 1.0
+    y1 = snac.decode(cfg, W, [c[1:2] for c in codes])
+    assert np.abs(y[1:2] - y1).max() < 1e-12          # Parakeet-style batched == serial
+
+
+def test_fp32_code_search_agrees_with_float64():
+    cfg = snac.SNACConfig()
+    W = snac.init_weights(cfg, 1234)
+    z = (np.random.default_rng(7).standard_normal((2, cfg.latent, 16)) * 0.5).astype(np.float32)
+    _, c32 = snac.quantize(cfg, W, z, fp32_search=True)
+    _, c64 = snac.quantize(cfg, W, z, fp32_search=False)
+    assert all(np.array_equal(a, b) for a, b in zip(c32, c64))
+    assert all(a.min() >= 0 and a.max() < 4096 for a in c32)
+
+
+def test_goldens():
+    g = np.load(GOLDEN / "snac.npz")
+    cfg = snac.SNACConfig()
+    W = snac.init_weights(cfg, 1234)
+    codes = snac.synth_codes(cfg, 2, 16, seed=2)
+    rng = np.random.default_rng(7)
+    noise = [rng.standard_normal(s).astype(np.float32) for s in snac.noise_shapes(cfg, 2, 16)]
+    y = snac.decode(cfg, W, codes, noise)
+    assert np.abs(y - g["wave"]).max() < 1e-6
+    z = (rng.standard_normal((2, cfg.latent, 16)) * 0.5).astype(np.float32)
+    _, qc = snac.quantize(cfg, W, z)
+    assert np.array_equal(qc[0], g["q_codes0"]) and np.array_equal(qc[2], g["q_codes2"])
