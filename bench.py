@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline metric on the reference's headline config (BASELINE.json):
+real-time factor (RTFx = audio seconds / wall seconds, Sources/Tools/mlx-audio-swift-tts/App.swift:204)
+of Orpheus-3B TTS, batch 8 x 64-token prompt -> 512 audio tokens -> SNAC decode, per B200.
+
+A "step" is one pass of the hot path over one batch: 8 prompts -> prefill -> 512 decode steps (EOS masked so
+work is fixed) -> parseOutput / 7-token de-interleave -> SNAC decode -> 8 waveforms (6.229 s each).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    torchrun ... bench.py --gpus N ...          (one rank per GPU; utterances shard, weak scaling)
+
+`value` : inputs already resident in HBM, waveforms left in HBM (b2a_tts_generate_dev).
+`e2e`   : same metric through the host-buffer C ABI call a user makes (b2a_tts_generate): pinned host ids
+          in, waveforms copied back to pinned host memory, inside the timed region.
+Timed with CUDA events on the stream the library launches on; max over ranks; rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+ORPHEUS = dict(hidden_size=3072, num_hidden_layers=28, intermediate_size=8192, num_attention_heads=24,
+               num_key_value_heads=8, head_dim=128, vocab_size=156940, rms_norm_eps=1e-5, rope_theta=500000.0,
+               tie_word_embeddings=True,
+               rope_scaling={"rope_type": "llama3", "factor": 32.0, "low_freq_factor": 1.0, "high_freq_factor": 4.0,
+                             "original_max_position_embeddings": 8192})
+BATCH, PROMPT_LEN, GEN_TOKENS = 8, 64, 512
+METRIC, UNIT = "orpheus3b_tts_rtfx_batch8", "x_realtime(audio_s/s)"
+
+
+def workload_name(cfg=ORPHEUS):
+    return (f"Orpheus-3B bf16 (hidden {cfg['hidden_size']} x {cfg['num_hidden_layers']} layers, vocab {cfg['vocab_size']}), "
+            f"{PROMPT_LEN}-token prompt, {GEN_TOKENS} audio tokens, batch {BATCH}, SNAC-24kHz decode")
+
+
+def audio_seconds_per_utterance(n_prompt: int, n_gen: int) -> float:
+    # parseOutput on prompt+generated (no 128257 in random-init output): floor((L+G)/7) frames x 2048 samples
+    return ((n_prompt + n_gen) // 7) * 4 * 512 / 24000.0
+
+
+def make_prompts(rank: int) -> np.ndarray:
+    rng = np.random.default_rng(3 + rank)
+    body = rng.integers(0, 128000, size=(BATCH, PROMPT_LEN - 3), dtype=np.int32)
+    ids = np.empty((BATCH, PROMPT_LEN), dtype=np.int32)
+    ids[:, 0] = 128259
+    ids[:, 1:-2] = body
+    ids[:, -2], ids[:, -1] = 128009, 128260
+    return ids
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc, self.thr = index, [], None, None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            return
+        self.thr = threading.Thread(target=self._read, daemon=True)
+        self.thr.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def weight_bytes(cfg) -> int:
+    H, I, hd = cfg["hidden_size"], cfg["intermediate_size"], cfg["head_dim"]
+    nq, nkv, L, V = cfg["num_attention_heads"], cfg["num_key_value_heads"], cfg["num_hidden_layers"], cfg["vocab_size"]
+    per_layer = (nq + 2 * nkv) * hd * H + H * nq * hd + 3 * I * H
+    return 2 * (L * per_layer + V * H)        # every matrix once + the tied lm head; bf16
+
+
+def kv_bytes(cfg, batch, ctx) -> int:
+    return 2 * batch * cfg["num_key_value_heads"] * ctx * cfg["head_dim"] * 2 * cfg["num_hidden_layers"]
+
+
+# ------------------------------------------------------------------------------------------------- CPU legs
+def cpu_reference_sample(cfg, threads: int):
+    """The reference path restated on the CPU (oracle/, kind "port"), bounded sample.
+    Full width, 2- and 4-layer models timed to separate per-layer cost from the lm head; extrapolated to
+    28 layers x (64-token prefill + 512 decode steps); SNAC decode timed on 1 of 8 utterances (fp32)."""
+    import torch
+    from oracle import llama as ol
+    from oracle import snac as osn
+    torch.set_num_threads(threads)
+    L_full = cfg["num_hidden_layers"]
+
+    def build(nl):
+        c = ol.LlamaConfig(hidden_size=cfg["hidden_size"], num_hidden_layers=nl, intermediate_size=cfg["intermediate_size"],
+                           num_attention_heads=cfg["num_attention_heads"], num_key_value_heads=cfg["num_key_value_heads"],
+                           head_dim=cfg["head_dim"], vocab_size=cfg["vocab_size"])
+        return c
+
+    c4 = build(4)
+    g = torch.Generator().manual_seed(0)
+    W = {}
+    H, I, hd = c4.hidden_size, c4.intermediate_size, c4.head_dim
+
+    def lin(o, i):
+        return torch.randn(o, i, generator=g) * 0.02      # fp32 (bf16-valued weights pre-widened once)
+
+    W["model.embed_tokens.weight"] = lin(c4.vocab_size, H)
+    for l in range(4):
+        p = f"model.layers.{l}."
+        W[p + "self_attn.q_proj.weight"] = lin(c4.num_attention_heads * hd, H)
+        W[p + "self_attn.k_proj.weight"] = lin(c4.num_key_value_heads * hd, H)
+        W[p + "self_attn.v_proj.weight"] = lin(c4.num_key_value_heads * hd, H)
+        W[p + "self_attn.o_proj.weight"] = lin(H, c4.num_attention_heads * hd)
+        W[p + "mlp.gate_proj.weight"] = lin(I, H)
+        W[p + "mlp.up_proj.weight"] = lin(I, H)
+        W[p + "mlp.down_proj.weight"] = lin(H, I)
+        W[p + "input_layernorm.weight"] = torch.ones(H)
+        W[p + "post_attention_layernorm.weight"] = torch.ones(H)
+    W["model.norm.weight"] = torch.ones(H)
+    ids = torch.as_tensor(make_prompts(0), dtype=torch.long)
+    res = {}
+    for nl in (2, 4):
+        mo = ol.LlamaOracle(build(nl), W, round_acts=True)
+        t0 = time.perf_counter()
+        lg = mo.forward(ids)
+        t_pre = time.perf_counter() - t0
+        nxt = lg[:, -1].argmax(-1, keepdim=True)
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            lg = mo.forward(nxt)
+            ts.append(time.perf_counter() - t0)
+            nxt = lg[:, -1].argmax(-1, keepdim=True)
+        res[nl] = (t_pre, float(np.median(ts)))
+    per_layer_pre = (res[4][0] - res[2][0]) / 2
+    per_layer_dec = (res[4][1] - res[2][1]) / 2
+    head_pre = max(res[2][0] - 2 * per_layer_pre, 0.0)
+    head_dec = max(res[2][1] - 2 * per_layer_dec, 0.0)
+    t_prefill = L_full * per_layer_pre + head_pre
+    t_step = L_full * per_layer_dec + head_dec
+    # SNAC on one utterance, fp32
+    osn.DTYPE = torch.float32
+    scfg = osn.SNACConfig()
+    SW = osn.init_weights(scfg, 1234)
+    frames = (PROMPT_LEN + GEN_TOKENS) // 7
+    codes = osn.synth_codes(scfg, 1, 4 * frames, seed=2)
+    t0 = time.perf_counter()
+    osn.decode(scfg, SW, codes, None)
+    t_snac1 = time.perf_counter() - t0
+    osn.DTYPE = torch.float64
+    total = t_prefill + GEN_TOKENS * t_step + BATCH * t_snac1
+    audio = BATCH * audio_seconds_per_utterance(PROMPT_LEN, GEN_TOKENS)
+    sample = (f"oracle port (torch-CPU fp32 math on bf16-valued weights, {threads} threads): full-width 2- and 4-layer models "
+              f"timed (prefill {res[4][0]:.2f}s / decode step {res[4][1]*1e3:.0f}ms at 4 layers), per-layer + lm-head cost "
+              f"extrapolated linearly to {L_full} layers x ({PROMPT_LEN}-token prefill + {GEN_TOKENS} steps); SNAC decode timed on "
+              f"1 of {BATCH} utterances ({t_snac1:.2f}s) x {BATCH}")
+    return audio / total, total, sample
+
+
+def run_reference_arm(args, rank: int, world: int):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    vals, totals, sample = [], [], ""
+    for i in range(args.warmup + args.steps):
+        v, tot, sample = cpu_reference_sample(ORPHEUS, threads)
+        if i >= args.warmup:
+            vals.append(v); totals.append(tot)
+    v = float(np.mean(vals))
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": float(np.mean(totals)) * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload_name(), "note": "CPU restatement of the reference path (the Swift/MLX reference "
+                       "cannot be built in this image); extrapolated from a bounded sample"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tiny", action="store_true", help="small model (plumbing check only; NOT a bench number)")
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import mlx_audio_swift_b200 as m
+
+    assert m.device_count() > 0, "bench.py needs a CUDA device: libb200audio has no CPU fallback"
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    cfg = dict(ORPHEUS)
+    if args.tiny:
+        cfg.update(hidden_size=512, num_hidden_layers=2, intermediate_size=1024, num_attention_heads=4, num_key_value_heads=2)
+    codec = m.SNAC(weights=m.SNAC.random_init_weights(1234), device=local)
+    tts = m.LlamaTTSModel.random_init(cfg, snac=codec, device=local, max_batch=BATCH, max_context=PROMPT_LEN + GEN_TOKENS + 16,
+                                      std=0.02, seed=1234 + rank)
+    params = m.GenerateParameters(max_tokens=GEN_TOKENS, temperature=0.6, top_p=0.8, repetition_penalty=1.3,
+                                  repetition_context_size=20, seed=rank, mask_eos=True, wrap_codes=True)
+    frames = (PROMPT_LEN + GEN_TOKENS) // 7
+    wave_len = frames * 2048
+    audio_s = BATCH * wave_len / 24000.0
+
+    ids_host = torch.from_numpy(make_prompts(rank)).pin_memory()
+    toks_host = torch.zeros((BATCH, GEN_TOKENS), dtype=torch.int32).pin_memory()
+    ntok_host = torch.zeros(BATCH, dtype=torch.int32).pin_memory()
+    wave_host = torch.zeros((BATCH, wave_len), dtype=torch.float32).pin_memory()
+    wlen_host = torch.zeros(BATCH, dtype=torch.int64)
+    ids_dev = ids_host.cuda(non_blocking=False)
+    wave_dev = torch.zeros((BATCH, wave_len), dtype=torch.float32, device="cuda")
+    gathered = torch.zeros((world, BATCH, wave_len), dtype=torch.float32, device="cuda") if world > 1 else None
+    stream = torch.cuda.ExternalStream(tts.stream, device=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_dev():
+        wl, info = tts.generate_dev(ids_dev, params, wave_dev, wave_len)
+        if dist is not None:      # the ONE collective of the path: re-join decoded waveforms
+            with torch.cuda.stream(stream):
+                dist.all_gather_into_tensor(gathered, wave_dev)
+        return info
+
+    def step_e2e():
+        info = tts.generate_into(ids_host, params, toks_host, ntok_host, wave_host, wlen_host)
+        return info
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = m.launch_count()
+        e0.record(stream)
+        infos = [fn() for _ in range(steps)]
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), m.launch_count() - n0, infos
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev, launches, infos = timed(step_dev, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, _, _ = timed(step_e2e, args.steps, max(1, min(args.warmup, 1)))
+    assert int(wlen_host[0]) == wave_len and bool(torch.isfinite(wave_host).all()), "benchmark produced no / bad audio"
+
+    # roofline of the dominant kernel group: one captured decode step (weights streamed once + KV read)
+    ctx = PROMPT_LEN + GEN_TOKENS // 2
+    step_ms = tts.time_steps(BATCH, ctx, 24)
+    peak, peak_src = measured_peaks()
+    alg_bytes = weight_bytes(cfg) + kv_bytes(cfg, BATCH, ctx)
+    achieved = alg_bytes / (step_ms * 1e-3) / 1e9
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    value = world * audio_s * args.steps / (ms_dev * 1e-3)
+    e2e = world * audio_s * args.steps / (ms_e2e * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": workload_name(cfg) + (" [TINY plumbing run -- not a bench number]" if args.tiny else ""),
+                   "global_batch": BATCH * world, "parallelism": f"utterance-dp{world}",
+                   "sampling": "T=0.6 top_p=0.8 rep_penalty=1.3/20 (reference defaults), EOS masked",
+                   "l2": "inputs larger than L2: every decode step streams %.2f GB of weights" % (weight_bytes(cfg) / 1e9),
+                   "audio_s_per_step": audio_s * world},
+        "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": int(ids_host.numel() * 4), "d2h_bytes_per_step": int(wave_host.numel() * 4 + toks_host.numel() * 4)},
+        "gpu_launches": int(launches),
+        "stages_s": {"prefill": infos[-1].prefill_time, "decode": infos[-1].generate_time, "codec": infos[-1].codec_time},
+        "roofline": {"kernel": "decode step (CUDA graph: 28 x [rmsnorm, qkv gemv, attention, o gemv, rmsnorm, gate/up gemv+swiglu, "
+                               "down gemv] + lm-head gemv + sampler)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_step": alg_bytes, "ms_per_decode_step": step_ms, "context": ctx},
+        "clocks": clocks,
+    }
+    if not args.no_cpu_baseline and world == 1 and not args.tiny:
+        threads = os.cpu_count() or 1
+        v, tot, sample = cpu_reference_sample(cfg, threads)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

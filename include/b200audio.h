@@ -135,6 +135,7 @@ typedef struct b2a_snac b2a_snac;
 int32_t b2a_snac_create(int32_t device, const b2a_snac_config* cfg, const b2a_tensor* tensors,
                         int32_t n_tensors, b2a_snac** out);
 int64_t b2a_snac_hop_length(const b2a_snac* h);
+void* b2a_snac_stream(b2a_snac* h); /* the handle's cudaStream_t, for event timing */
 int32_t b2a_snac_decode(b2a_snac* h, const int32_t* const* codes, int32_t batch, int64_t t_latent,
                         const float* const* noise, int32_t noise_mode, uint64_t seed, float* wave);
 int32_t b2a_snac_decode_dev(b2a_snac* h, const int32_t* const* d_codes, int32_t batch, int64_t t_latent,
@@ -226,6 +227,19 @@ int32_t b2a_tts_generate_dev(b2a_tts* h, const int32_t* d_input_ids, int32_t bat
                              const b2a_gen_params* params, float* d_wave_out, int64_t wave_cap,
                              int64_t* wave_len, b2a_gen_info* info);
 int32_t b2a_tts_cancel(b2a_tts* h);
+/* Benchmark / full-size property-test helpers (no reference counterpart):
+ *   b2a_tts_create_random : same as b2a_tts_create but the weights are drawn ON THE DEVICE
+ *                           (N(0, std^2) bf16 from a counter-based generator, norm gains 1) so a
+ *                           3B-parameter random-init model needs no host copy.
+ *   b2a_tts_stream        : the handle's cudaStream_t (as void*) so a caller can record CUDA
+ *                           events on the stream the kernels are launched on.
+ *   b2a_tts_time_steps    : runs `iters` captured decode steps for `batch` rows at context
+ *                           `ctx` (greedy, no host sync inside) between two CUDA events on the
+ *                           handle's stream; *ms_per_step = average device time of one step. */
+int32_t b2a_tts_create_random(int32_t device, const b2a_llama_config* cfg, float std, uint64_t seed,
+                              b2a_snac* snac, b2a_tts** out);
+void* b2a_tts_stream(b2a_tts* h);
+int32_t b2a_tts_time_steps(b2a_tts* h, int32_t batch, int32_t ctx, int32_t iters, float* ms_per_step);
 /* parseOutput (:383-434) and llamaDecodeAudioFromCodes' de-interleave (:41-63), host-side ints.
  * tokens [B, n]; code_lists_out [B, n] / code_lens[B]; then per row codes0/1/2 sized n/7, 2n/7, 4n/7 */
 int32_t b2a_tts_parse_output(const int32_t* tokens, int32_t batch, int32_t n, int32_t* code_lists_out,

@@ -524,6 +524,23 @@ __global__ void init_rows_kernel(const int* __restrict__ ids, int L, int B, int 
     recent_n[b] = n;
 }
 
+// device-side random init (benchmarks / full-size property tests): N(0, std^2) -> bf16
+__global__ void random_bf16_kernel(bf16* __restrict__ w, long long n, float std, unsigned long long seed) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        const float u1 = ((unsigned)(z >> 40) + 1.0f) * (1.0f / 16777217.0f);
+        const float u2 = (unsigned)((z >> 8) & 0xFFFFFF) * (1.0f / 16777216.0f);
+        w[i] = __float2bfloat16_rn(std * sqrtf(-2.0f * __logf(u1)) * cospif(2.0f * u2));
+    }
+}
+__global__ void fill_f32_kernel(float* p, int n, float v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------------
@@ -598,15 +615,51 @@ struct b2a_tts {
         B2A_CUDA(cudaMemcpy(dst.p + offset_elems, t.data, expect * sizeof(bf16), cudaMemcpyHostToDevice));
     }
 
-    b2a_tts(int dev, const b2a_llama_config& c, const TensorTable& tt, b2a_snac* sn) : device(dev), cfg(c), snac(sn) {
+    void check_config() {
+        const b2a_llama_config& c = cfg;
         B2A_CHECK(c.head_dim == HD, B2A_ERR_INVALID_INPUT, "llama: head_dim must be 128");
         B2A_CHECK(c.hidden_size % 8 == 0 && c.intermediate_size % 8 == 0, B2A_ERR_INVALID_INPUT, "llama: sizes must be multiples of 8");
         B2A_CHECK(c.num_attention_heads % c.num_key_value_heads == 0 && c.num_attention_heads / c.num_key_value_heads <= MAXG,
                   B2A_ERR_INVALID_INPUT, "llama: unsupported GQA ratio");
         B2A_CHECK(c.max_batch >= 1 && c.max_batch <= 8, B2A_ERR_INVALID_INPUT, "llama: max_batch must be in 1..8");
         B2A_CHECK(c.max_context >= 8, B2A_ERR_INVALID_INPUT, "llama: max_context too small");
-        require_device(dev);
+        require_device(device);
         B2A_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    }
+
+    void alloc_state() {
+        const b2a_llama_config& c = cfg;
+        const int H = c.hidden_size, I = c.intermediate_size, nq = c.num_attention_heads, nkv = c.num_key_value_heads;
+        const int NQ = nq * HD, NKV = nkv * HD;
+        std::vector<float> fr = llama3_freqs(c);
+        freqs.upload(fr.data(), fr.size());
+        const size_t kv = (size_t)c.num_hidden_layers * c.max_batch * nkv * c.max_context * HD;
+        kcache.alloc(kv);
+        vcache.alloc(kv);
+        const int B = 8;
+        x.alloc((size_t)B * H); y.alloc((size_t)B * H); qkv.alloc((size_t)B * (NQ + 2 * NKV));
+        logits.alloc((size_t)B * c.vocab_size); probs.alloc((size_t)B * c.vocab_size);
+        xn.alloc((size_t)B * H); attn.alloc((size_t)B * NQ); act.alloc((size_t)B * I);
+        B2A_CUDA(cudaMemset(xn.p, 0, (size_t)B * H * sizeof(bf16)));
+        B2A_CUDA(cudaMemset(attn.p, 0, (size_t)B * NQ * sizeof(bf16)));
+        B2A_CUDA(cudaMemset(act.p, 0, (size_t)B * I * sizeof(bf16)));
+        B2A_CUDA(cudaMemset(x.p, 0, (size_t)B * H * sizeof(float)));
+        B2A_CUDA(cudaMemset(y.p, 0, (size_t)B * H * sizeof(float)));
+        B2A_CUDA(cudaMemset(qkv.p, 0, (size_t)B * (NQ + 2 * NKV) * sizeof(float)));
+        tokens.alloc(B); pos.alloc(B); recent.alloc(B * 64); recent_n.alloc(B); n_gen.alloc(B); done.alloc(B);
+        n_active.alloc(1); forced.alloc(B);
+        B2A_CUDA(cudaMemset(tokens.p, 0, B * sizeof(int)));
+        B2A_CUDA(cudaMemset(pos.p, 0, B * sizeof(int)));
+        h_flag.alloc(16);
+        gemv_attrs<1>(); gemv_attrs<2>(); gemv_attrs<4>(); gemv_attrs<8>();
+        const size_t at_sm = (size_t)(nq / nkv) * (HD + c.max_context) * sizeof(float);
+        B2A_CHECK(at_sm <= 200 * 1024, B2A_ERR_INVALID_INPUT, "llama: max_context too large for the attention score tile");
+        B2A_CUDA(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)at_sm));
+        B2A_CUDA(cudaDeviceSynchronize());
+    }
+
+    b2a_tts(int dev, const b2a_llama_config& c, const TensorTable& tt, b2a_snac* sn) : device(dev), cfg(c), snac(sn) {
+        check_config();
         const int H = c.hidden_size, I = c.intermediate_size, nq = c.num_attention_heads, nkv = c.num_key_value_heads;
         const int NQ = nq * HD, NKV = nkv * HD;
         upload_bf16(tt, "model.embed_tokens.weight", (int64_t)c.vocab_size * H, embed, 0, (size_t)c.vocab_size * H);
@@ -642,29 +695,41 @@ struct b2a_tts {
         }
         std::vector<float> gf = tt.f32("model.norm.weight", H);
         final_ln.upload(gf.data(), H);
-        std::vector<float> fr = llama3_freqs(c);
-        freqs.upload(fr.data(), fr.size());
-        const size_t kv = (size_t)c.num_hidden_layers * c.max_batch * nkv * c.max_context * HD;
-        kcache.alloc(kv);
-        vcache.alloc(kv);
-        const int B = 8;
-        x.alloc((size_t)B * H); y.alloc((size_t)B * H); qkv.alloc((size_t)B * (NQ + 2 * NKV));
-        logits.alloc((size_t)B * c.vocab_size); probs.alloc((size_t)B * c.vocab_size);
-        xn.alloc((size_t)B * H); attn.alloc((size_t)B * NQ); act.alloc((size_t)B * I);
-        B2A_CUDA(cudaMemset(xn.p, 0, (size_t)B * H * sizeof(bf16)));
-        B2A_CUDA(cudaMemset(attn.p, 0, (size_t)B * NQ * sizeof(bf16)));
-        B2A_CUDA(cudaMemset(act.p, 0, (size_t)B * I * sizeof(bf16)));
-        B2A_CUDA(cudaMemset(x.p, 0, (size_t)B * H * sizeof(float)));
-        tokens.alloc(B); pos.alloc(B); recent.alloc(B * 64); recent_n.alloc(B); n_gen.alloc(B); done.alloc(B);
-        n_active.alloc(1); forced.alloc(B);
-        B2A_CUDA(cudaMemset(tokens.p, 0, B * sizeof(int)));
-        h_flag.alloc(16);
-        gemv_attrs<1>(); gemv_attrs<2>(); gemv_attrs<4>(); gemv_attrs<8>();
-        const size_t at_sm = (size_t)(nq / nkv) * (HD + c.max_context) * sizeof(float);
-        B2A_CHECK(at_sm <= 200 * 1024, B2A_ERR_INVALID_INPUT, "llama: max_context too large for the attention score tile");
-        B2A_CUDA(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)at_sm));
-        B2A_CUDA(cudaMemset(y.p, 0, (size_t)B * H * sizeof(float)));
-        B2A_CUDA(cudaDeviceSynchronize());
+        alloc_state();
+    }
+
+    // random-init weights generated on the device (b2a_tts_create_random)
+    b2a_tts(int dev, const b2a_llama_config& c, float std, unsigned long long seed, b2a_snac* sn) : device(dev), cfg(c), snac(sn) {
+        check_config();
+        const int H = c.hidden_size, I = c.intermediate_size, nq = c.num_attention_heads, nkv = c.num_key_value_heads;
+        const int NQ = nq * HD, NKV = nkv * HD;
+        unsigned long long sd = seed * 1000003ull + 17;
+        auto rnd = [&](DBuf<bf16>& d, size_t n) {
+            d.alloc(n);
+            random_bf16_kernel<<<148 * 8, 256, 0, stream>>>(d.p, (long long)n, std, sd++);
+            count_launch();
+        };
+        auto ones = [&](DBuf<float>& d, int n) {
+            d.alloc(n);
+            fill_f32_kernel<<<cdiv(n, 256), 256, 0, stream>>>(d.p, n, 1.0f);
+            count_launch();
+        };
+        rnd(embed, (size_t)c.vocab_size * H);
+        if (c.tie_word_embeddings) lm_head = embed.p;
+        else { rnd(lm_head_w, (size_t)c.vocab_size * H); lm_head = lm_head_w.p; }
+        layers.resize(c.num_hidden_layers);
+        for (auto& L : layers) {
+            rnd(L.wqkv, (size_t)(NQ + 2 * NKV) * H);
+            rnd(L.wo, (size_t)H * NQ);
+            rnd(L.wgu, (size_t)2 * I * H);
+            rnd(L.wdown, (size_t)H * I);
+            ones(L.ln1, H);
+            ones(L.ln2, H);
+        }
+        ones(final_ln, H);
+        B2A_CUDA(cudaStreamSynchronize(stream));
+        B2A_CUDA(cudaGetLastError());
+        alloc_state();
     }
 
     template <int NB, int ROWS, int EPI>
@@ -974,6 +1039,59 @@ int32_t b2a_tts_create(int32_t device, const b2a_llama_config* cfg, const b2a_te
         B2A_CHECK(cfg && tensors && n > 0, B2A_ERR_MODEL_NOT_INITIALIZED, "b2a_tts_create: missing config or weights");
         TensorTable tt(tensors, n);
         *out = new b2a_tts(device, *cfg, tt, snac);
+    });
+}
+
+int32_t b2a_tts_create_random(int32_t device, const b2a_llama_config* cfg, float std, uint64_t seed, b2a_snac* snac,
+                              b2a_tts** out) {
+    return guarded([&] {
+        B2A_CHECK(out, B2A_ERR_INVALID_INPUT, "b2a_tts_create_random: null out");
+        *out = nullptr;
+        B2A_CHECK(cfg && std > 0.f, B2A_ERR_MODEL_NOT_INITIALIZED, "b2a_tts_create_random: missing config");
+        *out = new b2a_tts(device, *cfg, std, seed, snac);
+    });
+}
+
+void* b2a_tts_stream(b2a_tts* h) { return h ? (void*)h->stream : nullptr; }
+
+int32_t b2a_tts_time_steps(b2a_tts* h, int32_t B, int32_t ctx, int32_t iters, float* ms_per_step) {
+    return guarded([&] {
+        B2A_CHECK(h && ms_per_step && iters > 0, B2A_ERR_INVALID_INPUT, "b2a_tts_time_steps: bad argument");
+        B2A_CHECK(B >= 1 && B <= h->cfg.max_batch && ctx >= 0 && ctx + iters < h->cfg.max_context, B2A_ERR_INVALID_INPUT,
+                  "b2a_tts_time_steps: batch / context out of range");
+        B2A_CUDA(cudaSetDevice(h->device));
+        cudaStream_t s = h->stream;
+        h->set_batch(B);
+        const int MT = iters + 8;
+        h->ids.alloc((size_t)B * 1);
+        h->out_tokens.alloc((size_t)B * MT);
+        h->recent.alloc(8);
+        SampleArgs sa{};
+        sa.logits = h->logits.p; sa.probs = h->probs.p; sa.tokens = h->tokens.p; sa.pos = h->pos.p; sa.recent = h->recent.p;
+        sa.recent_n = h->recent_n.p; sa.out_tokens = h->out_tokens.p; sa.n_gen = h->n_gen.p; sa.done = h->done.p;
+        sa.n_active = h->n_active.p; sa.forced = nullptr; sa.V = h->cfg.vocab_size; sa.R = 1; sa.max_tokens = MT;
+        sa.temperature = 0.f; sa.top_p = 1.f; sa.rep_penalty = 1.f; sa.seed = 0; sa.mask_eos = 1;
+        h->capture(B, sa, 1);
+        B2A_CUDA(cudaMemsetAsync(h->ids.p, 0, (size_t)B * sizeof(int), s));
+        init_rows_kernel<<<1, 32, 0, s>>>(h->ids.p, 1, B, 0, h->tokens.p, h->pos.p, h->recent.p, h->recent_n.p, h->n_gen.p,
+                                          h->done.p, h->n_active.p, ctx);
+        count_launch();
+        // K/V beyond what earlier calls wrote is whatever is in the cache: zero it so reads are defined
+        // (timing only; values do not matter).
+        cudaEvent_t e0, e1;
+        B2A_CUDA(cudaEventCreate(&e0));
+        B2A_CUDA(cudaEventCreate(&e1));
+        B2A_CUDA(cudaGraphLaunch(h->g_step, s));   // warm-up
+        B2A_CUDA(cudaEventRecord(e0, s));
+        for (int i = 0; i < iters - 1; ++i) B2A_CUDA(cudaGraphLaunch(h->g_step, s));
+        B2A_CUDA(cudaEventRecord(e1, s));
+        B2A_CUDA(cudaStreamSynchronize(s));
+        count_launch(h->launches_step * iters);
+        float ms = 0.f;
+        B2A_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        *ms_per_step = ms / (float)std::max(1, iters - 1);
     });
 }
 

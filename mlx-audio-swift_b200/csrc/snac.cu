@@ -623,6 +623,7 @@ int32_t b2a_snac_create(int32_t device, const b2a_snac_config* cfg, const b2a_te
 }
 
 int64_t b2a_snac_hop_length(const b2a_snac* h) { return h ? h->hop : 0; }
+void* b2a_snac_stream(b2a_snac* h) { return h ? (void*)h->stream : nullptr; }
 
 int32_t b2a_snac_decode_dev(b2a_snac* h, const int32_t* const* d_codes, int32_t batch, int64_t T,
                             const float* const* d_noise, int32_t noise_mode, uint64_t seed, float* d_wave, void* stream) {

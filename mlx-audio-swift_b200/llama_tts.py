@@ -50,6 +50,40 @@ class LlamaTTSModel:
     sample_rate = 24000
     default_generation_parameters = GenerateParameters()
 
+    @staticmethod
+    def _c_config(config: dict, max_batch: int, max_context: int) -> _ffi.LlamaConfig:
+        rs = config.get("rope_scaling") or {}
+        nh = config["num_attention_heads"]
+        return _ffi.LlamaConfig(
+            config["hidden_size"], config["num_hidden_layers"], config["intermediate_size"], nh,
+            config.get("num_key_value_heads", nh), config.get("head_dim") or config["hidden_size"] // nh,
+            config["vocab_size"], config["rms_norm_eps"], config.get("rope_theta", 10000.0),
+            float(rs.get("factor", 32.0)), float(rs.get("low_freq_factor", 1.0)), float(rs.get("high_freq_factor", 4.0)),
+            float(rs.get("original_max_position_embeddings", 8192.0)), int(config.get("tie_word_embeddings", True)),
+            max_batch, max_context)
+
+    @classmethod
+    def random_init(cls, config: dict, snac: Optional[SNAC] = None, device: int = 0, max_batch: int = 8,
+                    max_context: int = 2048, std: float = 0.02, seed: int = 1234) -> "LlamaTTSModel":
+        """Random-init weights drawn on the device (benchmarks / full-size property tests)."""
+        self = cls.__new__(cls)
+        c = cls._c_config(config, max_batch, max_context)
+        self.config, self.vocab_size, self._snac_model = config, config["vocab_size"], snac
+        self._h = C.c_void_p()
+        _ffi.check(_ffi.lib().b2a_tts_create_random(device, C.byref(c), std, seed, snac._h if snac else None,
+                                                    C.byref(self._h)))
+        return self
+
+    @property
+    def stream(self) -> int:
+        return int(_ffi.lib().b2a_tts_stream(self._h) or 0)
+
+    def time_steps(self, batch: int, ctx: int, iters: int) -> float:
+        """Average device milliseconds of one captured decode step (CUDA events on the handle's stream)."""
+        ms = C.c_float(0)
+        _ffi.check(_ffi.lib().b2a_tts_time_steps(self._h, batch, ctx, iters, C.byref(ms)))
+        return float(ms.value)
+
     def __init__(self, config: dict, weights: Dict, snac: Optional[SNAC] = None, device: int = 0,
                  max_batch: int = 8, max_context: int = 2048):
         rs = config.get("rope_scaling") or {}
@@ -146,6 +180,19 @@ class LlamaTTSModel:
                                  info.generate_time, info.tokens_per_second, info.peak_memory_gb, info.codec_time)
         return tokens, waves, gi
 
+    def generate_into(self, ids, parameters: GenerateParameters, tokens, n_tokens, wave, wave_len):
+        """Zero-allocation form of generate_batch for callers that own (pinned) host buffers: `ids` [B, L]
+        int32, `tokens` [B, max_tokens] int32, `n_tokens` [B] int32, `wave` [B, cap] float32, `wave_len` [B]
+        int64 -- numpy arrays or torch CPU tensors.  Returns AudioGenerationInfo."""
+        B, L = ids.shape
+        info = _ffi.GenInfo()
+        gp = parameters._c()
+        cap = wave.shape[1] if wave is not None else 0
+        _ffi.check(_ffi.lib().b2a_tts_generate(self._h, _ffi.ptr(ids), B, L, C.byref(gp), _ffi.ptr(tokens), _ffi.ptr(n_tokens),
+                                               _ffi.ptr(wave), cap, _ffi.ptr(wave_len), C.byref(info), _ffi.TOKEN_CB(), None))
+        return AudioGenerationInfo(info.prompt_token_count, info.generation_token_count, info.prefill_time,
+                                   info.generate_time, info.tokens_per_second, info.peak_memory_gb, info.codec_time)
+
     def generate(self, prompt_token_ids: Sequence[int], parameters: Optional[GenerateParameters] = None) -> np.ndarray:
         """generate(text:voice:...) (:658-765) for ONE utterance, after tokenisation: returns the 1-D waveform."""
         if self._snac_model is None:
@@ -173,7 +220,8 @@ class LlamaTTSModel:
         gp = parameters._c()
         _ffi.check(_ffi.lib().b2a_tts_generate_dev(self._h, _ffi.ptr(d_input_ids), B, L, C.byref(gp), _ffi.ptr(d_wave),
                                                    wave_cap, _ffi.ptr(wlen), C.byref(info)))
-        return wlen, info
+        return wlen, AudioGenerationInfo(info.prompt_token_count, info.generation_token_count, info.prefill_time,
+                                         info.generate_time, info.tokens_per_second, info.peak_memory_gb, info.codec_time)
 
     def cancel(self) -> None:
         _ffi.check(_ffi.lib().b2a_tts_cancel(self._h))

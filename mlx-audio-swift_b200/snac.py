@@ -41,6 +41,50 @@ class SNAC:
         del keep
         self.hop_length = int(_ffi.lib().b2a_snac_hop_length(self._h))
 
+    @staticmethod
+    def random_init_weights(seed: int = 1234, latent: int = 768, decoder_dim: int = 1024,
+                            decoder_rates: Sequence[int] = (8, 8, 4, 2), vq_strides: Sequence[int] = (4, 2, 1),
+                            codebook_size: int = 4096, codebook_dim: int = 8) -> Dict[str, np.ndarray]:
+        """Random-init snac_24khz-shaped weights (benchmarks): conv v ~ U(+-1/sqrt(fan_in)) as
+        Layers.swift:81-86, g = ||v||, zero biases, Snake alpha = 1."""
+        rng = np.random.default_rng(seed)
+        w: Dict[str, np.ndarray] = {}
+
+        def wn(prefix, shape, fan, bias_n):
+            s = (1.0 / fan) ** 0.5
+            v = rng.uniform(-s, s, size=shape).astype(np.float32)
+            w[prefix + ".weight_v"] = v
+            w[prefix + ".weight_g"] = np.sqrt((v.astype(np.float64) ** 2).sum(axis=(1, 2), keepdims=True)).astype(np.float32)
+            if bias_n:
+                w[prefix + ".bias"] = np.zeros(bias_n, dtype=np.float32)
+
+        for i in range(len(vq_strides)):
+            q = f"quantizer.quantizers.{i}"
+            wn(q + ".in_proj", (codebook_dim, 1, latent), latent, codebook_dim)
+            wn(q + ".out_proj", (latent, 1, codebook_dim), codebook_dim, latent)
+            w[q + ".codebook.weight"] = rng.standard_normal((codebook_size, codebook_dim)).astype(np.float32)
+        p = "decoder.model.layers"
+        wn(f"{p}.0", (latent, 7, 1), 7 * latent, latent)
+        wn(f"{p}.1", (decoder_dim, 1, latent), latent, decoder_dim)
+        li = 2
+        for i, s in enumerate(decoder_rates):
+            cin, cout = decoder_dim // 2 ** i, decoder_dim // 2 ** (i + 1)
+            b = f"{p}.{li}.block.layers"
+            w[f"{b}.0.alpha"] = np.ones((1, cin, 1), dtype=np.float32)
+            wn(f"{b}.1", (cin, 2 * s, cout), cin * 2 * s, cout)
+            wn(f"{b}.2.linear", (cout, 1, cout), cout, 0)
+            for j in (3, 4, 5):
+                r = f"{b}.{j}.block.layers"
+                w[f"{r}.0.alpha"] = np.ones((1, cout, 1), dtype=np.float32)
+                wn(f"{r}.1", (cout, 7, 1), cout * 7, cout)
+                w[f"{r}.2.alpha"] = np.ones((1, cout, 1), dtype=np.float32)
+                wn(f"{r}.3", (cout, 1, cout), cout, cout)
+            li += 1
+        cf = decoder_dim // 2 ** len(decoder_rates)
+        w[f"{p}.{li}.alpha"] = np.ones((1, cf, 1), dtype=np.float32)
+        wn(f"{p}.{li + 1}", (1, 7, cf), cf * 7, 1)
+        return w
+
     # -- loading (SNACDecoder.swift:135-189) ------------------------------------------------------
     @classmethod
     def from_config_dict(cls, cfg: dict, weights, device: int = 0) -> "SNAC":
@@ -57,6 +101,10 @@ class SNAC:
         from safetensors.numpy import load_file
         cfg = json.loads((model_dir / "config.json").read_text())
         return cls.from_config_dict(cfg, load_file(str(wpath)), device)
+
+    @property
+    def stream(self) -> int:
+        return int(_ffi.lib().b2a_snac_stream(self._h) or 0)
 
     # -- AudioCodecModel ------------------------------------------------------------------------
     @property

@@ -112,8 +112,11 @@ def init_weights(cfg: SNACConfig, seed: int = 1234) -> Dict[str, np.ndarray]:
 
 # --------------------------------------------------------------------------- primitives
 
+DTYPE = torch.float64   # bench.py's cpu_baseline leg switches this to float32 (the reference computes in fp32)
+
+
 def _t(a) -> torch.Tensor:
-    return torch.as_tensor(np.asarray(a), dtype=torch.float64)
+    return torch.as_tensor(np.asarray(a), dtype=DTYPE)
 
 
 def wn_conv_weight(w: Dict, prefix: str) -> torch.Tensor:
