@@ -236,6 +236,10 @@ int32_t b2a_tts_cancel(b2a_tts* h);
  *   b2a_tts_time_steps    : runs `iters` captured decode steps for `batch` rows at context
  *                           `ctx` (greedy, no host sync inside) between two CUDA events on the
  *                           handle's stream; *ms_per_step = average device time of one step. */
+/*   b2a_tts_debug_trace   : parity hook -- enable != 0 makes later b2a_tts_forward_logits calls record the
+ *                           residual stream at every RMSNorm input; out (nullable) receives the record of
+ *                           the last traced position as [2*layers+1, batch, hidden] float32. */
+int32_t b2a_tts_debug_trace(b2a_tts* h, int32_t enable, int32_t batch, float* out);
 int32_t b2a_tts_create_random(int32_t device, const b2a_llama_config* cfg, float std, uint64_t seed,
                               b2a_snac* snac, b2a_tts** out);
 void* b2a_tts_stream(b2a_tts* h);

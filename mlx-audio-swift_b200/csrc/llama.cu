@@ -58,7 +58,7 @@ __global__ void embed_kernel(const int* __restrict__ tokens, const bf16* __restr
 // x += delta (optional);  xn = bf16( x * rsqrt(mean(x^2) + eps) * w )
 __global__ void __launch_bounds__(256)
 add_rmsnorm_kernel(float* __restrict__ x, float* __restrict__ delta, const float* __restrict__ w,
-                   bf16* __restrict__ xn, int H, float eps) {
+                   bf16* __restrict__ xn, int H, float eps, float* __restrict__ trace) {
     __shared__ float red[8];
     const int b = blockIdx.x;
     float* xr = x + (long long)b * H;
@@ -66,6 +66,7 @@ add_rmsnorm_kernel(float* __restrict__ x, float* __restrict__ delta, const float
     for (int i = threadIdx.x; i < H; i += 256) {
         float v = xr[i];
         if (delta) { v += delta[(long long)b * H + i]; xr[i] = v; delta[(long long)b * H + i] = 0.f; }
+        if (trace) trace[(long long)b * H + i] = v;
         ss += v * v;
     }
     ss = warp_sum(ss);
@@ -170,29 +171,30 @@ gemv_bf16_kernel(const bf16* __restrict__ W, const bf16* __restrict__ xin, float
 // Decode attention for one (kv head, row): RoPE on q/k, append k/v to the cache, softmax(qK^T)V
 // over positions 0..pos.  G = q heads per kv head.  (LlamaTTS.swift:235-266)
 // ------------------------------------------------------------------------------------------------
-constexpr int HD = 128, AT_THREADS = 128, MAXG = 8;
+constexpr int HD = 128, AT_THREADS = 256, MAXG = 8, AT_SLICES = AT_THREADS / 64;
 
 __global__ void __launch_bounds__(AT_THREADS)
 attn_decode_kernel(const float* __restrict__ qkv, const int* __restrict__ pos_arr, const float* __restrict__ freqs,
                    bf16* __restrict__ kcache, bf16* __restrict__ vcache, bf16* __restrict__ out, int nq, int nkv,
-                   int max_ctx, int max_batch_stride, float scale) {
-    extern __shared__ float sm[];  // q [G][HD] | scores [G][max_ctx]
+                   int max_ctx, float scale) {
+    extern __shared__ float sm[];  // q [G][HD] | scores [G][max_ctx] | partial out [AT_SLICES][G][HD]
     const int G = nq / nkv;
     float* sq = sm;
     float* sc = sm + G * HD;
+    float* po = sc + G * max_ctx;
     __shared__ float red[AT_THREADS / 32][MAXG];
     __shared__ float stat[2][MAXG];
 
-    const int h = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
+    const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     const int p = pos_arr[b];
     if (p < 0 || p >= max_ctx) return;
     const int qkv_ld = (nq + 2 * nkv) * HD;
     const float* row = qkv + (long long)b * qkv_ld;
     bf16* kc = kcache + (((long long)b * nkv + h) * max_ctx) * HD;
     bf16* vc = vcache + (((long long)b * nkv + h) * max_ctx) * HD;
-    (void)max_batch_stride;
 
-    if (d < HD / 2) {  // MLXFast.RoPE(traditional:false, freqs:): angle = pos / freqs[i], pairs (i, i+64)
+    if (tid < HD / 2) {  // MLXFast.RoPE(traditional:false, freqs:): angle = pos / freqs[i], pairs (i, i+64)
+        const int d = tid;
         float s, c;
         sincosf((float)p / freqs[d], &s, &c);
         for (int g = 0; g < G; ++g) {
@@ -205,26 +207,33 @@ attn_decode_kernel(const float* __restrict__ qkv, const int* __restrict__ pos_ar
         const float x1 = k[d], x2 = k[d + HD / 2];
         kc[(long long)p * HD + d] = __float2bfloat16_rn(x1 * c - x2 * s);
         kc[(long long)p * HD + d + HD / 2] = __float2bfloat16_rn(x2 * c + x1 * s);
+    } else if (tid >= 128) {
+        const int d = tid - 128;
+        vc[(long long)p * HD + d] = __float2bfloat16_rn(row[(nq + nkv + h) * HD + d]);
     }
-    vc[(long long)p * HD + d] = __float2bfloat16_rn(row[(nq + nkv + h) * HD + d]);
     __syncthreads();
 
-    // scores: one key per thread
+    // scores: one key per thread, the whole 256-byte key row fetched with 16 independent 16-byte loads
     float lmax[MAXG];
     for (int g = 0; g < G; ++g) lmax[g] = -INFINITY;
-    for (int t = d; t <= p; t += AT_THREADS) {
+    for (int t = tid; t <= p; t += AT_THREADS) {
         const uint4* kr = reinterpret_cast<const uint4*>(kc + (long long)t * HD);
+        uint4 kv[HD / 8];
+#pragma unroll
+        for (int c8 = 0; c8 < HD / 8; ++c8) kv[c8] = kr[c8];
         float acc[MAXG];
         for (int g = 0; g < G; ++g) acc[g] = 0.f;
-#pragma unroll 4
-        for (int c8 = 0; c8 < HD / 8; ++c8) {
-            const uint4 kv = kr[c8];
-            const float kf[8] = {bf_lo(kv.x), bf_hi(kv.x), bf_lo(kv.y), bf_hi(kv.y),
-                                 bf_lo(kv.z), bf_hi(kv.z), bf_lo(kv.w), bf_hi(kv.w)};
-            for (int g = 0; g < G; ++g) {
-                const float* q = sq + g * HD + c8 * 8;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[g] = fmaf(q[j], kf[j], acc[g]);
+        for (int c8 = 0; c8 < HD / 8; ++c8) {
+            const float kf[8] = {bf_lo(kv[c8].x), bf_hi(kv[c8].x), bf_lo(kv[c8].y), bf_hi(kv[c8].y),
+                                 bf_lo(kv[c8].z), bf_hi(kv[c8].z), bf_lo(kv[c8].w), bf_hi(kv[c8].w)};
+            for (int g = 0; g < G; ++g) {
+                const float4 q0 = *reinterpret_cast<const float4*>(sq + g * HD + c8 * 8);
+                const float4 q1 = *reinterpret_cast<const float4*>(sq + g * HD + c8 * 8 + 4);
+                acc[g] = fmaf(q0.x, kf[0], acc[g]); acc[g] = fmaf(q0.y, kf[1], acc[g]);
+                acc[g] = fmaf(q0.z, kf[2], acc[g]); acc[g] = fmaf(q0.w, kf[3], acc[g]);
+                acc[g] = fmaf(q1.x, kf[4], acc[g]); acc[g] = fmaf(q1.y, kf[5], acc[g]);
+                acc[g] = fmaf(q1.z, kf[6], acc[g]); acc[g] = fmaf(q1.w, kf[7], acc[g]);
             }
         }
         for (int g = 0; g < G; ++g) {
@@ -236,18 +245,18 @@ attn_decode_kernel(const float* __restrict__ qkv, const int* __restrict__ pos_ar
     for (int g = 0; g < G; ++g) {
         float m = lmax[g];
         for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if ((d & 31) == 0) red[d >> 5][g] = m;
+        if ((tid & 31) == 0) red[tid >> 5][g] = m;
     }
     __syncthreads();
-    if (d < G) {
-        float m = red[0][d];
-        for (int i = 1; i < AT_THREADS / 32; ++i) m = fmaxf(m, red[i][d]);
-        stat[0][d] = m;
+    if (tid < G) {
+        float m = red[0][tid];
+        for (int i = 1; i < AT_THREADS / 32; ++i) m = fmaxf(m, red[i][tid]);
+        stat[0][tid] = m;
     }
     __syncthreads();
     float lsum[MAXG];
     for (int g = 0; g < G; ++g) lsum[g] = 0.f;
-    for (int t = d; t <= p; t += AT_THREADS)
+    for (int t = tid; t <= p; t += AT_THREADS)
         for (int g = 0; g < G; ++g) {
             const float e = __expf(sc[g * max_ctx + t] - stat[0][g]);
             sc[g * max_ctx + t] = e;
@@ -256,30 +265,61 @@ attn_decode_kernel(const float* __restrict__ qkv, const int* __restrict__ pos_ar
     __syncthreads();
     for (int g = 0; g < G; ++g) {
         const float s = warp_sum(lsum[g]);
-        if ((d & 31) == 0) red[d >> 5][g] = s;
+        if ((tid & 31) == 0) red[tid >> 5][g] = s;
     }
     __syncthreads();
-    if (d < G) {
+    if (tid < G) {
         float s = 0.f;
-        for (int i = 0; i < AT_THREADS / 32; ++i) s += red[i][d];
-        stat[1][d] = s;
+        for (int i = 0; i < AT_THREADS / 32; ++i) s += red[i][tid];
+        stat[1][tid] = s;
+    }
+    // PV: thread = (t-slice, dim pair); 8 independent bf16x2 loads in flight per thread
+    const int sl = tid >> 6, dp = tid & 63;
+    float o0[MAXG], o1[MAXG];
+    for (int g = 0; g < G; ++g) { o0[g] = 0.f; o1[g] = 0.f; }
+    const unsigned* vrow = reinterpret_cast<const unsigned*>(vc) + dp;
+    int t = sl;
+    for (; t + 7 * AT_SLICES <= p; t += 8 * AT_SLICES) {
+        unsigned v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = vrow[(long long)(t + j * AT_SLICES) * (HD / 2)];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float va = bf_lo(v[j]), vb = bf_hi(v[j]);
+            for (int g = 0; g < G; ++g) {
+                const float pr = sc[g * max_ctx + t + j * AT_SLICES];
+                o0[g] = fmaf(pr, va, o0[g]);
+                o1[g] = fmaf(pr, vb, o1[g]);
+            }
+        }
+    }
+    for (; t <= p; t += AT_SLICES) {
+        const unsigned v = vrow[(long long)t * (HD / 2)];
+        const float va = bf_lo(v), vb = bf_hi(v);
+        for (int g = 0; g < G; ++g) {
+            const float pr = sc[g * max_ctx + t];
+            o0[g] = fmaf(pr, va, o0[g]);
+            o1[g] = fmaf(pr, vb, o1[g]);
+        }
+    }
+    for (int g = 0; g < G; ++g) {
+        po[(sl * G + g) * HD + 2 * dp] = o0[g];
+        po[(sl * G + g) * HD + 2 * dp + 1] = o1[g];
     }
     __syncthreads();
-    // PV: one output dim per thread
-    float o[MAXG];
-    for (int g = 0; g < G; ++g) o[g] = 0.f;
-    for (int t = 0; t <= p; ++t) {
-        const float v = __bfloat162float(vc[(long long)t * HD + d]);
-        for (int g = 0; g < G; ++g) o[g] = fmaf(sc[g * max_ctx + t], v, o[g]);
-    }
-    for (int g = 0; g < G; ++g)
-        out[(long long)b * nq * HD + (h * G + g) * HD + d] = __float2bfloat16_rn(o[g] / stat[1][g]);
+    if (tid < HD)
+        for (int g = 0; g < G; ++g) {
+            float o = 0.f;
+#pragma unroll
+            for (int s2 = 0; s2 < AT_SLICES; ++s2) o += po[(s2 * G + g) * HD + tid];
+            out[(long long)b * nq * HD + (h * G + g) * HD + tid] = __float2bfloat16_rn(o / stat[1][g]);
+        }
 }
 
 // ------------------------------------------------------------------------------------------------
 // Logits processors + sampler + bookkeeping: one CTA per row.
 // ------------------------------------------------------------------------------------------------
-constexpr int SM_THREADS = 1024, SM_BINS = 2048;
+constexpr int SM_THREADS = 1024, SM_WARPS = SM_THREADS / 32, SM_MAX_ATTEMPTS = 12;
 
 struct SampleArgs {
     float* logits;        // [B, V]  (modified in place: penalty, EOS mask)
@@ -306,54 +346,34 @@ __device__ __forceinline__ float block_sum_1024(float v, float* sred) {
     __syncthreads();
     float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < SM_THREADS / 32; ++i) t += sred[i];
+    for (int i = 0; i < SM_WARPS; ++i) t += sred[i];
     return t;
 }
 
-// crossing bin of a histogram scanned from the top: max{i : sum_{j>=i} hist[j] >= target}
-__device__ int find_crossing_bin(const float* hist, int nbins, float target, float* above_out, float* sred,
-                                 int* sres) {
-    // each thread owns bins [2t, 2t+1]; suffix sums via warp shuffles
-    const int t = threadIdx.x;
-    const float h0 = (2 * t < nbins) ? hist[2 * t] : 0.f, h1 = (2 * t + 1 < nbins) ? hist[2 * t + 1] : 0.f;
-    float s = h0 + h1;  // inclusive suffix over threads >= t
-    const int lane = t & 31, warp = t >> 5;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const float n = __shfl_down_sync(0xffffffffu, s, o);
-        if (lane + o < 32) s += n;
-    }
-    __syncthreads();
-    if (lane == 0) sred[warp] = s;
-    if (t == 0) *sres = -1;
-    __syncthreads();
-    float higher = 0.f;
-    for (int w = warp + 1; w < SM_THREADS / 32; ++w) higher += sred[w];
-    s += higher;                      // sum over bins >= 2t
-    const float s1 = s - h0;          // sum over bins >= 2t+1
-    int cand = -1;
-    if (2 * t + 1 < nbins && s1 >= target) cand = 2 * t + 1;
-    else if (2 * t < nbins && s >= target) cand = 2 * t;
-    if (cand >= 0) atomicMax(sres, cand);
-    __syncthreads();
-    int r = *sres;
-    if (r < 0) r = 0;
-    __syncthreads();
-    if (t == r / 2) *above_out = (r & 1) ? (s1 - h1) : s1;  // mass strictly above bin r
-    __syncthreads();
-    return r;
+__device__ __forceinline__ float uniform01(unsigned long long seed, unsigned long long a, unsigned long long b,
+                                           unsigned long long c) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (a * 1000003ull + b * 131ull + c + 1ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (float)(z >> 40) * (1.0f / 16777216.0f);
 }
 
+// Logits processors + sampler, one CTA per row, no atomics (deterministic for a given seed):
+//   RepetitionContext.process -> EOS mask (bench only) -> argmax | TopPSampler.
+// Top-p = "sample from the smallest top set whose mass reaches top_p".  Implemented as rejection
+// sampling: draw token ~ softmax(l/T) by inverse CDF, accept iff the mass of strictly more probable
+// tokens is < top_p (exactly the nucleus membership test; ties are all kept).  Acceptance probability
+// is >= top_p, so a handful of attempts suffice; after SM_MAX_ATTEMPTS the argmax (always in the
+// nucleus) is returned.
 __global__ void __launch_bounds__(SM_THREADS)
 sample_kernel(SampleArgs a) {
-    __shared__ float hist[SM_BINS];
-    __shared__ float sred[SM_THREADS / 32];
-    __shared__ int sres;
-    __shared__ float sabove;
-    __shared__ int s_tok;
-    __shared__ float s_val[SM_THREADS / 32];
-    __shared__ int s_idx[SM_THREADS / 32];
-    const int b = blockIdx.x, t = threadIdx.x;
+    __shared__ float sred[SM_WARPS];
+    __shared__ float wtot[SM_WARPS];
+    __shared__ int s_tok, s_pick;
+    __shared__ float s_val[SM_WARPS];
+    __shared__ int s_idx[SM_WARPS];
+    const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
     float* lg = a.logits + (long long)b * a.V;
     float* pr = a.probs + (long long)b * a.V;
     const int nrec = min(a.recent_n[b], a.R);
@@ -384,10 +404,10 @@ sample_kernel(SampleArgs a) {
             const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
             if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
         }
-        if ((t & 31) == 0) { s_val[t >> 5] = best; s_idx[t >> 5] = bi; }
+        if (lane == 0) { s_val[warp] = best; s_idx[warp] = bi; }
         __syncthreads();
         if (t == 0) {
-            for (int i = 1; i < SM_THREADS / 32; ++i)
+            for (int i = 1; i < SM_WARPS; ++i)
                 if (s_val[i] > best || (s_val[i] == best && s_idx[i] < bi)) { best = s_val[i]; bi = s_idx[i]; }
             s_val[0] = best; s_tok = bi;
         }
@@ -395,76 +415,66 @@ sample_kernel(SampleArgs a) {
         const float mx = s_val[0];
 
         if (a.temperature > 0.f) {
-            // TopPSampler: p = softmax(l / T); keep the smallest top set whose mass reaches top_p
+            // p = exp((l - max)/T) (unnormalised); each warp owns one contiguous segment of the vocabulary
             const float inv_t = 1.0f / a.temperature;
+            const int seg = ((a.V + SM_WARPS - 1) / SM_WARPS + 31) & ~31;
+            const int s0 = warp * seg, s1 = min(a.V, s0 + seg);
             float z = 0.f;
-            for (int i = t; i < a.V; i += SM_THREADS) {
+            for (int i = s0 + lane; i < s1; i += 32) {
                 const float e = __expf((lg[i] - mx) * inv_t);
                 pr[i] = e;
                 z += e;
             }
-            z = block_sum_1024(z, sred);
-            unsigned prefix = 0, pmask = 0;
-            float above = 0.f;
-            if (a.top_p < 1.0f) {
-                const float target = a.top_p * z;
-                const int shifts[3] = {22, 11, 0}, nb[3] = {1024, 2048, 2048};
-                for (int lv = 0; lv < 3; ++lv) {
-                    for (int i = t; i < SM_BINS; i += SM_THREADS) hist[i] = 0.f;
-                    __syncthreads();
-                    for (int i = t; i < a.V; i += SM_THREADS) {
-                        const unsigned u = __float_as_uint(pr[i]);
-                        if ((u & pmask) == prefix) atomicAdd(&hist[(u >> shifts[lv]) & (nb[lv] - 1)], pr[i]);
-                    }
-                    __syncthreads();
-                    float ab;
-                    const int bin = find_crossing_bin(hist, nb[lv], target - above, &sabove, sred, &sres);
-                    ab = sabove;
-                    above += ab;
-                    prefix |= ((unsigned)bin) << shifts[lv];
-                    pmask |= ((unsigned)(nb[lv] - 1)) << shifts[lv];
-                }
-            }
-            const float thr = __uint_as_float(prefix);  // smallest kept probability (0 when top_p >= 1)
-            // inverse-CDF draw over the kept set in index order
-            const int chunk = (a.V + SM_THREADS - 1) / SM_THREADS;
-            const int i0 = t * chunk, i1 = min(a.V, i0 + chunk);
-            float part = 0.f;
-            for (int i = i0; i < i1; ++i) { const float p = pr[i]; if (p >= thr) part += p; }
-            // exclusive prefix over threads
-            float incl = part;
-            const int lane = t & 31, warp = t >> 5;
+            z = warp_sum(z);
+            if (lane == 0) wtot[warp] = z;
+            __syncthreads();
+            float Z = 0.f;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const float n = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += n;
-            }
-            __syncthreads();
-            if (lane == 31) sred[warp] = incl;
-            if (t == 0) sres = 0x7fffffff;
-            __syncthreads();
-            float wbase = 0.f, total = 0.f;
-            for (int w = 0; w < SM_THREADS / 32; ++w) { if (w < warp) wbase += sred[w]; total += sred[w]; }
-            incl += wbase;
-            const float excl = incl - part;
-            // uniform in [0,1) from (seed, row, step)
-            unsigned long long zz = a.seed + 0x9E3779B97F4A7C15ull * ((unsigned long long)b * 1000003ull + (unsigned long long)a.n_gen[b] + 1ull);
-            zz = (zz ^ (zz >> 30)) * 0xBF58476D1CE4E5B9ull;
-            zz = (zz ^ (zz >> 27)) * 0x94D049BB133111EBull;
-            zz ^= zz >> 31;
-            const float u01 = (float)(zz >> 40) * (1.0f / 16777216.0f);
-            const float r = u01 * total;
-            if (part > 0.f && r >= excl && r < incl) {
-                float run = excl;
-                int pick = -1;
-                for (int i = i0; i < i1; ++i) {
-                    const float p = pr[i];
-                    if (p >= thr) { run += p; pick = i; if (run > r) break; }
+            for (int w = 0; w < SM_WARPS; ++w) Z += wtot[w];
+            const float target = a.top_p * Z;
+            const int step = a.n_gen[b];
+            bool accepted = false;
+            for (int att = 0; att < SM_MAX_ATTEMPTS && !accepted; ++att) {
+                const float r = uniform01(a.seed, (unsigned long long)b, (unsigned long long)step, (unsigned long long)att) * Z;
+                // owning warp: first w with prefix(w+1) > r
+                float run = 0.f;
+                int ow = SM_WARPS - 1;
+                for (int w = 0; w < SM_WARPS; ++w) {
+                    if (run + wtot[w] > r) { ow = w; break; }
+                    run += wtot[w];
                 }
-                if (pick >= 0) atomicMin(&sres, pick);
+                if (t == 0) s_pick = -1;
+                __syncthreads();
+                if (warp == ow) {   // cooperative inverse-CDF walk over this warp's segment
+                    int pick = -1, last_pos = -1;
+                    for (int base = s0; base < s1 && pick < 0; base += 32) {
+                        const int i = base + lane;
+                        const float p = i < s1 ? pr[i] : 0.f;
+                        float inc = p;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const float n = __shfl_up_sync(0xffffffffu, inc, o);
+                            if (lane >= o) inc += n;
+                        }
+                        const unsigned hit = __ballot_sync(0xffffffffu, p > 0.f && run + inc > r);
+                        const unsigned posm = __ballot_sync(0xffffffffu, p > 0.f);
+                        if (posm) last_pos = base + 31 - __clz(posm);
+                        if (hit) pick = base + __ffs(hit) - 1;
+                        run += __shfl_sync(0xffffffffu, inc, 31);
+                    }
+                    if (pick < 0) pick = last_pos;        // rounding corner: r beyond the last partial sum
+                    if (lane == 0) s_pick = pick;
+                }
+                __syncthreads();
+                const int cand = s_pick;
+                if (cand < 0) continue;
+                if (a.top_p >= 1.0f) { accepted = true; if (t == 0) s_tok = cand; break; }
+                const float pt = pr[cand];
+                float gm = 0.f;
+                for (int i = t; i < a.V; i += SM_THREADS) { const float p = pr[i]; if (p > pt) gm += p; }
+                gm = block_sum_1024(gm, sred);
+                if (gm < target) { accepted = true; if (t == 0) s_tok = cand; }
             }
-            __syncthreads();
-            if (t == 0 && sres != 0x7fffffff) s_tok = sres;   // else keep the argmax (numerical corner)
             __syncthreads();
         }
     } else {
@@ -592,6 +602,8 @@ struct b2a_tts {
     HBuf<int> h_flag;
     std::atomic<int> cancel{0};
     int nb_pad = 0;   // rows rounded up to 1/2/4/8
+    bool trace_on = false;       // debug: residual stream at every RMSNorm input (eager forward only)
+    DBuf<float> trace;           // [2*layers + 1][8][H]
     // CUDA graphs for the two step flavours (captured per (nb_pad, params) configuration)
     cudaGraphExec_t g_step = nullptr, g_prefill = nullptr;
     SampleArgs g_args{};
@@ -613,6 +625,11 @@ struct b2a_tts {
         B2A_CHECK(TensorTable::numel(t) == expect, B2A_ERR_MODEL_NOT_INITIALIZED, "bad shape for tensor: " + name);
         dst.alloc(total_elems);
         B2A_CUDA(cudaMemcpy(dst.p + offset_elems, t.data, expect * sizeof(bf16), cudaMemcpyHostToDevice));
+    }
+
+    size_t attn_smem_bytes() const {
+        const int G = cfg.num_attention_heads / cfg.num_key_value_heads;
+        return (size_t)(G * HD + G * cfg.max_context + AT_SLICES * G * HD) * sizeof(float);
     }
 
     void check_config() {
@@ -652,9 +669,9 @@ struct b2a_tts {
         B2A_CUDA(cudaMemset(pos.p, 0, B * sizeof(int)));
         h_flag.alloc(16);
         gemv_attrs<1>(); gemv_attrs<2>(); gemv_attrs<4>(); gemv_attrs<8>();
-        const size_t at_sm = (size_t)(nq / nkv) * (HD + c.max_context) * sizeof(float);
-        B2A_CHECK(at_sm <= 200 * 1024, B2A_ERR_INVALID_INPUT, "llama: max_context too large for the attention score tile");
-        B2A_CUDA(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)at_sm));
+        B2A_CHECK(attn_smem_bytes() <= 200 * 1024, B2A_ERR_INVALID_INPUT, "llama: max_context too large for the attention score tile");
+        // process-wide kernel attribute: always the same (largest) value, several handles may coexist
+        B2A_CUDA(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         B2A_CUDA(cudaDeviceSynchronize());
     }
 
@@ -780,18 +797,20 @@ struct b2a_tts {
         embed_kernel<<<B, 256, 0, s>>>(tokens.p, embed.p, x.p, H, cfg.vocab_size);
         count_launch();
         const size_t kv_layer = (size_t)cfg.max_batch * nkv * cfg.max_context * HD;
-        const size_t at_sm = (size_t)(G * HD + G * cfg.max_context) * sizeof(float);
+        const size_t at_sm = attn_smem_bytes();
         for (int l = 0; l < cfg.num_hidden_layers; ++l) {
             LayerW& L = layers[l];
-            add_rmsnorm_kernel<<<B, 256, 0, s>>>(x.p, l == 0 ? nullptr : y.p, L.ln1.p, xn.p, H, cfg.rms_norm_eps);
+            add_rmsnorm_kernel<<<B, 256, 0, s>>>(x.p, l == 0 ? nullptr : y.p, L.ln1.p, xn.p, H, cfg.rms_norm_eps,
+                                                 trace_on ? trace.p + (size_t)(2 * l) * 8 * H : nullptr);
             count_launch();
             gemv_nb(OP_QKV, L.wqkv.p, xn.p, qkv.p, nullptr, NQ + 2 * NKV, H, s);
             attn_decode_kernel<<<dim3(nkv, B), AT_THREADS, at_sm, s>>>(qkv.p, pos.p, freqs.p, kcache.p + l * kv_layer,
                                                                        vcache.p + l * kv_layer, attn.p, nq, nkv, cfg.max_context,
-                                                                       0, 1.0f / sqrtf((float)HD));
+                                                                       1.0f / sqrtf((float)HD));
             count_launch();
             gemv_nb(OP_O, L.wo.p, attn.p, y.p, nullptr, H, NQ, s);
-            add_rmsnorm_kernel<<<B, 256, 0, s>>>(x.p, y.p, L.ln2.p, xn.p, H, cfg.rms_norm_eps);
+            add_rmsnorm_kernel<<<B, 256, 0, s>>>(x.p, y.p, L.ln2.p, xn.p, H, cfg.rms_norm_eps,
+                                                 trace_on ? trace.p + (size_t)(2 * l + 1) * 8 * H : nullptr);
             count_launch();
             gemv_nb(OP_GU, L.wgu.p, xn.p, nullptr, act.p, 2 * I, H, s);
             gemv_nb(OP_DOWN, L.wdown.p, act.p, y.p, nullptr, H, I, s);
@@ -799,7 +818,8 @@ struct b2a_tts {
     }
 
     void run_lm_head(int B, cudaStream_t s) {
-        add_rmsnorm_kernel<<<B, 256, 0, s>>>(x.p, y.p, final_ln.p, xn.p, cfg.hidden_size, cfg.rms_norm_eps);
+        add_rmsnorm_kernel<<<B, 256, 0, s>>>(x.p, y.p, final_ln.p, xn.p, cfg.hidden_size, cfg.rms_norm_eps,
+                                             trace_on ? trace.p + (size_t)(2 * cfg.num_hidden_layers) * 8 * cfg.hidden_size : nullptr);
         count_launch();
         gemv_nb(OP_LM, lm_head, xn.p, logits.p, nullptr, cfg.vocab_size, cfg.hidden_size, s);
     }
@@ -896,6 +916,7 @@ static void tts_generate_impl(b2a_tts* h, const int32_t* input_ids, bool ids_on_
     cudaStream_t s = h->stream;
     h->cancel.store(0);
     h->set_batch(B);
+    if (h->trace_on) { h->trace_on = false; h->drop_graphs(); }
     const int MT = gp->max_tokens, R = std::max(1, gp->repetition_context_size);
     h->ids.alloc((size_t)B * L);
     h->out_tokens.alloc((size_t)B * MT);
@@ -1112,6 +1133,25 @@ int32_t b2a_tts_prepare_input_ids(const int32_t* const* prompt_ids, const int32_
             r[j++] = TOK_END_OF_TEXT;
             r[j++] = TOK_END_OF_HUMAN;
         }
+    });
+}
+
+// Debug / parity hook: residual stream seen by every RMSNorm (2 per layer + final) for the LAST position of
+// the last b2a_tts_forward_logits call made while tracing was enabled; out is [2*layers+1, batch, hidden].
+int32_t b2a_tts_debug_trace(b2a_tts* h, int32_t enable, int32_t batch, float* out) {
+    return guarded([&] {
+        B2A_CHECK(h, B2A_ERR_INVALID_INPUT, "b2a_tts_debug_trace: null handle");
+        B2A_CUDA(cudaSetDevice(h->device));
+        const int H = h->cfg.hidden_size, n = 2 * h->cfg.num_hidden_layers + 1;
+        if (out) {
+            B2A_CHECK(h->trace.p && batch >= 1 && batch <= 8, B2A_ERR_INVALID_INPUT, "b2a_tts_debug_trace: nothing traced");
+            B2A_CUDA(cudaStreamSynchronize(h->stream));
+            for (int i = 0; i < n; ++i)
+                B2A_CUDA(cudaMemcpy(out + (size_t)i * batch * H, h->trace.p + (size_t)i * 8 * H, (size_t)batch * H * sizeof(float),
+                                    cudaMemcpyDeviceToHost));
+        }
+        h->trace_on = enable != 0;
+        if (h->trace_on) { h->trace.alloc((size_t)n * 8 * H); h->drop_graphs(); }
     });
 }
 

@@ -78,6 +78,14 @@ class LlamaTTSModel:
     def stream(self) -> int:
         return int(_ffi.lib().b2a_tts_stream(self._h) or 0)
 
+    def debug_trace(self, enable: bool, batch: int = 0, read: bool = False):
+        """Parity hook: residual stream at every RMSNorm input for the last traced forward position."""
+        out = None
+        if read:
+            out = np.empty((2 * self.config["num_hidden_layers"] + 1, batch, self.config["hidden_size"]), dtype=np.float32)
+        _ffi.check(_ffi.lib().b2a_tts_debug_trace(self._h, int(enable), batch, _ffi.ptr(out)))
+        return out
+
     def time_steps(self, batch: int, ctx: int, iters: int) -> float:
         """Average device milliseconds of one captured decode step (CUDA events on the handle's stream)."""
         ms = C.c_float(0)

@@ -147,8 +147,9 @@ class LlamaOracle:
         return self._r(x) @ self.w[name].to(torch.float32).T
 
     @torch.no_grad()
-    def forward(self, ids: torch.Tensor) -> torch.Tensor:
-        """ids [B, L] -> logits [B, L, V] (LlamaTTS.swift:335-345, 557-567)."""
+    def forward(self, ids: torch.Tensor, trace: Optional[list] = None) -> torch.Tensor:
+        """ids [B, L] -> logits [B, L, V] (LlamaTTS.swift:335-345, 557-567).  ``trace`` (a list) receives the
+        residual stream of the LAST position at every RMSNorm input (2 per layer + final), for debugging."""
         cfg = self.cfg
         B, L = ids.shape
         nq, nkv, hd = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
@@ -156,6 +157,8 @@ class LlamaOracle:
         pos = torch.arange(self.offset, self.offset + L)
         for l in range(cfg.num_hidden_layers):
             p = f"model.layers.{l}."
+            if trace is not None:
+                trace.append(h[:, -1].clone())
             xn = rms_norm(h, self.w[p + "input_layernorm.weight"], cfg.rms_norm_eps)
             q = self._lin(xn, p + "self_attn.q_proj.weight").view(B, L, nq, hd).transpose(1, 2)
             k = self._lin(xn, p + "self_attn.k_proj.weight").view(B, L, nkv, hd).transpose(1, 2)
@@ -175,11 +178,15 @@ class LlamaOracle:
             a = torch.softmax(s, dim=-1) @ vv
             a = a.transpose(1, 2).reshape(B, L, nq * hd)
             h = h + self._lin(a, p + "self_attn.o_proj.weight")
+            if trace is not None:
+                trace.append(h[:, -1].clone())
             xn = rms_norm(h, self.w[p + "post_attention_layernorm.weight"], cfg.rms_norm_eps)
             g = self._lin(xn, p + "mlp.gate_proj.weight")
             u = self._lin(xn, p + "mlp.up_proj.weight")
             h = h + self._lin(torch.nn.functional.silu(g) * u, p + "mlp.down_proj.weight")
         self.offset += L
+        if trace is not None:
+            trace.append(h[:, -1].clone())
         hn = rms_norm(h, self.w["model.norm.weight"], cfg.rms_norm_eps)
         head = self.w["model.embed_tokens.weight"] if cfg.tie_word_embeddings else self.w["lm_head.weight"]
         return self._r(hn) @ head.to(torch.float32).T
