@@ -1,0 +1,317 @@
+// tcgen05 + TMA "weights-as-A" GEMM for sm_100a:  D[M, N] = W[M, K] * X[N, K]^T   (bf16 in, fp32 accumulate)
+//   W : weights, [M, K] row-major (K-major)  -> A operand, 128 x 64 tiles by TMA (SWIZZLE_128B)
+//   X : activations, [N, K] row-major        -> B operand, BN x 64 tiles by TMA
+//   D : accumulated in TMEM (128 lanes x BN fp32 columns, double buffered), written TRANSPOSED as
+//       out[n, m] so it is the next layer's [tokens, features] activation matrix.
+// Swap-AB keeps the tensor-core M dimension (128) full with output features even when there are only
+// 8 tokens (autoregressive decode), where the kernel is purely a weight-streaming engine: one elected
+// thread issues TMA into a deep shared-memory ring (~200 KB in flight per SM), one elected thread issues
+// tcgen05.mma, four warps drain TMEM.  Work is split stream-K style: the (m_tile, k_block) units are
+// dealt evenly and contiguously to the CTAs; a CTA that owns only part of a tile's K range adds its
+// partial into the (zeroed) fp32 output with red.global.add.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b2a {
+namespace tc {
+
+constexpr int BM = 128, BK = 64, UMMA_K = 16;
+constexpr int THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+enum : int { EPI_STORE = 0, EPI_ATOMIC = 1, EPI_SWIGLU = 2, EPI_STORE_BF16 = 3 };
+
+struct Args {
+    float* out_f32;          // [N, ldo] fp32 (EPI_STORE / EPI_ATOMIC)
+    __nv_bfloat16* out_bf16; // [N, ldo] bf16 (EPI_SWIGLU: ldo = M/2 ; EPI_STORE_BF16)
+    int M, N, K;             // N = valid tokens (rows of X)
+    int ldo;                 // leading dimension of the output (elements)
+    int m_tiles, k_blocks;   // ceil(M/128), K/64
+    int stages;              // smem ring depth
+    int epi_full;            // epilogue when a CTA owns a tile's whole K range
+    int epi_partial;         // epilogue for partial K ranges (EPI_ATOMIC); < 0 => CTAs own whole tiles only
+    int hilo;                // X rows [0, BN/2) = hi(x), rows [BN/2, BN) = lo(x) = bf16(x - hi): columns j and
+                             // j + BN/2 of the accumulator are summed, giving fp32-activation accuracy for free
+    int lo_rows;             // bf16 outputs are written as hi at row n and lo at row n + lo_rows (0 => hi only)
+};
+
+// ----------------------------------------------------------------------------------------------- PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    // bounded spin: a protocol bug traps (cudaErrorLaunchFailure) instead of hanging the GPU
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
+        if (spins > (1u << 28)) __trap();
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// start>>4 [0,14) | LBO>>4 [16,30) = 1 | SBO>>4 [32,46) = 1024/16 | version [46,48) = 1 | layout [61,64) = 2
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=BF16 [7,10)=1, b=BF16 [10,13)=1,
+// a/b K-major (0), n_dim [17,23) = N>>3, m_dim [24,29) = M>>4
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+template <int BN>
+struct Smem {
+    static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE = A_BYTES + B_BYTES;
+    static constexpr int TMEM_COLS = (2 * BN) <= 32 ? 32 : (2 * BN) <= 64 ? 64 : (2 * BN) <= 128 ? 128 : (2 * BN) <= 256 ? 256 : 512;
+    static int max_stages() { return (227 * 1024 - 1024 - 256) / STAGE; }
+    static size_t bytes(int stages) { return 1024 + (size_t)stages * STAGE + 256; }
+};
+
+template <int BN>
+__global__ void __launch_bounds__(THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Args a) {
+    using S = Smem<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)a.stages * S::STAGE);
+    uint64_t* empty = full + a.stages;
+    uint64_t* tfull = empty + a.stages;   // [2]
+    uint64_t* tempty = tfull + 2;         // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.y * BN;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int i = 0; i < a.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<S::TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // stream-K partition of the (m_tile, k_block) units, k fastest
+    const long long units = (long long)a.m_tiles * a.k_blocks;
+    long long u0, u1;
+    if (a.epi_partial >= 0) {
+        u0 = units * blockIdx.x / gridDim.x;
+        u1 = units * (blockIdx.x + 1) / gridDim.x;
+    } else {   // whole tiles per CTA (epilogues that cannot be split along K, e.g. SwiGLU)
+        u0 = ((long long)a.m_tiles * blockIdx.x / gridDim.x) * a.k_blocks;
+        u1 = ((long long)a.m_tiles * (blockIdx.x + 1) / gridDim.x) * a.k_blocks;
+    }
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (long long u = u0; u < u1; ++u) {
+                const int mt = (int)(u / a.k_blocks), kb = (int)(u - (long long)mt * a.k_blocks);
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* sa = smem + (size_t)stage * S::STAGE;
+                mbar_arrive_expect_tx(&full[stage], S::STAGE);
+                tma_load_2d(sa, &tmA, &full[stage], kb * BK, mt * BM);
+                tma_load_2d(sa + S::A_BYTES, &tmB, &full[stage], kb * BK, n0);
+                if (++stage == a.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BN);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            long long u = u0;
+            while (u < u1) {
+                const int mt = (int)(u / a.k_blocks);
+                const long long seg_end = min(u1, (long long)(mt + 1) * a.k_blocks);
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem_base + (uint32_t)(acc * BN);
+                bool first = true;
+                for (; u < seg_end; ++u) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * S::STAGE);
+                    const uint64_t ad = make_smem_desc(sa), bd = make_smem_desc(sa + S::A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        umma_bf16(d, ad + (uint64_t)(k * UMMA_K * 2 / 16), bd + (uint64_t)(k * UMMA_K * 2 / 16), idesc,
+                                  (first && k == 0) ? 0u : 1u);
+                    }
+                    first = false;
+                    umma_commit(&empty[stage]);          // frees the smem slot when these MMAs retire
+                    if (++stage == a.stages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull[acc]);                // accumulator of this segment complete
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        const int q = warp & 3;                           // TMEM lane quadrant this warp may access
+        int acc = 0; uint32_t acc_phase = 0;
+        long long u = u0;
+        while (u < u1) {
+            const int mt = (int)(u / a.k_blocks);
+            const long long seg_begin = u;
+            const long long seg_end = min(u1, (long long)(mt + 1) * a.k_blocks);
+            u = seg_end;
+            const bool whole = (seg_begin == (long long)mt * a.k_blocks) && (seg_end == (long long)(mt + 1) * a.k_blocks);
+            const int epi = whole ? a.epi_full : a.epi_partial;
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const int m = mt * BM + q * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+            constexpr int HALF = BN / 2;
+            // hilo: process column chunk c0 of the hi half together with chunk c0 + HALF of the lo half
+            const int n_cols = a.hilo ? HALF : BN;
+            for (int c0 = 0; c0 < n_cols; c0 += (BN == 16 ? 8 : 16)) {
+                float v[16];
+                constexpr int CH = (BN == 16) ? 8 : 16;      // columns handled per iteration
+                if (BN == 16) {
+                    tmem_ld16(taddr, v);                     // all 16 columns: [0,8) hi, [8,16) lo
+                    if (a.hilo) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] += v[j + 8];
+                    }
+                } else {
+                    tmem_ld16(taddr + c0, v);
+                    if (a.hilo) {
+                        float w[16];
+                        tmem_ld16(taddr + c0 + HALF, w);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] += w[j];
+                    }
+                }
+                const bool last = (BN == 16) || (c0 + CH >= n_cols);
+                if (last) {                               // last TMEM read of this accumulator: hand it back early
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[acc]);
+                }
+                const int jn = (BN == 16) ? (a.hilo ? 8 : 16) : 16;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    if (j >= jn) break;
+                    const int n = n0 + c0 + j;
+                    float val = v[j];
+                    if (epi == EPI_SWIGLU) {
+                        // rows are (gate, up) pairs: even lane = gate, odd lane = up   (LlamaTTS.swift:282-284)
+                        const float other = __shfl_xor_sync(0xffffffffu, val, 1);
+                        if (n < a.N && m < a.M && (lane & 1) == 0) {
+                            const float r = val / (1.0f + __expf(-val)) * other;
+                            const __nv_bfloat16 hi = __float2bfloat16_rn(r);
+                            a.out_bf16[(long long)n * a.ldo + (m >> 1)] = hi;
+                            if (a.lo_rows)
+                                a.out_bf16[(long long)(n + a.lo_rows) * a.ldo + (m >> 1)] = __float2bfloat16_rn(r - __bfloat162float(hi));
+                        }
+                    } else if (n < a.N && m < a.M) {
+                        if (epi == EPI_STORE) a.out_f32[(long long)n * a.ldo + m] = val;
+                        else if (epi == EPI_ATOMIC) atomicAdd(&a.out_f32[(long long)n * a.ldo + m], val);
+                        else {
+                            const __nv_bfloat16 hi = __float2bfloat16_rn(val);
+                            a.out_bf16[(long long)n * a.ldo + m] = hi;
+                            if (a.lo_rows)
+                                a.out_bf16[(long long)(n + a.lo_rows) * a.ldo + m] = __float2bfloat16_rn(val - __bfloat162float(hi));
+                        }
+                    }
+                }
+                if (BN == 16) break;
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<S::TMEM_COLS>(tmem_base);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 2-D bf16 row-major [rows, cols] tensor map with a {64, box_rows} box and 128-byte swizzle
+CUtensorMap make_tmap_bf16(const void* base, long long rows, long long cols, int box_rows);
+
+template <int BN>
+void launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Args& a, int ctas, int n_tiles, cudaStream_t s);
+
+void set_attributes();   // cudaFuncSetAttribute for every instantiation (call once, outside graph capture)
+
+}  // namespace tc
+}  // namespace b2a
