@@ -117,7 +117,7 @@ def weight_bytes(cfg) -> int:
 
 
 def kv_bytes(cfg, batch, ctx) -> int:
-    return 2 * batch * cfg["num_key_value_heads"] * ctx * cfg["head_dim"] * 2 * cfg["num_hidden_layers"]
+    return 2 * batch * cfg["num_key_value_heads"] * ctx * cfg["head_dim"] * 4 * cfg["num_hidden_layers"]   # fp32 K and V
 
 
 # ------------------------------------------------------------------------------------------------- CPU legs
@@ -333,8 +333,8 @@ def main():
                 "h2d_bytes_per_step": int(ids_host.numel() * 4), "d2h_bytes_per_step": int(wave_host.numel() * 4 + toks_host.numel() * 4)},
         "gpu_launches": int(launches),
         "stages_s": {"prefill": infos[-1].prefill_time, "decode": infos[-1].generate_time, "codec": infos[-1].codec_time},
-        "roofline": {"kernel": "decode step (CUDA graph: 28 x [rmsnorm, qkv gemv, attention, o gemv, rmsnorm, gate/up gemv+swiglu, "
-                               "down gemv] + lm-head gemv + sampler)", "bound": "hbm", "achieved": achieved, "peak": peak,
+        "roofline": {"kernel": "decode step (CUDA graph: 28 x [rmsnorm, qkv tcgen05 gemm, flash-decode attention, o gemm, rmsnorm, "
+                               "gate/up gemm+swiglu, down gemm] + lm-head gemm + sampler); dominant kernel tc_gemm_kernel<16>", "bound": "hbm", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_step": alg_bytes, "ms_per_decode_step": step_ms, "context": ctx},
         "clocks": clocks,

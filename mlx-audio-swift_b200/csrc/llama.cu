@@ -13,8 +13,10 @@
 // bookkeeping) is captured in one CUDA graph and replayed per token; nothing syncs with the
 // host inside the loop except a poll of the "all rows finished" flag every few steps.
 #include "common.cuh"
+#include "tc_gemm.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <chrono>
 #include <cmath>
 
@@ -47,58 +49,88 @@ __device__ __forceinline__ float warp_sum(float v) {
 // embed + RMSNorm
 // ------------------------------------------------------------------------------------------------
 // x[b,:] = embed[token[b]]  (fp32 residual stream)
+// also clears y[b,:] (the fp32 GEMM accumulation target) so a step never sees a previous step's leftovers
 __global__ void embed_kernel(const int* __restrict__ tokens, const bf16* __restrict__ embed, float* __restrict__ x,
-                             int H, int V) {
+                             float* __restrict__ y, int H, int V) {
     const int b = blockIdx.x;
     int tok = tokens[b];
     tok = min(max(tok, 0), V - 1);
-    for (int i = threadIdx.x; i < H; i += blockDim.x) x[(long long)b * H + i] = __bfloat162float(embed[(long long)tok * H + i]);
+    for (int i = threadIdx.x; i < H; i += blockDim.x) {
+        x[(long long)b * H + i] = __bfloat162float(embed[(long long)tok * H + i]);
+        y[(long long)b * H + i] = 0.f;
+    }
 }
 
-// x += delta (optional);  xn = bf16( x * rsqrt(mean(x^2) + eps) * w )
-__global__ void __launch_bounds__(256)
+constexpr int LO_ROW = 8;   // activation matrices are [16, K] bf16: row b = hi(x_b), row 8 + b = lo(x_b) = bf16(x_b - hi)
+
+__device__ __forceinline__ void store_hilo(bf16* base, long long ld, int b, long long i, float v) {
+    const bf16 hi = __float2bfloat16_rn(v);
+    base[(long long)b * ld + i] = hi;
+    base[(long long)(LO_ROW + b) * ld + i] = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// x += delta (optional, delta is zeroed afterwards);  xn = hi/lo split of  x * rsqrt(mean(x^2) + eps) * w
+// One 1024-thread CTA per row, the row lives in registers (H <= 8192).  Also zeroes `zero_ptr[b, :zero_n]`
+// (the fp32 q|k|v row, so the next stream-K GEMM can accumulate into it with red.add).
+constexpr int RN_THREADS = 1024, RN_MAXV = 8;
+__global__ void __launch_bounds__(RN_THREADS)
 add_rmsnorm_kernel(float* __restrict__ x, float* __restrict__ delta, const float* __restrict__ w,
-                   bf16* __restrict__ xn, int H, float eps, float* __restrict__ trace) {
-    __shared__ float red[8];
-    const int b = blockIdx.x;
+                   bf16* __restrict__ xn, int H, float eps, float* __restrict__ trace, float* __restrict__ zero_ptr,
+                   int zero_n) {
+    __shared__ float red[RN_THREADS / 32];
+    const int b = blockIdx.x, tid = threadIdx.x;
     float* xr = x + (long long)b * H;
+    float v[RN_MAXV];
     float ss = 0.f;
-    for (int i = threadIdx.x; i < H; i += 256) {
-        float v = xr[i];
-        if (delta) { v += delta[(long long)b * H + i]; xr[i] = v; delta[(long long)b * H + i] = 0.f; }
-        if (trace) trace[(long long)b * H + i] = v;
-        ss += v * v;
+#pragma unroll
+    for (int j = 0; j < RN_MAXV; ++j) {
+        const int i = tid + j * RN_THREADS;
+        float val = 0.f;
+        if (i < H) {
+            val = xr[i];
+            if (delta) { val += delta[(long long)b * H + i]; xr[i] = val; delta[(long long)b * H + i] = 0.f; }
+            if (trace) trace[(long long)b * H + i] = val;
+        }
+        v[j] = val;
+        ss += val * val;
     }
     ss = warp_sum(ss);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    if ((tid & 31) == 0) red[tid >> 5] = ss;
     __syncthreads();
     float tot = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) tot += red[i];
+    for (int i = 0; i < RN_THREADS / 32; ++i) tot += red[i];
     const float r = rsqrtf(tot / (float)H + eps);
-    for (int i = threadIdx.x; i < H; i += 256) xn[(long long)b * H + i] = __float2bfloat16_rn(xr[i] * r * w[i]);
+#pragma unroll
+    for (int j = 0; j < RN_MAXV; ++j) {
+        const int i = tid + j * RN_THREADS;
+        if (i < H) store_hilo(xn, H, b, i, v[j] * r * w[i]);
+    }
+    if (zero_ptr)
+        for (int i = tid; i < zero_n; i += RN_THREADS) zero_ptr[(long long)b * zero_n + i] = 0.f;
 }
 
 // ------------------------------------------------------------------------------------------------
 // Weight-streaming GEMV: y[b, n] = sum_k W[n,k] * x[b,k],  NB rows of x in shared memory (bf16),
 // each warp owns ROWS consecutive weight rows and streams them with 16-byte no-allocate loads.
 // ------------------------------------------------------------------------------------------------
-constexpr int GV_MAX_THREADS = 512;
+constexpr int GV_MAX_THREADS = 256;
 enum : int { GV_F32 = 0, GV_SWIGLU = 1, GV_F32_ATOMIC = 2 };
 
-// grid = (row tiles, K splits).  blockDim.x = 32 * warps.  With gridDim.y == 2 (GV_F32_ATOMIC) the two
-// K halves are combined with atomicAdd into a zeroed y: a + b is commutative, so the result does not
-// depend on arrival order.
+// SIMT fallback (B2A_GEMM=simt, or K not a multiple of 64): same numerics as the tcgen05 path -- the
+// activation matrix holds hi rows [0, NB) and lo rows [8, 8 + NB); both halves are accumulated and summed.
+// grid = (row tiles, K splits); with gridDim.y == 2 the two K halves are combined by atomicAdd into a zeroed y.
 template <int NB, int ROWS, int EPI>
 __global__ void __launch_bounds__(GV_MAX_THREADS)
 gemv_bf16_kernel(const bf16* __restrict__ W, const bf16* __restrict__ xin, float* __restrict__ y,
                  bf16* __restrict__ act, int N, int K) {
-    extern __shared__ uint4 sx[];  // [NB][Kc/8]
+    extern __shared__ uint4 sx[];  // [2*NB][Kc/8]
     const int K8 = K >> 3;
     const int Kc8 = K8 / gridDim.y, kbase = blockIdx.y * Kc8;
-    for (int i = threadIdx.x; i < NB * Kc8; i += blockDim.x) {
-        const int b = i / Kc8, k = i - b * Kc8;
-        sx[i] = reinterpret_cast<const uint4*>(xin)[(long long)b * K8 + kbase + k];
+    for (int i = threadIdx.x; i < 2 * NB * Kc8; i += blockDim.x) {
+        const int r = i / Kc8, k = i - r * Kc8;
+        const int grow = r < NB ? r : LO_ROW + (r - NB);
+        sx[i] = reinterpret_cast<const uint4*>(xin)[(long long)grow * K8 + kbase + k];
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -109,25 +141,22 @@ gemv_bf16_kernel(const bf16* __restrict__ W, const bf16* __restrict__ xin, float
     for (int r = 0; r < ROWS; ++r)
         Wr[r] = reinterpret_cast<const uint4*>(W) + (long long)min(row0 + r, N - 1) * K8 + kbase;
 
-    float acc[ROWS][NB];
+    float acc[ROWS][2 * NB];
 #pragma unroll
     for (int r = 0; r < ROWS; ++r)
 #pragma unroll
-        for (int b = 0; b < NB; ++b) acc[r][b] = 0.f;
+        for (int b = 0; b < 2 * NB; ++b) acc[r][b] = 0.f;
 
-#pragma unroll 2
     for (int k8 = lane; k8 < Kc8; k8 += 32) {
-        uint4 wv[ROWS];
-#pragma unroll
-        for (int r = 0; r < ROWS; ++r) wv[r] = ldg_stream(Wr[r] + k8);
         float wf[ROWS][8];
 #pragma unroll
         for (int r = 0; r < ROWS; ++r) {
-            wf[r][0] = bf_lo(wv[r].x); wf[r][1] = bf_hi(wv[r].x); wf[r][2] = bf_lo(wv[r].y); wf[r][3] = bf_hi(wv[r].y);
-            wf[r][4] = bf_lo(wv[r].z); wf[r][5] = bf_hi(wv[r].z); wf[r][6] = bf_lo(wv[r].w); wf[r][7] = bf_hi(wv[r].w);
+            const uint4 wv = ldg_stream(Wr[r] + k8);
+            wf[r][0] = bf_lo(wv.x); wf[r][1] = bf_hi(wv.x); wf[r][2] = bf_lo(wv.y); wf[r][3] = bf_hi(wv.y);
+            wf[r][4] = bf_lo(wv.z); wf[r][5] = bf_hi(wv.z); wf[r][6] = bf_lo(wv.w); wf[r][7] = bf_hi(wv.w);
         }
 #pragma unroll
-        for (int b = 0; b < NB; ++b) {
+        for (int b = 0; b < 2 * NB; ++b) {
             const uint4 xv = sx[b * Kc8 + k8];
             const float xf[8] = {bf_lo(xv.x), bf_hi(xv.x), bf_lo(xv.y), bf_hi(xv.y),
                                  bf_lo(xv.z), bf_hi(xv.z), bf_lo(xv.w), bf_hi(xv.w)};
@@ -140,110 +169,143 @@ gemv_bf16_kernel(const bf16* __restrict__ W, const bf16* __restrict__ xin, float
 #pragma unroll
     for (int r = 0; r < ROWS; ++r)
 #pragma unroll
-        for (int b = 0; b < NB; ++b) acc[r][b] = warp_sum(acc[r][b]);
+        for (int b = 0; b < NB; ++b) acc[r][b] = warp_sum(acc[r][b] + acc[r][NB + b]);
     if (lane == 0) {
-        if (EPI == GV_F32) {
+        if (EPI == GV_F32 || EPI == GV_F32_ATOMIC) {
 #pragma unroll
             for (int r = 0; r < ROWS; ++r)
                 if (row0 + r < N)
 #pragma unroll
-                    for (int b = 0; b < NB; ++b) y[(long long)b * N + row0 + r] = acc[r][b];
-        } else if (EPI == GV_F32_ATOMIC) {
-#pragma unroll
-            for (int r = 0; r < ROWS; ++r)
-                if (row0 + r < N)
-#pragma unroll
-                    for (int b = 0; b < NB; ++b) atomicAdd(&y[(long long)b * N + row0 + r], acc[r][b]);
-        } else {  // rows are (gate, up) pairs: act[b, n/2] = bf16(silu(gate) * up)   (LlamaTTS.swift:282-284)
+                    for (int b = 0; b < NB; ++b) {
+                        if (EPI == GV_F32) y[(long long)b * N + row0 + r] = acc[r][b];
+                        else atomicAdd(&y[(long long)b * N + row0 + r], acc[r][b]);
+                    }
+        } else {  // rows are (gate, up) pairs: act[b, n/2] = silu(gate) * up   (LlamaTTS.swift:282-284)
 #pragma unroll
             for (int r = 0; r < ROWS; r += 2)
                 if (row0 + r + 1 < N)
 #pragma unroll
                     for (int b = 0; b < NB; ++b) {
                         const float g = acc[r][b], u = acc[r + 1][b];
-                        act[(long long)b * (N / 2) + (row0 + r) / 2] = __float2bfloat16_rn(g / (1.0f + __expf(-g)) * u);
+                        store_hilo(act, N / 2, b, (row0 + r) / 2, g / (1.0f + __expf(-g)) * u);
                     }
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Decode attention for one (kv head, row): RoPE on q/k, append k/v to the cache, softmax(qK^T)V
-// over positions 0..pos.  G = q heads per kv head.  (LlamaTTS.swift:235-266)
+// Decode attention (LlamaTTS.swift:235-266): RoPE on q/k, append k/v to the fp32 cache, softmax(qK^T)V.
+// grid = (kv heads, rows, key splits): split s owns keys [s*AT_CAP, (s+1)*AT_CAP); its K and V rows are
+// one contiguous block of the cache each, fetched with a single cp.async.bulk per matrix into shared memory
+// (one HBM round trip), the partial (max, sum, out) goes to a workspace and the last CTA of a (row, head)
+// to finish merges the partials (flash-decoding).
 // ------------------------------------------------------------------------------------------------
-constexpr int HD = 128, AT_THREADS = 256, MAXG = 8, AT_SLICES = AT_THREADS / 64;
+constexpr int HD = 128, AT_THREADS = 256, MAXG = 8, AT_CAP = 144;
 
+struct AttnArgs {
+    const float* qkv;      // [B, (nq + 2 nkv) * 128] fp32
+    const int* pos;        // [B]
+    const float* freqs;    // [64] llama3 rope divisors
+    float* kcache;         // this layer: [B][nkv][max_ctx][128] fp32
+    float* vcache;
+    bf16* out;             // [16, nq*128] hi/lo
+    float* part_o;         // [B][nkv][S][G][128]
+    float* part_ml;        // [B][nkv][S][G][2]
+    int* counters;         // [B][nkv], zero between launches
+    int nq, nkv, max_ctx, S;
+    float scale;
+};
+
+template <int G>
 __global__ void __launch_bounds__(AT_THREADS)
-attn_decode_kernel(const float* __restrict__ qkv, const int* __restrict__ pos_arr, const float* __restrict__ freqs,
-                   bf16* __restrict__ kcache, bf16* __restrict__ vcache, bf16* __restrict__ out, int nq, int nkv,
-                   int max_ctx, float scale) {
-    extern __shared__ float sm[];  // q [G][HD] | scores [G][max_ctx] | partial out [AT_SLICES][G][HD]
-    const int G = nq / nkv;
-    float* sq = sm;
-    float* sc = sm + G * HD;
-    float* po = sc + G * max_ctx;
+attn_decode_kernel(AttnArgs a) {
+    extern __shared__ __align__(16) uint8_t at_smem[];
+    float* sK = reinterpret_cast<float*>(at_smem);              // [AT_CAP][128]
+    float* sV = sK + AT_CAP * HD;                               // [AT_CAP][128]
+    float* sq = sV + AT_CAP * HD;                               // [G][128]
+    float* sc = sq + G * HD;                                    // [G][AT_CAP]
+    float* spo = sc + G * AT_CAP;                               // [2][G][128]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(spo + 2 * G * HD);
     __shared__ float red[AT_THREADS / 32][MAXG];
     __shared__ float stat[2][MAXG];
+    __shared__ int s_last;
 
-    const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
-    const int p = pos_arr[b];
-    if (p < 0 || p >= max_ctx) return;
-    const int qkv_ld = (nq + 2 * nkv) * HD;
-    const float* row = qkv + (long long)b * qkv_ld;
-    bf16* kc = kcache + (((long long)b * nkv + h) * max_ctx) * HD;
-    bf16* vc = vcache + (((long long)b * nkv + h) * max_ctx) * HD;
+    const int h = blockIdx.x, b = blockIdx.y, s = blockIdx.z, tid = threadIdx.x;
+    const int p = a.pos[b];
+    if (p < 0 || p >= a.max_ctx) return;
+    const int S_eff = p / AT_CAP + 1;
+    if (s >= S_eff) return;
+    const int t0 = s * AT_CAP, t1 = min(t0 + AT_CAP, p + 1), nk = t1 - t0;
+    const bool has_new = (s == S_eff - 1);                      // this split owns the new position p
+    const int n_load = has_new ? nk - 1 : nk;
+    const int qkv_ld = (a.nq + 2 * a.nkv) * HD;
+    const float* row = a.qkv + (long long)b * qkv_ld;
+    float* kc = a.kcache + (((long long)b * a.nkv + h) * a.max_ctx) * HD;
+    float* vc = a.vcache + (((long long)b * a.nkv + h) * a.max_ctx) * HD;
 
+    if (tid == 0) {
+        tc::mbar_init(bar, 1);
+        tc::fence_barrier_init();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (n_load > 0) {
+            const uint32_t bytes = (uint32_t)n_load * HD * 4;
+            tc::mbar_arrive_expect_tx(bar, 2 * bytes);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(tc::smem_u32(sK)), "l"(kc + (long long)t0 * HD), "r"(bytes), "r"(tc::smem_u32(bar)) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(tc::smem_u32(sV)), "l"(vc + (long long)t0 * HD), "r"(bytes), "r"(tc::smem_u32(bar)) : "memory");
+        } else {
+            tc::mbar_arrive(bar);
+        }
+    }
     if (tid < HD / 2) {  // MLXFast.RoPE(traditional:false, freqs:): angle = pos / freqs[i], pairs (i, i+64)
         const int d = tid;
-        float s, c;
-        sincosf((float)p / freqs[d], &s, &c);
-        for (int g = 0; g < G; ++g) {
+        float sn, cs;
+        sincosf((float)p / a.freqs[d], &sn, &cs);
+        _Pragma("unroll") for (int g = 0; g < G; ++g) {
             const float* q = row + (h * G + g) * HD;
             const float x1 = q[d], x2 = q[d + HD / 2];
-            sq[g * HD + d] = bf16_round(x1 * c - x2 * s);
-            sq[g * HD + d + HD / 2] = bf16_round(x2 * c + x1 * s);
+            sq[g * HD + d] = x1 * cs - x2 * sn;
+            sq[g * HD + d + HD / 2] = x2 * cs + x1 * sn;
         }
-        const float* k = row + (nq + h) * HD;
-        const float x1 = k[d], x2 = k[d + HD / 2];
-        kc[(long long)p * HD + d] = __float2bfloat16_rn(x1 * c - x2 * s);
-        kc[(long long)p * HD + d + HD / 2] = __float2bfloat16_rn(x2 * c + x1 * s);
-    } else if (tid >= 128) {
+        if (has_new) {
+            const float* k = row + (a.nq + h) * HD;
+            const float x1 = k[d], x2 = k[d + HD / 2];
+            const float k1 = x1 * cs - x2 * sn, k2 = x2 * cs + x1 * sn;
+            kc[(long long)p * HD + d] = k1;
+            kc[(long long)p * HD + d + HD / 2] = k2;
+            sK[(p - t0) * HD + d] = k1;
+            sK[(p - t0) * HD + d + HD / 2] = k2;
+        }
+    } else if (tid >= 128 && has_new) {
         const int d = tid - 128;
-        vc[(long long)p * HD + d] = __float2bfloat16_rn(row[(nq + nkv + h) * HD + d]);
+        const float v = row[(a.nq + a.nkv + h) * HD + d];
+        vc[(long long)p * HD + d] = v;
+        sV[(p - t0) * HD + d] = v;
     }
-    __syncthreads();
+    __syncthreads();            // barrier init + q / new-row staging visible
+    tc::mbar_wait(bar, 0);      // bulk-copied K and V have landed
 
-    // scores: one key per thread, the whole 256-byte key row fetched with 16 independent 16-byte loads
-    float lmax[MAXG];
-    for (int g = 0; g < G; ++g) lmax[g] = -INFINITY;
-    for (int t = tid; t <= p; t += AT_THREADS) {
-        const uint4* kr = reinterpret_cast<const uint4*>(kc + (long long)t * HD);
-        uint4 kv[HD / 8];
-#pragma unroll
-        for (int c8 = 0; c8 < HD / 8; ++c8) kv[c8] = kr[c8];
-        float acc[MAXG];
-        for (int g = 0; g < G; ++g) acc[g] = 0.f;
-#pragma unroll
-        for (int c8 = 0; c8 < HD / 8; ++c8) {
-            const float kf[8] = {bf_lo(kv[c8].x), bf_hi(kv[c8].x), bf_lo(kv[c8].y), bf_hi(kv[c8].y),
-                                 bf_lo(kv[c8].z), bf_hi(kv[c8].z), bf_lo(kv[c8].w), bf_hi(kv[c8].w)};
-            for (int g = 0; g < G; ++g) {
-                const float4 q0 = *reinterpret_cast<const float4*>(sq + g * HD + c8 * 8);
-                const float4 q1 = *reinterpret_cast<const float4*>(sq + g * HD + c8 * 8 + 4);
-                acc[g] = fmaf(q0.x, kf[0], acc[g]); acc[g] = fmaf(q0.y, kf[1], acc[g]);
-                acc[g] = fmaf(q0.z, kf[2], acc[g]); acc[g] = fmaf(q0.w, kf[3], acc[g]);
-                acc[g] = fmaf(q1.x, kf[4], acc[g]); acc[g] = fmaf(q1.y, kf[5], acc[g]);
-                acc[g] = fmaf(q1.z, kf[6], acc[g]); acc[g] = fmaf(q1.w, kf[7], acc[g]);
+    // scores: one key per thread; the float4 column index is rotated by the thread id so that the 32 lanes of
+    // a warp hit 32 different bank groups (rows are 512 B apart)
+    float sacc[G];
+    _Pragma("unroll") for (int g = 0; g < G; ++g) sacc[g] = 0.f;
+    if (tid < nk) {
+        const float4* kr = reinterpret_cast<const float4*>(sK + tid * HD);
+#pragma unroll 4
+        for (int i = 0; i < HD / 4; ++i) {
+            const int d4 = (i + tid) & (HD / 4 - 1);
+            const float4 kf = kr[d4];
+            _Pragma("unroll") for (int g = 0; g < G; ++g) {
+                const float4 qf = reinterpret_cast<const float4*>(sq + g * HD)[d4];
+                sacc[g] = fmaf(qf.x, kf.x, sacc[g]); sacc[g] = fmaf(qf.y, kf.y, sacc[g]);
+                sacc[g] = fmaf(qf.z, kf.z, sacc[g]); sacc[g] = fmaf(qf.w, kf.w, sacc[g]);
             }
         }
-        for (int g = 0; g < G; ++g) {
-            const float s = acc[g] * scale;
-            sc[g * max_ctx + t] = s;
-            lmax[g] = fmaxf(lmax[g], s);
-        }
     }
-    for (int g = 0; g < G; ++g) {
-        float m = lmax[g];
+    _Pragma("unroll") for (int g = 0; g < G; ++g) {
+        float m = tid < nk ? sacc[g] * a.scale : -INFINITY;
+        sacc[g] = m;
         for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
         if ((tid & 31) == 0) red[tid >> 5][g] = m;
     }
@@ -254,66 +316,58 @@ attn_decode_kernel(const float* __restrict__ qkv, const int* __restrict__ pos_ar
         stat[0][tid] = m;
     }
     __syncthreads();
-    float lsum[MAXG];
-    for (int g = 0; g < G; ++g) lsum[g] = 0.f;
-    for (int t = tid; t <= p; t += AT_THREADS)
-        for (int g = 0; g < G; ++g) {
-            const float e = __expf(sc[g * max_ctx + t] - stat[0][g]);
-            sc[g * max_ctx + t] = e;
-            lsum[g] += e;
-        }
-    __syncthreads();
-    for (int g = 0; g < G; ++g) {
-        const float s = warp_sum(lsum[g]);
-        if ((tid & 31) == 0) red[tid >> 5][g] = s;
+    _Pragma("unroll") for (int g = 0; g < G; ++g) {
+        const float e = tid < nk ? __expf(sacc[g] - stat[0][g]) : 0.f;
+        if (tid < nk) sc[g * AT_CAP + tid] = e;
+        const float sum = warp_sum(e);
+        if ((tid & 31) == 0) red[tid >> 5][g] = sum;
     }
     __syncthreads();
     if (tid < G) {
-        float s = 0.f;
-        for (int i = 0; i < AT_THREADS / 32; ++i) s += red[i][tid];
-        stat[1][tid] = s;
+        float sum = 0.f;
+        for (int i = 0; i < AT_THREADS / 32; ++i) sum += red[i][tid];
+        stat[1][tid] = sum;
     }
-    // PV: thread = (t-slice, dim pair); 8 independent bf16x2 loads in flight per thread
-    const int sl = tid >> 6, dp = tid & 63;
-    float o0[MAXG], o1[MAXG];
-    for (int g = 0; g < G; ++g) { o0[g] = 0.f; o1[g] = 0.f; }
-    const unsigned* vrow = reinterpret_cast<const unsigned*>(vc) + dp;
-    int t = sl;
-    for (; t + 7 * AT_SLICES <= p; t += 8 * AT_SLICES) {
-        unsigned v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = vrow[(long long)(t + j * AT_SLICES) * (HD / 2)];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float va = bf_lo(v[j]), vb = bf_hi(v[j]);
-            for (int g = 0; g < G; ++g) {
-                const float pr = sc[g * max_ctx + t + j * AT_SLICES];
-                o0[g] = fmaf(pr, va, o0[g]);
-                o1[g] = fmaf(pr, vb, o1[g]);
-            }
-        }
+    // PV: thread = (key parity, dim); consecutive lanes read consecutive floats of a V row (conflict-free)
+    const int half = tid >> 7, d = tid & 127;
+    float o[G];
+    _Pragma("unroll") for (int g = 0; g < G; ++g) o[g] = 0.f;
+    for (int t = half; t < nk; t += 2) {
+        const float v = sV[t * HD + d];
+        _Pragma("unroll") for (int g = 0; g < G; ++g) o[g] = fmaf(sc[g * AT_CAP + t], v, o[g]);
     }
-    for (; t <= p; t += AT_SLICES) {
-        const unsigned v = vrow[(long long)t * (HD / 2)];
-        const float va = bf_lo(v), vb = bf_hi(v);
-        for (int g = 0; g < G; ++g) {
-            const float pr = sc[g * max_ctx + t];
-            o0[g] = fmaf(pr, va, o0[g]);
-            o1[g] = fmaf(pr, vb, o1[g]);
-        }
-    }
-    for (int g = 0; g < G; ++g) {
-        po[(sl * G + g) * HD + 2 * dp] = o0[g];
-        po[(sl * G + g) * HD + 2 * dp + 1] = o1[g];
-    }
+    _Pragma("unroll") for (int g = 0; g < G; ++g) spo[(half * G + g) * HD + d] = o[g];
     __syncthreads();
+    const long long pbase = (((long long)b * a.nkv + h) * a.S + s) * G;
     if (tid < HD)
-        for (int g = 0; g < G; ++g) {
-            float o = 0.f;
-#pragma unroll
-            for (int s2 = 0; s2 < AT_SLICES; ++s2) o += po[(s2 * G + g) * HD + tid];
-            out[(long long)b * nq * HD + (h * G + g) * HD + tid] = __float2bfloat16_rn(o / stat[1][g]);
+        _Pragma("unroll") for (int g = 0; g < G; ++g)
+            a.part_o[(pbase + g) * HD + tid] = spo[g * HD + tid] + spo[(G + g) * HD + tid];
+    if (tid < G) {
+        a.part_ml[(pbase + tid) * 2] = stat[0][tid];
+        a.part_ml[(pbase + tid) * 2 + 1] = stat[1][tid];
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(&a.counters[b * a.nkv + h], 1) == S_eff - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // merge the S_eff partials
+    if (tid < HD) {
+        const long long mbase = (((long long)b * a.nkv + h) * a.S) * G;
+        _Pragma("unroll") for (int g = 0; g < G; ++g) {
+            float M = -INFINITY;
+            for (int j = 0; j < S_eff; ++j) M = fmaxf(M, a.part_ml[(mbase + (long long)j * G + g) * 2]);
+            float L = 0.f, O = 0.f;
+            for (int j = 0; j < S_eff; ++j) {
+                const float wj = __expf(a.part_ml[(mbase + (long long)j * G + g) * 2] - M);
+                L = fmaf(a.part_ml[(mbase + (long long)j * G + g) * 2 + 1], wj, L);
+                O = fmaf(a.part_o[(mbase + (long long)j * G + g) * HD + tid], wj, O);
+            }
+            store_hilo(a.out, (long long)a.nq * HD, b, (h * G + g) * HD + tid, O / L);
         }
+    }
+    if (tid == 0) a.counters[b * a.nkv + h] = 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -594,10 +648,19 @@ struct b2a_tts {
     DBuf<bf16> embed, lm_head_w;
     const bf16* lm_head = nullptr;
     DBuf<float> final_ln, freqs;
-    DBuf<bf16> kcache, vcache;   // [layer][B][nkv][ctx][hd]
-    // activations
+    DBuf<float> kcache, vcache;   // [layer][B][nkv][ctx][hd] fp32
+    // activations: fp32 residual stream; GEMM inputs as [16, K] bf16 hi/lo pairs
     DBuf<float> x, y, qkv, logits, probs;
     DBuf<bf16> xn, attn, act;
+    // attention workspace (flash-decoding partials)
+    DBuf<float> part_o, part_ml;
+    DBuf<int> at_counters;
+    int at_splits = 1;
+    // tcgen05 / TMA path
+    bool use_tc = true;
+    int num_sms = 148;
+    std::vector<CUtensorMap> tm_qkv, tm_o, tm_gu, tm_down;
+    CUtensorMap tm_lm{}, tmx_xn{}, tmx_attn{}, tmx_act{};
     DBuf<int> tokens, pos, recent, recent_n, out_tokens, n_gen, done, n_active, ids, forced;
     HBuf<int> h_flag;
     std::atomic<int> cancel{0};
@@ -627,17 +690,38 @@ struct b2a_tts {
         B2A_CUDA(cudaMemcpy(dst.p + offset_elems, t.data, expect * sizeof(bf16), cudaMemcpyHostToDevice));
     }
 
+    template <int G>
+    static void attn_attr() {
+        B2A_CUDA(cudaFuncSetAttribute(attn_decode_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    }
+    void attn_launch(const AttnArgs& aa, int B, cudaStream_t s) {
+        const dim3 grid(aa.nkv, B, aa.S);
+        const size_t sm = attn_smem_bytes();
+        switch (aa.nq / aa.nkv) {
+            case 1: attn_decode_kernel<1><<<grid, AT_THREADS, sm, s>>>(aa); break;
+            case 2: attn_decode_kernel<2><<<grid, AT_THREADS, sm, s>>>(aa); break;
+            case 3: attn_decode_kernel<3><<<grid, AT_THREADS, sm, s>>>(aa); break;
+            case 4: attn_decode_kernel<4><<<grid, AT_THREADS, sm, s>>>(aa); break;
+            case 6: attn_decode_kernel<6><<<grid, AT_THREADS, sm, s>>>(aa); break;
+            default: attn_decode_kernel<8><<<grid, AT_THREADS, sm, s>>>(aa); break;
+        }
+        count_launch();
+    }
     size_t attn_smem_bytes() const {
         const int G = cfg.num_attention_heads / cfg.num_key_value_heads;
-        return (size_t)(G * HD + G * cfg.max_context + AT_SLICES * G * HD) * sizeof(float);
+        return (size_t)(2 * AT_CAP * HD + G * HD + G * AT_CAP + 2 * G * HD) * sizeof(float) + 16;
     }
 
     void check_config() {
         const b2a_llama_config& c = cfg;
         B2A_CHECK(c.head_dim == HD, B2A_ERR_INVALID_INPUT, "llama: head_dim must be 128");
         B2A_CHECK(c.hidden_size % 8 == 0 && c.intermediate_size % 8 == 0, B2A_ERR_INVALID_INPUT, "llama: sizes must be multiples of 8");
-        B2A_CHECK(c.num_attention_heads % c.num_key_value_heads == 0 && c.num_attention_heads / c.num_key_value_heads <= MAXG,
-                  B2A_ERR_INVALID_INPUT, "llama: unsupported GQA ratio");
+        {
+            const int g = c.num_key_value_heads > 0 && c.num_attention_heads % c.num_key_value_heads == 0
+                              ? c.num_attention_heads / c.num_key_value_heads : 0;
+            B2A_CHECK(g == 1 || g == 2 || g == 3 || g == 4 || g == 6 || g == 8, B2A_ERR_INVALID_INPUT,
+                      "llama: unsupported GQA ratio (q heads per kv head must be 1, 2, 3, 4, 6 or 8)");
+        }
         B2A_CHECK(c.max_batch >= 1 && c.max_batch <= 8, B2A_ERR_INVALID_INPUT, "llama: max_batch must be in 1..8");
         B2A_CHECK(c.max_context >= 8, B2A_ERR_INVALID_INPUT, "llama: max_context too small");
         require_device(device);
@@ -648,18 +732,21 @@ struct b2a_tts {
         const b2a_llama_config& c = cfg;
         const int H = c.hidden_size, I = c.intermediate_size, nq = c.num_attention_heads, nkv = c.num_key_value_heads;
         const int NQ = nq * HD, NKV = nkv * HD;
+        B2A_CHECK(H <= RN_THREADS * RN_MAXV, B2A_ERR_INVALID_INPUT, "llama: hidden_size above 8192 is not supported");
         std::vector<float> fr = llama3_freqs(c);
         freqs.upload(fr.data(), fr.size());
         const size_t kv = (size_t)c.num_hidden_layers * c.max_batch * nkv * c.max_context * HD;
         kcache.alloc(kv);
         vcache.alloc(kv);
-        const int B = 8;
+        B2A_CUDA(cudaMemset(kcache.p, 0, kv * sizeof(float)));
+        B2A_CUDA(cudaMemset(vcache.p, 0, kv * sizeof(float)));
+        const int B = 8, R16 = 16;
         x.alloc((size_t)B * H); y.alloc((size_t)B * H); qkv.alloc((size_t)B * (NQ + 2 * NKV));
         logits.alloc((size_t)B * c.vocab_size); probs.alloc((size_t)B * c.vocab_size);
-        xn.alloc((size_t)B * H); attn.alloc((size_t)B * NQ); act.alloc((size_t)B * I);
-        B2A_CUDA(cudaMemset(xn.p, 0, (size_t)B * H * sizeof(bf16)));
-        B2A_CUDA(cudaMemset(attn.p, 0, (size_t)B * NQ * sizeof(bf16)));
-        B2A_CUDA(cudaMemset(act.p, 0, (size_t)B * I * sizeof(bf16)));
+        xn.alloc((size_t)R16 * H); attn.alloc((size_t)R16 * NQ); act.alloc((size_t)R16 * I);
+        B2A_CUDA(cudaMemset(xn.p, 0, (size_t)R16 * H * sizeof(bf16)));
+        B2A_CUDA(cudaMemset(attn.p, 0, (size_t)R16 * NQ * sizeof(bf16)));
+        B2A_CUDA(cudaMemset(act.p, 0, (size_t)R16 * I * sizeof(bf16)));
         B2A_CUDA(cudaMemset(x.p, 0, (size_t)B * H * sizeof(float)));
         B2A_CUDA(cudaMemset(y.p, 0, (size_t)B * H * sizeof(float)));
         B2A_CUDA(cudaMemset(qkv.p, 0, (size_t)B * (NQ + 2 * NKV) * sizeof(float)));
@@ -668,10 +755,34 @@ struct b2a_tts {
         B2A_CUDA(cudaMemset(tokens.p, 0, B * sizeof(int)));
         B2A_CUDA(cudaMemset(pos.p, 0, B * sizeof(int)));
         h_flag.alloc(16);
+        // attention workspace
+        const int G = nq / nkv;
+        at_splits = cdiv(c.max_context, AT_CAP);
+        part_o.alloc((size_t)B * nkv * at_splits * G * HD);
+        part_ml.alloc((size_t)B * nkv * at_splits * G * 2);
+        at_counters.alloc((size_t)B * nkv);
+        B2A_CUDA(cudaMemset(at_counters.p, 0, (size_t)B * nkv * sizeof(int)));
+        // process-wide kernel attributes: always the same (largest) value, several handles may coexist
         gemv_attrs<1>(); gemv_attrs<2>(); gemv_attrs<4>(); gemv_attrs<8>();
-        B2A_CHECK(attn_smem_bytes() <= 200 * 1024, B2A_ERR_INVALID_INPUT, "llama: max_context too large for the attention score tile");
-        // process-wide kernel attribute: always the same (largest) value, several handles may coexist
-        B2A_CUDA(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        B2A_CHECK(attn_smem_bytes() <= 220 * 1024, B2A_ERR_INVALID_INPUT, "llama: GQA ratio too large for the attention tile");
+        attn_attr<1>(); attn_attr<2>(); attn_attr<3>(); attn_attr<4>(); attn_attr<6>(); attn_attr<8>();
+        B2A_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
+        // tcgen05 / TMA path: needs every GEMM K to be a multiple of 64; B2A_GEMM=simt forces the SIMT fallback
+        const char* env = getenv("B2A_GEMM");
+        use_tc = !(env && std::string(env) == "simt") && H % tc::BK == 0 && NQ % tc::BK == 0 && I % tc::BK == 0;
+        if (use_tc) {
+            tc::set_attributes();
+            for (auto& L : layers) {
+                tm_qkv.push_back(tc::make_tmap_bf16(L.wqkv.p, NQ + 2 * NKV, H, tc::BM));
+                tm_o.push_back(tc::make_tmap_bf16(L.wo.p, H, NQ, tc::BM));
+                tm_gu.push_back(tc::make_tmap_bf16(L.wgu.p, 2 * I, H, tc::BM));
+                tm_down.push_back(tc::make_tmap_bf16(L.wdown.p, H, I, tc::BM));
+            }
+            tm_lm = tc::make_tmap_bf16(lm_head, c.vocab_size, H, tc::BM);
+            tmx_xn = tc::make_tmap_bf16(xn.p, R16, H, 16);
+            tmx_attn = tc::make_tmap_bf16(attn.p, R16, NQ, 16);
+            tmx_act = tc::make_tmap_bf16(act.p, R16, I, 16);
+        }
         B2A_CUDA(cudaDeviceSynchronize());
     }
 
@@ -752,36 +863,36 @@ struct b2a_tts {
     template <int NB, int ROWS, int EPI>
     void gemv_launch(const bf16* W, const bf16* xin, float* yout, bf16* actout, int N, int K, int warps, int ksplit,
                      cudaStream_t s) {
-        const size_t sm = (size_t)NB * (K / ksplit) * sizeof(bf16);
+        const size_t sm = (size_t)2 * NB * (K / ksplit) * sizeof(bf16);
         dim3 grid(cdiv(N, warps * ROWS), ksplit);
         gemv_bf16_kernel<NB, ROWS, EPI><<<grid, warps * 32, sm, s>>>(W, xin, yout, actout, N, K);
         count_launch();
     }
     template <int NB, int ROWS, int EPI>
     static void gemv_attr() {
-        B2A_CUDA(cudaFuncSetAttribute(gemv_bf16_kernel<NB, ROWS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        B2A_CUDA(cudaFuncSetAttribute(gemv_bf16_kernel<NB, ROWS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     }
     template <int NB>
     static void gemv_attrs() {
-        gemv_attr<NB, 2, GV_F32>(); gemv_attr<NB, 4, GV_F32>(); gemv_attr<NB, 4, GV_SWIGLU>(); gemv_attr<NB, 2, GV_F32_ATOMIC>();
+        gemv_attr<NB, 2, GV_F32>(); gemv_attr<NB, 2, GV_SWIGLU>(); gemv_attr<NB, 2, GV_F32_ATOMIC>();
     }
     enum { OP_QKV, OP_O, OP_GU, OP_DOWN, OP_LM };
     template <int NB>
     void gemv_op(int op, const bf16* W, const bf16* xin, float* yout, bf16* actout, int N, int K, cudaStream_t s) {
+        const bool split = (K / 8) % 2 == 0 && (size_t)2 * NB * K * sizeof(bf16) > 96 * 1024;
         switch (op) {
-            case OP_QKV: gemv_launch<NB, 2, GV_F32>(W, xin, yout, actout, N, K, 8, 1, s); break;
-            case OP_O: gemv_launch<NB, 2, GV_F32>(W, xin, yout, actout, N, K, 4, 1, s); break;
-            case OP_GU: gemv_launch<NB, 4, GV_SWIGLU>(W, xin, yout, actout, N, K, 8, 1, s); break;
+            case OP_GU: gemv_launch<NB, 2, GV_SWIGLU>(W, xin, yout, actout, N, K, 8, 1, s); break;
             case OP_DOWN:
-                if ((K / 8) % 2 == 0) gemv_launch<NB, 2, GV_F32_ATOMIC>(W, xin, yout, actout, N, K, 4, 2, s);
+            case OP_O:
+                if (split) gemv_launch<NB, 2, GV_F32_ATOMIC>(W, xin, yout, actout, N, K, 4, 2, s);
                 else gemv_launch<NB, 2, GV_F32>(W, xin, yout, actout, N, K, 4, 1, s);
                 break;
-            default: gemv_launch<NB, 4, GV_F32>(W, xin, yout, actout, N, K, 8, 1, s); break;
+            default: gemv_launch<NB, 2, GV_F32>(W, xin, yout, actout, N, K, 8, 1, s); break;
         }
     }
     void gemv_nb(int op, const bf16* W, const bf16* xin, float* yout, bf16* actout, int N, int K, cudaStream_t s) {
-        B2A_CHECK((size_t)nb_pad * K * sizeof(bf16) <= 160 * 1024 * (op == OP_DOWN ? 2 : 1), B2A_ERR_INVALID_INPUT,
-                  "llama: layer too wide for the shared-memory activation tile");
+        B2A_CHECK((size_t)2 * nb_pad * K * sizeof(bf16) <= 200 * 1024 * ((op == OP_DOWN || op == OP_O) ? 2 : 1),
+                  B2A_ERR_INVALID_INPUT, "llama: layer too wide for the shared-memory activation tile");
         switch (nb_pad) {
             case 1: gemv_op<1>(op, W, xin, yout, actout, N, K, s); break;
             case 2: gemv_op<2>(op, W, xin, yout, actout, N, K, s); break;
@@ -790,40 +901,91 @@ struct b2a_tts {
         }
     }
 
-    // embed(tokens) -> all layers; leaves the residual stream in x and the last MLP output in y
-    void run_layers(int B, cudaStream_t s) {
-        const int H = cfg.hidden_size, I = cfg.intermediate_size, nq = cfg.num_attention_heads, nkv = cfg.num_key_value_heads;
-        const int NQ = nq * HD, NKV = nkv * HD, G = nq / nkv;
-        embed_kernel<<<B, 256, 0, s>>>(tokens.p, embed.p, x.p, H, cfg.vocab_size);
-        count_launch();
-        const size_t kv_layer = (size_t)cfg.max_batch * nkv * cfg.max_context * HD;
-        const size_t at_sm = attn_smem_bytes();
-        for (int l = 0; l < cfg.num_hidden_layers; ++l) {
-            LayerW& L = layers[l];
-            add_rmsnorm_kernel<<<B, 256, 0, s>>>(x.p, l == 0 ? nullptr : y.p, L.ln1.p, xn.p, H, cfg.rms_norm_eps,
-                                                 trace_on ? trace.p + (size_t)(2 * l) * 8 * H : nullptr);
-            count_launch();
-            gemv_nb(OP_QKV, L.wqkv.p, xn.p, qkv.p, nullptr, NQ + 2 * NKV, H, s);
-            attn_decode_kernel<<<dim3(nkv, B), AT_THREADS, at_sm, s>>>(qkv.p, pos.p, freqs.p, kcache.p + l * kv_layer,
-                                                                       vcache.p + l * kv_layer, attn.p, nq, nkv, cfg.max_context,
-                                                                       1.0f / sqrtf((float)HD));
-            count_launch();
-            gemv_nb(OP_O, L.wo.p, attn.p, y.p, nullptr, H, NQ, s);
-            add_rmsnorm_kernel<<<B, 256, 0, s>>>(x.p, y.p, L.ln2.p, xn.p, H, cfg.rms_norm_eps,
-                                                 trace_on ? trace.p + (size_t)(2 * l + 1) * 8 * H : nullptr);
-            count_launch();
-            gemv_nb(OP_GU, L.wgu.p, xn.p, nullptr, act.p, 2 * I, H, s);
-            gemv_nb(OP_DOWN, L.wdown.p, act.p, y.p, nullptr, H, I, s);
+    // D[tokens, M] = X[tokens, K] * W[M, K]^T on the tcgen05 path (hi/lo activations, BN = 16)
+    void tc_gemm(const CUtensorMap& tmW, const CUtensorMap& tmX, int op, float* yout, bf16* actout, int B, int M, int K,
+                 cudaStream_t s) {
+        tc::Args a{};
+        a.out_f32 = yout; a.out_bf16 = actout; a.M = M; a.N = B; a.K = K;
+        a.m_tiles = cdiv(M, tc::BM); a.k_blocks = K / tc::BK;
+        a.stages = tc::Smem<16>::max_stages();
+        a.hilo = 1;
+        int ctas = num_sms;
+        if (op == OP_GU) {
+            a.ldo = M / 2; a.epi_full = tc::EPI_SWIGLU; a.epi_partial = -1; a.lo_rows = LO_ROW;
+            ctas = std::min(num_sms, a.m_tiles);
+        } else if (op == OP_LM) {
+            a.ldo = M; a.epi_full = tc::EPI_STORE; a.epi_partial = -1; a.lo_rows = 0;
+            ctas = std::min(num_sms, a.m_tiles);
+        } else {   // qkv / o / down: stream-K, partial tiles accumulate into the zeroed fp32 output
+            a.ldo = M; a.epi_full = tc::EPI_STORE; a.epi_partial = tc::EPI_ATOMIC; a.lo_rows = 0;
+            ctas = (int)std::min<long long>(num_sms, (long long)a.m_tiles * a.k_blocks);
+        }
+        tc::launch<16>(tmW, tmX, a, ctas, 1, s);
+    }
+
+    void gemm(int op, int layer, int B, cudaStream_t s) {
+        const int H = cfg.hidden_size, I = cfg.intermediate_size, NQ = cfg.num_attention_heads * HD,
+                  NKV = cfg.num_key_value_heads * HD;
+        LayerW* L = layer >= 0 ? &layers[layer] : nullptr;
+        switch (op) {
+            case OP_QKV:
+                if (use_tc) tc_gemm(tm_qkv[layer], tmx_xn, op, qkv.p, nullptr, B, NQ + 2 * NKV, H, s);
+                else gemv_nb(op, L->wqkv.p, xn.p, qkv.p, nullptr, NQ + 2 * NKV, H, s);
+                break;
+            case OP_O:
+                if (use_tc) tc_gemm(tm_o[layer], tmx_attn, op, y.p, nullptr, B, H, NQ, s);
+                else gemv_nb(op, L->wo.p, attn.p, y.p, nullptr, H, NQ, s);
+                break;
+            case OP_GU:
+                if (use_tc) tc_gemm(tm_gu[layer], tmx_xn, op, nullptr, act.p, B, 2 * I, H, s);
+                else gemv_nb(op, L->wgu.p, xn.p, nullptr, act.p, 2 * I, H, s);
+                break;
+            case OP_DOWN:
+                if (use_tc) tc_gemm(tm_down[layer], tmx_act, op, y.p, nullptr, B, H, I, s);
+                else gemv_nb(op, L->wdown.p, act.p, y.p, nullptr, H, I, s);
+                break;
+            default:
+                if (use_tc) tc_gemm(tm_lm, tmx_xn, op, logits.p, nullptr, B, cfg.vocab_size, H, s);
+                else gemv_nb(op, lm_head, xn.p, logits.p, nullptr, cfg.vocab_size, H, s);
+                break;
         }
     }
 
-    void run_lm_head(int B, cudaStream_t s) {
-        add_rmsnorm_kernel<<<B, 256, 0, s>>>(x.p, y.p, final_ln.p, xn.p, cfg.hidden_size, cfg.rms_norm_eps,
-                                             trace_on ? trace.p + (size_t)(2 * cfg.num_hidden_layers) * 8 * cfg.hidden_size : nullptr);
+    // embed(tokens) -> all layers; leaves the residual stream in x and the last MLP output in y
+    void run_layers(int B, cudaStream_t s) {
+        const int H = cfg.hidden_size, nq = cfg.num_attention_heads, nkv = cfg.num_key_value_heads;
+        const int QKV_N = (nq + 2 * nkv) * HD, G = nq / nkv;
+        embed_kernel<<<B, 256, 0, s>>>(tokens.p, embed.p, x.p, y.p, H, cfg.vocab_size);
         count_launch();
-        gemv_nb(OP_LM, lm_head, xn.p, logits.p, nullptr, cfg.vocab_size, cfg.hidden_size, s);
+        const size_t kv_layer = (size_t)cfg.max_batch * nkv * cfg.max_context * HD;
+        for (int l = 0; l < cfg.num_hidden_layers; ++l) {
+            LayerW& L = layers[l];
+            add_rmsnorm_kernel<<<B, RN_THREADS, 0, s>>>(x.p, l == 0 ? nullptr : y.p, L.ln1.p, xn.p, H, cfg.rms_norm_eps,
+                                                        trace_on ? trace.p + (size_t)(2 * l) * 8 * H : nullptr, nullptr, 0);
+            count_launch();
+            gemm(OP_QKV, l, B, s);
+            AttnArgs aa{qkv.p, pos.p, freqs.p, kcache.p + l * kv_layer, vcache.p + l * kv_layer, attn.p, part_o.p, part_ml.p,
+                        at_counters.p, nq, nkv, cfg.max_context, at_splits, 1.0f / sqrtf((float)HD)};
+            attn_launch(aa, B, s);
+            gemm(OP_O, l, B, s);
+            // also zeroes this row of q|k|v so the next layer's stream-K QKV GEMM can accumulate into it
+            add_rmsnorm_kernel<<<B, RN_THREADS, 0, s>>>(x.p, y.p, L.ln2.p, xn.p, H, cfg.rms_norm_eps,
+                                                        trace_on ? trace.p + (size_t)(2 * l + 1) * 8 * H : nullptr, qkv.p, QKV_N);
+            count_launch();
+            gemm(OP_GU, l, B, s);
+            gemm(OP_DOWN, l, B, s);
+        }
+        (void)G;
     }
-    // NOTE: gemv writes y[b*N + n] with N = vocab: logits are [nb_pad, V] row-major.
+
+    void run_lm_head(int B, cudaStream_t s) {
+        add_rmsnorm_kernel<<<B, RN_THREADS, 0, s>>>(x.p, y.p, final_ln.p, xn.p, cfg.hidden_size, cfg.rms_norm_eps,
+                                                    trace_on ? trace.p + (size_t)(2 * cfg.num_hidden_layers) * 8 * cfg.hidden_size : nullptr,
+                                                    nullptr, 0);
+        count_launch();
+        gemm(OP_LM, -1, B, s);
+    }
+    // logits are [8, V] row-major.
 
     void set_batch(int B) {
         nb_pad = B <= 1 ? 1 : B <= 2 ? 2 : B <= 4 ? 4 : 8;

@@ -64,9 +64,9 @@ def llama_tiny():
                             num_key_value_heads=1, head_dim=128, vocab_size=2048)
     W = llama.init_weights(cfg, 1234, std=0.08)
     ids = np.random.default_rng(3).integers(0, 2048, size=(2, 12))
-    mo = llama.LlamaOracle(cfg, W, round_acts=True)
+    mo = llama.LlamaOracle(cfg, W, round_acts=False)
     lg = mo.forward(torch.as_tensor(ids)).numpy()
-    gen = llama.generate_tokens(llama.LlamaOracle(cfg, W, True), ids, max_tokens=24, temperature=0.0,
+    gen = llama.generate_tokens(llama.LlamaOracle(cfg, W, False), ids, max_tokens=24, temperature=0.0,
                                 rep_penalty=1.3, rep_context=20)
     np.savez_compressed(OUT / "llama_tiny.npz", ids=ids, logits_last=lg[:, -1].astype(np.float32),
                         logits_stats=stats(lg), greedy=np.asarray(gen, dtype=np.int32),

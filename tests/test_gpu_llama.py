@@ -1,6 +1,8 @@
-"""CUDA Llama/Orpheus step (through the C ABI) vs the oracle: logits (1e-3 relative L2 against the oracle
-with identical bf16 rounding points), greedy tokens bit-exact, logits processors / sampler semantics,
-end-to-end tokens -> codes -> waveform."""
+"""CUDA Llama/Orpheus step (through the C ABI) vs the oracle: logits within 1e-3 relative L2 of the fp32-activation
+oracle on the same bf16 weights (the device path carries activations as bf16 hi/lo pairs and an fp32 KV cache, so it
+tracks that value to ~1e-5), greedy tokens bit-exact, logits processors / sampler semantics, end-to-end
+tokens -> codes -> waveform.  The oracle's round_acts=True mode (bf16 activations, what MLX itself does) is reported
+for scale: it sits ~1e-2 away from both."""
 import numpy as np
 import pytest
 import torch
@@ -36,12 +38,13 @@ def test_logits_vs_oracle_and_golden(tiny):
     g = np.load(GOLDEN / "llama_tiny.npz")
     ids = g["ids"]
     lg = m(ids)
-    ref = ol.LlamaOracle(cfg, W, round_acts=True).forward(torch.as_tensor(ids)).numpy()
-    ideal = ol.LlamaOracle(cfg, W, round_acts=False).forward(torch.as_tensor(ids)).numpy()
+    ref = ol.LlamaOracle(cfg, W, round_acts=False).forward(torch.as_tensor(ids)).numpy()
+    bf16_style = ol.LlamaOracle(cfg, W, round_acts=True).forward(torch.as_tensor(ids)).numpy()
     assert lg.shape == ref.shape == (2, 12, 2048)
     assert rel_err(lg, ref) < TOL, rel_err(lg, ref)
+    assert rel_err(lg, ref) < 1e-4, rel_err(lg, ref)          # what the hi/lo + fp32-KV path actually achieves
     assert rel_err(lg[:, -1], g["logits_last"]) < TOL
-    assert rel_err(lg, ideal) < 2e-2            # distance to the pure-fp32 value (bf16 activation rounding)
+    assert rel_err(bf16_style, ref) > 10 * rel_err(lg, ref)   # a bf16-activation pipeline (MLX) is far noisier
     assert np.array_equal(lg.argmax(-1), ref.argmax(-1))
 
 
@@ -69,7 +72,7 @@ def test_greedy_tokens_bit_exact(tiny):
     # no penalty variant against a live oracle run
     toks2, _, _ = m.generate_batch(ids, P(max_tokens=16, temperature=0.0, top_p=1.0, repetition_penalty=1.0,
                                           repetition_context_size=0), decode_audio=False)
-    ref = ol.generate_tokens(ol.LlamaOracle(cfg, W, True), ids, 16, temperature=0.0, rep_penalty=1.0, rep_context=0)
+    ref = ol.generate_tokens(ol.LlamaOracle(cfg, W, False), ids, 16, temperature=0.0, rep_penalty=1.0, rep_context=0)
     assert toks2 == ref
 
 
@@ -77,7 +80,7 @@ def test_top_p_sampler_stays_in_nucleus_and_matches_distribution(tiny):
     cfg, W, m = tiny
     ids = np.random.default_rng(5).integers(0, 2048, size=(1, 8)).astype(np.int32)
     P = type(m.default_generation_parameters)
-    logits = ol.LlamaOracle(cfg, W, True).forward(torch.as_tensor(ids)).numpy()[0, -1]
+    logits = ol.LlamaOracle(cfg, W, False).forward(torch.as_tensor(ids)).numpy()[0, -1]
     temp, top_p = 0.6, 0.8
     proc = ol.repetition_penalty(logits, ids[0].tolist()[-20:], 1.3)
     kept = ol.top_p_filter(proc, temp, top_p)
@@ -122,7 +125,7 @@ def test_end_to_end_tokens_to_waveform_and_errors(b2a):
     toks, waves, info = m.generate_batch(ids, P(max_tokens=30, temperature=0.0, top_p=1.0, repetition_penalty=1.3,
                                                 repetition_context_size=20, mask_eos=True, wrap_codes=True),
                                          on_token=lambda b, s, t: events.append((b, s, t)))
-    ref = ol.generate_tokens(ol.LlamaOracle(cfg, W, True), ids, 30, temperature=0.0, rep_penalty=1.3, rep_context=20,
+    ref = ol.generate_tokens(ol.LlamaOracle(cfg, W, False), ids, 30, temperature=0.0, rep_penalty=1.3, rep_context=20,
                              mask_eos=True)
     assert toks == ref                                             # greedy tokens bit-exact at the real vocab size
     assert [e[2] for e in events if e[0] == 0] == toks[0]          # .token events in order
@@ -149,3 +152,30 @@ def test_end_to_end_tokens_to_waveform_and_errors(b2a):
     # with an empty generation the prompt itself is parsed (reference behaviour); just check it terminates
     toks3, _, info3 = m.generate_batch(ids, P(max_tokens=5, temperature=0.0), decode_audio=False)
     assert all(len(t) <= 5 for t in toks3)
+
+
+def test_simt_fallback_matches_tcgen05_path(b2a, tiny, monkeypatch):
+    """B2A_GEMM=simt selects the CUDA-core GEMV fallback (same hi/lo numerics): both paths agree to fp32 noise."""
+    cfg, W, m = tiny
+    ids = np.random.default_rng(17).integers(0, 2048, size=(3, 9)).astype(np.int32)
+    a = m(ids)
+    monkeypatch.setenv("B2A_GEMM", "simt")
+    m2 = b2a.LlamaTTSModel(hf_config(cfg), W, max_batch=4, max_context=64)
+    monkeypatch.delenv("B2A_GEMM")
+    b = m2(ids)
+    assert rel_err(b, a) < 1e-5
+    ref = ol.LlamaOracle(cfg, W, round_acts=False).forward(torch.as_tensor(ids)).numpy()
+    assert rel_err(b, ref) < 1e-4
+
+
+def test_long_context_attention_splits(b2a):
+    """Context beyond one 144-key attention split (flash-decoding merge) against the oracle."""
+    cfg = ol.LlamaConfig(hidden_size=128, num_hidden_layers=1, intermediate_size=256, num_attention_heads=3,
+                         num_key_value_heads=1, head_dim=128, vocab_size=512)
+    W = ol.init_weights(cfg, 5, std=0.1)
+    m = b2a.LlamaTTSModel(hf_config(cfg), W, max_batch=2, max_context=400)
+    ids = np.random.default_rng(1).integers(0, 512, size=(2, 330)).astype(np.int32)
+    lg = m(ids)
+    ref = ol.LlamaOracle(cfg, W, round_acts=False).forward(torch.as_tensor(ids)).numpy()
+    for pos in (0, 143, 144, 145, 287, 288, 329):
+        assert rel_err(lg[:, pos], ref[:, pos]) < 1e-4, pos

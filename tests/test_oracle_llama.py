@@ -91,5 +91,5 @@ def test_goldens():
     cfg = llama.LlamaConfig(hidden_size=256, num_hidden_layers=2, intermediate_size=512, num_attention_heads=2,
                             num_key_value_heads=1, head_dim=128, vocab_size=2048)
     W = llama.init_weights(cfg, 1234, std=0.08)
-    lg = llama.LlamaOracle(cfg, W, True).forward(torch.as_tensor(g["ids"])).numpy()
+    lg = llama.LlamaOracle(cfg, W, False).forward(torch.as_tensor(g["ids"])).numpy()
     assert rel_err(lg[:, -1], g["logits_last"]) < 1e-5
