@@ -1,12 +1,23 @@
 // Library-wide state of libb200audio: error text, launch counter, device check.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace b2a {
 
 static thread_local std::string t_last_error;
 std::atomic<long long> g_launches{0};
 
 void set_last_error(const std::string& msg) { t_last_error = msg; }
+
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("B2A_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
 
 void require_device(int device) {
     int n = 0;

@@ -10,6 +10,7 @@
 #include <map>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/b200audio.h"
@@ -141,5 +142,29 @@ struct TensorTable {
 };
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// Programmatic dependent launch (PDL): every kernel of the decode step is launched with
+// programmaticStreamSerializationAllowed so that its prologue (barrier init, TMEM allocation, and -- for the
+// GEMMs -- the TMA prefetch of the first ring-full of WEIGHTS, which never depend on the previous kernel) overlaps
+// with the tail of the kernel before it.  Device side: pdl_trigger() lets the next kernel start launching,
+// pdl_wait() blocks until the previous kernel has completed and its writes are visible.  B2A_PDL=0 disables it.
+bool pdl_enabled();
+
+template <class... KArgs, class... Args>
+static inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    B2A_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...));
+    count_launch();
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 
 }  // namespace b2a

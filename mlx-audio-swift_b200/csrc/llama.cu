@@ -53,6 +53,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 __global__ void embed_kernel(const int* __restrict__ tokens, const bf16* __restrict__ embed, float* __restrict__ x,
                              float* __restrict__ y, int H, int V) {
     const int b = blockIdx.x;
+    pdl_trigger();
+    pdl_wait();
     int tok = tokens[b];
     tok = min(max(tok, 0), V - 1);
     for (int i = threadIdx.x; i < H; i += blockDim.x) {
@@ -79,6 +81,8 @@ add_rmsnorm_kernel(float* __restrict__ x, float* __restrict__ delta, const float
                    int zero_n) {
     __shared__ float red[RN_THREADS / 32];
     const int b = blockIdx.x, tid = threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
     float* xr = x + (long long)b * H;
     float v[RN_MAXV];
     float ss = 0.f;
@@ -125,6 +129,8 @@ __global__ void __launch_bounds__(GV_MAX_THREADS)
 gemv_bf16_kernel(const bf16* __restrict__ W, const bf16* __restrict__ xin, float* __restrict__ y,
                  bf16* __restrict__ act, int N, int K) {
     extern __shared__ uint4 sx[];  // [2*NB][Kc/8]
+    pdl_trigger();
+    pdl_wait();
     const int K8 = K >> 3;
     const int Kc8 = K8 / gridDim.y, kbase = blockIdx.y * Kc8;
     for (int i = threadIdx.x; i < 2 * NB * Kc8; i += blockDim.x) {
@@ -200,7 +206,7 @@ gemv_bf16_kernel(const bf16* __restrict__ W, const bf16* __restrict__ xin, float
 // (one HBM round trip), the partial (max, sum, out) goes to a workspace and the last CTA of a (row, head)
 // to finish merges the partials (flash-decoding).
 // ------------------------------------------------------------------------------------------------
-constexpr int HD = 128, AT_THREADS = 256, MAXG = 8, AT_CAP = 144;
+constexpr int HD = 128, AT_THREADS = 256, MAXG = 8, AT_CAP = 64;   // AT_CAP * 4 == AT_THREADS
 
 struct AttnArgs {
     const float* qkv;      // [B, (nq + 2 nkv) * 128] fp32
@@ -231,6 +237,8 @@ attn_decode_kernel(AttnArgs a) {
     __shared__ int s_last;
 
     const int h = blockIdx.x, b = blockIdx.y, s = blockIdx.z, tid = threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
     const int p = a.pos[b];
     if (p < 0 || p >= a.max_ctx) return;
     const int S_eff = p / AT_CAP + 1;
@@ -286,15 +294,16 @@ attn_decode_kernel(AttnArgs a) {
     __syncthreads();            // barrier init + q / new-row staging visible
     tc::mbar_wait(bar, 0);      // bulk-copied K and V have landed
 
-    // scores: one key per thread; the float4 column index is rotated by the thread id so that the 32 lanes of
-    // a warp hit 32 different bank groups (rows are 512 B apart)
+    // scores: 4 threads per key (32 dims each); float4 columns are interleaved across the 4 threads and rotated by
+    // the key index so every quarter-warp touches 8 distinct 16-byte bank groups (rows are 512 B apart)
     float sacc[G];
     _Pragma("unroll") for (int g = 0; g < G; ++g) sacc[g] = 0.f;
-    if (tid < nk) {
-        const float4* kr = reinterpret_cast<const float4*>(sK + tid * HD);
-#pragma unroll 4
-        for (int i = 0; i < HD / 4; ++i) {
-            const int d4 = (i + tid) & (HD / 4 - 1);
+    const int key = tid >> 2, part = tid & 3;
+    if (key < nk) {
+        const float4* kr = reinterpret_cast<const float4*>(sK + key * HD);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int d4 = part + 4 * ((j + key) & 7);
             const float4 kf = kr[d4];
             _Pragma("unroll") for (int g = 0; g < G; ++g) {
                 const float4 qf = reinterpret_cast<const float4*>(sq + g * HD)[d4];
@@ -304,7 +313,10 @@ attn_decode_kernel(AttnArgs a) {
         }
     }
     _Pragma("unroll") for (int g = 0; g < G; ++g) {
-        float m = tid < nk ? sacc[g] * a.scale : -INFINITY;
+        float v = sacc[g];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        float m = key < nk ? v * a.scale : -INFINITY;
         sacc[g] = m;
         for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
         if ((tid & 31) == 0) red[tid >> 5][g] = m;
@@ -317,8 +329,8 @@ attn_decode_kernel(AttnArgs a) {
     }
     __syncthreads();
     _Pragma("unroll") for (int g = 0; g < G; ++g) {
-        const float e = tid < nk ? __expf(sacc[g] - stat[0][g]) : 0.f;
-        if (tid < nk) sc[g * AT_CAP + tid] = e;
+        const float e = (key < nk && part == 0) ? __expf(sacc[g] - stat[0][g]) : 0.f;
+        if (key < nk && part == 0) sc[g * AT_CAP + key] = e;
         const float sum = warp_sum(e);
         if ((tid & 31) == 0) red[tid >> 5][g] = sum;
     }
@@ -428,6 +440,8 @@ sample_kernel(SampleArgs a) {
     __shared__ float s_val[SM_WARPS];
     __shared__ int s_idx[SM_WARPS];
     const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    pdl_trigger();
+    pdl_wait();
     float* lg = a.logits + (long long)b * a.V;
     float* pr = a.probs + (long long)b * a.V;
     const int nrec = min(a.recent_n[b], a.R);
@@ -567,6 +581,8 @@ sample_kernel(SampleArgs a) {
 // prefill bookkeeping for positions that do not need logits: next token = ids[b, pos+1]
 __global__ void prefill_advance_kernel(const int* __restrict__ ids, int L, int* tokens, int* pos, int B) {
     const int b = threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
     if (b >= B) return;
     const int p = pos[b] + 1;
     pos[b] = p;
@@ -698,14 +714,13 @@ struct b2a_tts {
         const dim3 grid(aa.nkv, B, aa.S);
         const size_t sm = attn_smem_bytes();
         switch (aa.nq / aa.nkv) {
-            case 1: attn_decode_kernel<1><<<grid, AT_THREADS, sm, s>>>(aa); break;
-            case 2: attn_decode_kernel<2><<<grid, AT_THREADS, sm, s>>>(aa); break;
-            case 3: attn_decode_kernel<3><<<grid, AT_THREADS, sm, s>>>(aa); break;
-            case 4: attn_decode_kernel<4><<<grid, AT_THREADS, sm, s>>>(aa); break;
-            case 6: attn_decode_kernel<6><<<grid, AT_THREADS, sm, s>>>(aa); break;
-            default: attn_decode_kernel<8><<<grid, AT_THREADS, sm, s>>>(aa); break;
+            case 1: launch_pdl(attn_decode_kernel<1>, grid, dim3(AT_THREADS), sm, s, aa); break;
+            case 2: launch_pdl(attn_decode_kernel<2>, grid, dim3(AT_THREADS), sm, s, aa); break;
+            case 3: launch_pdl(attn_decode_kernel<3>, grid, dim3(AT_THREADS), sm, s, aa); break;
+            case 4: launch_pdl(attn_decode_kernel<4>, grid, dim3(AT_THREADS), sm, s, aa); break;
+            case 6: launch_pdl(attn_decode_kernel<6>, grid, dim3(AT_THREADS), sm, s, aa); break;
+            default: launch_pdl(attn_decode_kernel<8>, grid, dim3(AT_THREADS), sm, s, aa); break;
         }
-        count_launch();
     }
     size_t attn_smem_bytes() const {
         const int G = cfg.num_attention_heads / cfg.num_key_value_heads;
@@ -865,8 +880,7 @@ struct b2a_tts {
                      cudaStream_t s) {
         const size_t sm = (size_t)2 * NB * (K / ksplit) * sizeof(bf16);
         dim3 grid(cdiv(N, warps * ROWS), ksplit);
-        gemv_bf16_kernel<NB, ROWS, EPI><<<grid, warps * 32, sm, s>>>(W, xin, yout, actout, N, K);
-        count_launch();
+        launch_pdl(gemv_bf16_kernel<NB, ROWS, EPI>, grid, dim3(warps * 32), sm, s, W, xin, yout, actout, N, K);
     }
     template <int NB, int ROWS, int EPI>
     static void gemv_attr() {
@@ -907,7 +921,7 @@ struct b2a_tts {
         tc::Args a{};
         a.out_f32 = yout; a.out_bf16 = actout; a.M = M; a.N = B; a.K = K;
         a.m_tiles = cdiv(M, tc::BM); a.k_blocks = K / tc::BK;
-        a.stages = tc::Smem<16>::max_stages();
+        a.stages = 6;   // 6 x 18 KB ring: two GEMM CTAs (this kernel's and the next kernel's prefetching one) fit per SM
         a.hilo = 1;
         int ctas = num_sms;
         if (op == OP_GU) {
@@ -955,23 +969,20 @@ struct b2a_tts {
     void run_layers(int B, cudaStream_t s) {
         const int H = cfg.hidden_size, nq = cfg.num_attention_heads, nkv = cfg.num_key_value_heads;
         const int QKV_N = (nq + 2 * nkv) * HD, G = nq / nkv;
-        embed_kernel<<<B, 256, 0, s>>>(tokens.p, embed.p, x.p, y.p, H, cfg.vocab_size);
-        count_launch();
+        launch_pdl(embed_kernel, dim3(B), dim3(256), 0, s, tokens.p, embed.p, x.p, y.p, H, cfg.vocab_size);
         const size_t kv_layer = (size_t)cfg.max_batch * nkv * cfg.max_context * HD;
         for (int l = 0; l < cfg.num_hidden_layers; ++l) {
             LayerW& L = layers[l];
-            add_rmsnorm_kernel<<<B, RN_THREADS, 0, s>>>(x.p, l == 0 ? nullptr : y.p, L.ln1.p, xn.p, H, cfg.rms_norm_eps,
-                                                        trace_on ? trace.p + (size_t)(2 * l) * 8 * H : nullptr, nullptr, 0);
-            count_launch();
+            launch_pdl(add_rmsnorm_kernel, dim3(B), dim3(RN_THREADS), 0, s, x.p, l == 0 ? (float*)nullptr : y.p, L.ln1.p, xn.p, H,
+                       cfg.rms_norm_eps, trace_on ? trace.p + (size_t)(2 * l) * 8 * H : (float*)nullptr, (float*)nullptr, 0);
             gemm(OP_QKV, l, B, s);
             AttnArgs aa{qkv.p, pos.p, freqs.p, kcache.p + l * kv_layer, vcache.p + l * kv_layer, attn.p, part_o.p, part_ml.p,
                         at_counters.p, nq, nkv, cfg.max_context, at_splits, 1.0f / sqrtf((float)HD)};
             attn_launch(aa, B, s);
             gemm(OP_O, l, B, s);
             // also zeroes this row of q|k|v so the next layer's stream-K QKV GEMM can accumulate into it
-            add_rmsnorm_kernel<<<B, RN_THREADS, 0, s>>>(x.p, y.p, L.ln2.p, xn.p, H, cfg.rms_norm_eps,
-                                                        trace_on ? trace.p + (size_t)(2 * l + 1) * 8 * H : nullptr, qkv.p, QKV_N);
-            count_launch();
+            launch_pdl(add_rmsnorm_kernel, dim3(B), dim3(RN_THREADS), 0, s, x.p, y.p, L.ln2.p, xn.p, H, cfg.rms_norm_eps,
+                       trace_on ? trace.p + (size_t)(2 * l + 1) * 8 * H : (float*)nullptr, qkv.p, QKV_N);
             gemm(OP_GU, l, B, s);
             gemm(OP_DOWN, l, B, s);
         }
@@ -979,10 +990,8 @@ struct b2a_tts {
     }
 
     void run_lm_head(int B, cudaStream_t s) {
-        add_rmsnorm_kernel<<<B, RN_THREADS, 0, s>>>(x.p, y.p, final_ln.p, xn.p, cfg.hidden_size, cfg.rms_norm_eps,
-                                                    trace_on ? trace.p + (size_t)(2 * cfg.num_hidden_layers) * 8 * cfg.hidden_size : nullptr,
-                                                    nullptr, 0);
-        count_launch();
+        launch_pdl(add_rmsnorm_kernel, dim3(B), dim3(RN_THREADS), 0, s, x.p, y.p, final_ln.p, xn.p, cfg.hidden_size, cfg.rms_norm_eps,
+                   trace_on ? trace.p + (size_t)(2 * cfg.num_hidden_layers) * 8 * cfg.hidden_size : (float*)nullptr, (float*)nullptr, 0);
         gemm(OP_LM, -1, B, s);
     }
     // logits are [8, V] row-major.
@@ -1009,15 +1018,13 @@ struct b2a_tts {
         B2A_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
         run_layers(B, stream);
         run_lm_head(B, stream);
-        sample_kernel<<<B, SM_THREADS, 0, stream>>>(sa);
-        count_launch();
+        launch_pdl(sample_kernel, dim3(B), dim3(SM_THREADS), 0, stream, sa);
         B2A_CUDA(cudaStreamEndCapture(stream, &g));
         B2A_CUDA(cudaGraphInstantiate(&g_step, g, 0));
         cudaGraphDestroy(g);
         B2A_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
         run_layers(B, stream);
-        prefill_advance_kernel<<<1, 32, 0, stream>>>(ids.p, L, tokens.p, pos.p, B);
-        count_launch();
+        launch_pdl(prefill_advance_kernel, dim3(1), dim3(32), 0, stream, ids.p, L, tokens.p, pos.p, B);
         B2A_CUDA(cudaStreamEndCapture(stream, &g));
         B2A_CUDA(cudaGraphInstantiate(&g_prefill, g, 0));
         cudaGraphDestroy(g);

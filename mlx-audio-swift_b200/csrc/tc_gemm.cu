@@ -34,8 +34,7 @@ CUtensorMap make_tmap_bf16(const void* base, long long rows, long long cols, int
 
 template <int BN>
 void launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Args& a, int ctas, int n_tiles, cudaStream_t s) {
-    tc_gemm_kernel<BN><<<dim3(ctas, n_tiles), THREADS, Smem<BN>::bytes(a.stages), s>>>(tmA, tmB, a);
-    count_launch();
+    launch_pdl(tc_gemm_kernel<BN>, dim3(ctas, n_tiles), dim3(THREADS), Smem<BN>::bytes(a.stages), s, tmA, tmB, a);
 }
 template void launch<16>(const CUtensorMap&, const CUtensorMap&, const Args&, int, int, cudaStream_t);
 template void launch<128>(const CUtensorMap&, const CUtensorMap&, const Args&, int, int, cudaStream_t);

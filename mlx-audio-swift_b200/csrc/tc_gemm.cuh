@@ -149,6 +149,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.y * BN;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: let the next kernel's prologue start
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -176,8 +177,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 0) {
         if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (long long u = u0; u < u1; ++u) {
+            // Weights never depend on the previous kernel: fill the whole ring with A tiles right away, then wait
+            // for the previous kernel (PDL) before loading the activation (B) tiles that complete those stages.
+            const int npre = (int)min((long long)a.stages, u1 - u0);
+            for (int i = 0; i < npre; ++i) {
+                const long long u = u0 + i;
+                const int mt = (int)(u / a.k_blocks), kb = (int)(u - (long long)mt * a.k_blocks);
+                mbar_arrive_expect_tx(&full[i], S::STAGE);
+                tma_load_2d(smem + (size_t)i * S::STAGE, &tmA, &full[i], kb * BK, mt * BM);
+            }
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            for (int i = 0; i < npre; ++i) {
+                const long long u = u0 + i;
+                const int mt = (int)(u / a.k_blocks), kb = (int)(u - (long long)mt * a.k_blocks);
+                tma_load_2d(smem + (size_t)i * S::STAGE + S::A_BYTES, &tmB, &full[i], kb * BK, n0);
+            }
+            int stage = npre == a.stages ? 0 : npre;
+            uint32_t phase = npre == a.stages ? 1 : 0;
+            for (long long u = u0 + npre; u < u1; ++u) {
                 const int mt = (int)(u / a.k_blocks), kb = (int)(u - (long long)mt * a.k_blocks);
                 mbar_wait(&empty[stage], phase ^ 1);
                 uint8_t* sa = smem + (size_t)stage * S::STAGE;
