@@ -65,10 +65,13 @@ __global__ void embed_kernel(const int* __restrict__ tokens, const bf16* __restr
 
 constexpr int LO_ROW = 8;   // activation matrices are [16, K] bf16: row b = hi(x_b), row 8 + b = lo(x_b) = bf16(x_b - hi)
 
-__device__ __forceinline__ void store_hilo(bf16* base, long long ld, int b, long long i, float v) {
+// token t of a [tokens, K] activation matrix lives in rows  hi = (t / half) * 2 * half + t % half,  lo = hi + half
+// (half = 8 for the decode step's [16, K] matrices, 64 for the prefill's 128-row TMA tiles)
+__device__ __forceinline__ void store_hilo(bf16* base, long long ld, int t, long long i, float v, int half = LO_ROW) {
     const bf16 hi = __float2bfloat16_rn(v);
-    base[(long long)b * ld + i] = hi;
-    base[(long long)(LO_ROW + b) * ld + i] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    const long long r = (long long)(t / half) * 2 * half + (t % half);
+    base[r * ld + i] = hi;
+    base[(r + half) * ld + i] = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
 
 // x += delta (optional, delta is zeroed afterwards);  xn = hi/lo split of  x * rsqrt(mean(x^2) + eps) * w
@@ -78,7 +81,7 @@ constexpr int RN_THREADS = 1024, RN_MAXV = 8;
 __global__ void __launch_bounds__(RN_THREADS)
 add_rmsnorm_kernel(float* __restrict__ x, float* __restrict__ delta, const float* __restrict__ w,
                    bf16* __restrict__ xn, int H, float eps, float* __restrict__ trace, float* __restrict__ zero_ptr,
-                   int zero_n) {
+                   int zero_n, int half) {
     __shared__ float red[RN_THREADS / 32];
     const int b = blockIdx.x, tid = threadIdx.x;
     pdl_trigger();
@@ -108,7 +111,7 @@ add_rmsnorm_kernel(float* __restrict__ x, float* __restrict__ delta, const float
 #pragma unroll
     for (int j = 0; j < RN_MAXV; ++j) {
         const int i = tid + j * RN_THREADS;
-        if (i < H) store_hilo(xn, H, b, i, v[j] * r * w[i]);
+        if (i < H) store_hilo(xn, H, b, i, v[j] * r * w[i], half);
     }
     if (zero_ptr)
         for (int i = tid; i < zero_n; i += RN_THREADS) zero_ptr[(long long)b * zero_n + i] = 0.f;
@@ -380,6 +383,149 @@ attn_decode_kernel(AttnArgs a) {
         }
     }
     if (tid == 0) a.counters[b * a.nkv + h] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Batched prefill (LlamaTTS.swift:711 `self(inputIds, cache)` on the whole prompt): all B*L prompt tokens go
+// through each layer at once -- GEMMs on the tcgen05 kernel with 128-column tiles (64 tokens as hi/lo pairs),
+// causal attention over the prompt per (row, kv head, 32-query tile), K/V written to the fp32 cache.
+// ------------------------------------------------------------------------------------------------
+constexpr int PF_HALF = 64;      // tokens per 128-row TMA tile
+constexpr int PA_QT = 32, PA_THREADS = 256, PA_MAXL = 128;
+
+__global__ void embed_rows_kernel(const int* __restrict__ ids, const bf16* __restrict__ embed, float* __restrict__ x,
+                                  int H, int V) {
+    const int t = blockIdx.x;
+    int tok = ids[t];
+    tok = min(max(tok, 0), V - 1);
+    for (int i = threadIdx.x; i < H; i += blockDim.x) x[(long long)t * H + i] = __bfloat162float(embed[(long long)tok * H + i]);
+}
+
+// cos/sin of pos / freqs[d] for pos < L (MLXFast.RoPE with custom freqs, LlamaTTS.swift:192-200)
+__global__ void rope_table_kernel(const float* __restrict__ freqs, float2* __restrict__ tab, int L) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L * (HD / 2)) return;
+    const int p = i / (HD / 2), d = i - p * (HD / 2);
+    float s, c;
+    sincosf((float)p / freqs[d], &s, &c);
+    tab[i] = make_float2(c, s);
+}
+
+struct PrefillAttnArgs {
+    const float* qkv;     // [T, (nq + 2 nkv) * 128]
+    const float2* rope;   // [L, 64] (cos, sin)
+    float* kcache;        // this layer [B][nkv][max_ctx][128]
+    float* vcache;
+    bf16* out;            // [2 * T_pad, nq * 128] hi/lo, 64-token tiles
+    int nq, nkv, max_ctx, L;
+    float scale;
+};
+
+template <int G>
+__global__ void __launch_bounds__(PA_THREADS)
+prefill_attn_kernel(PrefillAttnArgs a) {
+    extern __shared__ __align__(16) uint8_t pa_smem[];
+    const int h = blockIdx.x, b = blockIdx.y, q0 = blockIdx.z * PA_QT;
+    const int nqt = min(PA_QT, a.L - q0), kmax = q0 + nqt;     // causal: keys 0 .. q0 + nqt - 1
+    float* sK = reinterpret_cast<float*>(pa_smem);              // [kmax][128]
+    float* sV = sK + (size_t)a.L * HD;                          // [kmax][128]
+    float* sQ = sV + (size_t)a.L * HD;                          // [G][PA_QT][128]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ld = (a.nq + 2 * a.nkv) * HD;
+    const float* base = a.qkv + (long long)b * a.L * ld;
+    float* kc = a.kcache + (((long long)b * a.nkv + h) * a.max_ctx) * HD;
+    float* vc = a.vcache + (((long long)b * a.nkv + h) * a.max_ctx) * HD;
+
+    // K (RoPE) and V of keys [0, kmax) -> shared memory; this tile's own keys also go to the cache
+    for (int i = tid; i < kmax * (HD / 2); i += PA_THREADS) {
+        const int t = i / (HD / 2), d = i - t * (HD / 2);
+        const float2 cs = a.rope[t * (HD / 2) + d];
+        const float* k = base + (long long)t * ld + (a.nq + h) * HD;
+        const float x1 = k[d], x2 = k[d + HD / 2];
+        const float k1 = x1 * cs.x - x2 * cs.y, k2 = x2 * cs.x + x1 * cs.y;
+        sK[t * HD + d] = k1; sK[t * HD + d + HD / 2] = k2;
+        if (t >= q0) { kc[(long long)t * HD + d] = k1; kc[(long long)t * HD + d + HD / 2] = k2; }
+    }
+    for (int i = tid; i < kmax * HD; i += PA_THREADS) {
+        const int t = i / HD, d = i - t * HD;
+        const float v = base[(long long)t * ld + (a.nq + a.nkv + h) * HD + d];
+        sV[i] = v;
+        if (t >= q0) vc[(long long)t * HD + d] = v;
+    }
+    for (int i = tid; i < G * nqt * (HD / 2); i += PA_THREADS) {
+        const int g = i / (nqt * (HD / 2)), r = i - g * nqt * (HD / 2), qi = r / (HD / 2), d = r - qi * (HD / 2);
+        const float2 cs = a.rope[(q0 + qi) * (HD / 2) + d];
+        const float* q = base + (long long)(q0 + qi) * ld + (h * G + g) * HD;
+        const float x1 = q[d], x2 = q[d + HD / 2];
+        sQ[(g * PA_QT + qi) * HD + d] = x1 * cs.x - x2 * cs.y;
+        sQ[(g * PA_QT + qi) * HD + d + HD / 2] = x2 * cs.x + x1 * cs.y;
+    }
+    __syncthreads();
+
+    // one (head, query) row per warp iteration; lanes over keys for the scores, over dims for P*V
+    constexpr int KJ = PA_MAXL / 32;
+    for (int r = warp; r < G * nqt; r += PA_THREADS / 32) {
+        const int g = r / nqt, qi = r - g * nqt, qpos = q0 + qi;
+        const float4* q4 = reinterpret_cast<const float4*>(sQ + (g * PA_QT + qi) * HD);
+        float sc[KJ];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < KJ; ++j) {
+            const int t = j * 32 + lane;
+            float acc = -INFINITY;
+            if (t <= qpos) {
+                const float4* k4 = reinterpret_cast<const float4*>(sK + t * HD);
+                acc = 0.f;
+#pragma unroll 8
+                for (int i = 0; i < HD / 4; ++i) {
+                    const int d4 = (i + lane) & (HD / 4 - 1);     // rotate: conflict-free rows 512 B apart
+                    const float4 kf = k4[d4], qf = q4[d4];
+                    acc = fmaf(qf.x, kf.x, acc); acc = fmaf(qf.y, kf.y, acc);
+                    acc = fmaf(qf.z, kf.z, acc); acc = fmaf(qf.w, kf.w, acc);
+                }
+                acc *= a.scale;
+            }
+            sc[j] = acc;
+            mx = fmaxf(mx, acc);
+        }
+        for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < KJ; ++j) { sc[j] = sc[j] == -INFINITY ? 0.f : __expf(sc[j] - mx); sum += sc[j]; }
+        sum = warp_sum(sum);
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < KJ; ++j) {
+            if (j * 32 > qpos) break;
+            for (int l = 0; l < 32; ++l) {
+                const int t = j * 32 + l;
+                if (t > qpos) break;
+                const float p = __shfl_sync(0xffffffffu, sc[j], l);
+                const float4 v = reinterpret_cast<const float4*>(sV + t * HD)[lane];
+                o.x = fmaf(p, v.x, o.x); o.y = fmaf(p, v.y, o.y); o.z = fmaf(p, v.z, o.z); o.w = fmaf(p, v.w, o.w);
+            }
+        }
+        const float inv = 1.0f / sum;
+        const int tok = b * a.L + qpos;
+        const long long col = (long long)(h * G + g) * HD + lane * 4;
+        const long long ldo = (long long)a.nq * HD;
+        store_hilo(a.out, ldo, tok, col + 0, o.x * inv, PF_HALF);
+        store_hilo(a.out, ldo, tok, col + 1, o.y * inv, PF_HALF);
+        store_hilo(a.out, ldo, tok, col + 2, o.z * inv, PF_HALF);
+        store_hilo(a.out, ldo, tok, col + 3, o.w * inv, PF_HALF);
+    }
+}
+
+// decode buffers <- last prompt position of every row:  x[b] = xp[b*L + L-1], y[b] = yp[...], pos[b] = L - 1
+__global__ void gather_last_kernel(const float* __restrict__ xp, const float* __restrict__ yp, float* __restrict__ x,
+                                   float* __restrict__ y, int* __restrict__ pos, int L, int H) {
+    const int b = blockIdx.x;
+    const long long src = ((long long)b * L + L - 1) * H;
+    for (int i = threadIdx.x; i < H; i += blockDim.x) {
+        x[(long long)b * H + i] = xp[src + i];
+        y[(long long)b * H + i] = yp[src + i];
+    }
+    if (threadIdx.x == 0) pos[b] = L - 1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -677,6 +823,13 @@ struct b2a_tts {
     int num_sms = 148;
     std::vector<CUtensorMap> tm_qkv, tm_o, tm_gu, tm_down;
     CUtensorMap tm_lm{}, tmx_xn{}, tmx_attn{}, tmx_act{};
+    // batched prefill workspace (sized for the largest B*L seen so far)
+    DBuf<float> xp, yp, qkvp;
+    DBuf<bf16> xnp, attnp, actp;
+    DBuf<float2> rope_tab;
+    CUtensorMap tmp_xn{}, tmp_attn{}, tmp_act{};
+    int pf_tokens_cap = 0;
+    bool use_batched_prefill = true;
     DBuf<int> tokens, pos, recent, recent_n, out_tokens, n_gen, done, n_active, ids, forced;
     HBuf<int> h_flag;
     std::atomic<int> cancel{0};
@@ -785,6 +938,8 @@ struct b2a_tts {
         // tcgen05 / TMA path: needs every GEMM K to be a multiple of 64; B2A_GEMM=simt forces the SIMT fallback
         const char* env = getenv("B2A_GEMM");
         use_tc = !(env && std::string(env) == "simt") && H % tc::BK == 0 && NQ % tc::BK == 0 && I % tc::BK == 0;
+        const char* envp = getenv("B2A_PREFILL");
+        use_batched_prefill = !(envp && std::string(envp) == "step");
         if (use_tc) {
             tc::set_attributes();
             for (auto& L : layers) {
@@ -974,7 +1129,7 @@ struct b2a_tts {
         for (int l = 0; l < cfg.num_hidden_layers; ++l) {
             LayerW& L = layers[l];
             launch_pdl(add_rmsnorm_kernel, dim3(B), dim3(RN_THREADS), 0, s, x.p, l == 0 ? (float*)nullptr : y.p, L.ln1.p, xn.p, H,
-                       cfg.rms_norm_eps, trace_on ? trace.p + (size_t)(2 * l) * 8 * H : (float*)nullptr, (float*)nullptr, 0);
+                       cfg.rms_norm_eps, trace_on ? trace.p + (size_t)(2 * l) * 8 * H : (float*)nullptr, (float*)nullptr, 0, LO_ROW);
             gemm(OP_QKV, l, B, s);
             AttnArgs aa{qkv.p, pos.p, freqs.p, kcache.p + l * kv_layer, vcache.p + l * kv_layer, attn.p, part_o.p, part_ml.p,
                         at_counters.p, nq, nkv, cfg.max_context, at_splits, 1.0f / sqrtf((float)HD)};
@@ -982,7 +1137,7 @@ struct b2a_tts {
             gemm(OP_O, l, B, s);
             // also zeroes this row of q|k|v so the next layer's stream-K QKV GEMM can accumulate into it
             launch_pdl(add_rmsnorm_kernel, dim3(B), dim3(RN_THREADS), 0, s, x.p, y.p, L.ln2.p, xn.p, H, cfg.rms_norm_eps,
-                       trace_on ? trace.p + (size_t)(2 * l + 1) * 8 * H : (float*)nullptr, qkv.p, QKV_N);
+                       trace_on ? trace.p + (size_t)(2 * l + 1) * 8 * H : (float*)nullptr, qkv.p, QKV_N, LO_ROW);
             gemm(OP_GU, l, B, s);
             gemm(OP_DOWN, l, B, s);
         }
@@ -991,10 +1146,89 @@ struct b2a_tts {
 
     void run_lm_head(int B, cudaStream_t s) {
         launch_pdl(add_rmsnorm_kernel, dim3(B), dim3(RN_THREADS), 0, s, x.p, y.p, final_ln.p, xn.p, cfg.hidden_size, cfg.rms_norm_eps,
-                   trace_on ? trace.p + (size_t)(2 * cfg.num_hidden_layers) * 8 * cfg.hidden_size : (float*)nullptr, (float*)nullptr, 0);
+                   trace_on ? trace.p + (size_t)(2 * cfg.num_hidden_layers) * 8 * cfg.hidden_size : (float*)nullptr, (float*)nullptr, 0, LO_ROW);
         gemm(OP_LM, -1, B, s);
     }
     // logits are [8, V] row-major.
+
+    template <int G>
+    static void pattn_attr() {
+        B2A_CUDA(cudaFuncSetAttribute(prefill_attn_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    }
+    size_t pattn_smem(int L) const {
+        const int G = cfg.num_attention_heads / cfg.num_key_value_heads;
+        return ((size_t)2 * L * HD + (size_t)G * PA_QT * HD) * sizeof(float);
+    }
+    bool can_batch_prefill(int L) const {
+        return use_tc && use_batched_prefill && L >= 2 && L <= PA_MAXL && pattn_smem(L) <= 220 * 1024;
+    }
+
+    // D[T, M] = X[T, K] W^T for all prompt tokens: 128-column tiles (64 tokens as hi/lo), CTAs own whole tiles
+    void pf_gemm(const CUtensorMap& tmW, const CUtensorMap& tmX, int epi, float* yout, bf16* actout, int T, int M, int K,
+                 cudaStream_t s) {
+        tc::Args a{};
+        a.out_f32 = yout; a.out_bf16 = actout; a.M = M; a.N = T; a.K = K;
+        a.m_tiles = cdiv(M, tc::BM); a.k_blocks = K / tc::BK;
+        a.stages = 6; a.hilo = 1; a.epi_full = epi; a.epi_partial = -1;
+        a.ldo = epi == tc::EPI_SWIGLU ? M / 2 : M;
+        a.lo_rows = epi == tc::EPI_SWIGLU ? PF_HALF : 0;
+        const int n_tiles = cdiv(T, PF_HALF);
+        const int ctas = std::max(1, std::min(a.m_tiles, num_sms / n_tiles));
+        tc::launch<128>(tmW, tmX, a, ctas, n_tiles, s);
+    }
+
+    // Prompt pass over all B*L tokens; leaves K/V for positions 0..L-1 in the cache and the last position's
+    // residual stream in the decode buffers (x, y), pos[b] = L-1: the caller then runs lm head + sampler.
+    void prefill_batched(int B, int L, cudaStream_t s) {
+        const int H = cfg.hidden_size, I = cfg.intermediate_size, nq = cfg.num_attention_heads, nkv = cfg.num_key_value_heads;
+        const int NQ = nq * HD, QKV_N = (nq + 2 * nkv) * HD, T = B * L, G = nq / nkv;
+        const int n_tiles = cdiv(T, PF_HALF), Tp = n_tiles * PF_HALF;
+        if (Tp > pf_tokens_cap) {
+            xp.alloc((size_t)Tp * H); yp.alloc((size_t)Tp * H); qkvp.alloc((size_t)Tp * QKV_N);
+            xnp.alloc((size_t)2 * Tp * H); attnp.alloc((size_t)2 * Tp * NQ); actp.alloc((size_t)2 * Tp * I);
+            pf_tokens_cap = Tp;
+            tmp_xn = tc::make_tmap_bf16(xnp.p, 2 * Tp, H, 128);
+            tmp_attn = tc::make_tmap_bf16(attnp.p, 2 * Tp, NQ, 128);
+            tmp_act = tc::make_tmap_bf16(actp.p, 2 * Tp, I, 128);
+            pattn_attr<1>(); pattn_attr<2>(); pattn_attr<3>(); pattn_attr<4>(); pattn_attr<6>(); pattn_attr<8>();
+        }
+        rope_tab.alloc((size_t)PA_MAXL * (HD / 2));
+        // padding tokens of the last tile must read as zero
+        B2A_CUDA(cudaMemsetAsync(xnp.p, 0, (size_t)2 * pf_tokens_cap * H * sizeof(bf16), s));
+        B2A_CUDA(cudaMemsetAsync(attnp.p, 0, (size_t)2 * pf_tokens_cap * NQ * sizeof(bf16), s));
+        B2A_CUDA(cudaMemsetAsync(actp.p, 0, (size_t)2 * pf_tokens_cap * I * sizeof(bf16), s));
+        embed_rows_kernel<<<T, 256, 0, s>>>(ids.p, embed.p, xp.p, H, cfg.vocab_size);
+        rope_table_kernel<<<cdiv(L * (HD / 2), 256), 256, 0, s>>>(freqs.p, rope_tab.p, L);
+        count_launch(2);
+        const size_t kv_layer = (size_t)cfg.max_batch * nkv * cfg.max_context * HD;
+        for (int l = 0; l < cfg.num_hidden_layers; ++l) {
+            LayerW& Lw = layers[l];
+            launch_pdl(add_rmsnorm_kernel, dim3(T), dim3(RN_THREADS), 0, s, xp.p, l == 0 ? (float*)nullptr : yp.p, Lw.ln1.p, xnp.p, H,
+                       cfg.rms_norm_eps, (float*)nullptr, (float*)nullptr, 0, PF_HALF);
+            pf_gemm(tm_qkv[l], tmp_xn, tc::EPI_STORE, qkvp.p, nullptr, T, QKV_N, H, s);
+            PrefillAttnArgs pa{qkvp.p, rope_tab.p, kcache.p + l * kv_layer, vcache.p + l * kv_layer, attnp.p, nq, nkv,
+                               cfg.max_context, L, 1.0f / sqrtf((float)HD)};
+            const dim3 grid(nkv, B, cdiv(L, PA_QT));
+            const size_t sm = pattn_smem(L);
+            switch (G) {
+                case 1: prefill_attn_kernel<1><<<grid, PA_THREADS, sm, s>>>(pa); break;
+                case 2: prefill_attn_kernel<2><<<grid, PA_THREADS, sm, s>>>(pa); break;
+                case 3: prefill_attn_kernel<3><<<grid, PA_THREADS, sm, s>>>(pa); break;
+                case 4: prefill_attn_kernel<4><<<grid, PA_THREADS, sm, s>>>(pa); break;
+                case 6: prefill_attn_kernel<6><<<grid, PA_THREADS, sm, s>>>(pa); break;
+                default: prefill_attn_kernel<8><<<grid, PA_THREADS, sm, s>>>(pa); break;
+            }
+            count_launch();
+            pf_gemm(tm_o[l], tmp_attn, tc::EPI_STORE, yp.p, nullptr, T, H, NQ, s);
+            launch_pdl(add_rmsnorm_kernel, dim3(T), dim3(RN_THREADS), 0, s, xp.p, yp.p, Lw.ln2.p, xnp.p, H, cfg.rms_norm_eps,
+                       (float*)nullptr, (float*)nullptr, 0, PF_HALF);
+            pf_gemm(tm_gu[l], tmp_xn, tc::EPI_SWIGLU, nullptr, actp.p, T, 2 * I, H, s);
+            pf_gemm(tm_down[l], tmp_act, tc::EPI_STORE, yp.p, nullptr, T, H, I, s);
+        }
+        gather_last_kernel<<<B, 256, 0, s>>>(xp.p, yp.p, x.p, y.p, pos.p, L, H);
+        count_launch();
+        B2A_CUDA(cudaGetLastError());
+    }
 
     void set_batch(int B) {
         nb_pad = B <= 1 ? 1 : B <= 2 ? 2 : B <= 4 ? 4 : 8;
@@ -1106,18 +1340,41 @@ static void tts_generate_impl(b2a_tts* h, const int32_t* input_ids, bool ids_on_
     init_rows_kernel<<<1, 32, 0, s>>>(h->ids.p, L, B, gp->repetition_context_size > 0 ? R : 0, h->tokens.p, h->pos.p, h->recent.p,
                                       h->recent_n.p, h->n_gen.p, h->done.p, h->n_active.p, 0);
     count_launch();
-    // prefill: positions 0..L-2 need no logits; position L-1 runs the full step (logits -> first token)
-    for (int p = 0; p < L - 1; ++p) {
-        B2A_CUDA(cudaGraphLaunch(h->g_prefill, s));
-        count_launch(h->launches_prefill);
+    // prefill.  Batched: every prompt token through each layer at once (tcgen05 GEMMs, 64 tokens per tile), then
+    // lm head + sampler on the last position.  Fallback (B2A_PREFILL=step, L > 128, SIMT mode): replay the decode
+    // step per position -- positions 0..L-2 need no logits, position L-1 runs the full step.
+    int steps = 0;
+    if (h->can_batch_prefill(L)) {
+        h->prefill_batched(B, L, s);
+        h->run_lm_head(B, s);
+        launch_pdl(sample_kernel, dim3(B), dim3(SM_THREADS), 0, s, sa);
+        steps = 1;
+    } else {
+        for (int p = 0; p < L - 1; ++p) {
+            B2A_CUDA(cudaGraphLaunch(h->g_prefill, s));
+            count_launch(h->launches_prefill);
+        }
     }
     B2A_CUDA(cudaStreamSynchronize(s));
     const double t1 = now_s();
-    int steps = 0;
     bool cancelled = false;
     int streamed = 0;
     std::vector<int> h_tok;
-    while (steps < MT) {
+    auto stream_tokens = [&]() {   // .token events (LlamaTTS.swift:862), row-major per step
+        h_tok.resize((size_t)B * MT);
+        std::vector<int> ng(B);
+        B2A_CUDA(cudaMemcpy(ng.data(), h->n_gen.p, B * sizeof(int), cudaMemcpyDeviceToHost));
+        B2A_CUDA(cudaMemcpy(h_tok.data(), h->out_tokens.p, (size_t)B * MT * sizeof(int), cudaMemcpyDeviceToHost));
+        for (int b = 0; b < B; ++b)
+            if (ng[b] > streamed) on_token(user, b, streamed, h_tok[(size_t)b * MT + streamed]);
+        ++streamed;
+    };
+    if (steps == 1) {
+        if (on_token) stream_tokens();
+        B2A_CUDA(cudaMemcpyAsync(h->h_flag.p, h->n_active.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+        B2A_CUDA(cudaStreamSynchronize(s));
+    }
+    while (steps < MT && !(steps == 1 && h->h_flag.p[0] <= 0)) {
         const int burst = on_token ? 1 : std::min(16, MT - steps);
         for (int i = 0; i < burst; ++i) {
             B2A_CUDA(cudaGraphLaunch(h->g_step, s));
@@ -1126,15 +1383,7 @@ static void tts_generate_impl(b2a_tts* h, const int32_t* input_ids, bool ids_on_
         steps += burst;
         B2A_CUDA(cudaMemcpyAsync(h->h_flag.p, h->n_active.p, sizeof(int), cudaMemcpyDeviceToHost, s));
         B2A_CUDA(cudaStreamSynchronize(s));
-        if (on_token) {   // .token events (LlamaTTS.swift:862), row-major per step
-            h_tok.resize((size_t)B * MT);
-            std::vector<int> ng(B);
-            B2A_CUDA(cudaMemcpy(ng.data(), h->n_gen.p, B * sizeof(int), cudaMemcpyDeviceToHost));
-            B2A_CUDA(cudaMemcpy(h_tok.data(), h->out_tokens.p, (size_t)B * MT * sizeof(int), cudaMemcpyDeviceToHost));
-            for (int b = 0; b < B; ++b)
-                if (ng[b] > streamed) on_token(user, b, streamed, h_tok[(size_t)b * MT + streamed]);
-            ++streamed;
-        }
+        if (on_token) stream_tokens();
         if (h->cancel.load()) { cancelled = true; break; }
         if (h->h_flag.p[0] <= 0) break;
     }

@@ -33,7 +33,8 @@ struct Args {
     int epi_partial;         // epilogue for partial K ranges (EPI_ATOMIC); < 0 => CTAs own whole tiles only
     int hilo;                // X rows [0, BN/2) = hi(x), rows [BN/2, BN) = lo(x) = bf16(x - hi): columns j and
                              // j + BN/2 of the accumulator are summed, giving fp32-activation accuracy for free
-    int lo_rows;             // bf16 outputs are written as hi at row n and lo at row n + lo_rows (0 => hi only)
+    int lo_rows;             // != 0: bf16 outputs are written as hi/lo pairs in the same tile-interleaved row layout the
+                             // kernel reads X in: token t -> hi row (t / (BN/2)) * BN + t % (BN/2), lo row = hi row + BN/2
 };
 
 // ----------------------------------------------------------------------------------------------- PTX
@@ -281,7 +282,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     if (j >= jn) break;
-                    const int n = n0 + c0 + j;
+                    const int n = (a.hilo ? (int)blockIdx.y * HALF : n0) + c0 + j;     // token index
+                    const long long hrow = a.lo_rows ? (long long)(n / HALF) * BN + (n % HALF) : n;
                     float val = v[j];
                     if (epi == EPI_SWIGLU) {
                         // rows are (gate, up) pairs: even lane = gate, odd lane = up   (LlamaTTS.swift:282-284)
@@ -289,18 +291,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (n < a.N && m < a.M && (lane & 1) == 0) {
                             const float r = val / (1.0f + __expf(-val)) * other;
                             const __nv_bfloat16 hi = __float2bfloat16_rn(r);
-                            a.out_bf16[(long long)n * a.ldo + (m >> 1)] = hi;
+                            a.out_bf16[hrow * a.ldo + (m >> 1)] = hi;
                             if (a.lo_rows)
-                                a.out_bf16[(long long)(n + a.lo_rows) * a.ldo + (m >> 1)] = __float2bfloat16_rn(r - __bfloat162float(hi));
+                                a.out_bf16[(hrow + HALF) * a.ldo + (m >> 1)] = __float2bfloat16_rn(r - __bfloat162float(hi));
                         }
                     } else if (n < a.N && m < a.M) {
                         if (epi == EPI_STORE) a.out_f32[(long long)n * a.ldo + m] = val;
                         else if (epi == EPI_ATOMIC) atomicAdd(&a.out_f32[(long long)n * a.ldo + m], val);
                         else {
                             const __nv_bfloat16 hi = __float2bfloat16_rn(val);
-                            a.out_bf16[(long long)n * a.ldo + m] = hi;
+                            a.out_bf16[hrow * a.ldo + m] = hi;
                             if (a.lo_rows)
-                                a.out_bf16[(long long)(n + a.lo_rows) * a.ldo + m] = __float2bfloat16_rn(val - __bfloat162float(hi));
+                                a.out_bf16[(hrow + HALF) * a.ldo + m] = __float2bfloat16_rn(val - __bfloat162float(hi));
                         }
                     }
                 }

@@ -179,3 +179,23 @@ def test_long_context_attention_splits(b2a):
     ref = ol.LlamaOracle(cfg, W, round_acts=False).forward(torch.as_tensor(ids)).numpy()
     for pos in (0, 143, 144, 145, 287, 288, 329):
         assert rel_err(lg[:, pos], ref[:, pos]) < 1e-4, pos
+
+
+@pytest.mark.parametrize("B,L", [(3, 37), (8, 64), (1, 2), (2, 128)])
+def test_batched_prefill_matches_stepwise_and_oracle(b2a, tiny, monkeypatch, B, L):
+    """The tcgen05 batched prompt pass (64-token hi/lo tiles + causal prompt attention) must give the same greedy
+    continuation as replaying the decode step per position, and as the oracle."""
+    cfg, W, _ = tiny
+    ids = np.random.default_rng(100 + L).integers(0, 2048, size=(B, L)).astype(np.int32)
+    P = b2a.GenerateParameters(max_tokens=12, temperature=0.0, top_p=1.0, repetition_penalty=1.0, repetition_context_size=0)
+    m_b = b2a.LlamaTTSModel(hf_config(cfg), W, max_batch=8, max_context=192)
+    a, _, _ = m_b.generate_batch(ids, P, decode_audio=False)
+    monkeypatch.setenv("B2A_PREFILL", "step")
+    m_s = b2a.LlamaTTSModel(hf_config(cfg), W, max_batch=8, max_context=192)
+    monkeypatch.delenv("B2A_PREFILL")
+    s, _, _ = m_s.generate_batch(ids, P, decode_audio=False)
+    assert a == s
+    ref = ol.generate_tokens(ol.LlamaOracle(cfg, W, False), ids, 12, temperature=0.0, rep_penalty=1.0, rep_context=0)
+    assert a == ref
+    # after a batched prefill the KV cache must be what the decode path expects: continue with forward_logits
+    nxt = np.asarray([[t[-1]] for t in a], dtype=np.int32)
