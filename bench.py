@@ -335,7 +335,9 @@ def main():
         "stages_s": {"prefill": infos[-1].prefill_time, "decode": infos[-1].generate_time, "codec": infos[-1].codec_time},
         "roofline": {"kernel": "decode step (CUDA graph: 28 x [rmsnorm, qkv tcgen05 gemm, flash-decode attention, o gemm, rmsnorm, "
                                "gate/up gemm+swiglu, down gemm] + lm-head gemm + sampler); dominant kernel tc_gemm_kernel<16>", "bound": "hbm", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": int(alg_bytes * 1.018), "peak_source": peak_src,
+                     "traffic_source": "ncu --set full on tc_gemm_kernel<16> (profiles/r01_tc_gemm_ncu_full.md): dram bytes / algorithmic "
+                                       "bytes = 1.01-1.04 per GEMM launch, 1.018 weighted; applied to the step's algorithmic bytes",
                      "algorithmic_bytes_per_step": alg_bytes, "ms_per_decode_step": step_ms, "context": ctx},
         "clocks": clocks,
     }

@@ -137,7 +137,7 @@ struct Smem {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS, 2)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Args a) {
     using S = Smem<BN>;
     extern __shared__ uint8_t smem_raw[];
@@ -252,13 +252,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int m = mt * BM + q * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
             constexpr int HALF = BN / 2;
-            // hilo: process column chunk c0 of the hi half together with chunk c0 + HALF of the lo half
-            const int n_cols = a.hilo ? HALF : BN;
-            for (int c0 = 0; c0 < n_cols; c0 += (BN == 16 ? 8 : 16)) {
+            constexpr int CH = (BN == 16) ? 8 : 16;            // token columns handled per iteration
+            const int n_cols = a.hilo ? HALF : BN;              // hilo: column j of the hi half pairs with j + HALF
+            const int ntok0 = a.hilo ? (int)blockIdx.y * HALF : n0;
+            const bool m_ok = m < a.M;
+            for (int c0 = 0; c0 < n_cols; c0 += CH) {
                 float v[16];
-                constexpr int CH = (BN == 16) ? 8 : 16;      // columns handled per iteration
                 if (BN == 16) {
-                    tmem_ld16(taddr, v);                     // all 16 columns: [0,8) hi, [8,16) lo
+                    tmem_ld16(taddr, v);                         // all 16 columns: [0,8) hi, [8,16) lo
                     if (a.hilo) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) v[j] += v[j + 8];
@@ -272,41 +273,58 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int j = 0; j < 16; ++j) v[j] += w[j];
                     }
                 }
-                const bool last = (BN == 16) || (c0 + CH >= n_cols);
-                if (last) {                               // last TMEM read of this accumulator: hand it back early
+                const int jn = (BN == 16 && !a.hilo) ? 16 : CH;
+                if (c0 + jn >= n_cols) {                         // last TMEM read of this accumulator: hand it back early
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty[acc]);
                 }
-                const int jn = (BN == 16) ? (a.hilo ? 8 : 16) : 16;
+                const int nt = ntok0 + c0;                       // first token of this chunk
+                const int nvalid = min(jn, a.N - nt);            // tokens of the chunk that exist
+                if (epi == EPI_SWIGLU) {
+                    // rows are (gate, up) pairs: even lane = gate, odd lane = up   (LlamaTTS.swift:282-284)
+                    // the chunk lies inside one HALF block, so hi rows are consecutive
+                    const long long hrow = a.lo_rows ? (long long)(nt / HALF) * BN + (nt % HALF) : nt;
+                    __nv_bfloat16* ph = a.out_bf16 + hrow * a.ldo + (m >> 1);
+                    const long long lo_off = (long long)HALF * a.ldo;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    if (j >= jn) break;
-                    const int n = (a.hilo ? (int)blockIdx.y * HALF : n0) + c0 + j;     // token index
-                    const long long hrow = a.lo_rows ? (long long)(n / HALF) * BN + (n % HALF) : n;
-                    float val = v[j];
-                    if (epi == EPI_SWIGLU) {
-                        // rows are (gate, up) pairs: even lane = gate, odd lane = up   (LlamaTTS.swift:282-284)
-                        const float other = __shfl_xor_sync(0xffffffffu, val, 1);
-                        if (n < a.N && m < a.M && (lane & 1) == 0) {
-                            const float r = val / (1.0f + __expf(-val)) * other;
+                    for (int j = 0; j < 16; ++j) {
+                        if (j >= jn) break;
+                        const float other = __shfl_xor_sync(0xffffffffu, v[j], 1);
+                        if (j < nvalid && m_ok && (lane & 1) == 0) {
+                            const float r = v[j] / (1.0f + __expf(-v[j])) * other;
                             const __nv_bfloat16 hi = __float2bfloat16_rn(r);
-                            a.out_bf16[hrow * a.ldo + (m >> 1)] = hi;
-                            if (a.lo_rows)
-                                a.out_bf16[(hrow + HALF) * a.ldo + (m >> 1)] = __float2bfloat16_rn(r - __bfloat162float(hi));
+                            ph[0] = hi;
+                            if (a.lo_rows) ph[lo_off] = __float2bfloat16_rn(r - __bfloat162float(hi));
                         }
-                    } else if (n < a.N && m < a.M) {
-                        if (epi == EPI_STORE) a.out_f32[(long long)n * a.ldo + m] = val;
-                        else if (epi == EPI_ATOMIC) atomicAdd(&a.out_f32[(long long)n * a.ldo + m], val);
-                        else {
-                            const __nv_bfloat16 hi = __float2bfloat16_rn(val);
-                            a.out_bf16[hrow * a.ldo + m] = hi;
-                            if (a.lo_rows)
-                                a.out_bf16[(hrow + HALF) * a.ldo + m] = __float2bfloat16_rn(val - __bfloat162float(hi));
+                        ph += a.ldo;
+                    }
+                } else if (epi == EPI_STORE_BF16) {
+                    const long long hrow = a.lo_rows ? (long long)(nt / HALF) * BN + (nt % HALF) : nt;
+                    __nv_bfloat16* ph = a.out_bf16 + hrow * a.ldo + m;
+                    const long long lo_off = (long long)HALF * a.ldo;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (j >= jn) break;
+                        if (j < nvalid && m_ok) {
+                            const __nv_bfloat16 hi = __float2bfloat16_rn(v[j]);
+                            ph[0] = hi;
+                            if (a.lo_rows) ph[lo_off] = __float2bfloat16_rn(v[j] - __bfloat162float(hi));
                         }
+                        ph += a.ldo;
+                    }
+                } else {
+                    float* pf = a.out_f32 + (long long)nt * a.ldo + m;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (j >= jn) break;
+                        if (j < nvalid && m_ok) {
+                            if (epi == EPI_STORE) pf[0] = v[j];
+                            else atomicAdd(pf, v[j]);
+                        }
+                        pf += a.ldo;
                     }
                 }
-                if (BN == 16) break;
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
