@@ -254,6 +254,74 @@ int32_t b2a_tts_interleave(const int32_t* codes0, const int32_t* codes1, const i
                            int32_t n_frames, int32_t* code_list);
 void b2a_tts_destroy(b2a_tts* h);
 
+/* ------------------------------------------------------------------ Whisper STT
+ * Replaces class WhisperModel (Sources/MLXAudioSTT/Models/Whisper/WhisperModel.swift:7-309) behind
+ * STTGenerationModel (Sources/MLXAudioSTT/Generation.swift:52-64):
+ *   fromDirectory / sanitize (:321-382)           -> b2a_stt_create (config + HF-named tensors: conv weights in the
+ *                                                    PyTorch [out,in,k] layout, matrices bf16 or fp32 (rounded to bf16))
+ *   model.encoder(features) (WhisperLayers.swift:146-155) -> b2a_stt_encode          (parity hook)
+ *   model.decoder(tokens:...) + projectToVocab     -> b2a_stt_decoder_logits          (parity hook, after an encode)
+ *   generate(audio:) / transcribeChunk (:36,186-282) -> b2a_stt_transcribe: B independent <=30 s clips
+ *     ("batched == serial"; the reference transcribes one chunk at a time), greedy decode with the reference's
+ *     suppress masks; returns token ids (detokenisation stays with the host tokenizer).  The 30 s chunking of
+ *     longer audio (:165-182) is the caller's loop.
+ * pcm is [B, n_samples] float32 16 kHz mono, every clip padded / trimmed to 30 s like WhisperAudio.padOrTrimToWindow. */
+typedef struct b2a_whisper_config {
+    int32_t vocab_size;
+    int32_t num_mel_bins;
+    int32_t d_model;
+    int32_t encoder_layers;
+    int32_t encoder_attention_heads;
+    int32_t encoder_ffn_dim;
+    int32_t max_source_positions;
+    int32_t decoder_layers;
+    int32_t decoder_attention_heads;
+    int32_t decoder_ffn_dim;
+    int32_t max_target_positions;
+    int32_t max_batch; /* <= 16 clips per call */
+} b2a_whisper_config;
+
+/* STTGenerateParameters as used by transcribeChunk + WhisperGenerationConfig's suppress lists */
+typedef struct b2a_stt_params {
+    int32_t max_tokens;           /* defaultGenerationParameters: max_target_positions - 16 */
+    float temperature;            /* only 0 (greedy argmax, lowest index wins ties) is implemented */
+    const int32_t* prompt_ids;    /* decoder prefix from buildPromptTokens (WhisperTokenizer.swift:98-113) */
+    int32_t n_prompt;
+    const int32_t* begin_suppress; /* suppressed at step 0 only (default [endOfText]) */
+    int32_t n_begin_suppress;
+    const int32_t* suppress;      /* suppressed at every step */
+    int32_t n_suppress;
+    int32_t timestamp_begin;      /* ids >= this are always suppressed (WhisperModel.swift:236) */
+    int32_t eot;                  /* end-of-text id: stops a clip */
+    int32_t mask_eot;             /* benchmark only: never stop (fixed work) */
+} b2a_stt_params;
+
+typedef struct b2a_stt_info {
+    int32_t prompt_tokens;
+    int32_t generation_tokens;
+    int32_t decode_steps;
+    double encode_time; /* log-mel + encoder + cross K/V */
+    double decode_time;
+    double total_time;
+} b2a_stt_info;
+
+typedef struct b2a_stt b2a_stt;
+int32_t b2a_stt_create(int32_t device, const b2a_whisper_config* cfg, const b2a_tensor* tensors,
+                       int32_t n_tensors, b2a_stt** out);
+int32_t b2a_stt_create_random(int32_t device, const b2a_whisper_config* cfg, float std, uint64_t seed, b2a_stt** out);
+void* b2a_stt_stream(b2a_stt* h);
+/* enc_out [B, 1500, d_model] float32 (host) */
+int32_t b2a_stt_encode(b2a_stt* h, const float* pcm, int32_t batch, int64_t n_samples, float* enc_out);
+/* tokens [B, T] teacher-forced from position 0 against the last encode; logits_out [B, T, vocab] (host) */
+int32_t b2a_stt_decoder_logits(b2a_stt* h, const int32_t* tokens, int32_t batch, int32_t len, float* logits_out);
+/* tokens_out [B, params->max_tokens], n_tokens_out [B] (host) */
+int32_t b2a_stt_transcribe(b2a_stt* h, const float* pcm, int32_t batch, int64_t n_samples, const b2a_stt_params* params,
+                           int32_t* tokens_out, int32_t* n_tokens_out, b2a_stt_info* info);
+int32_t b2a_stt_transcribe_dev(b2a_stt* h, const float* d_pcm, int32_t batch, int64_t n_samples,
+                               const b2a_stt_params* params, int32_t* tokens_out, int32_t* n_tokens_out, b2a_stt_info* info);
+int32_t b2a_stt_cancel(b2a_stt* h);
+void b2a_stt_destroy(b2a_stt* h);
+
 #ifdef __cplusplus
 }
 #endif

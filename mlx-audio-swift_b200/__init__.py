@@ -7,10 +7,11 @@ from ._ffi import AudioGenerationError
 from .dsp import IncrementalMelSpectrogram, LogMel, compute_mel_spectrogram, hanning_window, mel_filters, whisper_encoder_features
 from .snac import SNAC
 from .llama_tts import AudioGenerationInfo, GenerateParameters, LlamaTTSModel
+from .whisper import STTGenerateParameters, STTOutput, WhisperModel
 
 __all__ = ["AudioGenerationError", "IncrementalMelSpectrogram", "LogMel", "compute_mel_spectrogram", "hanning_window",
            "mel_filters", "whisper_encoder_features", "SNAC", "LlamaTTSModel", "GenerateParameters",
-           "AudioGenerationInfo"]
+           "AudioGenerationInfo", "WhisperModel", "STTGenerateParameters", "STTOutput"]
 
 
 def device_count() -> int:

@@ -61,6 +61,23 @@ class GenInfo(C.Structure):
                 ("peak_memory_gb", C.c_double)]
 
 
+class WhisperConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("vocab_size", "num_mel_bins", "d_model", "encoder_layers", "encoder_attention_heads",
+                                          "encoder_ffn_dim", "max_source_positions", "decoder_layers", "decoder_attention_heads",
+                                          "decoder_ffn_dim", "max_target_positions", "max_batch")]
+
+
+class SttParams(C.Structure):
+    _fields_ = [("max_tokens", C.c_int32), ("temperature", C.c_float), ("prompt_ids", C.c_void_p), ("n_prompt", C.c_int32),
+                ("begin_suppress", C.c_void_p), ("n_begin_suppress", C.c_int32), ("suppress", C.c_void_p),
+                ("n_suppress", C.c_int32), ("timestamp_begin", C.c_int32), ("eot", C.c_int32), ("mask_eot", C.c_int32)]
+
+
+class SttInfo(C.Structure):
+    _fields_ = [("prompt_tokens", C.c_int32), ("generation_tokens", C.c_int32), ("decode_steps", C.c_int32),
+                ("encode_time", C.c_double), ("decode_time", C.c_double), ("total_time", C.c_double)]
+
+
 TOKEN_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int32, C.c_int32, C.c_int32)
 
 # name -> (restype, argtypes); every symbol include/b200audio.h declares
@@ -107,6 +124,15 @@ SIGNATURES = {
     "b2a_tts_deinterleave": (C.c_int32, [_P, C.c_int32, _P, _P, _P, C.POINTER(C.c_int32)]),
     "b2a_tts_interleave": (C.c_int32, [_P, _P, _P, C.c_int32, _P]),
     "b2a_tts_destroy": (None, [_P]),
+    "b2a_stt_create": (C.c_int32, [C.c_int32, C.POINTER(WhisperConfig), C.POINTER(Tensor), C.c_int32, C.POINTER(_P)]),
+    "b2a_stt_create_random": (C.c_int32, [C.c_int32, C.POINTER(WhisperConfig), C.c_float, C.c_uint64, C.POINTER(_P)]),
+    "b2a_stt_stream": (C.c_void_p, [_P]),
+    "b2a_stt_encode": (C.c_int32, [_P, _P, C.c_int32, C.c_int64, _P]),
+    "b2a_stt_decoder_logits": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, _P]),
+    "b2a_stt_transcribe": (C.c_int32, [_P, _P, C.c_int32, C.c_int64, C.POINTER(SttParams), _P, _P, C.POINTER(SttInfo)]),
+    "b2a_stt_transcribe_dev": (C.c_int32, [_P, _P, C.c_int32, C.c_int64, C.POINTER(SttParams), _P, _P, C.POINTER(SttInfo)]),
+    "b2a_stt_cancel": (C.c_int32, [_P]),
+    "b2a_stt_destroy": (None, [_P]),
 }
 
 _lib = None

@@ -37,10 +37,12 @@ void launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Args& a, int c
     launch_pdl(tc_gemm_kernel<BN>, dim3(ctas, n_tiles), dim3(THREADS), Smem<BN>::bytes(a.stages), s, tmA, tmB, a);
 }
 template void launch<16>(const CUtensorMap&, const CUtensorMap&, const Args&, int, int, cudaStream_t);
+template void launch<32>(const CUtensorMap&, const CUtensorMap&, const Args&, int, int, cudaStream_t);
 template void launch<128>(const CUtensorMap&, const CUtensorMap&, const Args&, int, int, cudaStream_t);
 
 void set_attributes() {
     B2A_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B2A_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     B2A_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 }
 
@@ -55,7 +57,7 @@ extern "C" int32_t b2a_tc_gemm_test(const void* W, const void* X, void* out, int
     using namespace b2a;
     using namespace b2a::tc;
     return guarded([&] {
-        B2A_CHECK(W && X && out && (bn == 16 || bn == 128) && K % BK == 0, B2A_ERR_INVALID_INPUT, "b2a_tc_gemm_test: bad argument");
+        B2A_CHECK(W && X && out && (bn == 16 || bn == 32 || bn == 128) && K % BK == 0, B2A_ERR_INVALID_INPUT, "b2a_tc_gemm_test: bad argument");
         require_device(0);
         set_attributes();
         const int x_rows = hilo ? bn : N;
@@ -64,11 +66,12 @@ extern "C" int32_t b2a_tc_gemm_test(const void* W, const void* X, void* out, int
         a.out_f32 = (float*)out; a.out_bf16 = (__nv_bfloat16*)out; a.M = M; a.N = N; a.K = K;
         a.ldo = epi == EPI_SWIGLU ? M / 2 : M;
         a.m_tiles = cdiv(M, BM); a.k_blocks = K / BK;
-        a.stages = bn == 16 ? Smem<16>::max_stages() : Smem<128>::max_stages();
+        a.stages = bn == 16 ? Smem<16>::max_stages() : bn == 32 ? Smem<32>::max_stages() : Smem<128>::max_stages();
         a.epi_full = epi; a.epi_partial = split ? EPI_ATOMIC : -1; a.hilo = hilo;
         a.lo_rows = (hilo && epi != EPI_STORE) ? bn / 2 : 0;
         const int n_tiles = hilo ? 1 : cdiv(N, bn);
         if (bn == 16) launch<16>(ta, tb, a, ctas, n_tiles, (cudaStream_t)stream);
+        else if (bn == 32) launch<32>(ta, tb, a, ctas, n_tiles, (cudaStream_t)stream);
         else launch<128>(ta, tb, a, ctas, n_tiles, (cudaStream_t)stream);
         B2A_CUDA(cudaGetLastError());
         B2A_CUDA(cudaStreamSynchronize((cudaStream_t)stream));

@@ -20,7 +20,8 @@ namespace tc {
 
 constexpr int BM = 128, BK = 64, UMMA_K = 16;
 constexpr int THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
-enum : int { EPI_STORE = 0, EPI_ATOMIC = 1, EPI_SWIGLU = 2, EPI_STORE_BF16 = 3 };
+enum : int { EPI_STORE = 0, EPI_ATOMIC = 1, EPI_SWIGLU = 2, EPI_STORE_BF16 = 3, EPI_ADD = 4 };
+enum : int { ACT_NONE = 0, ACT_GELU = 1 };
 
 struct Args {
     float* out_f32;          // [N, ldo] fp32 (EPI_STORE / EPI_ATOMIC)
@@ -33,6 +34,8 @@ struct Args {
     int epi_partial;         // epilogue for partial K ranges (EPI_ATOMIC); < 0 => CTAs own whole tiles only
     int hilo;                // X rows [0, BN/2) = hi(x), rows [BN/2, BN) = lo(x) = bf16(x - hi): columns j and
                              // j + BN/2 of the accumulator are summed, giving fp32-activation accuracy for free
+    const float* bias;       // nullable [M]: added to every output column before the activation
+    int act;                 // ACT_NONE | ACT_GELU (exact erf GELU, WhisperLayers.swift:101)
     int lo_rows;             // != 0: bf16 outputs are written as hi/lo pairs in the same tile-interleaved row layout the
                              // kernel reads X in: token t -> hi row (t / (BN/2)) * BN + t % (BN/2), lo row = hi row + BN/2
 };
@@ -279,6 +282,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty[acc]);
                 }
+                if (a.bias || a.act) {
+                    const float bv = (a.bias && m_ok) ? a.bias[m] : 0.f;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float t = v[j] + bv;
+                        if (a.act == ACT_GELU) t = 0.5f * t * (1.0f + erff(t * 0.70710678118654752f));
+                        v[j] = t;
+                    }
+                }
                 const int nt = ntok0 + c0;                       // first token of this chunk
                 const int nvalid = min(jn, a.N - nt);            // tokens of the chunk that exist
                 if (epi == EPI_SWIGLU) {
@@ -320,6 +332,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (j >= jn) break;
                         if (j < nvalid && m_ok) {
                             if (epi == EPI_STORE) pf[0] = v[j];
+                            else if (epi == EPI_ADD) pf[0] += v[j];       // residual accumulate (whole-tile CTAs only)
                             else atomicAdd(pf, v[j]);
                         }
                         pf += a.ldo;

@@ -1,0 +1,170 @@
+"""Host-side mirror of `WhisperModel` (Sources/MLXAudioSTT/Models/Whisper/WhisperModel.swift:7-309) behind
+STTGenerationModel (Sources/MLXAudioSTT/Generation.swift:52-64), over the C ABI.  Tokenisation / detokenisation stay
+with the host (`WhisperTokenizer`); `generate` returns token ids plus the STTOutput statistics."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _ffi
+
+# multilingual vocabulary ids (WhisperTokenizer.swift)
+EOT, SOT, TRANSLATE, TRANSCRIBE, NO_TIMESTAMPS, TIMESTAMP_BEGIN = 50257, 50258, 50358, 50359, 50363, 50364
+LANG_EN = 50259
+CHUNK_SAMPLES = 480000
+
+
+@dataclass
+class STTGenerateParameters:
+    """Sources/MLXAudioSTT/Generation.swift:3-50 as used by Whisper (defaultGenerationParameters, WhisperModel.swift:21-34)."""
+    max_tokens: int = 448 - 16
+    temperature: float = 0.0
+    language_id: Optional[int] = LANG_EN      # already resolved to its token id; None = let the model decide
+    task: str = "transcribe"
+    begin_suppress_tokens: Sequence[int] = (EOT,)
+    suppress_tokens: Sequence[int] = ()
+    mask_eot: bool = False                    # benchmark only
+
+
+@dataclass
+class STTOutput:
+    """Sources/MLXAudioSTT/Models/GLMASR/STTOutput.swift:80-133 (text is left to the host tokenizer)."""
+    tokens: List[List[int]]
+    prompt_tokens: int
+    generation_tokens: int
+    total_tokens: int
+    prompt_tps: float
+    generation_tps: float
+    total_time: float
+    encode_time: float = 0.0
+    decode_time: float = 0.0
+    segments: Optional[list] = None
+
+
+def build_prompt_tokens(language_id: Optional[int] = LANG_EN, task: str = "transcribe", multilingual: bool = True) -> List[int]:
+    """WhisperTokenizer.buildPromptTokens (WhisperTokenizer.swift:98-113) on resolved ids."""
+    toks = [SOT]
+    if multilingual:
+        if language_id is not None:
+            toks.append(language_id)
+        toks.append(TRANSLATE if task.lower() == "translate" else TRANSCRIBE)
+    toks.append(NO_TIMESTAMPS)
+    return toks
+
+
+class WhisperModel:
+    sample_rate = 16000
+
+    @staticmethod
+    def _c_config(config: dict, max_batch: int) -> _ffi.WhisperConfig:
+        d = config.get("d_model", 384)
+        return _ffi.WhisperConfig(config.get("vocab_size", 51865), config.get("num_mel_bins", 80), d,
+                                  config.get("encoder_layers", 4), config.get("encoder_attention_heads", 6),
+                                  config.get("encoder_ffn_dim", 4 * d), config.get("max_source_positions", 1500),
+                                  config.get("decoder_layers", 4), config.get("decoder_attention_heads", 6),
+                                  config.get("decoder_ffn_dim", 4 * d), config.get("max_target_positions", 448), max_batch)
+
+    def __init__(self, config: dict, weights: Dict, device: int = 0, max_batch: int = 16):
+        self.config = config
+        # sanitizeHuggingFace (WhisperModel.swift:335-365): drop the tied proj_out, accept keys without "model."
+        w = {}
+        for k, v in weights.items():
+            if k in ("proj_out.weight", "model.proj_out.weight"):
+                continue
+            if not k.startswith("model.") and (k.startswith("encoder.") or k.startswith("decoder.")):
+                k = "model." + k
+            w[k] = v
+        c = self._c_config(config, max_batch)
+        table, keep = _ffi.make_tensor_table(w)
+        self._h = C.c_void_p()
+        _ffi.check(_ffi.lib().b2a_stt_create(device, C.byref(c), table, len(w), C.byref(self._h)))
+        del keep
+
+    @classmethod
+    def random_init(cls, config: dict, device: int = 0, max_batch: int = 16, std: float = 0.05, seed: int = 1234):
+        self = cls.__new__(cls)
+        self.config = config
+        c = cls._c_config(config, max_batch)
+        self._h = C.c_void_p()
+        _ffi.check(_ffi.lib().b2a_stt_create_random(device, C.byref(c), std, seed, C.byref(self._h)))
+        return self
+
+    @property
+    def stream(self) -> int:
+        return int(_ffi.lib().b2a_stt_stream(self._h) or 0)
+
+    @property
+    def default_generation_parameters(self) -> STTGenerateParameters:
+        return STTGenerateParameters(max_tokens=self.config.get("max_target_positions", 448) - 16)
+
+    @staticmethod
+    def _clips(audio) -> np.ndarray:
+        x = np.ascontiguousarray(audio, dtype=np.float32)
+        if x.ndim == 1:
+            x = x[None]
+        return x
+
+    def encode(self, audio) -> np.ndarray:
+        """model.encoder(WhisperAudio.encoderFeatures(audio)) -> [B, 1500, d_model]."""
+        x = self._clips(audio)
+        out = np.empty((x.shape[0], 1500, self.config.get("d_model", 384)), dtype=np.float32)
+        _ffi.check(_ffi.lib().b2a_stt_encode(self._h, _ffi.ptr(x), x.shape[0], x.shape[1], _ffi.ptr(out)))
+        return out
+
+    def decoder_logits(self, tokens) -> np.ndarray:
+        """Teacher-forced decoder pass against the last `encode`: tokens [B, T] -> logits [B, T, vocab]."""
+        t = np.ascontiguousarray(tokens, dtype=np.int32)
+        out = np.empty((t.shape[0], t.shape[1], self.config.get("vocab_size", 51865)), dtype=np.float32)
+        _ffi.check(_ffi.lib().b2a_stt_decoder_logits(self._h, _ffi.ptr(t), t.shape[0], t.shape[1], _ffi.ptr(out)))
+        return out
+
+    def _params(self, p: STTGenerateParameters):
+        prompt = np.asarray(build_prompt_tokens(p.language_id, p.task), dtype=np.int32)
+        bs = np.asarray(list(p.begin_suppress_tokens), dtype=np.int32)
+        su = np.asarray(list(p.suppress_tokens), dtype=np.int32)
+        sp = _ffi.SttParams(p.max_tokens, p.temperature, prompt.ctypes.data, len(prompt), bs.ctypes.data if len(bs) else None,
+                            len(bs), su.ctypes.data if len(su) else None, len(su), TIMESTAMP_BEGIN, EOT, int(p.mask_eot))
+        return sp, (prompt, bs, su)
+
+    def generate(self, audio, generation_parameters: Optional[STTGenerateParameters] = None) -> STTOutput:
+        """generate(audio:generationParameters:) (WhisperModel.swift:36-93) for a batch of <=30 s clips [B, n]."""
+        p = generation_parameters or self.default_generation_parameters
+        x = self._clips(audio)
+        B = x.shape[0]
+        sp, keep = self._params(p)
+        toks = np.zeros((B, p.max_tokens), dtype=np.int32)
+        ntok = np.zeros(B, dtype=np.int32)
+        info = _ffi.SttInfo()
+        _ffi.check(_ffi.lib().b2a_stt_transcribe(self._h, _ffi.ptr(x), B, x.shape[1], C.byref(sp), _ffi.ptr(toks), _ffi.ptr(ntok),
+                                                 C.byref(info)))
+        del keep
+        tt = max(info.total_time, 1e-9)
+        return STTOutput([toks[b, :ntok[b]].tolist() for b in range(B)], info.prompt_tokens, info.generation_tokens,
+                         info.prompt_tokens + info.generation_tokens, info.prompt_tokens / tt, info.generation_tokens / tt,
+                         info.total_time, info.encode_time, info.decode_time)
+
+    def generate_dev(self, d_pcm, generation_parameters: STTGenerateParameters, tokens_host, n_tokens_host) -> STTOutput:
+        """Device-resident audio (torch CUDA tensor [B, n]); token ids land in the caller's host arrays."""
+        sp, keep = self._params(generation_parameters)
+        B, n = d_pcm.shape
+        info = _ffi.SttInfo()
+        _ffi.check(_ffi.lib().b2a_stt_transcribe_dev(self._h, _ffi.ptr(d_pcm), B, n, C.byref(sp), _ffi.ptr(tokens_host),
+                                                     _ffi.ptr(n_tokens_host), C.byref(info)))
+        del keep
+        tt = max(info.total_time, 1e-9)
+        return STTOutput([], info.prompt_tokens, info.generation_tokens, info.prompt_tokens + info.generation_tokens,
+                         info.prompt_tokens / tt, info.generation_tokens / tt, info.total_time, info.encode_time, info.decode_time)
+
+    def cancel(self) -> None:
+        _ffi.check(_ffi.lib().b2a_stt_cancel(self._h))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                _ffi.lib().b2a_stt_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass

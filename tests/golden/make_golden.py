@@ -12,6 +12,7 @@ import torch
 ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 from oracle import dsp, llama, snac  # noqa: E402
+from oracle import whisper as ow  # noqa: E402
 
 OUT = Path(__file__).resolve().parent
 
@@ -73,7 +74,20 @@ def llama_tiny():
                         freqs=llama.llama3_rope_freqs(llama.LlamaConfig()))
 
 
+def whisper_tiny():
+    cfg = ow.WhisperConfig.tiny_test()
+    W = ow.init_weights(cfg, 1234)
+    x = dsp.synth_audio(64000, 3)
+    o = ow.WhisperOracle(cfg, W)
+    feats = torch.from_numpy(dsp.whisper_encoder_features(x)).float()
+    enc = o.encode(feats).numpy()
+    toks, logits = ow.transcribe_tokens(ow.WhisperOracle(cfg, W), x, ow.build_prompt_tokens(), max_tokens=12, mask_eot=True,
+                                        return_logits=True)
+    np.savez_compressed(OUT / "whisper_tiny.npz", greedy=np.asarray(toks, dtype=np.int32), enc_stats=stats(enc),
+                        enc_rows=enc[0, [0, 1, 700, 1499]].astype(np.float32), first_logits_stats=stats(np.clip(logits[0], -50, 50)))
+
+
 if __name__ == "__main__":
-    mel(); snac_small(); llama_tiny()
+    mel(); snac_small(); llama_tiny(); whisper_tiny()
     for f in sorted(OUT.glob("*.npz")):
         print(f.name, f.stat().st_size)
