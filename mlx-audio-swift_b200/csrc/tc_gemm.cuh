@@ -259,7 +259,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int n_cols = a.hilo ? HALF : BN;              // hilo: column j of the hi half pairs with j + HALF
             const int ntok0 = a.hilo ? (int)blockIdx.y * HALF : n0;
             const bool m_ok = m < a.M;
-            for (int c0 = 0; c0 < n_cols; c0 += CH) {
+            const int cstep = (BN == 16 && !a.hilo) ? 16 : CH;
+            for (int c0 = 0; c0 < n_cols; c0 += cstep) {
                 float v[16];
                 if (BN == 16) {
                     tmem_ld16(taddr, v);                         // all 16 columns: [0,8) hi, [8,16) lo

@@ -1,0 +1,93 @@
+"""Per-stage measurements for the other BASELINE.json configs (not the driver's bench line): CUDA events on the
+library's streams, inputs resident in HBM, roofline numerators from SURVEY.md section 8d.
+
+    python tools/bench_kernels.py [mel] [snac] [whisper]      -> one JSON line per stage
+"""
+import json
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import mlx_audio_swift_b200 as m  # noqa: E402
+
+PEAKS = json.loads((Path(__file__).resolve().parents[1] / "MEASURED_PEAKS.json").read_text()) \
+    if (Path(__file__).resolve().parents[1] / "MEASURED_PEAKS.json").exists() else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
+
+
+def timed(fn, stream_ptr, iters=10, warmup=3):
+    s = torch.cuda.ExternalStream(stream_ptr) if stream_ptr else torch.cuda.current_stream()
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(s)
+    for _ in range(iters):
+        fn()
+    e1.record(s)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def synth(n, seed):
+    rng = np.random.default_rng(seed)
+    t = np.arange(n) / 16000.0
+    return np.clip(0.5 * np.sin(2 * np.pi * 220 * t) + 0.1 * rng.standard_normal(n), -1, 1).astype(np.float32)
+
+
+def bench_mel():
+    for B, n, name in ((1, 160000, "config1: 10 s clip (core log-mel)"), (16, 480000, "config3 front-end: 16 x 30 s (Whisper log-mel)"),
+                       (128, 480000, "128 x 30 s (Whisper log-mel, larger than L2)")):
+        kind = "core" if B == 1 else "whisper"
+        lm = m.LogMel(kind, n_mels=80)
+        x = torch.from_numpy(np.stack([synth(n, i % 4) for i in range(min(B, 4))])).cuda().repeat((B + 3) // 4, 1)[:B].contiguous()
+        F = lm.frames(n)
+        out = torch.empty((B, F, 80), device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+        ms = timed(lambda: lm.compute_dev(x, out, st), 0)
+        alg = 4 * B * n + 4 * B * F * 80
+        print(json.dumps({"stage": "mel", "workload": name, "ms": ms, "algorithmic_bytes": alg, "achieved_GBs": alg / ms / 1e6,
+                          "frac_of_hbm": alg / ms / 1e6 / PEAKS["hbm_gbs"], "audio_s_per_s": B * n / 16000 / (ms * 1e-3),
+                          "note": "two kernels: fused STFT->power->mel->log10 + in-place max-8 clamp (adds 2*4*F*80 bytes/clip, not counted)"}))
+
+
+def bench_snac():
+    codec = m.SNAC(weights=m.SNAC.random_init_weights(1234))
+    B, T = 8, 1024
+    rng = np.random.default_rng(2)
+    codes = [torch.from_numpy(rng.integers(0, 4096, size=(B, T // s), dtype=np.int32)).cuda() for s in (4, 2, 1)]
+    wave = torch.empty((B, 1, T * 512), device="cuda")
+    ms = timed(lambda: codec.decode_dev(codes, wave, seed=1, stream=codec.stream), codec.stream, iters=3, warmup=1)
+    flop = 212e9 * B
+    fused_bytes = 441.5e6 * B
+    print(json.dumps({"stage": "snac_decode", "workload": "config2: batch 8 x 1024 latent steps -> 8 x 524288 samples (174.8 s audio)",
+                      "ms": ms, "dense_flop": flop, "achieved_TFLOPs": flop / ms / 1e9, "per_block_fused_bytes": fused_bytes,
+                      "achieved_GBs_vs_fused_bound": fused_bytes / ms / 1e6, "frac_of_hbm": fused_bytes / ms / 1e6 / PEAKS["hbm_gbs"],
+                      "x_realtime": B * T * 512 / 24000 / (ms * 1e-3), "note": "round 1: fp32 CUDA-core GEMMs (compute-bound)"}))
+
+
+def bench_whisper():
+    cfg = dict(vocab_size=51865, num_mel_bins=80, d_model=512, encoder_layers=6, encoder_attention_heads=8, encoder_ffn_dim=2048,
+               max_source_positions=1500, decoder_layers=6, decoder_attention_heads=8, decoder_ffn_dim=2048, max_target_positions=448)
+    wm = m.WhisperModel.random_init(cfg, max_batch=16)
+    B = 16
+    x = torch.from_numpy(np.stack([synth(480000, i) for i in range(B)])).cuda()
+    P = m.STTGenerateParameters(max_tokens=64, mask_eot=True)
+    toks = np.zeros((B, 64), dtype=np.int32)
+    nt = np.zeros(B, dtype=np.int32)
+    outs = []
+    ms = timed(lambda: outs.append(wm.generate_dev(x, P, toks, nt)), wm.stream, iters=3, warmup=1)
+    o = outs[-1]
+    print(json.dumps({"stage": "whisper_base", "workload": "config3: 16 x 30 s, greedy, 64 forced decode steps", "ms": ms,
+                      "x_realtime": B * 30 / (ms * 1e-3), "encode_ms": o.encode_time * 1e3, "decode_ms": o.decode_time * 1e3,
+                      "encoder_TFLOPs_useful": 87.4e9 * B / max(o.encode_time, 1e-9) / 1e12,
+                      "note": "encode = log-mel + conv stem + 6 layers + cross K/V; decode = 4-token prefix + 64 graph-replayed steps"}))
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["mel", "snac", "whisper"]
+    for w in which:
+        {"mel": bench_mel, "snac": bench_snac, "whisper": bench_whisper}[w]()
