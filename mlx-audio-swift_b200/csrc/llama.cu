@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <chrono>
 #include <cmath>
 
@@ -1120,6 +1121,12 @@ struct b2a_tts {
         }
     }
 
+    // timing ablation only (B2A_SKIP=norm|attn|gemm|qkv|o|gu|down, comma separated): skips launches, results invalid
+    static bool skip(const char* what) {
+        const char* e = getenv("B2A_SKIP");
+        return e && strstr(e, what) != nullptr;
+    }
+
     // embed(tokens) -> all layers; leaves the residual stream in x and the last MLP output in y
     void run_layers(int B, cudaStream_t s) {
         const int H = cfg.hidden_size, nq = cfg.num_attention_heads, nkv = cfg.num_key_value_heads;
@@ -1128,18 +1135,20 @@ struct b2a_tts {
         const size_t kv_layer = (size_t)cfg.max_batch * nkv * cfg.max_context * HD;
         for (int l = 0; l < cfg.num_hidden_layers; ++l) {
             LayerW& L = layers[l];
+            if (!skip("norm"))
             launch_pdl(add_rmsnorm_kernel, dim3(B), dim3(RN_THREADS), 0, s, x.p, l == 0 ? (float*)nullptr : y.p, L.ln1.p, xn.p, H,
                        cfg.rms_norm_eps, trace_on ? trace.p + (size_t)(2 * l) * 8 * H : (float*)nullptr, (float*)nullptr, 0, LO_ROW);
-            gemm(OP_QKV, l, B, s);
+            if (!skip("gemm") && !skip("qkv")) gemm(OP_QKV, l, B, s);
             AttnArgs aa{qkv.p, pos.p, freqs.p, kcache.p + l * kv_layer, vcache.p + l * kv_layer, attn.p, part_o.p, part_ml.p,
                         at_counters.p, nq, nkv, cfg.max_context, at_splits, 1.0f / sqrtf((float)HD)};
-            attn_launch(aa, B, s);
-            gemm(OP_O, l, B, s);
+            if (!skip("attn")) attn_launch(aa, B, s);
+            if (!skip("gemm") && !skip("o_proj")) gemm(OP_O, l, B, s);
             // also zeroes this row of q|k|v so the next layer's stream-K QKV GEMM can accumulate into it
+            if (!skip("norm"))
             launch_pdl(add_rmsnorm_kernel, dim3(B), dim3(RN_THREADS), 0, s, x.p, y.p, L.ln2.p, xn.p, H, cfg.rms_norm_eps,
                        trace_on ? trace.p + (size_t)(2 * l + 1) * 8 * H : (float*)nullptr, qkv.p, QKV_N, LO_ROW);
-            gemm(OP_GU, l, B, s);
-            gemm(OP_DOWN, l, B, s);
+            if (!skip("gemm") && !skip("gate")) gemm(OP_GU, l, B, s);
+            if (!skip("gemm") && !skip("down")) gemm(OP_DOWN, l, B, s);
         }
         (void)G;
     }

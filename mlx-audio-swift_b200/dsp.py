@@ -61,9 +61,12 @@ class IncrementalMelSpectrogram:
         return int(_ffi.lib().b2a_mel_total_frames(self._h))
 
     def __del__(self):
-        if getattr(self, "_h", None) and self._h.value:
-            _ffi.lib().b2a_mel_destroy(self._h)
-            self._h = C.c_void_p()
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                _ffi.lib().b2a_mel_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:   # interpreter shutdown: ctypes globals may already be gone
+            pass
 
 
 class LogMel:
@@ -95,9 +98,12 @@ class LogMel:
         _ffi.check(_ffi.lib().b2a_logmel_compute_dev(self._h, _ffi.ptr(d_pcm), B, n, _ffi.ptr(d_out), C.c_void_p(stream)))
 
     def __del__(self):
-        if getattr(self, "_h", None) and self._h.value:
-            _ffi.lib().b2a_logmel_destroy(self._h)
-            self._h = C.c_void_p()
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                _ffi.lib().b2a_logmel_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:   # interpreter shutdown: ctypes globals may already be gone
+            pass
 
 
 def compute_mel_spectrogram(audio, sample_rate: int, n_fft: int, hop_length: int, n_mels: int, device: int = 0):

@@ -235,6 +235,9 @@ class LlamaTTSModel:
         _ffi.check(_ffi.lib().b2a_tts_cancel(self._h))
 
     def __del__(self):
-        if getattr(self, "_h", None) and self._h.value:
-            _ffi.lib().b2a_tts_destroy(self._h)
-            self._h = C.c_void_p()
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                _ffi.lib().b2a_tts_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:   # interpreter shutdown: ctypes globals may already be gone
+            pass

@@ -154,6 +154,9 @@ class SNAC:
         return zq, codes
 
     def __del__(self):
-        if getattr(self, "_h", None) and self._h.value:
-            _ffi.lib().b2a_snac_destroy(self._h)
-            self._h = C.c_void_p()
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                _ffi.lib().b2a_snac_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:   # interpreter shutdown: ctypes globals may already be gone
+            pass
