@@ -12,7 +12,7 @@ CSRC = HERE / "csrc"
 LIBDIR = HERE / "lib"
 LIB = LIBDIR / "libb200audio.so"
 SOURCES = ["api.cu", "mel.cu", "snac.cu", "llama.cu", "tc_gemm.cu", "whisper.cu"]
-NVCC_FLAGS = [
+NVCC_FLAGS = (["-DB2A_ATTN_TIMING"] if os.environ.get("B2A_ATTN_TIMING") else []) + [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
 ]

@@ -212,6 +212,13 @@ gemv_bf16_kernel(const bf16* __restrict__ W, const bf16* __restrict__ xin, float
 // ------------------------------------------------------------------------------------------------
 constexpr int HD = 128, AT_THREADS = 256, MAXG = 8, AT_CAP = 64;   // AT_CAP * 4 == AT_THREADS
 
+#ifdef B2A_ATTN_TIMING
+__device__ long long g_attn_ts[8 * 4096];
+#define ATS(i) do { if (threadIdx.x == 0) g_attn_ts[(((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (i)] = clock64(); } while (0)
+#else
+#define ATS(i) do {} while (0)
+#endif
+
 struct AttnArgs {
     const float* qkv;      // [B, (nq + 2 nkv) * 128] fp32
     const int* pos;        // [B]
@@ -234,19 +241,21 @@ attn_decode_kernel(AttnArgs a) {
     float* sV = sK + AT_CAP * HD;                               // [AT_CAP][128]
     float* sq = sV + AT_CAP * HD;                               // [G][128]
     float* sc = sq + G * HD;                                    // [G][AT_CAP]
-    float* spo = sc + G * AT_CAP;                               // [2][G][128]
-    uint64_t* bar = reinterpret_cast<uint64_t*>(spo + 2 * G * HD);
+    float* wpo = sc + G * AT_CAP;                               // [8 warps][G][128] warp-partial outputs
+    uint64_t* bar = reinterpret_cast<uint64_t*>(wpo + (AT_THREADS / 32) * G * HD);
     __shared__ float red[AT_THREADS / 32][MAXG];
-    __shared__ float stat[2][MAXG];
     __shared__ int s_last;
 
     const int h = blockIdx.x, b = blockIdx.y, s = blockIdx.z, tid = threadIdx.x;
+    ATS(0);
     pdl_trigger();
-    pdl_wait();
+    // Everything that does not depend on this step's q|k|v runs BEFORE griddepcontrol.wait and overlaps with the
+    // tail of the QKV GEMM: pos[] is only written by the sampler (last kernel of the previous step's graph), the
+    // cache rows < pos by earlier steps.  So: position, RoPE angles, mbarrier, and the bulk K/V loads go first.
     const int p = a.pos[b];
-    if (p < 0 || p >= a.max_ctx) return;
-    const int S_eff = p / AT_CAP + 1;
-    if (s >= S_eff) return;
+    const bool row_ok = p >= 0 && p < a.max_ctx;
+    const int S_eff = row_ok ? p / AT_CAP + 1 : 0;
+    if (s >= S_eff) { pdl_wait(); return; }
     const int t0 = s * AT_CAP, t1 = min(t0 + AT_CAP, p + 1), nk = t1 - t0;
     const bool has_new = (s == S_eff - 1);                      // this split owns the new position p
     const int n_load = has_new ? nk - 1 : nk;
@@ -270,10 +279,12 @@ attn_decode_kernel(AttnArgs a) {
             tc::mbar_arrive(bar);
         }
     }
-    if (tid < HD / 2) {  // MLXFast.RoPE(traditional:false, freqs:): angle = pos / freqs[i], pairs (i, i+64)
+    float sn = 0.f, cs = 1.f;
+    if (tid < HD / 2) sincosf((float)p / a.freqs[tid], &sn, &cs);   // MLXFast.RoPE(freqs:): angle = pos / freqs[i]
+    pdl_wait();
+    ATS(1);
+    if (tid < HD / 2) {  // non-traditional RoPE: pairs (i, i+64)
         const int d = tid;
-        float sn, cs;
-        sincosf((float)p / a.freqs[d], &sn, &cs);
         _Pragma("unroll") for (int g = 0; g < G; ++g) {
             const float* q = row + (h * G + g) * HD;
             const float x1 = q[d], x2 = q[d + HD / 2];
@@ -296,18 +307,21 @@ attn_decode_kernel(AttnArgs a) {
         sV[(p - t0) * HD + d] = v;
     }
     __syncthreads();            // barrier init + q / new-row staging visible
+    ATS(2);
     tc::mbar_wait(bar, 0);      // bulk-copied K and V have landed
+    ATS(3);
 
-    // scores: 4 threads per key (32 dims each); float4 columns are interleaved across the 4 threads and rotated by
-    // the key index so every quarter-warp touches 8 distinct 16-byte bank groups (rows are 512 B apart)
+    // Each warp owns 8 keys end to end (4 lanes per key): scores, a warp-local softmax (max / sum by shuffles) and
+    // its partial P*V; the 8 warp partials are merged through shared memory with ONE block barrier.
+    const int lane = tid & 31, warp = tid >> 5;
+    const int key = warp * 8 + (lane >> 2), part = lane & 3;
     float sacc[G];
     _Pragma("unroll") for (int g = 0; g < G; ++g) sacc[g] = 0.f;
-    const int key = tid >> 2, part = tid & 3;
     if (key < nk) {
         const float4* kr = reinterpret_cast<const float4*>(sK + key * HD);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int d4 = part + 4 * ((j + key) & 7);
+            const int d4 = part + 4 * ((j + key) & 7);     // rotated columns: every quarter-warp hits 8 distinct bank groups
             const float4 kf = kr[d4];
             _Pragma("unroll") for (int g = 0; g < G; ++g) {
                 const float4 qf = reinterpret_cast<const float4*>(sq + g * HD)[d4];
@@ -316,56 +330,65 @@ attn_decode_kernel(AttnArgs a) {
             }
         }
     }
+    float pw[G], mw[G], lw[G];
     _Pragma("unroll") for (int g = 0; g < G; ++g) {
         float v = sacc[g];
         v += __shfl_xor_sync(0xffffffffu, v, 1);
         v += __shfl_xor_sync(0xffffffffu, v, 2);
-        float m = key < nk ? v * a.scale : -INFINITY;
-        sacc[g] = m;
-        for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if ((tid & 31) == 0) red[tid >> 5][g] = m;
+        const float sv = key < nk ? v * a.scale : -INFINITY;
+        float m = sv;
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
+        const float e = (m == -INFINITY) ? 0.f : __expf(sv - m);    // all 4 lanes of a key hold the same value
+        float l = part == 0 ? e : 0.f;
+        l = warp_sum(l);
+        pw[g] = e; mw[g] = m; lw[g] = l;
     }
-    __syncthreads();
-    if (tid < G) {
-        float m = red[0][tid];
-        for (int i = 1; i < AT_THREADS / 32; ++i) m = fmaxf(m, red[i][tid]);
-        stat[0][tid] = m;
+    // warp-partial P*V: lane owns dims 4*lane .. 4*lane+3 (conflict-free float4 reads of a V row)
+    float4 o4[G];
+    _Pragma("unroll") for (int g = 0; g < G; ++g) o4[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+        const int t = warp * 8 + kk;
+        if (t < nk) {
+            const float4 v = reinterpret_cast<const float4*>(sV + t * HD)[lane];
+            _Pragma("unroll") for (int g = 0; g < G; ++g) {
+                const float pk = __shfl_sync(0xffffffffu, pw[g], kk * 4);
+                o4[g].x = fmaf(pk, v.x, o4[g].x); o4[g].y = fmaf(pk, v.y, o4[g].y);
+                o4[g].z = fmaf(pk, v.z, o4[g].z); o4[g].w = fmaf(pk, v.w, o4[g].w);
+            }
+        }
     }
-    __syncthreads();
+    // spo doubles as the warp-partial buffer: [8 warps][G][128]; red / sc hold the warp (max, sum)
     _Pragma("unroll") for (int g = 0; g < G; ++g) {
-        const float e = (key < nk && part == 0) ? __expf(sacc[g] - stat[0][g]) : 0.f;
-        if (key < nk && part == 0) sc[g * AT_CAP + key] = e;
-        const float sum = warp_sum(e);
-        if ((tid & 31) == 0) red[tid >> 5][g] = sum;
+        reinterpret_cast<float4*>(wpo + (warp * G + g) * HD)[lane] = o4[g];
+        if (lane == 0) { red[warp][g] = mw[g]; sc[g * AT_CAP + warp] = lw[g]; }
     }
-    __syncthreads();
-    if (tid < G) {
-        float sum = 0.f;
-        for (int i = 0; i < AT_THREADS / 32; ++i) sum += red[i][tid];
-        stat[1][tid] = sum;
-    }
-    // PV: thread = (key parity, dim); consecutive lanes read consecutive floats of a V row (conflict-free)
-    const int half = tid >> 7, d = tid & 127;
-    float o[G];
-    _Pragma("unroll") for (int g = 0; g < G; ++g) o[g] = 0.f;
-    for (int t = half; t < nk; t += 2) {
-        const float v = sV[t * HD + d];
-        _Pragma("unroll") for (int g = 0; g < G; ++g) o[g] = fmaf(sc[g * AT_CAP + t], v, o[g]);
-    }
-    _Pragma("unroll") for (int g = 0; g < G; ++g) spo[(half * G + g) * HD + d] = o[g];
     __syncthreads();
     const long long pbase = (((long long)b * a.nkv + h) * a.S + s) * G;
-    if (tid < HD)
-        _Pragma("unroll") for (int g = 0; g < G; ++g)
-            a.part_o[(pbase + g) * HD + tid] = spo[g * HD + tid] + spo[(G + g) * HD + tid];
-    if (tid < G) {
-        a.part_ml[(pbase + tid) * 2] = stat[0][tid];
-        a.part_ml[(pbase + tid) * 2 + 1] = stat[1][tid];
+    if (tid < HD) {
+        _Pragma("unroll") for (int g = 0; g < G; ++g) {
+            float M = red[0][g];
+#pragma unroll
+            for (int w = 1; w < AT_THREADS / 32; ++w) M = fmaxf(M, red[w][g]);
+            float L = 0.f, O = 0.f;
+#pragma unroll
+            for (int w = 0; w < AT_THREADS / 32; ++w) {
+                const float sc_w = red[w][g] == -INFINITY ? 0.f : __expf(red[w][g] - M);
+                L = fmaf(sc[g * AT_CAP + w], sc_w, L);
+                O = fmaf(wpo[(w * G + g) * HD + tid], sc_w, O);
+            }
+            a.part_o[(pbase + g) * HD + tid] = O;
+            if (tid == 0) { a.part_ml[(pbase + g) * 2] = M; a.part_ml[(pbase + g) * 2 + 1] = L; }
+        }
     }
+    ATS(4);
     __threadfence();
     __syncthreads();
     if (tid == 0) s_last = (atomicAdd(&a.counters[b * a.nkv + h], 1) == S_eff - 1);
     __syncthreads();
+    ATS(5);
     if (!s_last) return;
     __threadfence();
     // merge the S_eff partials
@@ -384,7 +407,14 @@ attn_decode_kernel(AttnArgs a) {
         }
     }
     if (tid == 0) a.counters[b * a.nkv + h] = 0;
+    ATS(6);
 }
+
+#ifdef B2A_ATTN_TIMING
+extern "C" int b2a_debug_attn_ts(long long* out, int n) {
+    return (int)cudaMemcpyFromSymbol(out, g_attn_ts, sizeof(long long) * n);
+}
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // Batched prefill (LlamaTTS.swift:711 `self(inputIds, cache)` on the whole prompt): all B*L prompt tokens go
@@ -878,7 +908,7 @@ struct b2a_tts {
     }
     size_t attn_smem_bytes() const {
         const int G = cfg.num_attention_heads / cfg.num_key_value_heads;
-        return (size_t)(2 * AT_CAP * HD + G * HD + G * AT_CAP + 2 * G * HD) * sizeof(float) + 16;
+        return (size_t)(2 * AT_CAP * HD + G * HD + G * AT_CAP + (AT_THREADS / 32) * G * HD) * sizeof(float) + 16;
     }
 
     void check_config() {

@@ -14,9 +14,11 @@
 // Snake activations are fused into the epilogue of the producing kernel (or the prologue of the
 // depthwise conv), the residual add / noise injection into the GEMM epilogue.
 #include "common.cuh"
+#include "conv_gemm.cuh"
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace b2a {
 
@@ -342,6 +344,124 @@ nearest_code_kernel(const float* __restrict__ en, const float* __restrict__ e2, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Channels-last (NLC) tensor-core path: activations fp32 [B*T, C] plus bf16 hi/lo copies in 64-token tiles that
+// the conv GEMM (conv_gemm.cuh) reads through TMA.  The kernels below are the non-GEMM pieces.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void put_hilo_nlc(__nv_bfloat16* base, long long ld, long long tok, long long col, float v) {
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const long long r = (tok / 64) * 128 + (tok % 64);
+    base[r * ld + col] = hi;
+    base[(r + 64) * ld + col] = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// z[b*T + t, c] = sum_i (bias_i[c] + Wout_i[c,:] . codebook_i[codes_i[b, t/s_i], :])      (VQ.swift:165-191)
+__global__ void rvq_lookup_nlc_kernel(RvqArgs a, float* __restrict__ out) {
+    const long long tok = blockIdx.x;                  // b*T + t
+    const int b = (int)(tok / a.T), t = (int)(tok - (long long)b * a.T);
+    __shared__ float se[4][16];
+    if (threadIdx.x < a.n_levels * a.D) {
+        const int i = threadIdx.x / a.D, d = threadIdx.x - i * a.D;
+        const RvqLevel& L = a.lv[i];
+        int code = L.codes[(long long)b * (a.T / L.stride) + t / L.stride];
+        code = min(max(code, 0), a.codebook_size - 1);
+        se[i][d] = L.codebook[(long long)code * a.D + d];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+        float acc = 0.f;
+        for (int i = 0; i < a.n_levels; ++i) {
+            const float* w = a.lv[i].wout + (long long)c * a.D;
+            float v = a.lv[i].bias[c];
+            for (int d = 0; d < a.D; ++d) v = fmaf(w[d], se[i][d], v);
+            acc += v;
+        }
+        out[tok * a.C + c] = acc;
+    }
+}
+
+// Depthwise conv k7 (dilation d) along time in NLC, optional Snake before / after, output as bf16 hi/lo tiles.
+// CTA = 64 tokens (+ halo) x CT channels; the Snake'd input tile lives in shared memory (sin once per element).
+constexpr int DWN_TT = 64, DWN_THREADS = 256;
+__global__ void __launch_bounds__(DWN_THREADS)
+dw7_nlc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, const float* __restrict__ w /*[C,7]*/,
+               const float* __restrict__ bias, const float* __restrict__ alpha_in, const float* __restrict__ alpha_out,
+               int T, int C, int CT, int dil) {
+    extern __shared__ float dsm[];     // [(64 + 6*dil)][CT]
+    const int t0 = blockIdx.x * DWN_TT, c0 = blockIdx.y * CT, b = blockIdx.z;
+    const int halo = 3 * dil, rows = DWN_TT + 2 * halo;
+    const float* xb = x + (long long)b * T * C;
+    for (int i = threadIdx.x; i < rows * CT; i += DWN_THREADS) {
+        const int r = i / CT, c = i - r * CT;
+        const int t = t0 + r - halo;
+        float v = 0.f;
+        if (t >= 0 && t < T && c0 + c < C) {
+            v = xb[(long long)t * C + c0 + c];
+            if (alpha_in) v = snake_f(v, alpha_in[c0 + c]);
+        }
+        dsm[i] = v;
+    }
+    __syncthreads();
+    const int c = threadIdx.x % CT, grp = threadIdx.x / CT, ngrp = DWN_THREADS / CT;
+    if (c0 + c >= C) return;
+    float wk[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) wk[k] = w[(c0 + c) * 7 + k];
+    const float bv = bias ? bias[c0 + c] : 0.f;
+    const float ao = alpha_out ? alpha_out[c0 + c] : 0.f;
+    for (int tt = grp; tt < DWN_TT; tt += ngrp) {
+        const int t = t0 + tt;
+        if (t >= T) break;
+        float acc = bv;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) acc = fmaf(wk[k], dsm[(tt + k * dil) * CT + c], acc);
+        if (alpha_out) acc = snake_f(acc, ao);
+        put_hilo_nlc(out, C, (long long)b * T + t, c0 + c, acc);
+    }
+}
+
+// zero the two half-rows per utterance of the 2-tap im2col matrix that no producer writes:
+// row b*(T+1) cols [C, 2C) (tap 1 of q = 0) and row b*(T+1)+T cols [0, C) (tap 0 of q = T)
+__global__ void x2_zero_edges_kernel(__nv_bfloat16* __restrict__ x2, int T, int C) {
+    const int b = blockIdx.x;
+    const long long r0 = (long long)b * (T + 1), r1 = r0 + T;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const long long h0 = (r0 / 64) * 128 + (r0 % 64), h1 = (r1 / 64) * 128 + (r1 % 64);
+        const __nv_bfloat16 z = __float2bfloat16_rn(0.f);
+        x2[h0 * 2 * C + C + c] = z; x2[(h0 + 64) * 2 * C + C + c] = z;
+        x2[h1 * 2 * C + c] = z; x2[(h1 + 64) * 2 * C + c] = z;
+    }
+}
+
+// final Snake -> conv k7 (C -> 1) -> tanh in NLC (Layers.swift:411-415): 128 tokens per CTA, 2 threads per token
+constexpr int FN_TT = 128, FN_THREADS = 256, FN_MAXC = 64;
+__global__ void __launch_bounds__(FN_THREADS)
+final_nlc_kernel(const float* __restrict__ x, float* __restrict__ wave, const float* __restrict__ w /*[C,7]*/,
+                 const float* __restrict__ alpha, float bias, int T, int C) {
+    __shared__ float sx[(FN_TT + 6) * FN_MAXC];
+    __shared__ float sw[FN_MAXC * 7];
+    const int t0 = blockIdx.x * FN_TT, b = blockIdx.y;
+    const float* xb = x + (long long)b * T * C;
+    for (int i = threadIdx.x; i < (FN_TT + 6) * C; i += FN_THREADS) {
+        const int r = i / C, c = i - r * C;
+        const int t = t0 + r - 3;
+        sx[i] = (t >= 0 && t < T) ? snake_f(xb[(long long)t * C + c], alpha[c]) : 0.f;
+    }
+    for (int i = threadIdx.x; i < C * 7; i += FN_THREADS) sw[i] = w[i];
+    __syncthreads();
+    const int tt = threadIdx.x >> 1, hf = threadIdx.x & 1, lane = threadIdx.x & 31;
+    const int ch = C / 2;
+    float acc = 0.f;
+    for (int i = 0; i < ch; ++i) {
+        const int c = hf * ch + ((i + lane) % ch);      // rotate channels across lanes: conflict-free
+#pragma unroll
+        for (int k = 0; k < 7; ++k) acc = fmaf(sw[c * 7 + k], sx[(tt + k) * C + c], acc);
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    const int t = t0 + tt;
+    if (hf == 0 && t < T) wave[(long long)b * T + t] = tanhf(acc + bias);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Host-side model
 // ------------------------------------------------------------------------------------------------
 struct ConvW {       // folded weights on the device
@@ -349,12 +469,33 @@ struct ConvW {       // folded weights on the device
     bool has_bias = false;
 };
 
-struct ResUnit { DBuf<float> a0, a2; ConvW dw, pw; int dil; };
+// fp32 weight matrix [M, K] as two bf16 K-major operands (hi + lo) with their TMA maps
+struct TcW {
+    DBuf<__nv_bfloat16> hi, lo;
+    CUtensorMap th{}, tl{};
+    int M = 0, K = 0;
+    void build(const std::vector<float>& W, int M_, int K_) {
+        M = M_; K = K_;
+        std::vector<__nv_bfloat16> h((size_t)M * K), l((size_t)M * K);
+        for (size_t i = 0; i < h.size(); ++i) {
+            h[i] = __float2bfloat16_rn(W[i]);
+            l[i] = __float2bfloat16_rn(W[i] - __bfloat162float(h[i]));
+        }
+        hi.upload(h.data(), h.size());
+        lo.upload(l.data(), l.size());
+        B2A_CUDA(cudaDeviceSynchronize());
+        th = tc::make_tmap_bf16(hi.p, M, K, tc::BM);
+        tl = tc::make_tmap_bf16(lo.p, M, K, tc::BM);
+    }
+};
+
+struct ResUnit { DBuf<float> a0, a2; ConvW dw, pw; TcW pw_tc; int dil; };
 struct DecBlock {
     int cin, cout, stride, pad;
     DBuf<float> alpha;   // Snake before the transposed conv
     ConvW ct;            // A[(co*s+r), (tap*Cin+ci)]
     ConvW noise;         // [cout, cout], no bias
+    TcW ct_tc, noise_tc; // tensor-core operands: ct_tc rows are m = r*cout + co (phase-major)
     bool has_noise;
     ResUnit ru[3];
 };
@@ -395,6 +536,11 @@ struct b2a_snac {
     std::vector<Level> levels;
     // decoder
     ConvW dw0, pw0, conv0;   // depthwise: dw0 + pw0 ; otherwise conv0 (k7 dense, unsupported on device)
+    TcW pw0_tc;
+    bool use_tc = true;      // tcgen05 / NLC path (B2A_SNAC=simt selects the fp32 CUDA-core path)
+    int num_sms = 148;
+    DBuf<float> xs;                      // NLC fp32 activations of the current stage
+    DBuf<__nv_bfloat16> hA, x2;          // hi/lo tiles: GEMM input of the stage / 2-tap im2col of the next transposed conv
     std::vector<DecBlock> blocks;
     DBuf<float> alpha_final;
     ConvW final_conv;
@@ -449,6 +595,7 @@ struct b2a_snac {
             load_bias(tt, p + "0", latent, dw0);
             std::vector<float> w1 = fold_wn(tt, p + "1", C, 1, latent, true);
             pw0.w.upload(w1.data(), w1.size());
+            host_pw0 = w1;
             load_bias(tt, p + "1", C, pw0);
         }
         int li = 2;
@@ -470,12 +617,20 @@ struct b2a_snac {
                             A[((size_t)(co * s + r)) * (2 * B.cin) + tap * B.cin + ci] =
                                 wt[((size_t)ci * k + (r + tap * s)) * B.cout + co];
             B.ct.w.upload(A.data(), A.size());
+            {   // tensor-core operand: rows phase-major (m = r*cout + co) so a warp's 32 lanes write 32 consecutive channels
+                std::vector<float> At((size_t)B.cout * s * 2 * B.cin);
+                for (int co = 0; co < B.cout; ++co)
+                    for (int r = 0; r < s; ++r)
+                        memcpy(&At[((size_t)r * B.cout + co) * 2 * B.cin], &A[((size_t)co * s + r) * 2 * B.cin], (size_t)2 * B.cin * sizeof(float));
+                host_ct.push_back(At);
+            }
             load_bias(tt, b + "1", B.cout, B.ct);
             int j = 2;
             B.has_noise = c.noise != 0;
             if (B.has_noise) {
                 std::vector<float> wn_ = fold_wn(tt, b + "2.linear", B.cout, 1, B.cout, true);
                 B.noise.w.upload(wn_.data(), wn_.size());
+                host_noise.push_back(wn_);
                 j = 3;
             }
             const int dils[3] = {1, 3, 9};
@@ -491,6 +646,7 @@ struct b2a_snac {
                 load_bias(tt, r + "1", B.cout, R.dw);
                 std::vector<float> wp = fold_wn(tt, r + "3", B.cout, 1, B.cout, true);
                 R.pw.w.upload(wp.data(), wp.size());
+                host_pw.push_back(wp);
                 load_bias(tt, r + "3", B.cout, R.pw);
             }
         }
@@ -506,6 +662,116 @@ struct b2a_snac {
             if (tt.find(p + std::to_string(li + 1) + ".bias")) final_bias = tt.f32(p + std::to_string(li + 1) + ".bias", 1)[0];
         }
         B2A_CUDA(cudaStreamSynchronize(stream));
+        B2A_CUDA(cudaGetLastError());
+        B2A_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
+        const char* env = getenv("B2A_SNAC");
+        bool shapes_ok = latent % 64 == 0 && C % 64 == 0 && final_c <= FN_MAXC && final_c % 2 == 0 && c.noise != 0;
+        for (auto& B : blocks) shapes_ok = shapes_ok && B.cin % 64 == 0 && B.cout % 64 == 0;
+        use_tc = shapes_ok && !(env && std::string(env) == "simt");
+        if (use_tc) {
+            B2A_CUDA(cudaFuncSetAttribute(cg::conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cg::SMEM_BYTES));
+            B2A_CUDA(cudaFuncSetAttribute(dw7_nlc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            pw0_tc.build(host_pw0, C, latent);
+            size_t ip = 0;
+            for (size_t i = 0; i < blocks.size(); ++i) {
+                DecBlock& B = blocks[i];
+                B.ct_tc.build(host_ct[i], B.cout * B.stride, 2 * B.cin);
+                B.noise_tc.build(host_noise[i], B.cout, B.cout);
+                for (int u = 0; u < 3; ++u) B.ru[u].pw_tc.build(host_pw[ip++], B.cout, B.cout);
+            }
+        }
+        host_pw0.clear(); host_ct.clear(); host_noise.clear(); host_pw.clear();
+    }
+    std::vector<float> host_pw0;
+    std::vector<std::vector<float>> host_ct, host_noise, host_pw;
+
+    // ---- tensor-core / NLC decode --------------------------------------------------------------------------
+    void cgemm(const TcW& W, const __nv_bfloat16* X, long long x_rows, cg::Args a, cudaStream_t s) {
+        a.M = W.M; a.K = W.K;
+        a.m_tiles = cdiv(W.M, tc::BM); a.k_blocks = W.K / tc::BK; a.n_tiles = cdiv(a.N, cg::HALF);
+        const CUtensorMap tb = tc::make_tmap_bf16(X, x_rows, W.K, 128);
+        const long long tiles = (long long)a.n_tiles * a.m_tiles;
+        launch_pdl(cg::conv_gemm_kernel, dim3((unsigned)std::min<long long>(num_sms, tiles)), dim3(tc::THREADS), cg::SMEM_BYTES, s,
+                   W.th, W.tl, tb, a);
+    }
+    void dw_nlc(const ConvW& W, const float* xin, __nv_bfloat16* out, const float* a_in, const float* a_out, int batch, int T, int C,
+                int dil, cudaStream_t s) {
+        const int CT = std::min(C, 128);
+        const size_t sm = (size_t)(DWN_TT + 6 * dil) * CT * sizeof(float);
+        dw7_nlc_kernel<<<dim3(cdiv(T, DWN_TT), cdiv(C, CT), batch), DWN_THREADS, sm, s>>>(xin, out, W.w.p, W.has_bias ? W.bias.p : nullptr,
+                                                                                       a_in, a_out, T, C, CT, dil);
+        count_launch();
+    }
+    static long long pad64(long long n) { return (n + 63) / 64 * 64; }
+
+    void decode_dev_tc(const int* const* d_codes_in, int batch, long long T, const float* const* d_noise_in, int noise_mode,
+                       unsigned long long seed, float* d_wave_out, cudaStream_t s) {
+        const int C = cfg.decoder_dim;
+        // buffer sizes over all stages
+        size_t max_x = (size_t)batch * T * std::max(latent, C), max_h = (size_t)(2 * pad64((long long)batch * T)) * (size_t)std::max(latent, C), max_x2 = 0;
+        {
+            long long t = T;
+            for (auto& B : blocks) {
+                max_x2 = std::max<size_t>(max_x2, (size_t)(2 * pad64((long long)batch * (t + 1))) * 2 * B.cin);
+                t *= B.stride;
+                max_x = std::max<size_t>(max_x, (size_t)batch * t * B.cout);
+                max_h = std::max<size_t>(max_h, (size_t)(2 * pad64((long long)batch * t)) * B.cout);
+            }
+        }
+        xs.alloc(max_x); hA.alloc(max_h); x2.alloc(max_x2);
+        // RVQ lookup -> z (NLC) ; depthwise k7 -> hi/lo ; 1x1 (768 -> 1024) + Snake(block 0) -> 2-tap im2col of block 0
+        RvqArgs ra{};
+        ra.n_levels = (int)levels.size(); ra.D = cfg.codebook_dim; ra.C = latent; ra.T = (int)T; ra.codebook_size = cfg.codebook_size;
+        for (size_t i = 0; i < levels.size(); ++i)
+            ra.lv[i] = RvqLevel{d_codes_in[i], levels[i].codebook.p, levels[i].wout.p, levels[i].bout.p, levels[i].stride};
+        rvq_lookup_nlc_kernel<<<(unsigned)(batch * T), 256, 0, s>>>(ra, xs.p);
+        count_launch();
+        dw_nlc(dw0, xs.p, hA.p, nullptr, nullptr, batch, (int)T, latent, 1, s);
+        {
+            x2_zero_edges_kernel<<<batch, 256, 0, s>>>(x2.p, (int)T, C);
+            count_launch();
+            cg::Args a{};
+            a.N = (int)(batch * T); a.epi = cg::E_STORE_HILO; a.bias = pw0.has_bias ? pw0.bias.p : nullptr; a.alpha = blocks[0].alpha.p;
+            a.hl = x2.p; a.ldh = 2 * C; a.dual = 1; a.T = (int)T;
+            cgemm(pw0_tc, hA.p, 2 * pad64((long long)batch * T), a, s);
+        }
+        long long t = T;
+        for (size_t i = 0; i < blocks.size(); ++i) {
+            DecBlock& B = blocks[i];
+            const long long tout = t * B.stride, ntok = (long long)batch * tout;
+            {   // transposed conv: tokens (b, q), q = 0..t ; rows m = r*cout + co ; scatter to t_out = q*s + r - pad
+                cg::Args a{};
+                a.N = (int)(batch * (t + 1)); a.epi = cg::E_CONVT; a.bias = B.ct.has_bias ? B.ct.bias.p : nullptr;
+                a.x = xs.p; a.ldx = B.cout; a.hl = hA.p; a.ldh = B.cout; a.T = (int)tout; a.Cout = B.cout; a.stride = B.stride;
+                a.pad = B.pad; a.Tin = (int)t;
+                cgemm(B.ct_tc, x2.p, 2 * pad64((long long)batch * (t + 1)), a, s);
+            }
+            const float* nz = d_noise_in ? d_noise_in[i] : nullptr;
+            if (B.has_noise && (nz || noise_mode == 0)) {
+                cg::Args a{};
+                a.N = (int)ntok; a.epi = cg::E_NOISE; a.x = xs.p; a.ldx = B.cout; a.noise = nz;
+                a.seed = seed + 0x1000193ull * (i + 1); a.T = (int)tout;
+                cgemm(B.noise_tc, hA.p, 2 * pad64(ntok), a, s);
+            }
+            for (int u = 0; u < 3; ++u) {
+                ResUnit& R = B.ru[u];
+                dw_nlc(R.dw, xs.p, hA.p, R.a0.p, R.a2.p, batch, (int)tout, B.cout, R.dil, s);
+                cg::Args a{};
+                a.N = (int)ntok; a.bias = R.pw.has_bias ? R.pw.bias.p : nullptr; a.x = xs.p; a.ldx = B.cout; a.T = (int)tout;
+                if (u == 2 && i + 1 < blocks.size()) {
+                    x2_zero_edges_kernel<<<batch, 256, 0, s>>>(x2.p, (int)tout, B.cout);
+                    count_launch();
+                    a.epi = cg::E_ADD_HILO; a.alpha = blocks[i + 1].alpha.p; a.hl = x2.p; a.ldh = 2 * B.cout; a.dual = 1;
+                } else {
+                    a.epi = cg::E_ADD;
+                }
+                cgemm(R.pw_tc, hA.p, 2 * pad64(ntok), a, s);
+            }
+            t = tout;
+        }
+        final_nlc_kernel<<<dim3(cdiv(t, FN_TT), batch), FN_THREADS, 0, s>>>(xs.p, d_wave_out, final_conv.w.p, alpha_final.p, final_bias,
+                                                                            (int)t, final_c);
+        count_launch();
         B2A_CUDA(cudaGetLastError());
     }
 
@@ -547,6 +813,10 @@ struct b2a_snac {
             B2A_CHECK(T % L.stride == 0, B2A_ERR_INVALID_INPUT, "snac decode: t_latent must be a multiple of every vq stride");
         B2A_CHECK(T * hop < (1ll << 31) / 2, B2A_ERR_INVALID_INPUT, "snac decode: sequence too long");
         B2A_CUDA(cudaSetDevice(device));
+        if (use_tc && (long long)batch * T * hop < (1ll << 31) - 64) {
+            decode_dev_tc(d_codes_in, batch, T, d_noise_in, noise_mode, seed, d_wave_out, s);
+            return;
+        }
         const size_t need = max_act(batch, T);
         bufX.alloc(need);
         bufY.alloc(need);

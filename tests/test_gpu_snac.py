@@ -110,3 +110,21 @@ def test_rvq_code_search_larger_random(model):
         # identical to the ordered-fp32 oracle wherever the fp32 projection agrees; any mismatch must be a
         # genuine near-tie of the float64 search as well
         assert mism.size == 0 or np.array_equal(codes[i], ocodes64[i]), (i, mism[:5])
+
+
+def test_simt_fallback_path_matches_tensor_core_path(b2a, monkeypatch):
+    """B2A_SNAC=simt selects the fp32 CUDA-core (NCT) decoder; the default tcgen05 / NLC decoder (fp32 weights and
+    activations as bf16 hi/lo pairs) must agree with it and with the oracle."""
+    cfg = osnac.SNACConfig()
+    W = osnac.init_weights(cfg, 1234)
+    codes = osnac.synth_codes(cfg, 2, 24, seed=8)
+    rng = np.random.default_rng(3)
+    noise = [rng.standard_normal(s).astype(np.float32) for s in osnac.noise_shapes(cfg, 2, 24)]
+    tc = b2a.SNAC(weights=W)
+    monkeypatch.setenv("B2A_SNAC", "simt")
+    simt = b2a.SNAC(weights=W)
+    monkeypatch.delenv("B2A_SNAC")
+    a, c = tc.decode(codes, noise=noise), simt.decode(codes, noise=noise)
+    ref = osnac.decode(cfg, W, codes, noise)
+    assert max_rel_to_peak(a, ref) < TOL and max_rel_to_peak(c, ref) < TOL
+    assert max_rel_to_peak(a, c) < 1e-4
