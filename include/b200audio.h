@@ -254,6 +254,35 @@ int32_t b2a_tts_interleave(const int32_t* codes0, const int32_t* codes1, const i
                            int32_t n_frames, int32_t* code_list);
 void b2a_tts_destroy(b2a_tts* h);
 
+/* ------------------------------------------------------------------ Vocos vocoder
+ * Replaces class Vocos (Sources/MLXAudioCodecs/Vocos/Vocos.swift:284-322) behind AudioDecoderModel
+ * (Sources/MLXAudioCodecs/AudioCodecModel.swift:4-13):
+ *   Vocos(backbone:head:) + weights (keys backbone.* / head.*, MLX layouts) -> b2a_vocos_create
+ *   decode(_ features:) / decodeAudio (:302-306,318-320)                   -> b2a_vocos_decode
+ * features are [B, L, input_channels] float32 (the layout VocosBackbone expects, VocosBackbone.swift:170-175);
+ * the waveform is [B, (L-1)*hop_length] (ISTFTHead centre trim, Vocos.swift:150-158).  Only the LayerNorm variant
+ * (adanorm_num_embeddings == 0) is implemented.                                                    */
+typedef struct b2a_vocos_config {
+    int32_t input_channels;
+    int32_t dim;
+    int32_t intermediate_dim;
+    int32_t num_layers;
+    int32_t n_fft;
+    int32_t hop_length;
+    int32_t input_kernel_size;
+    int32_t dw_kernel_size;
+    int32_t adanorm_num_embeddings; /* must be 0 */
+} b2a_vocos_config;
+
+typedef struct b2a_vocos b2a_vocos;
+int32_t b2a_vocos_create(int32_t device, const b2a_vocos_config* cfg, const b2a_tensor* tensors, int32_t n_tensors,
+                         b2a_vocos** out);
+int64_t b2a_vocos_output_length(const b2a_vocos* h, int32_t frames);
+void* b2a_vocos_stream(b2a_vocos* h);
+int32_t b2a_vocos_decode(b2a_vocos* h, const float* features, int32_t batch, int32_t frames, float* wave);
+int32_t b2a_vocos_decode_dev(b2a_vocos* h, const float* d_features, int32_t batch, int32_t frames, float* d_wave, void* stream);
+void b2a_vocos_destroy(b2a_vocos* h);
+
 /* ------------------------------------------------------------------ Whisper STT
  * Replaces class WhisperModel (Sources/MLXAudioSTT/Models/Whisper/WhisperModel.swift:7-309) behind
  * STTGenerationModel (Sources/MLXAudioSTT/Generation.swift:52-64):

@@ -7,11 +7,12 @@ from ._ffi import AudioGenerationError
 from .dsp import IncrementalMelSpectrogram, LogMel, compute_mel_spectrogram, hanning_window, mel_filters, whisper_encoder_features
 from .snac import SNAC
 from .llama_tts import AudioGenerationInfo, GenerateParameters, LlamaTTSModel
+from .vocos import Vocos
 from .whisper import STTGenerateParameters, STTOutput, WhisperModel
 
 __all__ = ["AudioGenerationError", "IncrementalMelSpectrogram", "LogMel", "compute_mel_spectrogram", "hanning_window",
            "mel_filters", "whisper_encoder_features", "SNAC", "LlamaTTSModel", "GenerateParameters",
-           "AudioGenerationInfo", "WhisperModel", "STTGenerateParameters", "STTOutput"]
+           "AudioGenerationInfo", "Vocos", "WhisperModel", "STTGenerateParameters", "STTOutput"]
 
 
 def device_count() -> int:

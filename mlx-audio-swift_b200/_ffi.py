@@ -61,6 +61,11 @@ class GenInfo(C.Structure):
                 ("peak_memory_gb", C.c_double)]
 
 
+class VocosConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("input_channels", "dim", "intermediate_dim", "num_layers", "n_fft", "hop_length",
+                                          "input_kernel_size", "dw_kernel_size", "adanorm_num_embeddings")]
+
+
 class WhisperConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("vocab_size", "num_mel_bins", "d_model", "encoder_layers", "encoder_attention_heads",
                                           "encoder_ffn_dim", "max_source_positions", "decoder_layers", "decoder_attention_heads",
@@ -124,6 +129,12 @@ SIGNATURES = {
     "b2a_tts_deinterleave": (C.c_int32, [_P, C.c_int32, _P, _P, _P, C.POINTER(C.c_int32)]),
     "b2a_tts_interleave": (C.c_int32, [_P, _P, _P, C.c_int32, _P]),
     "b2a_tts_destroy": (None, [_P]),
+    "b2a_vocos_create": (C.c_int32, [C.c_int32, C.POINTER(VocosConfig), C.POINTER(Tensor), C.c_int32, C.POINTER(_P)]),
+    "b2a_vocos_output_length": (C.c_int64, [_P, C.c_int32]),
+    "b2a_vocos_stream": (C.c_void_p, [_P]),
+    "b2a_vocos_decode": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, _P]),
+    "b2a_vocos_decode_dev": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
+    "b2a_vocos_destroy": (None, [_P]),
     "b2a_stt_create": (C.c_int32, [C.c_int32, C.POINTER(WhisperConfig), C.POINTER(Tensor), C.c_int32, C.POINTER(_P)]),
     "b2a_stt_create_random": (C.c_int32, [C.c_int32, C.POINTER(WhisperConfig), C.c_float, C.c_uint64, C.POINTER(_P)]),
     "b2a_stt_stream": (C.c_void_p, [_P]),

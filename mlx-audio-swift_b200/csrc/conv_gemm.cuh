@@ -20,7 +20,7 @@ constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE = 2 * A_BYTES 
 constexpr int STAGES = 4;
 constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE + 256;
 
-enum : int { E_STORE_HILO = 0, E_CONVT = 1, E_NOISE = 2, E_ADD = 3, E_ADD_HILO = 4 };
+enum : int { E_STORE_HILO = 0, E_CONVT = 1, E_NOISE = 2, E_ADD = 3, E_ADD_HILO = 4, E_STORE_F32 = 5 };
 
 struct Args {
     int M, K, N;              // N = tokens (rows of X)
@@ -28,6 +28,8 @@ struct Args {
     int epi;
     const float* bias;        // [channels] (E_CONVT: per output channel co) or null
     const float* alpha;       // Snake alpha applied to values written as hi/lo (null = identity)
+    const float* gamma;       // nullable per-channel scale applied to (acc + bias) before any add (ConvNeXt layer scale)
+    int gelu;                 // exact-erf GELU on (acc + bias) (Vocos pwconv1)
     float* x;                 // fp32 [tokens, ldx] read-modify-write target (E_NOISE / E_ADD / E_ADD_HILO) or E_CONVT output
     int ldx;
     __nv_bfloat16* hl;        // hi/lo output matrix (64-token tiles), leading dimension ldh
@@ -62,7 +64,7 @@ __device__ __forceinline__ void put_hilo(__nv_bfloat16* base, long long ld, long
     base[(r + HALF) * ld + col] = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
+static __global__ void __launch_bounds__(THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmB, Args a) {
     extern __shared__ uint8_t smem_raw[];
@@ -140,12 +142,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int m = mt * BM + q * 32 + lane;
             const bool m_ok = m < a.M;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-            float bias = 0.f, al = 0.f;
+            float bias = 0.f, al = 0.f, gm = 1.f;
             int co = m, r = 0;
             if (a.epi == E_CONVT) { r = m / a.Cout; co = m - r * a.Cout; }
             if (m_ok) {
                 if (a.bias) bias = a.bias[co];
                 if (a.alpha) al = a.alpha[m];
+                if (a.gamma) gm = a.gamma[m];
             }
             for (int c0 = 0; c0 < HALF; c0 += 16) {
                 float v[16], w[16];
@@ -161,6 +164,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const long long n = (long long)nt * HALF + c0 + j;      // token (row of X)
                     if (n >= a.N || !m_ok) continue;
                     float val = v[j] + w[j] + bias;
+                    if (a.gelu) val = 0.5f * val * (1.0f + erff(val * 0.70710678118654752f));
+                    val *= gm;
+                    if (a.epi == E_STORE_F32) { a.x[n * a.ldx + m] = val; continue; }
                     if (a.epi == E_CONVT) {
                         const int b = (int)(n / (a.Tin + 1)), qq = (int)(n - (long long)b * (a.Tin + 1));
                         const int to = qq * a.stride + r - a.pad;

@@ -1,0 +1,341 @@
+// Vocos vocoder decode for sm_100a.  Replaces (reference paths):
+//   Sources/MLXAudioCodecs/Vocos/VocosBackbone.swift:18-100,109-204   ConvNeXt backbone
+//   Sources/MLXAudioCodecs/Vocos/Vocos.swift:54-179                    ISTFTHead (IRFFT on device + overlap-add in
+//                                                                      scalar host loops with per-frame D2H copies)
+//   Sources/MLXAudioCodecs/Vocos/Vocos.swift:284-322                   Vocos.decode / decodeAudio
+// Channels-last throughout (the reference's own layout).  Every Linear / dense conv -- embed conv (im2col), pwconv1/2,
+// the head projection AND the inverse real FFT (a [n_fft, n_fft+2] windowed-IDFT matrix) -- is the persistent
+// dual-operand tcgen05 GEMM of conv_gemm.cuh (fp32 weights and activations as bf16 hi/lo pairs).  Depthwise conv +
+// LayerNorm are one kernel; overlap-add is a gather (every output sample sums its <= n_fft/hop frames), so nothing
+// leaves the device and the result is deterministic.
+#include "common.cuh"
+#include "conv_gemm.cuh"
+
+#include <algorithm>
+#include <cmath>
+
+namespace b2a {
+namespace vc {
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ void put_hilo(bf16* base, long long ld, long long tok, long long col, float v) {
+    const bf16 hi = __float2bfloat16_rn(v);
+    const long long r = (tok / 64) * 128 + (tok % 64);
+    base[r * ld + col] = hi;
+    base[(r + 64) * ld + col] = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// k-tap im2col along time (zero padded, "same"): out row (b, t) = [x[t-k/2] | ... | x[t+k/2]] as hi/lo, Kp >= k*C
+__global__ void im2colk_kernel(const float* __restrict__ in, bf16* __restrict__ out, int L, int C, int k, int Kp) {
+    const long long tok = blockIdx.x;
+    const int b = (int)(tok / L), t = (int)(tok - (long long)b * L);
+    for (int i = threadIdx.x; i < Kp; i += blockDim.x) {
+        float v = 0.f;
+        if (i < k * C) {
+            const int kk = i / C, c = i - kk * C;
+            const int ti = t + kk - k / 2;
+            if (ti >= 0 && ti < L) v = in[((long long)b * L + ti) * C + c];
+        }
+        put_hilo(out, Kp, tok, i, v);
+    }
+}
+
+// block reduce helpers for one row per CTA
+template <int THREADS>
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    v = wsum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < THREADS / 32; ++i) t += red[i];
+    return t;
+}
+
+// (optional depthwise conv k over time) -> LayerNorm(eps) over channels.  One CTA per token, one thread per channel slot.
+// out_f32 (nullable): normalised row as fp32 (residual stream) ; out_hl (nullable): hi/lo tiles (GEMM input).
+constexpr int DL_THREADS = 256, DL_MAXV = 4;    // channels <= 1024
+__global__ void __launch_bounds__(DL_THREADS)
+dw_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ dw_w /*[C,k] or null*/, const float* __restrict__ dw_b,
+                    const float* __restrict__ ln_w, const float* __restrict__ ln_b, float* __restrict__ out_f32,
+                    bf16* __restrict__ out_hl, int L, int C, int k, float eps) {
+    __shared__ float red[DL_THREADS / 32];
+    const long long tok = blockIdx.x;
+    const int b = (int)(tok / L), t = (int)(tok - (long long)b * L);
+    float v[DL_MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < DL_MAXV; ++j) {
+        const int c = threadIdx.x + j * DL_THREADS;
+        float val = 0.f;
+        if (c < C) {
+            if (dw_w) {
+                val = dw_b ? dw_b[c] : 0.f;
+                for (int kk = 0; kk < k; ++kk) {
+                    const int ti = t + kk - k / 2;
+                    if (ti >= 0 && ti < L) val = fmaf(dw_w[c * k + kk], x[((long long)b * L + ti) * C + c], val);
+                }
+            } else {
+                val = x[tok * C + c];
+            }
+        }
+        v[j] = val;
+        s += val;
+    }
+    const float mean = block_sum<DL_THREADS>(s, red) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < DL_MAXV; ++j) {
+        const int c = threadIdx.x + j * DL_THREADS;
+        if (c < C) { const float d = v[j] - mean; q += d * d; }
+    }
+    const float r = rsqrtf(block_sum<DL_THREADS>(q, red) / (float)C + eps);
+#pragma unroll
+    for (int j = 0; j < DL_MAXV; ++j) {
+        const int c = threadIdx.x + j * DL_THREADS;
+        if (c < C) {
+            const float o = (v[j] - mean) * r * ln_w[c] + ln_b[c];
+            if (out_f32) out_f32[tok * C + c] = o;
+            if (out_hl) put_hilo(out_hl, C, tok, c, o);
+        }
+    }
+}
+
+// head projection output h [tokens, n_fft+2] -> [mag*cos | mag*sin] as hi/lo (Vocos.swift:75-90): mag = min(exp(.), 100)
+__global__ void spec_kernel(const float* __restrict__ h, bf16* __restrict__ out, int half, int Kp) {
+    const long long tok = blockIdx.x;
+    for (int i = threadIdx.x; i < Kp; i += blockDim.x) {
+        float v = 0.f;
+        if (i < 2 * half) {
+            const int kq = i < half ? i : i - half;
+            const float mag = fminf(expf(h[tok * 2 * half + kq]), 100.0f);
+            float sn, cs;
+            sincosf(h[tok * 2 * half + half + kq], &sn, &cs);
+            v = mag * (i < half ? cs : sn);
+        }
+        put_hilo(out, Kp, tok, i, v);
+    }
+}
+
+// overlap-add as a gather + window-sum normalisation + centre trim (Vocos.swift:123-160)
+__global__ void ola_kernel(const float* __restrict__ frames /*[B*L, n_fft] already windowed*/, const float* __restrict__ win,
+                           float* __restrict__ wave, int L, int n_fft, int hop, int out_len) {
+    const int b = blockIdx.y;
+    const int tp = blockIdx.x * blockDim.x + threadIdx.x;     // trimmed index
+    if (tp >= out_len) return;
+    const int t = tp + n_fft / 2;
+    int i1 = t / hop;
+    if (i1 > L - 1) i1 = L - 1;
+    float acc = 0.f, ws = 0.f;
+    for (int i = i1; i >= 0 && t - i * hop < n_fft; --i) {
+        const int j = t - i * hop;
+        acc += frames[((long long)b * L + i) * n_fft + j];
+        ws += win[j];
+    }
+    wave[(long long)b * out_len + tp] = ws != 0.f ? acc / ws : acc;
+}
+
+struct TcW {
+    DBuf<bf16> hi, lo;
+    DBuf<float> bias;
+    CUtensorMap th{}, tl{};
+    int M = 0, K = 0;
+    bool has_bias = false;
+    void build(const std::vector<float>& W, int M_, int K_) {
+        M = M_; K = K_;
+        std::vector<bf16> h((size_t)M * K), l((size_t)M * K);
+        for (size_t i = 0; i < h.size(); ++i) {
+            h[i] = __float2bfloat16_rn(W[i]);
+            l[i] = __float2bfloat16_rn(W[i] - __bfloat162float(h[i]));
+        }
+        hi.upload(h.data(), h.size());
+        lo.upload(l.data(), l.size());
+        B2A_CUDA(cudaDeviceSynchronize());
+        th = tc::make_tmap_bf16(hi.p, M, K, tc::BM);
+        tl = tc::make_tmap_bf16(lo.p, M, K, tc::BM);
+    }
+    void set_bias(const std::vector<float>& b) { bias.upload(b.data(), b.size()); has_bias = true; B2A_CUDA(cudaDeviceSynchronize()); }
+};
+
+struct Block { DBuf<float> dw_w, dw_b, ln_w, ln_b, gamma; TcW pw1, pw2; };
+
+}  // namespace vc
+}  // namespace b2a
+
+using namespace b2a;
+using namespace b2a::vc;
+
+struct b2a_vocos {
+    int device;
+    b2a_vocos_config cfg;
+    cudaStream_t stream = nullptr;
+    int num_sms = 148, kp_embed = 0, kp_spec = 0;
+    TcW embed, head, idft;
+    DBuf<float> n0_w, n0_b, nf_w, nf_b, win;
+    std::vector<Block> blocks;
+    // workspace
+    DBuf<float> feats, h, spec, frames, wave;
+    DBuf<bf16> xa, xb;
+
+    ~b2a_vocos() { if (stream) cudaStreamDestroy(stream); }
+    static long long pad64(long long n) { return (n + 63) / 64 * 64; }
+
+    b2a_vocos(int dev, const b2a_vocos_config& c, const TensorTable& tt) : device(dev), cfg(c) {
+        B2A_CHECK(c.dim % 64 == 0 && c.dim <= DL_THREADS * DL_MAXV && c.intermediate_dim % 64 == 0, B2A_ERR_INVALID_INPUT,
+                  "vocos: dim / intermediate_dim must be multiples of 64 (dim <= 1024)");
+        B2A_CHECK(c.n_fft % 2 == 0 && c.n_fft >= 16 && c.hop_length >= 1 && c.hop_length <= c.n_fft, B2A_ERR_INVALID_INPUT, "vocos: bad n_fft / hop_length");
+        B2A_CHECK(c.input_kernel_size % 2 == 1 && c.dw_kernel_size % 2 == 1 && c.dw_kernel_size <= 15, B2A_ERR_INVALID_INPUT, "vocos: kernel sizes must be odd");
+        B2A_CHECK(c.adanorm_num_embeddings == 0, B2A_ERR_INVALID_INPUT, "vocos: AdaLayerNorm (bandwidth-conditioned) models are not implemented");
+        require_device(dev);
+        B2A_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        B2A_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
+        B2A_CUDA(cudaFuncSetAttribute(cg::conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cg::SMEM_BYTES));
+        const int D = c.dim, I = c.intermediate_dim, Cin = c.input_channels, k = c.input_kernel_size, N = c.n_fft, half = N / 2 + 1;
+        // embed conv: MLX weight [out, k, in] is already [out, k*in + i]; pad K to a multiple of 64
+        kp_embed = (int)pad64((long long)k * Cin);
+        {
+            std::vector<float> w = tt.f32("backbone.embed.weight", (int64_t)D * k * Cin), wp((size_t)D * kp_embed, 0.f);
+            for (int o = 0; o < D; ++o) memcpy(&wp[(size_t)o * kp_embed], &w[(size_t)o * k * Cin], (size_t)k * Cin * sizeof(float));
+            embed.build(wp, D, kp_embed);
+            embed.set_bias(tt.f32("backbone.embed.bias", D));
+        }
+        auto up = [&](DBuf<float>& d, const std::string& name, int n) { std::vector<float> v = tt.f32(name, n); d.upload(v.data(), n); };
+        up(n0_w, "backbone.norm.weight", D); up(n0_b, "backbone.norm.bias", D);
+        up(nf_w, "backbone.final_layer_norm.weight", D); up(nf_b, "backbone.final_layer_norm.bias", D);
+        blocks.resize(c.num_layers);
+        for (int l = 0; l < c.num_layers; ++l) {
+            const std::string p = "backbone.convnext." + std::to_string(l) + ".";
+            Block& B = blocks[l];
+            up(B.dw_w, p + "dwconv.weight", D * c.dw_kernel_size);          // [dim, k, 1]
+            up(B.dw_b, p + "dwconv.bias", D);
+            up(B.ln_w, p + "norm.weight", D); up(B.ln_b, p + "norm.bias", D);
+            B.pw1.build(tt.f32(p + "pwconv1.weight", (int64_t)I * D), I, D); B.pw1.set_bias(tt.f32(p + "pwconv1.bias", I));
+            B.pw2.build(tt.f32(p + "pwconv2.weight", (int64_t)D * I), D, I); B.pw2.set_bias(tt.f32(p + "pwconv2.bias", D));
+            if (tt.find(p + "gamma")) up(B.gamma, p + "gamma", D);
+        }
+        head.build(tt.f32("head.out.weight", (int64_t)(N + 2) * D), N + 2, D);
+        head.set_bias(tt.f32("head.out.bias", N + 2));
+        // windowed inverse real DFT as a matrix: frame[j] = w[j]/N * (Re0 + (-1)^j Re_{N/2} + 2 sum_k (Re_k cos - Im_k sin))
+        kp_spec = (int)pad64(2 * half);
+        {
+            std::vector<float> wv(N), A((size_t)N * kp_spec, 0.f);
+            for (int j = 0; j < N; ++j) wv[j] = N == 1 ? 1.f : (float)(0.5 - 0.5 * std::cos(2.0 * M_PI * j / (N - 1)));   // Vocos.swift:170-178
+            for (int j = 0; j < N; ++j)
+                for (int kq = 0; kq < half; ++kq) {
+                    const double ang = 2.0 * M_PI * (double)((long long)j * kq % N) / N;
+                    const double ck = (kq == 0 || kq == N / 2) ? 1.0 : 2.0;
+                    A[(size_t)j * kp_spec + kq] = (float)(wv[j] * ck * std::cos(ang) / N);
+                    A[(size_t)j * kp_spec + half + kq] = (kq == 0 || kq == N / 2) ? 0.f : (float)(-wv[j] * 2.0 * std::sin(ang) / N);
+                }
+            idft.build(A, N, kp_spec);
+            win.upload(wv.data(), N);
+        }
+        B2A_CUDA(cudaDeviceSynchronize());
+    }
+
+    void cgemm(const TcW& W, const bf16* X, long long x_rows, cg::Args a, cudaStream_t s) {
+        a.M = W.M; a.K = W.K;
+        a.m_tiles = cdiv(W.M, tc::BM); a.k_blocks = W.K / tc::BK; a.n_tiles = cdiv(a.N, cg::HALF);
+        a.bias = W.has_bias ? W.bias.p : nullptr;
+        const CUtensorMap tb = tc::make_tmap_bf16(X, x_rows, W.K, 128);
+        const long long tiles = (long long)a.n_tiles * a.m_tiles;
+        launch_pdl(cg::conv_gemm_kernel, dim3((unsigned)std::min<long long>(num_sms, tiles)), dim3(tc::THREADS), cg::SMEM_BYTES, s,
+                   W.th, W.tl, tb, a);
+    }
+
+    long long out_len(int L) const { return (long long)(L - 1) * cfg.hop_length; }
+
+    // d_feats [B, L, input_channels] fp32 (device) -> d_wave [B, (L-1)*hop]
+    void decode_dev(const float* d_feats, int B, int L, float* d_wave, cudaStream_t s) {
+        B2A_CHECK(B >= 1 && L >= 2, B2A_ERR_INVALID_INPUT, "vocos decode: need at least 2 frames");
+        B2A_CUDA(cudaSetDevice(device));
+        const int D = cfg.dim, I = cfg.intermediate_dim, N = cfg.n_fft;
+        const long long T = (long long)B * L, Tp = pad64(T);
+        B2A_CHECK(T < (1ll << 30), B2A_ERR_INVALID_INPUT, "vocos decode: too many frames");
+        const size_t kmax = (size_t)std::max(std::max(kp_embed, I), std::max(D, kp_spec));
+        xa.alloc((size_t)2 * Tp * kmax); xb.alloc((size_t)2 * Tp * kmax);
+        h.alloc((size_t)T * D); spec.alloc((size_t)T * (N + 2)); frames.alloc((size_t)T * N);
+        // embed conv (im2col GEMM) -> LayerNorm -> residual stream h
+        im2colk_kernel<<<(unsigned)T, 256, 0, s>>>(d_feats, xa.p, L, cfg.input_channels, cfg.input_kernel_size, kp_embed);
+        count_launch();
+        {
+            cg::Args a{}; a.N = (int)T; a.epi = cg::E_STORE_F32; a.x = spec.p; a.ldx = D;      // spec doubles as scratch [T, D]
+            cgemm(embed, xa.p, 2 * Tp, a, s);
+        }
+        dw_layernorm_kernel<<<(unsigned)T, DL_THREADS, 0, s>>>(spec.p, nullptr, nullptr, n0_w.p, n0_b.p, h.p, nullptr, L, D, 1, 1e-6f);
+        count_launch();
+        for (auto& Bk : blocks) {
+            dw_layernorm_kernel<<<(unsigned)T, DL_THREADS, 0, s>>>(h.p, Bk.dw_w.p, Bk.dw_b.p, Bk.ln_w.p, Bk.ln_b.p, nullptr, xa.p, L, D,
+                                                                   cfg.dw_kernel_size, 1e-6f);
+            count_launch();
+            cg::Args a1{}; a1.N = (int)T; a1.epi = cg::E_STORE_HILO; a1.gelu = 1; a1.hl = xb.p; a1.ldh = I; a1.T = L;
+            cgemm(Bk.pw1, xa.p, 2 * Tp, a1, s);
+            cg::Args a2{}; a2.N = (int)T; a2.epi = cg::E_ADD; a2.x = h.p; a2.ldx = D; a2.gamma = Bk.gamma.p;      // h += gamma * pw2(...)
+            cgemm(Bk.pw2, xb.p, 2 * Tp, a2, s);
+        }
+        dw_layernorm_kernel<<<(unsigned)T, DL_THREADS, 0, s>>>(h.p, nullptr, nullptr, nf_w.p, nf_b.p, nullptr, xa.p, L, D, 1, 1e-6f);
+        count_launch();
+        {
+            cg::Args a{}; a.N = (int)T; a.epi = cg::E_STORE_F32; a.x = spec.p; a.ldx = N + 2;
+            cgemm(head, xa.p, 2 * Tp, a, s);
+        }
+        spec_kernel<<<(unsigned)T, 256, 0, s>>>(spec.p, xb.p, N / 2 + 1, kp_spec);
+        count_launch();
+        {
+            cg::Args a{}; a.N = (int)T; a.epi = cg::E_STORE_F32; a.x = frames.p; a.ldx = N;
+            cgemm(idft, xb.p, 2 * Tp, a, s);
+        }
+        const int ol = (int)out_len(L);
+        ola_kernel<<<dim3(cdiv(ol, 256), B), 256, 0, s>>>(frames.p, win.p, d_wave, L, N, cfg.hop_length, ol);
+        count_launch();
+        B2A_CUDA(cudaGetLastError());
+    }
+};
+
+extern "C" {
+
+int32_t b2a_vocos_create(int32_t device, const b2a_vocos_config* cfg, const b2a_tensor* tensors, int32_t n, b2a_vocos** out) {
+    return guarded([&] {
+        B2A_CHECK(out, B2A_ERR_INVALID_INPUT, "b2a_vocos_create: null out");
+        *out = nullptr;
+        B2A_CHECK(cfg && tensors && n > 0, B2A_ERR_MODEL_NOT_INITIALIZED, "b2a_vocos_create: missing config or weights");
+        TensorTable tt(tensors, n);
+        *out = new b2a_vocos(device, *cfg, tt);
+    });
+}
+
+int64_t b2a_vocos_output_length(const b2a_vocos* h, int32_t frames) { return h && frames >= 2 ? h->out_len(frames) : 0; }
+void* b2a_vocos_stream(b2a_vocos* h) { return h ? (void*)h->stream : nullptr; }
+
+int32_t b2a_vocos_decode_dev(b2a_vocos* h, const float* d_feats, int32_t B, int32_t L, float* d_wave, void* stream) {
+    return guarded([&] {
+        B2A_CHECK(h && d_feats && d_wave, B2A_ERR_INVALID_INPUT, "b2a_vocos_decode_dev: null argument");
+        h->decode_dev(d_feats, B, L, d_wave, stream ? (cudaStream_t)stream : h->stream);
+    });
+}
+
+int32_t b2a_vocos_decode(b2a_vocos* h, const float* feats, int32_t B, int32_t L, float* wave) {
+    return guarded([&] {
+        B2A_CHECK(h && feats && wave, B2A_ERR_INVALID_INPUT, "b2a_vocos_decode: null argument");
+        B2A_CHECK(B >= 1 && L >= 2, B2A_ERR_AUDIO_DECODING_FAILED, "b2a_vocos_decode: need at least 2 frames");
+        B2A_CUDA(cudaSetDevice(h->device));
+        cudaStream_t s = h->stream;
+        const size_t nin = (size_t)B * L * h->cfg.input_channels, nout = (size_t)B * h->out_len(L);
+        h->feats.alloc(nin); h->wave.alloc(nout);
+        B2A_CUDA(cudaMemcpyAsync(h->feats.p, feats, nin * sizeof(float), cudaMemcpyHostToDevice, s));
+        h->decode_dev(h->feats.p, B, L, h->wave.p, s);
+        B2A_CUDA(cudaMemcpyAsync(wave, h->wave.p, nout * sizeof(float), cudaMemcpyDeviceToHost, s));
+        B2A_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+void b2a_vocos_destroy(b2a_vocos* h) { delete h; }
+
+}  // extern "C"
