@@ -159,9 +159,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty[acc]);
                 }
+                // read-modify-write epilogues: issue all 16 loads of the chunk BEFORE any store (a store to x followed by
+                // a load from x would otherwise serialise every iteration on a full memory round trip)
+                const bool rmw = a.epi == E_NOISE || a.epi == E_ADD || a.epi == E_ADD_HILO;
+                const long long n_first = (long long)nt * HALF + c0;
+                float xv[16];
+                if (rmw) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) xv[j] = (m_ok && n_first + j < a.N) ? a.x[(n_first + j) * a.ldx + m] : 0.f;
+                }
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const long long n = (long long)nt * HALF + c0 + j;      // token (row of X)
+                    const long long n = n_first + j;      // token (row of X)
                     if (n >= a.N || !m_ok) continue;
                     float val = v[j] + w[j] + bias;
                     if (a.gelu) val = 0.5f * val * (1.0f + erff(val * 0.70710678118654752f));
@@ -178,14 +187,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                     if (a.epi == E_NOISE) {
                         const float nz = a.noise ? a.noise[n] : gauss(a.seed, (unsigned long long)n);
-                        float* px = a.x + n * a.ldx + m;
-                        *px = *px + nz * val;
+                        a.x[n * a.ldx + m] = xv[j] + nz * val;
                         continue;
                     }
-                    if (a.epi == E_ADD || a.epi == E_ADD_HILO) {
-                        float* px = a.x + n * a.ldx + m;
-                        val += *px;
-                        *px = val;
+                    if (rmw) {
+                        val += xv[j];
+                        a.x[n * a.ldx + m] = val;
                         if (a.epi == E_ADD) continue;
                     }
                     if (a.alpha) val = snake(val, al);

@@ -328,12 +328,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 } else {
                     float* pf = a.out_f32 + (long long)nt * a.ldo + m;
+                    if (epi == EPI_ADD) {     // residual accumulate (whole-tile CTAs only): all loads before any store
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (j < jn && j < nvalid && m_ok) v[j] += pf[(long long)j * a.ldo];
+                    }
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         if (j >= jn) break;
                         if (j < nvalid && m_ok) {
-                            if (epi == EPI_STORE) pf[0] = v[j];
-                            else if (epi == EPI_ADD) pf[0] += v[j];       // residual accumulate (whole-tile CTAs only)
+                            if (epi == EPI_STORE || epi == EPI_ADD) pf[0] = v[j];
                             else atomicAdd(pf, v[j]);
                         }
                         pf += a.ldo;
