@@ -283,6 +283,56 @@ int32_t b2a_vocos_decode(b2a_vocos* h, const float* features, int32_t batch, int
 int32_t b2a_vocos_decode_dev(b2a_vocos* h, const float* d_features, int32_t batch, int32_t frames, float* d_wave, void* stream);
 void b2a_vocos_destroy(b2a_vocos* h);
 
+/* ------------------------------------------------------------------ Encodec decode
+ * Replaces class Encodec's decode side (Sources/MLXAudioCodecs/Encodec/Encodec.swift:170-402) behind AudioCodecModel /
+ * AudioDecoderModel (Sources/MLXAudioCodecs/AudioCodecModel.swift:4-27, conformance at Encodec.swift:447-461):
+ *   Encodec(config:) + fromModelDirectory weights (:405-431; keys quantizer.layers.N.codebook.embed,
+ *     decoder.layers.N.{conv,lstm.L.{Wx,Wh,bias},block.{1,3}.conv,shortcut.conv}.*, MLX layouts:
+ *     Conv1d / ConvTranspose1d [out, k, in], LSTM [4H, in])                    -> b2a_encodec_create
+ *   decode(_ audioCodes:_ audioScales:paddingMask:) / decodeAudio (:366-402,458-460) -> b2a_encodec_decode
+ * audio_codes are [n_chunks, B, n_q, T] int32 (n_q <= the codebooks the checkpoint holds: the bandwidth chosen at encode
+ * time), audio_scales [n_chunks, B] float32 or NULL (nil scales); the waveform is [B, samples, audio_channels] with
+ * samples = b2a_encodec_output_length(n_chunks, T) (T*hop un-chunked; stride*(n_chunks-1) + T*hop with linearOverlapAdd).
+ * The padding-mask truncation (:397-399) is a host-side slice of the result.  The reference's fatalError on
+ * "Expected one frame" (:375-377) is B2A_ERR_AUDIO_DECODING_FAILED here.  Only norm_type "weight_norm" (plain folded
+ * conv weights, no norm layer: EncodecLayers.swift:133-137) is implemented; "time_group_norm" -> invalidInput. */
+typedef struct b2a_encodec_config {
+    int32_t audio_channels;
+    int32_t num_filters;
+    int32_t kernel_size;
+    int32_t num_residual_layers;
+    int32_t dilation_growth_rate;
+    int32_t codebook_size;
+    int32_t codebook_dim;
+    int32_t hidden_size;
+    int32_t num_lstm_layers;
+    int32_t residual_kernel_size;
+    int32_t use_causal_conv;
+    int32_t pad_mode_reflect;       /* 1 = "reflect" (clamped indices, EncodecLayers.swift:160-186), 0 = zero padding */
+    int32_t norm_type;              /* 0 = weight_norm; anything else -> invalidInput */
+    int32_t last_kernel_size;
+    int32_t compress;
+    int32_t n_upsampling_ratios;
+    int32_t upsampling_ratios[8];
+    int32_t sampling_rate;
+    int32_t use_conv_shortcut;
+    float trim_right_ratio;
+    float chunk_length_s;           /* <= 0: nil (one frame) */
+    float overlap;                  /* < 0: nil */
+} b2a_encodec_config;
+
+typedef struct b2a_encodec b2a_encodec;
+int32_t b2a_encodec_create(int32_t device, const b2a_encodec_config* cfg, const b2a_tensor* tensors, int32_t n_tensors,
+                           b2a_encodec** out);
+int64_t b2a_encodec_output_length(const b2a_encodec* h, int32_t n_chunks, int32_t frames);
+int32_t b2a_encodec_num_codebooks(const b2a_encodec* h);
+void* b2a_encodec_stream(b2a_encodec* h);
+int32_t b2a_encodec_decode(b2a_encodec* h, const int32_t* audio_codes, int32_t n_chunks, int32_t batch, int32_t n_q,
+                           int32_t frames, const float* audio_scales, float* wave);
+int32_t b2a_encodec_decode_dev(b2a_encodec* h, const int32_t* d_audio_codes, int32_t n_chunks, int32_t batch, int32_t n_q,
+                               int32_t frames, const float* d_audio_scales, float* d_wave, void* stream);
+void b2a_encodec_destroy(b2a_encodec* h);
+
 /* ------------------------------------------------------------------ Whisper STT
  * Replaces class WhisperModel (Sources/MLXAudioSTT/Models/Whisper/WhisperModel.swift:7-309) behind
  * STTGenerationModel (Sources/MLXAudioSTT/Generation.swift:52-64):

@@ -8,11 +8,12 @@ from .dsp import IncrementalMelSpectrogram, LogMel, compute_mel_spectrogram, han
 from .snac import SNAC
 from .llama_tts import AudioGenerationInfo, GenerateParameters, LlamaTTSModel
 from .vocos import Vocos
+from .encodec import Encodec, EncodecConfig, EncodecEncodedAudio
 from .whisper import STTGenerateParameters, STTOutput, WhisperModel
 
 __all__ = ["AudioGenerationError", "IncrementalMelSpectrogram", "LogMel", "compute_mel_spectrogram", "hanning_window",
            "mel_filters", "whisper_encoder_features", "SNAC", "LlamaTTSModel", "GenerateParameters",
-           "AudioGenerationInfo", "Vocos", "WhisperModel", "STTGenerateParameters", "STTOutput"]
+           "AudioGenerationInfo", "Vocos", "Encodec", "EncodecConfig", "EncodecEncodedAudio", "WhisperModel", "STTGenerateParameters", "STTOutput"]
 
 
 def device_count() -> int:

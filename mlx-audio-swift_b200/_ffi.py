@@ -66,6 +66,15 @@ class VocosConfig(C.Structure):
                                           "input_kernel_size", "dw_kernel_size", "adanorm_num_embeddings")]
 
 
+class EncodecConfig(C.Structure):
+    _fields_ = ([(n, C.c_int32) for n in ("audio_channels", "num_filters", "kernel_size", "num_residual_layers",
+                                           "dilation_growth_rate", "codebook_size", "codebook_dim", "hidden_size",
+                                           "num_lstm_layers", "residual_kernel_size", "use_causal_conv", "pad_mode_reflect",
+                                           "norm_type", "last_kernel_size", "compress", "n_upsampling_ratios")]
+                + [("upsampling_ratios", C.c_int32 * 8), ("sampling_rate", C.c_int32), ("use_conv_shortcut", C.c_int32),
+                   ("trim_right_ratio", C.c_float), ("chunk_length_s", C.c_float), ("overlap", C.c_float)])
+
+
 class WhisperConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("vocab_size", "num_mel_bins", "d_model", "encoder_layers", "encoder_attention_heads",
                                           "encoder_ffn_dim", "max_source_positions", "decoder_layers", "decoder_attention_heads",
@@ -135,6 +144,13 @@ SIGNATURES = {
     "b2a_vocos_decode": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, _P]),
     "b2a_vocos_decode_dev": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
     "b2a_vocos_destroy": (None, [_P]),
+    "b2a_encodec_create": (C.c_int32, [C.c_int32, C.POINTER(EncodecConfig), C.POINTER(Tensor), C.c_int32, C.POINTER(_P)]),
+    "b2a_encodec_output_length": (C.c_int64, [_P, C.c_int32, C.c_int32]),
+    "b2a_encodec_num_codebooks": (C.c_int32, [_P]),
+    "b2a_encodec_stream": (C.c_void_p, [_P]),
+    "b2a_encodec_decode": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "b2a_encodec_decode_dev": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),
+    "b2a_encodec_destroy": (None, [_P]),
     "b2a_stt_create": (C.c_int32, [C.c_int32, C.POINTER(WhisperConfig), C.POINTER(Tensor), C.c_int32, C.POINTER(_P)]),
     "b2a_stt_create_random": (C.c_int32, [C.c_int32, C.POINTER(WhisperConfig), C.c_float, C.c_uint64, C.POINTER(_P)]),
     "b2a_stt_stream": (C.c_void_p, [_P]),
