@@ -18,6 +18,12 @@ using namespace b2a::tc;
 constexpr int BN = 128, HALF = 64;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE = 2 * A_BYTES + B_BYTES;   // 48 KB
 constexpr int STAGES = 4;
+// warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..17: epilogue.  Sixteen epilogue warps = four per
+// scheduler: the epilogue math (Snake, GELU, hi/lo split) is dependent-issue latency bound with one warp per scheduler
+// (measured: 20 us per 64-token tile with 4 warps).  Warp w drains TMEM lane quadrant w % 4 (hardware rule) and the
+// 16-token column group (w - 2) / 4.
+constexpr int EPI_WARPS = 16;
+constexpr int CG_THREADS = 64 + 32 * EPI_WARPS;
 constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE + 256;
 
 enum : int { E_STORE_HILO = 0, E_CONVT = 1, E_NOISE = 2, E_ADD = 3, E_ADD_HILO = 4, E_STORE_F32 = 5 };
@@ -44,8 +50,16 @@ struct Args {
     unsigned long long seed;
 };
 
+// sin with an explicit two-term 2*pi range reduction + MUFU.SIN: |error| < 5e-7 for |x| < 1e4 (the libdevice sinf slow
+// path costs ~40 dependent instructions per call and made every Snake epilogue issue bound)
+__device__ __forceinline__ float fast_sin(float x) {
+    const float k = rintf(x * 0.15915494309189535f);
+    float r = fmaf(k, -6.28318548202514648f, x);
+    r = fmaf(k, 1.7484555e-7f, r);
+    return __sinf(r);
+}
 __device__ __forceinline__ float snake(float v, float al) {
-    const float s = sinf(al * v);
+    const float s = fast_sin(al * v);
     return v + (1.0f / (al + 1e-9f)) * s * s;
 }
 __device__ __forceinline__ float gauss(unsigned long long seed, unsigned long long idx) {
@@ -64,7 +78,7 @@ __device__ __forceinline__ void put_hilo(__nv_bfloat16* base, long long ld, long
     base[(r + HALF) * ld + col] = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
 
-static __global__ void __launch_bounds__(THREADS, 1)
+static __global__ void __launch_bounds__(CG_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmB, Args a) {
     extern __shared__ uint8_t smem_raw[];
@@ -79,7 +93,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB);
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<256>(tmem_slot);
@@ -133,15 +147,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
     } else {
-        const int q = warp & 3;
+        const int q = warp & 3, c0 = ((warp - 2) >> 2) * 16;
         int acc = 0; uint32_t acc_phase = 0;
+        const bool rmw = a.epi == E_NOISE || a.epi == E_ADD || a.epi == E_ADD_HILO;
         for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
             const int nt = (int)(t / a.m_tiles), mt = (int)(t - (long long)nt * a.m_tiles);
-            mbar_wait(&tfull[acc], acc_phase);
-            tc_fence_after();
             const int m = mt * BM + q * 32 + lane;
             const bool m_ok = m < a.M;
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
             float bias = 0.f, al = 0.f, gm = 1.f;
             int co = m, r = 0;
             if (a.epi == E_CONVT) { r = m / a.Cout; co = m - r * a.Cout; }
@@ -150,60 +162,64 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (a.alpha) al = a.alpha[m];
                 if (a.gamma) gm = a.gamma[m];
             }
-            for (int c0 = 0; c0 < HALF; c0 += 16) {
-                float v[16], w[16];
-                tmem_ld16(taddr + c0, v);
-                tmem_ld16(taddr + c0 + HALF, w);
-                if (c0 + 16 >= HALF) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty[acc]);
+            const long long n_first = (long long)nt * HALF + c0;
+            // everything that does not depend on the accumulator is fetched BEFORE waiting for the MMA: the residual /
+            // read-modify-write operand (16 independent loads) and the NoiseBlock noise (one value per token: lane j computes
+            // or loads token j, broadcast by shuffle below)
+            float xv[16];
+            if (rmw) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) xv[j] = (m_ok && n_first + j < a.N) ? a.x[(n_first + j) * a.ldx + m] : 0.f;
+            }
+            float nz_lane = 0.f;
+            if (a.epi == E_NOISE) {
+                const long long n = n_first + (lane & 15);
+                if (n < a.N) nz_lane = a.noise ? a.noise[n] : gauss(a.seed, (unsigned long long)n);
+            }
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+            float v[16], w[16];
+            tmem_ld16(taddr + c0, v);
+            tmem_ld16(taddr + c0 + HALF, w);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const long long n = n_first + j;      // token (row of X)
+                const float nz = a.epi == E_NOISE ? __shfl_sync(0xffffffffu, nz_lane, j) : 0.f;
+                if (n >= a.N || !m_ok) continue;
+                float val = v[j] + w[j] + bias;
+                if (a.gelu) val = 0.5f * val * (1.0f + erff(val * 0.70710678118654752f));
+                val *= gm;
+                if (a.epi == E_STORE_F32) { a.x[n * a.ldx + m] = val; continue; }
+                if (a.epi == E_CONVT) {
+                    const int b = (int)(n / (a.Tin + 1)), qq = (int)(n - (long long)b * (a.Tin + 1));
+                    const int to = qq * a.stride + r - a.pad;
+                    if (to < 0 || to >= a.T) continue;
+                    const long long tok = (long long)b * a.T + to;
+                    a.x[tok * a.ldx + co] = val;
+                    if (a.hl) put_hilo(a.hl, a.ldh, tok, co, val);
+                    continue;
                 }
-                // read-modify-write epilogues: issue all 16 loads of the chunk BEFORE any store (a store to x followed by
-                // a load from x would otherwise serialise every iteration on a full memory round trip)
-                const bool rmw = a.epi == E_NOISE || a.epi == E_ADD || a.epi == E_ADD_HILO;
-                const long long n_first = (long long)nt * HALF + c0;
-                float xv[16];
+                if (a.epi == E_NOISE) {
+                    a.x[n * a.ldx + m] = xv[j] + nz * val;
+                    continue;
+                }
                 if (rmw) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) xv[j] = (m_ok && n_first + j < a.N) ? a.x[(n_first + j) * a.ldx + m] : 0.f;
+                    val += xv[j];
+                    a.x[n * a.ldx + m] = val;
+                    if (a.epi == E_ADD) continue;
                 }
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const long long n = n_first + j;      // token (row of X)
-                    if (n >= a.N || !m_ok) continue;
-                    float val = v[j] + w[j] + bias;
-                    if (a.gelu) val = 0.5f * val * (1.0f + erff(val * 0.70710678118654752f));
-                    val *= gm;
-                    if (a.epi == E_STORE_F32) { a.x[n * a.ldx + m] = val; continue; }
-                    if (a.epi == E_CONVT) {
-                        const int b = (int)(n / (a.Tin + 1)), qq = (int)(n - (long long)b * (a.Tin + 1));
-                        const int to = qq * a.stride + r - a.pad;
-                        if (to < 0 || to >= a.T) continue;
-                        const long long tok = (long long)b * a.T + to;
-                        a.x[tok * a.ldx + co] = val;
-                        put_hilo(a.hl, a.ldh, tok, co, val);
-                        continue;
-                    }
-                    if (a.epi == E_NOISE) {
-                        const float nz = a.noise ? a.noise[n] : gauss(a.seed, (unsigned long long)n);
-                        a.x[n * a.ldx + m] = xv[j] + nz * val;
-                        continue;
-                    }
-                    if (rmw) {
-                        val += xv[j];
-                        a.x[n * a.ldx + m] = val;
-                        if (a.epi == E_ADD) continue;
-                    }
-                    if (a.alpha) val = snake(val, al);
-                    if (a.dual) {
-                        const long long b = n / a.T, tt = n - b * a.T;
-                        const long long row = b * (a.T + 1) + tt;
-                        put_hilo(a.hl, a.ldh, row, m, val);
-                        put_hilo(a.hl, a.ldh, row + 1, a.M + m, val);
-                    } else {
-                        put_hilo(a.hl, a.ldh, n, m, val);
-                    }
+                if (a.alpha) val = snake(val, al);
+                if (a.dual) {
+                    const long long b = n / a.T, tt = n - b * a.T;
+                    const long long row = b * (a.T + 1) + tt;
+                    put_hilo(a.hl, a.ldh, row, m, val);
+                    put_hilo(a.hl, a.ldh, row + 1, a.M + m, val);
+                } else {
+                    put_hilo(a.hl, a.ldh, n, m, val);
                 }
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }

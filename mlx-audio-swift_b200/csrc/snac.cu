@@ -15,6 +15,7 @@
 // depthwise conv), the residual add / noise injection into the GEMM epilogue.
 #include "common.cuh"
 #include "conv_gemm.cuh"
+#include "snac_fused.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -24,7 +25,12 @@ namespace b2a {
 
 __device__ __forceinline__ float snake_f(float x, float alpha) {
     // Layers.swift:44-50: x + 1/(alpha + 1e-9) * sin(alpha*x)^2
-    const float s = sinf(alpha * x);
+    // explicit 2*pi range reduction + MUFU.SIN (|error| < 5e-7): libdevice sinf is ~40 dependent instructions per call
+    const float ax = alpha * x;
+    const float k = rintf(ax * 0.15915494309189535f);
+    float r = fmaf(k, -6.28318548202514648f, ax);
+    r = fmaf(k, 1.7484555e-7f, r);
+    const float s = __sinf(r);
     return x + (1.0f / (alpha + 1e-9f)) * s * s;
 }
 
@@ -380,42 +386,70 @@ __global__ void rvq_lookup_nlc_kernel(RvqArgs a, float* __restrict__ out) {
 }
 
 // Depthwise conv k7 (dilation d) along time in NLC, optional Snake before / after, output as bf16 hi/lo tiles.
-// CTA = 64 tokens (+ halo) x CT channels; the Snake'd input tile lives in shared memory (sin once per element).
-constexpr int DWN_TT = 64, DWN_THREADS = 256;
+// CTA = 128 tokens (+ halo) x CT <= 64 channels; the Snake'd input tile lives in shared memory (sin once per element,
+// halo overhead 1.42x at dilation 9); float4 global loads, one channel PAIR per thread so hi and lo leave as bf16x2.
+// C must be even (every SNAC width is a multiple of 64); C % 4 == 0 takes the vector load path.
+constexpr int DWN_TT = 128, DWN_THREADS = 256;
 __global__ void __launch_bounds__(DWN_THREADS)
 dw7_nlc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, const float* __restrict__ w /*[C,7]*/,
                const float* __restrict__ bias, const float* __restrict__ alpha_in, const float* __restrict__ alpha_out,
                int T, int C, int CT, int dil) {
-    extern __shared__ float dsm[];     // [(64 + 6*dil)][CT]
+    extern __shared__ __align__(16) float dsm[];     // [(128 + 6*dil)][CT]
     const int t0 = blockIdx.x * DWN_TT, c0 = blockIdx.y * CT, b = blockIdx.z;
     const int halo = 3 * dil, rows = DWN_TT + 2 * halo;
     const float* xb = x + (long long)b * T * C;
-    for (int i = threadIdx.x; i < rows * CT; i += DWN_THREADS) {
-        const int r = i / CT, c = i - r * CT;
-        const int t = t0 + r - halo;
-        float v = 0.f;
-        if (t >= 0 && t < T && c0 + c < C) {
-            v = xb[(long long)t * C + c0 + c];
-            if (alpha_in) v = snake_f(v, alpha_in[c0 + c]);
+    if ((C & 3) == 0 && (CT & 3) == 0) {
+        const int cq = CT >> 2;
+        for (int i = threadIdx.x; i < rows * cq; i += DWN_THREADS) {
+            const int r = i / cq, c = (i - r * cq) * 4;
+            const int t = t0 + r - halo;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t >= 0 && t < T && c0 + c < C) {
+                v = *reinterpret_cast<const float4*>(xb + (long long)t * C + c0 + c);
+                if (alpha_in) {
+                    const float4 al = *reinterpret_cast<const float4*>(alpha_in + c0 + c);
+                    v.x = snake_f(v.x, al.x); v.y = snake_f(v.y, al.y); v.z = snake_f(v.z, al.z); v.w = snake_f(v.w, al.w);
+                }
+            }
+            *reinterpret_cast<float4*>(dsm + (size_t)r * CT + c) = v;
         }
-        dsm[i] = v;
+    } else {
+        for (int i = threadIdx.x; i < rows * CT; i += DWN_THREADS) {
+            const int r = i / CT, c = i - r * CT;
+            const int t = t0 + r - halo;
+            float v = 0.f;
+            if (t >= 0 && t < T && c0 + c < C) {
+                v = xb[(long long)t * C + c0 + c];
+                if (alpha_in) v = snake_f(v, alpha_in[c0 + c]);
+            }
+            dsm[i] = v;
+        }
     }
     __syncthreads();
-    const int c = threadIdx.x % CT, grp = threadIdx.x / CT, ngrp = DWN_THREADS / CT;
+    const int hp = CT >> 1;                                    // channel pairs per row
+    const int c = (threadIdx.x % hp) * 2, grp = threadIdx.x / hp, ngrp = DWN_THREADS / hp;
     if (c0 + c >= C) return;
-    float wk[7];
+    float wa[7], wb[7];
 #pragma unroll
-    for (int k = 0; k < 7; ++k) wk[k] = w[(c0 + c) * 7 + k];
-    const float bv = bias ? bias[c0 + c] : 0.f;
-    const float ao = alpha_out ? alpha_out[c0 + c] : 0.f;
+    for (int k = 0; k < 7; ++k) { wa[k] = w[(c0 + c) * 7 + k]; wb[k] = w[(c0 + c + 1) * 7 + k]; }
+    const float ba = bias ? bias[c0 + c] : 0.f, bb = bias ? bias[c0 + c + 1] : 0.f;
+    const float aoa = alpha_out ? alpha_out[c0 + c] : 0.f, aob = alpha_out ? alpha_out[c0 + c + 1] : 0.f;
     for (int tt = grp; tt < DWN_TT; tt += ngrp) {
         const int t = t0 + tt;
         if (t >= T) break;
-        float acc = bv;
+        float va = ba, vb = bb;
 #pragma unroll
-        for (int k = 0; k < 7; ++k) acc = fmaf(wk[k], dsm[(tt + k * dil) * CT + c], acc);
-        if (alpha_out) acc = snake_f(acc, ao);
-        put_hilo_nlc(out, C, (long long)b * T + t, c0 + c, acc);
+        for (int k = 0; k < 7; ++k) {
+            const float2 xv = *reinterpret_cast<const float2*>(dsm + (size_t)(tt + k * dil) * CT + c);
+            va = fmaf(wa[k], xv.x, va); vb = fmaf(wb[k], xv.y, vb);
+        }
+        if (alpha_out) { va = snake_f(va, aoa); vb = snake_f(vb, aob); }
+        const long long tok = (long long)b * T + t;
+        const long long r = (tok / 64) * 128 + (tok % 64);
+        const __nv_bfloat162 hi = __floats2bfloat162_rn(va, vb);
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(va - __low2float(hi), vb - __high2float(hi));
+        *reinterpret_cast<__nv_bfloat162*>(out + r * C + c0 + c) = hi;
+        *reinterpret_cast<__nv_bfloat162*>(out + (r + 64) * C + c0 + c) = lo;
     }
 }
 
@@ -539,7 +573,8 @@ struct b2a_snac {
     TcW pw0_tc;
     bool use_tc = true;      // tcgen05 / NLC path (B2A_SNAC=simt selects the fp32 CUDA-core path)
     int num_sms = 148;
-    DBuf<float> xs;                      // NLC fp32 activations of the current stage
+    DBuf<float> xs, xs2;                 // NLC fp32 activations of the current stage (ping-pong for the fused units)
+    bool use_fused = true;               // fused ResidualUnit / NoiseBlock kernel for C <= 128 (B2A_SNAC_FUSED=0 disables)
     DBuf<__nv_bfloat16> hA, x2;          // hi/lo tiles: GEMM input of the stage / 2-tap im2col of the next transposed conv
     std::vector<DecBlock> blocks;
     DBuf<float> alpha_final;
@@ -671,6 +706,12 @@ struct b2a_snac {
         if (use_tc) {
             B2A_CUDA(cudaFuncSetAttribute(cg::conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cg::SMEM_BYTES));
             B2A_CUDA(cudaFuncSetAttribute(dw7_nlc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            B2A_CUDA(cudaFuncSetAttribute(rf::ru_fused_kernel<rf::MODE_RU, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            B2A_CUDA(cudaFuncSetAttribute(rf::ru_fused_kernel<rf::MODE_RU, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            B2A_CUDA(cudaFuncSetAttribute(rf::ru_fused_kernel<rf::MODE_RU, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            B2A_CUDA(cudaFuncSetAttribute(rf::ru_fused_kernel<rf::MODE_NOISE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            const char* ef = getenv("B2A_SNAC_FUSED");
+            use_fused = !(ef && std::string(ef) == "0");
             pw0_tc.build(host_pw0, C, latent);
             size_t ip = 0;
             for (size_t i = 0; i < blocks.size(); ++i) {
@@ -691,18 +732,38 @@ struct b2a_snac {
         a.m_tiles = cdiv(W.M, tc::BM); a.k_blocks = W.K / tc::BK; a.n_tiles = cdiv(a.N, cg::HALF);
         const CUtensorMap tb = tc::make_tmap_bf16(X, x_rows, W.K, 128);
         const long long tiles = (long long)a.n_tiles * a.m_tiles;
-        launch_pdl(cg::conv_gemm_kernel, dim3((unsigned)std::min<long long>(num_sms, tiles)), dim3(tc::THREADS), cg::SMEM_BYTES, s,
+        launch_pdl(cg::conv_gemm_kernel, dim3((unsigned)std::min<long long>(num_sms, tiles)), dim3(cg::CG_THREADS), cg::SMEM_BYTES, s,
                    W.th, W.tl, tb, a);
     }
     void dw_nlc(const ConvW& W, const float* xin, __nv_bfloat16* out, const float* a_in, const float* a_out, int batch, int T, int C,
                 int dil, cudaStream_t s) {
-        const int CT = std::min(C, 128);
+        const int CT = std::min(C, 64);
+        B2A_CHECK(C % 2 == 0 && (C <= 64 || C % 64 == 0), B2A_ERR_INVALID_INPUT, "snac: channel widths must be even (multiples of 64 above 64)");
         const size_t sm = (size_t)(DWN_TT + 6 * dil) * CT * sizeof(float);
         dw7_nlc_kernel<<<dim3(cdiv(T, DWN_TT), cdiv(C, CT), batch), DWN_THREADS, sm, s>>>(xin, out, W.w.p, W.has_bias ? W.bias.p : nullptr,
                                                                                        a_in, a_out, T, C, CT, dil);
         count_launch();
     }
     static long long pad64(long long n) { return (n + 63) / 64 * 64; }
+    bool fused_ok(int C, int dil) const {
+        return use_fused && (C == 64 || C == 128) && rf::smem_bytes(C, dil, rf::MODE_RU) <= 227 * 1024;
+    }
+    bool block_fused(const DecBlock& B) const {
+        bool ok = fused_ok(B.cout, 9);
+        for (int u = 0; u < 3; ++u) ok = ok && (B.ru[u].dil == 1 || B.ru[u].dil == 3 || B.ru[u].dil == 9);
+        return ok;
+    }
+    void fused(const TcW& W, rf::Args a, int batch, long long T, cudaStream_t s) {
+        a.B = batch; a.T = (int)T;
+        a.tiles_per_utt = cdiv(T, rf::TOK); a.n_tiles = (long long)batch * a.tiles_per_utt;
+        const long long ctas = std::min<long long>(num_sms, (a.n_tiles + rf::TEAMS - 1) / rf::TEAMS);
+        const size_t sm = rf::smem_bytes(a.C, a.dil, a.mode);
+        const dim3 g((unsigned)ctas), bl(rf::THREADS);
+        if (a.mode == rf::MODE_NOISE) launch_pdl(rf::ru_fused_kernel<rf::MODE_NOISE, 0>, g, bl, sm, s, W.th, W.tl, a);
+        else if (a.dil == 1) launch_pdl(rf::ru_fused_kernel<rf::MODE_RU, 1>, g, bl, sm, s, W.th, W.tl, a);
+        else if (a.dil == 3) launch_pdl(rf::ru_fused_kernel<rf::MODE_RU, 3>, g, bl, sm, s, W.th, W.tl, a);
+        else launch_pdl(rf::ru_fused_kernel<rf::MODE_RU, 9>, g, bl, sm, s, W.th, W.tl, a);
+    }
 
     void decode_dev_tc(const int* const* d_codes_in, int batch, long long T, const float* const* d_noise_in, int noise_mode,
                        unsigned long long seed, float* d_wave_out, cudaStream_t s) {
@@ -718,7 +779,7 @@ struct b2a_snac {
                 max_h = std::max<size_t>(max_h, (size_t)(2 * pad64((long long)batch * t)) * B.cout);
             }
         }
-        xs.alloc(max_x); hA.alloc(max_h); x2.alloc(max_x2);
+        xs.alloc(max_x); xs2.alloc(max_x); hA.alloc(max_h); x2.alloc(max_x2);
         // RVQ lookup -> z (NLC) ; depthwise k7 -> hi/lo ; 1x1 (768 -> 1024) + Snake(block 0) -> 2-tap im2col of block 0
         RvqArgs ra{};
         ra.n_levels = (int)levels.size(); ra.D = cfg.codebook_dim; ra.C = latent; ra.T = (int)T; ra.codebook_size = cfg.codebook_size;
@@ -742,11 +803,41 @@ struct b2a_snac {
             {   // transposed conv: tokens (b, q), q = 0..t ; rows m = r*cout + co ; scatter to t_out = q*s + r - pad
                 cg::Args a{};
                 a.N = (int)(batch * (t + 1)); a.epi = cg::E_CONVT; a.bias = B.ct.has_bias ? B.ct.bias.p : nullptr;
-                a.x = xs.p; a.ldx = B.cout; a.hl = hA.p; a.ldh = B.cout; a.T = (int)tout; a.Cout = B.cout; a.stride = B.stride;
+                a.x = xs.p; a.ldx = B.cout; a.hl = block_fused(B) ? nullptr : hA.p;     // the fused units read fp32 only
+                a.ldh = B.cout; a.T = (int)tout; a.Cout = B.cout; a.stride = B.stride;
                 a.pad = B.pad; a.Tin = (int)t;
                 cgemm(B.ct_tc, x2.p, 2 * pad64((long long)batch * (t + 1)), a, s);
             }
             const float* nz = d_noise_in ? d_noise_in[i] : nullptr;
+            const bool fz = block_fused(B);
+            if (fz) {
+                // narrow stages: one fused kernel per NoiseBlock / ResidualUnit, fp32 in -> fp32 out (ping-pong xs <-> xs2)
+                float* cur = xs.p; float* oth = xs2.p;
+                if (B.has_noise && (nz || noise_mode == 0)) {
+                    rf::Args a{};
+                    a.x = cur; a.y = oth; a.C = B.cout; a.mode = rf::MODE_NOISE; a.dil = 0; a.noise = nz;
+                    a.seed = seed + 0x1000193ull * (i + 1);
+                    fused(B.noise_tc, a, batch, tout, s);
+                    std::swap(cur, oth);
+                }
+                for (int u = 0; u < 3; ++u) {
+                    ResUnit& R = B.ru[u];
+                    rf::Args a{};
+                    a.x = cur; a.y = oth; a.C = B.cout; a.mode = rf::MODE_RU; a.dil = R.dil;
+                    a.dw_w = R.dw.w.p; a.dw_b = R.dw.has_bias ? R.dw.bias.p : nullptr; a.a_in = R.a0.p; a.a_mid = R.a2.p;
+                    a.pw_bias = R.pw.has_bias ? R.pw.bias.p : nullptr;
+                    if (u == 2 && i + 1 < blocks.size()) {
+                        x2_zero_edges_kernel<<<batch, 256, 0, s>>>(x2.p, (int)tout, B.cout);
+                        count_launch();
+                        a.hl = x2.p; a.a_next = blocks[i + 1].alpha.p;
+                    }
+                    fused(R.pw_tc, a, batch, tout, s);
+                    std::swap(cur, oth);
+                }
+                if (cur != xs.p) { std::swap(xs.p, xs2.p); std::swap(xs.n, xs2.n); }       // the live activation is always xs
+                t = tout;
+                continue;
+            }
             if (B.has_noise && (nz || noise_mode == 0)) {
                 cg::Args a{};
                 a.N = (int)ntok; a.epi = cg::E_NOISE; a.x = xs.p; a.ldx = B.cout; a.noise = nz;

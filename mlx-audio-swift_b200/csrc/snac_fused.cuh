@@ -1,0 +1,272 @@
+// Fused SNAC ResidualUnit / NoiseBlock for the narrow, memory-bound decoder stages (C = 64 or 128 channels):
+//     RU    (Layers.swift:202-232):  y = x + W * snake_b(dw7_dil(snake_a(x)) + b_dw) + b_pw
+//     NOISE (Layers.swift:263-279):  y = x + n[t] * (W x)
+// ONE kernel per unit: fp32 activation in, fp32 activation out (8 B per element instead of the 20 B the unfused
+// dw7 -> hi/lo -> GEMM -> read-modify-write sequence moves).  The depthwise conv, both Snakes and the fp32 -> bf16 hi/lo split
+// run on CUDA cores straight into the tcgen05 B-operand tile in shared memory (K-major, 128-byte swizzle -- the layout TMA would
+// have produced); the 1x1 conv is a tcgen05.mma against weights that stay resident in shared memory for the whole kernel (both
+// bf16 halves, loaded once by TMA); the accumulator comes back from TMEM, picks up bias + residual and leaves as fp32 (plus,
+// for the last unit of a block, the Snake'd hi/lo 2-tap im2col the next transposed conv reads).
+// A CTA is two independent TEAMS of 8 warps working on alternating 64-token tiles, each with its own staging buffers, operand
+// tile, TMEM accumulator and mbarrier: while one team waits on memory or the tensor core the other one computes, which is the
+// overlap a producer/consumer warp specialisation would give, with none of its plumbing.
+#pragma once
+#include "conv_gemm.cuh"
+
+namespace b2a {
+namespace rf {
+
+using namespace b2a::tc;
+
+constexpr int TOK = 64;                       // tokens per tile (x hi/lo = 128 B-operand rows)
+constexpr int TEAM_WARPS = 8, TEAM_THREADS = TEAM_WARPS * 32, TEAMS = 2, THREADS = TEAMS * TEAM_THREADS;
+constexpr int OP_KB_BYTES = 128 * BK * 2;     // one k-block of the operand tile: 128 rows x 64 bf16 = 16 KB
+constexpr int W_KB_BYTES = BM * BK * 2;       // one k-block of one weight half: 128 rows x 64 bf16 = 16 KB
+enum : int { MODE_RU = 0, MODE_NOISE = 1 };
+
+struct Args {
+    const float* x;            // [B*T, C] fp32
+    float* y;                  // [B*T, C] fp32 (must not alias x: neighbouring tiles read x's halo)
+    int C, T, B, mode, dil;
+    const float* dw_w;         // [C, 7]
+    const float* dw_b;         // [C] or null
+    const float* a_in;         // Snake alpha before the depthwise conv
+    const float* a_mid;        // Snake alpha after it
+    const float* pw_bias;      // [C] or null
+    const float* noise;        // [B*T] or null => counter-based N(0,1) from seed
+    unsigned long long seed;
+    __nv_bfloat16* hl;         // optional: Snake(a_next) of y as the next block's 2-tap im2col (conv_gemm.cuh "dual"), ld = 2*C
+    const float* a_next;
+    int tiles_per_utt;
+    long long n_tiles;
+};
+
+static inline size_t team_bytes(int C, int dil, int mode) {
+    const size_t s_rows = mode == MODE_RU ? (size_t)(TOK + 6 * dil) : 0;
+    return (((size_t)(C / BK) * OP_KB_BYTES + s_rows * BK * sizeof(float)) + 1023) / 1024 * 1024;   // operand tiles need 1024-B alignment
+}
+static inline size_t smem_bytes(int C, int dil, int mode) {
+    return 1024 + (size_t)2 * (C / BK) * W_KB_BYTES + (size_t)TEAMS * team_bytes(C, dil, mode) + 256;
+}
+
+__device__ __forceinline__ void team_sync(int team) {
+    asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(TEAM_THREADS) : "memory");
+}
+// byte offset of element (row, col) of a [rows][64] bf16 K-major SWIZZLE_128B tile
+__device__ __forceinline__ uint32_t sw128(int row, int col) {
+    return (uint32_t)(row * 128 + ((((col >> 3) ^ (row & 7)) << 4) | ((col & 7) << 1)));
+}
+
+// MODE_RU: DIL in {1, 3, 9}; MODE_NOISE: DIL = 0.  The input rows of the NEXT (tile, k-block) unit are prefetched into
+// registers (P float4 per thread) before the current unit's depthwise conv / MMA / epilogue, so their latency is hidden.
+template <int MODE, int DIL>
+static __global__ void __launch_bounds__(THREADS, 1)
+ru_fused_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl, Args a) {
+    constexpr int ROWS = MODE == MODE_RU ? TOK + 6 * DIL : TOK;
+    constexpr int HALO = 3 * DIL;
+    constexpr int P = (ROWS * 16 + TEAM_THREADS - 1) / TEAM_THREADS;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int kbs = a.C / BK;
+    uint8_t* wh = smem;                                         // [kbs][128][64] bf16
+    uint8_t* wl = wh + (size_t)kbs * W_KB_BYTES;
+    uint8_t* team_base = wl + (size_t)kbs * W_KB_BYTES;
+    const size_t tbytes = (((size_t)kbs * OP_KB_BYTES + (size_t)(MODE == MODE_RU ? ROWS : 0) * BK * sizeof(float)) + 1023) / 1024 * 1024;
+    uint64_t* wbar = reinterpret_cast<uint64_t*>(team_base + TEAMS * tbytes);
+    uint64_t* mbar = wbar + 1;                                  // [TEAMS]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + TEAMS);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int team = warp / TEAM_WARPS, tw = warp % TEAM_WARPS, tt_id = tid % TEAM_THREADS;
+    uint8_t* op = team_base + team * tbytes;                    // [kbs][128][64] bf16 (rows 0..63 hi, 64..127 lo)
+    float* S = reinterpret_cast<float*>(op + (size_t)kbs * OP_KB_BYTES);   // [ROWS][64] fp32
+
+    if (tid == 0) {
+        tma_prefetch_desc(&tmWh); tma_prefetch_desc(&tmWl);
+        mbar_init(wbar, 1);
+        for (int i = 0; i < TEAMS; ++i) mbar_init(&mbar[i], 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc<256>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (tid == 0) {   // weights: both halves, every k-block, once per CTA (rows >= C are zero-filled by TMA)
+        mbar_arrive_expect_tx(wbar, (uint32_t)(2 * kbs * W_KB_BYTES));
+        for (int kb = 0; kb < kbs; ++kb) {
+            tma_load_2d(wh + (size_t)kb * W_KB_BYTES, &tmWh, wbar, kb * BK, 0);
+            tma_load_2d(wl + (size_t)kb * W_KB_BYTES, &tmWl, wbar, kb * BK, 0);
+        }
+    }
+    pdl_wait();      // everything above is independent of the previous kernel's output
+
+    uint32_t mphase = 0;
+    bool w_ready = false;
+    const uint32_t d_tmem = tmem_base + (uint32_t)(team * 128);
+    const long long tstep = (long long)gridDim.x * TEAMS;
+    long long tile = (long long)blockIdx.x * TEAMS + team;
+    int kb = 0;
+    float4 R[P];
+    // rows [t0 - HALO, t0 - HALO + ROWS) x channels [kb*64, kb*64 + 64) of utterance b, zero outside [0, T)
+    auto issue_loads = [&](long long tl, int kbl) {
+        const int b = (int)(tl / a.tiles_per_utt), t0 = (int)(tl - (long long)b * a.tiles_per_utt) * TOK;
+        const float* xb = a.x + (long long)b * a.T * a.C + kbl * BK;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const int i = tt_id + p * TEAM_THREADS;
+            const int r = i >> 4, c = (i & 15) * 4;
+            const int t = t0 + r - HALO;
+            R[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < ROWS && t >= 0 && t < a.T) R[p] = *reinterpret_cast<const float4*>(xb + (long long)t * a.C + c);
+        }
+    };
+    if (tile < a.n_tiles) issue_loads(tile, 0);
+    while (tile < a.n_tiles) {
+        const int b = (int)(tile / a.tiles_per_utt), t0 = (int)(tile - (long long)b * a.tiles_per_utt) * TOK;
+        uint8_t* opk = op + (size_t)kb * OP_KB_BYTES;
+        // ---------------- registers -> Snake'd staging tile (RU) or straight to the hi/lo operand tile (NOISE)
+        if (MODE == MODE_RU) {
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                const int i = tt_id + p * TEAM_THREADS;
+                const int r = i >> 4, c = (i & 15) * 4;
+                if (r < ROWS) {
+                    const float4 al = *reinterpret_cast<const float4*>(a.a_in + kb * BK + c);
+                    float4 v = R[p];
+                    v.x = cg::snake(v.x, al.x); v.y = cg::snake(v.y, al.y); v.z = cg::snake(v.z, al.z); v.w = cg::snake(v.w, al.w);
+                    *reinterpret_cast<float4*>(S + r * BK + c) = v;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                const int i = tt_id + p * TEAM_THREADS;
+                const int r = i >> 4, c = (i & 15) * 4;
+                const float4 v = R[p];
+                const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+                const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - __low2float(h0), v.y - __high2float(h0));
+                const __nv_bfloat162 l1 = __floats2bfloat162_rn(v.z - __low2float(h1), v.w - __high2float(h1));
+                uint2 hv, lv;
+                hv.x = *reinterpret_cast<const uint32_t*>(&h0); hv.y = *reinterpret_cast<const uint32_t*>(&h1);
+                lv.x = *reinterpret_cast<const uint32_t*>(&l0); lv.y = *reinterpret_cast<const uint32_t*>(&l1);
+                *reinterpret_cast<uint2*>(opk + sw128(r, c)) = hv;
+                *reinterpret_cast<uint2*>(opk + sw128(r + TOK, c)) = lv;
+            }
+        }
+        if (MODE == MODE_RU) team_sync(team);
+        // ---------------- prefetch the next unit's rows (in flight during everything below)
+        long long ntile = tile;
+        int nkb = kb + 1;
+        if (nkb == kbs) { nkb = 0; ntile = tile + tstep; }
+        if (ntile < a.n_tiles) issue_loads(ntile, nkb);
+        const bool last_kb = kb == kbs - 1;
+        // residual / noise operands of the epilogue: issued before the depthwise conv so that they are hidden too
+        const int q = warp & 3, m = q * 32 + lane, cg0 = (tw >> 2) * 32;
+        const bool m_ok = m < a.C;
+        const long long nbase = (long long)b * a.T + t0;
+        float xr[2][16];        // residual rows: the first 16 tokens now, the other 16 after the MMA is issued
+        float nz_lane = 0.f;
+        if (last_kb) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) xr[0][j] = (m_ok && t0 + cg0 + j < a.T) ? a.x[(nbase + cg0 + j) * a.C + m] : 0.f;
+            if (MODE == MODE_NOISE && t0 + cg0 + lane < a.T) {
+                const long long n = nbase + cg0 + lane;
+                nz_lane = a.noise ? a.noise[n] : cg::gauss(a.seed, (unsigned long long)n);
+            }
+        }
+        if (MODE == MODE_RU) {
+            // thread -> channel pair (2 * (tt_id % 32)), 8 token groups of 8 tokens
+            const int c = (tt_id & 31) * 2, g = tt_id >> 5, ch = kb * BK + c;
+            float wa[7], wb[7];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) { wa[k] = a.dw_w[ch * 7 + k]; wb[k] = a.dw_w[(ch + 1) * 7 + k]; }
+            const float ba = a.dw_b ? a.dw_b[ch] : 0.f, bb = a.dw_b ? a.dw_b[ch + 1] : 0.f;
+            const float ama = a.a_mid[ch], amb = a.a_mid[ch + 1];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int tt = g * 8 + j;
+                float va = ba, vb = bb;
+#pragma unroll
+                for (int k = 0; k < 7; ++k) {
+                    const float2 xv = *reinterpret_cast<const float2*>(S + (tt + k * DIL) * BK + c);
+                    va = fmaf(wa[k], xv.x, va); vb = fmaf(wb[k], xv.y, vb);
+                }
+                va = cg::snake(va, ama); vb = cg::snake(vb, amb);
+                if (t0 + tt >= a.T) { va = 0.f; vb = 0.f; }
+                const __nv_bfloat162 hi = __floats2bfloat162_rn(va, vb);
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(va - __low2float(hi), vb - __high2float(hi));
+                *reinterpret_cast<__nv_bfloat162*>(opk + sw128(tt, c)) = hi;
+                *reinterpret_cast<__nv_bfloat162*>(opk + sw128(tt + TOK, c)) = lo;
+            }
+        }
+        if (!last_kb) {
+            if (MODE == MODE_RU) team_sync(team);          // S is rewritten by the next k-block
+            kb = nkb;
+            continue;
+        }
+        // generic-proxy writes of the operand tile -> visible to the tensor core (async proxy)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        team_sync(team);
+        // ---------------- MMA: D[128 ch, 0:128] = Wh * [Xh; Xl],  D[:, 0:64] += Wl * Xh
+        if (tt_id == 0) {
+            if (!w_ready) { mbar_wait(wbar, 0); w_ready = true; }
+            tc_fence_after();
+            constexpr uint32_t idesc_full = make_idesc(128), idesc_half = make_idesc(TOK);
+            for (int k2 = 0; k2 < kbs; ++k2) {
+                const uint64_t ad = make_smem_desc(smem_u32(wh + (size_t)k2 * W_KB_BYTES));
+                const uint64_t a2d = make_smem_desc(smem_u32(wl + (size_t)k2 * W_KB_BYTES));
+                const uint64_t bd = make_smem_desc(smem_u32(op + (size_t)k2 * OP_KB_BYTES));
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    const uint64_t off = (uint64_t)(k * UMMA_K * 2 / 16);
+                    umma_bf16(d_tmem, ad + off, bd + off, idesc_full, (k2 == 0 && k == 0) ? 0u : 1u);
+                    umma_bf16(d_tmem, a2d + off, bd + off, idesc_half, 1u);
+                }
+            }
+            umma_commit(&mbar[team]);
+        }
+        // ---------------- epilogue: warp -> TMEM lane quadrant (warp % 4), 32-token column group (tw / 4)
+        const float bias = (m_ok && a.pw_bias) ? a.pw_bias[m] : 0.f;
+        const float an = (m_ok && a.hl) ? a.a_next[m] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) xr[1][j] = (m_ok && t0 + cg0 + 16 + j < a.T) ? a.x[(nbase + cg0 + 16 + j) * a.C + m] : 0.f;
+        mbar_wait(&mbar[team], mphase);
+        mphase ^= 1;
+        tc_fence_after();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t taddr = d_tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg0 + h * 16);
+            float v[16], w[16];
+            tmem_ld16(taddr, v);
+            tmem_ld16(taddr + TOK, w);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int tt = cg0 + h * 16 + j;
+                const float nz = MODE == MODE_NOISE ? __shfl_sync(0xffffffffu, nz_lane, h * 16 + j) : 1.f;
+                if (!m_ok || t0 + tt >= a.T) continue;
+                const float val = xr[h][j] + nz * (v[j] + w[j] + bias);
+                a.y[(nbase + tt) * a.C + m] = val;
+                if (a.hl) {
+                    const float sv = cg::snake(val, an);
+                    const long long row = (long long)b * (a.T + 1) + t0 + tt;
+                    cg::put_hilo(a.hl, 2 * a.C, row, m, sv);
+                    cg::put_hilo(a.hl, 2 * a.C, row + 1, a.C + m, sv);
+                }
+            }
+        }
+        tc_fence_before();
+        team_sync(team);     // the accumulator and the operand tile are free again
+        tile = ntile; kb = nkb;
+    }
+    pdl_trigger();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc<256>(tmem_base);
+    }
+}
+
+}  // namespace rf
+}  // namespace b2a

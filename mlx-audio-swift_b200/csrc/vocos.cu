@@ -246,7 +246,7 @@ struct b2a_vocos {
         a.bias = W.has_bias ? W.bias.p : nullptr;
         const CUtensorMap tb = tc::make_tmap_bf16(X, x_rows, W.K, 128);
         const long long tiles = (long long)a.n_tiles * a.m_tiles;
-        launch_pdl(cg::conv_gemm_kernel, dim3((unsigned)std::min<long long>(num_sms, tiles)), dim3(tc::THREADS), cg::SMEM_BYTES, s,
+        launch_pdl(cg::conv_gemm_kernel, dim3((unsigned)std::min<long long>(num_sms, tiles)), dim3(cg::CG_THREADS), cg::SMEM_BYTES, s,
                    W.th, W.tl, tb, a);
     }
 
