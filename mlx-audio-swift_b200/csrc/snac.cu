@@ -523,13 +523,13 @@ struct TcW {
     }
 };
 
-struct ResUnit { DBuf<float> a0, a2; ConvW dw, pw; TcW pw_tc; int dil; };
+struct ResUnit { DBuf<float> a0, a2; ConvW dw, pw; TcW pw_tc, pw_bd; int dil; };   // pw_bd: [W 0; 0 W] for the fused C = 64 kernel
 struct DecBlock {
     int cin, cout, stride, pad;
     DBuf<float> alpha;   // Snake before the transposed conv
     ConvW ct;            // A[(co*s+r), (tap*Cin+ci)]
     ConvW noise;         // [cout, cout], no bias
-    TcW ct_tc, noise_tc; // tensor-core operands: ct_tc rows are m = r*cout + co (phase-major)
+    TcW ct_tc, noise_tc, noise_bd; // tensor-core operands: ct_tc rows are m = r*cout + co (phase-major); *_bd block-diagonal (C = 64)
     bool has_noise;
     ResUnit ru[3];
 };
@@ -706,10 +706,7 @@ struct b2a_snac {
         if (use_tc) {
             B2A_CUDA(cudaFuncSetAttribute(cg::conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cg::SMEM_BYTES));
             B2A_CUDA(cudaFuncSetAttribute(dw7_nlc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            B2A_CUDA(cudaFuncSetAttribute(rf::ru_fused_kernel<rf::MODE_RU, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            B2A_CUDA(cudaFuncSetAttribute(rf::ru_fused_kernel<rf::MODE_RU, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            B2A_CUDA(cudaFuncSetAttribute(rf::ru_fused_kernel<rf::MODE_RU, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            B2A_CUDA(cudaFuncSetAttribute(rf::ru_fused_kernel<rf::MODE_NOISE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            fused_attrs<64>(); fused_attrs<128>();
             const char* ef = getenv("B2A_SNAC_FUSED");
             use_fused = !(ef && std::string(ef) == "0");
             pw0_tc.build(host_pw0, C, latent);
@@ -718,7 +715,17 @@ struct b2a_snac {
                 DecBlock& B = blocks[i];
                 B.ct_tc.build(host_ct[i], B.cout * B.stride, 2 * B.cin);
                 B.noise_tc.build(host_noise[i], B.cout, B.cout);
-                for (int u = 0; u < 3; ++u) B.ru[u].pw_tc.build(host_pw[ip++], B.cout, B.cout);
+                auto blockdiag = [&](const std::vector<float>& w) {       // [64, 64] -> [128, 128] = [W 0; 0 W]
+                    std::vector<float> d((size_t)128 * 128, 0.f);
+                    for (int r = 0; r < 64; ++r)
+                        for (int c2 = 0; c2 < 64; ++c2) { d[(size_t)r * 128 + c2] = w[(size_t)r * 64 + c2]; d[(size_t)(r + 64) * 128 + 64 + c2] = w[(size_t)r * 64 + c2]; }
+                    return d;
+                };
+                if (B.cout == 64) B.noise_bd.build(blockdiag(host_noise[i]), 128, 128);
+                for (int u = 0; u < 3; ++u) {
+                    if (B.cout == 64) B.ru[u].pw_bd.build(blockdiag(host_pw[ip]), 128, 128);
+                    B.ru[u].pw_tc.build(host_pw[ip++], B.cout, B.cout);
+                }
             }
         }
         host_pw0.clear(); host_ct.clear(); host_noise.clear(); host_pw.clear();
@@ -745,24 +752,35 @@ struct b2a_snac {
         count_launch();
     }
     static long long pad64(long long n) { return (n + 63) / 64 * 64; }
-    bool fused_ok(int C, int dil) const {
-        return use_fused && (C == 64 || C == 128) && rf::smem_bytes(C, dil, rf::MODE_RU) <= 227 * 1024;
+    template <int CC>
+    static void fused_attrs() {
+        B2A_CUDA(cudaFuncSetAttribute(rf::ru_fused_kernel<rf::MODE_RU, 1, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        B2A_CUDA(cudaFuncSetAttribute(rf::ru_fused_kernel<rf::MODE_RU, 3, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        B2A_CUDA(cudaFuncSetAttribute(rf::ru_fused_kernel<rf::MODE_RU, 9, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        B2A_CUDA(cudaFuncSetAttribute(rf::ru_fused_kernel<rf::MODE_NOISE, 0, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     }
     bool block_fused(const DecBlock& B) const {
-        bool ok = fused_ok(B.cout, 9);
+        bool ok = use_fused && (B.cout == 64 || B.cout == 128);
         for (int u = 0; u < 3; ++u) ok = ok && (B.ru[u].dil == 1 || B.ru[u].dil == 3 || B.ru[u].dil == 9);
         return ok;
     }
+    template <int CC>
+    void fused_c(const TcW& W, const rf::Args& a, dim3 g, size_t sm, cudaStream_t s) {
+        const dim3 bl(rf::THREADS);
+        if (a.mode == rf::MODE_NOISE) launch_pdl(rf::ru_fused_kernel<rf::MODE_NOISE, 0, CC>, g, bl, sm, s, W.th, W.tl, a);
+        else if (a.dil == 1) launch_pdl(rf::ru_fused_kernel<rf::MODE_RU, 1, CC>, g, bl, sm, s, W.th, W.tl, a);
+        else if (a.dil == 3) launch_pdl(rf::ru_fused_kernel<rf::MODE_RU, 3, CC>, g, bl, sm, s, W.th, W.tl, a);
+        else launch_pdl(rf::ru_fused_kernel<rf::MODE_RU, 9, CC>, g, bl, sm, s, W.th, W.tl, a);
+    }
+    // W: the [128, 128] operand (the layer's own weights for C = 128, the block-diagonal copy for C = 64)
     void fused(const TcW& W, rf::Args a, int batch, long long T, cudaStream_t s) {
         a.B = batch; a.T = (int)T;
-        a.tiles_per_utt = cdiv(T, rf::TOK); a.n_tiles = (long long)batch * a.tiles_per_utt;
+        const int tile_tokens = a.C == 64 ? 2 * rf::TOK : rf::TOK;
+        a.tiles_per_utt = cdiv(T, tile_tokens); a.n_tiles = (long long)batch * a.tiles_per_utt;
         const long long ctas = std::min<long long>(num_sms, (a.n_tiles + rf::TEAMS - 1) / rf::TEAMS);
-        const size_t sm = rf::smem_bytes(a.C, a.dil, a.mode);
-        const dim3 g((unsigned)ctas), bl(rf::THREADS);
-        if (a.mode == rf::MODE_NOISE) launch_pdl(rf::ru_fused_kernel<rf::MODE_NOISE, 0>, g, bl, sm, s, W.th, W.tl, a);
-        else if (a.dil == 1) launch_pdl(rf::ru_fused_kernel<rf::MODE_RU, 1>, g, bl, sm, s, W.th, W.tl, a);
-        else if (a.dil == 3) launch_pdl(rf::ru_fused_kernel<rf::MODE_RU, 3>, g, bl, sm, s, W.th, W.tl, a);
-        else launch_pdl(rf::ru_fused_kernel<rf::MODE_RU, 9>, g, bl, sm, s, W.th, W.tl, a);
+        const size_t sm = rf::smem_bytes(a.dil, a.mode);
+        if (a.C == 64) fused_c<64>(W, a, dim3((unsigned)ctas), sm, s);
+        else fused_c<128>(W, a, dim3((unsigned)ctas), sm, s);
     }
 
     void decode_dev_tc(const int* const* d_codes_in, int batch, long long T, const float* const* d_noise_in, int noise_mode,
@@ -817,7 +835,7 @@ struct b2a_snac {
                     rf::Args a{};
                     a.x = cur; a.y = oth; a.C = B.cout; a.mode = rf::MODE_NOISE; a.dil = 0; a.noise = nz;
                     a.seed = seed + 0x1000193ull * (i + 1);
-                    fused(B.noise_tc, a, batch, tout, s);
+                    fused(B.cout == 64 ? B.noise_bd : B.noise_tc, a, batch, tout, s);
                     std::swap(cur, oth);
                 }
                 for (int u = 0; u < 3; ++u) {
@@ -831,7 +849,7 @@ struct b2a_snac {
                         count_launch();
                         a.hl = x2.p; a.a_next = blocks[i + 1].alpha.p;
                     }
-                    fused(R.pw_tc, a, batch, tout, s);
+                    fused(B.cout == 64 ? R.pw_bd : R.pw_tc, a, batch, tout, s);
                     std::swap(cur, oth);
                 }
                 if (cur != xs.p) { std::swap(xs.p, xs2.p); std::swap(xs.n, xs2.n); }       // the live activation is always xs

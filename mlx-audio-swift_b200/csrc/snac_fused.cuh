@@ -7,9 +7,14 @@
 // have produced); the 1x1 conv is a tcgen05.mma against weights that stay resident in shared memory for the whole kernel (both
 // bf16 halves, loaded once by TMA); the accumulator comes back from TMEM, picks up bias + residual and leaves as fp32 (plus,
 // for the last unit of a block, the Snake'd hi/lo 2-tap im2col the next transposed conv reads).
-// A CTA is two independent TEAMS of 8 warps working on alternating 64-token tiles, each with its own staging buffers, operand
+// A CTA is two independent TEAMS of 8 warps working on alternating tiles, each with its own staging buffers, operand
 // tile, TMEM accumulator and mbarrier: while one team waits on memory or the tensor core the other one computes, which is the
 // overlap a producer/consumer warp specialisation would give, with none of its plumbing.
+// The MMA always has M = 128 rows and K = 128.  C = 128: rows = output channels, the two k-blocks are the two channel halves of
+// one 64-token tile.  C = 64: the weight operand is the block-diagonal [W 0; 0 W] and the two k-blocks hold two consecutive
+// 64-token sub-tiles, so rows 0..63 / 64..127 of the accumulator are the 64 output channels of sub-tile 0 / 1 and all 128
+// TMEM lanes (all epilogue warps) do useful work.  C is a template parameter so that every activation address in the inner
+// loops is base + immediate (the first version spent ~100 instructions per element, mostly on 64-bit address arithmetic).
 #pragma once
 #include "conv_gemm.cuh"
 
@@ -41,12 +46,12 @@ struct Args {
     long long n_tiles;
 };
 
-static inline size_t team_bytes(int C, int dil, int mode) {
+static inline size_t team_bytes(int dil, int mode) {
     const size_t s_rows = mode == MODE_RU ? (size_t)(TOK + 6 * dil) : 0;
-    return (((size_t)(C / BK) * OP_KB_BYTES + s_rows * BK * sizeof(float)) + 1023) / 1024 * 1024;   // operand tiles need 1024-B alignment
+    return (((size_t)2 * OP_KB_BYTES + s_rows * BK * sizeof(float)) + 1023) / 1024 * 1024;   // operand tiles need 1024-B alignment
 }
-static inline size_t smem_bytes(int C, int dil, int mode) {
-    return 1024 + (size_t)2 * (C / BK) * W_KB_BYTES + (size_t)TEAMS * team_bytes(C, dil, mode) + 256;
+static inline size_t smem_bytes(int dil, int mode) {
+    return 1024 + (size_t)4 * W_KB_BYTES + (size_t)TEAMS * team_bytes(dil, mode) + 256;
 }
 
 __device__ __forceinline__ void team_sync(int team) {
@@ -59,27 +64,29 @@ __device__ __forceinline__ uint32_t sw128(int row, int col) {
 
 // MODE_RU: DIL in {1, 3, 9}; MODE_NOISE: DIL = 0.  The input rows of the NEXT (tile, k-block) unit are prefetched into
 // registers (P float4 per thread) before the current unit's depthwise conv / MMA / epilogue, so their latency is hidden.
-template <int MODE, int DIL>
+template <int MODE, int DIL, int C>
 static __global__ void __launch_bounds__(THREADS, 1)
 ru_fused_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl, Args a) {
+    static_assert(C == 64 || C == 128, "C must be 64 or 128");
     constexpr int ROWS = MODE == MODE_RU ? TOK + 6 * DIL : TOK;
     constexpr int HALO = 3 * DIL;
     constexpr int P = (ROWS * 16 + TEAM_THREADS - 1) / TEAM_THREADS;
+    constexpr int TT = C == 64 ? 2 * TOK : TOK;                 // tokens per tile
+    constexpr int KBS = 2;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int kbs = a.C / BK;
-    uint8_t* wh = smem;                                         // [kbs][128][64] bf16
-    uint8_t* wl = wh + (size_t)kbs * W_KB_BYTES;
-    uint8_t* team_base = wl + (size_t)kbs * W_KB_BYTES;
-    const size_t tbytes = (((size_t)kbs * OP_KB_BYTES + (size_t)(MODE == MODE_RU ? ROWS : 0) * BK * sizeof(float)) + 1023) / 1024 * 1024;
+    uint8_t* wh = smem;                                         // [2][128][64] bf16
+    uint8_t* wl = wh + (size_t)KBS * W_KB_BYTES;
+    uint8_t* team_base = wl + (size_t)KBS * W_KB_BYTES;
+    constexpr size_t tbytes = (((size_t)KBS * OP_KB_BYTES + (size_t)(MODE == MODE_RU ? ROWS : 0) * BK * sizeof(float)) + 1023) / 1024 * 1024;
     uint64_t* wbar = reinterpret_cast<uint64_t*>(team_base + TEAMS * tbytes);
     uint64_t* mbar = wbar + 1;                                  // [TEAMS]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + TEAMS);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int team = warp / TEAM_WARPS, tw = warp % TEAM_WARPS, tt_id = tid % TEAM_THREADS;
-    uint8_t* op = team_base + team * tbytes;                    // [kbs][128][64] bf16 (rows 0..63 hi, 64..127 lo)
-    float* S = reinterpret_cast<float*>(op + (size_t)kbs * OP_KB_BYTES);   // [ROWS][64] fp32
+    uint8_t* op = team_base + team * tbytes;                    // [2][128][64] bf16 (rows 0..63 hi, 64..127 lo)
+    float* S = reinterpret_cast<float*>(op + (size_t)KBS * OP_KB_BYTES);   // [ROWS][64] fp32
 
     if (tid == 0) {
         tma_prefetch_desc(&tmWh); tma_prefetch_desc(&tmWl);
@@ -92,9 +99,9 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    if (tid == 0) {   // weights: both halves, every k-block, once per CTA (rows >= C are zero-filled by TMA)
-        mbar_arrive_expect_tx(wbar, (uint32_t)(2 * kbs * W_KB_BYTES));
-        for (int kb = 0; kb < kbs; ++kb) {
+    if (tid == 0) {   // weights: both halves, both k-blocks, once per CTA
+        mbar_arrive_expect_tx(wbar, (uint32_t)(2 * KBS * W_KB_BYTES));
+        for (int kb = 0; kb < KBS; ++kb) {
             tma_load_2d(wh + (size_t)kb * W_KB_BYTES, &tmWh, wbar, kb * BK, 0);
             tma_load_2d(wl + (size_t)kb * W_KB_BYTES, &tmWl, wbar, kb * BK, 0);
         }
@@ -108,41 +115,41 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant_
     long long tile = (long long)blockIdx.x * TEAMS + team;
     int kb = 0;
     float4 R[P];
-    // rows [t0 - HALO, t0 - HALO + ROWS) x channels [kb*64, kb*64 + 64) of utterance b, zero outside [0, T)
+    // unit (tile, kb): 64 tokens starting at t0 + (C == 64 ? 64*kb : 0), channels (C == 64 ? 0 : 64*kb) .. +64;
+    // rows [tb - HALO, tb - HALO + ROWS) are fetched, zero outside [0, T)
+    const int ld_r = tt_id >> 4, ld_c = (tt_id & 15) * 4;       // this thread's (row, channel) in each 16-row slab
     auto issue_loads = [&](long long tl, int kbl) {
-        const int b = (int)(tl / a.tiles_per_utt), t0 = (int)(tl - (long long)b * a.tiles_per_utt) * TOK;
-        const float* xb = a.x + (long long)b * a.T * a.C + kbl * BK;
+        const int b = (int)(tl / a.tiles_per_utt), t0 = (int)(tl - (long long)b * a.tiles_per_utt) * TT;
+        const int tb = t0 + (C == 64 ? kbl * TOK : 0) - HALO + ld_r;
+        const float* xp = a.x + ((long long)b * a.T + tb) * C + (C == 64 ? 0 : kbl * BK) + ld_c;
 #pragma unroll
         for (int p = 0; p < P; ++p) {
-            const int i = tt_id + p * TEAM_THREADS;
-            const int r = i >> 4, c = (i & 15) * 4;
-            const int t = t0 + r - HALO;
+            const int t = tb + p * 16;
             R[p] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < ROWS && t >= 0 && t < a.T) R[p] = *reinterpret_cast<const float4*>(xb + (long long)t * a.C + c);
+            if (ld_r + p * 16 < ROWS && t >= 0 && t < a.T) R[p] = *reinterpret_cast<const float4*>(xp + p * 16 * C);
         }
     };
     if (tile < a.n_tiles) issue_loads(tile, 0);
     while (tile < a.n_tiles) {
-        const int b = (int)(tile / a.tiles_per_utt), t0 = (int)(tile - (long long)b * a.tiles_per_utt) * TOK;
+        const int b = (int)(tile / a.tiles_per_utt), t0 = (int)(tile - (long long)b * a.tiles_per_utt) * TT;
+        const int tb = t0 + (C == 64 ? kb * TOK : 0);            // first token of this unit
+        const int cb = C == 64 ? 0 : kb * BK;                    // first channel of this unit
         uint8_t* opk = op + (size_t)kb * OP_KB_BYTES;
         // ---------------- registers -> Snake'd staging tile (RU) or straight to the hi/lo operand tile (NOISE)
         if (MODE == MODE_RU) {
+            const float4 al = *reinterpret_cast<const float4*>(a.a_in + cb + ld_c);
 #pragma unroll
             for (int p = 0; p < P; ++p) {
-                const int i = tt_id + p * TEAM_THREADS;
-                const int r = i >> 4, c = (i & 15) * 4;
-                if (r < ROWS) {
-                    const float4 al = *reinterpret_cast<const float4*>(a.a_in + kb * BK + c);
+                if (ld_r + p * 16 < ROWS) {
                     float4 v = R[p];
                     v.x = cg::snake(v.x, al.x); v.y = cg::snake(v.y, al.y); v.z = cg::snake(v.z, al.z); v.w = cg::snake(v.w, al.w);
-                    *reinterpret_cast<float4*>(S + r * BK + c) = v;
+                    *reinterpret_cast<float4*>(S + (ld_r + p * 16) * BK + ld_c) = v;
                 }
             }
         } else {
 #pragma unroll
             for (int p = 0; p < P; ++p) {
-                const int i = tt_id + p * TEAM_THREADS;
-                const int r = i >> 4, c = (i & 15) * 4;
+                const int r = ld_r + p * 16;
                 const float4 v = R[p];
                 const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
                 const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - __low2float(h0), v.y - __high2float(h0));
@@ -150,54 +157,57 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant_
                 uint2 hv, lv;
                 hv.x = *reinterpret_cast<const uint32_t*>(&h0); hv.y = *reinterpret_cast<const uint32_t*>(&h1);
                 lv.x = *reinterpret_cast<const uint32_t*>(&l0); lv.y = *reinterpret_cast<const uint32_t*>(&l1);
-                *reinterpret_cast<uint2*>(opk + sw128(r, c)) = hv;
-                *reinterpret_cast<uint2*>(opk + sw128(r + TOK, c)) = lv;
+                *reinterpret_cast<uint2*>(opk + sw128(r, ld_c)) = hv;
+                *reinterpret_cast<uint2*>(opk + sw128(r + TOK, ld_c)) = lv;
             }
         }
         if (MODE == MODE_RU) team_sync(team);
         // ---------------- prefetch the next unit's rows (in flight during everything below)
         long long ntile = tile;
         int nkb = kb + 1;
-        if (nkb == kbs) { nkb = 0; ntile = tile + tstep; }
+        if (nkb == KBS) { nkb = 0; ntile = tile + tstep; }
         if (ntile < a.n_tiles) issue_loads(ntile, nkb);
-        const bool last_kb = kb == kbs - 1;
-        // residual / noise operands of the epilogue: issued before the depthwise conv so that they are hidden too
+        const bool last_kb = kb == KBS - 1;
+        // epilogue coordinates: TMEM lane m = q*32 + lane, columns cg0 .. cg0+31 (tokens of the 64-token unit)
         const int q = warp & 3, m = q * 32 + lane, cg0 = (tw >> 2) * 32;
-        const bool m_ok = m < a.C;
-        const long long nbase = (long long)b * a.T + t0;
+        const int ech = C == 64 ? (m & 63) : m;                                   // output channel
+        const int etok = t0 + (C == 64 ? (m >> 6) * TOK : 0) + cg0;               // first of this thread's 32 tokens
+        const long long erow = (long long)b * a.T + etok;
+        const float* xres = a.x + erow * C + ech;
+        const int nval = a.T - etok;                                              // tokens j < nval are inside the utterance
         float xr[2][16];        // residual rows: the first 16 tokens now, the other 16 after the MMA is issued
         float nz_lane = 0.f;
         if (last_kb) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) xr[0][j] = (m_ok && t0 + cg0 + j < a.T) ? a.x[(nbase + cg0 + j) * a.C + m] : 0.f;
-            if (MODE == MODE_NOISE && t0 + cg0 + lane < a.T) {
-                const long long n = nbase + cg0 + lane;
-                nz_lane = a.noise ? a.noise[n] : cg::gauss(a.seed, (unsigned long long)n);
-            }
+            for (int j = 0; j < 16; ++j) xr[0][j] = j < nval ? xres[j * C] : 0.f;
+            if (MODE == MODE_NOISE && lane < nval) nz_lane = a.noise ? a.noise[erow + lane] : cg::gauss(a.seed, (unsigned long long)(erow + lane));
         }
         if (MODE == MODE_RU) {
             // thread -> channel pair (2 * (tt_id % 32)), 8 token groups of 8 tokens
-            const int c = (tt_id & 31) * 2, g = tt_id >> 5, ch = kb * BK + c;
+            const int c = (tt_id & 31) * 2, g = tt_id >> 5, ch = cb + c;
             float wa[7], wb[7];
 #pragma unroll
             for (int k = 0; k < 7; ++k) { wa[k] = a.dw_w[ch * 7 + k]; wb[k] = a.dw_w[(ch + 1) * 7 + k]; }
             const float ba = a.dw_b ? a.dw_b[ch] : 0.f, bb = a.dw_b ? a.dw_b[ch + 1] : 0.f;
             const float ama = a.a_mid[ch], amb = a.a_mid[ch + 1];
+            const float* Sp = S + (g * 8) * BK + c;
+            uint8_t* oph = opk + (g * 8) * 128;                  // rows g*8 .. g*8+7: (row & 7) == j, so the swizzle is per j
+            const int nv = a.T - tb - g * 8;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const int tt = g * 8 + j;
                 float va = ba, vb = bb;
 #pragma unroll
                 for (int k = 0; k < 7; ++k) {
-                    const float2 xv = *reinterpret_cast<const float2*>(S + (tt + k * DIL) * BK + c);
+                    const float2 xv = *reinterpret_cast<const float2*>(Sp + (j + k * DIL) * BK);
                     va = fmaf(wa[k], xv.x, va); vb = fmaf(wb[k], xv.y, vb);
                 }
                 va = cg::snake(va, ama); vb = cg::snake(vb, amb);
-                if (t0 + tt >= a.T) { va = 0.f; vb = 0.f; }
+                if (j >= nv) { va = 0.f; vb = 0.f; }
                 const __nv_bfloat162 hi = __floats2bfloat162_rn(va, vb);
                 const __nv_bfloat162 lo = __floats2bfloat162_rn(va - __low2float(hi), vb - __high2float(hi));
-                *reinterpret_cast<__nv_bfloat162*>(opk + sw128(tt, c)) = hi;
-                *reinterpret_cast<__nv_bfloat162*>(opk + sw128(tt + TOK, c)) = lo;
+                const uint32_t off = (uint32_t)(j * 128 + ((((c >> 3) ^ j) << 4) | ((c & 7) << 1)));
+                *reinterpret_cast<__nv_bfloat162*>(oph + off) = hi;
+                *reinterpret_cast<__nv_bfloat162*>(oph + TOK * 128 + off) = lo;
             }
         }
         if (!last_kb) {
@@ -208,12 +218,13 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant_
         // generic-proxy writes of the operand tile -> visible to the tensor core (async proxy)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         team_sync(team);
-        // ---------------- MMA: D[128 ch, 0:128] = Wh * [Xh; Xl],  D[:, 0:64] += Wl * Xh
+        // ---------------- MMA: D[128, 0:128] = Wh * [Xh; Xl],  D[:, 0:64] += Wl * Xh   (K = 128 over the two k-blocks)
         if (tt_id == 0) {
             if (!w_ready) { mbar_wait(wbar, 0); w_ready = true; }
             tc_fence_after();
             constexpr uint32_t idesc_full = make_idesc(128), idesc_half = make_idesc(TOK);
-            for (int k2 = 0; k2 < kbs; ++k2) {
+#pragma unroll
+            for (int k2 = 0; k2 < KBS; ++k2) {
                 const uint64_t ad = make_smem_desc(smem_u32(wh + (size_t)k2 * W_KB_BYTES));
                 const uint64_t a2d = make_smem_desc(smem_u32(wl + (size_t)k2 * W_KB_BYTES));
                 const uint64_t bd = make_smem_desc(smem_u32(op + (size_t)k2 * OP_KB_BYTES));
@@ -226,11 +237,12 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant_
             }
             umma_commit(&mbar[team]);
         }
-        // ---------------- epilogue: warp -> TMEM lane quadrant (warp % 4), 32-token column group (tw / 4)
-        const float bias = (m_ok && a.pw_bias) ? a.pw_bias[m] : 0.f;
-        const float an = (m_ok && a.hl) ? a.a_next[m] : 0.f;
+        // ---------------- epilogue
+        const float bias = a.pw_bias ? a.pw_bias[ech] : 0.f;
+        const float an = a.hl ? a.a_next[ech] : 0.f;
+        float* yp = a.y + erow * C + ech;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) xr[1][j] = (m_ok && t0 + cg0 + 16 + j < a.T) ? a.x[(nbase + cg0 + 16 + j) * a.C + m] : 0.f;
+        for (int j = 0; j < 16; ++j) xr[1][j] = 16 + j < nval ? xres[(16 + j) * C] : 0.f;
         mbar_wait(&mbar[team], mphase);
         mphase ^= 1;
         tc_fence_after();
@@ -242,16 +254,16 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant_
             tmem_ld16(taddr + TOK, w);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                const int tt = cg0 + h * 16 + j;
                 const float nz = MODE == MODE_NOISE ? __shfl_sync(0xffffffffu, nz_lane, h * 16 + j) : 1.f;
-                if (!m_ok || t0 + tt >= a.T) continue;
-                const float val = xr[h][j] + nz * (v[j] + w[j] + bias);
-                a.y[(nbase + tt) * a.C + m] = val;
-                if (a.hl) {
-                    const float sv = cg::snake(val, an);
-                    const long long row = (long long)b * (a.T + 1) + t0 + tt;
-                    cg::put_hilo(a.hl, 2 * a.C, row, m, sv);
-                    cg::put_hilo(a.hl, 2 * a.C, row + 1, a.C + m, sv);
+                const float val = MODE == MODE_NOISE ? fmaf(nz, v[j] + w[j], xr[h][j]) : xr[h][j] + (v[j] + w[j] + bias);
+                if (h * 16 + j < nval) {
+                    yp[(h * 16 + j) * C] = val;
+                    if (a.hl) {
+                        const float sv = cg::snake(val, an);
+                        const long long row = (long long)b * (a.T + 1) + etok + h * 16 + j;
+                        cg::put_hilo(a.hl, 2 * C, row, ech, sv);
+                        cg::put_hilo(a.hl, 2 * C, row + 1, C + ech, sv);
+                    }
                 }
             }
         }
