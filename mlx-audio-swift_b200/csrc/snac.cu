@@ -466,33 +466,68 @@ __global__ void x2_zero_edges_kernel(__nv_bfloat16* __restrict__ x2, int T, int 
     }
 }
 
-// final Snake -> conv k7 (C -> 1) -> tanh in NLC (Layers.swift:411-415): 128 tokens per CTA, 2 threads per token
-constexpr int FN_TT = 128, FN_THREADS = 256, FN_MAXC = 64;
+// final Snake -> conv k7 (C -> 1) -> tanh in NLC (Layers.swift:411-415), C == 64.
+// 256 tokens per CTA; the Snake'd tile (+3 halo rows each side) is staged in shared memory.  Thread (tg, cg) owns 8 consecutive
+// tokens x 8 channels (two float4 column groups {4cg..4cg+3} and {32+4cg..}, so a quarter-warp's LDS.128 covers 128 contiguous
+// bytes): 14 row reads feed 8 x 7 x 8 FMAs against weights held in registers; the 8 channel groups are then reduced by shuffles.
+constexpr int FN_TT = 256, FN_THREADS = 256, FN_MAXC = 64;
 __global__ void __launch_bounds__(FN_THREADS)
 final_nlc_kernel(const float* __restrict__ x, float* __restrict__ wave, const float* __restrict__ w /*[C,7]*/,
                  const float* __restrict__ alpha, float bias, int T, int C) {
-    __shared__ float sx[(FN_TT + 6) * FN_MAXC];
-    __shared__ float sw[FN_MAXC * 7];
+    extern __shared__ __align__(16) float fsm[];     // [(256 + 6)][64]
     const int t0 = blockIdx.x * FN_TT, b = blockIdx.y;
-    const float* xb = x + (long long)b * T * C;
-    for (int i = threadIdx.x; i < (FN_TT + 6) * C; i += FN_THREADS) {
-        const int r = i / C, c = i - r * C;
+    const float* xb = x + (long long)b * T * FN_MAXC;
+    for (int i = threadIdx.x; i < (FN_TT + 6) * 16; i += FN_THREADS) {
+        const int r = i >> 4, c = (i & 15) * 4;
         const int t = t0 + r - 3;
-        sx[i] = (t >= 0 && t < T) ? snake_f(xb[(long long)t * C + c], alpha[c]) : 0.f;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t >= 0 && t < T) {
+            v = *reinterpret_cast<const float4*>(xb + (long long)t * FN_MAXC + c);
+            const float4 al = *reinterpret_cast<const float4*>(alpha + c);
+            v.x = snake_f(v.x, al.x); v.y = snake_f(v.y, al.y); v.z = snake_f(v.z, al.z); v.w = snake_f(v.w, al.w);
+        }
+        *reinterpret_cast<float4*>(fsm + r * FN_MAXC + c) = v;
     }
-    for (int i = threadIdx.x; i < C * 7; i += FN_THREADS) sw[i] = w[i];
-    __syncthreads();
-    const int tt = threadIdx.x >> 1, hf = threadIdx.x & 1, lane = threadIdx.x & 31;
-    const int ch = C / 2;
-    float acc = 0.f;
-    for (int i = 0; i < ch; ++i) {
-        const int c = hf * ch + ((i + lane) % ch);      // rotate channels across lanes: conflict-free
+    const int cgp = threadIdx.x & 7, tg = threadIdx.x >> 3;     // 8 channel groups x 32 token groups
+    float wk[8][7];
 #pragma unroll
-        for (int k = 0; k < 7; ++k) acc = fmaf(sw[c * 7 + k], sx[(tt + k) * C + c], acc);
+    for (int i = 0; i < 8; ++i) {
+        const int c = (i < 4 ? 0 : 28) + cgp * 4 + i;            // i >= 4 -> 32 + 4*cgp + (i - 4)
+#pragma unroll
+        for (int k = 0; k < 7; ++k) wk[i][k] = w[c * 7 + k];
     }
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    const int t = t0 + tt;
-    if (hf == 0 && t < T) wave[(long long)b * T + t] = tanhf(acc + bias);
+    __syncthreads();
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const float* base = fsm + (tg * 8) * FN_MAXC + cgp * 4;
+#pragma unroll
+    for (int r = 0; r < 14; ++r) {
+        const float4 lo = *reinterpret_cast<const float4*>(base + r * FN_MAXC);
+        const float4 hi = *reinterpret_cast<const float4*>(base + r * FN_MAXC + 32);
+        const float xv[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = r - j;
+            if (k >= 0 && k < 7) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[j] = fmaf(wk[i][k], xv[i], acc[j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float v = acc[j];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        acc[j] = v;
+    }
+    const int t = t0 + tg * 8 + cgp;                            // lane cgp of the group writes token cgp
+    float out = acc[0];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) out = cgp == j ? acc[j] : out;
+    if (t < T) wave[(long long)b * T + t] = tanhf(out + bias);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -700,13 +735,14 @@ struct b2a_snac {
         B2A_CUDA(cudaGetLastError());
         B2A_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
         const char* env = getenv("B2A_SNAC");
-        bool shapes_ok = latent % 64 == 0 && C % 64 == 0 && final_c <= FN_MAXC && final_c % 2 == 0 && c.noise != 0;
+        bool shapes_ok = latent % 64 == 0 && C % 64 == 0 && final_c == FN_MAXC && c.noise != 0;
         for (auto& B : blocks) shapes_ok = shapes_ok && B.cin % 64 == 0 && B.cout % 64 == 0;
         use_tc = shapes_ok && !(env && std::string(env) == "simt");
         if (use_tc) {
             B2A_CUDA(cudaFuncSetAttribute(cg::conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cg::SMEM_BYTES));
             B2A_CUDA(cudaFuncSetAttribute(dw7_nlc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
             fused_attrs<64>(); fused_attrs<128>();
+            B2A_CUDA(cudaFuncSetAttribute(final_nlc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (FN_TT + 6) * FN_MAXC * (int)sizeof(float)));
             const char* ef = getenv("B2A_SNAC_FUSED");
             use_fused = !(ef && std::string(ef) == "0");
             pw0_tc.build(host_pw0, C, latent);
@@ -878,7 +914,7 @@ struct b2a_snac {
             }
             t = tout;
         }
-        final_nlc_kernel<<<dim3(cdiv(t, FN_TT), batch), FN_THREADS, 0, s>>>(xs.p, d_wave_out, final_conv.w.p, alpha_final.p, final_bias,
+        final_nlc_kernel<<<dim3(cdiv(t, FN_TT), batch), FN_THREADS, (FN_TT + 6) * FN_MAXC * sizeof(float), s>>>(xs.p, d_wave_out, final_conv.w.p, alpha_final.p, final_bias,
                                                                             (int)t, final_c);
         count_launch();
         B2A_CUDA(cudaGetLastError());
