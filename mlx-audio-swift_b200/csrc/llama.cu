@@ -13,6 +13,7 @@
 // bookkeeping) is captured in one CUDA graph and replayed per token; nothing syncs with the
 // host inside the loop except a poll of the "all rows finished" flag every few steps.
 #include "common.cuh"
+#include <cooperative_groups.h>
 #include "tc_gemm.cuh"
 
 #include <algorithm>
@@ -82,10 +83,11 @@ constexpr int RN_THREADS = 1024, RN_MAXV = 8;
 __global__ void __launch_bounds__(RN_THREADS)
 add_rmsnorm_kernel(float* __restrict__ x, float* __restrict__ delta, const float* __restrict__ w,
                    bf16* __restrict__ xn, int H, float eps, float* __restrict__ trace, float* __restrict__ zero_ptr,
-                   int zero_n, int half) {
+                   int zero_n, int half, L2Prefetch pf) {
     __shared__ float red[RN_THREADS / 32];
     const int b = blockIdx.x, tid = threadIdx.x;
     pdl_trigger();
+    l2_prefetch(pf, b * RN_THREADS + tid, gridDim.x * RN_THREADS);
     pdl_wait();
     float* xr = x + (long long)b * H;
     float v[RN_MAXV];
@@ -231,6 +233,7 @@ struct AttnArgs {
     int* counters;         // [B][nkv], zero between launches
     int nq, nkv, max_ctx, S;
     float scale;
+    L2Prefetch pf;         // weights of a later GEMM, prefetched into L2 while attention (which reads little) runs
 };
 
 template <int G>
@@ -249,6 +252,8 @@ attn_decode_kernel(AttnArgs a) {
     const int h = blockIdx.x, b = blockIdx.y, s = blockIdx.z, tid = threadIdx.x;
     ATS(0);
     pdl_trigger();
+    l2_prefetch(a.pf, ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * AT_THREADS + tid,
+                gridDim.x * gridDim.y * gridDim.z * AT_THREADS);
     // Everything that does not depend on this step's q|k|v runs BEFORE griddepcontrol.wait and overlaps with the
     // tail of the QKV GEMM: pos[] is only written by the sampler (last kernel of the previous step's graph), the
     // cache rows < pos by earlier steps.  So: position, RoPE angles, mbarrier, and the bulk K/V loads go first.
@@ -408,6 +413,366 @@ attn_decode_kernel(AttnArgs a) {
     }
     if (tid == 0) a.counters[b * a.nkv + h] = 0;
     ATS(6);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Decode attention, one CTA per (kv head, row), looping over 64-key chunks with an online softmax (default).
+// The split-K kernel above pays three dependent global round trips after its compute (partials -> fence -> atomic ->
+// partial reads by the last CTA): measured 16.9 us per layer at context 320 for 21 MB of K/V.  Here nothing leaves the SM:
+// chunks stream through an NB-deep ring of shared-memory buffers (one cp.async.bulk per matrix per chunk, up to NB chunks in
+// flight, the first NB issued BEFORE griddepcontrol.wait so they overlap the tail of the QKV GEMM), every warp keeps a
+// running (max, sum, P*V) for its 8 keys of each chunk, and the 8 warp states are merged once at the end.
+// ------------------------------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(AT_THREADS)
+attn_decode_loop_kernel(AttnArgs a, int NB) {
+    extern __shared__ __align__(16) uint8_t at_smem[];
+    float* sKV = reinterpret_cast<float*>(at_smem);             // [NB][2][AT_CAP][128]  (K then V of each ring slot)
+    float* sq = sKV + (size_t)NB * 2 * AT_CAP * HD;             // [G][128]
+    float* snew = sq + G * HD;                                  // [2][128] the new k / v row of this step
+    float* wpo = snew + 2 * HD;                                 // [8 warps][G][128] warp-partial outputs
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wpo + (AT_THREADS / 32) * G * HD);   // [NB]
+    __shared__ float red_m[AT_THREADS / 32][MAXG], red_l[AT_THREADS / 32][MAXG];
+
+    const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    pdl_trigger();
+    l2_prefetch(a.pf, (blockIdx.y * gridDim.x + blockIdx.x) * AT_THREADS + tid, gridDim.x * gridDim.y * AT_THREADS);
+    const int p = a.pos[b];                                     // written by the previous step's sampler only
+    if (!(p >= 0 && p < a.max_ctx)) { pdl_wait(); return; }
+    const int nch = p / AT_CAP + 1;
+    const int qkv_ld = (a.nq + 2 * a.nkv) * HD;
+    const float* row = a.qkv + (long long)b * qkv_ld;
+    float* kc = a.kcache + (((long long)b * a.nkv + h) * a.max_ctx) * HD;
+    float* vc = a.vcache + (((long long)b * a.nkv + h) * a.max_ctx) * HD;
+    // rows of chunk c already in the cache (the new position p is staged from this step's q|k|v instead)
+    auto issue = [&](int c) {
+        const int slot = c % NB;
+        const int n_load = (c < nch - 1) ? AT_CAP : p - c * AT_CAP;
+        float* dK = sKV + (size_t)slot * 2 * AT_CAP * HD;
+        if (n_load > 0) {
+            const uint32_t bytes = (uint32_t)n_load * HD * 4;
+            tc::mbar_arrive_expect_tx(&bars[slot], 2 * bytes);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(tc::smem_u32(dK)), "l"(kc + (long long)c * AT_CAP * HD), "r"(bytes), "r"(tc::smem_u32(&bars[slot])) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(tc::smem_u32(dK + AT_CAP * HD)), "l"(vc + (long long)c * AT_CAP * HD), "r"(bytes), "r"(tc::smem_u32(&bars[slot])) : "memory");
+        } else {
+            tc::mbar_arrive(&bars[slot]);
+        }
+    };
+    if (tid == 0) {
+        for (int i = 0; i < NB; ++i) tc::mbar_init(&bars[i], 1);
+        tc::fence_barrier_init();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int c = 0; c < min(nch, NB); ++c) issue(c);
+    }
+    float sn = 0.f, cs = 1.f;
+    if (tid < HD / 2) sincosf((float)p / a.freqs[tid], &sn, &cs);   // MLXFast.RoPE(freqs:): angle = pos / freqs[i]
+    pdl_wait();
+    if (tid < HD / 2) {  // non-traditional RoPE: pairs (i, i+64)
+        const int d = tid;
+        _Pragma("unroll") for (int g = 0; g < G; ++g) {
+            const float* q = row + (h * G + g) * HD;
+            const float x1 = q[d], x2 = q[d + HD / 2];
+            sq[g * HD + d] = x1 * cs - x2 * sn;
+            sq[g * HD + d + HD / 2] = x2 * cs + x1 * sn;
+        }
+        const float* k = row + (a.nq + h) * HD;
+        const float x1 = k[d], x2 = k[d + HD / 2];
+        const float k1 = x1 * cs - x2 * sn, k2 = x2 * cs + x1 * sn;
+        kc[(long long)p * HD + d] = k1;
+        kc[(long long)p * HD + d + HD / 2] = k2;
+        snew[d] = k1;
+        snew[d + HD / 2] = k2;
+    } else if (tid >= 128) {
+        const int d = tid - 128;
+        const float v = row[(a.nq + a.nkv + h) * HD + d];
+        vc[(long long)p * HD + d] = v;
+        snew[HD + d] = v;
+    }
+    __syncthreads();            // barrier init + q / new-row staging visible
+
+    const int lane = tid & 31, warp = tid >> 5;
+    const int kslot = warp * 8 + (lane >> 2), part = lane & 3;
+    float m_run[G], l_run[G];
+    float4 o4[G];
+    _Pragma("unroll") for (int g = 0; g < G; ++g) { m_run[g] = -INFINITY; l_run[g] = 0.f; o4[g] = make_float4(0.f, 0.f, 0.f, 0.f); }
+
+    for (int c = 0; c < nch; ++c) {
+        const int slot = c % NB;
+        float* sK = sKV + (size_t)slot * 2 * AT_CAP * HD;
+        float* sV = sK + AT_CAP * HD;
+        const int t0 = c * AT_CAP, nk = min(AT_CAP, p + 1 - t0);
+        tc::mbar_wait(&bars[slot], (uint32_t)((c / NB) & 1));    // bulk-copied K and V of this chunk have landed
+        if (c == nch - 1) {                                      // splice in the new position (the bulk copy stopped before it)
+            if (tid < HD) sK[(p - t0) * HD + tid] = snew[tid];
+            else sV[(p - t0) * HD + tid - HD] = snew[tid];
+            __syncthreads();
+        }
+        float sacc[G];
+        _Pragma("unroll") for (int g = 0; g < G; ++g) sacc[g] = 0.f;
+        if (kslot < nk) {
+            const float4* kr = reinterpret_cast<const float4*>(sK + kslot * HD);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int d4 = part + 4 * ((j + kslot) & 7);     // rotated columns: every quarter-warp hits 8 distinct bank groups
+                const float4 kf = kr[d4];
+                _Pragma("unroll") for (int g = 0; g < G; ++g) {
+                    const float4 qf = reinterpret_cast<const float4*>(sq + g * HD)[d4];
+                    sacc[g] = fmaf(qf.x, kf.x, sacc[g]); sacc[g] = fmaf(qf.y, kf.y, sacc[g]);
+                    sacc[g] = fmaf(qf.z, kf.z, sacc[g]); sacc[g] = fmaf(qf.w, kf.w, sacc[g]);
+                }
+            }
+        }
+        float pw[G];
+        _Pragma("unroll") for (int g = 0; g < G; ++g) {
+            float v = sacc[g];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            const float sv = kslot < nk ? v * a.scale : -INFINITY;
+            float m = sv;
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
+            const float m_new = fmaxf(m_run[g], m);
+            const float rescale = (m_run[g] == -INFINITY) ? 0.f : __expf(m_run[g] - m_new);
+            const float e = (sv == -INFINITY) ? 0.f : __expf(sv - m_new);     // all 4 lanes of a key hold the same value
+            float l = part == 0 ? e : 0.f;
+            l = warp_sum(l);
+            l_run[g] = l_run[g] * rescale + l;
+            m_run[g] = m_new;
+            o4[g].x *= rescale; o4[g].y *= rescale; o4[g].z *= rescale; o4[g].w *= rescale;
+            pw[g] = e;
+        }
+        // warp-partial P*V: lane owns dims 4*lane .. 4*lane+3 (conflict-free float4 reads of a V row)
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+            const int t = warp * 8 + kk;
+            if (t < nk) {
+                const float4 v = reinterpret_cast<const float4*>(sV + t * HD)[lane];
+                _Pragma("unroll") for (int g = 0; g < G; ++g) {
+                    const float pk = __shfl_sync(0xffffffffu, pw[g], kk * 4);
+                    o4[g].x = fmaf(pk, v.x, o4[g].x); o4[g].y = fmaf(pk, v.y, o4[g].y);
+                    o4[g].z = fmaf(pk, v.z, o4[g].z); o4[g].w = fmaf(pk, v.w, o4[g].w);
+                }
+            }
+        }
+        if (c + NB < nch) {
+            __syncthreads();                                     // every warp is done with this slot
+            if (tid == 0) issue(c + NB);
+        }
+    }
+    // merge the 8 warp states
+    _Pragma("unroll") for (int g = 0; g < G; ++g) {
+        reinterpret_cast<float4*>(wpo + (warp * G + g) * HD)[lane] = o4[g];
+        if (lane == 0) { red_m[warp][g] = m_run[g]; red_l[warp][g] = l_run[g]; }
+    }
+    __syncthreads();
+    if (tid < HD) {
+        _Pragma("unroll") for (int g = 0; g < G; ++g) {
+            float M = red_m[0][g];
+#pragma unroll
+            for (int w = 1; w < AT_THREADS / 32; ++w) M = fmaxf(M, red_m[w][g]);
+            float L = 0.f, O = 0.f;
+#pragma unroll
+            for (int w = 0; w < AT_THREADS / 32; ++w) {
+                const float sc_w = red_m[w][g] == -INFINITY ? 0.f : __expf(red_m[w][g] - M);
+                L = fmaf(red_l[w][g], sc_w, L);
+                O = fmaf(wpo[(w * G + g) * HD + tid], sc_w, O);
+            }
+            store_hilo(a.out, (long long)a.nq * HD, b, (h * G + g) * HD + tid, O / L);
+        }
+    }
+}
+
+// Same, with the chunks of one (kv head, row) dealt alternately to the TWO CTAs of a thread-block cluster: 128 CTAs instead of
+// 64, so up to 2 x NB chunks (6 x 64 keys) are in flight before griddepcontrol.wait and the serial chunk count halves.  CTA 1
+// hands its (max, sum, P*V) state to CTA 0 through distributed shared memory; one cluster barrier, nothing goes through HBM.
+template <int G>
+__global__ void __cluster_dims__(1, 1, 2) __launch_bounds__(AT_THREADS)
+attn_decode_cluster_kernel(AttnArgs a, int NB) {
+    namespace cgr = cooperative_groups;
+    cgr::cluster_group cluster = cgr::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    extern __shared__ __align__(16) uint8_t at_smem[];
+    float* sKV = reinterpret_cast<float*>(at_smem);             // [NB][2][AT_CAP][128]  (K then V of each ring slot)
+    float* sq = sKV + (size_t)NB * 2 * AT_CAP * HD;             // [G][128]
+    float* snew = sq + G * HD;                                  // [2][128] the new k / v row of this step
+    float* wpo = snew + 2 * HD;                                 // [8 warps][G][128] warp-partial outputs
+    float* xo = wpo + (AT_THREADS / 32) * G * HD;               // [G][128] + [2][G]: the peer CTA's merged state (written remotely)
+    float* xml = xo + G * HD;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xml + 2 * MAXG);   // [NB]
+    __shared__ float red_m[AT_THREADS / 32][MAXG], red_l[AT_THREADS / 32][MAXG];
+
+    const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    pdl_trigger();
+    l2_prefetch(a.pf, ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * AT_THREADS + tid, gridDim.x * gridDim.y * gridDim.z * AT_THREADS);
+    const int p = a.pos[b];                                     // written by the previous step's sampler only
+    if (!(p >= 0 && p < a.max_ctx)) { pdl_wait(); return; }
+    const int nch = p / AT_CAP + 1;
+    const int n_my = nch > rank ? (nch - rank + 1) / 2 : 0;     // this CTA's chunks: rank, rank + 2, ...
+    const bool owner = ((nch - 1) & 1) == rank;                 // the CTA whose last chunk holds the new position
+    const int qkv_ld = (a.nq + 2 * a.nkv) * HD;
+    const float* row = a.qkv + (long long)b * qkv_ld;
+    float* kc = a.kcache + (((long long)b * a.nkv + h) * a.max_ctx) * HD;
+    float* vc = a.vcache + (((long long)b * a.nkv + h) * a.max_ctx) * HD;
+    // rows of chunk c already in the cache (the new position p is staged from this step's q|k|v instead)
+    auto issue = [&](int i) {
+        const int slot = i % NB, c = rank + 2 * i;
+        const int n_load = (c < nch - 1) ? AT_CAP : p - c * AT_CAP;
+        float* dK = sKV + (size_t)slot * 2 * AT_CAP * HD;
+        if (n_load > 0) {
+            const uint32_t bytes = (uint32_t)n_load * HD * 4;
+            tc::mbar_arrive_expect_tx(&bars[slot], 2 * bytes);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(tc::smem_u32(dK)), "l"(kc + (long long)c * AT_CAP * HD), "r"(bytes), "r"(tc::smem_u32(&bars[slot])) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(tc::smem_u32(dK + AT_CAP * HD)), "l"(vc + (long long)c * AT_CAP * HD), "r"(bytes), "r"(tc::smem_u32(&bars[slot])) : "memory");
+        } else {
+            tc::mbar_arrive(&bars[slot]);
+        }
+    };
+    if (tid == 0) {
+        for (int i = 0; i < NB; ++i) tc::mbar_init(&bars[i], 1);
+        tc::fence_barrier_init();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int i = 0; i < min(n_my, NB); ++i) issue(i);
+    }
+    float sn = 0.f, cs = 1.f;
+    if (tid < HD / 2) sincosf((float)p / a.freqs[tid], &sn, &cs);   // MLXFast.RoPE(freqs:): angle = pos / freqs[i]
+    pdl_wait();
+    if (tid < HD / 2) {  // non-traditional RoPE: pairs (i, i+64)
+        const int d = tid;
+        _Pragma("unroll") for (int g = 0; g < G; ++g) {
+            const float* q = row + (h * G + g) * HD;
+            const float x1 = q[d], x2 = q[d + HD / 2];
+            sq[g * HD + d] = x1 * cs - x2 * sn;
+            sq[g * HD + d + HD / 2] = x2 * cs + x1 * sn;
+        }
+        const float* k = row + (a.nq + h) * HD;
+        const float x1 = k[d], x2 = k[d + HD / 2];
+        const float k1 = x1 * cs - x2 * sn, k2 = x2 * cs + x1 * sn;
+        if (owner) { kc[(long long)p * HD + d] = k1; kc[(long long)p * HD + d + HD / 2] = k2; }
+        snew[d] = k1;
+        snew[d + HD / 2] = k2;
+    } else if (tid >= 128) {
+        const int d = tid - 128;
+        const float v = row[(a.nq + a.nkv + h) * HD + d];
+        if (owner) vc[(long long)p * HD + d] = v;
+        snew[HD + d] = v;
+    }
+    __syncthreads();            // barrier init + q / new-row staging visible
+
+    const int lane = tid & 31, warp = tid >> 5;
+    const int kslot = warp * 8 + (lane >> 2), part = lane & 3;
+    float m_run[G], l_run[G];
+    float4 o4[G];
+    _Pragma("unroll") for (int g = 0; g < G; ++g) { m_run[g] = -INFINITY; l_run[g] = 0.f; o4[g] = make_float4(0.f, 0.f, 0.f, 0.f); }
+
+    for (int i = 0; i < n_my; ++i) {
+        const int slot = i % NB, c = rank + 2 * i;
+        float* sK = sKV + (size_t)slot * 2 * AT_CAP * HD;
+        float* sV = sK + AT_CAP * HD;
+        const int t0 = c * AT_CAP, nk = min(AT_CAP, p + 1 - t0);
+        tc::mbar_wait(&bars[slot], (uint32_t)((i / NB) & 1));    // bulk-copied K and V of this chunk have landed
+        if (c == nch - 1) {                                      // splice in the new position (the bulk copy stopped before it)
+            if (tid < HD) sK[(p - t0) * HD + tid] = snew[tid];
+            else sV[(p - t0) * HD + tid - HD] = snew[tid];
+            __syncthreads();
+        }
+        float sacc[G];
+        _Pragma("unroll") for (int g = 0; g < G; ++g) sacc[g] = 0.f;
+        if (kslot < nk) {
+            const float4* kr = reinterpret_cast<const float4*>(sK + kslot * HD);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int d4 = part + 4 * ((j + kslot) & 7);     // rotated columns: every quarter-warp hits 8 distinct bank groups
+                const float4 kf = kr[d4];
+                _Pragma("unroll") for (int g = 0; g < G; ++g) {
+                    const float4 qf = reinterpret_cast<const float4*>(sq + g * HD)[d4];
+                    sacc[g] = fmaf(qf.x, kf.x, sacc[g]); sacc[g] = fmaf(qf.y, kf.y, sacc[g]);
+                    sacc[g] = fmaf(qf.z, kf.z, sacc[g]); sacc[g] = fmaf(qf.w, kf.w, sacc[g]);
+                }
+            }
+        }
+        float pw[G];
+        _Pragma("unroll") for (int g = 0; g < G; ++g) {
+            float v = sacc[g];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            const float sv = kslot < nk ? v * a.scale : -INFINITY;
+            float m = sv;
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
+            const float m_new = fmaxf(m_run[g], m);
+            const float rescale = (m_run[g] == -INFINITY) ? 0.f : __expf(m_run[g] - m_new);
+            const float e = (sv == -INFINITY) ? 0.f : __expf(sv - m_new);     // all 4 lanes of a key hold the same value
+            float l = part == 0 ? e : 0.f;
+            l = warp_sum(l);
+            l_run[g] = l_run[g] * rescale + l;
+            m_run[g] = m_new;
+            o4[g].x *= rescale; o4[g].y *= rescale; o4[g].z *= rescale; o4[g].w *= rescale;
+            pw[g] = e;
+        }
+        // warp-partial P*V: lane owns dims 4*lane .. 4*lane+3 (conflict-free float4 reads of a V row)
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+            const int t = warp * 8 + kk;
+            if (t < nk) {
+                const float4 v = reinterpret_cast<const float4*>(sV + t * HD)[lane];
+                _Pragma("unroll") for (int g = 0; g < G; ++g) {
+                    const float pk = __shfl_sync(0xffffffffu, pw[g], kk * 4);
+                    o4[g].x = fmaf(pk, v.x, o4[g].x); o4[g].y = fmaf(pk, v.y, o4[g].y);
+                    o4[g].z = fmaf(pk, v.z, o4[g].z); o4[g].w = fmaf(pk, v.w, o4[g].w);
+                }
+            }
+        }
+        if (i + NB < n_my) {
+            __syncthreads();                                     // every warp is done with this slot
+            if (tid == 0) issue(i + NB);
+        }
+    }
+    // merge the 8 warp states
+    _Pragma("unroll") for (int g = 0; g < G; ++g) {
+        reinterpret_cast<float4*>(wpo + (warp * G + g) * HD)[lane] = o4[g];
+        if (lane == 0) { red_m[warp][g] = m_run[g]; red_l[warp][g] = l_run[g]; }
+    }
+    __syncthreads();
+    float Ms[G], Ls[G], Os[G];
+    if (tid < HD) {
+        _Pragma("unroll") for (int g = 0; g < G; ++g) {
+            float M = red_m[0][g];
+#pragma unroll
+            for (int w = 1; w < AT_THREADS / 32; ++w) M = fmaxf(M, red_m[w][g]);
+            float L = 0.f, O = 0.f;
+#pragma unroll
+            for (int w = 0; w < AT_THREADS / 32; ++w) {
+                const float sc_w = red_m[w][g] == -INFINITY ? 0.f : __expf(red_m[w][g] - M);
+                L = fmaf(red_l[w][g], sc_w, L);
+                O = fmaf(wpo[(w * G + g) * HD + tid], sc_w, O);
+            }
+            Ms[g] = M; Ls[g] = L; Os[g] = O;
+        }
+        if (rank == 1) {                                         // hand the state to CTA 0 (distributed shared memory)
+            float* rxo = cluster.map_shared_rank(xo, 0);
+            float* rxml = cluster.map_shared_rank(xml, 0);
+            _Pragma("unroll") for (int g = 0; g < G; ++g) {
+                rxo[g * HD + tid] = Os[g];
+                if (tid == 0) { rxml[g] = Ms[g]; rxml[MAXG + g] = Ls[g]; }
+            }
+        }
+    }
+    cluster.sync();
+    if (rank == 0 && tid < HD) {
+        _Pragma("unroll") for (int g = 0; g < G; ++g) {
+            const float M1 = xml[g], L1 = xml[MAXG + g], O1 = xo[g * HD + tid];
+            const float M = fmaxf(Ms[g], M1);
+            const float w0 = Ms[g] == -INFINITY ? 0.f : __expf(Ms[g] - M), w1 = M1 == -INFINITY ? 0.f : __expf(M1 - M);
+            const float L = Ls[g] * w0 + L1 * w1, O = Os[g] * w0 + O1 * w1;
+            store_hilo(a.out, (long long)a.nq * HD, b, (h * G + g) * HD + tid, O / L);
+        }
+    }
 }
 
 #ifdef B2A_ATTN_TIMING
@@ -894,7 +1259,51 @@ struct b2a_tts {
     static void attn_attr() {
         B2A_CUDA(cudaFuncSetAttribute(attn_decode_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     }
+    template <int G>
+    static void attn_loop_attr() {
+        B2A_CUDA(cudaFuncSetAttribute(attn_decode_loop_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));   // + 512 B static
+    }
+    int attn_loop_bufs() const {
+        const int G = cfg.num_attention_heads / cfg.num_key_value_heads;
+        const size_t extra = (size_t)(G * HD + 2 * HD + (AT_THREADS / 32) * G * HD + G * HD + 2 * MAXG) * sizeof(float) + 64;
+        return (int)std::min<size_t>(3, (226 * 1024 - extra) / ((size_t)2 * AT_CAP * HD * sizeof(float)));
+    }
+    template <int G>
+    static void attn_cluster_attr() {
+        B2A_CUDA(cudaFuncSetAttribute(attn_decode_cluster_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    }
+    bool attn_loop = true;     // B2A_ATTN=split selects the flash-decoding split kernel, =loop the single-CTA loop
+    bool attn_cluster = true;  // default: two-CTA cluster per (kv head, row)
     void attn_launch(const AttnArgs& aa, int B, cudaStream_t s) {
+        if (attn_loop && attn_cluster) {
+            const int G = aa.nq / aa.nkv, NB = attn_loop_bufs();
+            const size_t sm = (size_t)NB * 2 * AT_CAP * HD * sizeof(float) +
+                              (size_t)(G * HD + 2 * HD + (AT_THREADS / 32) * G * HD + G * HD + 2 * MAXG) * sizeof(float) + 64;
+            const dim3 g3(aa.nkv, B, 2);
+            switch (G) {
+                case 1: launch_pdl(attn_decode_cluster_kernel<1>, g3, dim3(AT_THREADS), sm, s, aa, NB); break;
+                case 2: launch_pdl(attn_decode_cluster_kernel<2>, g3, dim3(AT_THREADS), sm, s, aa, NB); break;
+                case 3: launch_pdl(attn_decode_cluster_kernel<3>, g3, dim3(AT_THREADS), sm, s, aa, NB); break;
+                case 4: launch_pdl(attn_decode_cluster_kernel<4>, g3, dim3(AT_THREADS), sm, s, aa, NB); break;
+                case 6: launch_pdl(attn_decode_cluster_kernel<6>, g3, dim3(AT_THREADS), sm, s, aa, NB); break;
+                default: launch_pdl(attn_decode_cluster_kernel<8>, g3, dim3(AT_THREADS), sm, s, aa, NB); break;
+            }
+            return;
+        }
+        if (attn_loop) {
+            const int G = aa.nq / aa.nkv, NB = attn_loop_bufs();
+            const size_t sm = (size_t)NB * 2 * AT_CAP * HD * sizeof(float) + (size_t)(G * HD + 2 * HD + (AT_THREADS / 32) * G * HD) * sizeof(float) + 64;
+            const dim3 g2(aa.nkv, B);
+            switch (G) {
+                case 1: launch_pdl(attn_decode_loop_kernel<1>, g2, dim3(AT_THREADS), sm, s, aa, NB); break;
+                case 2: launch_pdl(attn_decode_loop_kernel<2>, g2, dim3(AT_THREADS), sm, s, aa, NB); break;
+                case 3: launch_pdl(attn_decode_loop_kernel<3>, g2, dim3(AT_THREADS), sm, s, aa, NB); break;
+                case 4: launch_pdl(attn_decode_loop_kernel<4>, g2, dim3(AT_THREADS), sm, s, aa, NB); break;
+                case 6: launch_pdl(attn_decode_loop_kernel<6>, g2, dim3(AT_THREADS), sm, s, aa, NB); break;
+                default: launch_pdl(attn_decode_loop_kernel<8>, g2, dim3(AT_THREADS), sm, s, aa, NB); break;
+            }
+            return;
+        }
         const dim3 grid(aa.nkv, B, aa.S);
         const size_t sm = attn_smem_bytes();
         switch (aa.nq / aa.nkv) {
@@ -965,6 +1374,9 @@ struct b2a_tts {
         gemv_attrs<1>(); gemv_attrs<2>(); gemv_attrs<4>(); gemv_attrs<8>();
         B2A_CHECK(attn_smem_bytes() <= 220 * 1024, B2A_ERR_INVALID_INPUT, "llama: GQA ratio too large for the attention tile");
         attn_attr<1>(); attn_attr<2>(); attn_attr<3>(); attn_attr<4>(); attn_attr<6>(); attn_attr<8>();
+        attn_loop_attr<1>(); attn_loop_attr<2>(); attn_loop_attr<3>(); attn_loop_attr<4>(); attn_loop_attr<6>(); attn_loop_attr<8>();
+        attn_cluster_attr<1>(); attn_cluster_attr<2>(); attn_cluster_attr<3>(); attn_cluster_attr<4>(); attn_cluster_attr<6>(); attn_cluster_attr<8>();
+        { const char* e = getenv("B2A_ATTN"); attn_loop = !(e && std::string(e) == "split"); attn_cluster = !(e && std::string(e) == "loop"); }
         B2A_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
         // tcgen05 / TMA path: needs every GEMM K to be a multiple of 64; B2A_GEMM=simt forces the SIMT fallback
         const char* env = getenv("B2A_GEMM");
@@ -1102,9 +1514,43 @@ struct b2a_tts {
     }
 
     // D[tokens, M] = X[tokens, K] * W[M, K]^T on the tcgen05 path (hi/lo activations, BN = 16)
+    // ---- L2 prefetch schedule (B2A_L2PF bit mask; see pf_of): which kernel prefetches which later GEMM's weights
+    enum : int { L2_NORM1 = 0, L2_QKV, L2_ATTN, L2_O, L2_NORM2, L2_GU, L2_DOWN };
+    int l2pf_mask = -1;
+    L2Prefetch pf_of(int site, int l) {
+        if (l2pf_mask < 0) {
+            const char* e = getenv("B2A_L2PF");
+            l2pf_mask = e ? (int)strtol(e, nullptr, 0) : L2PF_DEFAULT;
+        }
+        if (!use_tc || l < 0 || l >= cfg.num_hidden_layers) return L2Prefetch{nullptr, 0};
+        const long long H = cfg.hidden_size, I = cfg.intermediate_size, NQ = (long long)cfg.num_attention_heads * HD,
+                        NKV = (long long)cfg.num_key_value_heads * HD;
+        const long long b_qkv = (NQ + 2 * NKV) * H * 2, b_o = H * NQ * 2, b_gu = 2 * I * H * 2, b_down = H * I * 2;
+        LayerW& L = layers[l];
+        const bool last = l + 1 == cfg.num_hidden_layers;
+        switch (site) {
+            case L2_NORM1: if (l2pf_mask & 1) return L2Prefetch{L.wqkv.p, b_qkv}; break;                 // norm1 -> QKV
+            case L2_ATTN:
+                if ((l2pf_mask & 2) && (l2pf_mask & 4)) return L2Prefetch{L.wo.p, b_o};                   // attn -> O (GU by the O GEMM)
+                if (l2pf_mask & 2) return L2Prefetch{L.wgu.p, b_gu};                                      // attn -> GU
+                if (l2pf_mask & 4) return L2Prefetch{L.wo.p, b_o};
+                break;
+            case L2_QKV: if (l2pf_mask & 8) return L2Prefetch{L.wo.p, b_o}; break;                        // QKV GEMM -> O
+            case L2_O: if (l2pf_mask & 16) return L2Prefetch{L.wgu.p, b_gu}; break;                       // O GEMM -> GU
+            case L2_NORM2: if (l2pf_mask & 32) return L2Prefetch{L.wdown.p, b_down}; break;               // norm2 -> DOWN
+            case L2_GU: if (l2pf_mask & 64) return L2Prefetch{L.wdown.p, b_down}; break;                  // GU GEMM -> DOWN
+            case L2_DOWN:
+                if (l2pf_mask & 128) return last ? L2Prefetch{lm_head, 64ll << 20} : L2Prefetch{layers[l + 1].wqkv.p, b_qkv};   // DOWN -> next QKV
+                break;
+        }
+        return L2Prefetch{nullptr, 0};
+    }
+    static constexpr int L2PF_DEFAULT = 0;
+
     void tc_gemm(const CUtensorMap& tmW, const CUtensorMap& tmX, int op, float* yout, bf16* actout, int B, int M, int K,
-                 cudaStream_t s) {
+                 cudaStream_t s, L2Prefetch pf = L2Prefetch{nullptr, 0}) {
         tc::Args a{};
+        a.pf_ptr = pf.ptr; a.pf_bytes = pf.bytes;
         a.out_f32 = yout; a.out_bf16 = actout; a.M = M; a.N = B; a.K = K;
         a.m_tiles = cdiv(M, tc::BM); a.k_blocks = K / tc::BK;
         a.stages = 6;   // 6 x 18 KB ring: two GEMM CTAs (this kernel's and the next kernel's prefetching one) fit per SM
@@ -1129,19 +1575,19 @@ struct b2a_tts {
         LayerW* L = layer >= 0 ? &layers[layer] : nullptr;
         switch (op) {
             case OP_QKV:
-                if (use_tc) tc_gemm(tm_qkv[layer], tmx_xn, op, qkv.p, nullptr, B, NQ + 2 * NKV, H, s);
+                if (use_tc) tc_gemm(tm_qkv[layer], tmx_xn, op, qkv.p, nullptr, B, NQ + 2 * NKV, H, s, pf_of(L2_QKV, layer));
                 else gemv_nb(op, L->wqkv.p, xn.p, qkv.p, nullptr, NQ + 2 * NKV, H, s);
                 break;
             case OP_O:
-                if (use_tc) tc_gemm(tm_o[layer], tmx_attn, op, y.p, nullptr, B, H, NQ, s);
+                if (use_tc) tc_gemm(tm_o[layer], tmx_attn, op, y.p, nullptr, B, H, NQ, s, pf_of(L2_O, layer));
                 else gemv_nb(op, L->wo.p, attn.p, y.p, nullptr, H, NQ, s);
                 break;
             case OP_GU:
-                if (use_tc) tc_gemm(tm_gu[layer], tmx_xn, op, nullptr, act.p, B, 2 * I, H, s);
+                if (use_tc) tc_gemm(tm_gu[layer], tmx_xn, op, nullptr, act.p, B, 2 * I, H, s, pf_of(L2_GU, layer));
                 else gemv_nb(op, L->wgu.p, xn.p, nullptr, act.p, 2 * I, H, s);
                 break;
             case OP_DOWN:
-                if (use_tc) tc_gemm(tm_down[layer], tmx_act, op, y.p, nullptr, B, H, I, s);
+                if (use_tc) tc_gemm(tm_down[layer], tmx_act, op, y.p, nullptr, B, H, I, s, pf_of(L2_DOWN, layer));
                 else gemv_nb(op, L->wdown.p, act.p, y.p, nullptr, H, I, s);
                 break;
             default:
@@ -1167,16 +1613,17 @@ struct b2a_tts {
             LayerW& L = layers[l];
             if (!skip("norm"))
             launch_pdl(add_rmsnorm_kernel, dim3(B), dim3(RN_THREADS), 0, s, x.p, l == 0 ? (float*)nullptr : y.p, L.ln1.p, xn.p, H,
-                       cfg.rms_norm_eps, trace_on ? trace.p + (size_t)(2 * l) * 8 * H : (float*)nullptr, (float*)nullptr, 0, LO_ROW);
+                       cfg.rms_norm_eps, trace_on ? trace.p + (size_t)(2 * l) * 8 * H : (float*)nullptr, (float*)nullptr, 0, LO_ROW,
+                       pf_of(L2_NORM1, l));
             if (!skip("gemm") && !skip("qkv")) gemm(OP_QKV, l, B, s);
             AttnArgs aa{qkv.p, pos.p, freqs.p, kcache.p + l * kv_layer, vcache.p + l * kv_layer, attn.p, part_o.p, part_ml.p,
-                        at_counters.p, nq, nkv, cfg.max_context, at_splits, 1.0f / sqrtf((float)HD)};
+                        at_counters.p, nq, nkv, cfg.max_context, at_splits, 1.0f / sqrtf((float)HD), pf_of(L2_ATTN, l)};
             if (!skip("attn")) attn_launch(aa, B, s);
             if (!skip("gemm") && !skip("o_proj")) gemm(OP_O, l, B, s);
             // also zeroes this row of q|k|v so the next layer's stream-K QKV GEMM can accumulate into it
             if (!skip("norm"))
             launch_pdl(add_rmsnorm_kernel, dim3(B), dim3(RN_THREADS), 0, s, x.p, y.p, L.ln2.p, xn.p, H, cfg.rms_norm_eps,
-                       trace_on ? trace.p + (size_t)(2 * l + 1) * 8 * H : (float*)nullptr, qkv.p, QKV_N, LO_ROW);
+                       trace_on ? trace.p + (size_t)(2 * l + 1) * 8 * H : (float*)nullptr, qkv.p, QKV_N, LO_ROW, pf_of(L2_NORM2, l));
             if (!skip("gemm") && !skip("gate")) gemm(OP_GU, l, B, s);
             if (!skip("gemm") && !skip("down")) gemm(OP_DOWN, l, B, s);
         }
@@ -1185,7 +1632,8 @@ struct b2a_tts {
 
     void run_lm_head(int B, cudaStream_t s) {
         launch_pdl(add_rmsnorm_kernel, dim3(B), dim3(RN_THREADS), 0, s, x.p, y.p, final_ln.p, xn.p, cfg.hidden_size, cfg.rms_norm_eps,
-                   trace_on ? trace.p + (size_t)(2 * cfg.num_hidden_layers) * 8 * cfg.hidden_size : (float*)nullptr, (float*)nullptr, 0, LO_ROW);
+                   trace_on ? trace.p + (size_t)(2 * cfg.num_hidden_layers) * 8 * cfg.hidden_size : (float*)nullptr, (float*)nullptr, 0, LO_ROW,
+                   L2Prefetch{nullptr, 0});
         gemm(OP_LM, -1, B, s);
     }
     // logits are [8, V] row-major.
@@ -1243,7 +1691,7 @@ struct b2a_tts {
         for (int l = 0; l < cfg.num_hidden_layers; ++l) {
             LayerW& Lw = layers[l];
             launch_pdl(add_rmsnorm_kernel, dim3(T), dim3(RN_THREADS), 0, s, xp.p, l == 0 ? (float*)nullptr : yp.p, Lw.ln1.p, xnp.p, H,
-                       cfg.rms_norm_eps, (float*)nullptr, (float*)nullptr, 0, PF_HALF);
+                       cfg.rms_norm_eps, (float*)nullptr, (float*)nullptr, 0, PF_HALF, L2Prefetch{nullptr, 0});
             pf_gemm(tm_qkv[l], tmp_xn, tc::EPI_STORE, qkvp.p, nullptr, T, QKV_N, H, s);
             PrefillAttnArgs pa{qkvp.p, rope_tab.p, kcache.p + l * kv_layer, vcache.p + l * kv_layer, attnp.p, nq, nkv,
                                cfg.max_context, L, 1.0f / sqrtf((float)HD)};
@@ -1260,7 +1708,7 @@ struct b2a_tts {
             count_launch();
             pf_gemm(tm_o[l], tmp_attn, tc::EPI_STORE, yp.p, nullptr, T, H, NQ, s);
             launch_pdl(add_rmsnorm_kernel, dim3(T), dim3(RN_THREADS), 0, s, xp.p, yp.p, Lw.ln2.p, xnp.p, H, cfg.rms_norm_eps,
-                       (float*)nullptr, (float*)nullptr, 0, PF_HALF);
+                       (float*)nullptr, (float*)nullptr, 0, PF_HALF, L2Prefetch{nullptr, 0});
             pf_gemm(tm_gu[l], tmp_xn, tc::EPI_SWIGLU, nullptr, actp.p, T, 2 * I, H, s);
             pf_gemm(tm_down[l], tmp_act, tc::EPI_STORE, yp.p, nullptr, T, H, I, s);
         }

@@ -36,6 +36,8 @@ struct Args {
                              // j + BN/2 of the accumulator are summed, giving fp32-activation accuracy for free
     const float* bias;       // nullable [M]: added to every output column before the activation
     int act;                 // ACT_NONE | ACT_GELU (exact erf GELU, WhisperLayers.swift:101)
+    const void* pf_ptr;      // optional L2 prefetch of a later GEMM's weights (issued by the epilogue warps at kernel start)
+    long long pf_bytes;
     int lo_rows;             // != 0: bf16 outputs are written as hi/lo pairs in the same tile-interleaved row layout the
                              // kernel reads X in: token t -> hi row (t / (BN/2)) * BN + t % (BN/2), lo row = hi row + BN/2
 };
@@ -240,6 +242,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else {
+        if (a.pf_ptr) {
+            constexpr long long CH = 8192;
+            const long long w = (long long)blockIdx.x * 128 + (threadIdx.x - 64), nw = (long long)gridDim.x * 128;
+            for (long long off = w * CH; off < a.pf_bytes; off += nw * CH) {
+                const unsigned n = (unsigned)(a.pf_bytes - off < CH ? ((a.pf_bytes - off) & ~15ll) : CH);
+                if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"((const char*)a.pf_ptr + off), "r"(n) : "memory");
+            }
+        }
         const int q = warp & 3;                           // TMEM lane quadrant this warp may access
         int acc = 0; uint32_t acc_phase = 0;
         long long u = u0;
