@@ -121,90 +121,104 @@ def kv_bytes(cfg, batch, ctx) -> int:
 
 
 # ------------------------------------------------------------------------------------------------- CPU legs
-def cpu_reference_sample(cfg, threads: int):
-    """The reference path restated on the CPU (oracle/, kind "port"), bounded sample.
-    Full width, 2- and 4-layer models timed to separate per-layer cost from the lm head; extrapolated to
-    28 layers x (64-token prefill + 512 decode steps); SNAC decode timed on 1 of 8 utterances (fp32)."""
-    import torch
-    from oracle import llama as ol
-    from oracle import snac as osn
-    torch.set_num_threads(threads)
-    L_full = cfg["num_hidden_layers"]
+class CpuReference:
+    """The reference path restated on the CPU (oracle/, kind "port"), as a BOUNDED sample per call.
+    Weights (full width, 4 layers + the tied embedding) are built once.  One sample times: the prefill on a 16-token prompt
+    (x 4 = 64 tokens, linear in tokens) and one decode step, each on a 2- and a 4-layer model to separate the per-layer cost from
+    the lm head, extrapolated to 28 layers x (64-token prefill + 512 steps); and the SNAC decode of a quarter of one utterance's
+    frames (x 4 x 8 utterances, linear in frames)."""
 
-    def build(nl):
-        c = ol.LlamaConfig(hidden_size=cfg["hidden_size"], num_hidden_layers=nl, intermediate_size=cfg["intermediate_size"],
-                           num_attention_heads=cfg["num_attention_heads"], num_key_value_heads=cfg["num_key_value_heads"],
-                           head_dim=cfg["head_dim"], vocab_size=cfg["vocab_size"])
-        return c
+    PREFILL_TOKENS, SNAC_DIV = 16, 4
 
-    c4 = build(4)
-    g = torch.Generator().manual_seed(0)
-    W = {}
-    H, I, hd = c4.hidden_size, c4.intermediate_size, c4.head_dim
+    def __init__(self, cfg, threads: int):
+        import torch
+        from oracle import llama as ol
+        from oracle import snac as osn
+        torch.set_num_threads(threads)
+        self.cfg, self.threads, self.ol, self.osn, self.torch = cfg, threads, ol, osn, torch
+        g = torch.Generator().manual_seed(0)
+        H, I, hd = cfg["hidden_size"], cfg["intermediate_size"], cfg["head_dim"]
+        nq, nkv, V = cfg["num_attention_heads"], cfg["num_key_value_heads"], cfg["vocab_size"]
 
-    def lin(o, i):
-        return torch.randn(o, i, generator=g) * 0.02      # fp32 (bf16-valued weights pre-widened once)
+        def lin(o, i):
+            return torch.randn(o, i, generator=g) * 0.02      # fp32 (bf16-valued weights pre-widened once)
 
-    W["model.embed_tokens.weight"] = lin(c4.vocab_size, H)
-    for l in range(4):
-        p = f"model.layers.{l}."
-        W[p + "self_attn.q_proj.weight"] = lin(c4.num_attention_heads * hd, H)
-        W[p + "self_attn.k_proj.weight"] = lin(c4.num_key_value_heads * hd, H)
-        W[p + "self_attn.v_proj.weight"] = lin(c4.num_key_value_heads * hd, H)
-        W[p + "self_attn.o_proj.weight"] = lin(H, c4.num_attention_heads * hd)
-        W[p + "mlp.gate_proj.weight"] = lin(I, H)
-        W[p + "mlp.up_proj.weight"] = lin(I, H)
-        W[p + "mlp.down_proj.weight"] = lin(H, I)
-        W[p + "input_layernorm.weight"] = torch.ones(H)
-        W[p + "post_attention_layernorm.weight"] = torch.ones(H)
-    W["model.norm.weight"] = torch.ones(H)
-    ids = torch.as_tensor(make_prompts(0), dtype=torch.long)
-    res = {}
-    for nl in (2, 4):
-        mo = ol.LlamaOracle(build(nl), W, round_acts=True)
-        t0 = time.perf_counter()
-        lg = mo.forward(ids)
-        t_pre = time.perf_counter() - t0
-        nxt = lg[:, -1].argmax(-1, keepdim=True)
-        ts = []
-        for _ in range(3):
+        W = {"model.embed_tokens.weight": lin(V, H), "model.norm.weight": torch.ones(H)}
+        for l in range(4):
+            p = f"model.layers.{l}."
+            W[p + "self_attn.q_proj.weight"] = lin(nq * hd, H)
+            W[p + "self_attn.k_proj.weight"] = lin(nkv * hd, H)
+            W[p + "self_attn.v_proj.weight"] = lin(nkv * hd, H)
+            W[p + "self_attn.o_proj.weight"] = lin(H, nq * hd)
+            W[p + "mlp.gate_proj.weight"] = lin(I, H)
+            W[p + "mlp.up_proj.weight"] = lin(I, H)
+            W[p + "mlp.down_proj.weight"] = lin(H, I)
+            W[p + "input_layernorm.weight"] = torch.ones(H)
+            W[p + "post_attention_layernorm.weight"] = torch.ones(H)
+        self.W = W
+        self.scfg = osn.SNACConfig()
+        self.SW = osn.init_weights(self.scfg, 1234)
+
+    def _build(self, nl):
+        c = self.cfg
+        return self.ol.LlamaConfig(hidden_size=c["hidden_size"], num_hidden_layers=nl, intermediate_size=c["intermediate_size"],
+                                   num_attention_heads=c["num_attention_heads"], num_key_value_heads=c["num_key_value_heads"],
+                                   head_dim=c["head_dim"], vocab_size=c["vocab_size"])
+
+    def sample(self, light: bool = False):
+        """-> (RTFx, total seconds extrapolated, description).  light=True (warm-up samples): one decode step only."""
+        torch, ol, osn = self.torch, self.ol, self.osn
+        L_full = self.cfg["num_hidden_layers"]
+        ids = torch.as_tensor(make_prompts(0)[:, :self.PREFILL_TOKENS], dtype=torch.long)
+        res = {}
+        for nl in (2, 4):
+            mo = ol.LlamaOracle(self._build(nl), self.W, round_acts=True)
             t0 = time.perf_counter()
-            lg = mo.forward(nxt)
-            ts.append(time.perf_counter() - t0)
+            lg = mo.forward(ids if not light else ids[:, :2])
+            t_pre = (time.perf_counter() - t0) * (PROMPT_LEN / (self.PREFILL_TOKENS if not light else 2))
             nxt = lg[:, -1].argmax(-1, keepdim=True)
-        res[nl] = (t_pre, float(np.median(ts)))
-    per_layer_pre = (res[4][0] - res[2][0]) / 2
-    per_layer_dec = (res[4][1] - res[2][1]) / 2
-    head_pre = max(res[2][0] - 2 * per_layer_pre, 0.0)
-    head_dec = max(res[2][1] - 2 * per_layer_dec, 0.0)
-    t_prefill = L_full * per_layer_pre + head_pre
-    t_step = L_full * per_layer_dec + head_dec
-    # SNAC on one utterance, fp32
-    osn.DTYPE = torch.float32
-    scfg = osn.SNACConfig()
-    SW = osn.init_weights(scfg, 1234)
-    frames = (PROMPT_LEN + GEN_TOKENS) // 7
-    codes = osn.synth_codes(scfg, 1, 4 * frames, seed=2)
-    t0 = time.perf_counter()
-    osn.decode(scfg, SW, codes, None)
-    t_snac1 = time.perf_counter() - t0
-    osn.DTYPE = torch.float64
-    total = t_prefill + GEN_TOKENS * t_step + BATCH * t_snac1
-    audio = BATCH * audio_seconds_per_utterance(PROMPT_LEN, GEN_TOKENS)
-    sample = (f"oracle port (torch-CPU fp32 math on bf16-valued weights, {threads} threads): full-width 2- and 4-layer models "
-              f"timed (prefill {res[4][0]:.2f}s / decode step {res[4][1]*1e3:.0f}ms at 4 layers), per-layer + lm-head cost "
-              f"extrapolated linearly to {L_full} layers x ({PROMPT_LEN}-token prefill + {GEN_TOKENS} steps); SNAC decode timed on "
-              f"1 of {BATCH} utterances ({t_snac1:.2f}s) x {BATCH}")
-    return audio / total, total, sample
+            t0 = time.perf_counter()
+            mo.forward(nxt)
+            res[nl] = (t_pre, time.perf_counter() - t0)
+            if light:
+                res[4] = res[2] = res[nl]
+                break
+        per_layer_pre = max((res[4][0] - res[2][0]) / 2, 0.0)
+        per_layer_dec = max((res[4][1] - res[2][1]) / 2, 0.0)
+        head_pre = max(res[2][0] - 2 * per_layer_pre, 0.0)
+        head_dec = max(res[2][1] - 2 * per_layer_dec, 0.0)
+        t_prefill = L_full * per_layer_pre + head_pre
+        t_step = L_full * per_layer_dec + head_dec
+        frames = (PROMPT_LEN + GEN_TOKENS) // 7
+        fsub = max(frames // self.SNAC_DIV, 1) if not light else 1
+        osn.DTYPE = torch.float32
+        codes = osn.synth_codes(self.scfg, 1, 4 * fsub, seed=2)
+        t0 = time.perf_counter()
+        osn.decode(self.scfg, self.SW, codes, None)
+        t_snac1 = (time.perf_counter() - t0) * frames / fsub
+        osn.DTYPE = torch.float64
+        total = t_prefill + GEN_TOKENS * t_step + BATCH * t_snac1
+        audio = BATCH * audio_seconds_per_utterance(PROMPT_LEN, GEN_TOKENS)
+        desc = (f"oracle port (torch-CPU fp32 math on bf16-valued weights, {self.threads} threads): full-width 2- and 4-layer models timed "
+                f"(prefill of {self.PREFILL_TOKENS} of {PROMPT_LEN} prompt tokens x batch {BATCH}: {res[4][0]:.2f}s scaled / decode step "
+                f"{res[4][1]*1e3:.0f}ms at 4 layers), per-layer + lm-head cost extrapolated linearly to {L_full} layers x "
+                f"({PROMPT_LEN}-token prefill + {GEN_TOKENS} steps); SNAC decode timed on {fsub} of {frames} frames of 1 of {BATCH} "
+                f"utterances ({t_snac1:.2f}s scaled) x {BATCH}")
+        return audio / total, total, desc
+
+
+def cpu_reference_sample(cfg, threads: int):
+    return CpuReference(cfg, threads).sample()
 
 
 def run_reference_arm(args, rank: int, world: int):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
+    ref = CpuReference(ORPHEUS, threads)          # weights built once; every step is one bounded sample (see CpuReference)
     vals, totals, sample = [], [], ""
     for i in range(args.warmup + args.steps):
-        v, tot, sample = cpu_reference_sample(ORPHEUS, threads)
+        v, tot, sample = ref.sample(light=i < args.warmup)     # warm-up samples: threads / allocator only (one decode step)
         if i >= args.warmup:
             vals.append(v); totals.append(tot)
     v = float(np.mean(vals))
