@@ -742,6 +742,7 @@ struct b2a_snac {
             B2A_CUDA(cudaFuncSetAttribute(cg::conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cg::SMEM_BYTES));
             B2A_CUDA(cudaFuncSetAttribute(dw7_nlc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
             fused_attrs<64>(); fused_attrs<128>();
+            B2A_CUDA(cudaFuncSetAttribute(rf::convt_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rf::convt_smem_bytes()));
             B2A_CUDA(cudaFuncSetAttribute(final_nlc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (FN_TT + 6) * FN_MAXC * (int)sizeof(float)));
             const char* ef = getenv("B2A_SNAC_FUSED");
             use_fused = !(ef && std::string(ef) == "0");
@@ -800,6 +801,13 @@ struct b2a_snac {
         for (int u = 0; u < 3; ++u) ok = ok && (B.ru[u].dil == 1 || B.ru[u].dil == 3 || B.ru[u].dil == 9);
         return ok;
     }
+    // Snake + transposed conv fused (snac_fused.cuh convt_fused_kernel): 128 input channels -> stride * C_out = 128 phase rows,
+    // fed by a fused block (its fp32 output is the only copy)
+    bool convt_fused_ok(size_t i) const {
+        if (!use_fused || i == 0 || i >= blocks.size()) return false;
+        const DecBlock& B = blocks[i];
+        return B.cin == 128 && B.stride * B.cout == 128 && block_fused(blocks[i - 1]) && block_fused(B);
+    }
     template <int CC>
     void fused_c(const TcW& W, const rf::Args& a, dim3 g, size_t sm, cudaStream_t s) {
         const dim3 bl(rf::THREADS);
@@ -854,7 +862,16 @@ struct b2a_snac {
         for (size_t i = 0; i < blocks.size(); ++i) {
             DecBlock& B = blocks[i];
             const long long tout = t * B.stride, ntok = (long long)batch * tout;
-            {   // transposed conv: tokens (b, q), q = 0..t ; rows m = r*cout + co ; scatter to t_out = q*s + r - pad
+            if (convt_fused_ok(i)) {
+                // last block: Snake + transposed conv straight from the previous block's fp32 output (no 2-tap im2col round trip)
+                rf::ConvtArgs a{};
+                a.x = xs.p; a.y = xs2.p; a.alpha = B.alpha.p; a.bias = B.ct.has_bias ? B.ct.bias.p : nullptr;
+                a.Tin = (int)t; a.T = (int)tout; a.B = batch; a.stride = B.stride; a.cout = B.cout; a.pad = B.pad;
+                a.tiles_per_utt = cdiv(t + 1, rf::TOK); a.n_tiles = (long long)batch * a.tiles_per_utt;
+                const long long ctas = std::min<long long>(num_sms, (a.n_tiles + rf::TEAMS - 1) / rf::TEAMS);
+                launch_pdl(rf::convt_fused_kernel, dim3((unsigned)ctas), dim3(rf::THREADS), rf::convt_smem_bytes(), s, B.ct_tc.th, B.ct_tc.tl, a);
+                std::swap(xs.p, xs2.p); std::swap(xs.n, xs2.n);
+            } else {   // transposed conv: tokens (b, q), q = 0..t ; rows m = r*cout + co ; scatter to t_out = q*s + r - pad
                 cg::Args a{};
                 a.N = (int)(batch * (t + 1)); a.epi = cg::E_CONVT; a.bias = B.ct.has_bias ? B.ct.bias.p : nullptr;
                 a.x = xs.p; a.ldx = B.cout; a.hl = block_fused(B) ? nullptr : hA.p;     // the fused units read fp32 only
@@ -880,7 +897,7 @@ struct b2a_snac {
                     a.x = cur; a.y = oth; a.C = B.cout; a.mode = rf::MODE_RU; a.dil = R.dil;
                     a.dw_w = R.dw.w.p; a.dw_b = R.dw.has_bias ? R.dw.bias.p : nullptr; a.a_in = R.a0.p; a.a_mid = R.a2.p;
                     a.pw_bias = R.pw.has_bias ? R.pw.bias.p : nullptr;
-                    if (u == 2 && i + 1 < blocks.size()) {
+                    if (u == 2 && i + 1 < blocks.size() && !convt_fused_ok(i + 1)) {
                         x2_zero_edges_kernel<<<batch, 256, 0, s>>>(x2.p, (int)tout, B.cout);
                         count_launch();
                         a.hl = x2.p; a.a_next = blocks[i + 1].alpha.p;
