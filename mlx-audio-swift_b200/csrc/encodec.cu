@@ -92,20 +92,24 @@ __global__ void __launch_bounds__(256) ec_conv_kernel(ConvArgs a) {
 #pragma unroll
         for (int j = 0; j < RT; ++j) acc[i][j] = 0.f;
 
-    for (int k0 = 0; k0 < a.K; k0 += BK) {
-        // A tile: BM rows x 16 k (float4 per thread)
-        for (int e = tid; e < BM * 4; e += 256) {
+    // register double buffering: the global loads of k-tile i+1 are in flight while tile i is multiplied out of shared memory
+    constexpr int NA = (BM * 4 + 255) / 256, NX = (BT * 4 + 255) / 256;
+    float4 ra[NA], rx[NX];
+    auto load_tiles = [&](int k0) {
+#pragma unroll
+        for (int i = 0; i < NA; ++i) {
+            const int e = tid + i * 256;
             const int m = e >> 2, k4 = (e & 3) * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (m0 + m < a.M && k0 + k4 < a.K) v = *reinterpret_cast<const float4*>(a.A + (long long)(m0 + m) * a.K + k0 + k4);
-            As[k4 + 0][m] = v.x; As[k4 + 1][m] = v.y; As[k4 + 2][m] = v.z; As[k4 + 3][m] = v.w;
+            ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (e < BM * 4 && m0 + m < a.M && k0 + k4 < a.K) ra[i] = *reinterpret_cast<const float4*>(a.A + (long long)(m0 + m) * a.K + k0 + k4);
         }
-        // X tile: BT tokens x 16 k, gathered
-        for (int e = tid; e < BT * 4; e += 256) {
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+            const int e = tid + i * 256;
             const int t = e >> 2, k4 = (e & 3) * 4;
             const int q = q0 + t, kk = k0 + k4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (q < a.Lq && kk < a.K) {
+            if (e < BT * 4 && q < a.Lq && kk < a.K) {
                 if (kk < Ka) {
                     const int tap = kk / a.Ca, ci = kk - tap * a.Ca;
                     const int s = src_index(q, tap, a);
@@ -118,9 +122,33 @@ __global__ void __launch_bounds__(256) ec_conv_kernel(ConvArgs a) {
                     if (a.elu_b) { v.x = elu1(v.x); v.y = elu1(v.y); v.z = elu1(v.z); v.w = elu1(v.w); }
                 }
             }
-            Xs[k4 + 0][t] = v.x; Xs[k4 + 1][t] = v.y; Xs[k4 + 2][t] = v.z; Xs[k4 + 3][t] = v.w;
+            rx[i] = v;
         }
-        __syncthreads();
+    };
+    auto store_tiles = [&]() {
+#pragma unroll
+        for (int i = 0; i < NA; ++i) {
+            const int e = tid + i * 256;
+            if (e < BM * 4) {
+                const int m = e >> 2, k4 = (e & 3) * 4;
+                As[k4 + 0][m] = ra[i].x; As[k4 + 1][m] = ra[i].y; As[k4 + 2][m] = ra[i].z; As[k4 + 3][m] = ra[i].w;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+            const int e = tid + i * 256;
+            if (e < BT * 4) {
+                const int t = e >> 2, k4 = (e & 3) * 4;
+                Xs[k4 + 0][t] = rx[i].x; Xs[k4 + 1][t] = rx[i].y; Xs[k4 + 2][t] = rx[i].z; Xs[k4 + 3][t] = rx[i].w;
+            }
+        }
+    };
+    load_tiles(0);
+    store_tiles();
+    __syncthreads();
+    for (int k0 = 0; k0 < a.K; k0 += BK) {
+        const bool more = k0 + BK < a.K;
+        if (more) load_tiles(k0 + BK);
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
             float av[RM], xv[RT];
@@ -134,6 +162,10 @@ __global__ void __launch_bounds__(256) ec_conv_kernel(ConvArgs a) {
                 for (int j = 0; j < RT; ++j) acc[i][j] = fmaf(av[i], xv[j], acc[i][j]);
         }
         __syncthreads();
+        if (more) {
+            store_tiles();
+            __syncthreads();
+        }
     }
     float* outn = a.out + (long long)n * a.out_per_n;
     const float* resn = a.res ? a.res + (long long)n * a.out_per_n : nullptr;

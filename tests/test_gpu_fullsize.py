@@ -31,7 +31,7 @@ def test_orpheus3b_batch8_properties(b2a):
     P = b2a.GenerateParameters(max_tokens=G, temperature=0.0, top_p=1.0, repetition_penalty=1.3, repetition_context_size=20,
                                mask_eos=True, wrap_codes=True)
     toks, waves, info = tts.generate_batch(ids, P)
-    assert all(len(t) == G for t in toks) and info.generation_token_count == G
+    assert all(len(t) == G for t in toks) and info.generation_token_count == 8 * G      # the info counts every row
     assert toks[5] == toks[2]                                           # batched == serial: rows are independent
     frames = (L + G) // 7                                               # parseOutput on prompt + generated (LlamaTTS.swift:400-431)
     assert all(w is not None and len(w) == frames * 2048 and np.isfinite(w).all() for w in waves)
