@@ -254,6 +254,30 @@ int32_t b2a_tts_interleave(const int32_t* codes0, const int32_t* codes1, const i
                            int32_t n_frames, int32_t* code_list);
 void b2a_tts_destroy(b2a_tts* h);
 
+/* ------------------------------------------------------------------ weight / format plumbing
+ * Host-only.  Replaces MLX.loadArrays on *.safetensors (llamaTTSLoadWeights, LlamaTTS.swift:982-994: every file of a directory, later
+ * files win), WhisperModel.detectFormat / sanitize / remapMlxWhisperKey / whisperSinusoids (WhisperModel.swift:315-480),
+ * LlamaTTSModel.sanitize (LlamaTTS.swift:583-593) and the MLX affine de-quantisation behind quantize(model:) (:955-966).
+ * A b2a_weights handle keeps the files mapped; b2a_weights_get returns borrowed views valid until b2a_weights_free.
+ * F16 tensors are widened to F32, I64 narrowed to I32, U32 (packed quantised words) is reported as B2A_DTYPE_I32.
+ *   b2a_weights_sanitize_whisper: -> HF (`transformers`) names with the "model." prefix, conv weights in the PyTorch [out, in, k]
+ *     layout (what b2a_stt_create takes), missing encoder positions synthesised; *format = 0 huggingFace, 1 mlxWhisper.
+ *   b2a_weights_sanitize_llama: drops rotary inv_freq (and lm_head.weight when tied); bits > 0: every layer with a ".scales"
+ *     tensor is expanded to bf16 (w = scales * q + biases, value j of a uint32 word at bits [j*bits, (j+1)*bits); bits 2 / 4 / 8).
+ *   b2a_tts_config_from_json: config.json -> the b2a_llama_config struct, LlamaTTSConfig.swift:100-166, + the "quantization" block.
+ *   b2a_tts_create_from_directory = LlamaTTSModel.fromModelDirectory (LlamaTTS.swift:942-977) without tokenizer / SNAC download. */
+typedef struct b2a_weights b2a_weights;
+int32_t b2a_weights_load(const char* file_or_directory, b2a_weights** out);
+int32_t b2a_weights_count(const b2a_weights* w);
+int32_t b2a_weights_get(const b2a_weights* w, int32_t index, b2a_tensor* out);
+int32_t b2a_weights_sanitize_whisper(b2a_weights* w, int32_t* format);
+int32_t b2a_weights_sanitize_llama(b2a_weights* w, int32_t tie_word_embeddings, int32_t group_size, int32_t bits);
+void b2a_weights_free(b2a_weights* w);
+int32_t b2a_tts_config_from_json(const char* config_path, int32_t max_batch, int32_t max_context, b2a_llama_config* cfg,
+                                 int32_t* quant_group_size, int32_t* quant_bits);
+int32_t b2a_tts_create_from_directory(const char* model_dir, int32_t device, int32_t max_batch, int32_t max_context,
+                                      b2a_snac* snac, b2a_tts** out);
+
 /* ------------------------------------------------------------------ Vocos vocoder
  * Replaces class Vocos (Sources/MLXAudioCodecs/Vocos/Vocos.swift:284-322) behind AudioDecoderModel
  * (Sources/MLXAudioCodecs/AudioCodecModel.swift:4-13):

@@ -9,11 +9,12 @@ from .snac import SNAC
 from .llama_tts import AudioGenerationInfo, GenerateParameters, LlamaTTSModel
 from .vocos import Vocos
 from .encodec import Encodec, EncodecConfig, EncodecEncodedAudio
+from .loading import Weights, llama_config_from_json
 from .whisper import STTGenerateParameters, STTOutput, WhisperModel
 
 __all__ = ["AudioGenerationError", "IncrementalMelSpectrogram", "LogMel", "compute_mel_spectrogram", "hanning_window",
            "mel_filters", "whisper_encoder_features", "SNAC", "LlamaTTSModel", "GenerateParameters",
-           "AudioGenerationInfo", "Vocos", "Encodec", "EncodecConfig", "EncodecEncodedAudio", "WhisperModel", "STTGenerateParameters", "STTOutput"]
+           "AudioGenerationInfo", "Vocos", "Weights", "llama_config_from_json", "Encodec", "EncodecConfig", "EncodecEncodedAudio", "WhisperModel", "STTGenerateParameters", "STTOutput"]
 
 
 def device_count() -> int:

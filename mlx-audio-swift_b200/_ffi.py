@@ -151,6 +151,14 @@ SIGNATURES = {
     "b2a_encodec_decode": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "b2a_encodec_decode_dev": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),
     "b2a_encodec_destroy": (None, [_P]),
+    "b2a_weights_load": (C.c_int32, [C.c_char_p, C.POINTER(_P)]),
+    "b2a_weights_count": (C.c_int32, [_P]),
+    "b2a_weights_get": (C.c_int32, [_P, C.c_int32, C.POINTER(Tensor)]),
+    "b2a_weights_sanitize_whisper": (C.c_int32, [_P, C.POINTER(C.c_int32)]),
+    "b2a_weights_sanitize_llama": (C.c_int32, [_P, C.c_int32, C.c_int32, C.c_int32]),
+    "b2a_weights_free": (None, [_P]),
+    "b2a_tts_config_from_json": (C.c_int32, [C.c_char_p, C.c_int32, C.c_int32, C.POINTER(LlamaConfig), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "b2a_tts_create_from_directory": (C.c_int32, [C.c_char_p, C.c_int32, C.c_int32, C.c_int32, _P, C.POINTER(_P)]),
     "b2a_stt_create": (C.c_int32, [C.c_int32, C.POINTER(WhisperConfig), C.POINTER(Tensor), C.c_int32, C.POINTER(_P)]),
     "b2a_stt_create_random": (C.c_int32, [C.c_int32, C.POINTER(WhisperConfig), C.c_float, C.c_uint64, C.POINTER(_P)]),
     "b2a_stt_stream": (C.c_void_p, [_P]),

@@ -113,6 +113,22 @@ class LlamaTTSModel:
                                              C.byref(self._h)))
         del keep
 
+    @classmethod
+    def from_model_directory(cls, model_dir, snac: Optional[SNAC] = None, device: int = 0, max_batch: int = 8,
+                             max_context: int = 2048) -> "LlamaTTSModel":
+        """fromModelDirectory (LlamaTTS.swift:942-977): config.json + every *.safetensors -> sanitize -> MLX affine de-quantisation ->
+        weights on the device, all inside the library (b2a_tts_create_from_directory).  The tokenizer and the SNAC download of
+        post_load_hook (:595-602) stay with the host: pass `snac`."""
+        import json
+        from pathlib import Path
+        self = cls.__new__(cls)
+        self.config = json.loads((Path(model_dir) / "config.json").read_text())
+        self.vocab_size, self._snac_model = self.config["vocab_size"], snac
+        self._h = C.c_void_p()
+        _ffi.check(_ffi.lib().b2a_tts_create_from_directory(str(model_dir).encode(), device, max_batch, max_context,
+                                                            snac._h if snac else None, C.byref(self._h)))
+        return self
+
     # -- token plumbing -------------------------------------------------------------------------
     @staticmethod
     def prepare_input_ids(prompt_token_ids: Sequence[Sequence[int]]) -> Tuple[np.ndarray, np.ndarray]:

@@ -84,6 +84,27 @@ class WhisperModel:
         del keep
 
     @classmethod
+    def from_model_directory(cls, model_dir, device: int = 0, max_batch: int = 16) -> "WhisperModel":
+        """fromDirectory + sanitize (WhisperModel.swift:286-333): config.json + *.safetensors in either the HF (`openai/whisper-*`) or
+        the mlx-whisper (`mlx-community/whisper-*`) key layout; the remap, the conv re-layout and the sinusoid synthesis run in the
+        library (b2a_weights_sanitize_whisper)."""
+        import json
+        from pathlib import Path
+        from .loading import Weights
+        config = json.loads((Path(model_dir) / "config.json").read_text())
+        if "n_audio_state" in config:            # mlx-whisper / OpenAI dims (WhisperConfig.swift:94-131 accepts both spellings)
+            config = dict(vocab_size=config["n_vocab"], num_mel_bins=config["n_mels"], d_model=config["n_audio_state"],
+                          encoder_layers=config["n_audio_layer"], encoder_attention_heads=config["n_audio_head"],
+                          encoder_ffn_dim=4 * config["n_audio_state"], max_source_positions=config["n_audio_ctx"],
+                          decoder_layers=config["n_text_layer"], decoder_attention_heads=config["n_text_head"],
+                          decoder_ffn_dim=4 * config["n_text_state"], max_target_positions=config["n_text_ctx"])
+        w = Weights(model_dir)
+        w.sanitize_whisper()
+        tensors = w.tensors()
+        w.close()
+        return cls(config, tensors, device=device, max_batch=max_batch)
+
+    @classmethod
     def random_init(cls, config: dict, device: int = 0, max_batch: int = 16, std: float = 0.05, seed: int = 1234):
         self = cls.__new__(cls)
         self.config = config
