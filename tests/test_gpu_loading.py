@@ -94,7 +94,8 @@ def test_llama_from_model_directory_sharded_and_quantised(b2a, tmp_path):
     save_file_torch(shard2, str(d / "model-00002-of-00002.safetensors"))
     save_file({qname + ".weight": words.view(np.int32), qname + ".scales": scales, qname + ".biases": biases}, str(d / "model-quant.safetensors"))
     m = b2a.LlamaTTSModel.from_model_directory(d, max_batch=2, max_context=64)
-    assert np.array_equal(m(ids), ref)
+    got = m(ids)              # stream-K partial sums land with atomics: run-to-run differences of ~1e-6 are expected
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 2e-5
     (d / "config.json").write_text("{}")
     with pytest.raises(b2a.AudioGenerationError) as e:
         b2a.LlamaTTSModel.from_model_directory(d)
