@@ -422,6 +422,12 @@ int32_t b2a_stt_transcribe(b2a_stt* h, const float* pcm, int32_t batch, int64_t 
                            int32_t* tokens_out, int32_t* n_tokens_out, b2a_stt_info* info);
 int32_t b2a_stt_transcribe_dev(b2a_stt* h, const float* d_pcm, int32_t batch, int64_t n_samples,
                                const b2a_stt_params* params, int32_t* tokens_out, int32_t* n_tokens_out, b2a_stt_info* info);
+/* generate(audio:) beyond one window (WhisperModel.swift:95-182, chunkAudioFor30sWindows :165-182): consecutive 30 s windows of one
+ * mono 16 kHz signal, transcribed as a BATCH (the reference loops over them); tokens_out [n_chunks, params->max_tokens],
+ * n_tokens_out / offsets_s [n_chunks] (offsets_s nullable), *n_chunks_out = ceil(n / 480000) <= max_chunks. */
+int32_t b2a_stt_transcribe_long(b2a_stt* h, const float* pcm, int64_t n_samples, const b2a_stt_params* params, int32_t max_chunks,
+                                int32_t* tokens_out, int32_t* n_tokens_out, float* offsets_s, int32_t* n_chunks_out,
+                                b2a_stt_info* info);
 int32_t b2a_stt_cancel(b2a_stt* h);
 void b2a_stt_destroy(b2a_stt* h);
 

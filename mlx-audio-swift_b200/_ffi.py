@@ -166,6 +166,7 @@ SIGNATURES = {
     "b2a_stt_decoder_logits": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, _P]),
     "b2a_stt_transcribe": (C.c_int32, [_P, _P, C.c_int32, C.c_int64, C.POINTER(SttParams), _P, _P, C.POINTER(SttInfo)]),
     "b2a_stt_transcribe_dev": (C.c_int32, [_P, _P, C.c_int32, C.c_int64, C.POINTER(SttParams), _P, _P, C.POINTER(SttInfo)]),
+    "b2a_stt_transcribe_long": (C.c_int32, [_P, _P, C.c_int64, C.POINTER(SttParams), C.c_int32, _P, _P, _P, C.POINTER(C.c_int32), C.POINTER(SttInfo)]),
     "b2a_stt_cancel": (C.c_int32, [_P]),
     "b2a_stt_destroy": (None, [_P]),
 }

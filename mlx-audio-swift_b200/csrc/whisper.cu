@@ -1031,6 +1031,37 @@ int32_t b2a_stt_transcribe_dev(b2a_stt* h, const float* d_pcm, int32_t B, int64_
     return guarded([&] { stt_transcribe_impl(h, d_pcm, true, B, n, sp, tokens_out, n_tokens_out, info); });
 }
 
+// generate(audio:) on audio longer than one window (WhisperModel.swift:95-182): chunkAudioFor30sWindows cuts the mono signal into
+// consecutive 30 s windows (the last one shorter, zero-padded by padOrTrimToWindow inside transcribeChunk) and the reference
+// transcribes them ONE AT A TIME; the windows are independent, so here they go through the encoder / decoder as a batch
+// (groups of max_batch).  tokens_out [n_chunks, max_tokens], n_tokens_out [n_chunks], offsets_s [n_chunks] (chunk.offsetSeconds).
+int32_t b2a_stt_transcribe_long(b2a_stt* h, const float* pcm, int64_t n, const b2a_stt_params* sp, int32_t max_chunks,
+                                int32_t* tokens_out, int32_t* n_tokens_out, float* offsets_s, int32_t* n_chunks_out, b2a_stt_info* info) {
+    return guarded([&] {
+        B2A_CHECK(h && pcm && sp && tokens_out && n_tokens_out && n_chunks_out, B2A_ERR_INVALID_INPUT, "b2a_stt_transcribe_long: null argument");
+        const long long W = 480000;                                        // WhisperAudioConfig.chunkLengthSamples
+        const int chunks = n <= W ? 1 : (int)((n + W - 1) / W);
+        B2A_CHECK(n > 0 && chunks <= max_chunks, B2A_ERR_INVALID_INPUT, "b2a_stt_transcribe_long: more chunks than the output buffers hold");
+        *n_chunks_out = chunks;
+        const int MT = sp->max_tokens;
+        b2a_stt_info acc{}, part{};
+        std::vector<float> buf;
+        for (int c0 = 0; c0 < chunks; c0 += h->cfg.max_batch) {
+            const int nb = std::min(h->cfg.max_batch, chunks - c0);
+            buf.assign((size_t)nb * W, 0.f);
+            for (int i = 0; i < nb; ++i) {
+                const long long start = (long long)(c0 + i) * W, len = std::min<long long>(W, n - start);
+                memcpy(&buf[(size_t)i * W], pcm + start, (size_t)len * sizeof(float));
+                if (offsets_s) offsets_s[c0 + i] = (float)start / 16000.0f;
+            }
+            stt_transcribe_impl(h, buf.data(), false, nb, W, sp, tokens_out + (size_t)c0 * MT, n_tokens_out + c0, &part);
+            acc.prompt_tokens += part.prompt_tokens; acc.generation_tokens += part.generation_tokens; acc.decode_steps += part.decode_steps;
+            acc.encode_time += part.encode_time; acc.decode_time += part.decode_time; acc.total_time += part.total_time;
+        }
+        if (info) *info = acc;
+    });
+}
+
 int32_t b2a_stt_cancel(b2a_stt* h) {
     if (!h) return B2A_ERR_INVALID_INPUT;
     h->cancel.store(1);

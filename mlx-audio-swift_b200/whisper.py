@@ -179,6 +179,32 @@ class WhisperModel:
         return STTOutput([], info.prompt_tokens, info.generation_tokens, info.prompt_tokens + info.generation_tokens,
                          info.prompt_tokens / tt, info.generation_tokens / tt, info.total_time, info.encode_time, info.decode_time)
 
+    def generate_long(self, audio, generation_parameters: Optional[STTGenerateParameters] = None) -> STTOutput:
+        """generate(audio:) for ONE mono signal of any length (WhisperModel.swift:95-182): consecutive 30 s windows
+        (chunkAudioFor30sWindows :165-182), transcribed as a batch; `segments` carries (start, end) seconds per window like the
+        reference's allSegments; `tokens` is the per-window id lists (detokenise and join with " " on the host)."""
+        p = generation_parameters or self.default_generation_parameters
+        x = np.ascontiguousarray(audio, dtype=np.float32)
+        if x.ndim > 1:
+            x = np.ascontiguousarray(x.mean(axis=-1), dtype=np.float32)          # mono = audio.mean(axis: -1) (:98)
+        n = x.shape[0]
+        max_chunks = max(1, -(-n // 480000))
+        sp, keep = self._params(p)
+        toks = np.zeros((max_chunks, p.max_tokens), dtype=np.int32)
+        ntok = np.zeros(max_chunks, dtype=np.int32)
+        offs = np.zeros(max_chunks, dtype=np.float32)
+        nch = C.c_int32(0)
+        info = _ffi.SttInfo()
+        _ffi.check(_ffi.lib().b2a_stt_transcribe_long(self._h, _ffi.ptr(x), n, C.byref(sp), max_chunks, _ffi.ptr(toks), _ffi.ptr(ntok),
+                                                      _ffi.ptr(offs), C.byref(nch), C.byref(info)))
+        del keep
+        k = int(nch.value)
+        tt = max(info.total_time, 1e-9)
+        segs = [{"start": float(offs[i]), "end": float(offs[i]) + min(480000, n - i * 480000) / 16000.0} for i in range(k)]
+        return STTOutput([toks[i, :ntok[i]].tolist() for i in range(k)], info.prompt_tokens, info.generation_tokens,
+                         info.prompt_tokens + info.generation_tokens, info.prompt_tokens / tt, info.generation_tokens / tt,
+                         info.total_time, info.encode_time, info.decode_time, segs)
+
     def cancel(self) -> None:
         _ffi.check(_ffi.lib().b2a_stt_cancel(self._h))
 

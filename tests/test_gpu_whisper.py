@@ -102,3 +102,18 @@ def test_errors(b2a, tiny):
     bad = dict(hf_config(cfg)); bad["encoder_attention_heads"] = 4
     with pytest.raises(b2a.AudioGenerationError):
         b2a.WhisperModel(bad, W)
+
+
+def test_long_audio_is_chunked_into_30s_windows_and_batched(b2a, tiny):
+    # WhisperModel.swift:165-182: consecutive 30 s windows, last one shorter; each window == transcribing that slice alone
+    cfg, W, m = tiny
+    x = np.concatenate([dsp.synth_audio(480000, 5), dsp.synth_audio(480000, 6), dsp.synth_audio(160000, 7)])      # 70 s
+    P = b2a.STTGenerateParameters(max_tokens=6, mask_eot=True)
+    out = m.generate_long(x, P)
+    assert len(out.tokens) == 3 and [s["start"] for s in out.segments] == [0.0, 30.0, 60.0] and out.segments[2]["end"] == 70.0
+    for i, (lo, hi) in enumerate(((0, 480000), (480000, 960000), (960000, 1120000))):
+        assert out.tokens[i] == m.generate(x[lo:hi][None], P).tokens[0]
+    short = m.generate_long(x[:1000], P)                                   # <= one window: a single chunk (:169-171)
+    assert len(short.tokens) == 1 and short.segments[0]["start"] == 0.0
+    stereo = np.stack([x[:200000], x[:200000]], axis=-1)
+    assert m.generate_long(stereo, P).tokens == m.generate_long(x[:200000], P).tokens       # mono = mean over channels (:98)
