@@ -123,7 +123,7 @@ class LlamaTTSModel:
         from pathlib import Path
         self = cls.__new__(cls)
         self.config = json.loads((Path(model_dir) / "config.json").read_text())
-        self.vocab_size, self._snac_model = self.config["vocab_size"], snac
+        self.vocab_size, self._snac_model = self.config.get("vocab_size", 0), snac      # a bad config.json is the library's error to raise
         self._h = C.c_void_p()
         _ffi.check(_ffi.lib().b2a_tts_create_from_directory(str(model_dir).encode(), device, max_batch, max_context,
                                                             snac._h if snac else None, C.byref(self._h)))
