@@ -62,6 +62,11 @@ __device__ __forceinline__ float snake(float v, float al) {
     const float s = fast_sin(al * v);
     return v + (1.0f / (al + 1e-9f)) * s * s;
 }
+// same with the per-channel 1 / (alpha + 1e-9) computed once by the caller
+__device__ __forceinline__ float snake_inv(float v, float al, float inv) {
+    const float s = fast_sin(al * v);
+    return fmaf(inv * s, s, v);
+}
 __device__ __forceinline__ float gauss(unsigned long long seed, unsigned long long idx) {
     unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (idx + 1);
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -162,6 +167,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (a.alpha) al = a.alpha[m];
                 if (a.gamma) gm = a.gamma[m];
             }
+            const float inv_al = 1.0f / (al + 1e-9f);
             const long long n_first = (long long)nt * HALF + c0;
             // everything that does not depend on the accumulator is fetched BEFORE waiting for the MMA: the residual /
             // read-modify-write operand (16 independent loads) and the NoiseBlock noise (one value per token: lane j computes
@@ -212,7 +218,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     a.x[n * a.ldx + m] = val;
                     if (a.epi == E_ADD) continue;
                 }
-                if (a.alpha) val = snake(val, al);
+                if (a.alpha) val = snake_inv(val, al, inv_al);
                 if (a.dual) {
                     const long long b = n / a.T, tt = n - b * a.T;
                     const long long row = b * (a.T + 1) + tt;

@@ -23,6 +23,14 @@
 
 namespace b2a {
 
+__device__ __forceinline__ float snake_fi(float x, float alpha, float inv) {      // 1 / (alpha + 1e-9) hoisted by the caller
+    const float ax = alpha * x;
+    const float k = rintf(ax * 0.15915494309189535f);
+    float r = fmaf(k, -6.28318548202514648f, ax);
+    r = fmaf(k, 1.7484555e-7f, r);
+    const float s = __sinf(r);
+    return fmaf(inv * s, s, x);
+}
 __device__ __forceinline__ float snake_f(float x, float alpha) {
     // Layers.swift:44-50: x + 1/(alpha + 1e-9) * sin(alpha*x)^2
     // explicit 2*pi range reduction + MUFU.SIN (|error| < 5e-7): libdevice sinf is ~40 dependent instructions per call
@@ -408,7 +416,8 @@ dw7_nlc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, con
                 v = *reinterpret_cast<const float4*>(xb + (long long)t * C + c0 + c);
                 if (alpha_in) {
                     const float4 al = *reinterpret_cast<const float4*>(alpha_in + c0 + c);
-                    v.x = snake_f(v.x, al.x); v.y = snake_f(v.y, al.y); v.z = snake_f(v.z, al.z); v.w = snake_f(v.w, al.w);
+                    v.x = snake_fi(v.x, al.x, 1.0f / (al.x + 1e-9f)); v.y = snake_fi(v.y, al.y, 1.0f / (al.y + 1e-9f));
+                    v.z = snake_fi(v.z, al.z, 1.0f / (al.z + 1e-9f)); v.w = snake_fi(v.w, al.w, 1.0f / (al.w + 1e-9f));
                 }
             }
             *reinterpret_cast<float4*>(dsm + (size_t)r * CT + c) = v;
@@ -434,6 +443,7 @@ dw7_nlc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, con
     for (int k = 0; k < 7; ++k) { wa[k] = w[(c0 + c) * 7 + k]; wb[k] = w[(c0 + c + 1) * 7 + k]; }
     const float ba = bias ? bias[c0 + c] : 0.f, bb = bias ? bias[c0 + c + 1] : 0.f;
     const float aoa = alpha_out ? alpha_out[c0 + c] : 0.f, aob = alpha_out ? alpha_out[c0 + c + 1] : 0.f;
+    const float ioa = 1.0f / (aoa + 1e-9f), iob = 1.0f / (aob + 1e-9f);
     for (int tt = grp; tt < DWN_TT; tt += ngrp) {
         const int t = t0 + tt;
         if (t >= T) break;
@@ -443,7 +453,7 @@ dw7_nlc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, con
             const float2 xv = *reinterpret_cast<const float2*>(dsm + (size_t)(tt + k * dil) * CT + c);
             va = fmaf(wa[k], xv.x, va); vb = fmaf(wb[k], xv.y, vb);
         }
-        if (alpha_out) { va = snake_f(va, aoa); vb = snake_f(vb, aob); }
+        if (alpha_out) { va = snake_fi(va, aoa, ioa); vb = snake_fi(vb, aob, iob); }
         const long long tok = (long long)b * T + t;
         const long long r = (tok / 64) * 128 + (tok % 64);
         const __nv_bfloat162 hi = __floats2bfloat162_rn(va, vb);
@@ -477,16 +487,20 @@ final_nlc_kernel(const float* __restrict__ x, float* __restrict__ wave, const fl
     extern __shared__ __align__(16) float fsm[];     // [(256 + 6)][64]
     const int t0 = blockIdx.x * FN_TT, b = blockIdx.y;
     const float* xb = x + (long long)b * T * FN_MAXC;
-    for (int i = threadIdx.x; i < (FN_TT + 6) * 16; i += FN_THREADS) {
-        const int r = i >> 4, c = (i & 15) * 4;
-        const int t = t0 + r - 3;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (t >= 0 && t < T) {
-            v = *reinterpret_cast<const float4*>(xb + (long long)t * FN_MAXC + c);
-            const float4 al = *reinterpret_cast<const float4*>(alpha + c);
-            v.x = snake_f(v.x, al.x); v.y = snake_f(v.y, al.y); v.z = snake_f(v.z, al.z); v.w = snake_f(v.w, al.w);
+    {   // FN_THREADS is a multiple of 16: a thread always stages the same 4 channels
+        const int c = (threadIdx.x & 15) * 4;
+        const float4 al = *reinterpret_cast<const float4*>(alpha + c);
+        const float4 iv = make_float4(1.0f / (al.x + 1e-9f), 1.0f / (al.y + 1e-9f), 1.0f / (al.z + 1e-9f), 1.0f / (al.w + 1e-9f));
+        for (int i = threadIdx.x; i < (FN_TT + 6) * 16; i += FN_THREADS) {
+            const int r = i >> 4;
+            const int t = t0 + r - 3;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t >= 0 && t < T) {
+                v = *reinterpret_cast<const float4*>(xb + (long long)t * FN_MAXC + c);
+                v.x = snake_fi(v.x, al.x, iv.x); v.y = snake_fi(v.y, al.y, iv.y); v.z = snake_fi(v.z, al.z, iv.z); v.w = snake_fi(v.w, al.w, iv.w);
+            }
+            *reinterpret_cast<float4*>(fsm + r * FN_MAXC + c) = v;
         }
-        *reinterpret_cast<float4*>(fsm + r * FN_MAXC + c) = v;
     }
     const int cgp = threadIdx.x & 7, tg = threadIdx.x >> 3;     // 8 channel groups x 32 token groups
     float wk[8][7];
