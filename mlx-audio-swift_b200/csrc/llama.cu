@@ -1190,10 +1190,6 @@ static std::vector<float> llama3_freqs(const b2a_llama_config& c) {
     return f;
 }
 
-struct NormTail {                 // add+RMSNorm executed by extra CTAs of the producing GEMM (tc_gemm.cuh "norm tail")
-    const float* w = nullptr; float* trace = nullptr; float* zero_ptr = nullptr; int zero_n = 0;
-};
-
 struct LayerW {
     DBuf<bf16> wqkv, wo, wgu, wdown;
     DBuf<float> ln1, ln2;
@@ -1219,8 +1215,6 @@ struct b2a_tts {
     // attention workspace (flash-decoding partials)
     DBuf<float> part_o, part_ml;
     DBuf<int> at_counters;
-    DBuf<unsigned> tail_cnt;         // [2] counters of the GEMM norm tail (tc_gemm.cuh)
-    bool norm_tail = true;           // B2A_NORM=kernel: separate add_rmsnorm launches after the O / DOWN GEMMs
     DBuf<unsigned> chain_bars;       // [3][16] grid-barrier counters of the GEMM chain kernel (tc_chain.cuh)
     bool use_chain = false;          // B2A_CHAIN=1: experimental persistent GEMM-chain kernel (tc_chain.cuh); measured slower, see DESIGN.md
     int chain_seq = 0, chain_stages = 12;
@@ -1382,9 +1376,6 @@ struct b2a_tts {
         part_ml.alloc((size_t)B * nkv * at_splits * G * 2);
         at_counters.alloc((size_t)B * nkv);
         B2A_CUDA(cudaMemset(at_counters.p, 0, (size_t)B * nkv * sizeof(int)));
-        tail_cnt.alloc(2);
-        B2A_CUDA(cudaMemset(tail_cnt.p, 0, 2 * sizeof(unsigned)));
-        { const char* e = getenv("B2A_NORM"); norm_tail = !(e && std::string(e) == "kernel") && H == tc::THREADS * 16; }
         chain_bars.alloc(chain::NSETS * chain::SET_STRIDE);
         B2A_CUDA(cudaMemset(chain_bars.p, 0, chain::NSETS * chain::SET_STRIDE * sizeof(unsigned)));
         {
@@ -1573,13 +1564,9 @@ struct b2a_tts {
     static constexpr int L2PF_DEFAULT = 0;
 
     void tc_gemm(const CUtensorMap& tmW, const CUtensorMap& tmX, int op, float* yout, bf16* actout, int B, int M, int K,
-                 cudaStream_t s, L2Prefetch pf = L2Prefetch{nullptr, 0}, const NormTail& nt = NormTail{}) {
+                 cudaStream_t s, L2Prefetch pf = L2Prefetch{nullptr, 0}) {
         tc::Args a{};
         a.pf_ptr = pf.ptr; a.pf_bytes = pf.bytes;
-        if (nt.w) {
-            a.tail_x = x.p; a.tail_delta = yout; a.tail_w = nt.w; a.tail_xn = xn.p; a.tail_trace = nt.trace; a.tail_zero = nt.zero_ptr;
-            a.tail_zero_n = nt.zero_n; a.tail_cnt = tail_cnt.p; a.tail_rows = B; a.tail_H = cfg.hidden_size; a.tail_eps = cfg.rms_norm_eps;
-        }
         a.out_f32 = yout; a.out_bf16 = actout; a.M = M; a.N = B; a.K = K;
         a.m_tiles = cdiv(M, tc::BM); a.k_blocks = K / tc::BK;
         a.stages = 6;   // 6 x 18 KB ring: two GEMM CTAs (this kernel's and the next kernel's prefetching one) fit per SM
@@ -1595,11 +1582,10 @@ struct b2a_tts {
             a.ldo = M; a.epi_full = tc::EPI_STORE; a.epi_partial = tc::EPI_ATOMIC; a.lo_rows = 0;
             ctas = (int)std::min<long long>(num_sms, (long long)a.m_tiles * a.k_blocks);
         }
-        a.tail_gemm_ctas = ctas;
-        tc::launch<16>(tmW, tmX, a, ctas + (nt.w ? B : 0), 1, s);
+        tc::launch<16>(tmW, tmX, a, ctas, 1, s);
     }
 
-    void gemm(int op, int layer, int B, cudaStream_t s, const NormTail& nt = NormTail{}) {
+    void gemm(int op, int layer, int B, cudaStream_t s) {
         const int H = cfg.hidden_size, I = cfg.intermediate_size, NQ = cfg.num_attention_heads * HD,
                   NKV = cfg.num_key_value_heads * HD;
         LayerW* L = layer >= 0 ? &layers[layer] : nullptr;
@@ -1609,7 +1595,7 @@ struct b2a_tts {
                 else gemv_nb(op, L->wqkv.p, xn.p, qkv.p, nullptr, NQ + 2 * NKV, H, s);
                 break;
             case OP_O:
-                if (use_tc) tc_gemm(tm_o[layer], tmx_attn, op, y.p, nullptr, B, H, NQ, s, pf_of(L2_O, layer), nt);
+                if (use_tc) tc_gemm(tm_o[layer], tmx_attn, op, y.p, nullptr, B, H, NQ, s, pf_of(L2_O, layer));
                 else gemv_nb(op, L->wo.p, attn.p, y.p, nullptr, H, NQ, s);
                 break;
             case OP_GU:
@@ -1617,7 +1603,7 @@ struct b2a_tts {
                 else gemv_nb(op, L->wgu.p, xn.p, nullptr, act.p, 2 * I, H, s);
                 break;
             case OP_DOWN:
-                if (use_tc) tc_gemm(tm_down[layer], tmx_act, op, y.p, nullptr, B, H, I, s, pf_of(L2_DOWN, layer), nt);
+                if (use_tc) tc_gemm(tm_down[layer], tmx_act, op, y.p, nullptr, B, H, I, s, pf_of(L2_DOWN, layer));
                 else gemv_nb(op, L->wdown.p, act.p, y.p, nullptr, H, I, s);
                 break;
             default:
@@ -1711,43 +1697,29 @@ struct b2a_tts {
     }
 
     // embed(tokens) -> all layers; leaves the residual stream in x and the last MLP output in y
-    bool norm_tail_ok() const { return use_tc && norm_tail && getenv("B2A_SKIP") == nullptr; }
     void run_layers(int B, cudaStream_t s) {
         if (chain_ok()) { run_layers_chain(B, s, false); return; }
         const int H = cfg.hidden_size, nq = cfg.num_attention_heads, nkv = cfg.num_key_value_heads;
         const int QKV_N = (nq + 2 * nkv) * HD, G = nq / nkv;
         launch_pdl(embed_kernel, dim3(B), dim3(256), 0, s, tokens.p, embed.p, x.p, y.p, H, cfg.vocab_size);
         const size_t kv_layer = (size_t)cfg.max_batch * nkv * cfg.max_context * HD;
-        // norm tail: the add+RMSNorm after the O / DOWN GEMM runs in 8 extra CTAs of that GEMM (no kernel boundary); only the very
-        // first norm of the step and the final norm (run_lm_head) stay separate launches
-        const bool tail = norm_tail_ok();
-        auto tr = [&](int idx) { return trace_on ? trace.p + (size_t)idx * 8 * H : (float*)nullptr; };
         for (int l = 0; l < cfg.num_hidden_layers; ++l) {
             LayerW& L = layers[l];
-            if (!skip("norm") && !(tail && l > 0))
+            if (!skip("norm"))
             launch_pdl(add_rmsnorm_kernel, dim3(B), dim3(RN_THREADS), 0, s, x.p, l == 0 ? (float*)nullptr : y.p, L.ln1.p, xn.p, H,
-                       cfg.rms_norm_eps, tr(2 * l), (float*)nullptr, 0, LO_ROW, pf_of(L2_NORM1, l));
+                       cfg.rms_norm_eps, trace_on ? trace.p + (size_t)(2 * l) * 8 * H : (float*)nullptr, (float*)nullptr, 0, LO_ROW,
+                       pf_of(L2_NORM1, l));
             if (!skip("gemm") && !skip("qkv")) gemm(OP_QKV, l, B, s);
             AttnArgs aa{qkv.p, pos.p, freqs.p, kcache.p + l * kv_layer, vcache.p + l * kv_layer, attn.p, part_o.p, part_ml.p,
                         at_counters.p, nq, nkv, cfg.max_context, at_splits, 1.0f / sqrtf((float)HD), pf_of(L2_ATTN, l)};
             if (!skip("attn")) attn_launch(aa, B, s);
-            if (tail) {
-                NormTail n2; n2.w = L.ln2.p; n2.trace = tr(2 * l + 1); n2.zero_ptr = qkv.p; n2.zero_n = QKV_N;
-                gemm(OP_O, l, B, s, n2);
-            } else {
-                if (!skip("gemm") && !skip("o_proj")) gemm(OP_O, l, B, s);
-                // also zeroes this row of q|k|v so the next layer's stream-K QKV GEMM can accumulate into it
-                if (!skip("norm"))
-                launch_pdl(add_rmsnorm_kernel, dim3(B), dim3(RN_THREADS), 0, s, x.p, y.p, L.ln2.p, xn.p, H, cfg.rms_norm_eps,
-                           tr(2 * l + 1), qkv.p, QKV_N, LO_ROW, pf_of(L2_NORM2, l));
-            }
+            if (!skip("gemm") && !skip("o_proj")) gemm(OP_O, l, B, s);
+            // also zeroes this row of q|k|v so the next layer's stream-K QKV GEMM can accumulate into it
+            if (!skip("norm"))
+            launch_pdl(add_rmsnorm_kernel, dim3(B), dim3(RN_THREADS), 0, s, x.p, y.p, L.ln2.p, xn.p, H, cfg.rms_norm_eps,
+                       trace_on ? trace.p + (size_t)(2 * l + 1) * 8 * H : (float*)nullptr, qkv.p, QKV_N, LO_ROW, pf_of(L2_NORM2, l));
             if (!skip("gemm") && !skip("gate")) gemm(OP_GU, l, B, s);
-            if (tail && l + 1 < cfg.num_hidden_layers) {
-                NormTail n1; n1.w = layers[l + 1].ln1.p; n1.trace = tr(2 * l + 2);
-                gemm(OP_DOWN, l, B, s, n1);
-            } else if (!skip("gemm") && !skip("down")) {
-                gemm(OP_DOWN, l, B, s);
-            }
+            if (!skip("gemm") && !skip("down")) gemm(OP_DOWN, l, B, s);
         }
         (void)G;
     }
@@ -1876,9 +1848,8 @@ struct b2a_tts {
         B2A_CUDA(cudaGraphInstantiate(&g_prefill, g, 0));
         cudaGraphDestroy(g);
         g_nb = B; g_args = sa; g_L = L;
-        const int per_step_layers = norm_tail_ok() ? cfg.num_hidden_layers * 5 + 1 : cfg.num_hidden_layers * 7;
-        launches_step = chain_ok() ? 2 + cfg.num_hidden_layers * 2 + 1 : 1 + per_step_layers + 2 + 1;
-        launches_prefill = chain_ok() ? 2 + cfg.num_hidden_layers * 2 + 1 : 1 + per_step_layers + 1;
+        launches_step = chain_ok() ? 2 + cfg.num_hidden_layers * 2 + 1 : 1 + cfg.num_hidden_layers * 7 + 2 + 1;
+        launches_prefill = chain_ok() ? 2 + cfg.num_hidden_layers * 2 + 1 : 1 + cfg.num_hidden_layers * 7 + 1;
     }
     int g_L = 0, launches_step = 0, launches_prefill = 0;
 };

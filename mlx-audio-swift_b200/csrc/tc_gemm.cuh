@@ -36,14 +36,6 @@ struct Args {
                              // j + BN/2 of the accumulator are summed, giving fp32-activation accuracy for free
     const float* bias;       // nullable [M]: added to every output column before the activation
     int act;                 // ACT_NONE | ACT_GELU (exact erf GELU, WhisperLayers.swift:101)
-    // ---- norm tail (decode step): the kernel is launched with `tail_rows` EXTRA CTAs after the `tail_gemm_ctas` GEMM CTAs.  A GEMM CTA
-    // bumps tail_cnt[0] when its last output is written; tail CTA b waits for all of them and then does what add_rmsnorm_kernel
-    // did for row b (x += delta, delta = 0, xn = hi/lo(x * rsqrt(mean x^2 + eps) * w), zero zero_ptr[b]) -- without a kernel
-    // boundary in between (3-5 us each, 57 per step).  tail_x == nullptr: plain GEMM.
-    float* tail_x; float* tail_delta; const float* tail_w; __nv_bfloat16* tail_xn; float* tail_trace; float* tail_zero;
-    unsigned* tail_cnt;      // [2], zero between launches (the last tail CTA resets it)
-    int tail_gemm_ctas, tail_rows, tail_H, tail_zero_n;
-    float tail_eps;
     const void* pf_ptr;      // optional L2 prefetch of a later GEMM's weights (issued by the epilogue warps at kernel start)
     long long pf_bytes;
     int lo_rows;             // != 0: bf16 outputs are written as hi/lo pairs in the same tile-interleaved row layout the
@@ -145,7 +137,7 @@ template <int BN>
 struct Smem {
     static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE = A_BYTES + B_BYTES;
     static constexpr int TMEM_COLS = (2 * BN) <= 32 ? 32 : (2 * BN) <= 64 ? 64 : (2 * BN) <= 128 ? 128 : (2 * BN) <= 256 ? 256 : 512;
-    static int max_stages() { return (226 * 1024 - 1024 - 256) / STAGE; }
+    static int max_stages() { return (227 * 1024 - 1024 - 256) / STAGE; }
     static size_t bytes(int stages) { return 1024 + (size_t)stages * STAGE + 256; }
 };
 
@@ -164,62 +156,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.y * BN;
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: let the next kernel's prologue start
-    const int grid_x = a.tail_x ? a.tail_gemm_ctas : (int)gridDim.x;  // CTAs that share the GEMM
-    if (a.tail_x && (int)blockIdx.x >= a.tail_gemm_ctas) {
-        // ------------------------------------------------------------------ norm tail CTA: row b of the residual stream
-        __shared__ float tred[THREADS / 32];
-        const int b = (int)blockIdx.x - a.tail_gemm_ctas, H = a.tail_H, tid = threadIdx.x;
-        asm volatile("griddepcontrol.wait;" ::: "memory");
-        if (tid == 0) {
-            unsigned v;
-            for (;;) {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.tail_cnt) : "memory");
-                if (v >= (unsigned)a.tail_gemm_ctas) break;
-                __nanosleep(32);
-            }
-        }
-        __syncthreads();
-        constexpr int NV = 4;                                         // float4 per thread: H == THREADS * 4 * NV (3072)
-        const float4* xr = reinterpret_cast<const float4*>(a.tail_x + (long long)b * H);
-        const float4* dr = reinterpret_cast<const float4*>(a.tail_delta + (long long)b * H);
-        float4 xv[NV], dv[NV];
-#pragma unroll
-        for (int j = 0; j < NV; ++j) { xv[j] = __ldcg(xr + tid + j * THREADS); dv[j] = __ldcg(dr + tid + j * THREADS); }
-        float ss = 0.f;
-#pragma unroll
-        for (int j = 0; j < NV; ++j) {
-            xv[j].x += dv[j].x; xv[j].y += dv[j].y; xv[j].z += dv[j].z; xv[j].w += dv[j].w;
-            ss = fmaf(xv[j].x, xv[j].x, ss); ss = fmaf(xv[j].y, xv[j].y, ss); ss = fmaf(xv[j].z, xv[j].z, ss); ss = fmaf(xv[j].w, xv[j].w, ss);
-            reinterpret_cast<float4*>(a.tail_x + (long long)b * H)[tid + j * THREADS] = xv[j];
-            reinterpret_cast<float4*>(a.tail_delta + (long long)b * H)[tid + j * THREADS] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (a.tail_trace) reinterpret_cast<float4*>(a.tail_trace + (long long)b * H)[tid + j * THREADS] = xv[j];
-        }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-        if (lane == 0) tred[warp] = ss;
-        __syncthreads();
-        float tot = 0.f;
-#pragma unroll
-        for (int i = 0; i < THREADS / 32; ++i) tot += tred[i];
-        const float r = rsqrtf(tot / (float)H + a.tail_eps);
-#pragma unroll
-        for (int j = 0; j < NV; ++j) {
-            const int i4 = tid + j * THREADS;
-            const float4 wv = reinterpret_cast<const float4*>(a.tail_w)[i4];
-            const float g[4] = {xv[j].x * r * wv.x, xv[j].y * r * wv.y, xv[j].z * r * wv.z, xv[j].w * r * wv.w};
-            __nv_bfloat16 hi[4], lo[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { hi[k] = __float2bfloat16_rn(g[k]); lo[k] = __float2bfloat16_rn(g[k] - __bfloat162float(hi[k])); }
-            *reinterpret_cast<uint2*>(a.tail_xn + (long long)b * H + 4 * i4) = *reinterpret_cast<const uint2*>(hi);
-            *reinterpret_cast<uint2*>(a.tail_xn + (long long)(b + 8) * H + 4 * i4) = *reinterpret_cast<const uint2*>(lo);
-        }
-        if (a.tail_zero)
-            for (int i = tid; i < a.tail_zero_n; i += THREADS) a.tail_zero[(long long)b * a.tail_zero_n + i] = 0.f;
-        if (tid == 0) {                                               // the last tail CTA re-arms the counters for the next launch
-            if (atomicAdd(a.tail_cnt + 1, 1u) == (unsigned)(a.tail_rows - 1)) { a.tail_cnt[0] = 0u; a.tail_cnt[1] = 0u; }
-        }
-        return;
-    }
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -238,11 +174,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const long long units = (long long)a.m_tiles * a.k_blocks;
     long long u0, u1;
     if (a.epi_partial >= 0) {
-        u0 = units * blockIdx.x / grid_x;
-        u1 = units * (blockIdx.x + 1) / grid_x;
+        u0 = units * blockIdx.x / gridDim.x;
+        u1 = units * (blockIdx.x + 1) / gridDim.x;
     } else {   // whole tiles per CTA (epilogues that cannot be split along K, e.g. SwiGLU)
-        u0 = ((long long)a.m_tiles * blockIdx.x / grid_x) * a.k_blocks;
-        u1 = ((long long)a.m_tiles * (blockIdx.x + 1) / grid_x) * a.k_blocks;
+        u0 = ((long long)a.m_tiles * blockIdx.x / gridDim.x) * a.k_blocks;
+        u1 = ((long long)a.m_tiles * (blockIdx.x + 1) / gridDim.x) * a.k_blocks;
     }
 
     if (warp == 0) {
@@ -308,7 +244,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else {
         if (a.pf_ptr) {
             constexpr long long CH = 8192;
-            const long long w = (long long)blockIdx.x * 128 + (threadIdx.x - 64), nw = (long long)grid_x * 128;
+            const long long w = (long long)blockIdx.x * 128 + (threadIdx.x - 64), nw = (long long)gridDim.x * 128;
             for (long long off = w * CH; off < a.pf_bytes; off += nw * CH) {
                 const unsigned n = (unsigned)(a.pf_bytes - off < CH ? ((a.pf_bytes - off) & ~15ll) : CH);
                 if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"((const char*)a.pf_ptr + off), "r"(n) : "memory");
@@ -419,11 +355,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-        }
-        if (a.tail_x) {                                               // every output of this CTA is written: tell the norm tail
-            __threadfence();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (threadIdx.x == 64) atomicAdd(a.tail_cnt, 1u);
         }
     }
     tc_fence_before();

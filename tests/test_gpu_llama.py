@@ -199,25 +199,3 @@ def test_batched_prefill_matches_stepwise_and_oracle(b2a, tiny, monkeypatch, B, 
     assert a == ref
     # after a batched prefill the KV cache must be what the decode path expects: continue with forward_logits
     nxt = np.asarray([[t[-1]] for t in a], dtype=np.int32)
-
-
-def test_norm_tail_path_vs_oracle_and_separate_norm_kernels(b2a, monkeypatch):
-    """hidden_size 3072 enables the GEMM norm tail (add+RMSNorm in 8 extra CTAs of the O / DOWN GEMM, tc_gemm.cuh): logits against
-    the oracle, greedy tokens bit-exact, and agreement with the separate add_rmsnorm launches (B2A_NORM=kernel)."""
-    cfg = ol.LlamaConfig(hidden_size=3072, num_hidden_layers=3, intermediate_size=512, num_attention_heads=24,
-                         num_key_value_heads=8, head_dim=128, vocab_size=1024)
-    W = ol.init_weights(cfg, 11, std=0.03)
-    m = b2a.LlamaTTSModel(hf_config(cfg), W, max_batch=8, max_context=64)
-    ids = np.random.default_rng(3).integers(0, 1024, size=(8, 7)).astype(np.int32)
-    lg = m(ids)
-    orc = ol.LlamaOracle(cfg, W, round_acts=False)
-    ref = orc.forward(torch.as_tensor(ids)).numpy()
-    assert rel_err(lg, ref) < 1e-4, rel_err(lg, ref)
-    monkeypatch.setenv("B2A_NORM", "kernel")
-    m2 = b2a.LlamaTTSModel(hf_config(cfg), W, max_batch=8, max_context=64)
-    monkeypatch.delenv("B2A_NORM")
-    assert rel_err(m2(ids), lg) < 1e-5
-    P = type(m.default_generation_parameters)(max_tokens=9, temperature=0.0, top_p=1.0, repetition_penalty=1.3,
-                                              repetition_context_size=20, mask_eos=True)
-    toks, _, _ = m.generate_batch(ids[:3], P, decode_audio=False)
-    assert toks == ol.generate_tokens(orc, ids[:3], 9, temperature=0.0, rep_penalty=1.3, rep_context=20, mask_eos=True)
