@@ -347,11 +347,11 @@ def main():
                 "h2d_bytes_per_step": int(ids_host.numel() * 4), "d2h_bytes_per_step": int(wave_host.numel() * 4 + toks_host.numel() * 4)},
         "gpu_launches": int(launches),
         "stages_s": {"prefill": infos[-1].prefill_time, "decode": infos[-1].generate_time, "codec": infos[-1].codec_time},
-        "roofline": {"kernel": "decode step (CUDA graph: 28 x [rmsnorm, qkv tcgen05 gemm, flash-decode attention, o gemm, rmsnorm, "
+        "roofline": {"kernel": "decode step (CUDA graph: 28 x [rmsnorm, qkv tcgen05 gemm, 2-CTA-cluster attention, o gemm, rmsnorm, "
                                "gate/up gemm+swiglu, down gemm] + lm-head gemm + sampler); dominant kernel tc_gemm_kernel<16>", "bound": "hbm", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": int(alg_bytes * 1.018), "peak_source": peak_src,
-                     "traffic_source": "ncu --set full on tc_gemm_kernel<16> (profiles/r01_tc_gemm_ncu_full.md): dram bytes / algorithmic "
-                                       "bytes = 1.01-1.04 per GEMM launch, 1.018 weighted; applied to the step's algorithmic bytes",
+                     "traffic_source": "ncu --set full on tc_gemm_kernel<16> (profiles/r01_tc_gemm_ncu_full.md, r01_ncu_full_summary.md): dram bytes / "
+                                       "algorithmic bytes = 1.00-1.04 per GEMM launch, 1.018 weighted; applied to the step's algorithmic bytes",
                      "algorithmic_bytes_per_step": alg_bytes, "ms_per_decode_step": step_ms, "context": ctx},
         "clocks": clocks,
     }
