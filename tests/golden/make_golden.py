@@ -12,6 +12,8 @@ import torch
 ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 from oracle import dsp, llama, snac  # noqa: E402
+from oracle import encodec as oe  # noqa: E402
+from oracle import vocos as ov  # noqa: E402
 from oracle import whisper as ow  # noqa: E402
 
 OUT = Path(__file__).resolve().parent
@@ -87,7 +89,28 @@ def whisper_tiny():
                         enc_rows=enc[0, [0, 1, 700, 1499]].astype(np.float32), first_logits_stats=stats(np.clip(logits[0], -50, 50)))
 
 
+def codecs_small():
+    """Vocos (reference test geometry, 2 layers to keep it small) and Encodec-24 kHz decode: first-N + stats."""
+    vc = ov.VocosConfig(num_layers=2)
+    VW = ov.init_weights(vc, 7)
+    f = np.random.default_rng(1).standard_normal((2, 37, vc.input_channels)).astype(np.float32)
+    y = ov.decode(vc, VW, f)
+    ec = oe.EncodecConfig()
+    EW = oe.init_weights(ec, 7, n_codebooks=8)
+    codes = np.random.default_rng(1).integers(0, 1024, size=(1, 3, 8, 41))
+    z = oe.decode(ec, EW, codes)
+    np.savez_compressed(OUT / "codecs.npz", vocos_first=y[:, :64].astype(np.float32), vocos_stats=stats(y), vocos_shape=np.array(y.shape),
+                        encodec_first=z[:, :64, 0].astype(np.float32), encodec_last=z[:, -64:, 0].astype(np.float32),
+                        encodec_stats=stats(z), encodec_shape=np.array(z.shape))
+
+
 if __name__ == "__main__":
-    mel(); snac_small(); llama_tiny(); whisper_tiny()
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=None, help="regenerate a single fixture (mel | snac | llama | whisper | codecs)")
+    only = ap.parse_args().only
+    for name, fn in (("mel", mel), ("snac", snac_small), ("llama", llama_tiny), ("whisper", whisper_tiny), ("codecs", codecs_small)):
+        if only is None or only == name:
+            fn()
     for f in sorted(OUT.glob("*.npz")):
         print(f.name, f.stat().st_size)

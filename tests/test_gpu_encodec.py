@@ -93,3 +93,18 @@ def test_errors(b2a):
     with pytest.raises(E) as e:
         make(b2a, cfg, W2)
     assert e.value.case == "modelNotInitialized"
+
+
+def test_decode_vs_committed_golden(b2a):
+    """tests/golden/codecs.npz: first / last 64 samples and the (mean, |mean|, min, max) of the 24 kHz-geometry decode."""
+    from conftest import GOLDEN
+    g = np.load(GOLDEN / "codecs.npz")
+    cfg = oe.EncodecConfig()
+    W = oe.init_weights(cfg, 7, n_codebooks=8)
+    codes = np.random.default_rng(1).integers(0, 1024, size=(1, 3, 8, 41))
+    y = make(b2a, cfg, W).decode(codes)
+    peak = max(abs(g["encodec_stats"][2]), abs(g["encodec_stats"][3]))
+    assert y.shape == tuple(g["encodec_shape"])
+    assert np.abs(y[:, :64, 0] - g["encodec_first"]).max() < TOL * peak and np.abs(y[:, -64:, 0] - g["encodec_last"]).max() < TOL * peak
+    yy = y.astype(np.float64).reshape(-1)
+    assert np.abs(np.array([yy.mean(), np.abs(yy).mean(), yy.min(), yy.max()]) - g["encodec_stats"]).max() < TOL * peak

@@ -48,3 +48,17 @@ def test_shapes_and_errors(b2a):
     with pytest.raises(b2a.AudioGenerationError) as e:
         make(b2a, cfg, W2)
     assert e.value.case == "modelNotInitialized"
+
+
+def test_decode_vs_committed_golden(b2a):
+    """tests/golden/codecs.npz: first 64 samples per row and the (mean, |mean|, min, max) of the reference-geometry decode."""
+    from conftest import GOLDEN
+    g = np.load(GOLDEN / "codecs.npz")
+    cfg = ov.VocosConfig(num_layers=2)
+    W = ov.init_weights(cfg, 7)
+    f = np.random.default_rng(1).standard_normal((2, 37, cfg.input_channels)).astype(np.float32)
+    y = make(b2a, cfg, W).decode(f)
+    peak = max(abs(g["vocos_stats"][2]), abs(g["vocos_stats"][3]))
+    assert y.shape == tuple(g["vocos_shape"]) and np.abs(y[:, :64] - g["vocos_first"]).max() < TOL * peak
+    yy = y.astype(np.float64).reshape(-1)
+    assert np.abs(np.array([yy.mean(), np.abs(yy).mean(), yy.min(), yy.max()]) - g["vocos_stats"]).max() < TOL * peak

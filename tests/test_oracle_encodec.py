@@ -111,3 +111,17 @@ def test_chunked_decode_uses_overlap_add():
     codes = np.random.default_rng(1).integers(0, 16, size=(3, 1, 2, 3))
     y = oe.decode(cfg, W, codes, [None, np.array([2.0]), None])
     assert cfg.chunk_length == 960 and cfg.chunk_stride == 480 and y.shape == (1, 2 * 480 + 960, 1)
+
+
+def test_oracle_reproduces_committed_golden():
+    """tests/golden/codecs.npz (tests/golden/make_golden.py --only codecs): the fixture the GPU tests also compare with."""
+    from conftest import GOLDEN
+    g = np.load(GOLDEN / "codecs.npz")
+    cfg = oe.EncodecConfig()
+    W = oe.init_weights(cfg, 7, n_codebooks=8)
+    codes = np.random.default_rng(1).integers(0, 1024, size=(1, 3, 8, 41))
+    z = oe.decode(cfg, W, codes)
+    assert tuple(g["encodec_shape"]) == z.shape
+    assert np.abs(z[:, :64, 0] - g["encodec_first"]).max() < 1e-6 and np.abs(z[:, -64:, 0] - g["encodec_last"]).max() < 1e-6
+    zz = z.reshape(-1)
+    assert np.allclose([zz.mean(), np.abs(zz).mean(), zz.min(), zz.max()], g["encodec_stats"], rtol=1e-6, atol=1e-9)

@@ -27,3 +27,16 @@ def test_istft_head_is_window_sum_normalised_ola():
 def test_hann_is_symmetric():
     h = ov.hann_symmetric(1024).numpy()
     assert h[0] == 0 and abs(h[-1]) < 1e-12 and abs(h[511] - h[512]) < 1e-12
+
+
+def test_oracle_reproduces_committed_golden():
+    """tests/golden/codecs.npz (tests/golden/make_golden.py --only codecs): the fixture the GPU tests also compare with."""
+    from conftest import GOLDEN
+    g = np.load(GOLDEN / "codecs.npz")
+    cfg = ov.VocosConfig(num_layers=2)
+    W = ov.init_weights(cfg, 7)
+    f = np.random.default_rng(1).standard_normal((2, 37, cfg.input_channels)).astype(np.float32)
+    y = ov.decode(cfg, W, f)
+    assert tuple(g["vocos_shape"]) == y.shape and np.abs(y[:, :64] - g["vocos_first"]).max() < 1e-6
+    yy = np.asarray(y, dtype=np.float64).reshape(-1)
+    assert np.allclose([yy.mean(), np.abs(yy).mean(), yy.min(), yy.max()], g["vocos_stats"], rtol=1e-6, atol=1e-9)
