@@ -1,0 +1,127 @@
+"""Oracle for the Qwen3-TTS talker / code predictor pinned against independent implementations available
+offline: `transformers` Qwen3Model (the talker backbone: per-head q/k RMSNorm, rotate-half RoPE, GQA, SwiGLU) and Qwen3-VL's
+apply_interleaved_mrope; plus the closed-form semantics of sampleToken and the frame loop's cache discipline.  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import qwen3_tts as oq
+
+SMALL = dict(vocab_size=1100, hidden_size=64, intermediate_size=96, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,
+             head_dim=16, text_hidden_size=48, text_vocab_size=200, codec_eos_token_id=1090, mrope_section=(4, 2, 2))
+
+
+def small_cfg(**kw):
+    cp = oq.CodePredictorConfig(vocab_size=40, hidden_size=kw.pop("cp_hidden", 64), intermediate_size=80, num_hidden_layers=2,
+                                num_attention_heads=4, num_key_value_heads=2, head_dim=16, num_code_groups=kw.pop("groups", 5))
+    d = dict(SMALL); d.update(kw)
+    return oq.TalkerConfig(num_code_groups=cp.num_code_groups, code_predictor=cp, **d)
+
+
+def test_talker_backbone_matches_transformers_qwen3():
+    from transformers import Qwen3Config, Qwen3Model
+    cfg = small_cfg()
+    W = oq.init_weights(cfg, 3, std=0.2)
+    hc = Qwen3Config(vocab_size=cfg.vocab_size, hidden_size=cfg.hidden_size, intermediate_size=cfg.intermediate_size,
+                     num_hidden_layers=cfg.num_hidden_layers, num_attention_heads=cfg.num_attention_heads,
+                     num_key_value_heads=cfg.num_key_value_heads, head_dim=cfg.head_dim, rms_norm_eps=cfg.rms_norm_eps,
+                     rope_theta=cfg.rope_theta, attention_bias=False, max_position_embeddings=512, tie_word_embeddings=False,
+                     use_sliding_window=False, attn_implementation="eager")
+    m = Qwen3Model(hc).double().eval()
+    sd = m.state_dict()
+    for k in sd:
+        src = "model." + k if not k.startswith("embed_tokens") else "model.codec_embedding.weight"
+        sd[k] = W[src].to(torch.float64)
+    m.load_state_dict(sd)
+    x = torch.randn(2, 7, cfg.hidden_size, dtype=torch.float64, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        ref = m(inputs_embeds=x, use_cache=False).last_hidden_state
+    mine = oq.Talker(cfg, W).model(x)
+    assert (mine - ref).abs().max() < 1e-5 * ref.abs().max()          # HF evaluates the rotary angles in float32 (2e-7 here)
+    # incremental decoding through the KV cache == the full pass
+    t = oq.Talker(cfg, W)
+    cache = t.make_cache()
+    a = t.model(x[:, :4], cache)
+    outs = [a] + [t.model(x[:, i:i + 1], cache) for i in range(4, 7)]
+    assert (torch.cat(outs, dim=1) - mine).abs().max() < 1e-10
+
+
+def test_interleaved_mrope_matches_qwen3_vl():
+    from transformers.models.qwen3_vl.modeling_qwen3_vl import Qwen3VLTextRotaryEmbedding
+    freqs = torch.randn(3, 2, 5, 64, dtype=torch.float64, generator=torch.Generator().manual_seed(1))
+    for section in ((24, 20, 20), (16, 24, 24), (40, 12, 12)):
+        ref = Qwen3VLTextRotaryEmbedding.apply_interleaved_mrope(None, freqs.clone(), list(section))
+        assert torch.equal(oq.apply_interleaved_mrope(freqs, section), ref)
+    # identical position rows: MRoPE degenerates to plain RoPE (what the TTS text-only positions are, Qwen3TTSTalker.swift:281-285)
+    pos = torch.arange(3, 9).view(1, 6)
+    c1, s1 = oq.mrope_cos_sin(pos, 128, 1e6, (24, 20, 20))
+    c2, s2 = oq.rope_cos_sin(pos, 128, 1e6)
+    assert torch.equal(c1, c2) and torch.equal(s1, s2)
+
+
+def test_sample_token_filters():
+    V = 12
+    lg = torch.tensor([[2.0, 1.0, 0.5, 0.0, -0.5, -1.0, -1.5, -2.0, 3.0, -3.0, 0.25, 0.75]], dtype=torch.float64)
+    # suppress -> -inf; repetition penalty over UNIQUE generated tokens (positive / by p, negative * p)
+    f = oq.filter_logits(lg, temperature=0.0, repetition_penalty=2.0, generated_tokens=[0, 0, 4, 99], suppress_tokens=[8])
+    assert f[0, 8] == float("-inf") and f[0, 0] == 1.0 and f[0, 4] == -1.0 and f[0, 1] == 1.0
+    assert int(oq.sample_token(lg, temperature=0.0, suppress_tokens=[8])[0, 0]) == 0
+    # top-k keeps exactly the k largest
+    f = oq.filter_logits(lg, temperature=1.0, top_k=3)
+    assert set(torch.isfinite(f[0]).nonzero().flatten().tolist()) == {8, 0, 1}
+    # top-p: ascending cumulative mass > 1 - p survives (the reference's comparison, Qwen3TTS.swift:1080-1084)
+    p = torch.softmax(lg, -1)[0]
+    order = torch.argsort(lg[0])
+    cum = torch.cumsum(p[order], 0)
+    keep = set(order[cum > 1 - 0.6].tolist())
+    f = oq.filter_logits(lg, temperature=1.0, top_k=0, top_p=0.6)
+    assert set(torch.isfinite(f[0]).nonzero().flatten().tolist()) == keep
+    # min-p: logits below max + log(min_p) are dropped
+    f = oq.filter_logits(lg, temperature=1.0, top_k=0, min_p=0.2)
+    assert set(torch.isfinite(f[0]).nonzero().flatten().tolist()) == set((lg[0] >= 3.0 + np.log(0.2)).nonzero().flatten().tolist())
+    # the EOS logit is put back after the filters (so top-k cannot make stopping impossible)
+    f = oq.filter_logits(lg, temperature=1.0, top_k=2, eos_token_id=9)
+    assert f[0, 9] == -3.0 and torch.isfinite(f[0]).sum() == 3
+    g = torch.Generator().manual_seed(0)
+    draws = {int(oq.sample_token(lg, g, temperature=1.0, top_k=2)[0, 0]) for _ in range(50)}
+    assert draws <= {8, 0} and len(draws) == 2
+
+
+@pytest.mark.parametrize("cp_hidden", [64, 32])
+def test_frame_loop_shapes_cache_discipline_and_determinism(cp_hidden):
+    cfg = small_cfg(cp_hidden=cp_hidden)
+    W = oq.init_weights(cfg, 5, std=0.3)
+    assert ("code_predictor.small_to_mtp_projection.weight" in W) == (cp_hidden != cfg.hidden_size)
+    t = oq.Talker(cfg, W)
+    prompt = t.embed_text(torch.tensor([[3, 7, 11, 19]])) + t.embed_codec(torch.tensor([[1, 2, 3, 4]]))
+    trailing = t.embed_text(torch.tensor([[5, 6]]))
+    pad = t.embed_text(torch.tensor([[0]]))
+    codes = oq.generate_codes(cfg, W, prompt, trailing, pad, max_tokens=6, temperature=0.0, stop_on_eos=False)
+    assert codes.shape == (6, cfg.num_code_groups)
+    c0 = codes[:, 0]                                                        # the last 1024 ids (special tokens) are suppressed, EOS aside
+    assert bool(((c0 < cfg.vocab_size - 1024) | (c0 == cfg.codec_eos_token_id)).all())
+    assert int(codes[:, 1:].max()) < cfg.code_predictor.vocab_size
+    again = oq.generate_codes(cfg, W, prompt, trailing, pad, max_tokens=6, temperature=0.0, stop_on_eos=False)
+    assert torch.equal(codes, again)
+    # frame f's 15 predictor codes depend only on (talker hidden, code 0) of that frame: recompute frame 0 with a fresh predictor
+    pred = oq.CodePredictor(cfg, W)
+    logits, hidden = t(prompt, t.make_cache())
+    c0 = logits[:, -1].argmax(-1, keepdim=True)
+    cache = pred.make_cache()
+    got = [c0]
+    for ci in range(cfg.num_code_groups - 1):
+        inp = torch.cat([hidden[:, -1:], t.embed_codec(c0)], dim=1) if ci == 0 else pred.embed(ci - 1, got[-1])
+        got.append(pred(inp, cache, ci)[:, -1].argmax(-1, keepdim=True))
+    assert torch.equal(torch.cat(got, dim=1)[0], codes[0])
+    # sanitize strips the "talker." prefix and drops everything else (Qwen3TTSTalker.swift:356-365)
+    s = oq.sanitize({"talker.codec_head.weight": W["codec_head.weight"], "speaker_encoder.x": W["codec_head.weight"]})
+    assert list(s) == ["codec_head.weight"]
+
+
+def test_default_geometry_matches_the_reference_defaults():
+    c = oq.TalkerConfig()
+    assert (c.hidden_size, c.num_hidden_layers, c.num_attention_heads, c.num_key_value_heads, c.head_dim, c.intermediate_size,
+            c.vocab_size, c.text_vocab_size, c.text_hidden_size, c.codec_eos_token_id) == (1024, 28, 16, 8, 128, 3072, 3072, 151936, 2048, 2150)
+    p = c.code_predictor
+    assert (p.num_hidden_layers, p.hidden_size, p.vocab_size, p.num_code_groups) == (5, 1024, 2048, 16)
+    assert tuple(c.mrope_section) == (24, 20, 20) and sum(c.mrope_section) == c.head_dim // 2
