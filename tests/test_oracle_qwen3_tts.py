@@ -98,15 +98,16 @@ def test_frame_loop_shapes_cache_discipline_and_determinism(cp_hidden):
     pad = t.embed_text(torch.tensor([[0]]))
     codes = oq.generate_codes(cfg, W, prompt, trailing, pad, max_tokens=6, temperature=0.0, stop_on_eos=False)
     assert codes.shape == (6, cfg.num_code_groups)
-    c0 = codes[:, 0]                                                        # the last 1024 ids (special tokens) are suppressed, EOS aside
-    assert bool(((c0 < cfg.vocab_size - 1024) | (c0 == cfg.codec_eos_token_id)).all())
+    first = codes[:, 0]                                                     # the last 1024 ids (special tokens) are suppressed, EOS aside
+    assert bool(((first < cfg.vocab_size - 1024) | (first == cfg.codec_eos_token_id)).all())
     assert int(codes[:, 1:].max()) < cfg.code_predictor.vocab_size
     again = oq.generate_codes(cfg, W, prompt, trailing, pad, max_tokens=6, temperature=0.0, stop_on_eos=False)
     assert torch.equal(codes, again)
     # frame f's 15 predictor codes depend only on (talker hidden, code 0) of that frame: recompute frame 0 with a fresh predictor
     pred = oq.CodePredictor(cfg, W)
     logits, hidden = t(prompt, t.make_cache())
-    c0 = logits[:, -1].argmax(-1, keepdim=True)
+    suppress = [i for i in range(cfg.vocab_size - 1024, cfg.vocab_size) if i != cfg.codec_eos_token_id]
+    c0 = oq.sample_token(logits[:, -1], temperature=0.0, suppress_tokens=suppress)
     cache = pred.make_cache()
     got = [c0]
     for ci in range(cfg.num_code_groups - 1):
