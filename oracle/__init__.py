@@ -20,6 +20,9 @@ independent implementations available offline (``torch.stft``,
 ``torch.nn.functional.conv1d/conv_transpose1d``, ``transformers`` Llama/Whisper
 with random init), see ``tests/test_oracle_crosscheck.py``.
 
+Modules: ``dsp`` (mel), ``snac``, ``llama`` (Orpheus), ``whisper``, ``vocos``, ``encodec`` -- the rows of SURVEY.md section 8a --
+and ``qwen3_tts`` (row N1 of 8f: oracle only, no CUDA path yet).
+
 Every function cites the reference ``file:line`` it follows (paths relative
 to the reference checkout root).
 """
