@@ -72,6 +72,19 @@ class Encodec:
         _ffi.check(_ffi.lib().b2a_encodec_create(device, C.byref(c), table, len(weights), C.byref(self._h)))
         del keep
 
+    @classmethod
+    def from_model_directory(cls, model_dir, device: int = 0) -> "Encodec":
+        """fromModelDirectory (Encodec.swift:423-440): config.json + model.safetensors, keys as shipped (the library's reader)."""
+        import json
+        from pathlib import Path
+        from .loading import Weights
+        model_dir = Path(model_dir)
+        config = EncodecConfig.from_dict(json.loads((model_dir / "config.json").read_text()))
+        w = Weights(model_dir / "model.safetensors")
+        tensors = w.tensors()
+        w.close()
+        return cls(config, weights=tensors, device=device)
+
     # ---- properties of the reference class (Encodec.swift:186-208)
     @property
     def channels(self) -> int:
