@@ -64,8 +64,18 @@ static void mel_filters_host(int sr, int n_fft, int n_mels, float f_min, float f
 // Device side
 // ------------------------------------------------------------------------------------------------
 constexpr int NFFT = 400, NBINS = 201, R = 20, K1N = 11;  // 400 = 20*20, k1 = 0..10 by symmetry
-constexpr int FR = 8;                                        // frames per CTA
+constexpr int FR = 10;                                       // frames per CTA (20 threads per frame in the DFT passes)
 constexpr int MEL_THREADS = 256;
+
+// exp(-2*pi*i*j/20) = (C20[j], S20[j]): with both DFT loops fully unrolled every twiddle index is a compile-time constant, so the
+// 20-point sums are pure FMAs against immediates (the first version spent ~10 instructions per term on index arithmetic and
+// shared-memory twiddle loads)
+__device__ constexpr float C20[20] = {1.f, 0.95105654f, 0.809017003f, 0.587785244f, 0.309017003f, 6.12323426e-17f, -0.309017003f,
+                                      -0.587785244f, -0.809017003f, -0.95105654f, -1.f, -0.95105654f, -0.809017003f, -0.587785244f,
+                                      -0.309017003f, -1.83697015e-16f, 0.309017003f, 0.587785244f, 0.809017003f, 0.95105654f};
+__device__ constexpr float S20[20] = {-0.f, -0.309017003f, -0.587785244f, -0.809017003f, -0.95105654f, -1.f, -0.95105654f, -0.809017003f,
+                                      -0.587785244f, -0.309017003f, -1.22464685e-16f, 0.309017003f, 0.587785244f, 0.809017003f,
+                                      0.95105654f, 1.f, 0.95105654f, 0.809017003f, 0.587785244f, 0.309017003f};
 
 struct MelTables {          // device pointers, owned by MelCore
     const float* window;    // [400]
@@ -92,7 +102,6 @@ mel_log_kernel(const float* __restrict__ pcm, long long pcm_stride, long long n_
                float* __restrict__ max_buf) {
     __shared__ float s_x[(FR - 1) * 160 + NFFT + 8 + (FR - 1) * 96];  // sized for hop <= 256
     __shared__ float s_win[NFFT];
-    __shared__ float2 s_tw20[R];
     __shared__ float2 s_tw400[NFFT];
     __shared__ float2 s_y[FR][K1N][R];
     __shared__ float s_p[FR][NBINS + 3];
@@ -105,7 +114,6 @@ mel_log_kernel(const float* __restrict__ pcm, long long pcm_stride, long long n_
     const float* sig = pcm + (long long)b * pcm_stride;
 
     for (int i = tid; i < NFFT; i += MEL_THREADS) { s_win[i] = tb.window[i]; s_tw400[i] = tb.tw400[i]; }
-    if (tid < R) s_tw20[tid] = tb.tw20[tid];
     const int span = (nf - 1) * hop + NFFT;
     const long long base = (long long)f0 * hop;
     for (int i = tid; i < span; i += MEL_THREADS) {
@@ -123,45 +131,52 @@ mel_log_kernel(const float* __restrict__ pcm, long long pcm_stride, long long n_
     }
     __syncthreads();
 
-    // pass 1: Y[k1][n2] = tw400[n2*k1] * sum_n1 xw[20*n1+n2] * tw20[(n1*k1)%20], k1 = 0..10
-    for (int o = tid; o < nf * K1N * R; o += MEL_THREADS) {
-        const int f = o / (K1N * R), r = o - f * (K1N * R), k1 = r / R, n2 = r - k1 * R;
+    // pass 1: Y[k1][n2] = tw400[n2*k1] * sum_n1 xw[20*n1+n2] * tw20[(n1*k1)%20], k1 = 0..10.  One thread per (frame, n2): its 20
+    // windowed samples live in registers and feed all 11 k1 sums.
+    for (int o = tid; o < nf * R; o += MEL_THREADS) {
+        const int f = o / R, n2 = o - f * R;
         const float* x = s_x + f * hop + n2;
-        float re = 0.f, im = 0.f;
-        int t = 0;
+        float xr[R];
 #pragma unroll
-        for (int n1 = 0; n1 < R; ++n1) {
-            const float xv = x[R * n1] * s_win[R * n1 + n2];
-            const float2 w = s_tw20[t];
-            re = fmaf(xv, w.x, re);
-            im = fmaf(xv, w.y, im);
-            t += k1; if (t >= R) t -= R;
+        for (int n1 = 0; n1 < R; ++n1) xr[n1] = x[R * n1] * s_win[R * n1 + n2];
+#pragma unroll
+        for (int k1 = 0; k1 < K1N; ++k1) {
+            float re = 0.f, im = 0.f;
+#pragma unroll
+            for (int n1 = 0; n1 < R; ++n1) {
+                re = fmaf(xr[n1], C20[(n1 * k1) % R], re);
+                im = fmaf(xr[n1], S20[(n1 * k1) % R], im);
+            }
+            const float2 w = s_tw400[n2 * k1];
+            s_y[f][k1][n2] = make_float2(re * w.x - im * w.y, re * w.y + im * w.x);
         }
-        const float2 w = s_tw400[n2 * k1];
-        s_y[f][k1][n2] = make_float2(re * w.x - im * w.y, re * w.y + im * w.x);
     }
     __syncthreads();
 
-    // pass 2: X[k1+20*k2] = sum_n2 Y[k1][n2] tw20[(n2*k2)%20]; for k1 > 10 use
-    //         Y[k1][n2] = conj(Y[20-k1][n2]) * tw20[n2]  (real input).
-    for (int o = tid; o < nf * NBINS; o += MEL_THREADS) {
-        const int f = o / NBINS, k = o - f * NBINS, k1 = k % R, k2 = k / R;
+    // pass 2: X[k1+20*k2] = sum_n2 Y[k1][n2] tw20[(n2*k2)%20]; for k1 > 10, Y[k1][n2] = conj(Y[20-k1][n2]) * tw20[n2] (real input),
+    // i.e. X[k1+20*k2] = T[k2+1] with T[kk] = sum_n2 conj(Y[20-k1][n2]) tw20[(n2*kk)%20].  One thread per (frame, k1): it loads its
+    // row of Y once and evaluates T[0..10] against compile-time twiddles.
+    for (int o = tid; o < nf * R; o += MEL_THREADS) {
+        const int f = o / R, k1 = o - f * R;
         const bool mirror = k1 > R / 2;
         const float2* y = s_y[f][mirror ? R - k1 : k1];
-        const int step = mirror ? (k2 + 1) % R : k2;
         const float sgn = mirror ? -1.f : 1.f;
-        float re = 0.f, im = 0.f;
-        int t = 0;
+        float yr[R], yi[R];
 #pragma unroll
-        for (int n2 = 0; n2 < R; ++n2) {
-            const float2 yv = y[n2];
-            const float yi = sgn * yv.y;
-            const float2 w = s_tw20[t];
-            re += yv.x * w.x - yi * w.y;
-            im += yv.x * w.y + yi * w.x;
-            t += step; if (t >= R) t -= R;
+        for (int n2 = 0; n2 < R; ++n2) { const float2 v = y[n2]; yr[n2] = v.x; yi[n2] = sgn * v.y; }
+#pragma unroll
+        for (int kk = 0; kk < K1N; ++kk) {
+            float re = 0.f, im = 0.f;
+#pragma unroll
+            for (int n2 = 0; n2 < R; ++n2) {
+                const float c = C20[(n2 * kk) % R], sn = S20[(n2 * kk) % R];
+                re = fmaf(yr[n2], c, re); re = fmaf(-yi[n2], sn, re);
+                im = fmaf(yr[n2], sn, im); im = fmaf(yi[n2], c, im);
+            }
+            const int k2 = mirror ? kk - 1 : kk;
+            const int k = k1 + R * k2;
+            if (k2 >= 0 && k < NBINS) s_p[f][k] = re * re + im * im;
         }
-        s_p[f][k] = re * re + im * im;
     }
     __syncthreads();
 
