@@ -304,6 +304,38 @@ class CodePredictor:
         return _lin(self.W, f"code_predictor.lm_head.{generation_step}", x)
 
 
+# ------------------------------------------------------------------------------------------------ prompt embeddings
+def prepare_generation_inputs(cfg: TalkerConfig, W, chat_ids: Sequence[int], tts_bos: int, tts_eos: int, tts_pad: int,
+                              language_id: Optional[int] = None, speaker_id: Optional[int] = None,
+                              instruct_ids: Optional[Sequence[int]] = None, codec_think_id: int = 2154, codec_nothink_id: int = 2155,
+                              codec_think_bos_id: int = 2156, codec_think_eos_id: int = 2157, codec_pad_id: int = 2148,
+                              codec_bos_id: int = 2149):
+    """prepareGenerationInputs (Qwen3TTS.swift:883-999) from token ids (tokenisation stays with the host tokenizer).
+    chat_ids = tokens of "<|im_start|>assistant\n{text}<|im_end|>\n<|im_start|>assistant\n"; instruct_ids = tokens of
+    "<|im_start|>user\n{instruct}<|im_end|>\n" (VoiceDesign) or None.  Returns (input_embeds [1, L, H], trailing_text_hidden
+    [1, n, H], tts_pad_embed [1, 1, H])."""
+    t = Talker(cfg, W)
+    text = t.embed_text(torch.as_tensor([list(chat_ids)]))                                   # text_projection(text_embedding(ids)) (:898)
+    tts = t.embed_text(torch.as_tensor([[tts_bos, tts_eos, tts_pad]]))
+    bos_e, eos_e, pad_e = tts[:, 0:1], tts[:, 1:2], tts[:, 2:3]
+    if language_id is not None:                                                              # codec prefix (:938-951)
+        prefill = [codec_think_id, codec_think_bos_id, language_id, codec_think_eos_id]
+    else:
+        prefill = [codec_nothink_id, codec_think_bos_id, codec_think_eos_id]
+    codec = t.embed_codec(torch.as_tensor([prefill]))
+    suffix = t.embed_codec(torch.as_tensor([[codec_pad_id, codec_bos_id]]))
+    parts = [codec] + ([t.embed_codec(torch.as_tensor([[speaker_id]]))] if speaker_id is not None else []) + [suffix]
+    codec = torch.cat(parts, dim=1)                                                          # (:957-962)
+    role = text[:, :3]                                                                       # "<|im_start|>assistant\n"
+    pad_count = codec.shape[1] - 2
+    combined = torch.cat([pad_e.expand(1, pad_count, -1), bos_e], dim=1) + codec[:, :-1]     # (:976-979)
+    pieces = ([t.embed_text(torch.as_tensor([list(instruct_ids)]))] if instruct_ids else []) + [role, combined]
+    first_text = text[:, 3:4] + codec[:, -1:]                                                # (:989)
+    inputs = torch.cat(pieces + [first_text], dim=1)
+    trailing = torch.cat([text[:, 4:text.shape[1] - 5], eos_e], dim=1)                       # tokens 4 .. -5, then tts EOS (:993-996)
+    return inputs, trailing, pad_e
+
+
 # ------------------------------------------------------------------------------------------------ sampling
 def filter_logits(logits: torch.Tensor, temperature: float = 0.9, top_p: float = 1.0, top_k: int = 50, repetition_penalty: float = 1.0,
                   generated_tokens: Optional[Sequence[int]] = None, suppress_tokens: Optional[Sequence[int]] = None,

@@ -126,3 +126,31 @@ def test_default_geometry_matches_the_reference_defaults():
     p = c.code_predictor
     assert (p.num_hidden_layers, p.hidden_size, p.vocab_size, p.num_code_groups) == (5, 1024, 2048, 16)
     assert tuple(c.mrope_section) == (24, 20, 20) and sum(c.mrope_section) == c.head_dim // 2
+
+
+def test_prepare_generation_inputs_layout():
+    """Qwen3TTS.swift:883-999: [instruct] + role(3) + (pad.. + bos) + codec prefix[:-1], then first text token + last codec embed;
+    trailing = text[4:-5] + tts EOS."""
+    cfg = small_cfg()
+    W = oq.init_weights(cfg, 9, std=0.3)
+    t = oq.Talker(cfg, W)
+    chat = list(range(10, 10 + 14))                      # 3 role + 1 first + 5 trailing + 5 dropped suffix tokens
+    kw = dict(tts_bos=1, tts_eos=2, tts_pad=3, codec_think_id=20, codec_nothink_id=21, codec_think_bos_id=22, codec_think_eos_id=23,
+              codec_pad_id=24, codec_bos_id=25)
+    x, trailing, pad = oq.prepare_generation_inputs(cfg, W, chat, **kw)
+    # no language: prefix [nothink, think_bos, think_eos] + [pad, bos] -> 5 codec embeds, 4 of them under (3 x tts_pad + tts_bos)
+    assert x.shape == (1, 3 + 4 + 1, cfg.hidden_size) and trailing.shape == (1, 14 - 9 + 1, cfg.hidden_size)
+    text = t.embed_text(torch.tensor([chat]))
+    codec = t.embed_codec(torch.tensor([[21, 22, 23, 24, 25]]))
+    tts = t.embed_text(torch.tensor([[1, 2, 3]]))
+    assert torch.allclose(x[:, :3], text[:, :3])
+    assert torch.allclose(x[:, 3:6], tts[:, 2:3] + codec[:, 0:3]) and torch.allclose(x[:, 6:7], tts[:, 0:1] + codec[:, 3:4])
+    assert torch.allclose(x[:, 7:8], text[:, 3:4] + codec[:, 4:5])
+    assert torch.allclose(trailing[:, :-1], text[:, 4:9]) and torch.allclose(trailing[:, -1:], tts[:, 1:2]) and torch.equal(pad, tts[:, 2:3])
+    # language id -> 4-token think prefix; a speaker embedding sits between prefix and [pad, bos]; instruct goes first
+    x2, _, _ = oq.prepare_generation_inputs(cfg, W, chat, language_id=30, speaker_id=31, instruct_ids=[40, 41], **kw)
+    assert x2.shape[1] == 2 + 3 + (4 + 1 + 2 - 1) + 1
+    codec2 = t.embed_codec(torch.tensor([[20, 22, 30, 23, 31, 24, 25]]))
+    assert torch.allclose(x2[:, 2 + 3 + 5:2 + 3 + 6], tts[:, 0:1] + codec2[:, 5:6]) and torch.allclose(x2[:, -1:], text[:, 3:4] + codec2[:, 6:7])
+    codes = oq.generate_codes(cfg, W, x, trailing, pad, max_tokens=3, temperature=0.0, stop_on_eos=False)
+    assert codes.shape == (3, cfg.num_code_groups)
