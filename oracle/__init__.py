@@ -21,7 +21,8 @@ independent implementations available offline (``torch.stft``,
 with random init), see ``tests/test_oracle_crosscheck.py``.
 
 Modules: ``dsp`` (mel), ``snac``, ``llama`` (Orpheus), ``whisper``, ``vocos``, ``encodec`` -- the rows of SURVEY.md section 8a --
-and ``qwen3_tts`` (row N1 of 8f: oracle only, no CUDA path yet).
+and ``qwen3_tts`` + ``qwen3_tts_codec`` (row N1 of 8f, talker / code predictor and speech-tokenizer decoder: oracle
+only, no CUDA path yet).
 
 Every function cites the reference ``file:line`` it follows (paths relative
 to the reference checkout root).
