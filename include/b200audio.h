@@ -431,6 +431,57 @@ int32_t b2a_stt_transcribe_long(b2a_stt* h, const float* pcm, int64_t n_samples,
 int32_t b2a_stt_cancel(b2a_stt* h);
 void b2a_stt_destroy(b2a_stt* h);
 
+/* ------------------------------------------------------------------ Qwen3-TTS speech-tokenizer decoder
+ * EXPERIMENTAL: compiled and exported, parity tests gated behind B2A_EXPERIMENTAL_N1=1 until they have run on a GPU.
+ * Replaces Qwen3TTSSpeechTokenizerDecoder and the decode entry points of Qwen3TTSSpeechTokenizer
+ * (Sources/MLXAudioTTS/Models/Qwen3TTS/Qwen3TTSSpeechTokenizer.swift):
+ *   init(config:) + sanitized weights (keys below the "decoder." module, MLX layouts)  -> create
+ *   resetStreamingState (:949-970)                                                       -> reset
+ *   streamingStep (:973-1008)                                                            -> streaming_step[_dev]
+ *   streamingDecode(chunkTokens:) (:1070-1092, what decodeChunk uses, Qwen3TTS.swift:214-231) -> streaming_decode
+ *   chunkedDecode(chunkSize:leftContextSize:) (:1010-1024, used by decode :1059-1068)   -> chunked_decode
+ * codes are [B, num_quantizers given, T] int32 (the decoder's own layout, i.e. audioCodes transposed (0, 2, 1)); the
+ * waveform is [B, T * total_upsample] float32 in [-1, 1].  Config defaults: Qwen3TTSConfig.swift:358-385.            */
+typedef struct b2a_speech_tokenizer_config {
+    int32_t codebook_size;
+    int32_t codebook_dim;
+    int32_t latent_dim;
+    int32_t decoder_dim;
+    int32_t hidden_size;
+    int32_t intermediate_size;
+    int32_t head_dim;
+    int32_t num_attention_heads;
+    int32_t num_key_value_heads;
+    int32_t num_hidden_layers;
+    int32_t num_quantizers;
+    int32_t num_semantic_quantizers;
+    float rms_norm_eps;
+    float rope_theta;
+    int32_t attention_bias;
+    int32_t num_upsample_rates;
+    int32_t upsample_rates[8];
+    int32_t num_upsampling_ratios;
+    int32_t upsampling_ratios[8];
+    int32_t max_batch;        /* rows decoded together */
+    int32_t max_cache_frames; /* code frames one stream may span (the reference's cache is unbounded) */
+} b2a_speech_tokenizer_config;
+
+typedef struct b2a_speech_tokenizer b2a_speech_tokenizer;
+int32_t b2a_speech_tokenizer_create(int32_t device, const b2a_speech_tokenizer_config* cfg, const b2a_tensor* tensors,
+                                    int32_t n_tensors, b2a_speech_tokenizer** out);
+int32_t b2a_speech_tokenizer_total_upsample(const b2a_speech_tokenizer* h);
+void* b2a_speech_tokenizer_stream(b2a_speech_tokenizer* h);
+int32_t b2a_speech_tokenizer_reset(b2a_speech_tokenizer* h);
+int32_t b2a_speech_tokenizer_streaming_step(b2a_speech_tokenizer* h, const int32_t* codes, int32_t batch, int32_t num_groups,
+                                            int32_t frames, float* wave);
+int32_t b2a_speech_tokenizer_streaming_step_dev(b2a_speech_tokenizer* h, const int32_t* d_codes, int32_t batch, int32_t num_groups,
+                                                int32_t frames, float* d_wave, void* stream);
+int32_t b2a_speech_tokenizer_streaming_decode(b2a_speech_tokenizer* h, const int32_t* codes, int32_t batch, int32_t num_groups,
+                                              int32_t frames, int32_t chunk_tokens, float* wave);
+int32_t b2a_speech_tokenizer_chunked_decode(b2a_speech_tokenizer* h, const int32_t* codes, int32_t batch, int32_t num_groups,
+                                            int32_t frames, int32_t chunk_size, int32_t left_context, float* wave);
+void b2a_speech_tokenizer_destroy(b2a_speech_tokenizer* h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -75,6 +75,16 @@ class EncodecConfig(C.Structure):
                    ("trim_right_ratio", C.c_float), ("chunk_length_s", C.c_float), ("overlap", C.c_float)])
 
 
+class SpeechTokenizerConfig(C.Structure):
+    _fields_ = ([(n, C.c_int32) for n in ("codebook_size", "codebook_dim", "latent_dim", "decoder_dim", "hidden_size",
+                                           "intermediate_size", "head_dim", "num_attention_heads", "num_key_value_heads",
+                                           "num_hidden_layers", "num_quantizers", "num_semantic_quantizers")]
+                + [("rms_norm_eps", C.c_float), ("rope_theta", C.c_float), ("attention_bias", C.c_int32),
+                   ("num_upsample_rates", C.c_int32), ("upsample_rates", C.c_int32 * 8),
+                   ("num_upsampling_ratios", C.c_int32), ("upsampling_ratios", C.c_int32 * 8),
+                   ("max_batch", C.c_int32), ("max_cache_frames", C.c_int32)])
+
+
 class WhisperConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("vocab_size", "num_mel_bins", "d_model", "encoder_layers", "encoder_attention_heads",
                                           "encoder_ffn_dim", "max_source_positions", "decoder_layers", "decoder_attention_heads",
@@ -144,6 +154,15 @@ SIGNATURES = {
     "b2a_vocos_decode": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, _P]),
     "b2a_vocos_decode_dev": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
     "b2a_vocos_destroy": (None, [_P]),
+    "b2a_speech_tokenizer_create": (C.c_int32, [C.c_int32, C.POINTER(SpeechTokenizerConfig), C.POINTER(Tensor), C.c_int32, C.POINTER(_P)]),
+    "b2a_speech_tokenizer_total_upsample": (C.c_int32, [_P]),
+    "b2a_speech_tokenizer_stream": (C.c_void_p, [_P]),
+    "b2a_speech_tokenizer_reset": (C.c_int32, [_P]),
+    "b2a_speech_tokenizer_streaming_step": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "b2a_speech_tokenizer_streaming_step_dev": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "b2a_speech_tokenizer_streaming_decode": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "b2a_speech_tokenizer_chunked_decode": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "b2a_speech_tokenizer_destroy": (None, [_P]),
     "b2a_encodec_create": (C.c_int32, [C.c_int32, C.POINTER(EncodecConfig), C.POINTER(Tensor), C.c_int32, C.POINTER(_P)]),
     "b2a_encodec_output_length": (C.c_int64, [_P, C.c_int32, C.c_int32]),
     "b2a_encodec_num_codebooks": (C.c_int32, [_P]),

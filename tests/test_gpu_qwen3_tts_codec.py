@@ -1,0 +1,102 @@
+"""CUDA Qwen3-TTS speech-tokenizer decoder (through the C ABI) vs the oracle (row N1).
+
+GATED: the CUDA path was written in a round with no GPU time left and has not run on hardware yet.  Set
+B2A_EXPERIMENTAL_N1=1 to run these; until they have passed once on a B200 they stay out of the default ``-m gpu`` run."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import max_rel_to_peak, rel_err
+from oracle import qwen3_tts_codec as oc
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("B2A_EXPERIMENTAL_N1") != "1",
+                                                  reason="experimental N1 path: set B2A_EXPERIMENTAL_N1=1")]
+TOL = 1e-3
+
+
+def mid_config(**kw):
+    """Every structural feature of the shipped geometry at a size the float64 oracle decodes in seconds."""
+    base = dict(latent_dim=128, codebook_dim=128, codebook_size=64, decoder_dim=256, hidden_size=64, intermediate_size=128, head_dim=32,
+                num_attention_heads=4, num_key_value_heads=2, num_hidden_layers=2, num_quantizers=4, num_semantic_quantizers=1,
+                upsample_rates=[4, 3, 2, 2], upsampling_ratios=[2, 2], layer_scale_initial_scale=0.3)
+    base.update(kw)
+    return oc.TokenizerDecoderConfig(**base)
+
+
+def make(b2a_codec, cfg, W, **kw):
+    c = b2a_codec.Qwen3TTSTokenizerDecoderConfig.from_dict({k: getattr(cfg, k) for k in cfg.__dataclass_fields__})
+    return b2a_codec.Qwen3TTSSpeechTokenizerDecoder(c, weights={k: v.numpy() for k, v in W.items()}, **kw)
+
+
+@pytest.fixture(scope="module")
+def codec():
+    import importlib
+    return importlib.import_module("mlx_audio_swift_b200.qwen3_tts_codec")
+
+
+def test_one_shot_decode_vs_oracle(codec):
+    cfg = mid_config()
+    W = oc.init_weights(cfg, 5)
+    m = make(codec, cfg, W, max_batch=2)
+    codes = np.random.default_rng(1).integers(0, cfg.codebook_size, (2, cfg.num_quantizers, 70))      # crosses a 64-frame tile
+    ref = oc.SpeechTokenizerDecoder(cfg, W)(codes).numpy()
+    y = m(codes)
+    assert y.shape == ref.shape == (2, 1, 70 * cfg.total_upsample)
+    assert max_rel_to_peak(y, ref) < TOL and rel_err(y, ref) < TOL, (max_rel_to_peak(y, ref), rel_err(y, ref))
+    assert np.abs(m(codes[1:2]) - y[1:2]).max() < 1e-6                                             # batched == serial
+    y1 = m(codes[:, :1])                                                                            # only the semantic codebook
+    assert max_rel_to_peak(y1, oc.SpeechTokenizerDecoder(cfg, W)(codes[:, :1]).numpy()) < TOL
+
+
+@pytest.mark.parametrize("chunks", [[1] * 5, [3, 1, 7, 2], [40, 30]])
+def test_streaming_step_vs_oracle_including_the_bias_quirk(codec, chunks):
+    cfg = mid_config()
+    W = oc.init_weights(cfg, 6)
+    m = make(codec, cfg, W, max_batch=2)
+    d = oc.SpeechTokenizerDecoder(cfg, W)
+    codes = np.random.default_rng(2).integers(0, cfg.codebook_size, (2, cfg.num_quantizers, sum(chunks)))
+    m.reset_streaming_state(); d.reset_streaming_state()
+    s = 0
+    for n in chunks:
+        y, ref = m.streaming_step(codes[:, :, s: s + n]), d.streaming_step(codes[:, :, s: s + n]).numpy()
+        assert y.shape == ref.shape and max_rel_to_peak(y, ref) < TOL, (s, max_rel_to_peak(y, ref))
+        s += n
+
+
+def test_chunked_and_streaming_decode_wrappers(codec):
+    cfg = mid_config()
+    W = oc.init_weights(cfg, 8)
+    ac = np.random.default_rng(3).integers(1, cfg.codebook_size, (2, 13, cfg.num_quantizers))
+    ac[1, 9:, :] = 0
+    tok = codec.Qwen3TTSSpeechTokenizer(codec.Qwen3TTSTokenizerDecoderConfig.from_dict({k: getattr(cfg, k) for k in cfg.__dataclass_fields__}),
+                                        weights={k: v.numpy() for k, v in W.items()}, decode_upsample_rate=cfg.total_upsample, max_batch=2)
+    d = oc.SpeechTokenizerDecoder(cfg, W)
+    codes = ac.transpose(0, 2, 1)
+    ch = tok.decoder.chunked_decode(codes, chunk_size=5, left_context_size=2)
+    assert max_rel_to_peak(ch, d.chunked_decode(codes, 5, 2).numpy()) < TOL
+    wav, lengths = tok.decode(ac)
+    ref_wav, ref_len = oc.decode(cfg, W, ac)
+    assert lengths.tolist() == ref_len.tolist() and max_rel_to_peak(wav, ref_wav) < TOL
+    parts = tok.streaming_decode(ac, chunk_tokens=4)
+    refs = oc.streaming_decode(cfg, W, ac, chunk_tokens=4)
+    assert [p.shape for p in parts] == [r.shape for r in refs]
+    assert max(max_rel_to_peak(p, r) for p, r in zip(parts, refs)) < TOL
+    assert max_rel_to_peak(tok.decode_chunk(ac[:1], 300), oc.decode_chunk(cfg, W, ac[:1], 300)) < TOL
+
+
+def test_default_geometry_and_errors(b2a, codec):
+    cfg = oc.TokenizerDecoderConfig()
+    W = oc.init_weights(cfg, 1)
+    m = make(codec, cfg, W)
+    assert m.total_upsample == 1920
+    codes = np.random.default_rng(0).integers(0, 2048, (1, 16, 3))
+    ref = oc.SpeechTokenizerDecoder(cfg, W)(codes).numpy()
+    assert max_rel_to_peak(m(codes), ref) < TOL
+    with pytest.raises(b2a.AudioGenerationError) as e:
+        m(np.zeros((2, 16, 3), np.int32))                         # batch > max_batch
+    assert e.value.case == "invalidInput"
+    W2 = dict(W); W2.pop("pre_conv.conv.bias")
+    with pytest.raises(b2a.AudioGenerationError) as e:
+        make(codec, cfg, W2)
+    assert e.value.case == "modelNotInitialized"
