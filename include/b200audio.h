@@ -481,6 +481,11 @@ int32_t b2a_speech_tokenizer_streaming_decode(b2a_speech_tokenizer* h, const int
 int32_t b2a_speech_tokenizer_chunked_decode(b2a_speech_tokenizer* h, const int32_t* codes, int32_t batch, int32_t num_groups,
                                             int32_t frames, int32_t chunk_size, int32_t left_context, float* wave);
 void b2a_speech_tokenizer_destroy(b2a_speech_tokenizer* h);
+/* Host-only parity hook (no device needed): the GEMM weight matrix the implicit convolution reads for an MLX-layout
+ * [out, k, in] weight -- stride 0: causal conv, rows = out, taps = k; stride > 0: transposed conv with k = n * stride, rows =
+ * stride * out (phase-major), taps = n.  layout_out: [rows][taps][kpad] float32, kpad = ceil(in / 64) * 64.            */
+int32_t b2a_speech_tokenizer_debug_layout(const float* w, int32_t out, int32_t k, int32_t in, int32_t stride, float* layout_out,
+                                          int64_t capacity, int32_t* rows, int32_t* taps, int32_t* kpad);
 
 #ifdef __cplusplus
 }

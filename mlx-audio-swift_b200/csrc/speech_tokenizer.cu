@@ -320,18 +320,25 @@ struct IW {                       // implicit-conv weight: [M][taps][cblocks * 6
     CUtensorMap th{}, tl{};
     int M = 0, taps = 1, cblocks = 0, Cin = 0;
     bool has_bias = false;
+    // [M][taps][Cin] -> [M][taps][cblocks * 64], every tap's channel run zero-padded to whole 64-channel k-blocks
+    static std::vector<float> pad_k(const std::vector<float>& W, int M, int taps, int Cin) {
+        const int cb = cdiv(Cin, tc::BK);
+        const size_t K = (size_t)taps * cb * tc::BK;
+        std::vector<float> g((size_t)M * K, 0.f);
+        for (int m = 0; m < M; ++m)
+            for (int j = 0; j < taps; ++j)
+                memcpy(&g[(size_t)m * K + (size_t)j * cb * tc::BK], &W[((size_t)m * taps + j) * Cin], (size_t)Cin * sizeof(float));
+        return g;
+    }
     void build(const std::vector<float>& W /*[M][taps][Cin]*/, int M_, int taps_, int Cin_) {
         M = M_; taps = taps_; Cin = Cin_; cblocks = cdiv(Cin, tc::BK);
         const size_t K = (size_t)taps * cblocks * tc::BK;
-        std::vector<bf16> h((size_t)M * K, __float2bfloat16_rn(0.f)), l((size_t)M * K, __float2bfloat16_rn(0.f));
-        for (int m = 0; m < M; ++m)
-            for (int j = 0; j < taps; ++j)
-                for (int c = 0; c < Cin; ++c) {
-                    const float w = W[((size_t)m * taps + j) * Cin + c];
-                    const size_t o = (size_t)m * K + ((size_t)j * cblocks) * tc::BK + c;
-                    h[o] = __float2bfloat16_rn(w);
-                    l[o] = __float2bfloat16_rn(w - __bfloat162float(h[o]));
-                }
+        const std::vector<float> g = pad_k(W, M, taps, Cin);
+        std::vector<bf16> h(g.size()), l(g.size());
+        for (size_t i = 0; i < g.size(); ++i) {
+            h[i] = __float2bfloat16_rn(g[i]);
+            l[i] = __float2bfloat16_rn(g[i] - __bfloat162float(h[i]));
+        }
         hi.upload(h.data(), h.size());
         lo.upload(l.data(), l.size());
         B2A_CUDA(cudaDeviceSynchronize());
@@ -830,5 +837,23 @@ int32_t b2a_speech_tokenizer_chunked_decode(b2a_speech_tokenizer* h, const int32
 }
 
 void b2a_speech_tokenizer_destroy(b2a_speech_tokenizer* h) { delete h; }
+
+// Host-only: the GEMM weight matrix the implicit convolution reads, from an MLX-layout [out, k, in] weight.
+// stride == 0: plain causal conv (rows = out, taps = k); stride > 0: transposed conv with k = n * stride (rows = stride * out
+// phase-major, taps = n).  layout_out receives [rows][taps][ceil(in / 64) * 64] fp32 (capacity in floats).
+int32_t b2a_speech_tokenizer_debug_layout(const float* w, int32_t out, int32_t k, int32_t in, int32_t stride, float* layout_out, int64_t capacity,
+                                          int32_t* rows, int32_t* taps, int32_t* kpad) {
+    return guarded([&] {
+        B2A_CHECK(w && layout_out && rows && taps && kpad && out >= 1 && k >= 1 && in >= 1 && stride >= 0, B2A_ERR_INVALID_INPUT,
+                  "b2a_speech_tokenizer_debug_layout: bad argument");
+        B2A_CHECK(stride == 0 || k % stride == 0, B2A_ERR_INVALID_INPUT, "b2a_speech_tokenizer_debug_layout: kernel must be a multiple of the stride");
+        std::vector<float> src(w, w + (size_t)out * k * in);
+        const int M = stride ? stride * out : out, T = stride ? k / stride : k;
+        const std::vector<float> g = IW::pad_k(stride ? b2a_speech_tokenizer::convt_w(src, out, k, in, stride) : src, M, T, in);
+        B2A_CHECK((int64_t)g.size() <= capacity, B2A_ERR_INVALID_INPUT, "b2a_speech_tokenizer_debug_layout: output buffer too small");
+        memcpy(layout_out, g.data(), g.size() * sizeof(float));
+        *rows = M; *taps = T; *kpad = cdiv(in, tc::BK) * tc::BK;
+    });
+}
 
 }  // extern "C"
