@@ -486,6 +486,13 @@ void b2a_speech_tokenizer_destroy(b2a_speech_tokenizer* h);
  * stride * out (phase-major), taps = n.  layout_out: [rows][taps][kpad] float32, kpad = ceil(in / 64) * 64.            */
 int32_t b2a_speech_tokenizer_debug_layout(const float* w, int32_t out, int32_t k, int32_t in, int32_t stride, float* layout_out,
                                           int64_t capacity, int32_t* rows, int32_t* taps, int32_t* kpad);
+/* Test entry (tests/test_gpu_implicit_conv.py): one launch of the implicit-GEMM causal convolution kernel
+ * (csrc/implicit_conv.cuh) on HOST data: w [M][taps][Cin], x [B][Ttot][Cin]; out[b, t*up + rho, co] for m = rho * (M/up) + co is
+ * sum_j sum_c w[m, j, c] * x[b, t + shift0 + j*dil, c] through the fused epilogue (bias, bias twice at t = 0, GELU, gamma, add,
+ * SnakeBeta on the hi/lo copy).  xo [B][T*up][M/up] in/out or null; hl_out [B][Hout + T*up][M/up] or null.                 */
+int32_t b2a_implicit_conv_test(const float* w, int32_t M, int32_t taps, int32_t Cin, const float* x, int32_t B, int32_t Ttot, int32_t T,
+                               int32_t dil, int32_t shift0, int32_t up, const float* bias, const float* gamma, int32_t gelu, int32_t add,
+                               int32_t bias_twice_t0, const float* sa, const float* sb, int32_t Hout, float* xo, float* hl_out);
 
 #ifdef __cplusplus
 }

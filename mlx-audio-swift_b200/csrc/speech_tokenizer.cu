@@ -856,4 +856,56 @@ int32_t b2a_speech_tokenizer_debug_layout(const float* w, int32_t out, int32_t k
     });
 }
 
+// Standalone entry for tests/test_gpu_implicit_conv.py: one launch of ic::implicit_conv_kernel on host data.
+//   w [M][taps][Cin], x [B][Ttot][Cin] (split into hi/lo planes here), bias / gamma / sa / sb [M / up] or null,
+//   xo [B][T*up][M/up] in/out or null, hl_out [B][Hout + T*up][M/up] (hi + lo recombined; frames below Hout come back 0) or null.
+int32_t b2a_implicit_conv_test(const float* w, int32_t M, int32_t taps, int32_t Cin, const float* x, int32_t B, int32_t Ttot, int32_t T,
+                               int32_t dil, int32_t shift0, int32_t up, const float* bias, const float* gamma, int32_t gelu, int32_t add,
+                               int32_t bias_twice_t0, const float* sa, const float* sb, int32_t Hout, float* xo, float* hl_out) {
+    return guarded([&] {
+        B2A_CHECK(w && x && M >= 1 && taps >= 1 && Cin >= 8 && Cin % 8 == 0 && B >= 1 && Ttot >= 1 && T >= 1 && dil >= 1 && shift0 >= 0 && up >= 1 &&
+                      M % up == 0 && (M / up) % 8 == 0 && Hout >= 0 && (xo || hl_out) && (!add || xo) && ((sa == nullptr) == (sb == nullptr)),
+                  B2A_ERR_INVALID_INPUT, "b2a_implicit_conv_test: bad argument");
+        require_device(0);
+        B2A_CUDA(cudaSetDevice(0));
+        B2A_CUDA(cudaFuncSetAttribute(ic::implicit_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ic::SMEM_BYTES));
+        int num_sms = 148;
+        B2A_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, 0));
+        const int Cout = M / up;
+        const long long To = (long long)T * up;
+        IW W;
+        W.build(std::vector<float>(w, w + (size_t)M * taps * Cin), M, taps, Cin);
+        const size_t nx = (size_t)B * Ttot * Cin, no = (size_t)B * To * Cout, nh = (size_t)B * (Hout + To) * Cout;
+        std::vector<bf16> xp(2 * nx);
+        for (size_t i = 0; i < nx; ++i) {
+            xp[i] = __float2bfloat16_rn(x[i]);
+            xp[nx + i] = __float2bfloat16_rn(x[i] - __bfloat162float(xp[i]));
+        }
+        DBuf<bf16> dx, dh;
+        DBuf<float> dxo, dbias, dgamma, dsa, dsb;
+        dx.upload(xp.data(), xp.size());
+        ic::Args a{};
+        a.M = M; a.m_tiles = cdiv(M, tc::BM); a.taps = taps; a.cblocks = W.cblocks; a.dil = dil; a.shift0 = shift0;
+        a.B = B; a.T = T; a.t_tiles = cdiv(T, ic::HALF); a.Cout = Cout; a.up = up; a.gelu = gelu; a.add = add; a.bias_twice_t0 = bias_twice_t0; a.Hout = Hout;
+        if (bias) { dbias.upload(bias, Cout); a.bias = dbias.p; }
+        if (gamma) { dgamma.upload(gamma, Cout); a.gamma = dgamma.p; }
+        if (sa) { dsa.upload(sa, Cout); dsb.upload(sb, Cout); a.sa = dsa.p; a.sb = dsb.p; }
+        if (xo) { dxo.upload(xo, no); a.xo = dxo.p; }
+        if (hl_out) { dh.alloc(2 * nh); B2A_CUDA(cudaMemset(dh.p, 0, 2 * nh * sizeof(bf16))); a.hl = dh.p; }
+        B2A_CUDA(cudaDeviceSynchronize());
+        const CUtensorMap tb = make_tmap_planes(dx.p, Cin, Ttot, B);
+        const long long tiles = (long long)B * a.t_tiles * a.m_tiles;
+        launch_pdl(ic::implicit_conv_kernel, dim3((unsigned)std::min<long long>(num_sms, tiles)), dim3(ic::IC_THREADS), ic::SMEM_BYTES, (cudaStream_t)0,
+                   W.th, W.tl, tb, a);
+        B2A_CUDA(cudaGetLastError());
+        B2A_CUDA(cudaDeviceSynchronize());
+        if (xo) B2A_CUDA(cudaMemcpy(xo, dxo.p, no * sizeof(float), cudaMemcpyDeviceToHost));
+        if (hl_out) {
+            std::vector<bf16> hp(2 * nh);
+            B2A_CUDA(cudaMemcpy(hp.data(), dh.p, 2 * nh * sizeof(bf16), cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < nh; ++i) hl_out[i] = __bfloat162float(hp[i]) + __bfloat162float(hp[nh + i]);
+        }
+    });
+}
+
 }  // extern "C"

@@ -14,6 +14,7 @@ import numpy as np
 import pytest
 import torch
 
+from implicit_conv_model import implicit_conv
 from oracle import qwen3_tts_codec as oc
 
 
@@ -27,39 +28,6 @@ def lib_layout(b2a, w, stride=0):
     b2a._ffi.check(b2a._ffi.lib().b2a_speech_tokenizer_debug_layout(b2a._ffi.ptr(w), out, k, cin, stride, b2a._ffi.ptr(buf), cap,
                                                                     C.byref(rows), C.byref(taps), C.byref(kpad)))
     return buf[: rows.value * taps.value * kpad.value].reshape(rows.value, taps.value, kpad.value).astype(np.float64), cin
-
-
-def implicit_conv(Wg, cin, X, T, *, dil=1, shift0=0, up=1, bias=None, gamma=None, gelu=False, add=False, bias_twice_t0=False,
-                  xo=None, hl=None, Hout=0, sa=None, sb=None):
-    """The Args contract of ic::implicit_conv_kernel.  X: planes as one float64 array [B, Ttot, cin]; xo [B, T*up, Cout] and
-    hl [B, Hout + T*up, Cout] are written in place."""
-    M, taps, _ = Wg.shape
-    B, Ttot, _ = X.shape
-    Cout = M // up
-    acc = np.zeros((B, T, M))
-    for j in range(taps):
-        for t in range(T):
-            f = t + shift0 + j * dil
-            if 0 <= f < Ttot:                                      # out-of-range frames are TMA zero fill
-                acc[:, t, :] += X[:, f, :] @ Wg[:, j, :cin].T
-    for rho in range(up):
-        val = acc[:, :, rho * Cout:(rho + 1) * Cout].copy()
-        if bias is not None:
-            val += bias
-            if bias_twice_t0:
-                val[:, 0, :] += bias
-        if gelu:
-            val = 0.5 * val * (1.0 + np.vectorize(math.erf)(val / math.sqrt(2.0)))
-        if gamma is not None:
-            val = val * gamma
-        fo = np.arange(T) * up + rho
-        if add:
-            val = val + xo[:, fo, :]
-        if xo is not None:
-            xo[:, fo, :] = val
-        if hl is not None:
-            hv = val + sb * np.sin(sa * val) ** 2 if sa is not None else val
-            hl[:, Hout + fo, :] = hv
 
 
 class PlaneState:
