@@ -11,10 +11,12 @@ from .vocos import Vocos
 from .encodec import Encodec, EncodecConfig, EncodecEncodedAudio
 from .loading import Weights, llama_config_from_json
 from .whisper import STTGenerateParameters, STTOutput, WhisperModel
+from .streaming import StreamingConfig, StreamingEncoder, StreamingFrontEnd
 
 __all__ = ["AudioGenerationError", "IncrementalMelSpectrogram", "LogMel", "compute_mel_spectrogram", "hanning_window",
            "mel_filters", "whisper_encoder_features", "SNAC", "LlamaTTSModel", "GenerateParameters",
-           "AudioGenerationInfo", "Vocos", "Weights", "llama_config_from_json", "Encodec", "EncodecConfig", "EncodecEncodedAudio", "WhisperModel", "STTGenerateParameters", "STTOutput"]
+           "AudioGenerationInfo", "Vocos", "Weights", "llama_config_from_json", "Encodec", "EncodecConfig", "EncodecEncodedAudio", "WhisperModel", "STTGenerateParameters", "STTOutput",
+           "StreamingConfig", "StreamingEncoder", "StreamingFrontEnd"]
 
 
 def device_count() -> int:
