@@ -481,6 +481,16 @@ int32_t b2a_speech_tokenizer_streaming_decode(b2a_speech_tokenizer* h, const int
 int32_t b2a_speech_tokenizer_chunked_decode(b2a_speech_tokenizer* h, const int32_t* codes, int32_t batch, int32_t num_groups,
                                             int32_t frames, int32_t chunk_size, int32_t left_context, float* wave);
 void b2a_speech_tokenizer_destroy(b2a_speech_tokenizer* h);
+/* Loading (host-only except the final create): the decoder half of Qwen3TTSSpeechTokenizer.sanitize (:1094-1440) on an open
+ * checkpoint -- prefixes stripped, PyTorch conv / transposed-conv layouts moved to MLX's with the reference's shape heuristic
+ * (checkArrayShapeQwen3 :1445-1455), upsample.X.Y -> upsample.X.layers.Y, codebook statistics kept, encoder.* and speaker-encoder
+ * keys dropped, the leading "decoder." removed; Qwen3TTSTokenizerConfig decoding (Qwen3TTSConfig.swift:358-385,518-527; a missing
+ * config.json means defaults, Qwen3TTS.swift:1246-1255); loadSpeechTokenizer (Qwen3TTS.swift:1244-1275).                       */
+int32_t b2a_weights_sanitize_speech_tokenizer(b2a_weights* w);
+int32_t b2a_speech_tokenizer_config_from_json(const char* config_path, int32_t max_batch, int32_t max_cache_frames,
+                                              b2a_speech_tokenizer_config* cfg, int32_t* decode_upsample_rate);
+int32_t b2a_speech_tokenizer_create_from_directory(const char* dir, int32_t device, int32_t max_batch, int32_t max_cache_frames,
+                                                   b2a_speech_tokenizer** out, int32_t* decode_upsample_rate);
 /* Host-only parity hook (no device needed): the GEMM weight matrix the implicit convolution reads for an MLX-layout
  * [out, k, in] weight -- stride 0: causal conv, rows = out, taps = k; stride > 0: transposed conv with k = n * stride, rows =
  * stride * out (phase-major), taps = n.  layout_out: [rows][taps][kpad] float32, kpad = ceil(in / 64) * 64.            */

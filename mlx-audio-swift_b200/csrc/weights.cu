@@ -408,6 +408,104 @@ struct b2a_weights {
         }
     }
 
+
+    // ---- Qwen3-TTS speech tokenizer, decoder half of Qwen3TTSSpeechTokenizer.sanitize (Qwen3TTSSpeechTokenizer.swift:1094-1440).
+    // Output: the keys b2a_speech_tokenizer_create takes (below the "decoder." module) in MLX layouts.  encoder.* (voice-cloning
+    // encoder) and speaker-encoder keys are dropped.
+    static bool check_array_shape(const WItem& t) {      // checkArrayShapeQwen3 (:1445-1455)
+        if (t.ndim != 3) return false;
+        const int64_t d2 = t.shape[1], d3 = t.shape[2];
+        if (d2 == 1) return d3 > 64;
+        if (d3 == 1) return d2 <= 64;
+        return d2 < d3;
+    }
+    void permute3(WItem& t, int p0, int p1, int p2) {    // out[i, j, k] = in[index with out axis a taken from in axis p_a]
+        std::vector<float> v = as_f32(t);
+        const int64_t in_shape[3] = {t.shape[0], t.shape[1], t.shape[2]};
+        const int p[3] = {p0, p1, p2};
+        const int64_t o0 = in_shape[p0], o1 = in_shape[p1], o2 = in_shape[p2];
+        const int64_t in_stride[3] = {in_shape[1] * in_shape[2], in_shape[2], 1};
+        auto o = std::make_shared<std::vector<uint8_t>>((size_t)(o0 * o1 * o2) * 4);
+        float* of = (float*)o->data();
+        for (int64_t a = 0; a < o0; ++a)
+            for (int64_t b = 0; b < o1; ++b)
+                for (int64_t c = 0; c < o2; ++c)
+                    of[(a * o1 + b) * o2 + c] = v[a * in_stride[p[0]] + b * in_stride[p[1]] + c * in_stride[p[2]]];
+        t.owned = o; t.data = of; t.dtype = B2A_DTYPE_F32; t.shape[0] = o0; t.shape[1] = o1; t.shape[2] = o2;
+    }
+    static bool has_component_with_suffix(const std::string& key, const std::string& comp) {     // stripSpeakerEncoderPrefix != nil (Qwen3TTSSpeakerEncoder.swift:345-354)
+        size_t pos = 0;
+        while (pos <= key.size()) {
+            const size_t dot = key.find('.', pos);
+            const std::string part = key.substr(pos, dot == std::string::npos ? std::string::npos : dot - pos);
+            if (part == comp) return dot != std::string::npos && dot + 1 < key.size();
+            if (dot == std::string::npos) break;
+            pos = dot + 1;
+        }
+        return false;
+    }
+    void sanitize_speech_tokenizer() {
+        std::vector<WItem> out;
+        std::vector<std::pair<std::string, WItem>> usage, sums;
+        for (auto& it : items) {
+            std::string k = it.name;
+            for (bool stripped = true; stripped;) {                   // stripKnownPrefixes (:1118-1133)
+                stripped = false;
+                for (const char* pre : {"speech_tokenizer.", "encoder_model.", "decoder_model."}) {
+                    std::string rest;
+                    if (strip(k, pre, rest)) { k = rest; stripped = true; break; }
+                }
+            }
+            if (k.empty() || k == "encoder_model" || k == "decoder_model" || k == "speech_tokenizer") continue;
+            if (has_component_with_suffix(k, "speaker_encoder")) continue;
+            const bool cu = k.find("_codebook.cluster_usage") != std::string::npos, es = k.find("_codebook.embedding_sum") != std::string::npos;
+            if (cu || es) {                                           // :1226-1235
+                WItem t = it;
+                const std::string base = k.substr(0, k.rfind("._codebook."));
+                (cu ? usage : sums).emplace_back(base, std::move(t));
+                continue;
+            }
+            if (k.find("_codebook.initialized") != std::string::npos || k.find(".codebook.initialized") != std::string::npos) continue;
+            if (k.compare(0, 8, "encoder.") == 0) continue;
+            WItem t = it;
+            const bool tconv = (k.find("upsample") != std::string::npos && k.find(".0.conv.weight") != std::string::npos) ||
+                               (k.find("decoder.decoder") != std::string::npos && k.find("block.1.conv.weight") != std::string::npos);
+            if (t.ndim == 3) {
+                if (tconv) { if (!check_array_shape(t)) permute3(t, 1, 2, 0); }                      // torch [in, out, k] -> [out, k, in]
+                else if (k.find("conv.weight") != std::string::npos || k.find("_proj.weight") != std::string::npos) {
+                    if (!check_array_shape(t)) permute3(t, 0, 2, 1);                                  // torch [out, in, k] -> [out, k, in]
+                }
+            }
+            // upsample.X.Y.rest -> upsample.X.layers.Y.rest (:1406-1413)
+            const size_t u = k.find("upsample.");
+            if (u != std::string::npos) {
+                size_t a = u + 9, b = a;
+                while (b < k.size() && isdigit((unsigned char)k[b])) ++b;
+                if (b > a && b < k.size() && k[b] == '.') {
+                    size_t c = b + 1, d = c;
+                    while (d < k.size() && isdigit((unsigned char)k[d])) ++d;
+                    if (d > c) k = k.substr(0, b + 1) + "layers." + k.substr(c);
+                }
+            }
+            t.name = k;
+            out.push_back(std::move(t));
+        }
+        for (auto& u : usage)
+            for (auto& e : sums)
+                if (e.first == u.first) {                             // both statistics present (:1431-1438)
+                    WItem a = u.second, b = e.second;
+                    a.name = u.first + ".codebook.cluster_usage";
+                    b.name = u.first + ".codebook.embedding_sum";
+                    out.push_back(std::move(a));
+                    out.push_back(std::move(b));
+                }
+        for (auto& t : out) {                                         // the decoder module's own keys
+            std::string rest;
+            if (strip(t.name, "decoder.", rest) && !(rest.size() && isdigit((unsigned char)rest[0]))) t.name = rest;
+        }
+        items = std::move(out);
+    }
+
     std::vector<b2a_tensor> table() const {
         std::vector<b2a_tensor> t(items.size());
         for (size_t i = 0; i < items.size(); ++i) {
@@ -507,6 +605,71 @@ int32_t b2a_tts_create_from_directory(const char* model_dir, int32_t device, int
         w->sanitize_llama(cfg.tie_word_embeddings != 0, gs, bits);
         const std::vector<b2a_tensor> tab = w->table();
         st = b2a_tts_create(device, &cfg, tab.data(), (int32_t)tab.size(), snac, out);
+        if (st != B2A_OK) throw Error(st, b2a_last_error());
+    });
+}
+
+int32_t b2a_weights_sanitize_speech_tokenizer(b2a_weights* w) {
+    return guarded([&] {
+        B2A_CHECK(w, B2A_ERR_INVALID_INPUT, "b2a_weights_sanitize_speech_tokenizer: null handle");
+        w->sanitize_speech_tokenizer();
+    });
+}
+
+// speech_tokenizer/config.json -> b2a_speech_tokenizer_config (Qwen3TTSTokenizerConfig / ...DecoderConfig, Qwen3TTSConfig.swift:358-385,518-527).
+// A missing file means "all defaults", as loadSpeechTokenizer does (Qwen3TTS.swift:1246-1255).
+int32_t b2a_speech_tokenizer_config_from_json(const char* config_path, int32_t max_batch, int32_t max_cache_frames, b2a_speech_tokenizer_config* cfg,
+                                              int32_t* decode_upsample_rate) {
+    return guarded([&] {
+        B2A_CHECK(cfg, B2A_ERR_INVALID_INPUT, "b2a_speech_tokenizer_config_from_json: null argument");
+        Json j;
+        j.kind = Json::Obj;
+        struct stat st{};
+        if (config_path && *config_path && stat(config_path, &st) == 0) j = read_json_file(config_path);
+        B2A_CHECK(j.kind == Json::Obj, B2A_ERR_MODEL_NOT_INITIALIZED, "speech tokenizer config.json is not an object");
+        Json empty;
+        empty.kind = Json::Obj;
+        const Json* dj = j.find("decoder_config");
+        const Json& d = (dj && dj->kind == Json::Obj) ? *dj : empty;
+        b2a_speech_tokenizer_config c{};
+        c.codebook_size = (int)d.number("codebook_size", 2048); c.codebook_dim = (int)d.number("codebook_dim", 512);
+        c.latent_dim = (int)d.number("latent_dim", 1024); c.decoder_dim = (int)d.number("decoder_dim", 1536);
+        c.hidden_size = (int)d.number("hidden_size", 512); c.intermediate_size = (int)d.number("intermediate_size", 1024);
+        c.head_dim = (int)d.number("head_dim", 64); c.num_attention_heads = (int)d.number("num_attention_heads", 16);
+        c.num_key_value_heads = (int)d.number("num_key_value_heads", 16); c.num_hidden_layers = (int)d.number("num_hidden_layers", 8);
+        c.num_quantizers = (int)d.number("num_quantizers", 16); c.num_semantic_quantizers = (int)d.number("num_semantic_quantizers", 1);
+        c.rms_norm_eps = (float)d.number("rms_norm_eps", 1e-5); c.rope_theta = (float)d.number("rope_theta", 10000.0);
+        c.attention_bias = (int)d.number("attention_bias", 0);
+        auto list = [&](const char* key, std::initializer_list<int> dflt, int32_t* dst, int32_t* n) {
+            std::vector<int> v(dflt);
+            if (const Json* a = d.find(key); a && a->kind == Json::Arr) { v.clear(); for (auto& e : a->arr) v.push_back((int)e.num); }
+            B2A_CHECK(v.size() <= 8, B2A_ERR_MODEL_NOT_INITIALIZED, std::string("speech tokenizer config: more than 8 entries in ") + key);
+            *n = (int32_t)v.size();
+            for (size_t i = 0; i < v.size(); ++i) dst[i] = v[i];
+        };
+        list("upsample_rates", {8, 5, 4, 3}, c.upsample_rates, &c.num_upsample_rates);
+        list("upsampling_ratios", {2, 2}, c.upsampling_ratios, &c.num_upsampling_ratios);
+        c.max_batch = max_batch; c.max_cache_frames = max_cache_frames;
+        *cfg = c;
+        if (decode_upsample_rate) *decode_upsample_rate = (int32_t)j.number("decode_upsample_rate", 1920);
+    });
+}
+
+// loadSpeechTokenizer (Qwen3TTS.swift:1244-1275): <dir>/config.json (optional) + every *.safetensors -> sanitize -> create.
+int32_t b2a_speech_tokenizer_create_from_directory(const char* dir, int32_t device, int32_t max_batch, int32_t max_cache_frames,
+                                                   b2a_speech_tokenizer** out, int32_t* decode_upsample_rate) {
+    return guarded([&] {
+        B2A_CHECK(dir && out, B2A_ERR_INVALID_INPUT, "b2a_speech_tokenizer_create_from_directory: null argument");
+        *out = nullptr;
+        b2a_speech_tokenizer_config cfg{};
+        const std::string d = dir;
+        int32_t st = b2a_speech_tokenizer_config_from_json((d + "/config.json").c_str(), max_batch, max_cache_frames, &cfg, decode_upsample_rate);
+        if (st != B2A_OK) throw Error(st, b2a_last_error());
+        std::unique_ptr<b2a_weights> w(new b2a_weights());
+        w->load(d);
+        w->sanitize_speech_tokenizer();
+        const std::vector<b2a_tensor> tab = w->table();
+        st = b2a_speech_tokenizer_create(device, &cfg, tab.data(), (int32_t)tab.size(), out);
         if (st != B2A_OK) throw Error(st, b2a_last_error());
     });
 }

@@ -34,6 +34,10 @@ class Weights:
         """LlamaTTSModel.sanitize (LlamaTTS.swift:583-593) + MLX affine de-quantisation to bf16 when bits > 0."""
         _ffi.check(_ffi.lib().b2a_weights_sanitize_llama(self._h, int(tie_word_embeddings), group_size, bits))
 
+    def sanitize_speech_tokenizer(self) -> None:
+        """Decoder half of Qwen3TTSSpeechTokenizer.sanitize (Qwen3TTSSpeechTokenizer.swift:1094-1440); keys end up relative to the decoder."""
+        _ffi.check(_ffi.lib().b2a_weights_sanitize_speech_tokenizer(self._h))
+
     def tensors(self) -> Dict[str, object]:
         """name -> numpy array (float32 / int32) or torch.bfloat16 tensor.  COPIES (the handle owns the mapped bytes)."""
         import torch
@@ -68,3 +72,12 @@ def llama_config_from_json(config_path: Union[str, Path], max_batch: int = 8, ma
     cfg, gs, bits = _ffi.LlamaConfig(), C.c_int32(0), C.c_int32(0)
     _ffi.check(_ffi.lib().b2a_tts_config_from_json(str(config_path).encode(), max_batch, max_context, C.byref(cfg), C.byref(gs), C.byref(bits)))
     return cfg, int(gs.value), int(bits.value)
+
+
+def speech_tokenizer_config_from_json(config_path: Union[str, Path, None], max_batch: int = 1, max_cache_frames: int = 4096):
+    """speech_tokenizer/config.json -> (SpeechTokenizerConfig ctypes struct, decode_upsample_rate); a missing file gives the
+    defaults (Qwen3TTSConfig.swift:358-385,518-527; Qwen3TTS.swift:1246-1255)."""
+    cfg, rate = _ffi.SpeechTokenizerConfig(), C.c_int32(0)
+    path = b"" if config_path is None else str(config_path).encode()
+    _ffi.check(_ffi.lib().b2a_speech_tokenizer_config_from_json(path, max_batch, max_cache_frames, C.byref(cfg), C.byref(rate)))
+    return cfg, int(rate.value)

@@ -68,7 +68,8 @@ def sanitize(weights: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
                 if k.startswith(p):
                     k, stripped = k[len(p):], True
                     break
-        if k in ("", "encoder_model", "decoder_model", "speech_tokenizer") or k.startswith("speaker_encoder."):
+        parts = k.split(".")
+        if k in ("", "encoder_model", "decoder_model", "speech_tokenizer") or ("speaker_encoder" in parts and parts.index("speaker_encoder") + 1 < len(parts)):
             continue
         v = np.asarray(v)
         if "_codebook.cluster_usage" in k or "_codebook.embedding_sum" in k:
@@ -126,6 +127,19 @@ class Qwen3TTSSpeechTokenizerDecoder:
         _ffi.check(_ffi.lib().b2a_speech_tokenizer_create(device, C.byref(c), table, len(w), C.byref(self._h)))
         del keep
         self.total_upsample = int(_ffi.lib().b2a_speech_tokenizer_total_upsample(self._h))
+
+    @classmethod
+    def from_model_directory(cls, path, device: int = 0, max_batch: int = 1, max_cache_frames: int = 4096) -> "Qwen3TTSSpeechTokenizerDecoder":
+        """loadSpeechTokenizer (Qwen3TTS.swift:1244-1275): <path>/config.json (optional) + every *.safetensors -> sanitize -> weights on
+        the device, all inside the library."""
+        self = cls.__new__(cls)
+        self.config = None
+        self._h = C.c_void_p()
+        rate = C.c_int32(0)
+        _ffi.check(_ffi.lib().b2a_speech_tokenizer_create_from_directory(str(path).encode(), device, max_batch, max_cache_frames, C.byref(self._h), C.byref(rate)))
+        self.total_upsample = int(_ffi.lib().b2a_speech_tokenizer_total_upsample(self._h))
+        self.decode_upsample_rate = int(rate.value)
+        return self
 
     @property
     def stream(self) -> int:

@@ -205,7 +205,8 @@ def sanitize(weights: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
                 if k.startswith(p):
                     k, stripped = k[len(p):], True
                     break
-        if k in ("", "encoder_model", "decoder_model", "speech_tokenizer") or k.startswith("speaker_encoder."):
+        parts = k.split(".")                                      # stripSpeakerEncoderPrefix != nil (Qwen3TTSSpeakerEncoder.swift:345-354)
+        if k in ("", "encoder_model", "decoder_model", "speech_tokenizer") or ("speaker_encoder" in parts and parts.index("speaker_encoder") + 1 < len(parts)):
             continue
         if "_codebook.cluster_usage" in k or "_codebook.embedding_sum" in k:     # :1219-1229
             base = k[: k.rfind("._codebook.")]

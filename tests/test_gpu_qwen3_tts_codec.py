@@ -100,3 +100,26 @@ def test_default_geometry_and_errors(b2a, codec):
     with pytest.raises(b2a.AudioGenerationError) as e:
         make(codec, cfg, W2)
     assert e.value.case == "modelNotInitialized"
+
+
+def test_from_model_directory(codec, tmp_path):
+    """loadSpeechTokenizer: a PyTorch-layout safetensors checkpoint + config.json through the library's own sanitize."""
+    import json
+    from safetensors.torch import save_file
+    from test_qwen3_tts_codec_host import torch_layout_checkpoint
+    # every k = 1 conv needs > 64 input channels here: the reference's layout heuristic (checkArrayShapeQwen3) reads a PyTorch
+    # [out, <= 64, 1] weight as "already MLX" and would leave it untransposed (true of the reference itself, not only of this port)
+    cfg = mid_config(codebook_dim=144, decoder_dim=288, upsample_rates=[4, 3])
+    W = oc.init_weights(cfg, 12)
+    d = tmp_path / "speech_tokenizer"
+    d.mkdir()
+    save_file({k: v.contiguous() for k, v in torch_layout_checkpoint(W).items()}, str(d / "model.safetensors"))
+    keys = ("latent_dim", "codebook_dim", "codebook_size", "decoder_dim", "hidden_size", "intermediate_size", "head_dim", "num_attention_heads",
+            "num_key_value_heads", "num_hidden_layers", "num_quantizers", "num_semantic_quantizers", "upsample_rates", "upsampling_ratios")
+    (d / "config.json").write_text(json.dumps({"decode_upsample_rate": cfg.total_upsample, "decoder_config": {k: getattr(cfg, k) for k in keys}}))
+    m = codec.Qwen3TTSSpeechTokenizerDecoder.from_model_directory(d)
+    assert m.total_upsample == cfg.total_upsample == m.decode_upsample_rate
+    codes = np.random.default_rng(5).integers(0, cfg.codebook_size, (1, cfg.num_quantizers, 9))
+    Ws = oc.strip_decoder_prefix(oc.sanitize(torch_layout_checkpoint(W)))
+    assert all(tuple(Ws[k].shape) == tuple(W[k].shape) for k in W)
+    assert max_rel_to_peak(m(codes), oc.SpeechTokenizerDecoder(cfg, W)(codes).numpy()) < TOL
