@@ -13,6 +13,7 @@ ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 from oracle import dsp, llama, snac  # noqa: E402
 from oracle import encodec as oe  # noqa: E402
+from oracle import qwen3_tts_codec as oq  # noqa: E402
 from oracle import vocos as ov  # noqa: E402
 from oracle import whisper as ow  # noqa: E402
 
@@ -104,12 +105,32 @@ def codecs_small():
                         encodec_stats=stats(z), encodec_shape=np.array(z.shape))
 
 
+def qwen3_codec_config():
+    """The mid-size geometry the (gated) GPU tests of row N1 use."""
+    return oq.tiny_config(latent_dim=128, codebook_dim=128, codebook_size=64, decoder_dim=256, hidden_size=64, intermediate_size=128, head_dim=32,
+                          num_attention_heads=4, num_key_value_heads=2)
+
+
+def qwen3_codec():
+    """Qwen3-TTS speech-tokenizer decoder (row N1): one-shot decode and a three-chunk streaming decode (bias-twice behaviour included)."""
+    cfg = qwen3_codec_config()
+    W = oq.init_weights(cfg, 5)
+    codes = np.random.default_rng(1).integers(0, cfg.codebook_size, (2, cfg.num_quantizers, 20))
+    d = oq.SpeechTokenizerDecoder(cfg, W)
+    full = d(codes)[:, 0].numpy()
+    d.reset_streaming_state()
+    st = np.concatenate([d.streaming_step(codes[:, :, a:b])[:, 0].numpy() for a, b in ((0, 7), (7, 8), (8, 20))], axis=-1)
+    up = cfg.total_upsample
+    np.savez_compressed(OUT / "qwen3_codec.npz", full_first=full[:, :64].astype(np.float32), full_last=full[:, -64:].astype(np.float32), full_stats=stats(full),
+                        stream_boundary=st[:, 7 * up - 32: 8 * up + 32].astype(np.float32), stream_stats=stats(st), shape=np.array(full.shape))
+
+
 if __name__ == "__main__":
     import argparse
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default=None, help="regenerate a single fixture (mel | snac | llama | whisper | codecs)")
+    ap.add_argument("--only", default=None, help="regenerate a single fixture (mel | snac | llama | whisper | codecs | qwen3_codec)")
     only = ap.parse_args().only
-    for name, fn in (("mel", mel), ("snac", snac_small), ("llama", llama_tiny), ("whisper", whisper_tiny), ("codecs", codecs_small)):
+    for name, fn in (("mel", mel), ("snac", snac_small), ("llama", llama_tiny), ("whisper", whisper_tiny), ("codecs", codecs_small), ("qwen3_codec", qwen3_codec)):
         if only is None or only == name:
             fn()
     for f in sorted(OUT.glob("*.npz")):

@@ -123,3 +123,26 @@ def test_from_model_directory(codec, tmp_path):
     Ws = oc.strip_decoder_prefix(oc.sanitize(torch_layout_checkpoint(W)))
     assert all(tuple(Ws[k].shape) == tuple(W[k].shape) for k in W)
     assert max_rel_to_peak(m(codes), oc.SpeechTokenizerDecoder(cfg, W)(codes).numpy()) < TOL
+
+
+def test_decode_vs_committed_golden(codec):
+    """tests/golden/qwen3_codec.npz: first / last 64 samples + stats of the one-shot decode, and the samples around two chunk
+    boundaries of a streamed decode (where the reference counts the transposed-conv bias twice)."""
+    import importlib.util
+    from conftest import GOLDEN
+    spec = importlib.util.spec_from_file_location("make_golden", GOLDEN / "make_golden.py")
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    g = np.load(GOLDEN / "qwen3_codec.npz")
+    cfg = mg.qwen3_codec_config()
+    W = oc.init_weights(cfg, 5)
+    m = make(codec, cfg, W, max_batch=2)
+    codes = np.random.default_rng(1).integers(0, cfg.codebook_size, (2, cfg.num_quantizers, 20))
+    peak = max(abs(g["full_stats"][2]), abs(g["full_stats"][3]))
+    y = m(codes)[:, 0]
+    assert y.shape == tuple(g["shape"]) and np.abs(y[:, :64] - g["full_first"]).max() < TOL * peak and np.abs(y[:, -64:] - g["full_last"]).max() < TOL * peak
+    assert np.abs(mg.stats(y) - g["full_stats"]).max() < TOL * peak
+    m.reset_streaming_state()
+    st = np.concatenate([m.streaming_step(codes[:, :, a:b])[:, 0] for a, b in ((0, 7), (7, 8), (8, 20))], axis=-1)
+    up = cfg.total_upsample
+    assert np.abs(st[:, 7 * up - 32: 8 * up + 32] - g["stream_boundary"]).max() < TOL * peak

@@ -254,3 +254,25 @@ def test_check_array_shape_heuristic():
     assert oc.check_array_shape((1024, 7, 1)) and not oc.check_array_shape((1024, 1, 7))
     assert oc.check_array_shape((512, 1, 256)) and not oc.check_array_shape((512, 256, 1))
     assert not oc.check_array_shape((4, 4))
+
+
+def test_oracle_reproduces_committed_golden():
+    """tests/golden/qwen3_codec.npz (tests/golden/make_golden.py --only qwen3_codec): the fixture the gated GPU test also compares with."""
+    import importlib.util
+    from conftest import GOLDEN
+    spec = importlib.util.spec_from_file_location("make_golden", GOLDEN / "make_golden.py")
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    g = np.load(GOLDEN / "qwen3_codec.npz")
+    cfg = mg.qwen3_codec_config()
+    W = oc.init_weights(cfg, 5)
+    codes = np.random.default_rng(1).integers(0, cfg.codebook_size, (2, cfg.num_quantizers, 20))
+    d = oc.SpeechTokenizerDecoder(cfg, W)
+    full = d(codes)[:, 0].numpy()
+    assert tuple(g["shape"]) == full.shape and np.abs(full[:, :64] - g["full_first"]).max() < 1e-6 and np.abs(full[:, -64:] - g["full_last"]).max() < 1e-6
+    assert np.allclose(mg.stats(full), g["full_stats"], rtol=1e-6, atol=1e-9)
+    d.reset_streaming_state()
+    st = np.concatenate([d.streaming_step(codes[:, :, a:b])[:, 0].numpy() for a, b in ((0, 7), (7, 8), (8, 20))], axis=-1)
+    up = cfg.total_upsample
+    assert np.abs(st[:, 7 * up - 32: 8 * up + 32] - g["stream_boundary"]).max() < 1e-6
+    assert np.abs(st - full).max() > 1e-4                          # the chunked stream is NOT the one-shot decode (bias counted twice)
