@@ -121,6 +121,26 @@ def kv_bytes(cfg, batch, ctx) -> int:
 
 
 # ------------------------------------------------------------------------------------------------- CPU legs
+def usable_cpus() -> int:
+    """Hardware threads this process may really run on: the scheduler affinity mask capped by the cgroup CPU quota.
+    (os.cpu_count() reports the HOST's count; inside a quota-limited container, asking torch for that many threads
+    oversubscribes the cores it actually has and slows the CPU arm down many times over.)"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:                                                     # cgroup v2: "max 100000" or "<quota> <period>"
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            n = min(n, max(1, int(float(q) / float(per) + 0.999)))
+    except (OSError, ValueError):
+        try:                                                 # cgroup v1
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0 and per > 0:
+                n = min(n, max(1, (q + per - 1) // per))
+        except (OSError, ValueError):
+            pass
+    return max(1, n)
+
+
 class CpuReference:
     """The reference path restated on the CPU (oracle/, kind "port"), as a BOUNDED sample per call.
     Weights (full width, 4 layers + the tied embedding) are built once.  One sample times: the prefill on a 16-token prompt
@@ -131,11 +151,14 @@ class CpuReference:
     PREFILL_TOKENS, SNAC_DIV = 16, 4
 
     def __init__(self, cfg, threads: int):
+        """threads = the most the process may use (usable_cpus()); the count actually used is the fastest of a short calibration
+        over {threads, threads/2, threads/4, ...} on the decode step (see calibrate) and is what `cores` reports."""
         import torch
         from oracle import llama as ol
         from oracle import snac as osn
         torch.set_num_threads(threads)
         self.cfg, self.threads, self.ol, self.osn, self.torch = cfg, threads, ol, osn, torch
+        self.max_threads, self.calibration = threads, ""
         g = torch.Generator().manual_seed(0)
         H, I, hd = cfg["hidden_size"], cfg["intermediate_size"], cfg["head_dim"]
         nq, nkv, V = cfg["num_attention_heads"], cfg["num_key_value_heads"], cfg["vocab_size"]
@@ -158,6 +181,34 @@ class CpuReference:
         self.W = W
         self.scfg = osn.SNACConfig()
         self.SW = osn.init_weights(self.scfg, 1234)
+        self.calibrate()
+
+    def calibrate(self):
+        """Pick the thread count that makes the CPU arm FASTEST: the decode step (the dominant term, 512 of them) of the 2-layer
+        model is timed at max, max/2, max/4, ... threads (down to 4) and the best count is kept for everything."""
+        torch = self.torch
+        cands, n = [], self.max_threads
+        while n >= 4:
+            cands.append(n)
+            n //= 2
+        if not cands:
+            cands = [self.max_threads]
+        mo = self.ol.LlamaOracle(self._build(2), self.W, round_acts=True)
+        ids = torch.as_tensor(make_prompts(0)[:, :2], dtype=torch.long)
+        nxt = mo.forward(ids)[:, -1].argmax(-1, keepdim=True)
+        best, seen = None, []
+        for c in cands:
+            torch.set_num_threads(c)
+            mo.forward(nxt)                                   # settle the pool at this size
+            t0 = time.perf_counter()
+            mo.forward(nxt)
+            dt = time.perf_counter() - t0
+            seen.append(f"{c}: {dt * 1e3:.0f}ms")
+            if best is None or dt < best[1]:
+                best = (c, dt)
+        self.threads = best[0]
+        torch.set_num_threads(self.threads)
+        self.calibration = f"thread count chosen by timing one 2-layer decode step at {{{', '.join(seen)}}} of {self.max_threads} usable"
 
     def _build(self, nl):
         c = self.cfg
@@ -199,7 +250,7 @@ class CpuReference:
         osn.DTYPE = torch.float64
         total = t_prefill + GEN_TOKENS * t_step + BATCH * t_snac1
         audio = BATCH * audio_seconds_per_utterance(PROMPT_LEN, GEN_TOKENS)
-        desc = (f"oracle port (torch-CPU fp32 math on bf16-valued weights, {self.threads} threads): full-width 2- and 4-layer models timed "
+        desc = (f"oracle port (torch-CPU fp32 math on bf16-valued weights, {self.threads} threads, {self.calibration}): full-width 2- and 4-layer models timed "
                 f"(prefill of {self.PREFILL_TOKENS} of {PROMPT_LEN} prompt tokens x batch {BATCH}: {res[4][0]:.2f}s scaled / decode step "
                 f"{res[4][1]*1e3:.0f}ms at 4 layers), per-layer + lm-head cost extrapolated linearly to {L_full} layers x "
                 f"({PROMPT_LEN}-token prefill + {GEN_TOKENS} steps); SNAC decode timed on {fsub} of {frames} frames of 1 of {BATCH} "
@@ -208,14 +259,16 @@ class CpuReference:
 
 
 def cpu_reference_sample(cfg, threads: int):
-    return CpuReference(cfg, threads).sample()
+    """-> (RTFx, total seconds, description, threads actually used)."""
+    ref = CpuReference(cfg, threads)
+    return (*ref.sample(), ref.threads)
 
 
 def run_reference_arm(args, rank: int, world: int):
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    ref = CpuReference(ORPHEUS, threads)          # weights built once; every step is one bounded sample (see CpuReference)
+    ref = CpuReference(ORPHEUS, usable_cpus())    # weights built once; every step is one bounded sample (see CpuReference)
+    threads = ref.threads                          # the calibrated count (the fastest for this arm), reported as `cores`
     vals, totals, sample = [], [], ""
     for i in range(args.warmup + args.steps):
         v, tot, sample = ref.sample(light=i < args.warmup)     # warm-up samples: threads / allocator only (one decode step)
@@ -356,8 +409,7 @@ def main():
         "clocks": clocks,
     }
     if not args.no_cpu_baseline and world == 1 and not args.tiny:
-        threads = os.cpu_count() or 1
-        v, tot, sample = cpu_reference_sample(cfg, threads)
+        v, tot, sample, threads = cpu_reference_sample(cfg, usable_cpus())
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
     print(json.dumps(line), flush=True)
     if dist is not None:

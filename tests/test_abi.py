@@ -70,3 +70,13 @@ def test_product_path_never_imports_oracle():
     for f in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")):
         txt = f.read_text()
         assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_bench_cpu_arm_thread_budget():
+    """bench.py's CPU legs size their thread pool from what the process may really use, not from the host's CPU count."""
+    import os
+    import sys
+    sys.path.insert(0, str(ROOT))
+    import bench
+    n = bench.usable_cpus()
+    assert 1 <= n <= (os.cpu_count() or 1) and n <= len(os.sched_getaffinity(0))
