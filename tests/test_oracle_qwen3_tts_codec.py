@@ -1,6 +1,5 @@
 """Oracle for the Qwen3-TTS speech-tokenizer decoder (row N1, oracle only): building blocks pinned against the identically
 structured ``transformers`` Qwen3-Omni Code2Wav modules and torch conv primitives; streaming == full decode.  CPU only."""
-import math
 
 import numpy as np
 import pytest

@@ -12,7 +12,6 @@ import math
 
 import numpy as np
 import pytest
-import torch
 
 from implicit_conv_model import implicit_conv
 from oracle import qwen3_tts_codec as oc
