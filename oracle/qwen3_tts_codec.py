@@ -93,6 +93,17 @@ def tiny_config(**kw) -> TokenizerDecoderConfig:
     return TokenizerDecoderConfig(**base)
 
 
+def mid_config(**kw) -> TokenizerDecoderConfig:
+    """The geometry of the (gated) GPU tests and of tests/golden/qwen3_codec.npz: every structural feature of the shipped model,
+    every channel count >= 64 (one 64-channel TMA box never exceeds a tensor) with 96 as the non-multiple-of-64 case, and small
+    enough for the float64 oracle to decode ~70 code frames in seconds."""
+    base = dict(latent_dim=128, codebook_dim=128, codebook_size=64, decoder_dim=768, hidden_size=64, intermediate_size=128, head_dim=32,
+                num_attention_heads=4, num_key_value_heads=2, num_hidden_layers=2, num_quantizers=4, num_semantic_quantizers=1,
+                upsample_rates=[4, 3, 2], upsampling_ratios=[2, 2], layer_scale_initial_scale=0.3)
+    base.update(kw)
+    return TokenizerDecoderConfig(**base)
+
+
 # ---------------------------------------------------------------- weights
 
 def init_weights(cfg: TokenizerDecoderConfig, seed: int = 1234, std: float = 0.08, out_gain: float = 0.02) -> Dict[str, torch.Tensor]:

@@ -107,8 +107,7 @@ def codecs_small():
 
 def qwen3_codec_config():
     """The mid-size geometry the (gated) GPU tests of row N1 use."""
-    return oq.tiny_config(latent_dim=128, codebook_dim=128, codebook_size=64, decoder_dim=256, hidden_size=64, intermediate_size=128, head_dim=32,
-                          num_attention_heads=4, num_key_value_heads=2)
+    return oq.mid_config()
 
 
 def qwen3_codec():

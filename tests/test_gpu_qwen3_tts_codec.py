@@ -15,13 +15,7 @@ pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("B2A_EXPERIMENT
 TOL = 1e-3
 
 
-def mid_config(**kw):
-    """Every structural feature of the shipped geometry at a size the float64 oracle decodes in seconds."""
-    base = dict(latent_dim=128, codebook_dim=128, codebook_size=64, decoder_dim=256, hidden_size=64, intermediate_size=128, head_dim=32,
-                num_attention_heads=4, num_key_value_heads=2, num_hidden_layers=2, num_quantizers=4, num_semantic_quantizers=1,
-                upsample_rates=[4, 3, 2, 2], upsampling_ratios=[2, 2], layer_scale_initial_scale=0.3)
-    base.update(kw)
-    return oc.TokenizerDecoderConfig(**base)
+mid_config = oc.mid_config
 
 
 def make(b2a_codec, cfg, W, **kw):
@@ -109,7 +103,7 @@ def test_from_model_directory(codec, tmp_path):
     from test_qwen3_tts_codec_host import torch_layout_checkpoint
     # every k = 1 conv needs > 64 input channels here: the reference's layout heuristic (checkArrayShapeQwen3) reads a PyTorch
     # [out, <= 64, 1] weight as "already MLX" and would leave it untransposed (true of the reference itself, not only of this port)
-    cfg = mid_config(codebook_dim=144, decoder_dim=288, upsample_rates=[4, 3])
+    cfg = mid_config(codebook_dim=144, decoder_dim=576, upsample_rates=[4, 3])
     W = oc.init_weights(cfg, 12)
     d = tmp_path / "speech_tokenizer"
     d.mkdir()
