@@ -272,6 +272,10 @@ int32_t b2a_weights_count(const b2a_weights* w);
 int32_t b2a_weights_get(const b2a_weights* w, int32_t index, b2a_tensor* out);
 int32_t b2a_weights_sanitize_whisper(b2a_weights* w, int32_t* format);
 int32_t b2a_weights_sanitize_llama(b2a_weights* w, int32_t tie_word_embeddings, int32_t group_size, int32_t bits);
+/* Same, with the quantisation read from config.json the way the reference's loader does (LlamaTTS.swift:955-966 through
+ * mlx-swift-lm's PerLayerQuantization): "quantization": {"group_size", "bits", "<layer path>": false | {"group_size", "bits"}} --
+ * per-layer settings override the default, a layer marked false must not carry .scales.  b2a_tts_create_from_directory uses this. */
+int32_t b2a_weights_sanitize_llama_config(b2a_weights* w, const char* config_path);
 void b2a_weights_free(b2a_weights* w);
 int32_t b2a_tts_config_from_json(const char* config_path, int32_t max_batch, int32_t max_context, b2a_llama_config* cfg,
                                  int32_t* quant_group_size, int32_t* quant_bits);

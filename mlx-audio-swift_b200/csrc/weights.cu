@@ -157,6 +157,38 @@ static uint16_t float_to_bf16(float f) {     // round to nearest even (what __fl
     return (uint16_t)(u >> 16);
 }
 
+// The "quantization" object of config.json as mlx-swift-lm's BaseConfiguration.PerLayerQuantization reads it (un-vendored; call
+// sites LlamaTTSConfig.swift:137-139, LlamaTTS.swift:955-966): group_size / bits are the default, every other key is a layer path
+// whose value is either `false` (that layer is not quantised) or its own {group_size, bits}.
+struct QuantSpec {
+    int group_size = 0, bits = 0;
+    std::map<std::string, std::pair<int, int>> per_layer;
+    std::vector<std::string> off;
+    bool any() const { return bits > 0 || !per_layer.empty(); }
+    // 1 = quantised with (gs, b); 0 = no setting for this layer
+    int lookup(const std::string& path, int& gs, int& b) const {
+        for (auto& o : off) if (o == path) return 0;
+        auto it = per_layer.find(path);
+        if (it != per_layer.end()) { gs = it->second.first; b = it->second.second; return 1; }
+        if (bits > 0) { gs = group_size; b = bits; return 1; }
+        return 0;
+    }
+};
+static QuantSpec parse_quant(const Json& cfg) {
+    QuantSpec q;
+    const Json* j = cfg.find("quantization");
+    if (!j || j->kind != Json::Obj) return q;
+    q.group_size = (int)j->number("group_size", 64);
+    q.bits = (int)j->number("bits", 4);
+    for (auto& kv : j->obj) {
+        if (kv.first == "group_size" || kv.first == "bits" || kv.first == "mode") continue;
+        if (kv.second.kind == Json::Bool && !kv.second.b) q.off.push_back(kv.first);
+        else if (kv.second.kind == Json::Obj)
+            q.per_layer[kv.first] = {(int)kv.second.number("group_size", q.group_size), (int)kv.second.number("bits", q.bits)};
+    }
+    return q;
+}
+
 }  // namespace b2a
 
 using namespace b2a;
@@ -366,6 +398,11 @@ struct b2a_weights {
 
     // ---- Llama / Orpheus (LlamaTTS.swift:583-593 sanitize, :955-966 quantize)
     void sanitize_llama(bool tie, int group_size, int bits) {
+        QuantSpec q;
+        q.group_size = group_size; q.bits = bits;
+        sanitize_llama(tie, q);
+    }
+    void sanitize_llama(bool tie, const QuantSpec& spec) {
         std::vector<WItem> out;
         for (auto& it : items) {
             if (it.name.find("self_attn.rotary_emb.inv_freq") != std::string::npos) continue;
@@ -373,9 +410,7 @@ struct b2a_weights {
             out.push_back(it);
         }
         items = std::move(out);
-        if (bits <= 0) return;
-        B2A_CHECK(bits == 2 || bits == 4 || bits == 8, B2A_ERR_INVALID_INPUT, "MLX affine quantisation: bits must be 2, 4 or 8");
-        B2A_CHECK(group_size > 0 && group_size % (32 / bits) == 0, B2A_ERR_INVALID_INPUT, "MLX affine quantisation: bad group_size");
+        if (!spec.any()) return;
         // every "<path>.scales" marks a quantised layer (the reference tests weights["\(path).scales"], :958-962)
         std::vector<std::string> paths;
         for (auto& it : items) {
@@ -383,6 +418,10 @@ struct b2a_weights {
             if (n > 7 && it.name.substr(n - 7) == ".scales") paths.push_back(it.name.substr(0, n - 7));
         }
         for (auto& p : paths) {
+            int group_size = 0, bits = 0;
+            B2A_CHECK(spec.lookup(p, group_size, bits) == 1, B2A_ERR_MODEL_NOT_INITIALIZED, "quantised tensors for a layer the config does not quantise: " + p);
+            B2A_CHECK(bits == 2 || bits == 4 || bits == 8, B2A_ERR_INVALID_INPUT, "MLX affine quantisation: bits must be 2, 4 or 8");
+            B2A_CHECK(group_size > 0 && group_size % (32 / bits) == 0, B2A_ERR_INVALID_INPUT, "MLX affine quantisation: bad group_size");
             const int iw = find(p + ".weight"), is = find(p + ".scales"), ib = find(p + ".biases");
             B2A_CHECK(iw >= 0 && is >= 0 && ib >= 0, B2A_ERR_MODEL_NOT_INITIALIZED, "incomplete quantised layer: " + p);
             const WItem& w = items[iw];
@@ -407,7 +446,6 @@ struct b2a_weights {
             erase(p + ".scales"); erase(p + ".biases");
         }
     }
-
 
     // ---- Qwen3-TTS speech tokenizer, decoder half of Qwen3TTSSpeechTokenizer.sanitize (Qwen3TTSSpeechTokenizer.swift:1094-1440).
     // Output: the keys b2a_speech_tokenizer_create takes (below the "decoder." module) in MLX layouts.  encoder.* (voice-cloning
@@ -546,6 +584,15 @@ int32_t b2a_weights_sanitize_whisper(b2a_weights* w, int32_t* format) {
         if (format) *format = f;
     });
 }
+// sanitize + de-quantise as config.json says, per-layer overrides included ("quantization": {group_size, bits, "<layer path>": false | {..}})
+int32_t b2a_weights_sanitize_llama_config(b2a_weights* w, const char* config_path) {
+    return guarded([&] {
+        B2A_CHECK(w && config_path, B2A_ERR_INVALID_INPUT, "b2a_weights_sanitize_llama_config: null argument");
+        const Json j = read_json_file(config_path);
+        B2A_CHECK(j.kind == Json::Obj, B2A_ERR_MODEL_NOT_INITIALIZED, "config.json is not an object");
+        w->sanitize_llama(j.number("tie_word_embeddings", 1) != 0, parse_quant(j));
+    });
+}
 int32_t b2a_weights_sanitize_llama(b2a_weights* w, int32_t tie_word_embeddings, int32_t group_size, int32_t bits) {
     return guarded([&] {
         B2A_CHECK(w, B2A_ERR_INVALID_INPUT, "b2a_weights_sanitize_llama: null handle");
@@ -602,7 +649,7 @@ int32_t b2a_tts_create_from_directory(const char* model_dir, int32_t device, int
         if (st != B2A_OK) throw Error(st, b2a_last_error());
         std::unique_ptr<b2a_weights> w(new b2a_weights());
         w->load(dir);
-        w->sanitize_llama(cfg.tie_word_embeddings != 0, gs, bits);
+        w->sanitize_llama(cfg.tie_word_embeddings != 0, parse_quant(read_json_file(dir + "/config.json")));
         const std::vector<b2a_tensor> tab = w->table();
         st = b2a_tts_create(device, &cfg, tab.data(), (int32_t)tab.size(), snac, out);
         if (st != B2A_OK) throw Error(st, b2a_last_error());

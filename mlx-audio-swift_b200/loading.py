@@ -34,6 +34,10 @@ class Weights:
         """LlamaTTSModel.sanitize (LlamaTTS.swift:583-593) + MLX affine de-quantisation to bf16 when bits > 0."""
         _ffi.check(_ffi.lib().b2a_weights_sanitize_llama(self._h, int(tie_word_embeddings), group_size, bits))
 
+    def sanitize_llama_config(self, config_path: Union[str, Path]) -> None:
+        """sanitize + de-quantisation driven by config.json, per-layer "quantization" overrides included (LlamaTTS.swift:955-966)."""
+        _ffi.check(_ffi.lib().b2a_weights_sanitize_llama_config(self._h, str(config_path).encode()))
+
     def sanitize_speech_tokenizer(self) -> None:
         """Decoder half of Qwen3TTSSpeechTokenizer.sanitize (Qwen3TTSSpeechTokenizer.swift:1094-1440); keys end up relative to the decoder."""
         _ffi.check(_ffi.lib().b2a_weights_sanitize_speech_tokenizer(self._h))

@@ -137,6 +137,42 @@ def test_llama_sanitize_and_mlx_affine_dequant(b2a, tmp_path, bits, group_size):
         b2a.Weights(tmp_path).sanitize_llama(True, 64, 3)
 
 
+def test_llama_per_layer_quantization_from_config(b2a, tmp_path):
+    """config.json "quantization" with per-layer overrides (mlx-swift-lm PerLayerQuantization, call site LlamaTTS.swift:955-966):
+    the default 4-bit / 64, one layer at 8-bit / 32, one layer marked false."""
+    rng = np.random.default_rng(11)
+    a, b, c = (rng.standard_normal((16, 128)).astype(np.float32) for _ in range(3))
+    wa, sa, ba, qa = mlx_affine_quantize(a, 64, 4)
+    wb, sb, bb, qb = mlx_affine_quantize(b, 32, 8)
+    tensors = {"model.layers.0.mlp.down_proj.weight": wa.view(np.int32), "model.layers.0.mlp.down_proj.scales": sa, "model.layers.0.mlp.down_proj.biases": ba,
+               "model.embed_tokens.weight": wb.view(np.int32), "model.embed_tokens.scales": sb, "model.embed_tokens.biases": bb,
+               "model.layers.0.mlp.up_proj.weight": c, "lm_head.weight": np.ones((2, 2), np.float32)}
+    save_file(tensors, str(tmp_path / "model.safetensors"))
+    cfg = {"tie_word_embeddings": True, "quantization": {"group_size": 64, "bits": 4, "model.embed_tokens": {"group_size": 32, "bits": 8},
+                                                          "model.layers.0.mlp.up_proj": False}}
+    (tmp_path / "config.json").write_text(json.dumps(cfg))
+    w = b2a.Weights(tmp_path)
+    w.sanitize_llama_config(tmp_path / "config.json")
+    t = w.tensors()
+    assert set(t) == {"model.layers.0.mlp.down_proj.weight", "model.embed_tokens.weight", "model.layers.0.mlp.up_proj.weight"}
+    ref_a = (np.repeat(sa, 64, axis=1) * qa + np.repeat(ba, 64, axis=1)).astype(np.float32)
+    ref_b = (np.repeat(sb, 32, axis=1) * qb + np.repeat(bb, 32, axis=1)).astype(np.float32)
+    assert torch.equal(t["model.layers.0.mlp.down_proj.weight"], torch.from_numpy(ref_a).to(torch.bfloat16))
+    assert torch.equal(t["model.embed_tokens.weight"], torch.from_numpy(ref_b).to(torch.bfloat16))
+    assert np.array_equal(t["model.layers.0.mlp.up_proj.weight"], c)                      # untouched fp32
+    # a layer the config marks unquantised must not carry scales
+    cfg["quantization"]["model.layers.0.mlp.down_proj"] = False
+    (tmp_path / "config.json").write_text(json.dumps(cfg))
+    with pytest.raises(b2a.AudioGenerationError) as e:
+        b2a.Weights(tmp_path).sanitize_llama_config(tmp_path / "config.json")
+    assert e.value.case == "modelNotInitialized"
+    # no "quantization" at all: tensors pass through (the tied lm_head is still dropped)
+    (tmp_path / "config.json").write_text(json.dumps({"tie_word_embeddings": True}))
+    w3 = b2a.Weights(tmp_path)
+    w3.sanitize_llama_config(tmp_path / "config.json")
+    assert "model.embed_tokens.scales" in w3.tensors() and "lm_head.weight" not in w3.tensors()
+
+
 def test_llama_config_from_json(b2a, tmp_path):
     cfg = {"hidden_size": 3072, "num_hidden_layers": 28, "intermediate_size": 8192, "num_attention_heads": 24, "num_key_value_heads": 8,
            "rms_norm_eps": 1e-5, "vocab_size": 156940, "rope_theta": 500000.0, "tie_word_embeddings": True, "model_type": "llama",
