@@ -64,6 +64,11 @@ int64_t b2a_launch_count(void);
 int32_t b2a_hanning_window(int32_t size, int32_t periodic, float* out);
 int32_t b2a_mel_filters(int32_t sample_rate, int32_t n_fft, int32_t n_mels, float f_min, float f_max,
                         int32_t norm_slaney, int32_t mel_scale, float* out);
+/* The other two host helpers of DSP.swift, off the mel path but with known answers in the reference's tests
+ * (Tests/MLXAudioCodecsTests.swift:117-140): hammingWindow (:25-42; periodic != 0 is the default) and powerToDB (:61-73;
+ * top_db < 0 means no dynamic-range clipping).                                                                    */
+int32_t b2a_hamming_window(int32_t size, int32_t periodic, float* out);
+int32_t b2a_power_to_db(const float* spectrogram, int64_t n, float amin, float top_db, float* out);
 
 /* ------------------------------------------------------------------ streaming log-mel
  * Replaces class IncrementalMelSpectrogram

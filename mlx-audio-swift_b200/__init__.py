@@ -4,7 +4,8 @@ Everything numeric runs in `lib/libb200audio.so` (hand-written CUDA, C ABI in in
 this package is the host-side mirror of the reference interface for that path.  No CPU fallback."""
 from . import _ffi
 from ._ffi import AudioGenerationError
-from .dsp import IncrementalMelSpectrogram, LogMel, compute_mel_spectrogram, hanning_window, mel_filters, whisper_encoder_features
+from .dsp import (IncrementalMelSpectrogram, LogMel, compute_mel_spectrogram, hamming_window, hanning_window, mel_filters, power_to_db,
+                  whisper_encoder_features)
 from .snac import SNAC
 from .llama_tts import AudioGenerationInfo, GenerateParameters, LlamaTTSModel
 from .vocos import Vocos
@@ -13,7 +14,7 @@ from .loading import Weights, llama_config_from_json
 from .whisper import STTGenerateParameters, STTOutput, WhisperModel
 from .streaming import StreamingConfig, StreamingEncoder, StreamingFrontEnd
 
-__all__ = ["AudioGenerationError", "IncrementalMelSpectrogram", "LogMel", "compute_mel_spectrogram", "hanning_window",
+__all__ = ["AudioGenerationError", "IncrementalMelSpectrogram", "LogMel", "compute_mel_spectrogram", "hanning_window", "hamming_window", "power_to_db",
            "mel_filters", "whisper_encoder_features", "SNAC", "LlamaTTSModel", "GenerateParameters",
            "AudioGenerationInfo", "Vocos", "Weights", "llama_config_from_json", "Encodec", "EncodecConfig", "EncodecEncodedAudio", "WhisperModel", "STTGenerateParameters", "STTOutput",
            "StreamingConfig", "StreamingEncoder", "StreamingFrontEnd"]

@@ -112,6 +112,8 @@ SIGNATURES = {
     "b2a_device_count": (C.c_int32, []),
     "b2a_launch_count": (C.c_int64, []),
     "b2a_hanning_window": (C.c_int32, [C.c_int32, C.c_int32, _P]),
+    "b2a_hamming_window": (C.c_int32, [C.c_int32, C.c_int32, _P]),
+    "b2a_power_to_db": (C.c_int32, [_P, C.c_int64, C.c_float, C.c_float, _P]),
     "b2a_mel_filters": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_int32, _P]),
     "b2a_mel_create": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P)]),
     "b2a_mel_max_frames": (C.c_int64, [_P, C.c_int64]),

@@ -721,4 +721,27 @@ int32_t b2a_speech_tokenizer_create_from_directory(const char* dir, int32_t devi
     });
 }
 
+// ---- the other two host helpers of DSP.swift (not on the mel path; the reference's own tests hold known answers for them)
+// hammingWindow (Sources/MLXAudioCore/DSP.swift:25-42): periodic = the first `size` points of the (size + 1)-point window
+int32_t b2a_hamming_window(int32_t size, int32_t periodic, float* out) {
+    return guarded([&] {
+        B2A_CHECK(size >= 0 && (out || size == 0), B2A_ERR_INVALID_INPUT, "b2a_hamming_window: bad arguments");
+        if (size == 0) return;
+        if (size == 1) { out[0] = 1.0f; return; }
+        const int eff = periodic ? size + 1 : size;
+        const float denom = (float)(eff - 1);
+        for (int n = 0; n < size; ++n) out[n] = 0.54f - 0.46f * cosf(2.0f * (float)M_PI * (float)n / denom);
+    });
+}
+// powerToDB (DSP.swift:61-73): 10 log10(max(x, amin)), then max(., global max - top_db) when top_db >= 0
+int32_t b2a_power_to_db(const float* spectrogram, int64_t n, float amin, float top_db, float* out) {
+    return guarded([&] {
+        B2A_CHECK(n >= 0 && (n == 0 || (spectrogram && out)), B2A_ERR_INVALID_INPUT, "b2a_power_to_db: bad arguments");
+        float mx = -INFINITY;
+        for (int64_t i = 0; i < n; ++i) { out[i] = 10.0f * log10f(std::max(spectrogram[i], amin)); mx = std::max(mx, out[i]); }
+        if (top_db >= 0.f)
+            for (int64_t i = 0; i < n; ++i) out[i] = std::max(out[i], mx - top_db);
+    });
+}
+
 }  // extern "C"

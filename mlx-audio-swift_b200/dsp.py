@@ -21,6 +21,21 @@ def hanning_window(size: int, periodic: bool = False) -> np.ndarray:
     return out
 
 
+def hamming_window(size: int, periodic: bool = True) -> np.ndarray:
+    """hammingWindow(size:periodic:) (Sources/MLXAudioCore/DSP.swift:25-42)."""
+    out = np.empty(max(size, 0), dtype=np.float32)
+    _ffi.check(_ffi.lib().b2a_hamming_window(size, int(periodic), _ffi.ptr(out) if size > 0 else None))
+    return out
+
+
+def power_to_db(spectrogram, amin: float = 1e-10, top_db: Optional[float] = None) -> np.ndarray:
+    """powerToDB(_:amin:topDB:) (DSP.swift:61-73)."""
+    x = np.ascontiguousarray(spectrogram, dtype=np.float32)
+    out = np.empty_like(x)
+    _ffi.check(_ffi.lib().b2a_power_to_db(_ffi.ptr(x), x.size, amin, -1.0 if top_db is None else float(top_db), _ffi.ptr(out)))
+    return out
+
+
 def mel_filters(sample_rate: int, n_fft: int, n_mels: int, f_min: float = 0.0, f_max: Optional[float] = None,
                 norm: Optional[str] = "slaney", mel_scale: str = "htk") -> np.ndarray:
     out = np.empty((n_fft // 2 + 1, n_mels), dtype=np.float32)

@@ -29,6 +29,22 @@ def hanning_window(size: int) -> np.ndarray:
     return (f32(0.5) * (f32(1) - np.cos(f32(2) * f32(np.pi) * n / denom, dtype=f32))).astype(f32)
 
 
+def hamming_window(size: int, periodic: bool = True) -> np.ndarray:
+    """DSP.swift:25-42 -- periodic = the first ``size`` points of the (size + 1)-point window."""
+    if size <= 0:
+        return np.zeros(0)
+    if size == 1:
+        return np.ones(1)
+    eff = size + 1 if periodic else size
+    return (0.54 - 0.46 * np.cos(2.0 * np.pi * np.arange(eff) / (eff - 1)))[:size]
+
+
+def power_to_db(spectrogram, amin: float = 1e-10, top_db=None) -> np.ndarray:
+    """DSP.swift:61-73."""
+    db = 10.0 * np.log10(np.maximum(np.asarray(spectrogram, dtype=np.float64), amin))
+    return db if top_db is None else np.maximum(db, db.max() - top_db)
+
+
 def periodic_hann_window(size: int) -> np.ndarray:
     """WhisperAudio.swift:42-43 -- periodic Hann, 0.5*(1-cos(2*pi*n/N))."""
     n = np.arange(size, dtype=f32)

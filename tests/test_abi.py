@@ -31,6 +31,23 @@ def test_host_tables_match_oracle(b2a):
         assert np.array_equal(a != 0, o != 0) or np.abs(a - o)[(a != 0) != (o != 0)].max() < 1e-7
 
 
+def test_reference_known_answers_for_hamming_and_power_to_db(b2a):
+    """Tests/MLXAudioCodecsTests.swift:117-140 (SharedDSPTests), on the oracle and on the library's host helpers."""
+    for hw, pdb in ((dsp.hamming_window, dsp.power_to_db), (b2a.hamming_window, b2a.power_to_db)):
+        periodic, symmetric = hw(4), hw(4, periodic=False)
+        assert len(periodic) == 4 and len(symmetric) == 4
+        assert abs(periodic[0] - 0.08) < 1e-3 and abs(periodic[1] - 0.54) < 1e-3 and abs(periodic[3] - 0.54) < 1e-3
+        assert abs(symmetric[0] - 0.08) < 1e-3 and abs(symmetric[3] - 0.08) < 1e-3 and abs(symmetric[1] - symmetric[2]) < 1e-3
+        clipped = pdb(np.array([1e-10, 1e-5, 1.0], np.float32), top_db=80)
+        assert abs(clipped[0] + 80) < 1e-2 and abs(clipped[1] + 50) < 1e-2 and abs(clipped[2]) < 1e-3
+        assert len(hw(0)) == 0 and list(hw(1)) == [1.0]                             # the guard branches (:26-27)
+    for n, per in ((400, True), (400, False), (7, True)):
+        assert np.abs(b2a.hamming_window(n, per) - dsp.hamming_window(n, per)).max() < 5e-7          # float32 phase, as the reference computes it
+    x = np.random.default_rng(0).random(1000).astype(np.float32) ** 8
+    assert np.abs(b2a.power_to_db(x, top_db=30) - dsp.power_to_db(x, top_db=30)).max() < 1e-4
+    assert np.abs(b2a.power_to_db(x) - dsp.power_to_db(x)).max() < 1e-4
+
+
 def test_token_plumbing_matches_oracle(b2a):
     M = b2a.LlamaTTSModel
     prompts = [[1, 2, 3], [9], [4, 5, 6, 7, 8]]
