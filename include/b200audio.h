@@ -281,6 +281,11 @@ int32_t b2a_weights_sanitize_llama(b2a_weights* w, int32_t tie_word_embeddings, 
  * mlx-swift-lm's PerLayerQuantization): "quantization": {"group_size", "bits", "<layer path>": false | {"group_size", "bits"}} --
  * per-layer settings override the default, a layer marked false must not carry .scales.  b2a_tts_create_from_directory uses this. */
 int32_t b2a_weights_sanitize_llama_config(b2a_weights* w, const char* config_path);
+/* MLX affine de-quantisation (to bf16) of every layer that carries "<path>.scales", with one group_size / bits -- what
+ * WhisperModel.fromDirectory's quantize(model:groupSize:bits:) implies for a quantised checkpoint (WhisperModel.swift:499-511:
+ * every Linear and decoder.embed_tokens; the tied projection then multiplies by the de-quantised embedding,
+ * Tests/WhisperQuantizedTiedEmbeddingTests.swift).  Call after b2a_weights_sanitize_whisper.                              */
+int32_t b2a_weights_dequantize(b2a_weights* w, int32_t group_size, int32_t bits);
 void b2a_weights_free(b2a_weights* w);
 int32_t b2a_tts_config_from_json(const char* config_path, int32_t max_batch, int32_t max_context, b2a_llama_config* cfg,
                                  int32_t* quant_group_size, int32_t* quant_bits);

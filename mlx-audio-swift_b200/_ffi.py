@@ -184,6 +184,7 @@ SIGNATURES = {
     "b2a_weights_sanitize_whisper": (C.c_int32, [_P, C.POINTER(C.c_int32)]),
     "b2a_weights_sanitize_llama": (C.c_int32, [_P, C.c_int32, C.c_int32, C.c_int32]),
     "b2a_weights_sanitize_llama_config": (C.c_int32, [_P, C.c_char_p]),
+    "b2a_weights_dequantize": (C.c_int32, [_P, C.c_int32, C.c_int32]),
     "b2a_weights_free": (None, [_P]),
     "b2a_tts_config_from_json": (C.c_int32, [C.c_char_p, C.c_int32, C.c_int32, C.POINTER(LlamaConfig), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "b2a_tts_create_from_directory": (C.c_int32, [C.c_char_p, C.c_int32, C.c_int32, C.c_int32, _P, C.POINTER(_P)]),

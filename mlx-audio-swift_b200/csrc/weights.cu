@@ -410,8 +410,13 @@ struct b2a_weights {
             out.push_back(it);
         }
         items = std::move(out);
+        dequantize_layers(spec);
+    }
+    // MLX affine de-quantisation of every layer that carries "<path>.scales" (the reference tests weights["\(path).scales"],
+    // LlamaTTS.swift:958-962; Whisper quantises every Linear and decoder.embed_tokens, WhisperModel.swift:499-511): w = scales * q + biases,
+    // value j of a uint32 word at bits [j * bits, (j + 1) * bits), result stored as bf16.
+    void dequantize_layers(const QuantSpec& spec) {
         if (!spec.any()) return;
-        // every "<path>.scales" marks a quantised layer (the reference tests weights["\(path).scales"], :958-962)
         std::vector<std::string> paths;
         for (auto& it : items) {
             const size_t n = it.name.size();
@@ -582,6 +587,14 @@ int32_t b2a_weights_sanitize_whisper(b2a_weights* w, int32_t* format) {
         B2A_CHECK(w, B2A_ERR_INVALID_INPUT, "b2a_weights_sanitize_whisper: null handle");
         const int f = w->sanitize_whisper();
         if (format) *format = f;
+    });
+}
+int32_t b2a_weights_dequantize(b2a_weights* w, int32_t group_size, int32_t bits) {
+    return guarded([&] {
+        B2A_CHECK(w && bits > 0, B2A_ERR_INVALID_INPUT, "b2a_weights_dequantize: null handle or bits <= 0");
+        QuantSpec q;
+        q.group_size = group_size; q.bits = bits;
+        w->dequantize_layers(q);
     });
 }
 // sanitize + de-quantise as config.json says, per-layer overrides included ("quantization": {group_size, bits, "<layer path>": false | {..}})

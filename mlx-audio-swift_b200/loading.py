@@ -38,6 +38,10 @@ class Weights:
         """sanitize + de-quantisation driven by config.json, per-layer "quantization" overrides included (LlamaTTS.swift:955-966)."""
         _ffi.check(_ffi.lib().b2a_weights_sanitize_llama_config(self._h, str(config_path).encode()))
 
+    def dequantize(self, group_size: int, bits: int) -> None:
+        """MLX affine de-quantisation (to bf16) of every layer with "<path>.scales" (quantised Whisper checkpoints, WhisperModel.swift:499-511)."""
+        _ffi.check(_ffi.lib().b2a_weights_dequantize(self._h, group_size, bits))
+
     def sanitize_speech_tokenizer(self) -> None:
         """Decoder half of Qwen3TTSSpeechTokenizer.sanitize (Qwen3TTSSpeechTokenizer.swift:1094-1440); keys end up relative to the decoder."""
         _ffi.check(_ffi.lib().b2a_weights_sanitize_speech_tokenizer(self._h))

@@ -92,6 +92,7 @@ class WhisperModel:
         from pathlib import Path
         from .loading import Weights
         config = json.loads((Path(model_dir) / "config.json").read_text())
+        quant = config.get("quantization")         # quantised checkpoints: every Linear + decoder.embed_tokens (WhisperModel.swift:499-511)
         if "n_audio_state" in config:            # mlx-whisper / OpenAI dims (WhisperConfig.swift:94-131 accepts both spellings)
             config = dict(vocab_size=config["n_vocab"], num_mel_bins=config["n_mels"], d_model=config["n_audio_state"],
                           encoder_layers=config["n_audio_layer"], encoder_attention_heads=config["n_audio_head"],
@@ -100,6 +101,8 @@ class WhisperModel:
                           decoder_ffn_dim=4 * config["n_text_state"], max_target_positions=config["n_text_ctx"])
         w = Weights(model_dir)
         w.sanitize_whisper()
+        if isinstance(quant, dict):
+            w.dequantize(int(quant["group_size"]), int(quant["bits"]))
         tensors = w.tensors()
         w.close()
         return cls(config, tensors, device=device, max_batch=max_batch)

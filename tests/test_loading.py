@@ -137,6 +137,35 @@ def test_llama_sanitize_and_mlx_affine_dequant(b2a, tmp_path, bits, group_size):
         b2a.Weights(tmp_path).sanitize_llama(True, 64, 3)
 
 
+def test_quantized_whisper_checkpoint_is_dequantized_after_the_remap(b2a, tmp_path):
+    """WhisperModel.fromDirectory quantises every Linear and decoder.embed_tokens when config.json has "quantization"
+    (WhisperModel.swift:499-511); Tests/WhisperQuantizedTiedEmbeddingTests.swift pins that the tied projection then uses the
+    DE-QUANTISED embedding (tolerance 1e-2).  Here: an mlx-whisper-layout checkpoint with a packed token embedding and a packed Linear."""
+    rng = np.random.default_rng(5)
+    emb = rng.standard_normal((96, 64)).astype(np.float32)
+    fc1 = rng.standard_normal((128, 64)).astype(np.float32)
+    we, se, be, qe = mlx_affine_quantize(emb, 32, 4)
+    wf, sf, bf_, qf = mlx_affine_quantize(fc1, 32, 4)
+    save_file({"decoder.token_embedding.weight": we.view(np.int32), "decoder.token_embedding.scales": se, "decoder.token_embedding.biases": be,
+               "decoder.blocks.0.mlp1.weight": wf.view(np.int32), "decoder.blocks.0.mlp1.scales": sf, "decoder.blocks.0.mlp1.biases": bf_,
+               "decoder.blocks.0.mlp1.bias": np.zeros(128, np.float32), "encoder.conv2.weight": rng.standard_normal((64, 3, 64)).astype(np.float32)},
+              str(tmp_path / "weights.safetensors"))
+    w = b2a.Weights(tmp_path)
+    assert w.sanitize_whisper() == 1                                # mlx-whisper layout detected
+    w.dequantize(32, 4)
+    t = w.tensors()
+    assert "model.decoder.embed_tokens.scales" not in t and "model.decoder.layers.0.fc1.biases" not in t
+    assert "model.decoder.layers.0.fc1.bias" in t                  # the layer's own bias is not the quantiser's "biases"
+    dense_e = (np.repeat(se, 32, axis=1) * qe + np.repeat(be, 32, axis=1)).astype(np.float32)
+    dense_f = (np.repeat(sf, 32, axis=1) * qf + np.repeat(bf_, 32, axis=1)).astype(np.float32)
+    assert torch.equal(t["model.decoder.embed_tokens.weight"], torch.from_numpy(dense_e).to(torch.bfloat16))
+    assert torch.equal(t["model.decoder.layers.0.fc1.weight"], torch.from_numpy(dense_f).to(torch.bfloat16))
+    hidden = rng.standard_normal(64).astype(np.float32)            # the reference test's statement, with its tolerance
+    assert np.abs(t["model.decoder.embed_tokens.weight"].float().numpy() @ hidden - dense_e @ hidden).max() < 1e-2 * max(1.0, np.abs(dense_e @ hidden).max())
+    with pytest.raises(b2a.AudioGenerationError):
+        b2a.Weights(tmp_path).dequantize(32, 0)
+
+
 def test_llama_per_layer_quantization_from_config(b2a, tmp_path):
     """config.json "quantization" with per-layer overrides (mlx-swift-lm PerLayerQuantization, call site LlamaTTS.swift:955-966):
     the default 4-bit / 64, one layer at 8-bit / 32, one layer marked false."""
