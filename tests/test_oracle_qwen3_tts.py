@@ -154,3 +154,29 @@ def test_prepare_generation_inputs_layout():
     assert torch.allclose(x2[:, 2 + 3 + 5:2 + 3 + 6], tts[:, 0:1] + codec2[:, 5:6]) and torch.allclose(x2[:, -1:], text[:, 3:4] + codec2[:, 6:7])
     codes = oq.generate_codes(cfg, W, x, trailing, pad, max_tokens=3, temperature=0.0, stop_on_eos=False)
     assert codes.shape == (3, cfg.num_code_groups)
+
+
+def test_reference_tiny_model_end_to_end_shapes():
+    """The geometry of the reference's own Qwen3-TTS tests (Tests/MLXAudioTTSTests.swift:615-687: talker hidden 16 x 2 layers, head_dim 4,
+    2 code groups, 1-layer predictor, default-geometry speech-tokenizer decoder) through both oracle halves: prompt embeddings ->
+    frame loop (maxTokens 2, T 0.7, top-p 0.95) -> decodeChunk.  The reference asserts audio.ndim == 1 and a non-empty waveform
+    (:981-989, :1064-1072)."""
+    from oracle import qwen3_tts_codec as oc
+    cp = oq.CodePredictorConfig(vocab_size=2048, hidden_size=16, intermediate_size=32, num_hidden_layers=1, num_attention_heads=4,
+                                num_key_value_heads=4, head_dim=4, num_code_groups=2)
+    cfg = oq.TalkerConfig(vocab_size=3072, hidden_size=16, intermediate_size=32, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=4,
+                          head_dim=4, num_code_groups=2, text_hidden_size=16, text_vocab_size=64, codec_eos_token_id=3050, code_predictor=cp)
+    W = oq.init_weights(cfg, 3)
+    inp, trail, pad = oq.prepare_generation_inputs(cfg, W, chat_ids=[4, 10, 11, 30, 31, 32, 33, 34, 5, 12, 4, 10, 11], tts_bos=22, tts_eos=23, tts_pad=21,
+                                                   language_id=3057, codec_think_id=3051, codec_nothink_id=3052, codec_think_bos_id=3053,
+                                                   codec_think_eos_id=3054, codec_pad_id=3055, codec_bos_id=3056)
+    codes = oq.generate_codes(cfg, W, inp, trail, pad, max_tokens=2, temperature=0.7, top_p=0.95, generator=torch.Generator().manual_seed(0))
+    assert codes.shape == (2, 2) and int(codes.min()) >= 0 and int(codes[:, 0].max()) < 3072 - 1024 and int(codes[:, 1].max()) < 2048
+    again = oq.generate_codes(cfg, W, inp, trail, pad, max_tokens=2, temperature=0.7, top_p=0.95, generator=torch.Generator().manual_seed(0))
+    assert torch.equal(codes, again)                               # same seed, same frames (the reference re-seeds between its two calls)
+    dcfg = oc.TokenizerDecoderConfig()                             # "decoder_config": {} in the reference's fixture
+    DW = oc.init_weights(dcfg, 1)
+    audio = oc.decode_chunk(dcfg, DW, codes[None].numpy())         # [1, frames, groups]: only 2 of the 16 code groups are present
+    assert audio.ndim == 1 and audio.shape[0] == 2 * 1920 and np.abs(audio).max() > 0
+    parts = oc.streaming_decode(dcfg, DW, codes[None].numpy(), chunk_tokens=1)        # generateStream with a short interval: one chunk per frame
+    assert [p.shape for p in parts] == [(1, 1920), (1, 1920)]
