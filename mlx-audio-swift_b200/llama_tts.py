@@ -225,8 +225,10 @@ class LlamaTTSModel:
         _, waves, _ = self.generate_batch(ids, parameters)
         return waves[0]
 
-    def generate_stream(self, prompt_token_ids: Sequence[int], parameters: Optional[GenerateParameters] = None) -> Iterator:
-        """generateStream (:777-913): yields ('token', id)..., ('info', AudioGenerationInfo), ('audio', waveform)."""
+    def generate_stream(self, prompt_token_ids: Sequence[int], parameters: Optional[GenerateParameters] = None,
+                        streaming_interval: float = 2.0) -> Iterator:
+        """generateStream (:777-913): yields ('token', id)..., ('info', AudioGenerationInfo), ('audio', waveform).  `streaming_interval` is
+        accepted and ignored, as the protocol's default overload does for models that emit their audio once (Generation.swift:119-137)."""
         if self._snac_model is None:
             raise _ffi.AudioGenerationError(_ffi.ERR_MODEL_NOT_INITIALIZED, "SNAC model not loaded")
         ids, _ = self.prepare_input_ids([list(prompt_token_ids)])
@@ -235,6 +237,13 @@ class LlamaTTSModel:
         yield from events
         yield ("info", info)
         yield ("audio", waves[0])
+
+    def generate_samples_stream(self, prompt_token_ids: Sequence[int], parameters: Optional[GenerateParameters] = None,
+                                streaming_interval: float = 2.0) -> Iterator[np.ndarray]:
+        """generateSamplesStream (Generation.swift:52-74): only the .audio events of generateStream, as sample arrays."""
+        for kind, value in self.generate_stream(prompt_token_ids, parameters, streaming_interval):
+            if kind == "audio" and value is not None:
+                yield value
 
     def generate_dev(self, d_input_ids, parameters: GenerateParameters, d_wave, wave_cap: int):
         """Device-resident variant (bench `value`): torch CUDA int32 ids [B, L]; waveform stays in HBM."""
