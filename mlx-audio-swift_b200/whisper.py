@@ -208,6 +208,16 @@ class WhisperModel:
                          info.prompt_tokens + info.generation_tokens, info.prompt_tokens / tt, info.generation_tokens / tt,
                          info.total_time, info.encode_time, info.decode_time, segs)
 
+    def generate_stream(self, audio, generation_parameters: Optional[STTGenerateParameters] = None):
+        """generateStream(audio:generationParameters:) (WhisperModel.swift:92-156) on token ids: ('token', id) for every generated token,
+        window by window (the reference yields the detokenised deltas), then ('result', STTOutput).  The windows are transcribed as one
+        batch, so the token events arrive after the call returns, like LlamaTTSModel.generate_stream."""
+        out = self.generate_long(audio, generation_parameters)
+        for window in out.tokens:
+            for tok in window:
+                yield ("token", tok)
+        yield ("result", out)
+
     def cancel(self) -> None:
         _ffi.check(_ffi.lib().b2a_stt_cancel(self._h))
 
