@@ -510,6 +510,13 @@ int32_t b2a_speech_tokenizer_create_from_directory(const char* dir, int32_t devi
  * stride * out (phase-major), taps = n.  layout_out: [rows][taps][kpad] float32, kpad = ceil(in / 64) * 64.            */
 int32_t b2a_speech_tokenizer_debug_layout(const float* w, int32_t out, int32_t k, int32_t in, int32_t stride, float* layout_out,
                                           int64_t capacity, int32_t* rows, int32_t* taps, int32_t* kpad);
+/* Test entry (tests/test_gpu_qwen3_sampler.py) for the Qwen3-TTS in-graph sampler kernel (csrc/qwen3_sampler.cu = sampleToken,
+ * Qwen3TTS.swift:1003-1118; EXPERIMENTAL like the rest of row N1): HOST logits [B, V <= 4096]; suppress [lo, hi) except eos;
+ * seen = bitmap of the tokens generated so far [B, ceil(V/32)] (nullable; updated when track != 0); tokens_out [B];
+ * filtered_out [B, V] (nullable) = the logits handed to categorical, -inf where removed.                                  */
+int32_t b2a_qwen3_sample_test(const float* logits, int32_t batch, int32_t vocab, float temperature, float top_p, int32_t top_k,
+                              float min_p, float repetition_penalty, int32_t eos, int32_t suppress_lo, int32_t suppress_hi,
+                              uint32_t* seen, int32_t track, uint64_t seed, int32_t step, int32_t* tokens_out, float* filtered_out);
 /* Test entry (tests/test_gpu_implicit_conv.py): one launch of the implicit-GEMM causal convolution kernel
  * (csrc/implicit_conv.cuh) on HOST data: w [M][taps][Cin], x [B][Ttot][Cin]; out[b, t*up + rho, co] for m = rho * (M/up) + co is
  * sum_j sum_c w[m, j, c] * x[b, t + shift0 + j*dil, c] through the fused epilogue (bias, bias twice at t = 0, GELU, gamma, add,

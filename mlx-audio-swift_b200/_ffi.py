@@ -168,6 +168,8 @@ SIGNATURES = {
     "b2a_weights_sanitize_speech_tokenizer": (C.c_int32, [_P]),
     "b2a_speech_tokenizer_config_from_json": (C.c_int32, [C.c_char_p, C.c_int32, C.c_int32, C.POINTER(SpeechTokenizerConfig), C.POINTER(C.c_int32)]),
     "b2a_speech_tokenizer_create_from_directory": (C.c_int32, [C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P), C.POINTER(C.c_int32)]),
+    "b2a_qwen3_sample_test": (C.c_int32, [_P, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_int32,
+                                         C.c_int32, _P, C.c_int32, C.c_uint64, C.c_int32, _P, _P]),
     "b2a_implicit_conv_test": (C.c_int32, [_P, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                           _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int32, _P, _P]),
     "b2a_speech_tokenizer_debug_layout": (C.c_int32, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int64, _P, _P, _P]),

@@ -11,7 +11,7 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIBDIR = HERE / "lib"
 LIB = LIBDIR / "libb200audio.so"
-SOURCES = ["api.cu", "mel.cu", "snac.cu", "llama.cu", "tc_gemm.cu", "whisper.cu", "vocos.cu", "encodec.cu", "weights.cu", "speech_tokenizer.cu"]
+SOURCES = ["api.cu", "mel.cu", "snac.cu", "llama.cu", "tc_gemm.cu", "whisper.cu", "vocos.cu", "encodec.cu", "weights.cu", "speech_tokenizer.cu", "qwen3_sampler.cu"]
 NVCC_FLAGS = (["-DB2A_ATTN_TIMING"] if os.environ.get("B2A_ATTN_TIMING") else []) + [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
