@@ -200,9 +200,11 @@ class CpuReference:
         for c in cands:
             torch.set_num_threads(c)
             mo.forward(nxt)                                   # settle the pool at this size
-            t0 = time.perf_counter()
-            mo.forward(nxt)
-            dt = time.perf_counter() - t0
+            dt = float("inf")
+            for _ in range(2):                                # best of two: one timing is too noisy on a shared host
+                t0 = time.perf_counter()
+                mo.forward(nxt)
+                dt = min(dt, time.perf_counter() - t0)
             seen.append(f"{c}: {dt * 1e3:.0f}ms")
             if best is None or dt < best[1]:
                 best = (c, dt)
