@@ -91,3 +91,38 @@ def test_goldens():
     assert np.abs(full[:4] - g["inc_first"]).max() < 1e-6 and np.abs(full[-3:] - g["inc_last"]).max() < 1e-6
     w = dsp.whisper_encoder_features(x, 80)[0]
     assert np.abs(w[[0, 1, 999, 1000, 2999]] - g["whisper_rows"]).max() < 1e-6
+
+
+def test_mel_filterbank_matches_torchaudio():
+    """melFilters (DSP.swift:76-168) against torchaudio.functional.melscale_fbanks -- an independent implementation -- for the two
+    configurations on the path: HTK scale + Slaney norm (IncrementalMelSpectrogram / computeMelSpectrogram) and Slaney + Slaney
+    (Whisper).  The only structural difference is the reference's inclusive upper edge (`<=`, :149): at most one extra tiny entry."""
+    torchaudio = pytest.importorskip("torchaudio")
+    import warnings
+    for scale in ("htk", "slaney"):
+        for n_mels in (80, 128):
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                ref = torchaudio.functional.melscale_fbanks(n_freqs=201, f_min=0.0, f_max=8000.0, n_mels=n_mels, sample_rate=16000, norm="slaney",
+                                                            mel_scale=scale).double().numpy()
+            o = dsp.mel_filters(16000, 400, n_mels, norm="slaney", mel_scale=scale)
+            assert o.shape == ref.shape == (201, n_mels)
+            assert np.abs(o - ref).max() < 5e-7 * max(1.0, np.abs(ref).max() / 0.03)
+            extra = (o != 0) & (ref == 0)
+            assert extra.sum() <= 1 and not ((o == 0) & (ref != 0)).any()
+
+
+def test_offline_log_mel_matches_torchaudio_pipeline():
+    """computeMelSpectrogram (DSP.swift:181-273: reflect pad both sides, symmetric Hann, |rfft|^2, HTK/Slaney filterbank, log10, global
+    max - 8 clamp, (x + 4) / 4) against torchaudio's MelSpectrogram (independent STFT and filterbank) with the same post-processing."""
+    torchaudio = pytest.importorskip("torchaudio")
+    x = dsp.synth_audio(160000, 0)
+    o = dsp.compute_mel_spectrogram(x, 16000, 400, 160, 80)
+    win = torch.from_numpy(dsp.hanning_window(400)).double()
+    T = torchaudio.transforms.MelSpectrogram(sample_rate=16000, n_fft=400, hop_length=160, n_mels=80, f_min=0.0, f_max=8000.0, power=2.0, center=True,
+                                             pad_mode="reflect", norm="slaney", mel_scale="htk", window_fn=lambda n: win).double()
+    m = T(torch.from_numpy(x).double()).numpy().T
+    assert m.shape == o.shape == (1001, 80)                        # SURVEY config 1: 999 + 2 frames
+    lg = np.log10(np.maximum(m, 1e-10))
+    lg = (np.maximum(lg, lg.max() - 8.0) + 4.0) / 4.0
+    assert np.abs(lg - o).max() < 1e-4
