@@ -40,3 +40,33 @@ def test_oracle_reproduces_committed_golden():
     assert tuple(g["vocos_shape"]) == y.shape and np.abs(y[:, :64] - g["vocos_first"]).max() < 1e-6
     yy = np.asarray(y, dtype=np.float64).reshape(-1)
     assert np.allclose([yy.mean(), np.abs(yy).mean(), yy.min(), yy.max()], g["vocos_stats"], rtol=1e-6, atol=1e-9)
+
+
+def test_istft_head_overlap_add_matches_torch_istft_up_to_its_normalisation():
+    """torch.istft(center=True) = OLA(irfft * w) / OLA(w^2), trimmed by n_fft/2; the reference divides by OLA(w) instead (Vocos.swift:123-160,
+    window-SUM normalisation).  So oracle * OLA(w) / OLA(w^2) must equal torch.istft on the same spectrum: an independent check of the
+    inverse FFT, the windowing, the overlap-add indexing and the centre trim."""
+    cfg = ov.VocosConfig(dim=8, n_fft=64, hop_length=16)
+    rng = np.random.default_rng(0)
+    W = {"head.out.weight": rng.standard_normal((cfg.n_fft + 2, cfg.dim)) * 0.3, "head.out.bias": rng.standard_normal(cfg.n_fft + 2) * 0.1}
+    L = 23
+    x = torch.from_numpy(rng.standard_normal((2, L, cfg.dim)))
+    y = ov.istft_head(cfg, W, x)
+    h = x @ torch.from_numpy(W["head.out.weight"]).T + torch.from_numpy(W["head.out.bias"])
+    half = cfg.n_fft // 2 + 1
+    mag = torch.clamp(torch.exp(h[..., :half]), max=1e2)
+    spec = torch.complex(mag * torch.cos(h[..., half:]), mag * torch.sin(h[..., half:]))
+    # irfft ignores the imaginary part of the DC and Nyquist bins; torch.istft insists on a Hermitian-consistent input, so zero them
+    spec[..., 0] = torch.complex(spec[..., 0].real, torch.zeros_like(spec[..., 0].real))
+    spec[..., -1] = torch.complex(spec[..., -1].real, torch.zeros_like(spec[..., -1].real))
+    win = ov.hann_symmetric(cfg.n_fft)
+    ref = torch.istft(spec.transpose(1, 2), cfg.n_fft, cfg.hop_length, window=win, center=True, length=(L - 1) * cfg.hop_length).numpy()
+    out_len = (L - 1) * cfg.hop_length + cfg.n_fft
+    w1, w2 = np.zeros(out_len), np.zeros(out_len)
+    for i in range(L):
+        w1[i * cfg.hop_length: i * cfg.hop_length + cfg.n_fft] += win.numpy()
+        w2[i * cfg.hop_length: i * cfg.hop_length + cfg.n_fft] += win.numpy() ** 2
+    a = cfg.n_fft // 2
+    ratio = (w1 / np.maximum(w2, 1e-300))[a: a + (L - 1) * cfg.hop_length]
+    assert y.shape == ref.shape == (2, (L - 1) * cfg.hop_length)
+    assert np.abs(y * ratio - ref).max() < 1e-9 * max(1.0, np.abs(ref).max())
