@@ -93,3 +93,23 @@ def test_goldens():
     W = llama.init_weights(cfg, 1234, std=0.08)
     lg = llama.LlamaOracle(cfg, W, False).forward(torch.as_tensor(g["ids"])).numpy()
     assert rel_err(lg[:, -1], g["logits_last"]) < 1e-5
+
+
+def test_sampler_restatement_matches_transformers_logits_processors():
+    """The sampler / repetition penalty live in mlx-swift-lm (not on disk).  Their restatement is checked here against the independent
+    `transformers` processors that implement the same published rules: RepetitionPenaltyLogitsProcessor (logit < 0 -> * p, else / p, once
+    per unique token) and TemperatureLogitsWarper + TopPLogitsWarper (drop the ascending-sorted tail whose cumulative probability is <= 1 - top_p)."""
+    import torch
+    from transformers.generation.logits_process import RepetitionPenaltyLogitsProcessor, TemperatureLogitsWarper, TopPLogitsWarper
+    rng = np.random.default_rng(0)
+    for trial in range(5):
+        logits = (rng.standard_normal(500) * 3).astype(np.float32)
+        ctx = rng.integers(0, 500, size=20).tolist()
+        ours = llama.repetition_penalty(logits, ctx, 1.3)
+        ref = RepetitionPenaltyLogitsProcessor(1.3)(torch.as_tensor([ctx]), torch.from_numpy(logits)[None].clone())[0].numpy()
+        assert np.array_equal(ours, ref)
+        kept = llama.top_p_filter(ours, 0.6, 0.8)
+        warped = TopPLogitsWarper(0.8)(None, TemperatureLogitsWarper(0.6)(None, torch.from_numpy(ours)[None].double()))[0]
+        assert np.array_equal(kept > 0, torch.isfinite(warped).numpy()), trial
+        p = torch.softmax(torch.from_numpy(ours).double() / 0.6, dim=-1).numpy()
+        assert np.allclose(kept[kept > 0], p[kept > 0], rtol=1e-12)

@@ -180,3 +180,25 @@ def test_reference_tiny_model_end_to_end_shapes():
     assert audio.ndim == 1 and audio.shape[0] == 2 * 1920 and np.abs(audio).max() > 0
     parts = oc.streaming_decode(dcfg, DW, codes[None].numpy(), chunk_tokens=1)        # generateStream with a short interval: one chunk per frame
     assert [p.shape for p in parts] == [(1, 1920), (1, 1920)]
+
+
+def test_filter_logits_matches_transformers_warpers():
+    """sampleToken's top-k -> top-p -> min-p chain (Qwen3TTS.swift:1048-1105, applied to the UN-tempered logits) against the independent
+    `transformers` warpers that implement the same rules (TopK, TopP with the ascending-cumulative `<= 1 - top_p` removal, MinP relative
+    to the most probable token)."""
+    from transformers.generation.logits_process import MinPLogitsWarper, TopKLogitsWarper, TopPLogitsWarper
+    rng = np.random.default_rng(1)
+    for top_k, top_p, min_p in ((50, 1.0, 0.0), (50, 0.9, 0.0), (20, 0.7, 0.05), (0, 0.95, 0.1)):
+        for trial in range(3):
+            logits = torch.from_numpy((rng.standard_normal((1, 3072)) * 3).astype(np.float32)).double()
+            ours = oq.filter_logits(logits, temperature=0.9, top_p=top_p, top_k=top_k, min_p=min_p)
+            ref = logits.clone()
+            if top_k > 0:
+                ref = TopKLogitsWarper(top_k)(None, ref)
+            if top_p < 1.0:
+                ref = TopPLogitsWarper(top_p)(None, ref)
+            if min_p > 0.0:
+                ref = MinPLogitsWarper(min_p)(None, ref)
+            assert torch.equal(torch.isfinite(ours), torch.isfinite(ref)), (top_k, top_p, min_p, trial)
+            keep = torch.isfinite(ref)
+            assert torch.allclose(ours[keep], ref[keep])
