@@ -125,3 +125,15 @@ def test_oracle_reproduces_committed_golden():
     assert np.abs(z[:, :64, 0] - g["encodec_first"]).max() < 1e-6 and np.abs(z[:, -64:, 0] - g["encodec_last"]).max() < 1e-6
     zz = z.reshape(-1)
     assert np.allclose([zz.mean(), np.abs(zz).mean(), zz.min(), zz.max()], g["encodec_stats"], rtol=1e-6, atol=1e-9)
+
+
+def test_linear_overlap_add_matches_transformers():
+    """linearOverlapAdd (Encodec.swift:304-356) against transformers' EncodecModel._linear_overlap_add on ragged last frames."""
+    import torch
+    from transformers import EncodecModel
+    rng = np.random.default_rng(2)
+    for n_frames, L, last, hop in ((3, 8, 8, 4), (4, 12, 7, 6), (2, 10, 10, 9)):
+        frames = [rng.standard_normal((2, L if i < n_frames - 1 else last, 1)) for i in range(n_frames)]
+        ours = oe.linear_overlap_add(frames, hop)
+        ref = EncodecModel._linear_overlap_add([torch.from_numpy(f).permute(0, 2, 1) for f in frames], hop).permute(0, 2, 1).numpy()
+        assert ours.shape == ref.shape and np.abs(ours - ref).max() < 1e-12

@@ -89,3 +89,13 @@ def test_goldens():
     z = (rng.standard_normal((2, cfg.latent, 16)) * 0.5).astype(np.float32)
     _, qc = snac.quantize(cfg, W, z)
     assert np.array_equal(qc[0], g["q_codes0"]) and np.array_equal(qc[2], g["q_codes2"])
+
+
+def test_snake_matches_transformers_dac_snake1d():
+    """snake (Layers.swift:44-50) against the Snake1d of transformers' DAC (the codec SNAC's layers derive from)."""
+    from transformers.models.dac.modeling_dac import Snake1d
+    m = Snake1d(6).double()
+    with torch.no_grad():
+        m.alpha.copy_(torch.rand(1, 6, 1) * 2 + 0.1)
+    x = torch.randn(2, 6, 33, dtype=torch.float64)
+    assert (snac.snake(x, m.alpha.detach()) - m(x)).abs().max() < 1e-12

@@ -71,3 +71,12 @@ def test_goldens():
     x = dsp.synth_audio(64000, 3)
     toks = ow.transcribe_tokens(ow.WhisperOracle(cfg, W), x, ow.build_prompt_tokens(), max_tokens=12, mask_eot=True)
     assert toks == g["greedy"].tolist()
+
+
+def test_sinusoids_match_transformers():
+    """whisperSinusoids (WhisperModel.swift:384-397) against transformers' own `sinusoids` (what HF Whisper checkpoints are initialised with)."""
+    from transformers.models.whisper.modeling_whisper import sinusoids as hf_sinusoids
+    for length, channels in ((1500, 512), (1500, 384), (32, 64)):
+        # the reference evaluates sin / cos in Double and then narrows (:387-395); transformers works in float32, so the angle of the
+        # late positions carries ~1e-4 of rounding there -- same table up to that
+        assert np.abs(ow.sinusoids(length, channels).numpy() - hf_sinusoids(length, channels).numpy()).max() < 2e-4
