@@ -99,3 +99,28 @@ def test_snake_matches_transformers_dac_snake1d():
         m.alpha.copy_(torch.rand(1, 6, 1) * 2 + 0.1)
     x = torch.randn(2, 6, 33, dtype=torch.float64)
     assert (snac.snake(x, m.alpha.detach()) - m(x)).abs().max() < 1e-12
+
+
+def test_code_search_matches_transformers_dac_vector_quantize():
+    """VectorQuantize.decodeLatents (VQ.swift:96-120: L2-normalise encodings and codebook, argmax of -(|e|^2 - 2 e.c + |c|^2)) against
+    DacVectorQuantize.decode_latents of transformers (SNAC's quantiser is DAC's).  Float64 on the HF side; the oracle's ordered-fp32
+    search may only differ on near-ties."""
+    from transformers import DacConfig
+    from transformers.models.dac.modeling_dac import DacVectorQuantize
+    rng = np.random.default_rng(4)
+    vq = DacVectorQuantize(DacConfig(codebook_size=4096, codebook_dim=8, hidden_size=16)).double()
+    cb = rng.standard_normal((4096, 8)).astype(np.float32)
+    with torch.no_grad():
+        vq.codebook.weight.copy_(torch.from_numpy(cb).double())
+    enc = rng.standard_normal((3, 8, 700)).astype(np.float32)                  # [B, D, T]
+    _, ref = vq.decode_latents(torch.from_numpy(enc).double())
+    ours = snac.nearest_code_fp32(enc.transpose(0, 2, 1).reshape(-1, 8), cb).reshape(3, 700)
+    diff = ours != ref.numpy()
+    assert diff.mean() < 2e-3
+    if diff.any():                                                             # any disagreement must be a near-tie in cosine similarity
+        e = enc.transpose(0, 2, 1).reshape(-1, 8).astype(np.float64)
+        e /= np.linalg.norm(e, axis=1, keepdims=True)
+        c = cb.astype(np.float64) / np.linalg.norm(cb.astype(np.float64), axis=1, keepdims=True)
+        sim = e @ c.T
+        rows = np.flatnonzero(diff.reshape(-1))
+        assert np.abs(sim[rows, ours.reshape(-1)[rows]] - sim[rows, ref.numpy().reshape(-1)[rows]]).max() < 1e-6
