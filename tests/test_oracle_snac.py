@@ -124,3 +124,64 @@ def test_code_search_matches_transformers_dac_vector_quantize():
         sim = e @ c.T
         rows = np.flatnonzero(diff.reshape(-1))
         assert np.abs(sim[rows, ours.reshape(-1)[rows]] - sim[rows, ref.numpy().reshape(-1)[rows]]).max() < 1e-6
+
+
+def _load_dac_decoder(cfg, w):
+    """transformers' DacDecoder carrying the oracle's (weight-norm folded) SNAC weights; only valid for depthwise=False, noise=False."""
+    from transformers import DacConfig
+    from transformers.models.dac.modeling_dac import DacDecoder
+    dec = DacDecoder(DacConfig(hidden_size=cfg.latent, decoder_hidden_size=cfg.decoder_dim, upsampling_ratios=list(cfg.decoder_rates))).double()
+    p = "decoder.model.layers"
+    with torch.no_grad():
+        dec.conv1.weight.copy_(snac.wn_conv_weight(w, f"{p}.0")); dec.conv1.bias.copy_(snac._t(w[f"{p}.0.bias"]))
+        li = 1
+        for blk in dec.block:
+            b = f"{p}.{li}.block.layers"
+            blk.snake1.alpha.copy_(snac._t(w[f"{b}.0.alpha"]))
+            blk.conv_t1.weight.copy_(snac.wn_convT_weight(w, f"{b}.1")); blk.conv_t1.bias.copy_(snac._t(w[f"{b}.1.bias"]))
+            for j, ru in enumerate((blk.res_unit1, blk.res_unit2, blk.res_unit3)):
+                r = f"{b}.{2 + j}.block.layers"
+                ru.snake1.alpha.copy_(snac._t(w[f"{r}.0.alpha"])); ru.snake2.alpha.copy_(snac._t(w[f"{r}.2.alpha"]))
+                ru.conv1.weight.copy_(snac.wn_conv_weight(w, f"{r}.1")); ru.conv1.bias.copy_(snac._t(w[f"{r}.1.bias"]))
+                ru.conv2.weight.copy_(snac.wn_conv_weight(w, f"{r}.3")); ru.conv2.bias.copy_(snac._t(w[f"{r}.3.bias"]))
+            li += 1
+        dec.snake1.alpha.copy_(snac._t(w[f"{p}.{li}.alpha"]))
+        dec.conv2.weight.copy_(snac.wn_conv_weight(w, f"{p}.{li + 1}")); dec.conv2.bias.copy_(snac._t(w[f"{p}.{li + 1}.bias"]))
+    return dec
+
+
+def test_dense_decoder_matches_transformers_dac_decoder():
+    """With depthwise = false and noise = false the SNAC decoder (Layers.swift:364-421) IS the DAC decoder: k7 conv -> 4 x (Snake ->
+    transposed conv k = 2s, padding ceil(s/2) -> three dilated residual units) -> Snake -> k7 conv -> tanh.  The oracle in that mode,
+    weight norm included, against transformers' DacDecoder with the same weights: an independent check of the layer order, every
+    padding, the transposed-convolution semantics (SURVEY 8c trap 7) and Snake."""
+    cfg = snac.SNACConfig(encoder_dim=4, encoder_rates=(2, 2), decoder_dim=64, decoder_rates=(8, 8, 4, 2), noise=False, depthwise=False)
+    w = snac.init_weights(cfg, 7)
+    z = torch.randn(2, cfg.latent, 9, dtype=torch.float64)
+    ours = snac.decoder(cfg, w, z, None)
+    with torch.no_grad():
+        ref = _load_dac_decoder(cfg, w)(z)
+    assert ours.shape == ref.shape == (2, 1, 9 * 512) and (ours - ref).abs().max() < 1e-10
+
+
+def test_depthwise_residual_unit_is_the_dense_unit_with_a_diagonal_kernel():
+    """SNAC's depthwise ResidualUnit (Layers.swift:202-232, groups = dim) against transformers' dense DacResidualUnit whose k7 kernel is
+    the depthwise one placed on the channel diagonal."""
+    from transformers.models.dac.modeling_dac import DacResidualUnit
+    cfg = snac.SNACConfig(encoder_dim=4, encoder_rates=(2, 2), decoder_dim=32, decoder_rates=(2,), noise=False, depthwise=True)
+    w = snac.init_weights(cfg, 3)
+    C, dil = 16, 3
+    r = "decoder.model.layers.2.block.layers.3"                 # second residual unit of the only block (layers 0, 1 = dw + pw stem)
+    ru = DacResidualUnit(C, dilation=dil).double()
+    with torch.no_grad():
+        dw = snac.wn_conv_weight(w, r + ".block.layers.1")       # [C, 1, 7]
+        ru.conv1.weight.zero_()
+        for c in range(C):
+            ru.conv1.weight[c, c] = dw[c, 0]
+        ru.conv1.bias.copy_(snac._t(w[r + ".block.layers.1.bias"]))
+        ru.conv2.weight.copy_(snac.wn_conv_weight(w, r + ".block.layers.3")); ru.conv2.bias.copy_(snac._t(w[r + ".block.layers.3.bias"]))
+        ru.snake1.alpha.copy_(snac._t(w[r + ".block.layers.0.alpha"])); ru.snake2.alpha.copy_(snac._t(w[r + ".block.layers.2.alpha"]))
+    x = torch.randn(2, C, 40, dtype=torch.float64)
+    with torch.no_grad():
+        ref = ru(x)
+    assert (snac.residual_unit(w, r, x, dil, C) - ref).abs().max() < 1e-12
