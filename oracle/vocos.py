@@ -74,6 +74,18 @@ def hann_symmetric(n: int) -> torch.Tensor:
 
 
 @torch.no_grad()
+def convnext_layer(cfg: VocosConfig, w: Dict, l: int, h: torch.Tensor) -> torch.Tensor:
+    """ConvNeXtBlock l on h [B, L, dim] (VocosBackbone.swift:18-100): depthwise k "same" -> LayerNorm -> Linear -> exact GELU -> Linear -> gamma, + h."""
+    d = cfg.dim
+    p = f"backbone.convnext.{l}."
+    y = F.conv1d(h.transpose(1, 2), _t(w[p + "dwconv.weight"]).permute(0, 2, 1), _t(w[p + "dwconv.bias"]),
+                 padding=cfg.dw_kernel_size // 2, groups=d).transpose(1, 2)
+    y = F.layer_norm(y, (d,), _t(w[p + "norm.weight"]), _t(w[p + "norm.bias"]), 1e-6)
+    y = F.gelu(y @ _t(w[p + "pwconv1.weight"]).T + _t(w[p + "pwconv1.bias"]))
+    y = y @ _t(w[p + "pwconv2.weight"]).T + _t(w[p + "pwconv2.bias"])
+    return h + _t(w[p + "gamma"]) * y
+
+
 def backbone(cfg: VocosConfig, w: Dict, feats: np.ndarray) -> torch.Tensor:
     """feats [B, L, input_channels] -> [B, L, dim]."""
     x = _t(feats).transpose(1, 2)
@@ -82,13 +94,7 @@ def backbone(cfg: VocosConfig, w: Dict, feats: np.ndarray) -> torch.Tensor:
     d = cfg.dim
     h = F.layer_norm(h, (d,), _t(w["backbone.norm.weight"]), _t(w["backbone.norm.bias"]), 1e-6)
     for l in range(cfg.num_layers):
-        p = f"backbone.convnext.{l}."
-        y = F.conv1d(h.transpose(1, 2), _t(w[p + "dwconv.weight"]).permute(0, 2, 1), _t(w[p + "dwconv.bias"]),
-                     padding=cfg.dw_kernel_size // 2, groups=d).transpose(1, 2)
-        y = F.layer_norm(y, (d,), _t(w[p + "norm.weight"]), _t(w[p + "norm.bias"]), 1e-6)
-        y = F.gelu(y @ _t(w[p + "pwconv1.weight"]).T + _t(w[p + "pwconv1.bias"]))
-        y = y @ _t(w[p + "pwconv2.weight"]).T + _t(w[p + "pwconv2.bias"])
-        h = h + _t(w[p + "gamma"]) * y
+        h = convnext_layer(cfg, w, l, h)
     return F.layer_norm(h, (d,), _t(w["backbone.final_layer_norm.weight"]), _t(w["backbone.final_layer_norm.bias"]), 1e-6)
 
 

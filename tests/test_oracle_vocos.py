@@ -70,3 +70,27 @@ def test_istft_head_overlap_add_matches_torch_istft_up_to_its_normalisation():
     ratio = (w1 / np.maximum(w2, 1e-300))[a: a + (L - 1) * cfg.hop_length]
     assert y.shape == ref.shape == (2, (L - 1) * cfg.hop_length)
     assert np.abs(y * ratio - ref).max() < 1e-9 * max(1.0, np.abs(ref).max())
+
+
+def test_convnext_block_matches_transformers_convnext_layer():
+    """Vocos's ConvNeXtBlock (VocosBackbone.swift:18-100: depthwise k7 "same" -> LayerNorm 1e-6 -> Linear -> exact GELU -> Linear -> gamma ->
+    residual) against transformers' 2-D ConvNextLayer on a height-1 image: with padding 3 only the middle row of its 7x7 depthwise
+    kernel meets data, so it is the 1-D block whose taps are that row."""
+    from transformers import ConvNextConfig
+    from transformers.models.convnext.modeling_convnext import ConvNextLayer
+    cfg = ov.VocosConfig(input_channels=12, dim=12, intermediate_dim=48, num_layers=1, input_kernel_size=1)
+    W = ov.init_weights(cfg, 5)
+    layer = ConvNextLayer(ConvNextConfig(hidden_act="gelu", layer_scale_init_value=1.0), dim=12).double()
+    p = "backbone.convnext.0."
+    with torch.no_grad():
+        layer.dwconv.weight.zero_()
+        layer.dwconv.weight[:, 0, 3, :] = torch.as_tensor(np.asarray(W[p + "dwconv.weight"]), dtype=torch.float64)[:, :, 0]      # MLX [C, k, 1]
+        layer.dwconv.bias.copy_(torch.as_tensor(np.asarray(W[p + "dwconv.bias"])))
+        layer.layernorm.weight.copy_(torch.as_tensor(np.asarray(W[p + "norm.weight"]))); layer.layernorm.bias.copy_(torch.as_tensor(np.asarray(W[p + "norm.bias"])))
+        layer.pwconv1.weight.copy_(torch.as_tensor(np.asarray(W[p + "pwconv1.weight"]))); layer.pwconv1.bias.copy_(torch.as_tensor(np.asarray(W[p + "pwconv1.bias"])))
+        layer.pwconv2.weight.copy_(torch.as_tensor(np.asarray(W[p + "pwconv2.weight"]))); layer.pwconv2.bias.copy_(torch.as_tensor(np.asarray(W[p + "pwconv2.bias"])))
+        layer.layer_scale_parameter.copy_(torch.as_tensor(np.asarray(W[p + "gamma"])))
+    h = torch.randn(2, 31, 12, dtype=torch.float64)                       # [B, L, C], the state between blocks
+    with torch.no_grad():
+        ref = layer(h.transpose(1, 2)[:, :, None, :])[:, :, 0, :].transpose(1, 2)
+    assert (ov.convnext_layer(cfg, W, 0, h) - ref).abs().max() < 1e-12
