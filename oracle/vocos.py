@@ -86,6 +86,7 @@ def convnext_layer(cfg: VocosConfig, w: Dict, l: int, h: torch.Tensor) -> torch.
     return h + _t(w[p + "gamma"]) * y
 
 
+@torch.no_grad()
 def backbone(cfg: VocosConfig, w: Dict, feats: np.ndarray) -> torch.Tensor:
     """feats [B, L, input_channels] -> [B, L, dim]."""
     x = _t(feats).transpose(1, 2)
