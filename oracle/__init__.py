@@ -15,10 +15,11 @@ path -- only two "returns nil" robustness cases for
 ``IncrementalMelSpectrogram`` (``Tests/IncrementalMelSpectrogramTests.swift:7-17``),
 shape checks for Whisper features (``Tests/MLXAudioSTTTests.swift:4416-4422``)
 and closed-form window values.  Those are all reproduced in
-``tests/test_oracle_*.py``.  Beyond that the oracle is cross-checked against
-independent implementations available offline (``torch.stft``,
-``torch.nn.functional.conv1d/conv_transpose1d``, ``transformers`` Llama/Whisper
-with random init), see ``tests/test_oracle_crosscheck.py``.
+``tests/test_oracle_*.py``.  Beyond that the oracle is cross-checked against independent implementations available offline
+(``tests/test_oracle_*.py``): ``torch.stft`` and ``torchaudio`` (mel filterbanks, the whole offline log-mel), ``transformers``
+Whisper (feature extractor, encoder / decoder, sinusoids), Llama with llama3 rope scaling, the logits processors (repetition
+penalty, top-k / top-p / min-p), EncodecModel (decoder, RVQ, linear overlap-add), DAC (the SNAC decoder in its dense mode, Snake,
+the cosine code search), ConvNext (Vocos block), ``torch.istft`` (Vocos head), Qwen3 / Qwen3-VL / Qwen3-Omni Code2Wav (Qwen3-TTS).
 
 Modules: ``dsp`` (mel), ``snac``, ``llama`` (Orpheus), ``whisper``, ``vocos``, ``encodec`` -- the rows of SURVEY.md section 8a --
 and ``qwen3_tts`` + ``qwen3_tts_codec`` (row N1 of 8f, talker / code predictor and speech-tokenizer decoder: oracle
