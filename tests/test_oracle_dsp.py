@@ -126,3 +126,20 @@ def test_offline_log_mel_matches_torchaudio_pipeline():
     lg = np.log10(np.maximum(m, 1e-10))
     lg = (np.maximum(lg, lg.max() - 8.0) + 4.0) / 4.0
     assert np.abs(lg - o).max() < 1e-4
+
+
+def test_streaming_first_chunk_matches_torchaudio_frames():
+    """IncrementalMelSpectrogram.process on ONE chunk (IncrementalMelSpectrogram.swift:68-147): the reflect prefix of the first chunk makes
+    its frames the centre-padded STFT frames, so they must equal torchaudio's MelSpectrogram frames (independent STFT + filterbank) under
+    the same log / running-max clamp / (x + 4) / 4, with the maximum taken over the frames that chunk produced."""
+    torchaudio = pytest.importorskip("torchaudio")
+    x = dsp.synth_audio(160000, 0)
+    m = dsp.IncrementalMelSpectrogram(16000, 400, 160, 80)
+    a = m.process(x)
+    assert a.shape == (999, 80)                                       # SURVEY config 1: 999 frames from process, 2 more from flush
+    win = torch.from_numpy(dsp.hanning_window(400)).double()
+    T = torchaudio.transforms.MelSpectrogram(sample_rate=16000, n_fft=400, hop_length=160, n_mels=80, f_min=0.0, f_max=8000.0, power=2.0, center=True,
+                                             pad_mode="reflect", norm="slaney", mel_scale="htk", window_fn=lambda n: win).double()
+    lg = np.log10(np.maximum(T(torch.from_numpy(x).double()).numpy().T[:999], 1e-10))
+    ref = (np.maximum(lg, lg.max() - 8.0) + 4.0) / 4.0
+    assert np.abs(a - ref).max() < 1e-4
