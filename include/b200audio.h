@@ -520,10 +520,11 @@ int32_t b2a_qwen3_sample_test(const float* logits, int32_t batch, int32_t vocab,
 /* Test entry (tests/test_gpu_implicit_conv.py): one launch of the implicit-GEMM causal convolution kernel
  * (csrc/implicit_conv.cuh) on HOST data: w [M][taps][Cin], x [B][Ttot][Cin]; out[b, t*up + rho, co] for m = rho * (M/up) + co is
  * sum_j sum_c w[m, j, c] * x[b, t + shift0 + j*dil, c] through the fused epilogue (bias, bias twice at t = 0, GELU, gamma, add,
- * SnakeBeta on the hi/lo copy).  xo [B][T*up][M/up] in/out or null; hl_out [B][Hout + T*up][M/up] or null.                 */
+ * SnakeBeta on the hi/lo copy).  xo [B][T*up][M/up] in/out or null; hl_out [B][Hout + T*up][M/up] or null.  fp16 != 0: operands as
+ * fp16 hi/lo pairs instead of bf16 ones (what B2A_ST_FP16=1 selects for the speech-tokenizer decoder).                          */
 int32_t b2a_implicit_conv_test(const float* w, int32_t M, int32_t taps, int32_t Cin, const float* x, int32_t B, int32_t Ttot, int32_t T,
                                int32_t dil, int32_t shift0, int32_t up, const float* bias, const float* gamma, int32_t gelu, int32_t add,
-                               int32_t bias_twice_t0, const float* sa, const float* sb, int32_t Hout, float* xo, float* hl_out);
+                               int32_t bias_twice_t0, const float* sa, const float* sb, int32_t Hout, int32_t fp16, float* xo, float* hl_out);
 
 #ifdef __cplusplus
 }

@@ -19,6 +19,8 @@
 #pragma once
 #include "tc_gemm.cuh"
 
+#include <cuda_fp16.h>
+
 namespace b2a {
 namespace ic {
 
@@ -45,6 +47,8 @@ struct Args {
     float* xo;                    // fp32 [B, To, Cout] or null
     __nv_bfloat16* hl;            // planar hi/lo output [2][B][Hout + To][Cout] or null
     int Hout;
+    int f16;                      // operands (weights and planes) are fp16 hi/lo pairs instead of bf16 ones: same three products and cost, 22
+                                  // instead of 16 mantissa bits per operand (predicted error of the decoder 6e-5 instead of 3e-4); range 65504
     const float* sa;              // SnakeBeta on the hi/lo copy: v + sb * sin^2(sa * v), sa = exp(alpha), sb = 1 / (exp(beta) + 1e-9)
     const float* sb;
 };
@@ -61,6 +65,22 @@ __device__ __forceinline__ float fast_sin(float x) {
     float r = fmaf(k, -6.28318548202514648f, x);
     r = fmaf(k, 1.7484555e-7f, r);
     return __sinf(r);
+}
+// instruction descriptor for kind::f16 with fp16 (format 0) or bf16 (format 1) operands, fp32 accumulate, K-major A and B
+__host__ __device__ constexpr uint32_t make_idesc16(int n, int f16) {
+    return (1u << 4) | ((f16 ? 0u : 1u) << 7) | ((f16 ? 0u : 1u) << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+// v -> hi + lo in the operand format, stored as raw 16-bit words at idx and plane + idx
+__device__ __forceinline__ void put_hilo16(uint16_t* base, long long plane, long long idx, float v, int f16) {
+    if (f16) {
+        const __half hi = __float2half_rn(v);
+        base[idx] = __half_as_ushort(hi);
+        base[plane + idx] = __half_as_ushort(__float2half_rn(v - __half2float(hi)));
+    } else {
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        base[idx] = __bfloat16_as_ushort(hi);
+        base[plane + idx] = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(hi)));
+    }
 }
 __device__ __forceinline__ float snake_beta(float v, float a, float ib) {
     const float s = fast_sin(a * v);
@@ -116,7 +136,7 @@ implicit_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc_full = make_idesc(BN), idesc_half = make_idesc(HALF);
+            const uint32_t idesc_full = make_idesc16(BN, a.f16), idesc_half = make_idesc16(HALF, a.f16);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
@@ -191,10 +211,8 @@ implicit_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 if (a.xo) a.xo[((long long)b * To + fo) * a.Cout + co] = val;
                 if (a.hl) {
                     const float hv = a.sa ? snake_beta(val, sa, sb) : val;
-                    const __nv_bfloat16 hi = __float2bfloat16_rn(hv);
                     const long long idx = ((long long)b * (a.Hout + To) + a.Hout + fo) * a.Cout + co;
-                    a.hl[idx] = hi;
-                    a.hl[plane + idx] = __float2bfloat16_rn(hv - __bfloat162float(hi));
+                    put_hilo16(reinterpret_cast<uint16_t*>(a.hl), plane, idx, hv, a.f16);
                 }
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }

@@ -22,6 +22,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace b2a {
 namespace st {
@@ -42,7 +43,7 @@ static tc::EncodeTiledFn encode_fn() {
 }
 
 // planar hi/lo activations [2][B][Ttot][C] bf16 -> rank-4 map {C, Ttot, B, 2}, box {64, 64, 1, 2}, 128-byte swizzle
-static CUtensorMap make_tmap_planes(const bf16* base, int C, long long Ttot, int B) {
+static CUtensorMap make_tmap_planes(const bf16* base, int C, long long Ttot, int B, int f16) {
     B2A_CHECK(C % 8 == 0 && ((uintptr_t)base & 15) == 0 && Ttot >= 1 && B >= 1, B2A_ERR_INVALID_INPUT,
               "TMA: activation planes must be 16-byte aligned with channels % 8 == 0");
     CUtensorMap m;
@@ -50,11 +51,41 @@ static CUtensorMap make_tmap_planes(const bf16* base, int C, long long Ttot, int
     const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)Ttot * C * 2, (cuuint64_t)B * Ttot * C * 2};
     const cuuint32_t box[4] = {(cuuint32_t)tc::BK, (cuuint32_t)ic::HALF, 1, 2};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
-    const CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(base), dims, strides, box, estr,
+    const CUresult r = encode_fn()(&m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(base), dims, strides, box, estr,
                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     B2A_CHECK(r == CUDA_SUCCESS, B2A_ERR_CUDA, "cuTensorMapEncodeTiled (rank 4) failed (" + std::to_string((int)r) + ")");
     return m;
+}
+
+// weights [rows, cols] 16-bit row-major, {64, 128} box, 128-byte swizzle (tc::make_tmap_bf16 with a selectable element type)
+static CUtensorMap make_tmap_w16(const void* base, long long rows, long long cols, int f16) {
+    B2A_CHECK(cols % 8 == 0 && ((uintptr_t)base & 15) == 0, B2A_ERR_INVALID_INPUT, "TMA: tensor must be 16-byte aligned with cols % 8 == 0");
+    CUtensorMap m;
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)tc::BM};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode_fn()(&m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B2A_CHECK(r == CUDA_SUCCESS, B2A_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return m;
+}
+// host-side hi / lo split in the operand format, as raw 16-bit words
+static inline void split16(float v, int f16, uint16_t& hi, uint16_t& lo) {
+    if (f16) {
+        const __half h = __float2half_rn(v);
+        hi = __half_as_ushort(h);
+        lo = __half_as_ushort(__float2half_rn(v - __half2float(h)));
+    } else {
+        const bf16 h = __float2bfloat16_rn(v);
+        hi = __bfloat16_as_ushort(h);
+        lo = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(h)));
+    }
+}
+static inline float join16(uint16_t hi, uint16_t lo, int f16) {
+    return f16 ? __half2float(__ushort_as_half(hi)) + __half2float(__ushort_as_half(lo))
+               : __bfloat162float(__ushort_as_bfloat16(hi)) + __bfloat162float(__ushort_as_bfloat16(lo));
 }
 
 // ----------------------------------------------------------------------------------------------- SIMT kernels
@@ -74,15 +105,13 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
     for (int i = 0; i < THREADS / 32; ++i) t += red[i];
     return t;
 }
-__device__ __forceinline__ void put_planes(bf16* base, long long plane, long long idx, float v) {
-    const bf16 hi = __float2bfloat16_rn(v);
-    base[idx] = hi;
-    base[plane + idx] = __float2bfloat16_rn(v - __bfloat162float(hi));
+__device__ __forceinline__ void put_planes(bf16* base, long long plane, long long idx, float v, int f16) {
+    ic::put_hilo16(reinterpret_cast<uint16_t*>(base), plane, idx, v, f16);
 }
 
 // codes [B, nq, T] -> planes [2][B*T][2*D2]: channels [0, D2) = sum of the semantic codebooks, [D2, 2*D2) = sum of the rest
 __global__ void rvq_gather_kernel(const int* __restrict__ codes, const float* __restrict__ emb /*[nq][bins][D2]*/, bf16* __restrict__ out,
-                                  int B, int T, int nq, int nq_model, int nsem, int bins, int D2) {
+                                  int B, int T, int nq, int nq_model, int nsem, int bins, int D2, int f16) {
     const long long n = blockIdx.x;
     const int b = (int)(n / T), t = (int)(n - (long long)b * T);
     const long long plane = (long long)B * T * 2 * D2;
@@ -94,21 +123,21 @@ __global__ void rvq_gather_kernel(const int* __restrict__ codes, const float* __
             const float v = emb[((long long)qi * bins + code) * D2 + c];
             if (qi < nsem) s0 += v; else s1 += v;
         }
-        put_planes(out, plane, n * 2 * D2 + c, s0);
-        put_planes(out, plane, n * 2 * D2 + D2 + c, s1);
+        put_planes(out, plane, n * 2 * D2 + c, s0, f16);
+        put_planes(out, plane, n * 2 * D2 + D2 + c, s1, f16);
     }
 }
 
 // RMSNorm over channels -> planes [2][N][C]   (DecoderRMSNorm :301-314: w * (x * rsqrt(mean(x^2) + eps)))
 constexpr int RN_THREADS = 128;
 __global__ void __launch_bounds__(RN_THREADS)
-rmsnorm_planes_kernel(const float* __restrict__ x, const float* __restrict__ w, bf16* __restrict__ out, long long N, int C, float eps) {
+rmsnorm_planes_kernel(const float* __restrict__ x, const float* __restrict__ w, bf16* __restrict__ out, long long N, int C, float eps, int f16) {
     __shared__ float red[RN_THREADS / 32];
     const long long n = blockIdx.x;
     float ss = 0.f;
     for (int c = threadIdx.x; c < C; c += RN_THREADS) { const float v = x[n * C + c]; ss += v * v; }
     const float r = rsqrtf(block_sum<RN_THREADS>(ss, red) / (float)C + eps);
-    for (int c = threadIdx.x; c < C; c += RN_THREADS) put_planes(out, N * C, n * C + c, w[c] * (x[n * C + c] * r));
+    for (int c = threadIdx.x; c < C; c += RN_THREADS) put_planes(out, N * C, n * C + c, w[c] * (x[n * C + c] * r), f16);
 }
 
 // rotate-half RoPE on q (in place) and k (into the cache), v copied into the cache.  qkv [N, (nh + 2 nkv) * hd] fp32.
@@ -145,7 +174,7 @@ constexpr int AT_WARPS = 4;
 template <int DPL>
 __global__ void __launch_bounds__(AT_WARPS * 32)
 attn_kernel(const float* __restrict__ qkv, const float* __restrict__ Kc, const float* __restrict__ Vc, bf16* __restrict__ out,
-            int B, int T, int pos0, int nh, int nkv, int cap, float scale) {
+            int B, int T, int pos0, int nh, int nkv, int cap, float scale, int f16) {
     constexpr int HD = DPL * 32;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t = blockIdx.x * AT_WARPS + warp, h = blockIdx.y, b = blockIdx.z;
@@ -193,24 +222,24 @@ attn_kernel(const float* __restrict__ qkv, const float* __restrict__ Kc, const f
     const float inv = 1.0f / l;
     const long long N = (long long)B * T;
 #pragma unroll
-    for (int d = 0; d < DPL; ++d) put_planes(out, N * nh * HD, n * nh * HD + h * HD + lane * DPL + d, acc[d] * inv);
+    for (int d = 0; d < DPL; ++d) put_planes(out, N * nh * HD, n * nh * HD + h * HD + lane * DPL + d, acc[d] * inv, f16);
 }
 
 // gu [N, 2I] (gate | up) -> silu(gate) * up as planes [2][N][I]     (DecoderMLP :412-414)
-__global__ void swiglu_planes_kernel(const float* __restrict__ gu, bf16* __restrict__ out, long long N, int I) {
+__global__ void swiglu_planes_kernel(const float* __restrict__ gu, bf16* __restrict__ out, long long N, int I, int f16) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N * I) return;
     const long long n = i / I;
     const int c = (int)(i - n * I);
     const float g = gu[n * 2 * I + c], u = gu[n * 2 * I + I + c];
-    put_planes(out, N * I, i, g / (1.0f + __expf(-g)) * u);
+    put_planes(out, N * I, i, g / (1.0f + __expf(-g)) * u, f16);
 }
 
 // causal depthwise conv (k taps, history from `st` [B, k-1, C]) -> LayerNorm(eps) -> planes [2][B*T][C]
 constexpr int DL_THREADS = 256, DL_MAXV = 4;    // channels <= 1024
 __global__ void __launch_bounds__(DL_THREADS)
 dw_ln_kernel(const float* __restrict__ x, const float* __restrict__ st, const float* __restrict__ dw_w /*[C, k]*/, const float* __restrict__ dw_b,
-             const float* __restrict__ ln_w, const float* __restrict__ ln_b, bf16* __restrict__ out, int B, int T, int C, int k, float eps) {
+             const float* __restrict__ ln_w, const float* __restrict__ ln_b, bf16* __restrict__ out, int B, int T, int C, int k, float eps, int f16) {
     __shared__ float red[DL_THREADS / 32];
     const long long n = blockIdx.x;
     const int b = (int)(n / T), t = (int)(n - (long long)b * T), H = k - 1;
@@ -243,7 +272,7 @@ dw_ln_kernel(const float* __restrict__ x, const float* __restrict__ st, const fl
 #pragma unroll
     for (int j = 0; j < DL_MAXV; ++j) {
         const int c = threadIdx.x + j * DL_THREADS;
-        if (c < C) put_planes(out, N * C, n * C + c, (v[j] - mean) * r * ln_w[c] + ln_b[c]);
+        if (c < C) put_planes(out, N * C, n * C + c, (v[j] - mean) * r * ln_w[c] + ln_b[c], f16);
     }
 }
 
@@ -330,20 +359,17 @@ struct IW {                       // implicit-conv weight: [M][taps][cblocks * 6
                 memcpy(&g[(size_t)m * K + (size_t)j * cb * tc::BK], &W[((size_t)m * taps + j) * Cin], (size_t)Cin * sizeof(float));
         return g;
     }
-    void build(const std::vector<float>& W /*[M][taps][Cin]*/, int M_, int taps_, int Cin_) {
+    void build(const std::vector<float>& W /*[M][taps][Cin]*/, int M_, int taps_, int Cin_, int f16) {
         M = M_; taps = taps_; Cin = Cin_; cblocks = cdiv(Cin, tc::BK);
         const size_t K = (size_t)taps * cblocks * tc::BK;
         const std::vector<float> g = pad_k(W, M, taps, Cin);
-        std::vector<bf16> h(g.size()), l(g.size());
-        for (size_t i = 0; i < g.size(); ++i) {
-            h[i] = __float2bfloat16_rn(g[i]);
-            l[i] = __float2bfloat16_rn(g[i] - __bfloat162float(h[i]));
-        }
-        hi.upload(h.data(), h.size());
-        lo.upload(l.data(), l.size());
+        std::vector<uint16_t> h(g.size()), l(g.size());
+        for (size_t i = 0; i < g.size(); ++i) split16(g[i], f16, h[i], l[i]);
+        hi.upload(reinterpret_cast<const bf16*>(h.data()), h.size());
+        lo.upload(reinterpret_cast<const bf16*>(l.data()), l.size());
         B2A_CUDA(cudaDeviceSynchronize());
-        th = tc::make_tmap_bf16(hi.p, M, (long long)K, tc::BM);
-        tl = tc::make_tmap_bf16(lo.p, M, (long long)K, tc::BM);
+        th = make_tmap_w16(hi.p, M, (long long)K, f16);
+        tl = make_tmap_w16(lo.p, M, (long long)K, f16);
     }
     void set_bias(const std::vector<float>& b) { bias.upload(b.data(), b.size()); has_bias = true; B2A_CUDA(cudaDeviceSynchronize()); }
 };
@@ -369,6 +395,7 @@ struct b2a_speech_tokenizer {
     cudaStream_t stream = nullptr;
     int num_sms = 148;
     int total_up = 1, D2 = 0, Mqkv = 0;
+    int use_f16 = 0;              // B2A_ST_FP16=1: fp16 hi/lo operands instead of bf16 hi/lo (ic::Args::f16)
     // weights
     DBuf<float> emb;              // [nq][bins][D2] usage-normalised codebooks
     IW rvq_proj, pre_conv, in_proj, out_proj, dec0;
@@ -411,11 +438,11 @@ struct b2a_speech_tokenizer {
         up(s.a, a); up(s.ib, ib);
     }
     void load_conv(IW& w, const TensorTable& tt, const std::string& p, int out, int k, int in, bool bias = true) {
-        w.build(conv_w(tt, p + ".weight", out, k, in), out, k, in);
+        w.build(conv_w(tt, p + ".weight", out, k, in), out, k, in, use_f16);
         if (bias) w.set_bias(tt.f32(p + ".bias", out));
     }
     void load_linear(IW& w, const TensorTable& tt, const std::string& p, int out, int in, bool bias) {
-        w.build(tt.f32(p + ".weight", (int64_t)out * in), out, 1, in);
+        w.build(tt.f32(p + ".weight", (int64_t)out * in), out, 1, in, use_f16);
         if (bias) w.set_bias(tt.f32(p + ".bias", out));
     }
 
@@ -435,6 +462,7 @@ struct b2a_speech_tokenizer {
                   B2A_ERR_INVALID_INPUT, "speech tokenizer: decoder_dim / 2^blocks must be a multiple of 8 and <= 128");
         B2A_CHECK(c.max_batch >= 1 && c.max_cache_frames >= 1, B2A_ERR_INVALID_INPUT, "speech tokenizer: max_batch / max_cache_frames must be positive");
         require_device(dev);
+        { const char* e = getenv("B2A_ST_FP16"); use_f16 = (e && e[0] == '1') ? 1 : 0; }
         B2A_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         B2A_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
         B2A_CUDA(cudaFuncSetAttribute(ic::implicit_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ic::SMEM_BYTES));
@@ -461,7 +489,7 @@ struct b2a_speech_tokenizer {
                 memcpy(&w[(size_t)o * 2 * D2], &w1[(size_t)o * D2], (size_t)D2 * sizeof(float));
                 memcpy(&w[(size_t)o * 2 * D2 + D2], &w2[(size_t)o * D2], (size_t)D2 * sizeof(float));
             }
-            rvq_proj.build(w, cbd, 1, 2 * D2);
+            rvq_proj.build(w, cbd, 1, 2 * D2, use_f16);
         }
         load_conv(pre_conv, tt, "pre_conv.conv", L, 3, cbd);
         st_pre.H = 2; st_pre.C = cbd;
@@ -484,7 +512,7 @@ struct b2a_speech_tokenizer {
                 memcpy(w.data(), q.data(), q.size() * sizeof(float));
                 memcpy(w.data() + q.size(), k.data(), k.size() * sizeof(float));
                 memcpy(w.data() + q.size() + k.size(), v.data(), v.size() * sizeof(float));
-                T.qkv.build(w, Mqkv, 1, Hd);
+                T.qkv.build(w, Mqkv, 1, Hd, use_f16);
                 if (ab) {
                     std::vector<float> bq = tt.f32(p + "self_attn.q_proj.bias", nh * hd), bk = tt.f32(p + "self_attn.k_proj.bias", nkv * hd),
                                        bv = tt.f32(p + "self_attn.v_proj.bias", nkv * hd);
@@ -497,7 +525,7 @@ struct b2a_speech_tokenizer {
             {
                 std::vector<float> g = tt.f32(p + "mlp.gate_proj.weight", (int64_t)I * Hd), u = tt.f32(p + "mlp.up_proj.weight", (int64_t)I * Hd);
                 g.insert(g.end(), u.begin(), u.end());
-                T.gu.build(g, 2 * I, 1, Hd);
+                T.gu.build(g, 2 * I, 1, Hd, use_f16);
             }
             load_linear(T.down, tt, p + "mlp.down_proj", Hd, I, false);
             up(T.ln1, tt.f32(p + "input_layernorm.weight", Hd));
@@ -513,7 +541,7 @@ struct b2a_speech_tokenizer {
             U.factor = c.upsampling_ratios[i];
             B2A_CHECK(U.factor >= 1 && U.factor <= 16, B2A_ERR_INVALID_INPUT, "speech tokenizer: bad upsampling ratio");
             total_up *= U.factor;
-            U.ct.build(convt_w(conv_w(tt, p + "0.conv.weight", L, U.factor, L), L, U.factor, L, U.factor), U.factor * L, 1, L);
+            U.ct.build(convt_w(conv_w(tt, p + "0.conv.weight", L, U.factor, L), L, U.factor, L, U.factor), U.factor * L, 1, L, use_f16);
             U.ct.set_bias(tt.f32(p + "0.conv.bias", L));
             up(U.dw_w, tt.f32(p + "1.dwconv.conv.weight", (int64_t)L * 7));
             up(U.dw_b, tt.f32(p + "1.dwconv.conv.bias", L));
@@ -537,7 +565,7 @@ struct b2a_speech_tokenizer {
             Bk.cin = dd >> b; Bk.cout = dd >> (b + 1);
             B2A_CHECK(Bk.cin % 8 == 0 && Bk.cout % 8 == 0, B2A_ERR_INVALID_INPUT, "speech tokenizer: decoder channels must be multiples of 8");
             load_snake(Bk.sn, tt, p + "0", Bk.cin);
-            Bk.ct.build(convt_w(conv_w(tt, p + "1.conv.weight", Bk.cout, 2 * Bk.rate, Bk.cin), Bk.cout, 2 * Bk.rate, Bk.cin, Bk.rate), Bk.rate * Bk.cout, 2, Bk.cin);
+            Bk.ct.build(convt_w(conv_w(tt, p + "1.conv.weight", Bk.cout, 2 * Bk.rate, Bk.cin), Bk.cout, 2 * Bk.rate, Bk.cin, Bk.rate), Bk.rate * Bk.cout, 2, Bk.cin, use_f16);
             Bk.ct.set_bias(tt.f32(p + "1.conv.bias", Bk.cout));
             Bk.st.H = 1; Bk.st.C = Bk.cin;
             const int dil[3] = {1, 3, 9};
@@ -605,7 +633,8 @@ struct b2a_speech_tokenizer {
         a.Cout = W.M / a.up;
         a.t_tiles = cdiv(a.T, ic::HALF);
         a.bias = W.has_bias ? W.bias.p : nullptr;
-        const CUtensorMap tb = make_tmap_planes(in, W.Cin, in_frames, a.B);
+        a.f16 = use_f16;
+        const CUtensorMap tb = make_tmap_planes(in, W.Cin, in_frames, a.B, use_f16);
         const long long tiles = (long long)a.B * a.t_tiles * a.m_tiles;
         launch_pdl(ic::implicit_conv_kernel, dim3((unsigned)std::min<long long>(num_sms, tiles)), dim3(ic::IC_THREADS), ic::SMEM_BYTES, s,
                    W.th, W.tl, tb, a);
@@ -626,9 +655,9 @@ struct b2a_speech_tokenizer {
         const dim3 grid(cdiv(T, AT_WARPS), cfg.num_attention_heads, B), block(AT_WARPS * 32);
         const float scale = 1.0f / sqrtf((float)cfg.head_dim);
         const int nh = cfg.num_attention_heads, nkv = cfg.num_key_value_heads, cap = cfg.max_cache_frames;
-        if (cfg.head_dim == 32) attn_kernel<1><<<grid, block, 0, s>>>(Q.p, L.K.p, L.V.p, out, B, T, cache_len, nh, nkv, cap, scale);
-        else if (cfg.head_dim == 64) attn_kernel<2><<<grid, block, 0, s>>>(Q.p, L.K.p, L.V.p, out, B, T, cache_len, nh, nkv, cap, scale);
-        else attn_kernel<4><<<grid, block, 0, s>>>(Q.p, L.K.p, L.V.p, out, B, T, cache_len, nh, nkv, cap, scale);
+        if (cfg.head_dim == 32) attn_kernel<1><<<grid, block, 0, s>>>(Q.p, L.K.p, L.V.p, out, B, T, cache_len, nh, nkv, cap, scale, use_f16);
+        else if (cfg.head_dim == 64) attn_kernel<2><<<grid, block, 0, s>>>(Q.p, L.K.p, L.V.p, out, B, T, cache_len, nh, nkv, cap, scale, use_f16);
+        else attn_kernel<4><<<grid, block, 0, s>>>(Q.p, L.K.p, L.V.p, out, B, T, cache_len, nh, nkv, cap, scale, use_f16);
         count_launch();
     }
 
@@ -662,7 +691,7 @@ struct b2a_speech_tokenizer {
         }
         // 1. codebook gathers + both output projections                                    (:112-119)
         rvq_gather_kernel<<<(unsigned)N, 128, 0, s>>>(dcodes, emb.p, planes(P0, B, T, 2 * D2), B, T, nq, c.num_quantizers, c.num_semantic_quantizers,
-                                                     c.codebook_size, D2);
+                                                     c.codebook_size, D2, use_f16);
         count_launch();
         { ic::Args a{}; a.B = B; a.T = T; a.hl = planes(P1, B, T + 2, cbd); a.Hout = 2; conv(rvq_proj, P0.p, T, a, s); }
         // 2. pre_conv (k3 causal) -> input_proj                                             (:929-931, :454)
@@ -671,21 +700,21 @@ struct b2a_speech_tokenizer {
         { ic::Args a{}; a.B = B; a.T = T; a.xo = Xh.p; conv(in_proj, P0.p, T, a, s); }
         // 3. transformer layers over the KV cache                                           (:419-428, :473-476)
         for (auto& Ly : layers) {
-            rmsnorm_planes_kernel<<<(unsigned)N, RN_THREADS, 0, s>>>(Xh.p, Ly.ln1.p, planes(P0, B, T, Hd), N, Hd, c.rms_norm_eps);
+            rmsnorm_planes_kernel<<<(unsigned)N, RN_THREADS, 0, s>>>(Xh.p, Ly.ln1.p, planes(P0, B, T, Hd), N, Hd, c.rms_norm_eps, use_f16);
             count_launch();
             { ic::Args a{}; a.B = B; a.T = T; a.xo = Q.p; conv(Ly.qkv, P0.p, T, a, s); }
             rope_cache_kernel<<<(unsigned)N, 256, 0, s>>>(Q.p, Ly.K.p, Ly.V.p, inv_freq.p, T, cache_len, nh, c.num_key_value_heads, hd, c.max_cache_frames);
             count_launch();
             attention(Ly, B, T, planes(P1, B, T, nh * hd), s);
             { ic::Args a{}; a.B = B; a.T = T; a.xo = Xh.p; a.add = 1; a.gamma = Ly.sc_attn.p; conv(Ly.o, P1.p, T, a, s); }
-            rmsnorm_planes_kernel<<<(unsigned)N, RN_THREADS, 0, s>>>(Xh.p, Ly.ln2.p, planes(P0, B, T, Hd), N, Hd, c.rms_norm_eps);
+            rmsnorm_planes_kernel<<<(unsigned)N, RN_THREADS, 0, s>>>(Xh.p, Ly.ln2.p, planes(P0, B, T, Hd), N, Hd, c.rms_norm_eps, use_f16);
             count_launch();
             { ic::Args a{}; a.B = B; a.T = T; a.xo = Q.p; conv(Ly.gu, P0.p, T, a, s); }
-            swiglu_planes_kernel<<<(unsigned)cdiv(N * I, 256), 256, 0, s>>>(Q.p, planes(P1, B, T, I), N, I);
+            swiglu_planes_kernel<<<(unsigned)cdiv(N * I, 256), 256, 0, s>>>(Q.p, planes(P1, B, T, I), N, I, use_f16);
             count_launch();
             { ic::Args a{}; a.B = B; a.T = T; a.xo = Xh.p; a.add = 1; a.gamma = Ly.sc_mlp.p; conv(Ly.down, P1.p, T, a, s); }
         }
-        rmsnorm_planes_kernel<<<(unsigned)N, RN_THREADS, 0, s>>>(Xh.p, final_norm.p, planes(P0, B, T, Hd), N, Hd, c.rms_norm_eps);
+        rmsnorm_planes_kernel<<<(unsigned)N, RN_THREADS, 0, s>>>(Xh.p, final_norm.p, planes(P0, B, T, Hd), N, Hd, c.rms_norm_eps, use_f16);
         count_launch();
         { ic::Args a{}; a.B = B; a.T = T; a.hl = planes(P1, B, T, L); conv(out_proj, P0.p, T, a, s); }
         // 4. upsample layers: transposed conv (k = stride) + ConvNeXt                       (:758-775)
@@ -697,7 +726,7 @@ struct b2a_speech_tokenizer {
             UpLayer& U = ups[i];
             { ic::Args a{}; a.B = B; a.T = (int)Tc; a.up = U.factor; a.xo = Xc.p; conv(U.ct, cur, Hcur + Tc, a, s); }
             Tc *= U.factor;
-            dw_ln_kernel<<<(unsigned)(B * Tc), DL_THREADS, 0, s>>>(Xc.p, U.st.s[parity].p, U.dw_w.p, U.dw_b.p, U.ln_w.p, U.ln_b.p, cur, B, (int)Tc, L, 7, 1e-6f);
+            dw_ln_kernel<<<(unsigned)(B * Tc), DL_THREADS, 0, s>>>(Xc.p, U.st.s[parity].p, U.dw_w.p, U.dw_b.p, U.ln_w.p, U.ln_b.p, cur, B, (int)Tc, L, 7, 1e-6f, use_f16);
             count_launch();
             update_f32(Xc.p, U.st, B, Tc, s);
             { ic::Args a{}; a.B = B; a.T = (int)Tc; a.gelu = 1; a.hl = other; conv(U.pw1, cur, Tc, a, s); }
@@ -861,7 +890,7 @@ int32_t b2a_speech_tokenizer_debug_layout(const float* w, int32_t out, int32_t k
 //   xo [B][T*up][M/up] in/out or null, hl_out [B][Hout + T*up][M/up] (hi + lo recombined; frames below Hout come back 0) or null.
 int32_t b2a_implicit_conv_test(const float* w, int32_t M, int32_t taps, int32_t Cin, const float* x, int32_t B, int32_t Ttot, int32_t T,
                                int32_t dil, int32_t shift0, int32_t up, const float* bias, const float* gamma, int32_t gelu, int32_t add,
-                               int32_t bias_twice_t0, const float* sa, const float* sb, int32_t Hout, float* xo, float* hl_out) {
+                               int32_t bias_twice_t0, const float* sa, const float* sb, int32_t Hout, int32_t fp16, float* xo, float* hl_out) {
     return guarded([&] {
         B2A_CHECK(w && x && M >= 1 && taps >= 1 && Cin >= 8 && Cin % 8 == 0 && B >= 1 && Ttot >= 1 && T >= 1 && dil >= 1 && shift0 >= 0 && up >= 1 &&
                       M % up == 0 && (M / up) % 8 == 0 && Hout >= 0 && (xo || hl_out) && (!add || xo) && ((sa == nullptr) == (sb == nullptr)),
@@ -874,26 +903,23 @@ int32_t b2a_implicit_conv_test(const float* w, int32_t M, int32_t taps, int32_t 
         const int Cout = M / up;
         const long long To = (long long)T * up;
         IW W;
-        W.build(std::vector<float>(w, w + (size_t)M * taps * Cin), M, taps, Cin);
+        W.build(std::vector<float>(w, w + (size_t)M * taps * Cin), M, taps, Cin, fp16);
         const size_t nx = (size_t)B * Ttot * Cin, no = (size_t)B * To * Cout, nh = (size_t)B * (Hout + To) * Cout;
-        std::vector<bf16> xp(2 * nx);
-        for (size_t i = 0; i < nx; ++i) {
-            xp[i] = __float2bfloat16_rn(x[i]);
-            xp[nx + i] = __float2bfloat16_rn(x[i] - __bfloat162float(xp[i]));
-        }
+        std::vector<uint16_t> xp(2 * nx);
+        for (size_t i = 0; i < nx; ++i) split16(x[i], fp16, xp[i], xp[nx + i]);
         DBuf<bf16> dx, dh;
         DBuf<float> dxo, dbias, dgamma, dsa, dsb;
-        dx.upload(xp.data(), xp.size());
+        dx.upload(reinterpret_cast<const bf16*>(xp.data()), xp.size());
         ic::Args a{};
         a.M = M; a.m_tiles = cdiv(M, tc::BM); a.taps = taps; a.cblocks = W.cblocks; a.dil = dil; a.shift0 = shift0;
-        a.B = B; a.T = T; a.t_tiles = cdiv(T, ic::HALF); a.Cout = Cout; a.up = up; a.gelu = gelu; a.add = add; a.bias_twice_t0 = bias_twice_t0; a.Hout = Hout;
+        a.B = B; a.T = T; a.t_tiles = cdiv(T, ic::HALF); a.Cout = Cout; a.up = up; a.gelu = gelu; a.add = add; a.bias_twice_t0 = bias_twice_t0; a.Hout = Hout; a.f16 = fp16;
         if (bias) { dbias.upload(bias, Cout); a.bias = dbias.p; }
         if (gamma) { dgamma.upload(gamma, Cout); a.gamma = dgamma.p; }
         if (sa) { dsa.upload(sa, Cout); dsb.upload(sb, Cout); a.sa = dsa.p; a.sb = dsb.p; }
         if (xo) { dxo.upload(xo, no); a.xo = dxo.p; }
         if (hl_out) { dh.alloc(2 * nh); B2A_CUDA(cudaMemset(dh.p, 0, 2 * nh * sizeof(bf16))); a.hl = dh.p; }
         B2A_CUDA(cudaDeviceSynchronize());
-        const CUtensorMap tb = make_tmap_planes(dx.p, Cin, Ttot, B);
+        const CUtensorMap tb = make_tmap_planes(dx.p, Cin, Ttot, B, fp16);
         const long long tiles = (long long)B * a.t_tiles * a.m_tiles;
         launch_pdl(ic::implicit_conv_kernel, dim3((unsigned)std::min<long long>(num_sms, tiles)), dim3(ic::IC_THREADS), ic::SMEM_BYTES, (cudaStream_t)0,
                    W.th, W.tl, tb, a);
@@ -901,9 +927,9 @@ int32_t b2a_implicit_conv_test(const float* w, int32_t M, int32_t taps, int32_t 
         B2A_CUDA(cudaDeviceSynchronize());
         if (xo) B2A_CUDA(cudaMemcpy(xo, dxo.p, no * sizeof(float), cudaMemcpyDeviceToHost));
         if (hl_out) {
-            std::vector<bf16> hp(2 * nh);
-            B2A_CUDA(cudaMemcpy(hp.data(), dh.p, 2 * nh * sizeof(bf16), cudaMemcpyDeviceToHost));
-            for (size_t i = 0; i < nh; ++i) hl_out[i] = __bfloat162float(hp[i]) + __bfloat162float(hp[nh + i]);
+            std::vector<uint16_t> hp(2 * nh);
+            B2A_CUDA(cudaMemcpy(hp.data(), dh.p, 2 * nh * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < nh; ++i) hl_out[i] = join16(hp[i], hp[nh + i], fp16);
         }
     });
 }

@@ -38,14 +38,18 @@ def implicit_conv(Wg, cin, X, T, *, dil=1, shift0=0, up=1, bias=None, gamma=None
             hl[:, Hout + fo, :] = hv
 
 
+OPERAND = "bf16"          # "fp16": what Args::f16 / B2A_ST_FP16=1 selects
+
+
 def _bf16(x):
     import torch
-    return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(torch.bfloat16).to(torch.float32).numpy().astype(np.float64)
+    kind = torch.bfloat16 if OPERAND == "bf16" else torch.float16
+    return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(kind).to(torch.float32).numpy().astype(np.float64)
 
 
 def implicit_conv_hilo(Wg, cin, X, T, *, dil=1, shift0=0, up=1, bias=None, gamma=None, gelu=False, add=False, bias_twice_t0=False,
                        xo=None, hl=None, Hout=0, sa=None, sb=None):
-    """Same contract with the kernel's ARITHMETIC: weights and activations as bf16 hi + lo, the three tensor-core products
+    """Same contract with the kernel's ARITHMETIC: weights and activations as bf16 (or, with OPERAND = "fp16", fp16) hi + lo, the three tensor-core products
     Wh*Xh + Wh*Xl + Wl*Xh (Wl*Xl dropped), fp32 accumulator / epilogue values, hi/lo planes on output.  Used to predict the
     numerical error of the CUDA path before it has run."""
     Wh = _bf16(Wg); Wl = _bf16(Wg - Wh)

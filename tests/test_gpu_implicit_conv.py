@@ -11,7 +11,7 @@ pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("B2A_EXPERIMENT
                                                   reason="experimental N1 path: set B2A_EXPERIMENTAL_N1=1")]
 
 
-def run(b2a, w, x, T, *, dil=1, shift0=0, up=1, bias=None, gamma=None, gelu=False, add=None, twice=False, sa=None, sb=None, Hout=0, want_xo=True, want_hl=True):
+def run(b2a, w, x, T, *, dil=1, shift0=0, up=1, bias=None, gamma=None, gelu=False, add=None, twice=False, sa=None, sb=None, Hout=0, want_xo=True, want_hl=True, fp16=0):
     f = b2a._ffi
     M, taps, cin = w.shape
     B, Ttot, _ = x.shape
@@ -21,7 +21,7 @@ def run(b2a, w, x, T, *, dil=1, shift0=0, up=1, bias=None, gamma=None, gelu=Fals
     hl = np.zeros((B, Hout + T * up, cout), np.float32) if want_hl else None
     w32, x32, b32, g32, sa32, sb32 = c32(w), c32(x), c32(bias), c32(gamma), c32(sa), c32(sb)
     f.check(f.lib().b2a_implicit_conv_test(f.ptr(w32), M, taps, cin, f.ptr(x32), B, Ttot, T, dil, shift0, up, f.ptr(b32), f.ptr(g32), int(gelu),
-                                           int(add is not None), int(twice), f.ptr(sa32), f.ptr(sb32), Hout, f.ptr(xo), f.ptr(hl)))
+                                           int(add is not None), int(twice), f.ptr(sa32), f.ptr(sb32), Hout, fp16, f.ptr(xo), f.ptr(hl)))
     return xo, hl
 
 
@@ -87,3 +87,17 @@ def test_gelu_gamma_residual(b2a):
     xo, hl = run(b2a, w, x, T, bias=bias, gamma=gamma, add=res)
     rx, rh = model(w.astype(np.float32), x.astype(np.float32), T, bias=bias.astype(np.float32), gamma=gamma.astype(np.float32), add=res.astype(np.float32))
     assert close(xo, rx) and close(hl, rh)
+
+
+def test_fp16_operand_pairs(b2a):
+    """Same contract with fp16 hi/lo operands (Args::f16, B2A_ST_FP16=1): 22 mantissa bits per operand instead of 16."""
+    rng = np.random.default_rng(9)
+    w = rng.standard_normal((192, 7, 96)) / np.sqrt(7 * 96)
+    x = rng.standard_normal((2, 54 + 130, 96)) * 3.0
+    bias = rng.standard_normal(192)
+    xo16, hl16 = run(b2a, w, x, 130, dil=9, bias=bias, fp16=1)
+    xob, _ = run(b2a, w, x, 130, dil=9, bias=bias, fp16=0)
+    rx, rh = model(w.astype(np.float32), x.astype(np.float32), 130, dil=9, bias=bias.astype(np.float32))
+    e16, eb = np.abs(xo16 - rx).max(), np.abs(xob - rx).max()
+    assert e16 < 2e-6 * max(1.0, np.abs(rx).max()) and close(hl16, rh, 2e-6)
+    assert e16 < eb                                               # and it is the more accurate of the two formats

@@ -249,20 +249,22 @@ def test_data_flow_model_matches_oracle_streaming(b2a, chunks):
         s += n
 
 
-def test_predicted_numerics_of_the_hilo_arithmetic_stay_inside_the_parity_tolerance(b2a, monkeypatch):
+@pytest.mark.parametrize("operand,lo,hi", [("bf16", 1e-6, 6e-4), ("fp16", 1e-7, 1.5e-4)])
+def test_predicted_numerics_of_the_hilo_arithmetic_stay_inside_the_parity_tolerance(b2a, monkeypatch, operand, lo, hi):
     """The same data-flow model with the kernel's arithmetic (bf16 hi/lo operands, three products, fp32 accumulation): the error
     it predicts against the float64 oracle must leave room under the 1e-3 parity bar of the GPU tests.  (Measured here: about
-    3e-4 of the peak at this geometry and at the shipped one; plain fp32 arithmetic gives 3e-6, so the 16-bit operand split
-    is the whole budget.)"""
+    3e-4 of the peak at this geometry and at the shipped one with bf16 pairs, 6e-5 with fp16 pairs -- Args::f16, B2A_ST_FP16=1 --;
+    plain fp32 arithmetic gives 3e-6, so the operand split is the whole budget.)"""
     import sys
     monkeypatch.setattr(sys.modules[__name__], "implicit_conv", implicit_conv_model.implicit_conv_hilo)
+    monkeypatch.setattr(implicit_conv_model, "OPERAND", operand)
     cfg = oc.mid_config()
     W = oc.init_weights(cfg, 5)
     codes = np.random.default_rng(1).integers(0, cfg.codebook_size, (1, cfg.num_quantizers, 12))
     y = machine_step(Machine(b2a, cfg, W, 1), codes)
     ref = oc.SpeechTokenizerDecoder(cfg, W)(codes)[:, 0].numpy()
     err = np.abs(y - ref).max() / np.abs(ref).max()
-    assert 1e-6 < err < 6e-4, err
+    assert lo < err < hi, err
 
 
 def test_library_weight_layouts(b2a):
