@@ -14,6 +14,7 @@ sys.path.insert(0, str(ROOT))
 from oracle import dsp, llama, snac  # noqa: E402
 from oracle import encodec as oe  # noqa: E402
 from oracle import qwen3_tts_codec as oq  # noqa: E402
+from oracle import qwen3_tts as ot  # noqa: E402
 from oracle import vocos as ov  # noqa: E402
 from oracle import whisper as ow  # noqa: E402
 
@@ -124,12 +125,36 @@ def qwen3_codec():
                         stream_boundary=st[:, 7 * up - 32: 8 * up + 32].astype(np.float32), stream_stats=stats(st), shape=np.array(full.shape))
 
 
+def qwen3_talker_config():
+    """The geometry of the reference's own Qwen3-TTS tests (Tests/MLXAudioTTSTests.swift:615-687) with 4 code groups."""
+    cp = ot.CodePredictorConfig(vocab_size=2048, hidden_size=32, intermediate_size=64, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,
+                                head_dim=8, num_code_groups=4)
+    return ot.TalkerConfig(vocab_size=3072, hidden_size=32, intermediate_size=64, num_hidden_layers=3, num_attention_heads=4, num_key_value_heads=2,
+                           head_dim=8, num_code_groups=4, text_hidden_size=48, text_vocab_size=200, codec_eos_token_id=2150, mrope_section=(2, 1, 1),
+                           code_predictor=cp)
+
+
+QWEN3_CHAT_IDS = [151, 12, 13, 40, 41, 42, 43, 44, 45, 152, 14, 151, 12, 13]
+
+
+def qwen3_talker():
+    """Qwen3-TTS talker + code predictor (row N1): prompt embeddings, first-step logits and 5 greedy frames (T = 0: no RNG involved)."""
+    cfg = qwen3_talker_config()
+    W = ot.init_weights(cfg, 3)
+    inp, trail, pad = ot.prepare_generation_inputs(cfg, W, QWEN3_CHAT_IDS, tts_bos=160, tts_eos=161, tts_pad=162, language_id=2160)
+    logits, hidden = ot.Talker(cfg, W)(inp, None)
+    codes = ot.generate_codes(cfg, W, inp, trail, pad, max_tokens=5, temperature=0.0, repetition_penalty=1.05, stop_on_eos=False)
+    np.savez_compressed(OUT / "qwen3_talker.npz", input_embeds_stats=stats(inp.numpy()), input_shape=np.array(inp.shape),
+                        first_logits_stats=stats(logits[0, -1].numpy()), first_logits_top=np.argsort(-logits[0, -1].numpy())[:8].astype(np.int32),
+                        codes=codes.numpy().astype(np.int32))
+
+
 if __name__ == "__main__":
     import argparse
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default=None, help="regenerate a single fixture (mel | snac | llama | whisper | codecs | qwen3_codec)")
+    ap.add_argument("--only", default=None, help="regenerate a single fixture (mel | snac | llama | whisper | codecs | qwen3_codec | qwen3_talker)")
     only = ap.parse_args().only
-    for name, fn in (("mel", mel), ("snac", snac_small), ("llama", llama_tiny), ("whisper", whisper_tiny), ("codecs", codecs_small), ("qwen3_codec", qwen3_codec)):
+    for name, fn in (("mel", mel), ("snac", snac_small), ("llama", llama_tiny), ("whisper", whisper_tiny), ("codecs", codecs_small), ("qwen3_codec", qwen3_codec), ("qwen3_talker", qwen3_talker)):
         if only is None or only == name:
             fn()
     for f in sorted(OUT.glob("*.npz")):

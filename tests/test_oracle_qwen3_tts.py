@@ -202,3 +202,24 @@ def test_filter_logits_matches_transformers_warpers():
             assert torch.equal(torch.isfinite(ours), torch.isfinite(ref)), (top_k, top_p, min_p, trial)
             keep = torch.isfinite(ref)
             assert torch.allclose(ours[keep], ref[keep])
+
+
+def test_oracle_reproduces_committed_talker_golden():
+    """tests/golden/qwen3_talker.npz (make_golden.py --only qwen3_talker): prompt embeddings, first-step logits and five greedy frames of a
+    small talker + code predictor -- the fixture a CUDA talker will be compared with."""
+    import importlib.util
+    from conftest import GOLDEN
+    spec = importlib.util.spec_from_file_location("make_golden", GOLDEN / "make_golden.py")
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    g = np.load(GOLDEN / "qwen3_talker.npz")
+    cfg = mg.qwen3_talker_config()
+    W = oq.init_weights(cfg, 3)
+    inp, trail, pad = oq.prepare_generation_inputs(cfg, W, mg.QWEN3_CHAT_IDS, tts_bos=160, tts_eos=161, tts_pad=162, language_id=2160)
+    assert tuple(g["input_shape"]) == tuple(inp.shape) and np.allclose(mg.stats(inp.numpy()), g["input_embeds_stats"], rtol=1e-9, atol=1e-12)
+    logits, _ = oq.Talker(cfg, W)(inp, None)
+    assert np.array_equal(np.argsort(-logits[0, -1].numpy())[:8], g["first_logits_top"])
+    assert np.allclose(mg.stats(logits[0, -1].numpy()), g["first_logits_stats"], rtol=1e-9, atol=1e-12)
+    codes = oq.generate_codes(cfg, W, inp, trail, pad, max_tokens=5, temperature=0.0, repetition_penalty=1.05, stop_on_eos=False)
+    assert np.array_equal(codes.numpy(), g["codes"])
+    assert codes.shape == (5, 4) and int(codes[:, 0].max()) < 3072 - 1024           # the special-token block is suppressed (:383-385)
