@@ -137,10 +137,15 @@ def qwen3_talker_config():
 QWEN3_CHAT_IDS = [151, 12, 13, 40, 41, 42, 43, 44, 45, 152, 14, 151, 12, 13]
 
 
+def qwen3_talker_weights(cfg):
+    """bf16-VALUED weights (what a checkpoint holds and what a bf16-weight engine can represent exactly), norm gains included."""
+    return {k: v.to(torch.bfloat16).to(torch.float32) for k, v in ot.init_weights(cfg, 3).items()}
+
+
 def qwen3_talker():
     """Qwen3-TTS talker + code predictor (row N1): prompt embeddings, first-step logits and 5 greedy frames (T = 0: no RNG involved)."""
     cfg = qwen3_talker_config()
-    W = ot.init_weights(cfg, 3)
+    W = qwen3_talker_weights(cfg)
     inp, trail, pad = ot.prepare_generation_inputs(cfg, W, QWEN3_CHAT_IDS, tts_bos=160, tts_eos=161, tts_pad=162, language_id=2160)
     logits, hidden = ot.Talker(cfg, W)(inp, None)
     codes = ot.generate_codes(cfg, W, inp, trail, pad, max_tokens=5, temperature=0.0, repetition_penalty=1.05, stop_on_eos=False)

@@ -214,7 +214,7 @@ def test_oracle_reproduces_committed_talker_golden():
     spec.loader.exec_module(mg)
     g = np.load(GOLDEN / "qwen3_talker.npz")
     cfg = mg.qwen3_talker_config()
-    W = oq.init_weights(cfg, 3)
+    W = mg.qwen3_talker_weights(cfg)
     inp, trail, pad = oq.prepare_generation_inputs(cfg, W, mg.QWEN3_CHAT_IDS, tts_bos=160, tts_eos=161, tts_pad=162, language_id=2160)
     assert tuple(g["input_shape"]) == tuple(inp.shape) and np.allclose(mg.stats(inp.numpy()), g["input_embeds_stats"], rtol=1e-9, atol=1e-12)
     logits, _ = oq.Talker(cfg, W)(inp, None)
