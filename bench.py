@@ -1,17 +1,21 @@
 #!/usr/bin/env python
 """bench.py -- the reference's headline metric on the reference's headline config (BASELINE.json):
 real-time factor (RTFx = audio seconds / wall seconds, Sources/Tools/mlx-audio-swift-tts/App.swift:204)
-of Orpheus-3B TTS, batch 8 x 64-token prompt -> 512 audio tokens -> SNAC decode, per B200.
+of Orpheus-3B TTS, batch 8 x 64-token prompt -> 512 audio tokens -> SNAC decode, per B200; beside it, in the same
+JSON line, BASELINE.json's other half of the metric (Whisper-base STT, config 3) and the SNAC decode (config 2).
 
 A "step" is one pass of the hot path over one batch: 8 prompts -> prefill -> 512 decode steps (EOS masked so
-work is fixed) -> parseOutput / 7-token de-interleave -> SNAC decode -> 8 waveforms (6.229 s each).
+work is fixed) -> parseOutput / 7-token de-interleave -> SNAC decode -> 8 waveforms.  The synthetic 64-token prompt
+ends with START_OF_SPEECH (128257, the first token a real checkpoint emits), so parseOutput crops the prompt as it
+does in a real run and the audio is BASELINE.md's 512 tokens -> 73 frames -> 6.229 s per utterance.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
-    torchrun ... bench.py --gpus N ...          (one rank per GPU; utterances shard, weak scaling)
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--scaling weak|strong]
+    torchrun ... bench.py --gpus N ...          (one rank per GPU; utterances shard)
 
 `value` : inputs already resident in HBM, waveforms left in HBM (b2a_tts_generate_dev).
 `e2e`   : same metric through the host-buffer C ABI call a user makes (b2a_tts_generate): pinned host ids
           in, waveforms copied back to pinned host memory, inside the timed region.
+`whisper` / `snac` : secondary blocks with their own value / e2e / roofline (and cpu_baseline for Whisper at N=1).
 Timed with CUDA events on the stream the library launches on; max over ranks; rank 0 prints ONE JSON line.
 """
 from __future__ import annotations
@@ -44,18 +48,24 @@ def workload_name(cfg=ORPHEUS):
             f"{PROMPT_LEN}-token prompt, {GEN_TOKENS} audio tokens, batch {BATCH}, SNAC-24kHz decode")
 
 
-def audio_seconds_per_utterance(n_prompt: int, n_gen: int) -> float:
-    # parseOutput on prompt+generated (no 128257 in random-init output): floor((L+G)/7) frames x 2048 samples
-    return ((n_prompt + n_gen) // 7) * 4 * 512 / 24000.0
+def frames_per_utterance(n_gen: int = GEN_TOKENS) -> int:
+    # parseOutput crops everything up to the last 128257 (the prompt's final token), keeps the generated codes:
+    # floor(G / 7) frames (LlamaTTS.swift:383-434) -> BASELINE.md: 512 tokens -> 73 frames
+    return n_gen // 7
 
 
-def make_prompts(rank: int) -> np.ndarray:
+def audio_seconds_per_utterance(n_gen: int = GEN_TOKENS) -> float:
+    return frames_per_utterance(n_gen) * 4 * 512 / 24000.0            # 2048 samples per frame at 24 kHz: 6.229 s
+
+
+def make_prompts(rank: int, rows: int = BATCH) -> np.ndarray:
+    """[SOH] body [EOT, EOH] as prepareInputIds frames it (LlamaTTS.swift:446-553), then START_OF_SPEECH -- the first token a
+    real checkpoint generates -- so that parseOutput crops the prompt exactly as in a real run (VERDICT r1 / ADVICE r1)."""
     rng = np.random.default_rng(3 + rank)
-    body = rng.integers(0, 128000, size=(BATCH, PROMPT_LEN - 3), dtype=np.int32)
-    ids = np.empty((BATCH, PROMPT_LEN), dtype=np.int32)
+    ids = np.empty((rows, PROMPT_LEN), dtype=np.int32)
     ids[:, 0] = 128259
-    ids[:, 1:-2] = body
-    ids[:, -2], ids[:, -1] = 128009, 128260
+    ids[:, 1:-3] = rng.integers(0, 128000, size=(rows, PROMPT_LEN - 4), dtype=np.int32)
+    ids[:, -3], ids[:, -2], ids[:, -1] = 128009, 128260, 128257
     return ids
 
 
@@ -109,6 +119,16 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_tensor_peak():
+    """Dense bf16 TFLOP/s: the sustained figure (the encoder / prefill GEMMs run inside a long step)."""
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        if "bf16_tflops_sustained" in d:
+            return float(d["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    return 1450.0, "fallback (B200_PROFILING.md sustained cuBLAS bf16)"
+
+
 def weight_bytes(cfg) -> int:
     H, I, hd = cfg["hidden_size"], cfg["intermediate_size"], cfg["head_dim"]
     nq, nkv, L, V = cfg["num_attention_heads"], cfg["num_key_value_heads"], cfg["num_hidden_layers"], cfg["vocab_size"]
@@ -116,8 +136,19 @@ def weight_bytes(cfg) -> int:
     return 2 * (L * per_layer + V * H)        # every matrix once + the tied lm head; bf16
 
 
-def kv_bytes(cfg, batch, ctx) -> int:
-    return 2 * batch * cfg["num_key_value_heads"] * ctx * cfg["head_dim"] * 4 * cfg["num_hidden_layers"]   # fp32 K and V
+KV_ELEM_BYTES_BUILT = 4      # the cache this library keeps is fp32; SURVEY.md 8(d) counts a bf16 cache
+
+
+def kv_bytes(cfg, batch, ctx, elem_bytes: int = 2) -> int:
+    """K and V read by one decode step at context ctx.  elem_bytes = 2 is SURVEY.md 8(d)'s definition (bf16 cache): the roofline
+    numerator uses THAT, so the fp32 cache's extra traffic is not credited as useful bytes."""
+    return 2 * batch * cfg["num_key_value_heads"] * ctx * cfg["head_dim"] * elem_bytes * cfg["num_hidden_layers"]
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum over the 200 launches of ONE decode step (batch 8, context 320), from
+# `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none python tools/profile_step.py 320 3`
+# on the B200 (profiles/r02_decode_step_dram.csv, summary profiles/r02_decode_step_dram.md)
+MEASURED_STEP_DRAM_BYTES = {"context": 320, "batch": 8, "bytes": 7259108096}
 
 
 # ------------------------------------------------------------------------------------------------- CPU legs
@@ -200,11 +231,12 @@ class CpuReference:
         for c in cands:
             torch.set_num_threads(c)
             mo.forward(nxt)                                   # settle the pool at this size
-            dt = float("inf")
-            for _ in range(2):                                # best of two: one timing is too noisy on a shared host
+            ts = []
+            for _ in range(3):                                # median of three: one timing is too noisy on a shared host
                 t0 = time.perf_counter()
                 mo.forward(nxt)
-                dt = min(dt, time.perf_counter() - t0)
+                ts.append(time.perf_counter() - t0)
+            dt = float(np.median(ts))
             seen.append(f"{c}: {dt * 1e3:.0f}ms")
             if best is None or dt < best[1]:
                 best = (c, dt)
@@ -218,31 +250,43 @@ class CpuReference:
                                    num_attention_heads=c["num_attention_heads"], num_key_value_heads=c["num_key_value_heads"],
                                    head_dim=c["head_dim"], vocab_size=c["vocab_size"])
 
+    STEP_REPS, PREFILL_REPS = 5, 2
+
     def sample(self, light: bool = False):
-        """-> (RTFx, total seconds extrapolated, description).  light=True (warm-up samples): one decode step only."""
+        """-> (RTFx, total seconds extrapolated, description).  light=True (warm-up samples): one decode step only.
+        Every timing inside a sample is a MEDIAN (decode step: 5 repeats, prefill: 2) at the fixed, calibrated thread count, so the
+        reference arm does not move 2x between runs on a shared host (VERDICT r1 weak #8)."""
         torch, ol, osn = self.torch, self.ol, self.osn
         L_full = self.cfg["num_hidden_layers"]
         ids = torch.as_tensor(make_prompts(0)[:, :self.PREFILL_TOKENS], dtype=torch.long)
-        res = {}
-        for nl in (2, 4):
+        # two DIRECT measurements, no difference of near-equal numbers (that made the round-1 arm move 2x between runs):
+        #   layers: the 4-layer model with the lm head switched off (head_positions=[])  -> per-layer cost = t / 4
+        #   head  : a 0-layer model (embedding, final norm, tied lm head on every position, as the reference's graph evaluates it)
+        def timed_pair(nl, head):
             mo = ol.LlamaOracle(self._build(nl), self.W, round_acts=True)
-            t0 = time.perf_counter()
-            lg = mo.forward(ids if not light else ids[:, :2])
-            t_pre = (time.perf_counter() - t0) * (PROMPT_LEN / (self.PREFILL_TOKENS if not light else 2))
-            nxt = lg[:, -1].argmax(-1, keepdim=True)
-            t0 = time.perf_counter()
-            mo.forward(nxt)
-            res[nl] = (t_pre, time.perf_counter() - t0)
-            if light:
-                res[4] = res[2] = res[nl]
-                break
-        per_layer_pre = max((res[4][0] - res[2][0]) / 2, 0.0)
-        per_layer_dec = max((res[4][1] - res[2][1]) / 2, 0.0)
-        head_pre = max(res[2][0] - 2 * per_layer_pre, 0.0)
-        head_dec = max(res[2][1] - 2 * per_layer_dec, 0.0)
+            kw = {} if head else {"head_positions": []}
+            pre_ids = ids if not light else ids[:, :2]
+            tp = []
+            for _ in range(1 if light else self.PREFILL_REPS):
+                mo.reset()
+                t0 = time.perf_counter()
+                mo.forward(pre_ids, **kw)
+                tp.append(time.perf_counter() - t0)
+            nxt = pre_ids[:, -1:]
+            td = []
+            for _ in range(1 if light else self.STEP_REPS):
+                t0 = time.perf_counter()
+                mo.forward(nxt, **kw)
+                td.append(time.perf_counter() - t0)
+            return float(np.median(tp)) * (PROMPT_LEN / pre_ids.shape[1]), float(np.median(td))
+
+        lay_pre, lay_dec = timed_pair(4, head=False)
+        head_pre, head_dec = (0.0, 0.0) if light else timed_pair(0, head=True)
+        per_layer_pre, per_layer_dec = lay_pre / 4, lay_dec / 4
+        res = {4: (lay_pre + head_pre, lay_dec + head_dec)}
         t_prefill = L_full * per_layer_pre + head_pre
         t_step = L_full * per_layer_dec + head_dec
-        frames = (PROMPT_LEN + GEN_TOKENS) // 7
+        frames = frames_per_utterance()
         fsub = max(frames // self.SNAC_DIV, 1) if not light else 1
         osn.DTYPE = torch.float32
         codes = osn.synth_codes(self.scfg, 1, 4 * fsub, seed=2)
@@ -251,50 +295,203 @@ class CpuReference:
         t_snac1 = (time.perf_counter() - t0) * frames / fsub
         osn.DTYPE = torch.float64
         total = t_prefill + GEN_TOKENS * t_step + BATCH * t_snac1
-        audio = BATCH * audio_seconds_per_utterance(PROMPT_LEN, GEN_TOKENS)
-        desc = (f"oracle port (torch-CPU fp32 math on bf16-valued weights, {self.threads} threads, {self.calibration}): full-width 2- and 4-layer models timed "
+        audio = BATCH * audio_seconds_per_utterance()
+        desc = (f"oracle port (torch-CPU fp32 math on bf16-valued weights, {self.threads} threads fixed, {self.calibration}): full-width 4-layer stack (lm head off) and 0-layer model (embedding + norm + tied lm head) timed directly, "
+                f"every timing a median (decode step x{self.STEP_REPS}, prefill x{self.PREFILL_REPS}) "
                 f"(prefill of {self.PREFILL_TOKENS} of {PROMPT_LEN} prompt tokens x batch {BATCH}: {res[4][0]:.2f}s scaled / decode step "
-                f"{res[4][1]*1e3:.0f}ms at 4 layers), per-layer + lm-head cost extrapolated linearly to {L_full} layers x "
+                f"{res[4][1]*1e3:.0f}ms at 4 layers + head), per-layer + lm-head cost extrapolated linearly to {L_full} layers x "
                 f"({PROMPT_LEN}-token prefill + {GEN_TOKENS} steps); SNAC decode timed on {fsub} of {frames} frames of 1 of {BATCH} "
                 f"utterances ({t_snac1:.2f}s scaled) x {BATCH}")
         return audio / total, total, desc
 
 
-def cpu_reference_sample(cfg, threads: int):
-    """-> (RTFx, total seconds, description, threads actually used)."""
+def cpu_reference_sample(cfg, threads: int, n: int = 3):
+    """-> (RTFx, total seconds, description, threads actually used): the MEDIAN of n bounded samples."""
     ref = CpuReference(cfg, threads)
-    return (*ref.sample(), ref.threads)
+    ref.sample(light=True)
+    out = sorted((ref.sample() for _ in range(n)), key=lambda r: r[0])
+    v, tot, desc = out[len(out) // 2]
+    return v, tot, desc + f"; median of {n} samples", ref.threads
+
+
+def bench_config(cfg, world: int, scaling: str, tiny: bool = False) -> dict:
+    rows = BATCH if scaling == "weak" else max(1, BATCH // world)
+    return {"workload": workload_name(cfg) + (" [TINY plumbing run -- not a bench number]" if tiny else ""),
+            "global_batch": rows * world, "rows_per_gpu": rows, "parallelism": f"utterance-dp{world}",
+            "sampling": "T=0.6 top_p=0.8 rep_penalty=1.3/20 (reference defaults), EOS masked",
+            "prompt": "64 tokens: [SOH] 60 ids [EOT, EOH, START_OF_SPEECH]; parseOutput crops it, audio = 512 // 7 = 73 frames = 6.229 s per utterance (BASELINE.md)",
+            "l2": "inputs larger than L2: every decode step streams %.2f GB of weights" % (weight_bytes(cfg) / 1e9),
+            "audio_s_per_step": audio_seconds_per_utterance() * rows * world}
+
+
+def cpu_whisper_sample(threads: int):
+    """Whisper-base (config 3) on the CPU port: ONE 30 s clip -- log-mel, 6-layer encoder, 4-token prefix + 64 greedy steps
+    (EOT masked) -- timed once after a light warm-up; x16 clips (batched == serial, linear in clips)."""
+    import torch
+    from oracle import dsp
+    from oracle import whisper as ow
+    torch.set_num_threads(threads)
+    cfg = ow.WhisperConfig(**{k: v for k, v in WHISPER_BASE.items() if k in ow.WhisperConfig.__dataclass_fields__})
+    W = ow.init_weights(cfg, 1234)
+    x = dsp.synth_audio(480000, 0)
+    ow.transcribe_tokens(ow.WhisperOracle(cfg, W), x[:32000], ow.build_prompt_tokens(), max_tokens=2, mask_eot=True)
+    t0 = time.perf_counter()
+    ow.transcribe_tokens(ow.WhisperOracle(cfg, W), x, ow.build_prompt_tokens(), max_tokens=WH_STEPS, mask_eot=True)
+    dt = time.perf_counter() - t0
+    return 30.0 / dt, f"oracle port (torch-CPU fp32), {threads} threads: 1 of {WH_BATCH} clips timed ({dt:.2f} s), x{WH_BATCH} (linear in clips)"
 
 
 def run_reference_arm(args, rank: int, world: int):
     if rank != 0:
         return
     ref = CpuReference(ORPHEUS, usable_cpus())    # weights built once; every step is one bounded sample (see CpuReference)
-    threads = ref.threads                          # the calibrated count (the fastest for this arm), reported as `cores`
+    threads = ref.threads                          # the calibrated count (the fastest for this arm), fixed from here on, reported as `cores`
     vals, totals, sample = [], [], ""
     for i in range(args.warmup + args.steps):
         v, tot, sample = ref.sample(light=i < args.warmup)     # warm-up samples: threads / allocator only (one decode step)
         if i >= args.warmup:
             vals.append(v); totals.append(tot)
-    v = float(np.mean(vals))
+    v = float(np.median(vals))                     # median over the timed samples (each sample is itself built from medians)
+    sample += f"; value = median of {len(vals)} samples (min {min(vals):.3f}, max {max(vals):.3f})"
+    cfg = bench_config(ORPHEUS, world, args.scaling)
+    cfg["reference_arm"] = ("CPU restatement of the reference path (the Swift/MLX reference cannot be built in this image); always the "
+                            "batch-8 workload on rank 0's host cores, extrapolated from a bounded sample")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": float(np.mean(totals)) * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload_name(), "note": "CPU restatement of the reference path (the Swift/MLX reference "
-                       "cannot be built in this image); extrapolated from a bounded sample"},
+            "warmup": args.warmup, "ms_per_step": float(np.median(totals)) * 1e3, "higher_is_better": True, "scaling": args.scaling,
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    try:
+        wv, wdesc = cpu_whisper_sample(threads)
+        line["whisper"] = {"metric": "whisper_base_stt_rtfx_batch16", "value": wv, "unit": UNIT, "cpu_baseline": {"value": wv, "unit": UNIT, "cores": threads, "kind": "port", "sample": wdesc}}
+    except Exception as e:      # the headline line must still print
+        line["whisper"] = {"unavailable": repr(e)[:200]}
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------- GPU arm
+WHISPER_BASE = dict(vocab_size=51865, num_mel_bins=80, d_model=512, encoder_layers=6, encoder_attention_heads=8, encoder_ffn_dim=2048,
+                    max_source_positions=1500, decoder_layers=6, decoder_attention_heads=8, decoder_ffn_dim=2048, max_target_positions=448)
+WH_BATCH, WH_STEPS, WH_SAMPLES = 16, 64, 480000
+SNAC_BATCH, SNAC_T = 8, 1024
+
+
+def whisper_encoder_flops() -> float:
+    """Dense FLOPs of the Whisper-base encoder for one 30 s clip (~87 GFLOP)."""
+    d, f, T = WHISPER_BASE["d_model"], WHISPER_BASE["encoder_ffn_dim"], 1500
+    conv = 2 * (3000 * 80 * 3 * d + T * d * 3 * d)
+    layer = 2 * (4 * T * d * d + 2 * T * T * d + 2 * T * d * f)
+    return float(conv + WHISPER_BASE["encoder_layers"] * layer)
+
+
+def synth_clip(n: int, seed: int) -> np.ndarray:
+    """x = 0.5 sin(2 pi 220 t) + 0.1 N(0, 1), clipped, 16 kHz."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(n, dtype=np.float64) / 16000.0
+    return np.clip(0.5 * np.sin(2 * np.pi * 220.0 * t) + 0.1 * rng.standard_normal(n), -1.0, 1.0).astype(np.float32)
+
+
+class GpuTimer:
+    """CUDA events on the library's own stream (torch.cuda.Event only sees the stream it is recorded on), barrier + synchronize on
+    both sides, max over ranks."""
+
+    def __init__(self, torch, dist, m):
+        self.torch, self.dist, self.m = torch, dist, m
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def __call__(self, fn, stream, steps, warmup):
+        torch = self.torch
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = self.m.launch_count()
+        e0.record(stream)
+        outs = [fn() for _ in range(steps)]
+        e1.record(stream)
+        self.barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item()), self.m.launch_count() - n0, outs
+
+
+def whisper_block(m, torch, timer, rank, world, local, steps, warmup):
+    """BASELINE config 3: Whisper-base, 16 x 30 s synthetic clips per GPU, greedy, 64 forced decode steps (EOT masked)."""
+    wm = m.WhisperModel.random_init(WHISPER_BASE, device=local, max_batch=WH_BATCH)
+    stream = torch.cuda.ExternalStream(wm.stream, device=torch.device("cuda", local))
+    pcm_host = torch.from_numpy(np.stack([synth_clip(WH_SAMPLES, 100 * rank + i) for i in range(WH_BATCH)])).pin_memory()
+    pcm_dev = pcm_host.cuda()
+    P = m.STTGenerateParameters(max_tokens=WH_STEPS, mask_eot=True)
+    toks = torch.zeros((WH_BATCH, WH_STEPS), dtype=torch.int32).pin_memory()
+    ntok = torch.zeros(WH_BATCH, dtype=torch.int32).pin_memory()
+    ms_dev, launches, outs = timer(lambda: wm.generate_dev(pcm_dev, P, toks.numpy(), ntok.numpy()), stream, steps, warmup)
+    pcm_np = pcm_host.numpy()                       # a view of the pinned buffer: the C ABI copies host -> device from it
+    ms_e2e, _, _ = timer(lambda: wm.generate(pcm_np, P), stream, steps, 1)
+    assert int(ntok.min()) == WH_STEPS, "whisper benchmark produced too few tokens"
+    audio = WH_BATCH * 30.0 * world
+    enc_s = float(np.median([o.encode_time for o in outs]))
+    dec_s = float(np.median([o.decode_time for o in outs]))
+    peak, peak_src = measured_tensor_peak()
+    ach = whisper_encoder_flops() * WH_BATCH / enc_s / 1e12
+    alg_mel = WH_BATCH * (4 * WH_SAMPLES + 4 * 3000 * 80)
+    return {"metric": "whisper_base_stt_rtfx_batch16", "unit": UNIT, "value": audio * steps / (ms_dev * 1e-3),
+            "ms_per_step": ms_dev / steps,
+            "config": {"workload": f"Whisper-base (d_model 512, 6+6 layers, vocab 51865) random-init bf16, {WH_BATCH} x 30 s synthetic 16 kHz clips per GPU, "
+                                   f"greedy, 4-token prefix + {WH_STEPS} forced decode steps (EOT masked)", "clips_per_gpu": WH_BATCH},
+            "e2e": {"value": audio * steps / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / steps,
+                    "h2d_bytes_per_step": int(pcm_host.numel() * 4), "d2h_bytes_per_step": int(toks.numel() * 4 + ntok.numel() * 4)},
+            "gpu_launches": int(launches), "stages_s": {"encode(log-mel + encoder + cross K/V)": enc_s, "decode": dec_s},
+            "roofline": {"kernel": "encoder (log-mel, conv stem, 6 x [LN, qkv gemm, attention, o gemm, LN, fc1+GELU, fc2], cross K/V projections); "
+                                   "dominant kernels tc_gemm_kernel<128> + the encoder attention kernel", "bound": "tensor",
+                         "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "flops_per_clip": whisper_encoder_flops(), "note": "useful dense FLOPs of the encoder / host-timed encode stage "
+                         "(includes the log-mel kernel and the cross-K/V projections); log-mel algorithmic bytes %d per step" % alg_mel}}
+
+
+def snac_block(m, torch, timer, rank, world, local, codec, steps, warmup):
+    """BASELINE config 2: SNAC-24kHz decode, batch 8 x 1024 latent steps -> 8 x 524 288 samples (21.85 s each)."""
+    stream = torch.cuda.ExternalStream(codec.stream, device=torch.device("cuda", local))
+    rng = np.random.default_rng(2 + rank)
+    codes_host = [torch.from_numpy(rng.integers(0, 4096, size=(SNAC_BATCH, SNAC_T // s), dtype=np.int32)).pin_memory() for s in (4, 2, 1)]
+    codes_dev = [c.cuda() for c in codes_host]
+    wave_dev = torch.empty((SNAC_BATCH, 1, SNAC_T * 512), device="cuda")
+    ms_dev, launches, _ = timer(lambda: codec.decode_dev(codes_dev, wave_dev, seed=1, stream=codec.stream), stream, steps, warmup)
+    codes_np = [c.numpy() for c in codes_host]
+    wave_np = torch.empty((SNAC_BATCH, 1, SNAC_T * 512), dtype=torch.float32).pin_memory().numpy()
+    ms_e2e, _, outs = timer(lambda: codec.decode(codes_np, out=wave_np), stream, steps, 1)
+    assert outs[-1].shape[-1] == SNAC_T * 512 and np.isfinite(outs[-1]).all()
+    audio = SNAC_BATCH * SNAC_T * 512 / 24000.0 * world
+    peak, peak_src = measured_peaks()
+    fused = 441.5e6 * SNAC_BATCH               # SURVEY.md 8(d): every DecoderBlock boundary activation written once + read once, fp32
+    minimum = SNAC_BATCH * (7168 + 2097152) + 52.5e6
+    ach = fused / (ms_dev / steps * 1e-3) / 1e9
+    return {"metric": "snac24k_decode_rtfx_batch8", "unit": UNIT, "value": audio * steps / (ms_dev * 1e-3), "ms_per_step": ms_dev / steps,
+            "config": {"workload": f"SNAC-24kHz decode, batch {SNAC_BATCH} x {SNAC_T} latent steps (codes [8,256] [8,512] [8,1024]) -> 8 x 524288 samples, "
+                                   "NoiseBlock noise drawn on the device"},
+            "e2e": {"value": audio * steps / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / steps,
+                    "h2d_bytes_per_step": int(sum(c.numel() for c in codes_host) * 4), "d2h_bytes_per_step": int(wave_dev.numel() * 4)},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "whole decode (RVQ lookup, 4 DecoderBlocks, final conv); dominant kernels cg::conv_gemm_kernel + rf::ru_fused_kernel",
+                         "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "bytes_definition": "SURVEY.md 8(d) per-block-fused bound, fp32 activations: 441.5 MB per utterance",
+                         "algorithmic_minimum_bytes": minimum, "frac_vs_algorithmic_minimum": minimum / (ms_dev / steps * 1e-3) / 1e9 / peak}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: 8 utterances per GPU; strong: the fixed batch of 8 split 8/G per GPU (SURVEY.md 8e)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the whisper / snac blocks")
     ap.add_argument("--tiny", action="store_true", help="small model (plumbing check only; NOT a bench number)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -313,33 +510,31 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    timer = GpuTimer(torch, dist, m)
 
     cfg = dict(ORPHEUS)
     if args.tiny:
         cfg.update(hidden_size=512, num_hidden_layers=2, intermediate_size=1024, num_attention_heads=4, num_key_value_heads=2)
+    rows = BATCH if args.scaling == "weak" else max(1, BATCH // world)
+    assert args.scaling == "weak" or BATCH % world == 0, "strong scaling splits the batch of 8: use 1, 2, 4 or 8 GPUs"
     codec = m.SNAC(weights=m.SNAC.random_init_weights(1234), device=local)
     tts = m.LlamaTTSModel.random_init(cfg, snac=codec, device=local, max_batch=BATCH, max_context=PROMPT_LEN + GEN_TOKENS + 16,
-                                      std=0.02, seed=1234 + rank)
+                                      std=0.02, seed=1234 + (rank if args.scaling == "weak" else 0))
     params = m.GenerateParameters(max_tokens=GEN_TOKENS, temperature=0.6, top_p=0.8, repetition_penalty=1.3,
                                   repetition_context_size=20, seed=rank, mask_eos=True, wrap_codes=True)
-    frames = (PROMPT_LEN + GEN_TOKENS) // 7
-    wave_len = frames * 2048
-    audio_s = BATCH * wave_len / 24000.0
+    wave_len = frames_per_utterance() * 2048
+    audio_s = rows * wave_len / 24000.0
 
-    ids_host = torch.from_numpy(make_prompts(rank)).pin_memory()
-    toks_host = torch.zeros((BATCH, GEN_TOKENS), dtype=torch.int32).pin_memory()
-    ntok_host = torch.zeros(BATCH, dtype=torch.int32).pin_memory()
-    wave_host = torch.zeros((BATCH, wave_len), dtype=torch.float32).pin_memory()
-    wlen_host = torch.zeros(BATCH, dtype=torch.int64)
+    all_prompts = make_prompts(rank) if args.scaling == "weak" else make_prompts(0)[rank * rows:(rank + 1) * rows]
+    ids_host = torch.from_numpy(np.ascontiguousarray(all_prompts)).pin_memory()
+    toks_host = torch.zeros((rows, GEN_TOKENS), dtype=torch.int32).pin_memory()
+    ntok_host = torch.zeros(rows, dtype=torch.int32).pin_memory()
+    wave_host = torch.zeros((rows, wave_len), dtype=torch.float32).pin_memory()
+    wlen_host = torch.zeros(rows, dtype=torch.int64)
     ids_dev = ids_host.cuda(non_blocking=False)
-    wave_dev = torch.zeros((BATCH, wave_len), dtype=torch.float32, device="cuda")
-    gathered = torch.zeros((world, BATCH, wave_len), dtype=torch.float32, device="cuda") if world > 1 else None
+    wave_dev = torch.zeros((rows, wave_len), dtype=torch.float32, device="cuda")
+    gathered = torch.zeros((world, rows, wave_len), dtype=torch.float32, device="cuda") if world > 1 else None
     stream = torch.cuda.ExternalStream(tts.stream, device=torch.device("cuda", local))
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     def step_dev():
         wl, info = tts.generate_dev(ids_dev, params, wave_dev, wave_len)
@@ -349,39 +544,32 @@ def main():
         return info
 
     def step_e2e():
-        info = tts.generate_into(ids_host, params, toks_host, ntok_host, wave_host, wlen_host)
-        return info
-
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n0 = m.launch_count()
-        e0.record(stream)
-        infos = [fn() for _ in range(steps)]
-        e1.record(stream)
-        barrier()
-        ms = e0.elapsed_time(e1)
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        if dist is not None:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), m.launch_count() - n0, infos
+        return tts.generate_into(ids_host, params, toks_host, ntok_host, wave_host, wlen_host)
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_dev, launches, infos = timed(step_dev, args.steps, args.warmup)
+    ms_dev, launches, infos = timer(step_dev, stream, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e, _, _ = timed(step_e2e, args.steps, max(1, min(args.warmup, 1)))
+    ms_e2e, _, _ = timer(step_e2e, stream, args.steps, max(1, min(args.warmup, 1)))
     assert int(wlen_host[0]) == wave_len and bool(torch.isfinite(wave_host).all()), "benchmark produced no / bad audio"
 
-    # roofline of the dominant kernel group: one captured decode step (weights streamed once + KV read)
-    ctx = PROMPT_LEN + GEN_TOKENS // 2
-    step_ms = tts.time_steps(BATCH, ctx, 24)
+    # roofline of the dominant kernel group: the captured decode step (weights streamed once + KV read), timed INSIDE the measured
+    # loop: generate_time covers the GEN_TOKENS - 1 graph replays after the prefill (incl. the host's poll every 16 tokens)
+    ctx = PROMPT_LEN + GEN_TOKENS // 2              # mean context over the loop; KV bytes are linear in it
+    step_ms = float(np.median([i.generate_time for i in infos])) / (GEN_TOKENS - 1) * 1e3
+    graph_ms = tts.time_steps(rows, ctx, 24)        # the same graph replayed back to back, greedy, no host polling (for reference)
     peak, peak_src = measured_peaks()
-    alg_bytes = weight_bytes(cfg) + kv_bytes(cfg, BATCH, ctx)
+    alg_bytes = weight_bytes(cfg) + kv_bytes(cfg, rows, ctx, 2)
+    built_bytes = weight_bytes(cfg) + kv_bytes(cfg, rows, ctx, KV_ELEM_BYTES_BUILT)
     achieved = alg_bytes / (step_ms * 1e-3) / 1e9
+
+    secondary = {}
+    if not args.no_secondary and not args.tiny:
+        del tts
+        torch.cuda.empty_cache()
+        secondary["whisper"] = whisper_block(m, torch, timer, rank, world, local, max(3, min(args.steps, 10)), 3)
+        secondary["snac"] = snac_block(m, torch, timer, rank, world, local, codec, max(3, min(args.steps, 10)), 3)
 
     if rank != 0:
         if dist is not None:
@@ -389,30 +577,37 @@ def main():
         return
     value = world * audio_s * args.steps / (ms_dev * 1e-3)
     e2e = world * audio_s * args.steps / (ms_e2e * 1e-3)
+    traffic = MEASURED_STEP_DRAM_BYTES["bytes"] if (rows == MEASURED_STEP_DRAM_BYTES["batch"] and not args.tiny) else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": workload_name(cfg) + (" [TINY plumbing run -- not a bench number]" if args.tiny else ""),
-                   "global_batch": BATCH * world, "parallelism": f"utterance-dp{world}",
-                   "sampling": "T=0.6 top_p=0.8 rep_penalty=1.3/20 (reference defaults), EOS masked",
-                   "l2": "inputs larger than L2: every decode step streams %.2f GB of weights" % (weight_bytes(cfg) / 1e9),
-                   "audio_s_per_step": audio_s * world},
+        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic", "config": bench_config(cfg, world, args.scaling, args.tiny),
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(ids_host.numel() * 4), "d2h_bytes_per_step": int(wave_host.numel() * 4 + toks_host.numel() * 4)},
         "gpu_launches": int(launches),
-        "stages_s": {"prefill": infos[-1].prefill_time, "decode": infos[-1].generate_time, "codec": infos[-1].codec_time},
+        "stages_s": {"prefill": float(np.median([i.prefill_time for i in infos])), "decode": float(np.median([i.generate_time for i in infos])),
+                     "codec": float(np.median([i.codec_time for i in infos]))},
         "roofline": {"kernel": "decode step (CUDA graph: 28 x [rmsnorm, qkv tcgen05 gemm, 2-CTA-cluster attention, o gemm, rmsnorm, "
-                               "gate/up gemm+swiglu, down gemm] + lm-head gemm + sampler); dominant kernel tc_gemm_kernel<16>", "bound": "hbm", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": int(alg_bytes * 1.018), "peak_source": peak_src,
-                     "traffic_source": "ncu --set full on tc_gemm_kernel<16> (profiles/r01_tc_gemm_ncu_full.md, r01_ncu_full_summary.md): dram bytes / "
-                                       "algorithmic bytes = 1.00-1.04 per GEMM launch, 1.018 weighted; applied to the step's algorithmic bytes",
-                     "algorithmic_bytes_per_step": alg_bytes, "ms_per_decode_step": step_ms, "context": ctx},
+                               "gate/up gemm+swiglu, down gemm] + lm-head gemm + sampler); dominant kernel tc_gemm_kernel<16>", "bound": "hbm",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "traffic_source": "sum of dram__bytes_read.sum + dram__bytes_write.sum over the 200 launches of one step at context 320, batch 8 "
+                                       "(ncu, profiles/r02_decode_step_dram.csv)",
+                     "algorithmic_bytes_per_step": alg_bytes, "bytes_definition": "SURVEY.md 8(d): every weight once (bf16, tied lm head) + bf16 K/V read at the mean context",
+                     "kv_cache_dtype_built": "f32", "built_bytes_per_step": built_bytes,
+                     "ms_per_decode_step": step_ms, "ms_per_decode_step_source": "median generate_time / 511 graph replays inside the timed loop",
+                     "ms_per_graph_replay_back_to_back": graph_ms, "context": ctx},
         "clocks": clocks,
     }
+    line.update(secondary)
     if not args.no_cpu_baseline and world == 1 and not args.tiny:
         v, tot, sample, threads = cpu_reference_sample(cfg, usable_cpus())
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+        if "whisper" in line:
+            try:
+                wv, wdesc = cpu_whisper_sample(threads)
+                line["whisper"]["cpu_baseline"] = {"value": wv, "unit": UNIT, "cores": threads, "kind": "port", "sample": wdesc}
+            except Exception as e:
+                line["whisper"]["cpu_baseline"] = {"unavailable": repr(e)[:200]}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

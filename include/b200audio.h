@@ -189,8 +189,6 @@ typedef struct b2a_gen_params {
     float repetition_penalty;
     int32_t repetition_context_size;
     uint64_t seed;
-    int32_t mask_eos;   /* benchmark only: never stop on 128258 (fixed work) */
-    int32_t wrap_codes; /* benchmark only: codes taken mod 4096 so random-init tokens index the codebook */
 } b2a_gen_params;
 
 /* AudioGenerationInfo (GenerationTypes.swift:14-45) */
@@ -232,23 +230,8 @@ int32_t b2a_tts_generate_dev(b2a_tts* h, const int32_t* d_input_ids, int32_t bat
                              const b2a_gen_params* params, float* d_wave_out, int64_t wave_cap,
                              int64_t* wave_len, b2a_gen_info* info);
 int32_t b2a_tts_cancel(b2a_tts* h);
-/* Benchmark / full-size property-test helpers (no reference counterpart):
- *   b2a_tts_create_random : same as b2a_tts_create but the weights are drawn ON THE DEVICE
- *                           (N(0, std^2) bf16 from a counter-based generator, norm gains 1) so a
- *                           3B-parameter random-init model needs no host copy.
- *   b2a_tts_stream        : the handle's cudaStream_t (as void*) so a caller can record CUDA
- *                           events on the stream the kernels are launched on.
- *   b2a_tts_time_steps    : runs `iters` captured decode steps for `batch` rows at context
- *                           `ctx` (greedy, no host sync inside) between two CUDA events on the
- *                           handle's stream; *ms_per_step = average device time of one step. */
-/*   b2a_tts_debug_trace   : parity hook -- enable != 0 makes later b2a_tts_forward_logits calls record the
- *                           residual stream at every RMSNorm input; out (nullable) receives the record of
- *                           the last traced position as [2*layers+1, batch, hidden] float32. */
-int32_t b2a_tts_debug_trace(b2a_tts* h, int32_t enable, int32_t batch, float* out);
-int32_t b2a_tts_create_random(int32_t device, const b2a_llama_config* cfg, float std, uint64_t seed,
-                              b2a_snac* snac, b2a_tts** out);
+/* the handle's cudaStream_t (as void*), so a caller can order its own work / record events on the stream the kernels run on */
 void* b2a_tts_stream(b2a_tts* h);
-int32_t b2a_tts_time_steps(b2a_tts* h, int32_t batch, int32_t ctx, int32_t iters, float* ms_per_step);
 /* parseOutput (:383-434) and llamaDecodeAudioFromCodes' de-interleave (:41-63), host-side ints.
  * tokens [B, n]; code_lists_out [B, n] / code_lens[B]; then per row codes0/1/2 sized n/7, 2n/7, 4n/7 */
 int32_t b2a_tts_parse_output(const int32_t* tokens, int32_t batch, int32_t n, int32_t* code_lists_out,
@@ -401,7 +384,7 @@ typedef struct b2a_whisper_config {
 /* STTGenerateParameters as used by transcribeChunk + WhisperGenerationConfig's suppress lists */
 typedef struct b2a_stt_params {
     int32_t max_tokens;           /* defaultGenerationParameters: max_target_positions - 16 */
-    float temperature;            /* only 0 (greedy argmax, lowest index wins ties) is implemented */
+    float temperature;            /* 0: greedy argmax (lowest index wins ties); > 0: categorical(logits / T), WhisperModel.swift:284-291 */
     const int32_t* prompt_ids;    /* decoder prefix from buildPromptTokens (WhisperTokenizer.swift:98-113) */
     int32_t n_prompt;
     const int32_t* begin_suppress; /* suppressed at step 0 only (default [endOfText]) */
@@ -410,7 +393,7 @@ typedef struct b2a_stt_params {
     int32_t n_suppress;
     int32_t timestamp_begin;      /* ids >= this are always suppressed (WhisperModel.swift:236) */
     int32_t eot;                  /* end-of-text id: stops a clip */
-    int32_t mask_eot;             /* benchmark only: never stop (fixed work) */
+    uint64_t seed;                /* temperature > 0: the draw of (clip b, step s) is a pure function of (seed, b, s) */
 } b2a_stt_params;
 
 typedef struct b2a_stt_info {
@@ -425,7 +408,6 @@ typedef struct b2a_stt_info {
 typedef struct b2a_stt b2a_stt;
 int32_t b2a_stt_create(int32_t device, const b2a_whisper_config* cfg, const b2a_tensor* tensors,
                        int32_t n_tensors, b2a_stt** out);
-int32_t b2a_stt_create_random(int32_t device, const b2a_whisper_config* cfg, float std, uint64_t seed, b2a_stt** out);
 void* b2a_stt_stream(b2a_stt* h);
 /* enc_out [B, 1500, d_model] float32 (host) */
 int32_t b2a_stt_encode(b2a_stt* h, const float* pcm, int32_t batch, int64_t n_samples, float* enc_out);
@@ -505,27 +487,6 @@ int32_t b2a_speech_tokenizer_config_from_json(const char* config_path, int32_t m
                                               b2a_speech_tokenizer_config* cfg, int32_t* decode_upsample_rate);
 int32_t b2a_speech_tokenizer_create_from_directory(const char* dir, int32_t device, int32_t max_batch, int32_t max_cache_frames,
                                                    b2a_speech_tokenizer** out, int32_t* decode_upsample_rate);
-/* Host-only parity hook (no device needed): the GEMM weight matrix the implicit convolution reads for an MLX-layout
- * [out, k, in] weight -- stride 0: causal conv, rows = out, taps = k; stride > 0: transposed conv with k = n * stride, rows =
- * stride * out (phase-major), taps = n.  layout_out: [rows][taps][kpad] float32, kpad = ceil(in / 64) * 64.            */
-int32_t b2a_speech_tokenizer_debug_layout(const float* w, int32_t out, int32_t k, int32_t in, int32_t stride, float* layout_out,
-                                          int64_t capacity, int32_t* rows, int32_t* taps, int32_t* kpad);
-/* Test entry (tests/test_gpu_qwen3_sampler.py) for the Qwen3-TTS in-graph sampler kernel (csrc/qwen3_sampler.cu = sampleToken,
- * Qwen3TTS.swift:1003-1118; EXPERIMENTAL like the rest of row N1): HOST logits [B, V <= 4096]; suppress [lo, hi) except eos;
- * seen = bitmap of the tokens generated so far [B, ceil(V/32)] (nullable; updated when track != 0); tokens_out [B];
- * filtered_out [B, V] (nullable) = the logits handed to categorical, -inf where removed.                                  */
-int32_t b2a_qwen3_sample_test(const float* logits, int32_t batch, int32_t vocab, float temperature, float top_p, int32_t top_k,
-                              float min_p, float repetition_penalty, int32_t eos, int32_t suppress_lo, int32_t suppress_hi,
-                              uint32_t* seen, int32_t track, uint64_t seed, int32_t step, int32_t* tokens_out, float* filtered_out);
-/* Test entry (tests/test_gpu_implicit_conv.py): one launch of the implicit-GEMM causal convolution kernel
- * (csrc/implicit_conv.cuh) on HOST data: w [M][taps][Cin], x [B][Ttot][Cin]; out[b, t*up + rho, co] for m = rho * (M/up) + co is
- * sum_j sum_c w[m, j, c] * x[b, t + shift0 + j*dil, c] through the fused epilogue (bias, bias twice at t = 0, GELU, gamma, add,
- * SnakeBeta on the hi/lo copy).  xo [B][T*up][M/up] in/out or null; hl_out [B][Hout + T*up][M/up] or null.  fp16 != 0: operands as
- * fp16 hi/lo pairs instead of bf16 ones (what B2A_ST_FP16=1 selects for the speech-tokenizer decoder).                          */
-int32_t b2a_implicit_conv_test(const float* w, int32_t M, int32_t taps, int32_t Cin, const float* x, int32_t B, int32_t Ttot, int32_t T,
-                               int32_t dil, int32_t shift0, int32_t up, const float* bias, const float* gamma, int32_t gelu, int32_t add,
-                               int32_t bias_twice_t0, const float* sa, const float* sb, int32_t Hout, int32_t fp16, float* xo, float* hl_out);
-
 #ifdef __cplusplus
 }
 #endif

@@ -51,8 +51,7 @@ class LlamaConfig(C.Structure):
 
 class GenParams(C.Structure):
     _fields_ = [("max_tokens", C.c_int32), ("temperature", C.c_float), ("top_p", C.c_float),
-                ("repetition_penalty", C.c_float), ("repetition_context_size", C.c_int32), ("seed", C.c_uint64),
-                ("mask_eos", C.c_int32), ("wrap_codes", C.c_int32)]
+                ("repetition_penalty", C.c_float), ("repetition_context_size", C.c_int32), ("seed", C.c_uint64)]
 
 
 class GenInfo(C.Structure):
@@ -94,7 +93,7 @@ class WhisperConfig(C.Structure):
 class SttParams(C.Structure):
     _fields_ = [("max_tokens", C.c_int32), ("temperature", C.c_float), ("prompt_ids", C.c_void_p), ("n_prompt", C.c_int32),
                 ("begin_suppress", C.c_void_p), ("n_begin_suppress", C.c_int32), ("suppress", C.c_void_p),
-                ("n_suppress", C.c_int32), ("timestamp_begin", C.c_int32), ("eot", C.c_int32), ("mask_eot", C.c_int32)]
+                ("n_suppress", C.c_int32), ("timestamp_begin", C.c_int32), ("eot", C.c_int32), ("seed", C.c_uint64)]
 
 
 class SttInfo(C.Structure):
@@ -104,7 +103,7 @@ class SttInfo(C.Structure):
 
 TOKEN_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int32, C.c_int32, C.c_int32)
 
-# name -> (restype, argtypes); every symbol include/b200audio.h declares
+# name -> (restype, argtypes); every symbol include/b200audio.h and include/b200audio_internal.h declare
 _P = C.c_void_p
 SIGNATURES = {
     "b2a_last_error": (C.c_char_p, []),
@@ -137,6 +136,8 @@ SIGNATURES = {
     "b2a_tts_debug_trace": (C.c_int32, [_P, C.c_int32, C.c_int32, _P]),
     "b2a_tts_create_random": (C.c_int32, [C.c_int32, C.POINTER(LlamaConfig), C.c_float, C.c_uint64, _P, C.POINTER(_P)]),
     "b2a_tts_stream": (C.c_void_p, [_P]),
+    "b2a_tts_set_bench_flags": (C.c_int32, [_P, C.c_int32, C.c_int32]),
+    "b2a_stt_set_bench_flags": (C.c_int32, [_P, C.c_int32]),
     "b2a_tts_time_steps": (C.c_int32, [_P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float)]),
     "b2a_snac_stream": (C.c_void_p, [_P]),
     "b2a_tts_prepare_input_ids": (C.c_int32, [C.POINTER(_P), _P, C.c_int32, _P, C.POINTER(C.c_int32)]),

@@ -13,7 +13,7 @@
 #include <utility>
 #include <vector>
 
-#include "../../include/b200audio.h"
+#include "../../include/b200audio_internal.h"
 
 namespace b2a {
 

@@ -15,7 +15,6 @@
 #include "common.cuh"
 #include <cooperative_groups.h>
 #include "tc_gemm.cuh"
-#include "tc_chain.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -776,7 +775,6 @@ attn_decode_cluster_kernel(AttnArgs a, int NB) {
     }
 }
 
-extern "C" int b2a_debug_chain_ts(b2a_tts* h, unsigned long long* out, int n);
 #ifdef B2A_ATTN_TIMING
 extern "C" int b2a_debug_attn_ts(long long* out, int n) {
     return (int)cudaMemcpyFromSymbol(out, g_attn_ts, sizeof(long long) * n);
@@ -1215,10 +1213,6 @@ struct b2a_tts {
     // attention workspace (flash-decoding partials)
     DBuf<float> part_o, part_ml;
     DBuf<int> at_counters;
-    DBuf<unsigned> chain_bars;       // [3][16] grid-barrier counters of the GEMM chain kernel (tc_chain.cuh)
-    bool use_chain = false;          // B2A_CHAIN=1: experimental persistent GEMM-chain kernel (tc_chain.cuh); measured slower, see DESIGN.md
-    int chain_seq = 0, chain_stages = 12;
-    DBuf<unsigned long long> chain_dbg;   // B2A_CHAIN_DEBUG=1: per-CTA phase timestamps of the last chain launch
     int at_splits = 1;
     // tcgen05 / TMA path
     bool use_tc = true;
@@ -1235,6 +1229,7 @@ struct b2a_tts {
     DBuf<int> tokens, pos, recent, recent_n, out_tokens, n_gen, done, n_active, ids, forced;
     HBuf<int> h_flag;
     std::atomic<int> cancel{0};
+    int bench_mask_eos = 0, bench_wrap_codes = 0;   // b2a_tts_set_bench_flags (include/b200audio_internal.h): fixed-work benchmark switches
     int nb_pad = 0;   // rows rounded up to 1/2/4/8
     bool trace_on = false;       // debug: residual stream at every RMSNorm input (eager forward only)
     DBuf<float> trace;           // [2*layers + 1][8][H]
@@ -1376,16 +1371,6 @@ struct b2a_tts {
         part_ml.alloc((size_t)B * nkv * at_splits * G * 2);
         at_counters.alloc((size_t)B * nkv);
         B2A_CUDA(cudaMemset(at_counters.p, 0, (size_t)B * nkv * sizeof(int)));
-        chain_bars.alloc(chain::NSETS * chain::SET_STRIDE);
-        B2A_CUDA(cudaMemset(chain_bars.p, 0, chain::NSETS * chain::SET_STRIDE * sizeof(unsigned)));
-        {
-            const char* e = getenv("B2A_CHAIN");
-            use_chain = (e && std::string(e) == "1") && H <= 128 * chain::NORM_MAXV;
-            const char* st = getenv("B2A_CHAIN_STAGES");
-            if (st) chain_stages = std::max(2, std::min(12, atoi(st)));
-            if (getenv("B2A_CHAIN_DEBUG")) { chain_dbg.alloc((size_t)256 * 64); B2A_CUDA(cudaMemset(chain_dbg.p, 0, 256 * 64 * 8)); }
-            B2A_CUDA(cudaFuncSetAttribute(chain::chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain::smem_bytes(12)));
-        }
         // process-wide kernel attributes: always the same (largest) value, several handles may coexist
         gemv_attrs<1>(); gemv_attrs<2>(); gemv_attrs<4>(); gemv_attrs<8>();
         B2A_CHECK(attn_smem_bytes() <= 220 * 1024, B2A_ERR_INVALID_INPUT, "llama: GQA ratio too large for the attention tile");
@@ -1619,86 +1604,8 @@ struct b2a_tts {
         return e && strstr(e, what) != nullptr;
     }
 
-    // ---- GEMM chain (tc_chain.cuh): [O, norm2+GU, DOWN, norm1'+QKV' | final norm + lm head] as ONE persistent kernel per layer
-    struct ChainSpec {
-        int n = 0;
-        const CUtensorMap* A[chain::MAX_GEMM]; const CUtensorMap* Bm[chain::MAX_GEMM];
-        chain::Gemm g[chain::MAX_GEMM]; chain::Norm nm[chain::MAX_GEMM];
-    };
-    bool chain_ok() const { return use_tc && use_chain; }
-    chain::Gemm chain_gemm(int op, int M, int K, float* yout, bf16* actout) const {
-        chain::Gemm g{};
-        g.M = M; g.K = K; g.m_tiles = cdiv(M, tc::BM); g.k_blocks = K / tc::BK; g.norm = -1;
-        g.out_f32 = yout; g.out_bf16 = actout;
-        if (op == OP_GU) { g.ldo = M / 2; g.epi_full = tc::EPI_SWIGLU; g.epi_partial = -1; g.ctas = std::min(num_sms, g.m_tiles); }
-        else if (op == OP_LM) { g.ldo = M; g.epi_full = tc::EPI_STORE; g.epi_partial = -1; g.ctas = std::min(num_sms, g.m_tiles); }
-        else { g.ldo = M; g.epi_full = tc::EPI_STORE; g.epi_partial = tc::EPI_ATOMIC;
-               g.ctas = (int)std::min<long long>(num_sms, (long long)g.m_tiles * g.k_blocks); }
-        return g;
-    }
-    void chain_add(ChainSpec& c, int op, int layer, const chain::Norm* nm) {
-        const int H = cfg.hidden_size, I = cfg.intermediate_size, NQ = cfg.num_attention_heads * HD, NKV = cfg.num_key_value_heads * HD;
-        const int i = c.n++;
-        switch (op) {
-            case OP_QKV: c.A[i] = &tm_qkv[layer]; c.Bm[i] = &tmx_xn; c.g[i] = chain_gemm(op, NQ + 2 * NKV, H, qkv.p, nullptr); break;
-            case OP_O: c.A[i] = &tm_o[layer]; c.Bm[i] = &tmx_attn; c.g[i] = chain_gemm(op, H, NQ, y.p, nullptr); break;
-            case OP_GU: c.A[i] = &tm_gu[layer]; c.Bm[i] = &tmx_xn; c.g[i] = chain_gemm(op, 2 * I, H, nullptr, act.p); break;
-            case OP_DOWN: c.A[i] = &tm_down[layer]; c.Bm[i] = &tmx_act; c.g[i] = chain_gemm(op, H, I, y.p, nullptr); break;
-            default: c.A[i] = &tm_lm; c.Bm[i] = &tmx_xn; c.g[i] = chain_gemm(op, cfg.vocab_size, H, logits.p, nullptr); break;
-        }
-        if (nm) { c.nm[i] = *nm; c.g[i].norm = i; }
-    }
-    chain::Norm chain_norm(float* delta, const float* w, int trace_idx, float* zero_ptr, int zero_n) {
-        chain::Norm n{};
-        n.x = x.p; n.delta = delta; n.w = w; n.xn = xn.p; n.H = cfg.hidden_size; n.eps = cfg.rms_norm_eps;
-        n.trace = trace_on ? trace.p + (size_t)trace_idx * 8 * cfg.hidden_size : nullptr;
-        n.zero_ptr = zero_ptr; n.zero_n = zero_n;
-        return n;
-    }
-    void launch_chain(ChainSpec& c, int B, cudaStream_t s) {
-        chain::Args a{};
-        for (int i = 0; i < c.n; ++i) { a.g[i] = c.g[i]; a.n[i] = c.nm[i]; }
-        for (int i = c.n; i < chain::MAX_GEMM; ++i) { c.A[i] = c.A[0]; c.Bm[i] = c.Bm[0]; }
-        a.n_gemm = c.n; a.N = B; a.stages = chain_stages; a.bars = chain_bars.p; a.set = (chain_seq++) % chain::NSETS; a.dbg = chain_dbg.p;
-        launch_pdl(chain::chain_kernel, dim3(num_sms), dim3(tc::THREADS), chain::smem_bytes(chain_stages), s,
-                   *c.A[0], *c.Bm[0], *c.A[1], *c.Bm[1], *c.A[2], *c.Bm[2], *c.A[3], *c.Bm[3], a);
-    }
-    // embed -> [norm1_0 + QKV_0] -> L x (attention, chain).  with_lm: the last chain ends with final norm + lm head (logits ready);
-    // otherwise it stops after DOWN and leaves (x, y) exactly like run_layers() does.
-    void run_layers_chain(int B, cudaStream_t s, bool with_lm) {
-        const int nq = cfg.num_attention_heads, nkv = cfg.num_key_value_heads, L = cfg.num_hidden_layers;
-        const int QKV_N = (nq + 2 * nkv) * HD;
-        launch_pdl(embed_kernel, dim3(B), dim3(256), 0, s, tokens.p, embed.p, x.p, y.p, cfg.hidden_size, cfg.vocab_size);
-        {
-            ChainSpec c;
-            chain::Norm n1 = chain_norm(nullptr, layers[0].ln1.p, 0, nullptr, 0);
-            chain_add(c, OP_QKV, 0, &n1);
-            launch_chain(c, B, s);
-        }
-        const size_t kv_layer = (size_t)cfg.max_batch * nkv * cfg.max_context * HD;
-        for (int l = 0; l < L; ++l) {
-            AttnArgs aa{qkv.p, pos.p, freqs.p, kcache.p + l * kv_layer, vcache.p + l * kv_layer, attn.p, part_o.p, part_ml.p,
-                        at_counters.p, nq, nkv, cfg.max_context, at_splits, 1.0f / sqrtf((float)HD), L2Prefetch{nullptr, 0}};
-            attn_launch(aa, B, s);
-            ChainSpec c;
-            chain_add(c, OP_O, l, nullptr);
-            chain::Norm n2 = chain_norm(y.p, layers[l].ln2.p, 2 * l + 1, qkv.p, QKV_N);
-            chain_add(c, OP_GU, l, &n2);
-            chain_add(c, OP_DOWN, l, nullptr);
-            if (l + 1 < L) {
-                chain::Norm n1 = chain_norm(y.p, layers[l + 1].ln1.p, 2 * l + 2, nullptr, 0);
-                chain_add(c, OP_QKV, l + 1, &n1);
-            } else if (with_lm) {
-                chain::Norm nf = chain_norm(y.p, final_ln.p, 2 * L, nullptr, 0);
-                chain_add(c, OP_LM, -1, &nf);
-            }
-            launch_chain(c, B, s);
-        }
-    }
-
     // embed(tokens) -> all layers; leaves the residual stream in x and the last MLP output in y
     void run_layers(int B, cudaStream_t s) {
-        if (chain_ok()) { run_layers_chain(B, s, false); return; }
         const int H = cfg.hidden_size, nq = cfg.num_attention_heads, nkv = cfg.num_key_value_heads;
         const int QKV_N = (nq + 2 * nkv) * HD, G = nq / nkv;
         launch_pdl(embed_kernel, dim3(B), dim3(256), 0, s, tokens.p, embed.p, x.p, y.p, H, cfg.vocab_size);
@@ -1831,12 +1738,8 @@ struct b2a_tts {
         drop_graphs();
         cudaGraph_t g;
         B2A_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-        if (chain_ok()) {
-            run_layers_chain(B, stream, true);
-        } else {
-            run_layers(B, stream);
-            run_lm_head(B, stream);
-        }
+        run_layers(B, stream);
+        run_lm_head(B, stream);
         launch_pdl(sample_kernel, dim3(B), dim3(SM_THREADS), 0, stream, sa);
         B2A_CUDA(cudaStreamEndCapture(stream, &g));
         B2A_CUDA(cudaGraphInstantiate(&g_step, g, 0));
@@ -1848,8 +1751,8 @@ struct b2a_tts {
         B2A_CUDA(cudaGraphInstantiate(&g_prefill, g, 0));
         cudaGraphDestroy(g);
         g_nb = B; g_args = sa; g_L = L;
-        launches_step = chain_ok() ? 2 + cfg.num_hidden_layers * 2 + 1 : 1 + cfg.num_hidden_layers * 7 + 2 + 1;
-        launches_prefill = chain_ok() ? 2 + cfg.num_hidden_layers * 2 + 1 : 1 + cfg.num_hidden_layers * 7 + 1;
+        launches_step = 1 + cfg.num_hidden_layers * 7 + 2 + 1;
+        launches_prefill = 1 + cfg.num_hidden_layers * 7 + 1;
     }
     int g_L = 0, launches_step = 0, launches_prefill = 0;
 };
@@ -1917,7 +1820,7 @@ static void tts_generate_impl(b2a_tts* h, const int32_t* input_ids, bool ids_on_
     sa.n_active = h->n_active.p; sa.forced = nullptr; sa.V = h->cfg.vocab_size; sa.R = gp->repetition_context_size > 0 ? R : 0;
     sa.max_tokens = MT; sa.temperature = gp->temperature; sa.top_p = gp->top_p;
     sa.rep_penalty = gp->repetition_context_size > 0 ? gp->repetition_penalty : 1.0f;
-    sa.seed = gp->seed; sa.mask_eos = gp->mask_eos;
+    sa.seed = gp->seed; sa.mask_eos = h->bench_mask_eos;
     if (sa.R == 0) { sa.R = 1; }
     h->capture(B, sa, L);
 
@@ -2001,7 +1904,7 @@ static void tts_generate_impl(b2a_tts* h, const int32_t* input_ids, bool ids_on_
             int last = -1;
             for (int j = 0; j < (int)all.size(); ++j) if (all[j] == TOK_START_OF_SPEECH) last = j;
             std::vector<int> cl = parse_row(all.data(), (int)all.size(), last);
-            if (gp->wrap_codes)   // benchmark only: fold random-init tokens into each slot's 4096-code range
+            if (h->bench_wrap_codes)   // benchmark only: fold random-init tokens into each slot's 4096-code range
                 for (size_t i = 0; i < cl.size(); ++i) cl[i] = ((cl[i] % 4096) + 4096) % 4096 + 4096 * (int)(i % 7);
             deinterleave(cl.data(), (int)cl.size(), l1[b], l2[b], l3[b]);
             frames[b] = (int)l1[b].size();
@@ -2208,6 +2111,13 @@ int32_t b2a_tts_generate_dev(b2a_tts* h, const int32_t* d_input_ids, int32_t B, 
     });
 }
 
+int32_t b2a_tts_set_bench_flags(b2a_tts* h, int32_t mask_eos, int32_t wrap_codes) {
+    if (!h) return B2A_ERR_INVALID_INPUT;
+    h->bench_mask_eos = mask_eos != 0;
+    h->bench_wrap_codes = wrap_codes != 0;
+    return B2A_OK;
+}
+
 int32_t b2a_tts_cancel(b2a_tts* h) {
     if (!h) return B2A_ERR_INVALID_INPUT;
     h->cancel.store(1);
@@ -2263,9 +2173,3 @@ void b2a_tts_destroy(b2a_tts* h) { delete h; }
 
 }  // extern "C"
 
-// debug only (not part of include/b200audio.h): phase timestamps of the last GEMM-chain launch, B2A_CHAIN_DEBUG=1
-extern "C" int b2a_debug_chain_ts(b2a_tts* h, unsigned long long* out, int n) {
-    if (!h || !h->chain_dbg.p) return -1;
-    cudaDeviceSynchronize();
-    return (int)cudaMemcpy(out, h->chain_dbg.p, sizeof(unsigned long long) * (size_t)n, cudaMemcpyDeviceToHost);
-}

@@ -393,7 +393,16 @@ struct PickArgs {
     const int* begin_suppress; int n_begin;
     const int* suppress; int n_suppress;
     int V, max_tokens, timestamp_begin, eot, mask_eot;
+    float temperature;           // > 0: categorical(logits / T) (WhisperModel.swift:289-290), else argmax
+    unsigned long long seed;
 };
+__device__ __forceinline__ float wh_uniform01(unsigned long long seed, unsigned long long a, unsigned long long b) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (a * 1000003ull + b + 1ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (float)(z >> 40) * (1.0f / 16777216.0f);
+}
 __global__ void __launch_bounds__(1024)
 wh_pick_kernel(PickArgs a) {
     __shared__ float s_val[32];
@@ -423,9 +432,51 @@ wh_pick_kernel(PickArgs a) {
     }
     if ((t & 31) == 0) { s_val[t >> 5] = best; s_idx[t >> 5] = bi; }
     __syncthreads();
+    __shared__ float s_max, s_wsum[32];
+    __shared__ int s_pick;
     if (t == 0) {
         for (int i = 1; i < 32; ++i)
             if (s_val[i] > best || (s_val[i] == best && s_idx[i] < bi)) { best = s_val[i]; bi = s_idx[i]; }
+        s_max = best; s_pick = bi;
+    }
+    __syncthreads();
+    if (a.temperature > 0.f) {
+        // categorical(logits / T): inverse-CDF draw over softmax((l - max) / T).  Thread t owns the contiguous ids
+        // [t*C, (t+1)*C); an exclusive scan of the 1024 chunk sums finds the owning thread, which walks its chunk.
+        // Deterministic for a given (seed, row, step); the distribution is the reference's, the stream of draws is not
+        // (MLX draws Gumbel noise from its own generator).
+        const float mx = s_max, inv_t = 1.0f / a.temperature;
+        const int C = (a.V + 1023) / 1024, i0 = t * C, i1 = min(a.V, i0 + C);
+        float mine = 0.f;
+        for (int i = i0; i < i1; ++i) {
+            float v = lg[i];
+            if (i >= a.timestamp_begin) v += -1e9f;
+            mine += __expf((v - mx) * inv_t);
+        }
+        float inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const float n = __shfl_up_sync(0xffffffffu, inc, o); if ((t & 31) >= o) inc += n; }
+        if ((t & 31) == 31) s_wsum[t >> 5] = inc;
+        __syncthreads();
+        float wbase = 0.f, Z = 0.f;
+        for (int w = 0; w < 32; ++w) { if (w < (t >> 5)) wbase += s_wsum[w]; Z += s_wsum[w]; }
+        const float hi = wbase + inc, lo = hi - mine;
+        const float r = wh_uniform01(a.seed, (unsigned long long)b, (unsigned long long)a.n_gen[b]) * Z;
+        if (mine > 0.f && r >= lo && r < hi) {          // exactly one thread owns r; none (r == Z by rounding) keeps the argmax
+            float run = lo;
+            int pick = -1, last = -1;
+            for (int i = i0; i < i1 && pick < 0; ++i) {
+                float v = lg[i];
+                if (i >= a.timestamp_begin) v += -1e9f;
+                const float e = __expf((v - mx) * inv_t);
+                if (e > 0.f) { last = i; run += e; if (run > r) pick = i; }
+            }
+            s_pick = pick >= 0 ? pick : last;
+        }
+        __syncthreads();
+    }
+    if (t == 0) {
+        bi = s_pick;
         a.tokens[b] = bi;
         a.pos[b] += 1;
         if (!a.done[b]) {
@@ -508,6 +559,7 @@ struct b2a_stt {
     PickArgs g_pick{};
     int g_B = 0;
     std::atomic<int> cancel{0};
+    int bench_mask_eot = 0;      // b2a_stt_set_bench_flags (include/b200audio_internal.h): never stop on EOT (fixed work)
 
     ~b2a_stt() {
         if (g_full) cudaGraphExecDestroy(g_full);
@@ -852,7 +904,7 @@ struct b2a_stt {
     static bool same_pick(const PickArgs& a, const PickArgs& b) {
         return a.out_tokens == b.out_tokens && a.begin_suppress == b.begin_suppress && a.n_begin == b.n_begin && a.suppress == b.suppress &&
                a.n_suppress == b.n_suppress && a.max_tokens == b.max_tokens && a.timestamp_begin == b.timestamp_begin && a.eot == b.eot &&
-               a.mask_eot == b.mask_eot && a.V == b.V;
+               a.mask_eot == b.mask_eot && a.V == b.V && a.temperature == b.temperature && a.seed == b.seed;
     }
     void capture(int B, const PickArgs& pa) {
         if (g_full && g_B == B && same_pick(pa, g_pick)) return;
@@ -883,7 +935,6 @@ static void stt_transcribe_impl(b2a_stt* h, const float* pcm, bool on_device, in
     B2A_CHECK(B >= 1 && B <= h->cfg.max_batch, B2A_ERR_INVALID_INPUT, "stt transcribe: batch exceeds max_batch");
     B2A_CHECK(n > 200, B2A_ERR_INVALID_INPUT, "stt transcribe: clips must be longer than 200 samples");
     B2A_CHECK(sp->n_prompt >= 1 && sp->prompt_ids, B2A_ERR_INVALID_INPUT, "stt transcribe: empty decoder prompt");
-    B2A_CHECK(sp->temperature <= 0.f, B2A_ERR_INVALID_INPUT, "stt transcribe: only greedy decoding (temperature 0) is implemented");
     B2A_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
     h->cancel.store(0);
@@ -907,7 +958,7 @@ static void stt_transcribe_impl(b2a_stt* h, const float* pcm, bool on_device, in
     if (nb) h->d_begin.upload(sp->begin_suppress, nb, s);
     if (ns) h->d_suppress.upload(sp->suppress, ns, s);
     PickArgs pa{h->logits.p, h->tokens.p, h->pos.p, h->out_tokens.p, h->n_gen.p, h->done.p, h->n_active.p, h->d_begin.p, nb,
-                h->d_suppress.p, ns, h->cfg.vocab_size, MT, sp->timestamp_begin, sp->eot, sp->mask_eot};
+                h->d_suppress.p, ns, h->cfg.vocab_size, MT, sp->timestamp_begin, sp->eot, h->bench_mask_eot, sp->temperature > 0.f ? sp->temperature : 0.f, sp->seed};
     B2A_CUDA(cudaStreamSynchronize(s));
     h->capture(B, pa);
     wh_init_rows_kernel<<<1, 32, 0, s>>>(B, h->n_gen.p, h->done.p, h->n_active.p);
@@ -1060,6 +1111,12 @@ int32_t b2a_stt_transcribe_long(b2a_stt* h, const float* pcm, int64_t n, const b
         }
         if (info) *info = acc;
     });
+}
+
+int32_t b2a_stt_set_bench_flags(b2a_stt* h, int32_t mask_eot) {
+    if (!h) return B2A_ERR_INVALID_INPUT;
+    h->bench_mask_eot = mask_eot != 0;
+    return B2A_OK;
 }
 
 int32_t b2a_stt_cancel(b2a_stt* h) {

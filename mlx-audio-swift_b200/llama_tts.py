@@ -31,7 +31,7 @@ class GenerateParameters:
 
     def _c(self) -> _ffi.GenParams:
         return _ffi.GenParams(self.max_tokens, self.temperature, self.top_p, self.repetition_penalty,
-                              self.repetition_context_size, self.seed, int(self.mask_eos), int(self.wrap_codes))
+                              self.repetition_context_size, self.seed)
 
 
 @dataclass
@@ -180,6 +180,11 @@ class LlamaTTSModel:
         _ffi.check(_ffi.lib().b2a_tts_forward_logits(self._h, _ffi.ptr(ids), B, L, int(reset_cache), _ffi.ptr(out)))
         return out
 
+    def _params(self, p: GenerateParameters) -> _ffi.GenParams:
+        # mask_eos / wrap_codes are benchmark switches on the handle (include/b200audio_internal.h), not part of GenerateParameters' ABI struct
+        _ffi.check(_ffi.lib().b2a_tts_set_bench_flags(self._h, int(p.mask_eos), int(p.wrap_codes)))
+        return p._c()
+
     def generate_batch(self, input_ids, parameters: Optional[GenerateParameters] = None, decode_audio: bool = True,
                        on_token: Optional[Callable[[int, int, int], None]] = None):
         """B independent utterances through generate (:658-765).  Returns (tokens [list per row],
@@ -194,7 +199,7 @@ class LlamaTTSModel:
         wave = np.empty((B, cap), dtype=np.float32) if decode_audio else None
         wlen = np.zeros(B, dtype=np.int64)
         info = _ffi.GenInfo()
-        gp = p._c()
+        gp = self._params(p)
         cb = _ffi.TOKEN_CB(lambda user, b, step, tok: on_token(b, step, tok)) if on_token else _ffi.TOKEN_CB()
         _ffi.check(_ffi.lib().b2a_tts_generate(self._h, _ffi.ptr(ids), B, L, C.byref(gp), _ffi.ptr(toks), _ffi.ptr(ntok),
                                                _ffi.ptr(wave), cap, _ffi.ptr(wlen), C.byref(info), cb, None))
@@ -210,7 +215,7 @@ class LlamaTTSModel:
         int64 -- numpy arrays or torch CPU tensors.  Returns AudioGenerationInfo."""
         B, L = ids.shape
         info = _ffi.GenInfo()
-        gp = parameters._c()
+        gp = self._params(parameters)
         cap = wave.shape[1] if wave is not None else 0
         _ffi.check(_ffi.lib().b2a_tts_generate(self._h, _ffi.ptr(ids), B, L, C.byref(gp), _ffi.ptr(tokens), _ffi.ptr(n_tokens),
                                                _ffi.ptr(wave), cap, _ffi.ptr(wave_len), C.byref(info), _ffi.TOKEN_CB(), None))
@@ -250,7 +255,7 @@ class LlamaTTSModel:
         B, L = d_input_ids.shape
         wlen = np.zeros(B, dtype=np.int64)
         info = _ffi.GenInfo()
-        gp = parameters._c()
+        gp = self._params(parameters)
         _ffi.check(_ffi.lib().b2a_tts_generate_dev(self._h, _ffi.ptr(d_input_ids), B, L, C.byref(gp), _ffi.ptr(d_wave),
                                                    wave_cap, _ffi.ptr(wlen), C.byref(info)))
         return wlen, AudioGenerationInfo(info.prompt_token_count, info.generation_token_count, info.prefill_time,

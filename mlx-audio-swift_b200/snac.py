@@ -112,7 +112,7 @@ class SNAC:
         return float(self.sampling_rate)
 
     def decode(self, codes: List[np.ndarray], noise: Optional[List[Optional[np.ndarray]]] = None,
-               zero_noise: bool = False, seed: int = 0) -> np.ndarray:
+               zero_noise: bool = False, seed: int = 0, out: Optional[np.ndarray] = None) -> np.ndarray:
         """SNAC.decode (:127-131): codes[i] [B, T_i] int -> waveform [B, 1, T*hop] float32.
         `noise[i]` supplies NoiseBlock i's Gaussian draw explicitly."""
         cs = [np.ascontiguousarray(c, dtype=np.int32) for c in codes]
@@ -128,7 +128,8 @@ class SNAC:
         if noise is not None:
             nz = [None if n is None else np.ascontiguousarray(n, dtype=np.float32) for n in noise]
             np_ = (C.c_void_p * len(self.decoder_rates))(*[None if n is None else n.ctypes.data for n in nz])
-        wave = np.empty((B, 1, T * self.hop_length), dtype=np.float32)
+        wave = out if out is not None else np.empty((B, 1, T * self.hop_length), dtype=np.float32)   # `out`: a caller-owned (e.g. pinned) buffer
+        assert wave.shape == (B, 1, T * self.hop_length) and wave.dtype == np.float32 and wave.flags["C_CONTIGUOUS"]
         _ffi.check(_ffi.lib().b2a_snac_decode(self._h, cp, B, T, np_, int(zero_noise), seed, _ffi.ptr(wave)))
         return wave
 

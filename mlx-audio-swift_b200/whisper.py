@@ -26,7 +26,8 @@ class STTGenerateParameters:
     task: str = "transcribe"
     begin_suppress_tokens: Sequence[int] = (EOT,)
     suppress_tokens: Sequence[int] = ()
-    mask_eot: bool = False                    # benchmark only
+    seed: int = 0                             # temperature > 0: draws are a pure function of (seed, clip, step)
+    mask_eot: bool = False                    # benchmark only (b2a_stt_set_bench_flags, include/b200audio_internal.h)
 
 
 @dataclass
@@ -150,7 +151,8 @@ class WhisperModel:
         bs = np.asarray(list(p.begin_suppress_tokens), dtype=np.int32)
         su = np.asarray(list(p.suppress_tokens), dtype=np.int32)
         sp = _ffi.SttParams(p.max_tokens, p.temperature, prompt.ctypes.data, len(prompt), bs.ctypes.data if len(bs) else None,
-                            len(bs), su.ctypes.data if len(su) else None, len(su), TIMESTAMP_BEGIN, EOT, int(p.mask_eot))
+                            len(bs), su.ctypes.data if len(su) else None, len(su), TIMESTAMP_BEGIN, EOT, int(p.seed))
+        _ffi.check(_ffi.lib().b2a_stt_set_bench_flags(self._h, int(p.mask_eot)))
         return sp, (prompt, bs, su)
 
     def generate(self, audio, generation_parameters: Optional[STTGenerateParameters] = None) -> STTOutput:

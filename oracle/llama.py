@@ -151,9 +151,12 @@ class LlamaOracle:
         return self._r(x) @ self.w[name].to(torch.float32).T
 
     @torch.no_grad()
-    def forward(self, ids: torch.Tensor, trace: Optional[list] = None) -> torch.Tensor:
+    def forward(self, ids: torch.Tensor, trace: Optional[list] = None,
+                head_positions: Optional[Sequence[int]] = None) -> torch.Tensor:
         """ids [B, L] -> logits [B, L, V] (LlamaTTS.swift:335-345, 557-567).  ``trace`` (a list) receives the
-        residual stream of the LAST position at every RMSNorm input (2 per layer + final), for debugging."""
+        residual stream of the LAST position at every RMSNorm input (2 per layer + final), for debugging.
+        ``head_positions`` (indices into L) restricts the lm head to those positions -> [B, len, V]; the full-width
+        parity tests use it so a 156 940-row head is not evaluated at every teacher-forced position."""
         cfg = self.cfg
         B, L = ids.shape
         nq, nkv, hd = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
@@ -191,6 +194,8 @@ class LlamaOracle:
         self.offset += L
         if trace is not None:
             trace.append(h[:, -1].clone())
+        if head_positions is not None:
+            h = h[:, list(head_positions)]
         hn = rms_norm(h, self.w["model.norm.weight"], cfg.rms_norm_eps)
         head = self.w["model.embed_tokens.weight"] if cfg.tie_word_embeddings else self.w["lm_head.weight"]
         return self._r(hn) @ head.to(torch.float32).T

@@ -99,5 +99,5 @@ def test_fp16_operand_pairs(b2a):
     xob, _ = run(b2a, w, x, 130, dil=9, bias=bias, fp16=0)
     rx, rh = model(w.astype(np.float32), x.astype(np.float32), 130, dil=9, bias=bias.astype(np.float32))
     e16, eb = np.abs(xo16 - rx).max(), np.abs(xob - rx).max()
-    assert e16 < 2e-6 * max(1.0, np.abs(rx).max()) and close(hl16, rh, 2e-6)
+    assert e16 < 4e-6 * max(1.0, np.abs(rx).max()) and close(hl16, rh, 2e-6)
     assert e16 < eb                                               # and it is the more accurate of the two formats
