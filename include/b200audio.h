@@ -225,6 +225,17 @@ int32_t b2a_tts_generate(b2a_tts* h, const int32_t* input_ids, int32_t batch, in
                          const b2a_gen_params* params, int32_t* tokens_out, int32_t* n_tokens_out,
                          float* wave_out, int64_t wave_cap, int64_t* wave_len, b2a_gen_info* info,
                          b2a_token_cb on_token, void* user);
+/* generateStream with audio DURING generation.  The reference's Orpheus emits one .audio event at the end
+ * (LlamaTTS.swift:901-904); its streaming models decode their codes in chunks while generating (decodeAudioFromCodes' chunk loop,
+ * Sources/MLXAudioTTS/Models/Qwen3/Qwen3.swift:47-83; the CLI's --benchmark TTFB is the latency of the first .audio event,
+ * Sources/Tools/mlx-audio-swift-tts/App.swift:155-211).  Here every `frames_per_chunk` new 7-token frames of a row are decoded by
+ * SNAC with `left_context_frames` already-emitted frames in front of them (their samples are dropped) and handed to on_audio as
+ * 2048 * frames float32 samples; is_final marks a row's last chunk.  Concatenated chunks equal the one-shot waveform except near
+ * chunk boundaries (the codec's receptive field), exactly like the reference's chunked decode.                                 */
+typedef void (*b2a_audio_cb)(void* user, int32_t utterance, const float* samples, int64_t n_samples, int32_t is_final);
+int32_t b2a_tts_generate_stream(b2a_tts* h, const int32_t* input_ids, int32_t batch, int32_t len, const b2a_gen_params* params,
+                                int32_t frames_per_chunk, int32_t left_context_frames, int32_t* tokens_out, int32_t* n_tokens_out,
+                                b2a_gen_info* info, b2a_token_cb on_token, b2a_audio_cb on_audio, void* user);
 /* Device-resident variant for bench.py's `value`: ids already in HBM, waveform left in HBM. */
 int32_t b2a_tts_generate_dev(b2a_tts* h, const int32_t* d_input_ids, int32_t batch, int32_t len,
                              const b2a_gen_params* params, float* d_wave_out, int64_t wave_cap,
@@ -428,7 +439,6 @@ int32_t b2a_stt_cancel(b2a_stt* h);
 void b2a_stt_destroy(b2a_stt* h);
 
 /* ------------------------------------------------------------------ Qwen3-TTS speech-tokenizer decoder
- * EXPERIMENTAL: compiled and exported, parity tests gated behind B2A_EXPERIMENTAL_N1=1 until they have run on a GPU.
  * Replaces Qwen3TTSSpeechTokenizerDecoder and the decode entry points of Qwen3TTSSpeechTokenizer
  * (Sources/MLXAudioTTS/Models/Qwen3TTS/Qwen3TTSSpeechTokenizer.swift):
  *   init(config:) + sanitized weights (keys below the "decoder." module, MLX layouts)  -> create
@@ -487,6 +497,86 @@ int32_t b2a_speech_tokenizer_config_from_json(const char* config_path, int32_t m
                                               b2a_speech_tokenizer_config* cfg, int32_t* decode_upsample_rate);
 int32_t b2a_speech_tokenizer_create_from_directory(const char* dir, int32_t device, int32_t max_batch, int32_t max_cache_frames,
                                                    b2a_speech_tokenizer** out, int32_t* decode_upsample_rate);
+/* ------------------------------------------------------------------ Qwen3-TTS talker + code predictor
+ * Replaces the autoregressive half of class Qwen3TTSModel (Sources/MLXAudioTTS/Models/Qwen3TTS/):
+ *   Qwen3TTSTalkerForConditionalGeneration (Qwen3TTSTalker.swift:127-366: per-head q/k RMSNorm before RoPE, interleaved 3-section
+ *     MRoPE -- all three position rows are equal for the text-only prompts the reference builds, where it is plain rotate-half
+ *     RoPE --, inputs are EMBEDDINGS, codec_head)                                               -> the 28-layer stack
+ *   Qwen3TTSCodePredictor (Qwen3TTSCodePredictor.swift:14-243: 5 layers, 15 lm heads / embeddings, cache reset every frame) -> the
+ *     inner 15-step loop
+ *   the frame loop of generate (Qwen3TTS.swift:380-495: talker step -> sampleToken -> 15 predictor steps -> summed-embedding
+ *     feedback `text + codec_embed(c0) + sum_i predictor_embed_i(c_i+1)`) and sampleToken (:1003-1118) -> b2a_qwen3_talker_generate:
+ *     ONE CUDA graph per 12.5 Hz frame, nothing syncs with the host inside it
+ *   text_projection(text_embedding(ids)) / codec_embedding(ids) (:898-999, prepareGenerationInputs) -> b2a_qwen3_talker_embed_text /
+ *     _embed_codec: the host composes the prompt from these rows exactly as prepareGenerationInputs does (tokenisation, the chat
+ *     template and the special-token ids stay with the host)
+ * Weights: the reference's keys after sanitize strips "talker." (model.layers.N.*, model.codec_embedding.weight,
+ * model.text_embedding.weight, text_projection.linear_fc{1,2}.{weight,bias}, codec_head.weight, code_predictor.model.layers.N.*,
+ * code_predictor.model.codec_embedding.I.weight, code_predictor.lm_head.I.weight), bf16 or f32 (rounded to bf16: the engine holds
+ * bf16 matrices; an MLX affine-quantised (8-bit) checkpoint is expanded by b2a_weights_dequantize first).  head_dim must be 128
+ * and the predictor's hidden size must equal the talker's (no small_to_mtp_projection) -- true of the shipped 0.6B geometry.   */
+typedef struct b2a_qwen3_talker_config {
+    int32_t vocab_size;            /* codec vocabulary (3072) */
+    int32_t hidden_size;
+    int32_t intermediate_size;
+    int32_t num_hidden_layers;
+    int32_t num_attention_heads;
+    int32_t num_key_value_heads;
+    int32_t head_dim;
+    float rms_norm_eps;
+    float rope_theta;
+    int32_t num_code_groups;       /* 16: one talker code + 15 predictor codes per frame */
+    int32_t text_hidden_size;
+    int32_t text_vocab_size;
+    int32_t codec_eos_token_id;
+    int32_t cp_vocab_size;         /* code predictor (Qwen3TTSConfig.swift:45-63) */
+    int32_t cp_hidden_size;
+    int32_t cp_intermediate_size;
+    int32_t cp_num_hidden_layers;
+    int32_t cp_num_attention_heads;
+    int32_t cp_num_key_value_heads;
+    int32_t cp_head_dim;
+    float cp_rms_norm_eps;
+    float cp_rope_theta;
+    int32_t max_batch;             /* <= 8 utterances per call */
+    int32_t max_context;           /* prompt embeddings + frames per utterance */
+} b2a_qwen3_talker_config;
+
+/* Qwen3TTS generate's sampling parameters (Qwen3TTS.swift:360-385; sampleToken :1003-1118) */
+typedef struct b2a_qwen3_gen_params {
+    int32_t max_tokens;            /* frames; the caller applies min(maxTokens, max(75, 6 * text tokens)) (:380) */
+    float temperature;             /* <= 0: greedy argmax (lowest index wins ties) for the talker code AND the predictor codes */
+    float top_p;
+    int32_t top_k;
+    float min_p;
+    float repetition_penalty;      /* talker code only, over the unique codes generated so far */
+    uint64_t seed;
+} b2a_qwen3_gen_params;
+
+typedef struct b2a_qwen3_talker b2a_qwen3_talker;
+int32_t b2a_qwen3_talker_create(int32_t device, const b2a_qwen3_talker_config* cfg, const b2a_tensor* tensors, int32_t n_tensors,
+                                b2a_qwen3_talker** out);
+void* b2a_qwen3_talker_stream(b2a_qwen3_talker* h);
+/* out [n, hidden] float32 (host): text_projection(text_embedding(ids)) resp. codec_embedding(ids) */
+int32_t b2a_qwen3_talker_embed_text(b2a_qwen3_talker* h, const int32_t* ids, int32_t n, float* out);
+int32_t b2a_qwen3_talker_embed_codec(b2a_qwen3_talker* h, const int32_t* ids, int32_t n, float* out);
+/* Parity hook: the talker over input_embeds [B, L, hidden] from an empty cache -> codec logits of the LAST position
+ * [B, vocab] and its final-norm hidden state [B, hidden] (Qwen3TTSTalker.swift:340-350).                                   */
+int32_t b2a_qwen3_talker_forward(b2a_qwen3_talker* h, const float* input_embeds, int32_t batch, int32_t len, float* logits_out,
+                                 float* hidden_out);
+/* The frame loop.  input_embeds [B, L, hidden] (every row the same L), trailing_text_hidden [B, n_trailing_max, hidden] with
+ * n_trailing[B] valid rows each (one is consumed per frame, then tts_pad_embed [hidden] is used), codes_out [B, max_tokens,
+ * num_code_groups] int32, n_frames_out[B].  A row stops after the frame whose talker code is codec_eos_token_id (that frame is not
+ * emitted, :424-428) or at max_tokens.  on_frame (nullable) is called on the calling thread for every emitted frame with the
+ * frame's num_code_groups codes -- the hook a streaming caller decodes audio chunks from (generateStream, Qwen3TTS.swift:500-569). */
+typedef void (*b2a_frame_cb)(void* user, int32_t utterance, int32_t frame, const int32_t* codes);
+int32_t b2a_qwen3_talker_generate(b2a_qwen3_talker* h, const float* input_embeds, int32_t batch, int32_t len,
+                                  const float* trailing_text_hidden, const int32_t* n_trailing, int32_t n_trailing_max,
+                                  const float* tts_pad_embed, const b2a_qwen3_gen_params* params, int32_t* codes_out,
+                                  int32_t* n_frames_out, b2a_gen_info* info, b2a_frame_cb on_frame, void* user);
+int32_t b2a_qwen3_talker_cancel(b2a_qwen3_talker* h);
+void b2a_qwen3_talker_destroy(b2a_qwen3_talker* h);
+
 #ifdef __cplusplus
 }
 #endif

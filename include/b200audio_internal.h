@@ -28,6 +28,10 @@ int32_t b2a_stt_create_random(int32_t device, const b2a_whisper_config* cfg, flo
 int32_t b2a_tts_set_bench_flags(b2a_tts* h, int32_t mask_eos, int32_t wrap_codes);
 int32_t b2a_stt_set_bench_flags(b2a_stt* h, int32_t mask_eot);
 int32_t b2a_tts_time_steps(b2a_tts* h, int32_t batch, int32_t ctx, int32_t iters, float* ms_per_step);
+/*   b2a_qwen3_talker_create_random : the Qwen3-TTS talker + code predictor with device-drawn weights (BASELINE config 5 bench).
+ *   b2a_qwen3_talker_set_bench_flags : mask_eos != 0 -> the talker never emits codec_eos_token_id (fixed work per call).        */
+int32_t b2a_qwen3_talker_create_random(int32_t device, const b2a_qwen3_talker_config* cfg, float std, uint64_t seed, b2a_qwen3_talker** out);
+int32_t b2a_qwen3_talker_set_bench_flags(b2a_qwen3_talker* h, int32_t mask_eos);
 
 /* ------------------------------------------------------------------ parity hooks
  *   b2a_tts_debug_trace : enable != 0 makes later b2a_tts_forward_logits calls record the residual stream at every RMSNorm

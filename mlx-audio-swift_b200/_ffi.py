@@ -84,6 +84,21 @@ class SpeechTokenizerConfig(C.Structure):
                    ("max_batch", C.c_int32), ("max_cache_frames", C.c_int32)])
 
 
+class Qwen3TalkerConfig(C.Structure):
+    _fields_ = ([(n, C.c_int32) for n in ("vocab_size", "hidden_size", "intermediate_size", "num_hidden_layers", "num_attention_heads",
+                                           "num_key_value_heads", "head_dim")]
+                + [("rms_norm_eps", C.c_float), ("rope_theta", C.c_float)]
+                + [(n, C.c_int32) for n in ("num_code_groups", "text_hidden_size", "text_vocab_size", "codec_eos_token_id", "cp_vocab_size",
+                                             "cp_hidden_size", "cp_intermediate_size", "cp_num_hidden_layers", "cp_num_attention_heads",
+                                             "cp_num_key_value_heads", "cp_head_dim")]
+                + [("cp_rms_norm_eps", C.c_float), ("cp_rope_theta", C.c_float), ("max_batch", C.c_int32), ("max_context", C.c_int32)])
+
+
+class Qwen3GenParams(C.Structure):
+    _fields_ = [("max_tokens", C.c_int32), ("temperature", C.c_float), ("top_p", C.c_float), ("top_k", C.c_int32), ("min_p", C.c_float),
+                ("repetition_penalty", C.c_float), ("seed", C.c_uint64)]
+
+
 class WhisperConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("vocab_size", "num_mel_bins", "d_model", "encoder_layers", "encoder_attention_heads",
                                           "encoder_ffn_dim", "max_source_positions", "decoder_layers", "decoder_attention_heads",
@@ -102,6 +117,7 @@ class SttInfo(C.Structure):
 
 
 TOKEN_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int32, C.c_int32, C.c_int32)
+AUDIO_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int32, C.POINTER(C.c_float), C.c_int64, C.c_int32)
 
 # name -> (restype, argtypes); every symbol include/b200audio.h and include/b200audio_internal.h declare
 _P = C.c_void_p
@@ -144,6 +160,8 @@ SIGNATURES = {
     "b2a_tts_forward_logits": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "b2a_tts_generate": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, C.POINTER(GenParams), _P, _P, _P, C.c_int64, _P,
                                      C.POINTER(GenInfo), TOKEN_CB, _P]),
+    "b2a_tts_generate_stream": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, C.POINTER(GenParams), C.c_int32, C.c_int32, _P, _P,
+                                            C.POINTER(GenInfo), TOKEN_CB, AUDIO_CB, _P]),
     "b2a_tts_generate_dev": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, C.POINTER(GenParams), _P, C.c_int64, _P,
                                          C.POINTER(GenInfo)]),
     "b2a_tts_cancel": (C.c_int32, [_P]),
@@ -199,6 +217,17 @@ SIGNATURES = {
     "b2a_stt_transcribe": (C.c_int32, [_P, _P, C.c_int32, C.c_int64, C.POINTER(SttParams), _P, _P, C.POINTER(SttInfo)]),
     "b2a_stt_transcribe_dev": (C.c_int32, [_P, _P, C.c_int32, C.c_int64, C.POINTER(SttParams), _P, _P, C.POINTER(SttInfo)]),
     "b2a_stt_transcribe_long": (C.c_int32, [_P, _P, C.c_int64, C.POINTER(SttParams), C.c_int32, _P, _P, _P, C.POINTER(C.c_int32), C.POINTER(SttInfo)]),
+    "b2a_qwen3_talker_create": (C.c_int32, [C.c_int32, C.POINTER(Qwen3TalkerConfig), C.POINTER(Tensor), C.c_int32, C.POINTER(_P)]),
+    "b2a_qwen3_talker_create_random": (C.c_int32, [C.c_int32, C.POINTER(Qwen3TalkerConfig), C.c_float, C.c_uint64, C.POINTER(_P)]),
+    "b2a_qwen3_talker_set_bench_flags": (C.c_int32, [_P, C.c_int32]),
+    "b2a_qwen3_talker_stream": (C.c_void_p, [_P]),
+    "b2a_qwen3_talker_embed_text": (C.c_int32, [_P, _P, C.c_int32, _P]),
+    "b2a_qwen3_talker_embed_codec": (C.c_int32, [_P, _P, C.c_int32, _P]),
+    "b2a_qwen3_talker_forward": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
+    "b2a_qwen3_talker_generate": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, _P, _P, C.c_int32, _P, C.POINTER(Qwen3GenParams), _P, _P,
+                                              C.POINTER(GenInfo), _P, _P]),
+    "b2a_qwen3_talker_cancel": (C.c_int32, [_P]),
+    "b2a_qwen3_talker_destroy": (None, [_P]),
     "b2a_stt_cancel": (C.c_int32, [_P]),
     "b2a_stt_destroy": (None, [_P]),
 }

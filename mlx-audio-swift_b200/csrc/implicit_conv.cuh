@@ -49,6 +49,8 @@ struct Args {
     int Hout;
     int f16;                      // operands (weights and planes) are fp16 hi/lo pairs instead of bf16 ones: same three products and cost, 22
                                   // instead of 16 mantissa bits per operand (predicted error of the decoder 6e-5 instead of 3e-4); range 65504
+    const float* wscale;          // [M] or null: the accumulator of row m is multiplied by wscale[m] (fp16 operands: weight rows are stored
+                                  // times a power of two so that their lo halves are NORMAL fp16 numbers, not subnormals)
     const float* sa;              // SnakeBeta on the hi/lo copy: v + sb * sin^2(sa * v), sa = exp(alpha), sb = 1 / (exp(beta) + 1e-9)
     const float* sb;
 };
@@ -83,7 +85,7 @@ __device__ __forceinline__ void put_hilo16(uint16_t* base, long long plane, long
     }
 }
 __device__ __forceinline__ float snake_beta(float v, float a, float ib) {
-    const float s = fast_sin(a * v);
+    const float s = sinf(a * v);          // EXPERIMENT: precise sine
     return fmaf(ib * s, s, v);
 }
 
@@ -173,8 +175,9 @@ implicit_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             const bool m_ok = m < a.M;
             int rho = 0, co = m;
             if (a.up > 1) { rho = m / a.Cout; co = m - rho * a.Cout; }
-            float bias = 0.f, gm = 1.f, sa = 0.f, sb = 0.f;
+            float bias = 0.f, gm = 1.f, sa = 0.f, sb = 0.f, ws = 1.f;
             if (m_ok) {
+                if (a.wscale) ws = a.wscale[m];
                 if (a.bias) bias = a.bias[co];
                 if (a.gamma) gm = a.gamma[co];
                 if (a.sa) { sa = a.sa[co]; sb = a.sb[co]; }
@@ -202,7 +205,7 @@ implicit_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             for (int j = 0; j < 16; ++j) {
                 const int tf = t_first + j;
                 if (tf >= a.T || !m_ok) continue;
-                float val = v[j] + w[j] + bias;
+                float val = (v[j] + w[j]) * ws + bias;
                 if (a.bias_twice_t0 && tf == 0) val += bias;
                 if (a.gelu) val = 0.5f * val * (1.0f + erff(val * 0.70710678118654752f));
                 val *= gm;

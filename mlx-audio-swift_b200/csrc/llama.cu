@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include <cooperative_groups.h>
 #include "tc_gemm.cuh"
+#include "qwen3_sampler.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -65,6 +66,29 @@ __global__ void embed_kernel(const int* __restrict__ tokens, const bf16* __restr
     }
 }
 
+// inputs given as embeddings (row N1): x[b,:] = src[b,:], y cleared like embed_kernel does
+__global__ void ext_embed_kernel(const float* __restrict__ src, float* __restrict__ x, float* __restrict__ y, int H) {
+    const int b = blockIdx.x;
+    pdl_trigger();
+    pdl_wait();
+    for (int i = threadIdx.x; i < H; i += blockDim.x) {
+        x[(long long)b * H + i] = src[(long long)b * H + i];
+        y[(long long)b * H + i] = 0.f;
+    }
+}
+
+// fused-norm step, row N1 only: the fp32 normalised hidden state  out[b, :] = x[b, :] * rstd[b] * w  from the partial sums of squares
+__global__ void finalize_norm_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ ss, int parts,
+                                     float* __restrict__ out, int H, float eps) {
+    const int b = blockIdx.x;
+    pdl_trigger();
+    pdl_wait();
+    float t = 0.f;
+    for (int p = 0; p < parts; ++p) t += ss[p * 8 + b];
+    const float r = rsqrtf(t / (float)H + eps);
+    for (int i = threadIdx.x; i < H; i += blockDim.x) out[(long long)b * H + i] = x[(long long)b * H + i] * r * w[i];
+}
+
 constexpr int LO_ROW = 8;   // activation matrices are [16, K] bf16: row b = hi(x_b), row 8 + b = lo(x_b) = bf16(x_b - hi)
 
 // token t of a [tokens, K] activation matrix lives in rows  hi = (t / half) * 2 * half + t % half,  lo = hi + half
@@ -83,7 +107,8 @@ constexpr int RN_THREADS = 1024, RN_MAXV = 8;
 __global__ void __launch_bounds__(RN_THREADS)
 add_rmsnorm_kernel(float* __restrict__ x, float* __restrict__ delta, const float* __restrict__ w,
                    bf16* __restrict__ xn, int H, float eps, float* __restrict__ trace, float* __restrict__ zero_ptr,
-                   int zero_n, int half, L2Prefetch pf) {
+                   int zero_n, int half, L2Prefetch pf, float* __restrict__ normed = nullptr, float* __restrict__ ss_out = nullptr,
+                   int ss_parts = 0) {
     __shared__ float red[RN_THREADS / 32];
     const int b = blockIdx.x, tid = threadIdx.x;
     pdl_trigger();
@@ -110,11 +135,18 @@ add_rmsnorm_kernel(float* __restrict__ x, float* __restrict__ delta, const float
     float tot = 0.f;
 #pragma unroll
     for (int i = 0; i < RN_THREADS / 32; ++i) tot += red[i];
-    const float r = rsqrtf(tot / (float)H + eps);
+    // ss_out != null ("raw" mode, fused-norm decode step): xn = hi/lo of x * w UN-normalised, the row's sum of squares goes to
+    // ss_out[0, b] (parts 1.. are cleared): the consumer GEMM applies rstd in its epilogue (tc_gemm.cuh, Args::rstd_ss)
+    const float r = ss_out ? 1.0f : rsqrtf(tot / (float)H + eps);
+    if (ss_out && tid < ss_parts) ss_out[tid * 8 + b] = tid == 0 ? tot : 0.f;
 #pragma unroll
     for (int j = 0; j < RN_MAXV; ++j) {
         const int i = tid + j * RN_THREADS;
-        if (i < H) store_hilo(xn, H, b, i, v[j] * r * w[i], half);
+        if (i < H) {
+            const float o = v[j] * r * w[i];
+            store_hilo(xn, H, b, i, o, half);
+            if (normed) normed[(long long)b * H + i] = o;     // the fp32 normalised row (the talker's hidden state, row N1)
+        }
     }
     if (zero_ptr)
         for (int i = tid; i < zero_n; i += RN_THREADS) zero_ptr[(long long)b * zero_n + i] = 0.f;
@@ -234,6 +266,11 @@ struct AttnArgs {
     int nq, nkv, max_ctx, S;
     float scale;
     L2Prefetch pf;         // weights of a later GEMM, prefetched into L2 while attention (which reads little) runs
+    const float* qnorm;    // nullable [128]: per-head RMSNorm gain applied to every q head BEFORE RoPE (Qwen3TTSTalker.swift:127-186)
+    const float* knorm;    // nullable [128]: same for the k head  (cluster kernel only)
+    float qk_eps;
+    int zero_qkv;          // fused-norm step: clear this (row, kv head)'s q | k | v slices after reading them, so that the next layer's
+                           // stream-K QKV GEMM can red.add into the row (the stand-alone norm kernel that used to do it is gone)
 };
 
 template <int G>
@@ -641,15 +678,33 @@ attn_decode_cluster_kernel(AttnArgs a, int NB) {
     float sn = 0.f, cs = 1.f;
     if (tid < HD / 2) sincosf((float)p / a.freqs[tid], &sn, &cs);   // MLXFast.RoPE(freqs:): angle = pos / freqs[i]
     pdl_wait();
+    const float* qsrc = row + (long long)h * G * HD;            // this kv head's G query heads, contiguous
+    const float* ksrc = row + (a.nq + h) * HD;
+    if (a.qnorm) {
+        // per-head RMSNorm of q and k before RoPE: x * rsqrt(mean(x^2) + eps) * w, one warp per 128-vector, staged in the
+        // (not yet used) warp-partial output area
+        for (int vec = tid >> 5; vec < G + 1; vec += AT_THREADS / 32) {
+            const float* src = vec < G ? qsrc + vec * HD : ksrc;
+            const float* w = vec < G ? a.qnorm : a.knorm;
+            const float4 x = reinterpret_cast<const float4*>(src)[tid & 31];
+            const float ss = warp_sum(x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w);
+            const float r = rsqrtf(ss * (1.0f / HD) + a.qk_eps);
+            const float4 g4 = reinterpret_cast<const float4*>(w)[tid & 31];
+            reinterpret_cast<float4*>(wpo + vec * HD)[tid & 31] = make_float4(x.x * r * g4.x, x.y * r * g4.y, x.z * r * g4.z, x.w * r * g4.w);
+        }
+        __syncthreads();
+        qsrc = wpo;
+        ksrc = wpo + G * HD;
+    }
     if (tid < HD / 2) {  // non-traditional RoPE: pairs (i, i+64)
         const int d = tid;
         _Pragma("unroll") for (int g = 0; g < G; ++g) {
-            const float* q = row + (h * G + g) * HD;
+            const float* q = qsrc + g * HD;
             const float x1 = q[d], x2 = q[d + HD / 2];
             sq[g * HD + d] = x1 * cs - x2 * sn;
             sq[g * HD + d + HD / 2] = x2 * cs + x1 * sn;
         }
-        const float* k = row + (a.nq + h) * HD;
+        const float* k = ksrc;
         const float x1 = k[d], x2 = k[d + HD / 2];
         const float k1 = x1 * cs - x2 * sn, k2 = x2 * cs + x1 * sn;
         if (owner) { kc[(long long)p * HD + d] = k1; kc[(long long)p * HD + d + HD / 2] = k2; }
@@ -764,6 +819,11 @@ attn_decode_cluster_kernel(AttnArgs a, int NB) {
         }
     }
     cluster.sync();
+    if (a.zero_qkv && rank == 0) {
+        float* wrow = const_cast<float*>(row);
+        for (int i = tid; i < G * HD; i += AT_THREADS) wrow[(long long)h * G * HD + i] = 0.f;
+        if (tid < HD) { wrow[(a.nq + h) * HD + tid] = 0.f; wrow[(a.nq + a.nkv + h) * HD + tid] = 0.f; }
+    }
     if (rank == 0 && tid < HD) {
         _Pragma("unroll") for (int g = 0; g < G; ++g) {
             const float M1 = xml[g], L1 = xml[MAXG + g], O1 = xo[g * HD + tid];
@@ -1191,6 +1251,18 @@ static std::vector<float> llama3_freqs(const b2a_llama_config& c) {
 struct LayerW {
     DBuf<bf16> wqkv, wo, wgu, wdown;
     DBuf<float> ln1, ln2;
+    DBuf<float> qnorm, knorm;   // [128] each, only with StackSpec::qk_norm
+};
+
+// Which checkpoint keys a transformer stack is built from.  Orpheus: {"model.", embeddings + tied head}.  The Qwen3-TTS talker
+// and code predictor (row N1) reuse the same engine with per-head q/k RMSNorm, inputs given as EMBEDDINGS and heads owned by the
+// caller (Qwen3TTSTalker.swift:127-310, Qwen3TTSCodePredictor.swift:14-240).
+struct StackSpec {
+    std::string prefix = "model.";            // "<prefix>layers.N....", "<prefix>norm.weight"
+    bool qk_norm = false;                      // self_attn.q_norm / k_norm
+    bool has_embed = true;                     // "<prefix>embed_tokens.weight" (false: inputs are embeddings)
+    std::string head;                          // "" = tied to the embedding / none; else an untied [vocab, hidden] matrix
+    bool has_head = true;
 };
 
 }  // namespace b2a
@@ -1228,6 +1300,14 @@ struct b2a_tts {
     bool use_batched_prefill = true;
     DBuf<int> tokens, pos, recent, recent_n, out_tokens, n_gen, done, n_active, ids, forced;
     HBuf<int> h_flag;
+    // fused-norm decode step (default on the tcgen05 path): o_proj / down_proj run as cluster split-K GEMMs whose leader CTA does the
+    // residual add + the next norm's gain + hi/lo split + sum of squares; no stand-alone add_rmsnorm launches (tc_gemm.cuh)
+    bool fused = false;
+    int fused_cluster = 4, fused_parts = 0;
+    DBuf<float> ss_a, ss_b;          // [H / 128, 8] partial sums of squares: ss_a feeds the post-attention norm, ss_b the input norm
+    StackSpec spec;                  // which keys / features this stack was built with
+    const float* x_ext = nullptr;    // row N1: when set, a step starts from these embeddings [8, H] instead of embed(tokens)
+    float* normed_out = nullptr;     // row N1: when set, the final RMSNorm also writes its fp32 output here [8, H]
     std::atomic<int> cancel{0};
     int bench_mask_eos = 0, bench_wrap_codes = 0;   // b2a_tts_set_bench_flags (include/b200audio_internal.h): fixed-work benchmark switches
     int nb_pad = 0;   // rows rounded up to 1/2/4/8
@@ -1250,10 +1330,17 @@ struct b2a_tts {
     static void upload_bf16(const TensorTable& tt, const std::string& name, int64_t expect, DBuf<bf16>& dst, size_t offset_elems,
                             size_t total_elems) {
         const b2a_tensor& t = tt.get(name);
-        B2A_CHECK(t.dtype == B2A_DTYPE_BF16, B2A_ERR_MODEL_NOT_INITIALIZED, "tensor must be bf16: " + name);
+        B2A_CHECK(t.dtype == B2A_DTYPE_BF16 || t.dtype == B2A_DTYPE_F32, B2A_ERR_MODEL_NOT_INITIALIZED, "tensor must be bf16 or f32: " + name);
         B2A_CHECK(TensorTable::numel(t) == expect, B2A_ERR_MODEL_NOT_INITIALIZED, "bad shape for tensor: " + name);
         dst.alloc(total_elems);
-        B2A_CUDA(cudaMemcpy(dst.p + offset_elems, t.data, expect * sizeof(bf16), cudaMemcpyHostToDevice));
+        if (t.dtype == B2A_DTYPE_BF16) {
+            B2A_CUDA(cudaMemcpy(dst.p + offset_elems, t.data, expect * sizeof(bf16), cudaMemcpyHostToDevice));
+        } else {   // an fp32 checkpoint: the engine holds bf16 matrices, round to nearest even (stated deviation, as for Whisper)
+            std::vector<bf16> tmp((size_t)expect);
+            const float* src = (const float*)t.data;
+            for (int64_t i = 0; i < expect; ++i) tmp[i] = __float2bfloat16_rn(src[i]);
+            B2A_CUDA(cudaMemcpy(dst.p + offset_elems, tmp.data(), expect * sizeof(bf16), cudaMemcpyHostToDevice));
+        }
     }
 
     template <int G>
@@ -1378,6 +1465,19 @@ struct b2a_tts {
         attn_loop_attr<1>(); attn_loop_attr<2>(); attn_loop_attr<3>(); attn_loop_attr<4>(); attn_loop_attr<6>(); attn_loop_attr<8>();
         attn_cluster_attr<1>(); attn_cluster_attr<2>(); attn_cluster_attr<3>(); attn_cluster_attr<4>(); attn_cluster_attr<6>(); attn_cluster_attr<8>();
         { const char* e = getenv("B2A_ATTN"); attn_loop = !(e && std::string(e) == "split"); attn_cluster = !(e && std::string(e) == "loop"); }
+        if (spec.qk_norm) attn_loop = attn_cluster = true;   // only the cluster kernel applies the per-head q/k RMSNorm
+        {
+            const char* e = getenv("B2A_FUSED");
+            const char* cl = getenv("B2A_CLUSTER");
+            if (cl) fused_cluster = std::max(1, std::min(tc::SPLIT_MAX_CLUSTER, atoi(cl)));
+            fused_parts = H / tc::BM;
+            const char* g = getenv("B2A_GEMM");
+            const bool tc_ok = !(g && std::string(g) == "simt") && H % tc::BK == 0 && NQ % tc::BK == 0 && I % tc::BK == 0;
+            fused = !(e && std::string(e) == "0") && tc_ok && attn_loop && attn_cluster && H % tc::BM == 0 && fused_parts <= 64;
+            ss_a.alloc((size_t)64 * 8); ss_b.alloc((size_t)64 * 8);
+            B2A_CUDA(cudaMemset(ss_a.p, 0, 64 * 8 * sizeof(float)));
+            B2A_CUDA(cudaMemset(ss_b.p, 0, 64 * 8 * sizeof(float)));
+        }
         B2A_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
         // tcgen05 / TMA path: needs every GEMM K to be a multiple of 64; B2A_GEMM=simt forces the SIMT fallback
         const char* env = getenv("B2A_GEMM");
@@ -1392,7 +1492,7 @@ struct b2a_tts {
                 tm_gu.push_back(tc::make_tmap_bf16(L.wgu.p, 2 * I, H, tc::BM));
                 tm_down.push_back(tc::make_tmap_bf16(L.wdown.p, H, I, tc::BM));
             }
-            tm_lm = tc::make_tmap_bf16(lm_head, c.vocab_size, H, tc::BM);
+            if (lm_head) tm_lm = tc::make_tmap_bf16(lm_head, c.vocab_size, H, tc::BM);
             tmx_xn = tc::make_tmap_bf16(xn.p, R16, H, 16);
             tmx_attn = tc::make_tmap_bf16(attn.p, R16, NQ, 16);
             tmx_act = tc::make_tmap_bf16(act.p, R16, I, 16);
@@ -1400,17 +1500,30 @@ struct b2a_tts {
         B2A_CUDA(cudaDeviceSynchronize());
     }
 
-    b2a_tts(int dev, const b2a_llama_config& c, const TensorTable& tt, b2a_snac* sn) : device(dev), cfg(c), snac(sn) {
+    b2a_tts(int dev, const b2a_llama_config& c, const TensorTable& tt, b2a_snac* sn, const StackSpec& sp = StackSpec())
+        : device(dev), cfg(c), snac(sn), spec(sp) {
         check_config();
         const int H = c.hidden_size, I = c.intermediate_size, nq = c.num_attention_heads, nkv = c.num_key_value_heads;
         const int NQ = nq * HD, NKV = nkv * HD;
-        upload_bf16(tt, "model.embed_tokens.weight", (int64_t)c.vocab_size * H, embed, 0, (size_t)c.vocab_size * H);
-        if (c.tie_word_embeddings) lm_head = embed.p;   // embedTokens.asLinear (LlamaTTS.swift:563)
-        else { upload_bf16(tt, "lm_head.weight", (int64_t)c.vocab_size * H, lm_head_w, 0, (size_t)c.vocab_size * H); lm_head = lm_head_w.p; }
+        if (sp.has_embed) upload_bf16(tt, sp.prefix + "embed_tokens.weight", (int64_t)c.vocab_size * H, embed, 0, (size_t)c.vocab_size * H);
+        if (sp.has_head) {
+            if (sp.head.empty() && c.tie_word_embeddings) {
+                B2A_CHECK(sp.has_embed, B2A_ERR_MODEL_NOT_INITIALIZED, "a tied head needs the embedding");
+                lm_head = embed.p;   // embedTokens.asLinear (LlamaTTS.swift:563)
+            } else {
+                upload_bf16(tt, sp.head.empty() ? std::string("lm_head.weight") : sp.head, (int64_t)c.vocab_size * H, lm_head_w, 0, (size_t)c.vocab_size * H);
+                lm_head = lm_head_w.p;
+            }
+        }
         layers.resize(c.num_hidden_layers);
         std::vector<bf16> tmp;
         for (int l = 0; l < c.num_hidden_layers; ++l) {
-            const std::string p = "model.layers." + std::to_string(l) + ".";
+            const std::string p = sp.prefix + "layers." + std::to_string(l) + ".";
+            if (sp.qk_norm) {
+                std::vector<float> qn = tt.f32(p + "self_attn.q_norm.weight", HD), kn = tt.f32(p + "self_attn.k_norm.weight", HD);
+                layers[l].qnorm.upload(qn.data(), HD);
+                layers[l].knorm.upload(kn.data(), HD);
+            }
             LayerW& L = layers[l];
             const size_t qkv_n = (size_t)(NQ + 2 * NKV) * H;
             upload_bf16(tt, p + "self_attn.q_proj.weight", (int64_t)NQ * H, L.wqkv, 0, qkv_n);
@@ -1421,13 +1534,20 @@ struct b2a_tts {
             // gate / up rows interleaved: row 2n = gate_n, row 2n+1 = up_n
             const b2a_tensor& tg = tt.get(p + "mlp.gate_proj.weight");
             const b2a_tensor& tu = tt.get(p + "mlp.up_proj.weight");
-            B2A_CHECK(tg.dtype == B2A_DTYPE_BF16 && tu.dtype == B2A_DTYPE_BF16 && TensorTable::numel(tg) == (int64_t)I * H &&
-                          TensorTable::numel(tu) == (int64_t)I * H,
+            B2A_CHECK(tg.dtype == tu.dtype && (tg.dtype == B2A_DTYPE_BF16 || tg.dtype == B2A_DTYPE_F32) &&
+                          TensorTable::numel(tg) == (int64_t)I * H && TensorTable::numel(tu) == (int64_t)I * H,
                       B2A_ERR_MODEL_NOT_INITIALIZED, "bad gate/up projection: " + p);
             tmp.resize((size_t)2 * I * H);
             for (int n = 0; n < I; ++n) {
-                memcpy(&tmp[(size_t)(2 * n) * H], (const bf16*)tg.data + (size_t)n * H, H * sizeof(bf16));
-                memcpy(&tmp[(size_t)(2 * n + 1) * H], (const bf16*)tu.data + (size_t)n * H, H * sizeof(bf16));
+                if (tg.dtype == B2A_DTYPE_BF16) {
+                    memcpy(&tmp[(size_t)(2 * n) * H], (const bf16*)tg.data + (size_t)n * H, H * sizeof(bf16));
+                    memcpy(&tmp[(size_t)(2 * n + 1) * H], (const bf16*)tu.data + (size_t)n * H, H * sizeof(bf16));
+                } else {
+                    for (int k = 0; k < H; ++k) {
+                        tmp[(size_t)(2 * n) * H + k] = __float2bfloat16_rn(((const float*)tg.data)[(size_t)n * H + k]);
+                        tmp[(size_t)(2 * n + 1) * H + k] = __float2bfloat16_rn(((const float*)tu.data)[(size_t)n * H + k]);
+                    }
+                }
             }
             L.wgu.alloc(tmp.size());
             B2A_CUDA(cudaMemcpy(L.wgu.p, tmp.data(), tmp.size() * sizeof(bf16), cudaMemcpyHostToDevice));
@@ -1435,13 +1555,14 @@ struct b2a_tts {
             L.ln1.upload(g1.data(), H);
             L.ln2.upload(g2.data(), H);
         }
-        std::vector<float> gf = tt.f32("model.norm.weight", H);
+        std::vector<float> gf = tt.f32(sp.prefix + "norm.weight", H);
         final_ln.upload(gf.data(), H);
         alloc_state();
     }
 
     // random-init weights generated on the device (b2a_tts_create_random)
-    b2a_tts(int dev, const b2a_llama_config& c, float std, unsigned long long seed, b2a_snac* sn) : device(dev), cfg(c), snac(sn) {
+    b2a_tts(int dev, const b2a_llama_config& c, float std, unsigned long long seed, b2a_snac* sn, const StackSpec& sp = StackSpec())
+        : device(dev), cfg(c), snac(sn), spec(sp) {
         check_config();
         const int H = c.hidden_size, I = c.intermediate_size, nq = c.num_attention_heads, nkv = c.num_key_value_heads;
         const int NQ = nq * HD, NKV = nkv * HD;
@@ -1456,11 +1577,14 @@ struct b2a_tts {
             fill_f32_kernel<<<cdiv(n, 256), 256, 0, stream>>>(d.p, n, 1.0f);
             count_launch();
         };
-        rnd(embed, (size_t)c.vocab_size * H);
-        if (c.tie_word_embeddings) lm_head = embed.p;
-        else { rnd(lm_head_w, (size_t)c.vocab_size * H); lm_head = lm_head_w.p; }
+        if (sp.has_embed) rnd(embed, (size_t)c.vocab_size * H);
+        if (sp.has_head) {
+            if (sp.head.empty() && c.tie_word_embeddings && sp.has_embed) lm_head = embed.p;
+            else { rnd(lm_head_w, (size_t)c.vocab_size * H); lm_head = lm_head_w.p; }
+        }
         layers.resize(c.num_hidden_layers);
         for (auto& L : layers) {
+            if (sp.qk_norm) { ones(L.qnorm, HD); ones(L.knorm, HD); }
             rnd(L.wqkv, (size_t)(NQ + 2 * NKV) * H);
             rnd(L.wo, (size_t)H * NQ);
             rnd(L.wgu, (size_t)2 * I * H);
@@ -1549,9 +1673,10 @@ struct b2a_tts {
     static constexpr int L2PF_DEFAULT = 0;
 
     void tc_gemm(const CUtensorMap& tmW, const CUtensorMap& tmX, int op, float* yout, bf16* actout, int B, int M, int K,
-                 cudaStream_t s, L2Prefetch pf = L2Prefetch{nullptr, 0}) {
+                 cudaStream_t s, L2Prefetch pf = L2Prefetch{nullptr, 0}, const float* rstd_ss = nullptr) {
         tc::Args a{};
         a.pf_ptr = pf.ptr; a.pf_bytes = pf.bytes;
+        a.rstd_ss = rstd_ss; a.rstd_parts = fused_parts; a.rstd_inv_h = 1.0f / (float)cfg.hidden_size; a.rstd_eps = cfg.rms_norm_eps;
         a.out_f32 = yout; a.out_bf16 = actout; a.M = M; a.N = B; a.K = K;
         a.m_tiles = cdiv(M, tc::BM); a.k_blocks = K / tc::BK;
         a.stages = 6;   // 6 x 18 KB ring: two GEMM CTAs (this kernel's and the next kernel's prefetching one) fit per SM
@@ -1604,38 +1729,96 @@ struct b2a_tts {
         return e && strstr(e, what) != nullptr;
     }
 
+    // o_proj / down_proj as a cluster split-K GEMM with the residual add and the next norm fused into the leader's epilogue
+    void splitk_gemm(const CUtensorMap& tmW, const CUtensorMap& tmX, int M, int K, const float* gain, float* ss, int B, cudaStream_t s) {
+        tc::SplitArgs a{};
+        a.M = M; a.N = B; a.K = K; a.k_blocks = K / tc::BK; a.stages = 5;
+        a.h = x.p; a.gain = gain; a.xn = xn.p; a.ss = ss;
+        a.rstd_ss = nullptr; a.rstd_parts = 0; a.rstd_inv_h = 0.f; a.rstd_eps = 0.f;
+        tc::launch_splitk(tmW, tmX, a, cdiv(M, tc::BM), std::max(1, std::min(fused_cluster, a.k_blocks)), s);
+    }
+    // The fused-norm step: embed -> raw norm -> L x [qkv gemm (rstd in the epilogue) -> attention (clears q|k|v) -> o split-K (+ residual,
+    // norm 2) -> gate/up gemm (rstd, SwiGLU) -> down split-K (+ residual, next layer's norm 1 / the final norm)].  Leaves the residual
+    // stream in x, xn = hi/lo of x * final_norm_gain and its sums of squares in ss_b: the lm head GEMM applies rstd itself.
+    void run_layers_fused(int B, cudaStream_t s) {
+        const int H = cfg.hidden_size, I = cfg.intermediate_size, nq = cfg.num_attention_heads, nkv = cfg.num_key_value_heads;
+        const int NQ = nq * HD, NKV = nkv * HD, L = cfg.num_hidden_layers;
+        if (x_ext) launch_pdl(ext_embed_kernel, dim3(B), dim3(256), 0, s, x_ext, x.p, y.p, H);
+        else launch_pdl(embed_kernel, dim3(B), dim3(256), 0, s, tokens.p, embed.p, x.p, y.p, H, cfg.vocab_size);
+        launch_pdl(add_rmsnorm_kernel, dim3(B), dim3(RN_THREADS), 0, s, x.p, (float*)nullptr, layers[0].ln1.p, xn.p, H, cfg.rms_norm_eps,
+                   (float*)nullptr, (float*)nullptr, 0, LO_ROW, L2Prefetch{nullptr, 0}, (float*)nullptr, ss_b.p, fused_parts);
+        const size_t kv_layer = (size_t)cfg.max_batch * nkv * cfg.max_context * HD;
+        for (int l = 0; l < L; ++l) {
+            LayerW& Lw = layers[l];
+            tc_gemm(tm_qkv[l], tmx_xn, OP_QKV, qkv.p, nullptr, B, NQ + 2 * NKV, H, s, L2Prefetch{nullptr, 0}, ss_b.p);
+            AttnArgs aa{qkv.p, pos.p, freqs.p, kcache.p + l * kv_layer, vcache.p + l * kv_layer, attn.p, part_o.p, part_ml.p,
+                        at_counters.p, nq, nkv, cfg.max_context, at_splits, 1.0f / sqrtf((float)HD), L2Prefetch{nullptr, 0},
+                        spec.qk_norm ? Lw.qnorm.p : nullptr, spec.qk_norm ? Lw.knorm.p : nullptr, cfg.rms_norm_eps, 1};
+            attn_launch(aa, B, s);
+            splitk_gemm(tm_o[l], tmx_attn, H, NQ, Lw.ln2.p, ss_a.p, B, s);
+            tc_gemm(tm_gu[l], tmx_xn, OP_GU, nullptr, act.p, B, 2 * I, H, s, L2Prefetch{nullptr, 0}, ss_a.p);
+            splitk_gemm(tm_down[l], tmx_act, H, I, l + 1 < L ? layers[l + 1].ln1.p : final_ln.p, ss_b.p, B, s);
+        }
+    }
+    int launches_layers_fused() const { return 2 + cfg.num_hidden_layers * 5; }
+
     // embed(tokens) -> all layers; leaves the residual stream in x and the last MLP output in y
     void run_layers(int B, cudaStream_t s) {
+        if (fused && !trace_on) { run_layers_fused(B, s); return; }
         const int H = cfg.hidden_size, nq = cfg.num_attention_heads, nkv = cfg.num_key_value_heads;
         const int QKV_N = (nq + 2 * nkv) * HD, G = nq / nkv;
-        launch_pdl(embed_kernel, dim3(B), dim3(256), 0, s, tokens.p, embed.p, x.p, y.p, H, cfg.vocab_size);
+        if (x_ext) launch_pdl(ext_embed_kernel, dim3(B), dim3(256), 0, s, x_ext, x.p, y.p, H);
+        else launch_pdl(embed_kernel, dim3(B), dim3(256), 0, s, tokens.p, embed.p, x.p, y.p, H, cfg.vocab_size);
         const size_t kv_layer = (size_t)cfg.max_batch * nkv * cfg.max_context * HD;
         for (int l = 0; l < cfg.num_hidden_layers; ++l) {
             LayerW& L = layers[l];
             if (!skip("norm"))
             launch_pdl(add_rmsnorm_kernel, dim3(B), dim3(RN_THREADS), 0, s, x.p, l == 0 ? (float*)nullptr : y.p, L.ln1.p, xn.p, H,
                        cfg.rms_norm_eps, trace_on ? trace.p + (size_t)(2 * l) * 8 * H : (float*)nullptr, (float*)nullptr, 0, LO_ROW,
-                       pf_of(L2_NORM1, l));
+                       pf_of(L2_NORM1, l), (float*)nullptr, (float*)nullptr, 0);
             if (!skip("gemm") && !skip("qkv")) gemm(OP_QKV, l, B, s);
             AttnArgs aa{qkv.p, pos.p, freqs.p, kcache.p + l * kv_layer, vcache.p + l * kv_layer, attn.p, part_o.p, part_ml.p,
-                        at_counters.p, nq, nkv, cfg.max_context, at_splits, 1.0f / sqrtf((float)HD), pf_of(L2_ATTN, l)};
+                        at_counters.p, nq, nkv, cfg.max_context, at_splits, 1.0f / sqrtf((float)HD), pf_of(L2_ATTN, l),
+                        spec.qk_norm ? L.qnorm.p : nullptr, spec.qk_norm ? L.knorm.p : nullptr, cfg.rms_norm_eps, 0};
             if (!skip("attn")) attn_launch(aa, B, s);
             if (!skip("gemm") && !skip("o_proj")) gemm(OP_O, l, B, s);
             // also zeroes this row of q|k|v so the next layer's stream-K QKV GEMM can accumulate into it
             if (!skip("norm"))
             launch_pdl(add_rmsnorm_kernel, dim3(B), dim3(RN_THREADS), 0, s, x.p, y.p, L.ln2.p, xn.p, H, cfg.rms_norm_eps,
-                       trace_on ? trace.p + (size_t)(2 * l + 1) * 8 * H : (float*)nullptr, qkv.p, QKV_N, LO_ROW, pf_of(L2_NORM2, l));
+                       trace_on ? trace.p + (size_t)(2 * l + 1) * 8 * H : (float*)nullptr, qkv.p, QKV_N, LO_ROW, pf_of(L2_NORM2, l), (float*)nullptr, (float*)nullptr, 0);
             if (!skip("gemm") && !skip("gate")) gemm(OP_GU, l, B, s);
             if (!skip("gemm") && !skip("down")) gemm(OP_DOWN, l, B, s);
         }
         (void)G;
     }
 
-    void run_lm_head(int B, cudaStream_t s) {
+    void run_final_norm(int B, cudaStream_t s) {
+        if (fused && !trace_on) {   // x, xn (un-normalised) and ss_b are already final: only row N1 needs the fp32 normalised hidden
+            if (normed_out)
+                launch_pdl(finalize_norm_kernel, dim3(B), dim3(256), 0, s, (const float*)x.p, (const float*)final_ln.p, (const float*)ss_b.p, fused_parts,
+                           normed_out, cfg.hidden_size, cfg.rms_norm_eps);
+            return;
+        }
         launch_pdl(add_rmsnorm_kernel, dim3(B), dim3(RN_THREADS), 0, s, x.p, y.p, final_ln.p, xn.p, cfg.hidden_size, cfg.rms_norm_eps,
                    trace_on ? trace.p + (size_t)(2 * cfg.num_hidden_layers) * 8 * cfg.hidden_size : (float*)nullptr, (float*)nullptr, 0, LO_ROW,
-                   L2Prefetch{nullptr, 0});
+                   L2Prefetch{nullptr, 0}, normed_out, (float*)nullptr, 0);
+    }
+    void run_lm_head(int B, cudaStream_t s) {
+        run_final_norm(B, s);
+        if (fused && !trace_on) tc_gemm(tm_lm, tmx_xn, OP_LM, logits.p, nullptr, B, cfg.vocab_size, cfg.hidden_size, s, L2Prefetch{nullptr, 0}, ss_b.p);
+        else gemm(OP_LM, -1, B, s);
+    }
+    // after prefill_batched's gather_last (x, y hold the last position un-added): always the stand-alone norm + plain GEMM
+    void run_lm_head_after_prefill(int B, cudaStream_t s) {
+        launch_pdl(add_rmsnorm_kernel, dim3(B), dim3(RN_THREADS), 0, s, x.p, y.p, final_ln.p, xn.p, cfg.hidden_size, cfg.rms_norm_eps,
+                   (float*)nullptr, (float*)nullptr, 0, LO_ROW, L2Prefetch{nullptr, 0}, (float*)nullptr, (float*)nullptr, 0);
         gemm(OP_LM, -1, B, s);
+    }
+    // a head the caller owns (row N1: the code predictor's 15 lm heads): logits_out[b, :M] = W[M, H] * normed hidden
+    void run_head(const CUtensorMap& tmW, const bf16* W, int M, float* logits_out, int B, cudaStream_t s) {
+        if (use_tc) tc_gemm(tmW, tmx_xn, OP_LM, logits_out, nullptr, B, M, cfg.hidden_size, s, L2Prefetch{nullptr, 0},
+                            (fused && !trace_on) ? ss_b.p : nullptr);
+        else gemv_nb(OP_LM, W, xn.p, logits_out, nullptr, M, cfg.hidden_size, s);
     }
     // logits are [8, V] row-major.
 
@@ -1648,7 +1831,7 @@ struct b2a_tts {
         return ((size_t)2 * L * HD + (size_t)G * PA_QT * HD) * sizeof(float);
     }
     bool can_batch_prefill(int L) const {
-        return use_tc && use_batched_prefill && L >= 2 && L <= PA_MAXL && pattn_smem(L) <= 220 * 1024;
+        return use_tc && use_batched_prefill && spec.has_embed && !spec.qk_norm && L >= 2 && L <= PA_MAXL && pattn_smem(L) <= 220 * 1024;
     }
 
     // D[T, M] = X[T, K] W^T for all prompt tokens: 128-column tiles (64 tokens as hi/lo), CTAs own whole tiles
@@ -1692,7 +1875,7 @@ struct b2a_tts {
         for (int l = 0; l < cfg.num_hidden_layers; ++l) {
             LayerW& Lw = layers[l];
             launch_pdl(add_rmsnorm_kernel, dim3(T), dim3(RN_THREADS), 0, s, xp.p, l == 0 ? (float*)nullptr : yp.p, Lw.ln1.p, xnp.p, H,
-                       cfg.rms_norm_eps, (float*)nullptr, (float*)nullptr, 0, PF_HALF, L2Prefetch{nullptr, 0});
+                       cfg.rms_norm_eps, (float*)nullptr, (float*)nullptr, 0, PF_HALF, L2Prefetch{nullptr, 0}, (float*)nullptr, (float*)nullptr, 0);
             pf_gemm(tm_qkv[l], tmp_xn, tc::EPI_STORE, qkvp.p, nullptr, T, QKV_N, H, s);
             PrefillAttnArgs pa{qkvp.p, rope_tab.p, kcache.p + l * kv_layer, vcache.p + l * kv_layer, attnp.p, nq, nkv,
                                cfg.max_context, L, 1.0f / sqrtf((float)HD)};
@@ -1709,7 +1892,7 @@ struct b2a_tts {
             count_launch();
             pf_gemm(tm_o[l], tmp_attn, tc::EPI_STORE, yp.p, nullptr, T, H, NQ, s);
             launch_pdl(add_rmsnorm_kernel, dim3(T), dim3(RN_THREADS), 0, s, xp.p, yp.p, Lw.ln2.p, xnp.p, H, cfg.rms_norm_eps,
-                       (float*)nullptr, (float*)nullptr, 0, PF_HALF, L2Prefetch{nullptr, 0});
+                       (float*)nullptr, (float*)nullptr, 0, PF_HALF, L2Prefetch{nullptr, 0}, (float*)nullptr, (float*)nullptr, 0);
             pf_gemm(tm_gu[l], tmp_xn, tc::EPI_SWIGLU, nullptr, actp.p, T, 2 * I, H, s);
             pf_gemm(tm_down[l], tmp_act, tc::EPI_STORE, yp.p, nullptr, T, H, I, s);
         }
@@ -1751,8 +1934,8 @@ struct b2a_tts {
         B2A_CUDA(cudaGraphInstantiate(&g_prefill, g, 0));
         cudaGraphDestroy(g);
         g_nb = B; g_args = sa; g_L = L;
-        launches_step = 1 + cfg.num_hidden_layers * 7 + 2 + 1;
-        launches_prefill = 1 + cfg.num_hidden_layers * 7 + 1;
+        launches_step = fused ? launches_layers_fused() + 1 + 1 : 1 + cfg.num_hidden_layers * 7 + 2 + 1;
+        launches_prefill = fused ? launches_layers_fused() + 1 : 1 + cfg.num_hidden_layers * 7 + 1;
     }
     int g_L = 0, launches_step = 0, launches_prefill = 0;
 };
@@ -1790,10 +1973,19 @@ static double now_s() {
 }
 
 // shared body of b2a_tts_generate / _dev.  ids_on_device: input ids pointer is a device pointer.
+// chunked audio emission during generation (row N2): every `frames_per_chunk` new 7-token frames of a row are decoded with
+// `left_context` already-emitted frames in front (the codec is convolutional: the context absorbs the left edge) and handed to
+// on_audio; the samples of the context frames are dropped.
+struct StreamSpec {
+    int frames_per_chunk = 0;     // 0: no streaming
+    int left_context = 0;
+    b2a_audio_cb on_audio = nullptr;
+};
+
 static void tts_generate_impl(b2a_tts* h, const int32_t* input_ids, bool ids_on_device, int32_t B, int32_t L,
                               const b2a_gen_params* gp, int32_t* tokens_out, int32_t* n_tokens_out, float* wave_out,
                               bool wave_on_device, int64_t wave_cap, int64_t* wave_len, b2a_gen_info* info,
-                              b2a_token_cb on_token, void* user) {
+                              b2a_token_cb on_token, void* user, const StreamSpec& ss = StreamSpec()) {
     B2A_CHECK(h && input_ids && gp, B2A_ERR_INVALID_INPUT, "tts generate: null argument");
     B2A_CHECK(B >= 1 && B <= h->cfg.max_batch, B2A_ERR_INVALID_INPUT, "tts generate: batch exceeds max_batch");
     B2A_CHECK(L >= 1, B2A_ERR_INVALID_INPUT, "tts generate: empty prompt");
@@ -1834,7 +2026,7 @@ static void tts_generate_impl(b2a_tts* h, const int32_t* input_ids, bool ids_on_
     int steps = 0;
     if (h->can_batch_prefill(L)) {
         h->prefill_batched(B, L, s);
-        h->run_lm_head(B, s);
+        h->run_lm_head_after_prefill(B, s);
         launch_pdl(sample_kernel, dim3(B), dim3(SM_THREADS), 0, s, sa);
         steps = 1;
     } else {
@@ -1848,6 +2040,53 @@ static void tts_generate_impl(b2a_tts* h, const int32_t* input_ids, bool ids_on_
     bool cancelled = false;
     int streamed = 0;
     std::vector<int> h_tok;
+    // ---- streaming audio emission state
+    const bool streaming = ss.frames_per_chunk > 0 && ss.on_audio;
+    if (streaming) B2A_CHECK(h->snac && !ids_on_device, B2A_ERR_MODEL_NOT_INITIALIZED, "SNAC model not loaded");
+    std::vector<int> emitted(B, 0), s_prompt, s_tok, s_ng(B);
+    std::vector<float> s_wave;
+    double codec_stream_t = 0;
+    if (streaming) { s_prompt.assign(input_ids, input_ids + (size_t)B * L); s_tok.resize((size_t)B * MT); }
+    auto emit_audio = [&](bool final_call) {
+        const double c0 = now_s();
+        B2A_CUDA(cudaMemcpy(s_ng.data(), h->n_gen.p, B * sizeof(int), cudaMemcpyDeviceToHost));
+        B2A_CUDA(cudaMemcpy(s_tok.data(), h->out_tokens.p, (size_t)B * MT * sizeof(int), cudaMemcpyDeviceToHost));
+        const int64_t hop = b2a_snac_hop_length(h->snac);
+        for (int b = 0; b < B; ++b) {
+            const int ng = std::min(s_ng[b], MT);
+            std::vector<int> all(s_prompt.begin() + (size_t)b * L, s_prompt.begin() + (size_t)(b + 1) * L);
+            all.insert(all.end(), s_tok.begin() + (size_t)b * MT, s_tok.begin() + (size_t)b * MT + ng);
+            int last = -1;
+            for (int j = 0; j < (int)all.size(); ++j) if (all[j] == TOK_START_OF_SPEECH) last = j;
+            std::vector<int> cl = parse_row(all.data(), (int)all.size(), last);
+            if (h->bench_wrap_codes)
+                for (size_t i = 0; i < cl.size(); ++i) cl[i] = ((cl[i] % 4096) + 4096) % 4096 + 4096 * (int)(i % 7);
+            const int total = (int)cl.size() / 7;
+            while (total - emitted[b] >= ss.frames_per_chunk || (final_call && total > emitted[b])) {
+                const int f1 = final_call ? total : emitted[b] + ss.frames_per_chunk;
+                const int f0 = std::max(0, emitted[b] - ss.left_context);
+                std::vector<int> l1, l2, l3;
+                deinterleave(cl.data() + (size_t)f0 * 7, (f1 - f0) * 7, l1, l2, l3);
+                const int F = f1 - f0;
+                h->d_codes[0].upload(l1.data(), l1.size(), s);
+                h->d_codes[1].upload(l2.data(), l2.size(), s);
+                h->d_codes[2].upload(l3.data(), l3.size(), s);
+                const int64_t T = 4ll * F, wl = T * hop;
+                h->d_wave.alloc((size_t)wl);
+                const int* dc[3] = {h->d_codes[0].p, h->d_codes[1].p, h->d_codes[2].p};
+                B2A_CUDA(cudaStreamSynchronize(s));
+                const int32_t st = b2a_snac_decode_dev(h->snac, dc, 1, T, nullptr, 0, gp->seed + (uint64_t)b, h->d_wave.p, s);
+                B2A_CHECK(st == B2A_OK, B2A_ERR_AUDIO_DECODING_FAILED, std::string("SNAC decode failed: ") + b2a_last_error());
+                const int64_t skip = (int64_t)(emitted[b] - f0) * 4 * hop, n_new = wl - skip;
+                s_wave.resize((size_t)n_new);
+                B2A_CUDA(cudaMemcpyAsync(s_wave.data(), h->d_wave.p + skip, (size_t)n_new * sizeof(float), cudaMemcpyDeviceToHost, s));
+                B2A_CUDA(cudaStreamSynchronize(s));
+                emitted[b] = f1;
+                ss.on_audio(user, b, s_wave.data(), n_new, (final_call && f1 == total) ? 1 : 0);
+            }
+        }
+        codec_stream_t += now_s() - c0;
+    };
     auto stream_tokens = [&]() {   // .token events (LlamaTTS.swift:862), row-major per step
         h_tok.resize((size_t)B * MT);
         std::vector<int> ng(B);
@@ -1863,7 +2102,7 @@ static void tts_generate_impl(b2a_tts* h, const int32_t* input_ids, bool ids_on_
         B2A_CUDA(cudaStreamSynchronize(s));
     }
     while (steps < MT && !(steps == 1 && h->h_flag.p[0] <= 0)) {
-        const int burst = on_token ? 1 : std::min(16, MT - steps);
+        const int burst = on_token ? 1 : std::min(streaming ? 7 : 16, MT - steps);
         for (int i = 0; i < burst; ++i) {
             B2A_CUDA(cudaGraphLaunch(h->g_step, s));
             count_launch(h->launches_step);
@@ -1872,9 +2111,11 @@ static void tts_generate_impl(b2a_tts* h, const int32_t* input_ids, bool ids_on_
         B2A_CUDA(cudaMemcpyAsync(h->h_flag.p, h->n_active.p, sizeof(int), cudaMemcpyDeviceToHost, s));
         B2A_CUDA(cudaStreamSynchronize(s));
         if (on_token) stream_tokens();
+        if (streaming) emit_audio(false);
         if (h->cancel.load()) { cancelled = true; break; }
         if (h->h_flag.p[0] <= 0) break;
     }
+    if (streaming && !cancelled) emit_audio(true);
     const double t2 = now_s();
     B2A_CHECK(!cancelled, B2A_ERR_CANCELLED, "generation cancelled");
 
@@ -1949,7 +2190,7 @@ static void tts_generate_impl(b2a_tts* h, const int32_t* input_ids, bool ids_on_
         info->prefill_time = t1 - t0;
         info->generate_time = t2 - t1;
         info->tokens_per_second = total_gen / std::max(1e-9, t2 - t1);
-        info->codec_time = codec_t;
+        info->codec_time = codec_t + codec_stream_t;
         size_t fr = 0, tot = 0;
         cudaMemGetInfo(&fr, &tot);
         info->peak_memory_gb = (double)(tot - fr) / 1e9;
@@ -1957,6 +2198,18 @@ static void tts_generate_impl(b2a_tts* h, const int32_t* input_ids, bool ids_on_
 }
 
 extern "C" {
+
+int32_t b2a_tts_generate_stream(b2a_tts* h, const int32_t* input_ids, int32_t B, int32_t L, const b2a_gen_params* gp,
+                                int32_t frames_per_chunk, int32_t left_context_frames, int32_t* tokens_out, int32_t* n_tokens_out,
+                                b2a_gen_info* info, b2a_token_cb on_token, b2a_audio_cb on_audio, void* user) {
+    return guarded([&] {
+        B2A_CHECK(on_audio && frames_per_chunk >= 1 && left_context_frames >= 0, B2A_ERR_INVALID_INPUT,
+                  "b2a_tts_generate_stream: needs on_audio, frames_per_chunk >= 1, left_context_frames >= 0");
+        StreamSpec ss;
+        ss.frames_per_chunk = frames_per_chunk; ss.left_context = left_context_frames; ss.on_audio = on_audio;
+        tts_generate_impl(h, input_ids, false, B, L, gp, tokens_out, n_tokens_out, nullptr, false, 0, nullptr, info, on_token, user, ss);
+    });
+}
 
 int32_t b2a_tts_create(int32_t device, const b2a_llama_config* cfg, const b2a_tensor* tensors, int32_t n, b2a_snac* snac,
                        b2a_tts** out) {
@@ -2173,3 +2426,476 @@ void b2a_tts_destroy(b2a_tts* h) { delete h; }
 
 }  // extern "C"
 
+// ================================================================================================
+// Qwen3-TTS talker + code predictor on the same engine.
+//   Qwen3TTSTalker.swift:127-366, Qwen3TTSCodePredictor.swift:14-243, Qwen3TTS.swift:380-495 (frame loop), :1003-1118 (sampleToken)
+// Two b2a_tts stacks (talker: inputs are embeddings, untied codec_head; predictor: 5 layers, heads owned here) share one stream.
+// One frame = ONE CUDA graph: talker step -> sampler -> [hidden, embed(c0)] + 14 more predictor steps (cache positions 0..16 are
+// simply overwritten every frame = the reference's per-frame cache trim) -> summed-embedding feedback + bookkeeping.
+// ================================================================================================
+namespace b2a {
+
+// dst[b, :] = float(table[ids[b * id_stride + id_col], :]);  optionally pos[b] = pos_value (the predictor's cache position)
+__global__ void q3_gather_kernel(const bf16* __restrict__ table, int rows, const int* __restrict__ ids, int id_stride, int id_col,
+                                 float* __restrict__ dst, int H, int* pos, int pos_value) {
+    const int b = blockIdx.x;
+    pdl_trigger();
+    pdl_wait();
+    int t = ids[b * id_stride + id_col];
+    t = min(max(t, 0), rows - 1);
+    for (int i = threadIdx.x; i < H; i += blockDim.x) dst[(long long)b * H + i] = __bfloat162float(table[(long long)t * H + i]);
+    if (pos && threadIdx.x == 0) pos[b] = pos_value;
+}
+// dst[b, :] = src[b * src_stride + :]; optionally pos[b] = pos_value (pos_value < 0: pos untouched)
+__global__ void q3_copy_rows_kernel(const float* __restrict__ src, long long src_stride, float* __restrict__ dst, int H, int* pos, int pos_value) {
+    const int b = blockIdx.x;
+    pdl_trigger();
+    pdl_wait();
+    for (int i = threadIdx.x; i < H; i += blockDim.x) dst[(long long)b * H + i] = src[(long long)b * src_stride + i];
+    if (pos && pos_value >= 0 && threadIdx.x == 0) pos[b] = pos_value;
+}
+// y[t, o] = act(b[o] + sum_k W[o, k] x[t, k]); bf16 W, fp32 x / y; one warp per output, grid (ceil(O / 8), T).  The prompt's
+// ResizeMLP only (text_projection, Qwen3TTSTalker.swift:209-221): a few dozen rows per utterance, off the frame loop.
+__global__ void q3_linear_kernel(const bf16* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ x, float* __restrict__ y,
+                                 int O, int K, int silu) {
+    const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), t = blockIdx.y, lane = threadIdx.x & 31;
+    if (o >= O) return;
+    float acc = 0.f;
+    for (int k = lane; k < K; k += 32) acc = fmaf(__bfloat162float(W[(long long)o * K + k]), x[(long long)t * K + k], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+        acc += bias ? bias[o] : 0.f;
+        y[(long long)t * O + o] = silu ? acc / (1.0f + __expf(-acc)) : acc;
+    }
+}
+
+struct Q3Feedback {
+    const bf16* codec_emb; int codec_rows;
+    const bf16* const* cp_emb;   // device array of G-1 tables [cp_vocab, H]
+    int cp_rows;
+    const int* codes;            // [8, G] this frame
+    const float* trailing;       // [B, n_max, H]
+    const int* n_trailing;       // [B]
+    int n_max;
+    const float* pad;            // [H]
+    float* x_in;                 // [8, H] next talker input
+    int* talker_pos;             // [8]
+    int* row_frame;              // [8] frames stepped so far (= index of the trailing text row to consume)
+    int* out_codes;              // [B, max_tokens, G]
+    int* n_frames; int* done; int* n_active;
+    int G, H, max_tokens, eos, mask_eos;
+};
+// x_next = text + codec_embed(c0) + sum_i predictor_embed_i(c_{i+1})  (Qwen3TTS.swift:470-487) + per-row bookkeeping (:424-428)
+__global__ void q3_feedback_kernel(Q3Feedback a) {
+    const int b = blockIdx.x;
+    pdl_trigger();
+    pdl_wait();
+    const int f = a.row_frame[b];
+    const float* text = f < a.n_trailing[b] ? a.trailing + ((long long)b * a.n_max + f) * a.H : a.pad;
+    const int* c = a.codes + b * a.G;
+    for (int i = threadIdx.x; i < a.H; i += blockDim.x) {
+        float e = __bfloat162float(a.codec_emb[(long long)min(max(c[0], 0), a.codec_rows - 1) * a.H + i]);
+        for (int g = 1; g < a.G; ++g) e += __bfloat162float(a.cp_emb[g - 1][(long long)min(max(c[g], 0), a.cp_rows - 1) * a.H + i]);
+        a.x_in[(long long)b * a.H + i] = text[i] + e;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        a.row_frame[b] = f + 1;
+        a.talker_pos[b] += 1;
+        if (!a.done[b]) {
+            if (c[0] == a.eos && !a.mask_eos) { a.done[b] = 1; atomicSub(a.n_active, 1); }
+            else {
+                const int n = a.n_frames[b];
+                if (n < a.max_tokens) for (int g = 0; g < a.G; ++g) a.out_codes[((long long)b * a.max_tokens + n) * a.G + g] = c[g];
+                a.n_frames[b] = n + 1;
+                if (n + 1 >= a.max_tokens) { a.done[b] = 1; atomicSub(a.n_active, 1); }
+            }
+        }
+    }
+}
+__global__ void q3_init_rows_kernel(int B, int L, int* talker_pos, int* row_frame, int* n_frames, int* done, int* n_active, unsigned* seen, int words) {
+    const int b = threadIdx.x;
+    if (b == 0) *n_active = B;
+    if (b < 8) { talker_pos[b] = L - 1; row_frame[b] = 0; n_frames[b] = 0; done[b] = b < B ? 0 : 1; }
+    for (int i = threadIdx.x; i < 8 * words; i += blockDim.x) seen[i] = 0u;
+}
+// bench only: the talker never emits EOS -- its logit is dropped before the sampler sees the row
+__global__ void q3_mask_eos_kernel(float* logits, int V, int eos) {
+    if (threadIdx.x == 0 && eos >= 0 && eos < V) logits[(long long)blockIdx.x * V + eos] = -INFINITY;
+}
+
+}  // namespace b2a
+
+struct b2a_qwen3_talker {
+    int device;
+    b2a_qwen3_talker_config cfg;
+    b2a_tts* talker = nullptr;
+    b2a_tts* pred = nullptr;
+    cudaStream_t stream = nullptr;        // = talker->stream
+    DBuf<bf16> codec_emb, text_emb, fc1_w, fc2_w;
+    DBuf<float> fc1_b, fc2_b;
+    std::vector<DBuf<bf16>> cp_emb, cp_head;
+    std::vector<CUtensorMap> tm_cp_head;
+    DBuf<const bf16*> cp_emb_ptrs;
+    DBuf<float> x_in, hid, px, trailing, pad, embeds, tmp_a, tmp_b;
+    DBuf<int> codes, out_codes, n_frames, done, n_active, row_frame, n_trailing, ids;
+    DBuf<unsigned> seen;
+    HBuf<int> h_flag;
+    cudaGraphExec_t g_frame = nullptr;
+    b2a_qwen3_gen_params g_params{};
+    int g_B = 0, g_max_tokens = 0, g_nmax = 0, g_mask = -1;
+    const float* g_trailing = nullptr;
+    int launches_frame = 0;
+    int bench_mask_eos = 0;
+    std::atomic<int> cancel{0};
+
+    ~b2a_qwen3_talker() {
+        if (g_frame) cudaGraphExecDestroy(g_frame);
+        delete pred;
+        delete talker;
+    }
+    int G() const { return cfg.num_code_groups; }
+    int H() const { return cfg.hidden_size; }
+
+    static b2a_llama_config stack_cfg(const b2a_qwen3_talker_config& c, bool predictor) {
+        b2a_llama_config l{};
+        l.hidden_size = predictor ? c.cp_hidden_size : c.hidden_size;
+        l.num_hidden_layers = predictor ? c.cp_num_hidden_layers : c.num_hidden_layers;
+        l.intermediate_size = predictor ? c.cp_intermediate_size : c.intermediate_size;
+        l.num_attention_heads = predictor ? c.cp_num_attention_heads : c.num_attention_heads;
+        l.num_key_value_heads = predictor ? c.cp_num_key_value_heads : c.num_key_value_heads;
+        l.head_dim = predictor ? c.cp_head_dim : c.head_dim;
+        l.vocab_size = predictor ? c.cp_vocab_size : c.vocab_size;
+        l.rms_norm_eps = predictor ? c.cp_rms_norm_eps : c.rms_norm_eps;
+        l.rope_theta = predictor ? c.cp_rope_theta : c.rope_theta;
+        // plain rotate-half RoPE: factor 1 makes Llama3ScaledRoPE's three wavelength bands collapse to base^(2i/d)
+        l.rope_factor = 1.0f; l.rope_low_freq_factor = 1.0f; l.rope_high_freq_factor = 4.0f; l.rope_old_context_len = 8192.0f;
+        l.tie_word_embeddings = 0;
+        l.max_batch = c.max_batch;
+        l.max_context = predictor ? std::max(32, c.num_code_groups + 8) : c.max_context;
+        return l;
+    }
+    static StackSpec talker_spec() { StackSpec s; s.prefix = "model."; s.qk_norm = true; s.has_embed = false; s.head = "codec_head.weight"; s.has_head = true; return s; }
+    static StackSpec pred_spec() { StackSpec s; s.prefix = "code_predictor.model."; s.qk_norm = true; s.has_embed = false; s.has_head = false; return s; }
+
+    void check() {
+        const b2a_qwen3_talker_config& c = cfg;
+        B2A_CHECK(c.head_dim == HD && c.cp_head_dim == HD, B2A_ERR_INVALID_INPUT, "qwen3 talker: head_dim must be 128");
+        B2A_CHECK(c.cp_hidden_size == c.hidden_size, B2A_ERR_INVALID_INPUT,
+                  "qwen3 talker: code predictor hidden size must equal the talker's (small_to_mtp_projection is not implemented)");
+        B2A_CHECK(c.vocab_size >= 1 && c.vocab_size <= q3s::SLOTS && c.cp_vocab_size >= 1 && c.cp_vocab_size <= q3s::SLOTS, B2A_ERR_INVALID_INPUT,
+                  "qwen3 talker: codec vocabularies must be <= 4096");
+        B2A_CHECK(c.num_code_groups >= 2 && c.num_code_groups <= 32, B2A_ERR_INVALID_INPUT, "qwen3 talker: num_code_groups must be in 2..32");
+        B2A_CHECK(c.max_batch >= 1 && c.max_batch <= 8, B2A_ERR_INVALID_INPUT, "qwen3 talker: max_batch must be in 1..8");
+    }
+    void alloc_state() {
+        stream = talker->stream;
+        const int Hh = H();
+        x_in.alloc((size_t)8 * Hh); hid.alloc((size_t)8 * Hh); px.alloc((size_t)8 * Hh); pad.alloc(Hh);
+        B2A_CUDA(cudaMemset(x_in.p, 0, (size_t)8 * Hh * sizeof(float)));
+        B2A_CUDA(cudaMemset(hid.p, 0, (size_t)8 * Hh * sizeof(float)));
+        B2A_CUDA(cudaMemset(px.p, 0, (size_t)8 * Hh * sizeof(float)));
+        codes.alloc((size_t)8 * G()); n_frames.alloc(8); done.alloc(8); n_active.alloc(1); row_frame.alloc(8); n_trailing.alloc(8);
+        B2A_CUDA(cudaMemset(codes.p, 0, (size_t)8 * G() * sizeof(int)));
+        seen.alloc((size_t)8 * cdiv(cfg.vocab_size, 32));
+        h_flag.alloc(16);
+        std::vector<const bf16*> ptrs;
+        for (auto& e : cp_emb) ptrs.push_back(e.p);
+        cp_emb_ptrs.upload(ptrs.data(), ptrs.size());
+        if (pred->use_tc) {
+            tm_cp_head.clear();
+            for (auto& hd : cp_head) tm_cp_head.push_back(tc::make_tmap_bf16(hd.p, cfg.cp_vocab_size, Hh, tc::BM));
+        } else tm_cp_head.resize(cp_head.size());
+        talker->x_ext = x_in.p; talker->normed_out = hid.p;
+        pred->x_ext = px.p;
+        talker->set_batch(8); pred->set_batch(8);
+        B2A_CUDA(cudaDeviceSynchronize());
+    }
+
+    b2a_qwen3_talker(int dev, const b2a_qwen3_talker_config& c, const TensorTable& tt) : device(dev), cfg(c) {
+        check();
+        talker = new b2a_tts(dev, stack_cfg(c, false), tt, nullptr, talker_spec());
+        pred = new b2a_tts(dev, stack_cfg(c, true), tt, nullptr, pred_spec());
+        const int Hh = H(), TH = c.text_hidden_size;
+        b2a_tts::upload_bf16(tt, "model.codec_embedding.weight", (int64_t)c.vocab_size * Hh, codec_emb, 0, (size_t)c.vocab_size * Hh);
+        b2a_tts::upload_bf16(tt, "model.text_embedding.weight", (int64_t)c.text_vocab_size * TH, text_emb, 0, (size_t)c.text_vocab_size * TH);
+        b2a_tts::upload_bf16(tt, "text_projection.linear_fc1.weight", (int64_t)TH * TH, fc1_w, 0, (size_t)TH * TH);
+        b2a_tts::upload_bf16(tt, "text_projection.linear_fc2.weight", (int64_t)Hh * TH, fc2_w, 0, (size_t)Hh * TH);
+        std::vector<float> b1 = tt.f32("text_projection.linear_fc1.bias", TH), b2 = tt.f32("text_projection.linear_fc2.bias", Hh);
+        fc1_b.upload(b1.data(), TH); fc2_b.upload(b2.data(), Hh);
+        cp_emb.resize(G() - 1); cp_head.resize(G() - 1);
+        for (int i = 0; i < G() - 1; ++i) {
+            b2a_tts::upload_bf16(tt, "code_predictor.model.codec_embedding." + std::to_string(i) + ".weight", (int64_t)c.cp_vocab_size * Hh, cp_emb[i], 0,
+                                 (size_t)c.cp_vocab_size * Hh);
+            b2a_tts::upload_bf16(tt, "code_predictor.lm_head." + std::to_string(i) + ".weight", (int64_t)c.cp_vocab_size * Hh, cp_head[i], 0,
+                                 (size_t)c.cp_vocab_size * Hh);
+        }
+        alloc_state();
+    }
+    // device-drawn weights (bench): every matrix N(0, std^2) bf16, biases 0
+    b2a_qwen3_talker(int dev, const b2a_qwen3_talker_config& c, float std, unsigned long long seed) : device(dev), cfg(c) {
+        check();
+        talker = new b2a_tts(dev, stack_cfg(c, false), std, seed, nullptr, talker_spec());
+        pred = new b2a_tts(dev, stack_cfg(c, true), std, seed + 7777, nullptr, pred_spec());
+        const int Hh = H(), TH = c.text_hidden_size;
+        unsigned long long sd = seed * 7919ull + 3;
+        auto rnd = [&](DBuf<bf16>& d, size_t n) {
+            d.alloc(n);
+            random_bf16_kernel<<<148 * 8, 256, 0, talker->stream>>>(d.p, (long long)n, std, sd++);
+            count_launch();
+        };
+        rnd(codec_emb, (size_t)c.vocab_size * Hh); rnd(text_emb, (size_t)c.text_vocab_size * TH);
+        rnd(fc1_w, (size_t)TH * TH); rnd(fc2_w, (size_t)Hh * TH);
+        fc1_b.alloc(TH); fc2_b.alloc(Hh);
+        B2A_CUDA(cudaMemsetAsync(fc1_b.p, 0, TH * sizeof(float), talker->stream));
+        B2A_CUDA(cudaMemsetAsync(fc2_b.p, 0, Hh * sizeof(float), talker->stream));
+        cp_emb.resize(G() - 1); cp_head.resize(G() - 1);
+        for (int i = 0; i < G() - 1; ++i) { rnd(cp_emb[i], (size_t)c.cp_vocab_size * Hh); rnd(cp_head[i], (size_t)c.cp_vocab_size * Hh); }
+        B2A_CUDA(cudaStreamSynchronize(talker->stream));
+        alloc_state();
+    }
+
+    // ids [n] (device) -> out [n, H]: text_projection(text_embedding(ids)) = fc2(silu(fc1(e)))
+    void embed_text_dev(const int* d_ids, int n, float* d_out, cudaStream_t s) {
+        const int TH = cfg.text_hidden_size, Hh = H();
+        tmp_a.alloc((size_t)n * TH); tmp_b.alloc((size_t)n * TH);
+        q3_gather_kernel<<<n, 256, 0, s>>>(text_emb.p, cfg.text_vocab_size, d_ids, 1, 0, tmp_a.p, TH, nullptr, 0);
+        q3_linear_kernel<<<dim3(cdiv(TH, 8), n), 256, 0, s>>>(fc1_w.p, fc1_b.p, tmp_a.p, tmp_b.p, TH, TH, 1);
+        q3_linear_kernel<<<dim3(cdiv(Hh, 8), n), 256, 0, s>>>(fc2_w.p, fc2_b.p, tmp_b.p, d_out, Hh, TH, 0);
+        count_launch(3);
+        B2A_CUDA(cudaGetLastError());
+    }
+
+    q3s::Args sampler_args(const b2a_qwen3_gen_params& p, bool is_talker, int group) const {
+        q3s::Args a{};
+        a.logits = is_talker ? talker->logits.p : pred->logits.p;
+        a.V = is_talker ? cfg.vocab_size : cfg.cp_vocab_size;
+        a.temperature = p.temperature; a.top_p = p.top_p; a.top_k = p.top_k; a.min_p = p.min_p;
+        a.rep_penalty = is_talker ? p.repetition_penalty : 1.0f;
+        a.eos = is_talker ? cfg.codec_eos_token_id : -1;
+        a.suppress_lo = is_talker ? std::max(cfg.vocab_size - 1024, 0) : 0;      // the special-token block except EOS (:383-385)
+        a.suppress_hi = is_talker ? cfg.vocab_size : 0;
+        a.seen = is_talker ? seen.p : nullptr;
+        a.track = is_talker ? 1 : 0;
+        a.seed = p.seed;
+        a.step = group; a.step_ptr = row_frame.p; a.step_mul = G();
+        a.tokens = nullptr; a.filtered = nullptr;
+        return a;
+    }
+    void talker_step(int B, cudaStream_t s, bool with_head) {
+        talker->run_layers(B, s);
+        if (with_head) talker->run_lm_head(B, s);
+    }
+
+    void capture_frame(int B, const b2a_qwen3_gen_params& p, int max_tokens, int nmax) {
+        if (g_frame && g_B == B && g_max_tokens == max_tokens && g_nmax == nmax && g_mask == bench_mask_eos && g_trailing == trailing.p &&
+            memcmp(&g_params, &p, sizeof(p)) == 0) return;
+        if (g_frame) { cudaGraphExecDestroy(g_frame); g_frame = nullptr; }
+        cudaStream_t s = stream;
+        const int n0 = (int)b2a_launch_count();
+        cudaGraph_t g;
+        B2A_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        // 1. talker step on x_in -> hid (final norm), codec logits -> c0
+        talker_step(B, s, true);
+        if (bench_mask_eos) { q3_mask_eos_kernel<<<B, 32, 0, s>>>(talker->logits.p, cfg.vocab_size, cfg.codec_eos_token_id); count_launch(); }
+        {
+            q3s::Args a = sampler_args(p, true, 0);
+            a.tokens = codes.p; a.tokens_stride = G();
+            q3s::sample_kernel<<<B, q3s::THREADS, 0, s>>>(a);
+            count_launch();
+        }
+        // 2. code predictor: position 0 = the talker's hidden state, position 1 = codec_embed(c0) -> head 0 -> c1, then
+        //    position k + 1 = predictor_embed_{k-1}(c_k) -> head k -> c_{k+1}
+        launch_pdl(q3_copy_rows_kernel, dim3(B), dim3(256), 0, s, (const float*)hid.p, (long long)H(), px.p, H(), pred->pos.p, 0);
+        pred->run_layers(B, s);
+        for (int k = 0; k < G() - 1; ++k) {
+            if (k == 0) launch_pdl(q3_gather_kernel, dim3(B), dim3(256), 0, s, (const bf16*)codec_emb.p, cfg.vocab_size, (const int*)codes.p, G(), 0, px.p, H(), pred->pos.p, 1);
+            else launch_pdl(q3_gather_kernel, dim3(B), dim3(256), 0, s, (const bf16*)cp_emb[k - 1].p, cfg.cp_vocab_size, (const int*)codes.p, G(), k, px.p, H(), pred->pos.p, k + 1);
+            pred->run_layers(B, s);
+            pred->run_final_norm(B, s);
+            pred->run_head(tm_cp_head[k], cp_head[k].p, cfg.cp_vocab_size, pred->logits.p, B, s);
+            q3s::Args a = sampler_args(p, false, k + 1);
+            a.tokens = codes.p + (k + 1); a.tokens_stride = G();
+            q3s::sample_kernel<<<B, q3s::THREADS, 0, s>>>(a);
+            count_launch();
+        }
+        // 3. feedback + bookkeeping
+        Q3Feedback f{codec_emb.p, cfg.vocab_size, cp_emb_ptrs.p, cfg.cp_vocab_size, codes.p, trailing.p, n_trailing.p, nmax, pad.p, x_in.p,
+                     talker->pos.p, row_frame.p, out_codes.p, n_frames.p, done.p, n_active.p, G(), H(), max_tokens, cfg.codec_eos_token_id, bench_mask_eos};
+        launch_pdl(q3_feedback_kernel, dim3(B), dim3(256), 0, s, f);
+        B2A_CUDA(cudaStreamEndCapture(s, &g));
+        B2A_CUDA(cudaGraphInstantiate(&g_frame, g, 0));
+        cudaGraphDestroy(g);
+        launches_frame = (int)b2a_launch_count() - n0;
+        g_B = B; g_params = p; g_max_tokens = max_tokens; g_nmax = nmax; g_mask = bench_mask_eos; g_trailing = trailing.p;
+    }
+
+    // positions 0 .. L-2 of the prompt through the talker (no logits needed); leaves x_in = embeds[:, L-1], talker pos = L-1
+    void prefill(int B, int L, cudaStream_t s) {
+        for (int p = 0; p < L; ++p) {
+            launch_pdl(q3_copy_rows_kernel, dim3(B), dim3(256), 0, s, (const float*)(embeds.p + (size_t)p * H()), (long long)L * H(), x_in.p, H(),
+                       talker->pos.p, p);
+            if (p < L - 1) talker->run_layers(B, s);
+        }
+    }
+};
+
+extern "C" {
+
+int32_t b2a_qwen3_talker_create(int32_t device, const b2a_qwen3_talker_config* cfg, const b2a_tensor* tensors, int32_t n, b2a_qwen3_talker** out) {
+    return guarded([&] {
+        B2A_CHECK(out, B2A_ERR_INVALID_INPUT, "b2a_qwen3_talker_create: null out");
+        *out = nullptr;
+        B2A_CHECK(cfg && tensors && n > 0, B2A_ERR_MODEL_NOT_INITIALIZED, "b2a_qwen3_talker_create: missing config or weights");
+        TensorTable tt(tensors, n);
+        *out = new b2a_qwen3_talker(device, *cfg, tt);
+    });
+}
+int32_t b2a_qwen3_talker_create_random(int32_t device, const b2a_qwen3_talker_config* cfg, float std, uint64_t seed, b2a_qwen3_talker** out) {
+    return guarded([&] {
+        B2A_CHECK(out, B2A_ERR_INVALID_INPUT, "b2a_qwen3_talker_create_random: null out");
+        *out = nullptr;
+        B2A_CHECK(cfg && std > 0.f, B2A_ERR_MODEL_NOT_INITIALIZED, "b2a_qwen3_talker_create_random: missing config");
+        *out = new b2a_qwen3_talker(device, *cfg, std, seed);
+    });
+}
+void* b2a_qwen3_talker_stream(b2a_qwen3_talker* h) { return h ? (void*)h->stream : nullptr; }
+int32_t b2a_qwen3_talker_set_bench_flags(b2a_qwen3_talker* h, int32_t mask_eos) {
+    if (!h) return B2A_ERR_INVALID_INPUT;
+    h->bench_mask_eos = mask_eos != 0;
+    return B2A_OK;
+}
+int32_t b2a_qwen3_talker_cancel(b2a_qwen3_talker* h) {
+    if (!h) return B2A_ERR_INVALID_INPUT;
+    h->cancel.store(1);
+    return B2A_OK;
+}
+void b2a_qwen3_talker_destroy(b2a_qwen3_talker* h) { delete h; }
+
+int32_t b2a_qwen3_talker_embed_text(b2a_qwen3_talker* h, const int32_t* ids, int32_t n, float* out) {
+    return guarded([&] {
+        B2A_CHECK(h && ids && out && n >= 1, B2A_ERR_INVALID_INPUT, "b2a_qwen3_talker_embed_text: bad argument");
+        B2A_CUDA(cudaSetDevice(h->device));
+        for (int i = 0; i < n; ++i) B2A_CHECK(ids[i] >= 0 && ids[i] < h->cfg.text_vocab_size, B2A_ERR_INVALID_INPUT, "b2a_qwen3_talker_embed_text: id out of range");
+        cudaStream_t s = h->stream;
+        h->ids.upload(ids, n, s);
+        h->embeds.alloc((size_t)n * h->H());
+        h->embed_text_dev(h->ids.p, n, h->embeds.p, s);
+        B2A_CUDA(cudaMemcpyAsync(out, h->embeds.p, (size_t)n * h->H() * sizeof(float), cudaMemcpyDeviceToHost, s));
+        B2A_CUDA(cudaStreamSynchronize(s));
+    });
+}
+int32_t b2a_qwen3_talker_embed_codec(b2a_qwen3_talker* h, const int32_t* ids, int32_t n, float* out) {
+    return guarded([&] {
+        B2A_CHECK(h && ids && out && n >= 1, B2A_ERR_INVALID_INPUT, "b2a_qwen3_talker_embed_codec: bad argument");
+        B2A_CUDA(cudaSetDevice(h->device));
+        for (int i = 0; i < n; ++i) B2A_CHECK(ids[i] >= 0 && ids[i] < h->cfg.vocab_size, B2A_ERR_INVALID_INPUT, "b2a_qwen3_talker_embed_codec: id out of range");
+        cudaStream_t s = h->stream;
+        h->ids.upload(ids, n, s);
+        h->embeds.alloc((size_t)n * h->H());
+        q3_gather_kernel<<<n, 256, 0, s>>>(h->codec_emb.p, h->cfg.vocab_size, h->ids.p, 1, 0, h->embeds.p, h->H(), nullptr, 0);
+        count_launch();
+        B2A_CUDA(cudaMemcpyAsync(out, h->embeds.p, (size_t)n * h->H() * sizeof(float), cudaMemcpyDeviceToHost, s));
+        B2A_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+int32_t b2a_qwen3_talker_forward(b2a_qwen3_talker* h, const float* input_embeds, int32_t B, int32_t L, float* logits_out, float* hidden_out) {
+    return guarded([&] {
+        B2A_CHECK(h && input_embeds && B >= 1 && B <= h->cfg.max_batch && L >= 1 && L <= h->cfg.max_context, B2A_ERR_INVALID_INPUT,
+                  "b2a_qwen3_talker_forward: bad argument");
+        B2A_CUDA(cudaSetDevice(h->device));
+        cudaStream_t s = h->stream;
+        h->talker->set_batch(B); h->talker->drop_graphs();
+        h->embeds.upload(input_embeds, (size_t)B * L * h->H(), s);
+        h->prefill(B, L, s);
+        h->talker_step(B, s, true);
+        if (logits_out)
+            B2A_CUDA(cudaMemcpyAsync(logits_out, h->talker->logits.p, (size_t)B * h->cfg.vocab_size * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (hidden_out) B2A_CUDA(cudaMemcpyAsync(hidden_out, h->hid.p, (size_t)B * h->H() * sizeof(float), cudaMemcpyDeviceToHost, s));
+        B2A_CUDA(cudaStreamSynchronize(s));
+        B2A_CUDA(cudaGetLastError());
+    });
+}
+
+int32_t b2a_qwen3_talker_generate(b2a_qwen3_talker* h, const float* input_embeds, int32_t B, int32_t L, const float* trailing_text_hidden,
+                                  const int32_t* n_trailing, int32_t n_trailing_max, const float* tts_pad_embed, const b2a_qwen3_gen_params* gp,
+                                  int32_t* codes_out, int32_t* n_frames_out, b2a_gen_info* info, b2a_frame_cb on_frame, void* user) {
+    return guarded([&] {
+        B2A_CHECK(h && input_embeds && tts_pad_embed && gp && codes_out && n_frames_out, B2A_ERR_INVALID_INPUT, "qwen3 generate: null argument");
+        B2A_CHECK(B >= 1 && B <= h->cfg.max_batch, B2A_ERR_INVALID_INPUT, "qwen3 generate: batch exceeds max_batch");
+        B2A_CHECK(L >= 1 && gp->max_tokens >= 1 && L + gp->max_tokens <= h->cfg.max_context, B2A_ERR_INVALID_INPUT,
+                  "qwen3 generate: prompt + max_tokens exceeds max_context");
+        B2A_CHECK(n_trailing_max >= 0 && (n_trailing_max == 0 || (trailing_text_hidden && n_trailing)), B2A_ERR_INVALID_INPUT,
+                  "qwen3 generate: bad trailing text");
+        B2A_CHECK(gp->top_p > 0.f && gp->repetition_penalty > 0.f, B2A_ERR_INVALID_INPUT, "qwen3 generate: bad sampling parameters");
+        B2A_CUDA(cudaSetDevice(h->device));
+        cudaStream_t s = h->stream;
+        h->cancel.store(0);
+        const int Hh = h->H(), G = h->G(), MT = gp->max_tokens, nmax = std::max(1, n_trailing_max);
+        h->talker->set_batch(B); h->pred->set_batch(B);
+        h->talker->drop_graphs();
+        h->embeds.upload(input_embeds, (size_t)B * L * Hh, s);
+        h->trailing.alloc((size_t)B * nmax * Hh);
+        std::vector<int> nt(8, 0);
+        if (n_trailing_max > 0) {
+            B2A_CUDA(cudaMemcpyAsync(h->trailing.p, trailing_text_hidden, (size_t)B * n_trailing_max * Hh * sizeof(float), cudaMemcpyHostToDevice, s));
+            for (int b = 0; b < B; ++b) {
+                B2A_CHECK(n_trailing[b] >= 0 && n_trailing[b] <= n_trailing_max, B2A_ERR_INVALID_INPUT, "qwen3 generate: n_trailing out of range");
+                nt[b] = n_trailing[b];
+            }
+        }
+        h->n_trailing.upload(nt.data(), 8, s);
+        h->pad.upload(tts_pad_embed, Hh, s);
+        h->out_codes.alloc((size_t)B * MT * G);
+        B2A_CUDA(cudaStreamSynchronize(s));       // nt goes out of scope with the lambda only, but keep uploads ordered before capture
+        h->capture_frame(B, *gp, MT, nmax);
+        const double t0 = now_s();
+        q3_init_rows_kernel<<<1, 256, 0, s>>>(B, L, h->talker->pos.p, h->row_frame.p, h->n_frames.p, h->done.p, h->n_active.p, h->seen.p,
+                                              cdiv(h->cfg.vocab_size, 32));
+        count_launch();
+        h->prefill(B, L, s);
+        B2A_CUDA(cudaStreamSynchronize(s));
+        const double t1 = now_s();
+        int steps = 0, emitted = 0;
+        bool cancelled = false;
+        std::vector<int> hn(8), hc;
+        auto emit = [&]() {          // frames emitted since the last poll -> on_frame
+            B2A_CUDA(cudaMemcpy(hn.data(), h->n_frames.p, 8 * sizeof(int), cudaMemcpyDeviceToHost));
+            hc.resize((size_t)B * MT * G);
+            B2A_CUDA(cudaMemcpy(hc.data(), h->out_codes.p, hc.size() * sizeof(int), cudaMemcpyDeviceToHost));
+            for (int b = 0; b < B; ++b)
+                if (std::min(hn[b], MT) > emitted) on_frame(user, b, emitted, hc.data() + ((size_t)b * MT + emitted) * G);
+            ++emitted;
+        };
+        while (steps < MT) {
+            const int burst = on_frame ? 1 : std::min(4, MT - steps);
+            for (int i = 0; i < burst; ++i) { B2A_CUDA(cudaGraphLaunch(h->g_frame, s)); count_launch(h->launches_frame); }
+            steps += burst;
+            B2A_CUDA(cudaMemcpyAsync(h->h_flag.p, h->n_active.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+            B2A_CUDA(cudaStreamSynchronize(s));
+            if (on_frame) emit();
+            if (h->cancel.load()) { cancelled = true; break; }
+            if (h->h_flag.p[0] <= 0) break;
+        }
+        const double t2 = now_s();
+        B2A_CHECK(!cancelled, B2A_ERR_CANCELLED, "generation cancelled");
+        B2A_CUDA(cudaMemcpy(hn.data(), h->n_frames.p, 8 * sizeof(int), cudaMemcpyDeviceToHost));
+        B2A_CUDA(cudaMemcpy(codes_out, h->out_codes.p, (size_t)B * MT * G * sizeof(int), cudaMemcpyDeviceToHost));
+        int total = 0;
+        for (int b = 0; b < B; ++b) { n_frames_out[b] = std::min(hn[b], MT); total += n_frames_out[b]; }
+        if (info) {
+            info->prompt_token_count = L;
+            info->generation_token_count = total;
+            info->prefill_time = t1 - t0;
+            info->generate_time = t2 - t1;
+            info->tokens_per_second = total / std::max(1e-9, t2 - t1);
+            info->codec_time = 0;
+            size_t fr = 0, tot = 0;
+            cudaMemGetInfo(&fr, &tot);
+            info->peak_memory_gb = (double)(tot - fr) / 1e9;
+        }
+    });
+}
+
+}  // extern "C"

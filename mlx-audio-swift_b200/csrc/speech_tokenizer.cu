@@ -345,7 +345,7 @@ final_conv_kernel(const float* __restrict__ x, const float* __restrict__ st, con
 // ----------------------------------------------------------------------------------------------- weights
 struct IW {                       // implicit-conv weight: [M][taps][cblocks * 64] as bf16 hi / lo, K-major
     DBuf<bf16> hi, lo;
-    DBuf<float> bias;
+    DBuf<float> bias, rscale;     // rscale[m] (fp16 operands only): 1 / the power of two row m is stored times
     CUtensorMap th{}, tl{};
     int M = 0, taps = 1, cblocks = 0, Cin = 0;
     bool has_bias = false;
@@ -362,7 +362,24 @@ struct IW {                       // implicit-conv weight: [M][taps][cblocks * 6
     void build(const std::vector<float>& W /*[M][taps][Cin]*/, int M_, int taps_, int Cin_, int f16) {
         M = M_; taps = taps_; Cin = Cin_; cblocks = cdiv(Cin, tc::BK);
         const size_t K = (size_t)taps * cblocks * tc::BK;
-        const std::vector<float> g = pad_k(W, M, taps, Cin);
+        std::vector<float> g = pad_k(W, M, taps, Cin);
+        if (f16) {
+            // fp16 pairs: a weight of magnitude 0.01 has a SUBNORMAL lo half (|lo| < 2^-11 |w| < 6.1e-5), i.e. ~18 bits instead of 22.
+            // Store row m times 2^e with max|w_m| * 2^e in [8192, 16384) and undo the (exact) scaling in the epilogue.
+            std::vector<float> rs((size_t)M, 1.f);
+            for (int m = 0; m < M; ++m) {
+                float mx = 0.f;
+                for (size_t k = 0; k < K; ++k) mx = std::max(mx, fabsf(g[(size_t)m * K + k]));
+                if (mx > 0.f && std::isfinite(mx)) {
+                    int e = 0;
+                    frexpf(mx, &e);                              // mx = f * 2^e, f in [0.5, 1)
+                    const float sc = ldexpf(1.0f, 14 - e);       // mx * sc in [8192, 16384)
+                    for (size_t k = 0; k < K; ++k) g[(size_t)m * K + k] *= sc;
+                    rs[m] = 1.0f / sc;
+                }
+            }
+            rscale.upload(rs.data(), rs.size());
+        }
         std::vector<uint16_t> h(g.size()), l(g.size());
         for (size_t i = 0; i < g.size(); ++i) split16(g[i], f16, h[i], l[i]);
         hi.upload(reinterpret_cast<const bf16*>(h.data()), h.size());
@@ -634,6 +651,7 @@ struct b2a_speech_tokenizer {
         a.t_tiles = cdiv(a.T, ic::HALF);
         a.bias = W.has_bias ? W.bias.p : nullptr;
         a.f16 = use_f16;
+        a.wscale = use_f16 ? W.rscale.p : nullptr;
         const CUtensorMap tb = make_tmap_planes(in, W.Cin, in_frames, a.B, use_f16);
         const long long tiles = (long long)a.B * a.t_tiles * a.m_tiles;
         launch_pdl(ic::implicit_conv_kernel, dim3((unsigned)std::min<long long>(num_sms, tiles)), dim3(ic::IC_THREADS), ic::SMEM_BYTES, s,
@@ -913,6 +931,7 @@ int32_t b2a_implicit_conv_test(const float* w, int32_t M, int32_t taps, int32_t 
         ic::Args a{};
         a.M = M; a.m_tiles = cdiv(M, tc::BM); a.taps = taps; a.cblocks = W.cblocks; a.dil = dil; a.shift0 = shift0;
         a.B = B; a.T = T; a.t_tiles = cdiv(T, ic::HALF); a.Cout = Cout; a.up = up; a.gelu = gelu; a.add = add; a.bias_twice_t0 = bias_twice_t0; a.Hout = Hout; a.f16 = fp16;
+        a.wscale = fp16 ? W.rscale.p : nullptr;
         if (bias) { dbias.upload(bias, Cout); a.bias = dbias.p; }
         if (gamma) { dgamma.upload(gamma, Cout); a.gamma = dgamma.p; }
         if (sa) { dsa.upload(sa, Cout); dsb.upload(sb, Cout); a.sa = dsa.p; a.sb = dsb.p; }

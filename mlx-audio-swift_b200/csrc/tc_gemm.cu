@@ -1,5 +1,6 @@
 // Host side of the tcgen05/TMA GEMM: tensor-map creation (driver entry point fetched at run time so the
 // library has no link-time dependency on libcuda) and launch wrappers.
+#define B2A_TC_GEMM_IMPL
 #include "common.cuh"
 #include "tc_gemm.cuh"
 
@@ -40,7 +41,22 @@ template void launch<16>(const CUtensorMap&, const CUtensorMap&, const Args&, in
 template void launch<32>(const CUtensorMap&, const CUtensorMap&, const Args&, int, int, cudaStream_t);
 template void launch<128>(const CUtensorMap&, const CUtensorMap&, const Args&, int, int, cudaStream_t);
 
+void launch_splitk(const CUtensorMap& tmA, const CUtensorMap& tmB, const SplitArgs& a, int m_tiles, int cluster, cudaStream_t s) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(m_tiles * cluster)); cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = SmemSplit::bytes(a.stages, cluster); cfg.stream = s;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    at[1].id = cudaLaunchAttributeClusterDimension;
+    at[1].val.clusterDim.x = (unsigned)cluster; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 2;
+    B2A_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_splitk_kernel, tmA, tmB, a));
+    count_launch();
+}
+
 void set_attributes() {
+    B2A_CUDA(cudaFuncSetAttribute(tc_gemm_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     B2A_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     B2A_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     B2A_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -38,6 +38,9 @@ struct Args {
     int act;                 // ACT_NONE | ACT_GELU (exact erf GELU, WhisperLayers.swift:101)
     const void* pf_ptr;      // optional L2 prefetch of a later GEMM's weights (issued by the epilogue warps at kernel start)
     long long pf_bytes;
+    const float* rstd_ss;    // nullable [rstd_parts, 8]: the X rows are UN-normalised (h * gain); every accumulator column t is
+    int rstd_parts;          // multiplied by rsqrt(sum_p rstd_ss[p, t] * rstd_inv_h + rstd_eps) first (fused RMSNorm, BN = 16 only)
+    float rstd_inv_h, rstd_eps;
     int lo_rows;             // != 0: bf16 outputs are written as hi/lo pairs in the same tile-interleaved row layout the
                              // kernel reads X in: token t -> hi row (t / (BN/2)) * BN + t % (BN/2), lo row = hi row + BN/2
 };
@@ -253,6 +256,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int q = warp & 3;                           // TMEM lane quadrant this warp may access
         int acc = 0; uint32_t acc_phase = 0;
         long long u = u0;
+        float rstd[8];
+        bool have_rstd = false;
         while (u < u1) {
             const int mt = (int)(u / a.k_blocks);
             const long long seg_begin = u;
@@ -262,6 +267,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int epi = whole ? a.epi_full : a.epi_partial;
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
+            if (BN == 16 && a.rstd_ss && !have_rstd) {
+                // fused RMSNorm: the producer of X left h * gain un-normalised plus per-m-tile sums of squares (SplitArgs::ss);
+                // the accumulator column of token t is scaled by rstd[t].  (Reading after tfull: the previous kernel is complete.)
+                float t = 0.f;
+                if (lane < 8)
+                    for (int p = 0; p < a.rstd_parts; ++p) t += a.rstd_ss[p * 8 + lane];
+                const float rs = rsqrtf(t * a.rstd_inv_h + a.rstd_eps);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) rstd[j] = __shfl_sync(0xffffffffu, rs, j);
+                have_rstd = true;
+            }
             const int m = mt * BM + q * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
             constexpr int HALF = BN / 2;
@@ -277,6 +293,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (a.hilo) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) v[j] += v[j + 8];
+                    }
+                    if (have_rstd) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] *= rstd[j];
                     }
                 } else {
                     tmem_ld16(taddr + c0, v);
@@ -365,6 +385,198 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
+// ----------------------------------------------------------------------------------------------- cluster split-K
+// D[M, 8 tokens] = W[M, K] X^T for the two GEMMs of a decoder layer whose output feeds the residual stream (o_proj, down_proj),
+// with the residual add, the NEXT RMSNorm's gain, its hi/lo split and its sum of squares fused into the epilogue, so the step
+// has no stand-alone norm kernel.  One thread-block CLUSTER per 128-row m-tile: CTA r of the cluster streams k-blocks
+// [kb * r / C, kb * (r + 1) / C) of the tile (same TMA ring / single-thread tcgen05 issue as tc_gemm_kernel<16>), then every
+// non-leader writes its 128 x 8 fp32 partial into the leader's shared memory (distributed shared memory, st.shared::cluster),
+// one cluster barrier, and the leader adds the partials IN RANK ORDER (bit-reproducible, unlike stream-K's red.add) and runs
+//     h[t, m] += acc          (fp32 residual stream, updated in place)
+//     xn[t, m] = hi / lo of  h[t, m] * gain[m]        (UN-normalised: the consumer GEMM scales its accumulator by rstd[t])
+//     ss[mt, t] = sum over the tile's rows of h[t, m]^2   (the consumer reduces the m-tiles: rstd = rsqrt(sum / H + eps))
+// RMSNorm is linear in its per-token scale, so moving rstd behind the consumer GEMM is exact up to fp32 rounding.
+struct SplitArgs {
+    int M, N, K;                 // N = tokens (<= 8)
+    int k_blocks, stages;
+    float* h;                    // [8, M] residual stream (read-modify-write by the leader)
+    const float* gain;           // [M] the next norm's weight
+    __nv_bfloat16* xn;           // [16, M] hi rows 0..7 / lo rows 8..15
+    float* ss;                   // [m_tiles, 8] partial sums of squares
+    const float* rstd_ss;        // nullable: partial sums [rstd_parts, 8] of the norm this GEMM's INPUT went through
+    int rstd_parts;
+    float rstd_inv_h, rstd_eps;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_f4(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+constexpr int SPLIT_MAX_CLUSTER = 8;
+struct SmemSplit {
+    static constexpr int STAGE = Smem<16>::STAGE;
+    static constexpr int PART_BYTES = BM * 8 * 4;                      // one CTA's 128 x 8 fp32 partial
+    static size_t bytes(int stages, int cluster) { return 1024 + (size_t)stages * STAGE + (size_t)(cluster - 1) * PART_BYTES + 512; }
+};
+
+#ifdef B2A_TC_GEMM_IMPL   // the kernel body lives in tc_gemm.cu only (a non-template __global__ cannot be defined in every translation unit)
+__global__ void __launch_bounds__(THREADS, 2)
+tc_gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, SplitArgs a) {
+    using S = Smem<16>;
+    constexpr int BN = 16;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t C = cluster_nctarank(), rank = cluster_ctarank();
+    float* part = reinterpret_cast<float*>(smem + (size_t)a.stages * S::STAGE);                 // [C - 1][128][8]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)a.stages * S::STAGE + (size_t)(C - 1) * SmemSplit::PART_BYTES);
+    uint64_t* empty = full + a.stages;
+    uint64_t* tfull = empty + a.stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+    float* s_red = reinterpret_cast<float*>(tmem_slot + 2);                                      // [4][8] + [8]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mt = blockIdx.x / C;
+    const int kb0 = (int)((long long)a.k_blocks * rank / C), kb1 = (int)((long long)a.k_blocks * (rank + 1) / C);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int i = 0; i < a.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(tfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<32>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // weights first (they never depend on the previous kernel), then wait for it, then the activation tiles
+            const int n = kb1 - kb0, npre = min(a.stages, n);
+            for (int i = 0; i < npre; ++i) {
+                mbar_arrive_expect_tx(&full[i], S::STAGE);
+                tma_load_2d(smem + (size_t)i * S::STAGE, &tmA, &full[i], (kb0 + i) * BK, mt * BM);
+            }
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            for (int i = 0; i < npre; ++i) tma_load_2d(smem + (size_t)i * S::STAGE + S::A_BYTES, &tmB, &full[i], (kb0 + i) * BK, 0);
+            int stage = npre == a.stages ? 0 : npre;
+            uint32_t phase = npre == a.stages ? 1 : 0;
+            for (int i = npre; i < n; ++i) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* sa = smem + (size_t)stage * S::STAGE;
+                mbar_arrive_expect_tx(&full[stage], S::STAGE);
+                tma_load_2d(sa, &tmA, &full[stage], (kb0 + i) * BK, mt * BM);
+                tma_load_2d(sa + S::A_BYTES, &tmB, &full[stage], (kb0 + i) * BK, 0);
+                if (++stage == a.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BN);
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + (size_t)stage * S::STAGE);
+                const uint64_t ad = make_smem_desc(sa), bd = make_smem_desc(sa + S::A_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k)
+                    umma_bf16(tmem_base, ad + (uint64_t)(k * UMMA_K * 2 / 16), bd + (uint64_t)(k * UMMA_K * 2 / 16), idesc, (kb == kb0 && k == 0) ? 0u : 1u);
+                umma_commit(&empty[stage]);
+                if (++stage == a.stages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(tfull);
+        }
+    }
+    // ---- epilogue part 1 (warps 2..5): this CTA's partial = hi + lo columns; non-leaders hand it to the leader
+    float acc[8];
+    const int q = warp & 3, row = q * 32 + lane;
+    if (warp >= 2) {
+        mbar_wait(tfull, 0);
+        tc_fence_after();
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = v[j] + v[j + 8];
+        if (rank != 0) {
+            const uint32_t dst = map_to_rank(smem_u32(part + ((size_t)(rank - 1) * BM + row) * 8), 0);
+            st_cluster_f4(dst, acc[0], acc[1], acc[2], acc[3]);
+            st_cluster_f4(dst + 16, acc[4], acc[5], acc[6], acc[7]);
+        }
+    }
+    tc_fence_before();
+    __syncwarp();
+    cluster_sync_all();                                          // partials are in the leader's shared memory
+    if (rank == 0 && warp >= 2) {
+        for (uint32_t r = 1; r < C; ++r) {                       // fixed order: deterministic sums
+            const float4 p0 = *reinterpret_cast<const float4*>(part + ((size_t)(r - 1) * BM + row) * 8);
+            const float4 p1 = *reinterpret_cast<const float4*>(part + ((size_t)(r - 1) * BM + row) * 8 + 4);
+            acc[0] += p0.x; acc[1] += p0.y; acc[2] += p0.z; acc[3] += p0.w;
+            acc[4] += p1.x; acc[5] += p1.y; acc[6] += p1.z; acc[7] += p1.w;
+        }
+        const int w4 = warp - 2;                                 // 0..3 (s_red rows); q = warp & 3 is the TMEM quadrant
+        // rstd of the norm this GEMM's input went through (its producer wrote un-normalised hi/lo rows)
+        if (a.rstd_ss) {
+            if (w4 == 0 && lane < 8) {
+                float t = 0.f;
+                for (int p = 0; p < a.rstd_parts; ++p) t += a.rstd_ss[p * 8 + lane];
+                s_red[32 + lane] = rsqrtf(t * a.rstd_inv_h + a.rstd_eps);
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] *= s_red[32 + j];
+        }
+        const int m = mt * BM + row;
+        const bool m_ok = m < a.M;
+        const float g = m_ok ? a.gain[m] : 0.f;
+        float sq[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float hv = 0.f;
+            if (j < a.N && m_ok) {
+                hv = a.h[(long long)j * a.M + m] + acc[j];
+                a.h[(long long)j * a.M + m] = hv;
+                const float t = hv * g;
+                const __nv_bfloat16 hi = __float2bfloat16_rn(t);
+                a.xn[(long long)j * a.M + m] = hi;
+                a.xn[(long long)(8 + j) * a.M + m] = __float2bfloat16_rn(t - __bfloat162float(hi));
+            }
+            sq[j] = hv * hv;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+#pragma unroll
+            for (int o = 16; o; o >>= 1) sq[j] += __shfl_xor_sync(0xffffffffu, sq[j], o);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s_red[w4 * 8 + j] = sq[j];
+        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (w4 == 0 && lane < 8) a.ss[mt * 8 + lane] = s_red[lane] + s_red[8 + lane] + s_red[16 + lane] + s_red[24 + lane];
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<32>(tmem_base);
+    }
+}
+#endif  // B2A_TC_GEMM_IMPL
+
 // ----------------------------------------------------------------------------------------------- host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -375,6 +587,8 @@ CUtensorMap make_tmap_bf16(const void* base, long long rows, long long cols, int
 
 template <int BN>
 void launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Args& a, int ctas, int n_tiles, cudaStream_t s);
+
+void launch_splitk(const CUtensorMap& tmA, const CUtensorMap& tmB, const SplitArgs& a, int m_tiles, int cluster, cudaStream_t s);
 
 void set_attributes();   // cudaFuncSetAttribute for every instantiation (call once, outside graph capture)
 

@@ -230,13 +230,53 @@ class LlamaTTSModel:
         _, waves, _ = self.generate_batch(ids, parameters)
         return waves[0]
 
+    def generate_audio_chunks(self, input_ids, parameters: Optional[GenerateParameters] = None, frames_per_chunk: int = 4,
+                              left_context_frames: int = 8, on_audio: Optional[Callable[[int, np.ndarray, bool], None]] = None,
+                              on_token: Optional[Callable[[int, int, int], None]] = None):
+        """Row N2: audio DURING generation (b2a_tts_generate_stream).  Every `frames_per_chunk` new 7-token frames of a row are
+        decoded by SNAC with `left_context_frames` already-emitted frames in front and passed to on_audio(row, samples, is_final)
+        from inside the call.  Returns (tokens, [chunk list per row], AudioGenerationInfo)."""
+        p = parameters or self.default_generation_parameters
+        ids = np.ascontiguousarray(input_ids, dtype=np.int32)
+        B, L = ids.shape
+        toks = np.zeros((B, p.max_tokens), dtype=np.int32)
+        ntok = np.zeros(B, dtype=np.int32)
+        info = _ffi.GenInfo()
+        gp = self._params(p)
+        chunks: List[List[np.ndarray]] = [[] for _ in range(B)]
+
+        def audio(user, b, ptr, n, final):
+            a = np.ctypeslib.as_array(ptr, shape=(n,)).copy()
+            chunks[b].append(a)
+            if on_audio:
+                on_audio(b, a, bool(final))
+
+        acb = _ffi.AUDIO_CB(audio)
+        tcb = _ffi.TOKEN_CB(lambda user, b, step, tok: on_token(b, step, tok)) if on_token else _ffi.TOKEN_CB()
+        _ffi.check(_ffi.lib().b2a_tts_generate_stream(self._h, _ffi.ptr(ids), B, L, C.byref(gp), frames_per_chunk, left_context_frames,
+                                                      _ffi.ptr(toks), _ffi.ptr(ntok), C.byref(info), tcb, acb, None))
+        gi = AudioGenerationInfo(info.prompt_token_count, info.generation_token_count, info.prefill_time, info.generate_time,
+                                 info.tokens_per_second, info.peak_memory_gb, info.codec_time)
+        return [toks[b, :ntok[b]].tolist() for b in range(B)], chunks, gi
+
     def generate_stream(self, prompt_token_ids: Sequence[int], parameters: Optional[GenerateParameters] = None,
-                        streaming_interval: float = 2.0) -> Iterator:
-        """generateStream (:777-913): yields ('token', id)..., ('info', AudioGenerationInfo), ('audio', waveform).  `streaming_interval` is
-        accepted and ignored, as the protocol's default overload does for models that emit their audio once (Generation.swift:119-137)."""
+                        streaming_interval: Optional[float] = None) -> Iterator:
+        """generateStream (:777-913): yields ('token', id)..., ('info', AudioGenerationInfo), ('audio', waveform).  With
+        streaming_interval = None the audio comes once, at the end, as the reference's Orpheus does (the protocol's default overload
+        ignores the interval for such models, Generation.swift:119-137); with a float (seconds) ('audio', chunk) events are produced
+        every round(interval * 24000 / 2048) frames while tokens are still being generated (row N2)."""
         if self._snac_model is None:
             raise _ffi.AudioGenerationError(_ffi.ERR_MODEL_NOT_INITIALIZED, "SNAC model not loaded")
         ids, _ = self.prepare_input_ids([list(prompt_token_ids)])
+        if streaming_interval is not None:
+            events = []
+            fpc = max(1, int(round(streaming_interval * 24000.0 / 2048.0)))
+            _, _, info = self.generate_audio_chunks(ids, parameters, frames_per_chunk=fpc,
+                                                    on_audio=lambda b, a, fin: events.append(("audio", a)),
+                                                    on_token=lambda b, s, t: events.append(("token", t)))
+            yield from events
+            yield ("info", info)
+            return
         events = []
         _, waves, info = self.generate_batch(ids, parameters, on_token=lambda b, s, t: events.append(("token", t)))
         yield from events
@@ -244,7 +284,7 @@ class LlamaTTSModel:
         yield ("audio", waves[0])
 
     def generate_samples_stream(self, prompt_token_ids: Sequence[int], parameters: Optional[GenerateParameters] = None,
-                                streaming_interval: float = 2.0) -> Iterator[np.ndarray]:
+                                streaming_interval: Optional[float] = None) -> Iterator[np.ndarray]:
         """generateSamplesStream (Generation.swift:52-74): only the .audio events of generateStream, as sample arrays."""
         for kind, value in self.generate_stream(prompt_token_ids, parameters, streaming_interval):
             if kind == "audio" and value is not None:

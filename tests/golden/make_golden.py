@@ -154,12 +154,29 @@ def qwen3_talker():
                         codes=codes.numpy().astype(np.int32))
 
 
+def qwen3_talker_hd128():
+    """The same, at the smallest geometry the CUDA engine runs (head_dim 128): 5 greedy frames of tests/test_gpu_qwen3_talker.py's
+    small model (bf16-valued weights, T = 0)."""
+    cp = ot.CodePredictorConfig(vocab_size=2048, hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=2,
+                                num_key_value_heads=1, head_dim=128, num_code_groups=4)
+    cfg = ot.TalkerConfig(vocab_size=3072, hidden_size=256, intermediate_size=512, num_hidden_layers=3, num_attention_heads=2,
+                          num_key_value_heads=1, head_dim=128, num_code_groups=4, text_hidden_size=128, text_vocab_size=200,
+                          codec_eos_token_id=2150, code_predictor=cp)
+    W = {k: v.to(torch.bfloat16).to(torch.float64) for k, v in ot.init_weights(cfg, 3, std=0.05).items()}
+    chat = [151, 12, 13, 40, 41, 42, 43, 44, 45, 46, 47, 152, 14, 151, 12, 13]
+    inp, trail, pad = ot.prepare_generation_inputs(cfg, W, chat, tts_bos=160, tts_eos=161, tts_pad=162, language_id=2160)
+    logits, _ = ot.Talker(cfg, W)(inp, None)
+    codes = ot.generate_codes(cfg, W, inp, trail, pad, max_tokens=5, temperature=0.0, repetition_penalty=1.05, stop_on_eos=False)
+    np.savez_compressed(OUT / "qwen3_talker_hd128.npz", first_logits_stats=stats(logits[0, -1].numpy()),
+                        first_logits_top=np.argsort(-logits[0, -1].numpy())[:8].astype(np.int32), codes=codes.numpy().astype(np.int32))
+
+
 if __name__ == "__main__":
     import argparse
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default=None, help="regenerate a single fixture (mel | snac | llama | whisper | codecs | qwen3_codec | qwen3_talker)")
+    ap.add_argument("--only", default=None, help="regenerate a single fixture (mel | snac | llama | whisper | codecs | qwen3_codec | qwen3_talker | qwen3_talker_hd128)")
     only = ap.parse_args().only
-    for name, fn in (("mel", mel), ("snac", snac_small), ("llama", llama_tiny), ("whisper", whisper_tiny), ("codecs", codecs_small), ("qwen3_codec", qwen3_codec), ("qwen3_talker", qwen3_talker)):
+    for name, fn in (("mel", mel), ("snac", snac_small), ("llama", llama_tiny), ("whisper", whisper_tiny), ("codecs", codecs_small), ("qwen3_codec", qwen3_codec), ("qwen3_talker", qwen3_talker), ("qwen3_talker_hd128", qwen3_talker_hd128)):
         if only is None or only == name:
             fn()
     for f in sorted(OUT.glob("*.npz")):

@@ -199,3 +199,43 @@ def test_batched_prefill_matches_stepwise_and_oracle(b2a, tiny, monkeypatch, B, 
     assert a == ref
     # after a batched prefill the KV cache must be what the decode path expects: continue with forward_logits
     nxt = np.asarray([[t[-1]] for t in a], dtype=np.int32)
+
+
+def test_streamed_audio_chunks_match_the_one_shot_waveform(b2a):
+    """Row N2 (b2a_tts_generate_stream): chunks are produced DURING generation, they tile the utterance exactly, and away from chunk
+    ends (the codec's look-ahead) they equal the one-shot decode of the same codes."""
+    cfg = ol.LlamaConfig(hidden_size=256, num_hidden_layers=2, intermediate_size=512, num_attention_heads=2,
+                         num_key_value_heads=1, head_dim=128, vocab_size=156940)
+    W = ol.init_weights(cfg, 99, std=0.05)
+    scfg = osnac.SNACConfig()
+    scfg.noise = False                                              # NoiseBlock noise is drawn per call: compare the deterministic part
+    SW = osnac.init_weights(scfg, 1234)
+    snac = b2a.SNAC(weights=SW, noise=False)
+    m = b2a.LlamaTTSModel(hf_config(cfg), W, snac=snac, max_batch=2, max_context=512)
+    P = type(m.default_generation_parameters)
+    ids, _ = m.prepare_input_ids([[11, 22, 33, 44], [55, 66, 77, 88]])
+    ids[:, -1] = 128257                                             # START_OF_SPEECH: parseOutput keeps the generated codes only
+    p = P(max_tokens=7 * 23 + 3, temperature=0.0, top_p=1.0, repetition_penalty=1.3, repetition_context_size=20, mask_eos=True, wrap_codes=True)
+    toks, waves, _ = m.generate_batch(ids, p)
+    order = []
+    toks_s, chunks, info = m.generate_audio_chunks(ids, p, frames_per_chunk=4, left_context_frames=8,
+                                                   on_audio=lambda b, a, fin: order.append(("audio", b, len(a), fin)),
+                                                   on_token=lambda b, s, t: order.append(("token", b, s)))
+    assert toks_s == toks and info.codec_time > 0
+    # audio events are interleaved with token events (emission happens while tokens are still being generated)
+    first_audio = next(i for i, e in enumerate(order) if e[0] == "audio")
+    last_token = max(i for i, e in enumerate(order) if e[0] == "token")
+    assert first_audio < last_token
+    assert [e[3] for e in order if e[0] == "audio" and e[1] == 0][-1] is True
+    for b in range(2):
+        cat = np.concatenate(chunks[b])
+        assert len(cat) == len(waves[b]) == 23 * 2048 and all(len(c) == 4 * 2048 for c in chunks[b][:-1])
+        peak = np.abs(waves[b]).max()
+        err = np.abs(cat - waves[b]) / peak
+        edge = np.zeros(len(cat), bool)                             # the last 2 frames of every non-final chunk lack their look-ahead
+        pos = 0
+        for c in chunks[b][:-1]:
+            pos += len(c)
+            edge[pos - 2 * 2048: pos] = True
+        assert err[~edge].max() < 1e-3, err[~edge].max()
+        assert err.max() < 1.0                                      # and the edges are still the same signal, not garbage

@@ -103,7 +103,7 @@ def test_from_model_directory(codec, tmp_path):
     from test_qwen3_tts_codec_host import torch_layout_checkpoint
     # every k = 1 conv needs > 64 input channels here: the reference's layout heuristic (checkArrayShapeQwen3) reads a PyTorch
     # [out, <= 64, 1] weight as "already MLX" and would leave it untransposed (true of the reference itself, not only of this port)
-    cfg = mid_config(codebook_dim=144, decoder_dim=576, upsample_rates=[4, 3])
+    cfg = mid_config(codebook_dim=144, decoder_dim=512, upsample_rates=[4, 3])     # 512 -> 256 -> 128 output channels (the output conv holds <= 128)
     W = oc.init_weights(cfg, 12)
     d = tmp_path / "speech_tokenizer"
     d.mkdir()

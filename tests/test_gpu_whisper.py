@@ -92,13 +92,41 @@ def test_natural_stop_and_suppression(b2a, tiny):
     assert out3.tokens[0] == ref3 and out3.prompt_tokens == 3
 
 
+def test_temperature_sampling_is_categorical_over_the_masked_logits(b2a, tiny):
+    """WhisperModel.swift:284-291: temperature > 0 -> categorical(logits / T) after the suppress masks.  The draw stream cannot match
+    MLX's generator; the DISTRIBUTION is checked against the oracle's masked first-step logits, plus determinism per seed."""
+    cfg, W, m = tiny
+    x = dsp.synth_audio(48000, 9)
+    o = ow.WhisperOracle(cfg, W)
+    enc = o.encode(torch.from_numpy(dsp.whisper_encoder_features(x)).float())
+    prompt = ow.build_prompt_tokens()
+    lg = o.logits(o.decode(torch.as_tensor([prompt], dtype=torch.long), 0, enc)).numpy()[0, -1].astype(np.float64)
+    lg[ow.EOT] += -1e9                                  # begin-suppress (step 0), timestamps always
+    lg[ow.TIMESTAMP_BEGIN:] += -1e9
+    srt = np.sort(lg)
+    T = float(max(1e-3, (srt[-1] - srt[-8]) / 1.5))     # scaled to the logits: the top handful of tokens share most of the mass
+    p = np.exp((lg - lg.max()) / T); p /= p.sum()
+    draws = [m.generate(x, b2a.STTGenerateParameters(max_tokens=1, temperature=T, seed=s)).tokens[0][0] for s in range(300)]
+    assert all(t < ow.TIMESTAMP_BEGIN and t != ow.EOT for t in draws)
+    assert len(set(draws)) > 3
+    top = int(np.argmax(p))
+    f, e = draws.count(top) / len(draws), p[top]
+    assert abs(f - e) < 4 * np.sqrt(e * (1 - e) / len(draws)) + 0.02, (f, e)
+    heavy = np.argsort(-p)[:20]
+    assert sum(d in set(heavy.tolist()) for d in draws) / len(draws) > p[heavy].sum() - 0.08
+    a = m.generate(x, b2a.STTGenerateParameters(max_tokens=6, temperature=T, seed=5, mask_eot=True)).tokens
+    b = m.generate(x, b2a.STTGenerateParameters(max_tokens=6, temperature=T, seed=5, mask_eot=True)).tokens
+    c = m.generate(x, b2a.STTGenerateParameters(max_tokens=6, temperature=T, seed=6, mask_eot=True)).tokens
+    assert a == b and a != c
+    cold = m.generate(x, b2a.STTGenerateParameters(max_tokens=6, temperature=1e-4, seed=3, mask_eot=True)).tokens
+    assert cold == m.generate(x, b2a.STTGenerateParameters(max_tokens=6, mask_eot=True)).tokens      # T -> 0 is the argmax
+
+
 def test_errors(b2a, tiny):
     cfg, W, m = tiny
     with pytest.raises(b2a.AudioGenerationError) as e:
         m.generate(np.zeros((5, 16000), np.float32))           # max_batch 4
     assert e.value.case == "invalidInput"
-    with pytest.raises(b2a.AudioGenerationError):
-        m.generate(dsp.synth_audio(16000, 0), b2a.STTGenerateParameters(temperature=0.7))
     bad = dict(hf_config(cfg)); bad["encoder_attention_heads"] = 4
     with pytest.raises(b2a.AudioGenerationError):
         b2a.WhisperModel(bad, W)

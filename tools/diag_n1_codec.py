@@ -1,4 +1,6 @@
-"""Diagnostic (GPU): where does the Qwen3-TTS speech-tokenizer decoder leave the oracle at the default geometry?"""
+"""Diagnostic (GPU): Qwen3-TTS speech-tokenizer decoder vs the oracle at the default geometry, per frame, bf16 vs fp16 operand pairs
+(run once per mode: B2A_ST_FP16=0/1 is read when the handle is created)."""
+import os
 import sys
 from pathlib import Path
 import numpy as np
@@ -20,25 +22,12 @@ def run(name, cfg, T, seed=1):
     ref = oc.SpeechTokenizerDecoder(cfg, W)(codes).numpy()[0, 0]
     y = m(codes)[0, 0]
     up = cfg.total_upsample
-    peak = np.abs(ref).max()
-    e = np.abs(y - ref) / peak
+    e = np.abs(y - ref) / np.abs(ref).max()
     per = [float(e[f * up:(f + 1) * up].max()) for f in range(T)]
-    first = int(np.argmax(e > 2e-4)) if (e > 2e-4).any() else -1
-    print(f"{name:48s} T={T} max {e.max():.2e} argmax {int(e.argmax())} first>2e-4 at {first} per-frame {['%.1e' % p for p in per]}", flush=True)
+    print(f"fp16={os.environ.get('B2A_ST_FP16', '0')} {name:24s} T={T} max {e.max():.2e} per-frame {['%.1e' % p for p in per]}", flush=True)
 
 
 D = oc.TokenizerDecoderConfig
-for T in (1, 2, 3, 5):
+for T in (1, 3, 6):
     run("default", D(), T)
-run("default 1 layer", D(num_hidden_layers=1), 3)
-run("default rates [8,5]", D(upsample_rates=[8, 5]), 3)
-run("default rates [4,3,2]", D(upsample_rates=[4, 3, 2]), 3)
-run("default dim 768", D(decoder_dim=768), 3)
-run("default heads 4x32 kv2", D(num_attention_heads=4, num_key_value_heads=2, head_dim=32), 3)
-run("default hidden 64 inter 128", D(hidden_size=64, intermediate_size=128), 3)
-run("default nq 4", D(num_quantizers=4), 3)
-run("default codebook 64 dim 128 latent 128", D(codebook_size=64, codebook_dim=128, latent_dim=128), 3)
-run("default layer_scale 0.3", D(layer_scale_initial_scale=0.3), 3)
-run("mid", oc.mid_config(), 3)
-run("mid rates [8,5,4,3]", oc.mid_config(upsample_rates=[8, 5, 4, 3]), 3)
-run("mid dim 1536", oc.mid_config(decoder_dim=1536), 3)
+run("mid", oc.mid_config(), 6)
