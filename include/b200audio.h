@@ -292,8 +292,11 @@ int32_t b2a_tts_create_from_directory(const char* model_dir, int32_t device, int
  *   Vocos(backbone:head:) + weights (keys backbone.* / head.*, MLX layouts) -> b2a_vocos_create
  *   decode(_ features:) / decodeAudio (:302-306,318-320)                   -> b2a_vocos_decode
  * features are [B, L, input_channels] float32 (the layout VocosBackbone expects, VocosBackbone.swift:170-175);
- * the waveform is [B, (L-1)*hop_length] (ISTFTHead centre trim, Vocos.swift:150-158).  Only the LayerNorm variant
- * (adanorm_num_embeddings == 0) is implemented.                                                    */
+ * the waveform is [B, (L-1)*hop_length] (ISTFTHead centre trim, Vocos.swift:150-158).  AdaLayerNorm models
+ * (Vocos.swift:17-47; weights backbone.norm.{scale,shift}.{weight,bias}, backbone.convnext.N.norm.{scale,shift}.*) take their
+ * `bandwidthId` conditioning through b2a_vocos_decode_cond: cond [B, adanorm_num_embeddings] float32, the rows the scale / shift
+ * Linears are applied to (decode(_:bandwidthId:) :302-306); decoding such a model without it fails with invalidInput where the
+ * reference fatalErrors (VocosBackbone.swift:66-68,181-183).                                        */
 typedef struct b2a_vocos_config {
     int32_t input_channels;
     int32_t dim;
@@ -303,7 +306,7 @@ typedef struct b2a_vocos_config {
     int32_t hop_length;
     int32_t input_kernel_size;
     int32_t dw_kernel_size;
-    int32_t adanorm_num_embeddings; /* must be 0 */
+    int32_t adanorm_num_embeddings; /* 0: LayerNorm; > 0: AdaLayerNorm(numEmbeddings, dim) for backbone.norm and every block's norm */
 } b2a_vocos_config;
 
 typedef struct b2a_vocos b2a_vocos;
@@ -313,6 +316,7 @@ int64_t b2a_vocos_output_length(const b2a_vocos* h, int32_t frames);
 void* b2a_vocos_stream(b2a_vocos* h);
 int32_t b2a_vocos_decode(b2a_vocos* h, const float* features, int32_t batch, int32_t frames, float* wave);
 int32_t b2a_vocos_decode_dev(b2a_vocos* h, const float* d_features, int32_t batch, int32_t frames, float* d_wave, void* stream);
+int32_t b2a_vocos_decode_cond(b2a_vocos* h, const float* features, const float* cond, int32_t batch, int32_t frames, float* wave);
 void b2a_vocos_destroy(b2a_vocos* h);
 
 /* ------------------------------------------------------------------ Encodec decode

@@ -174,6 +174,7 @@ SIGNATURES = {
     "b2a_vocos_stream": (C.c_void_p, [_P]),
     "b2a_vocos_decode": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, _P]),
     "b2a_vocos_decode_dev": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
+    "b2a_vocos_decode_cond": (C.c_int32, [_P, _P, _P, C.c_int32, C.c_int32, _P]),
     "b2a_vocos_destroy": (None, [_P]),
     "b2a_speech_tokenizer_create": (C.c_int32, [C.c_int32, C.POINTER(SpeechTokenizerConfig), C.POINTER(Tensor), C.c_int32, C.POINTER(_P)]),
     "b2a_speech_tokenizer_total_upsample": (C.c_int32, [_P]),

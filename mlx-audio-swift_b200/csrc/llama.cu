@@ -644,7 +644,13 @@ attn_decode_cluster_kernel(AttnArgs a, int NB) {
     const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     pdl_trigger();
     l2_prefetch(a.pf, ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * AT_THREADS + tid, gridDim.x * gridDim.y * gridDim.z * AT_THREADS);
-    const int p = a.pos[b];                                     // written by the previous step's sampler only
+    // pos[b] is read BEFORE griddepcontrol.wait so that the cached K / V chunks stream in under the QKV GEMM's tail.  Programmatic
+    // launches chain (a kernel triggers its dependents at its first instruction, even while it is itself still waiting), so on a
+    // small model -- every kernel of several layers resident at once -- this prologue can run before a kernel launched many
+    // launches earlier has finished (measured: 1e-1 logits error on a 256-wide model).  The contract that makes the early read
+    // safe: EVERY kernel that writes pos[] never calls pdl_trigger() (sample_kernel, prefill_advance_kernel, the q3_* kernels that
+    // set a position), so nothing launched after it starts before it has completed.
+    const int p = a.pos[b];
     if (!(p >= 0 && p < a.max_ctx)) { pdl_wait(); return; }
     const int nch = p / AT_CAP + 1;
     const int n_my = nch > rank ? (nch - rank + 1) / 2 : 0;     // this CTA's chunks: rank, rank + 2, ...
@@ -1042,8 +1048,7 @@ sample_kernel(SampleArgs a) {
     __shared__ float s_val[SM_WARPS];
     __shared__ int s_idx[SM_WARPS];
     const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    pdl_trigger();
-    pdl_wait();
+    pdl_wait();                  // NO pdl_trigger(): this kernel writes pos[] (see attn_decode_cluster_kernel)
     float* lg = a.logits + (long long)b * a.V;
     float* pr = a.probs + (long long)b * a.V;
     const int nrec = min(a.recent_n[b], a.R);
@@ -1183,8 +1188,7 @@ sample_kernel(SampleArgs a) {
 // prefill bookkeeping for positions that do not need logits: next token = ids[b, pos+1]
 __global__ void prefill_advance_kernel(const int* __restrict__ ids, int L, int* tokens, int* pos, int B) {
     const int b = threadIdx.x;
-    pdl_trigger();
-    pdl_wait();
+    pdl_wait();                  // NO pdl_trigger(): writes pos[]
     if (b >= B) return;
     const int p = pos[b] + 1;
     pos[b] = p;
@@ -1303,7 +1307,7 @@ struct b2a_tts {
     // fused-norm decode step (default on the tcgen05 path): o_proj / down_proj run as cluster split-K GEMMs whose leader CTA does the
     // residual add + the next norm's gain + hi/lo split + sum of squares; no stand-alone add_rmsnorm launches (tc_gemm.cuh)
     bool fused = false;
-    int fused_cluster = 4, fused_parts = 0;
+    int fused_cluster = 6, fused_parts = 0;   // 6 CTAs per 128-row tile: 144 of 148 SMs for hidden 3072 (measured best of 3..8)
     DBuf<float> ss_a, ss_b;          // [H / 128, 8] partial sums of squares: ss_a feeds the post-attention norm, ss_b the input norm
     StackSpec spec;                  // which keys / features this stack was built with
     const float* x_ext = nullptr;    // row N1: when set, a step starts from these embeddings [8, H] instead of embed(tokens)
@@ -2439,7 +2443,7 @@ namespace b2a {
 __global__ void q3_gather_kernel(const bf16* __restrict__ table, int rows, const int* __restrict__ ids, int id_stride, int id_col,
                                  float* __restrict__ dst, int H, int* pos, int pos_value) {
     const int b = blockIdx.x;
-    pdl_trigger();
+    if (!pos) pdl_trigger();     // a kernel that writes pos[] must not trigger early (see attn_decode_cluster_kernel)
     pdl_wait();
     int t = ids[b * id_stride + id_col];
     t = min(max(t, 0), rows - 1);
@@ -2449,7 +2453,7 @@ __global__ void q3_gather_kernel(const bf16* __restrict__ table, int rows, const
 // dst[b, :] = src[b * src_stride + :]; optionally pos[b] = pos_value (pos_value < 0: pos untouched)
 __global__ void q3_copy_rows_kernel(const float* __restrict__ src, long long src_stride, float* __restrict__ dst, int H, int* pos, int pos_value) {
     const int b = blockIdx.x;
-    pdl_trigger();
+    if (!(pos && pos_value >= 0)) pdl_trigger();     // writers of pos[] never trigger early
     pdl_wait();
     for (int i = threadIdx.x; i < H; i += blockDim.x) dst[(long long)b * H + i] = src[(long long)b * src_stride + i];
     if (pos && pos_value >= 0 && threadIdx.x == 0) pos[b] = pos_value;
@@ -2488,8 +2492,7 @@ struct Q3Feedback {
 // x_next = text + codec_embed(c0) + sum_i predictor_embed_i(c_{i+1})  (Qwen3TTS.swift:470-487) + per-row bookkeeping (:424-428)
 __global__ void q3_feedback_kernel(Q3Feedback a) {
     const int b = blockIdx.x;
-    pdl_trigger();
-    pdl_wait();
+    pdl_wait();                  // NO pdl_trigger(): writes the talker's pos[]
     const int f = a.row_frame[b];
     const float* text = f < a.n_trailing[b] ? a.trailing + ((long long)b * a.n_max + f) * a.H : a.pad;
     const int* c = a.codes + b * a.G;

@@ -258,6 +258,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         long long u = u0;
         float rstd[8];
         bool have_rstd = false;
+        if (BN == 16 && a.rstd_ss) {
+            // fused RMSNorm: the producer of X left h * gain un-normalised plus per-m-tile sums of squares (SplitArgs::ss); the
+            // accumulator column of token t is scaled by rstd[t].  Computed while the main loop streams weights: these warps are
+            // idle until the first accumulator is ready, so they wait for the previous kernel themselves and reduce the partial
+            // sums with one independent load per lane and step (lane = part * 8 + token).
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            float t = 0.f;
+            for (int p0 = 0; p0 < a.rstd_parts; p0 += 4) {
+                const int p = p0 + (lane >> 3);
+                if (p < a.rstd_parts) t += a.rstd_ss[p * 8 + (lane & 7)];
+            }
+            t += __shfl_xor_sync(0xffffffffu, t, 8);
+            t += __shfl_xor_sync(0xffffffffu, t, 16);
+            const float rs = rsqrtf(t * a.rstd_inv_h + a.rstd_eps);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rstd[j] = __shfl_sync(0xffffffffu, rs, j);
+            have_rstd = true;
+        }
         while (u < u1) {
             const int mt = (int)(u / a.k_blocks);
             const long long seg_begin = u;
@@ -267,17 +285,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int epi = whole ? a.epi_full : a.epi_partial;
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
-            if (BN == 16 && a.rstd_ss && !have_rstd) {
-                // fused RMSNorm: the producer of X left h * gain un-normalised plus per-m-tile sums of squares (SplitArgs::ss);
-                // the accumulator column of token t is scaled by rstd[t].  (Reading after tfull: the previous kernel is complete.)
-                float t = 0.f;
-                if (lane < 8)
-                    for (int p = 0; p < a.rstd_parts; ++p) t += a.rstd_ss[p * 8 + lane];
-                const float rs = rsqrtf(t * a.rstd_inv_h + a.rstd_eps);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) rstd[j] = __shfl_sync(0xffffffffu, rs, j);
-                have_rstd = true;
-            }
             const int m = mt * BM + q * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
             constexpr int HALF = BN / 2;
@@ -503,9 +510,19 @@ tc_gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         }
     }
     // ---- epilogue part 1 (warps 2..5): this CTA's partial = hi + lo columns; non-leaders hand it to the leader
-    float acc[8];
+    float acc[8], hold[8];
+    float g = 0.f;
     const int q = warp & 3, row = q * 32 + lane;
+    const int m = mt * BM + row;
+    const bool m_ok = m < a.M;
     if (warp >= 2) {
+        if (rank == 0) {
+            // the residual rows and the gain do not depend on this GEMM: fetch them while the weights stream
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            g = m_ok ? a.gain[m] : 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) hold[j] = (j < a.N && m_ok) ? a.h[(long long)j * a.M + m] : 0.f;
+        }
         mbar_wait(tfull, 0);
         tc_fence_after();
         float v[16];
@@ -540,15 +557,12 @@ tc_gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[j] *= s_red[32 + j];
         }
-        const int m = mt * BM + row;
-        const bool m_ok = m < a.M;
-        const float g = m_ok ? a.gain[m] : 0.f;
         float sq[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             float hv = 0.f;
             if (j < a.N && m_ok) {
-                hv = a.h[(long long)j * a.M + m] + acc[j];
+                hv = hold[j] + acc[j];
                 a.h[(long long)j * a.M + m] = hv;
                 const float t = hv * g;
                 const __nv_bfloat16 hi = __float2bfloat16_rn(t);

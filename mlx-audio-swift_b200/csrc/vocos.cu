@@ -65,10 +65,12 @@ constexpr int DL_THREADS = 256, DL_MAXV = 4;    // channels <= 1024
 __global__ void __launch_bounds__(DL_THREADS)
 dw_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ dw_w /*[C,k] or null*/, const float* __restrict__ dw_b,
                     const float* __restrict__ ln_w, const float* __restrict__ ln_b, float* __restrict__ out_f32,
-                    bf16* __restrict__ out_hl, int L, int C, int k, float eps) {
+                    bf16* __restrict__ out_hl, int L, int C, int k, float eps, int ln_batch_stride = 0) {
     __shared__ float red[DL_THREADS / 32];
     const long long tok = blockIdx.x;
     const int b = (int)(tok / L), t = (int)(tok - (long long)b * L);
+    ln_w += (long long)b * ln_batch_stride;     // AdaLayerNorm: the gain / shift rows of this utterance's conditioning (0 = shared LayerNorm)
+    ln_b += (long long)b * ln_batch_stride;
     float v[DL_MAXV];
     float s = 0.f;
 #pragma unroll
@@ -106,6 +108,19 @@ dw_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ dw_w 
             if (out_hl) put_hilo(out_hl, C, tok, c, o);
         }
     }
+}
+
+// AdaLayerNorm's conditioning (Vocos.swift:31-33): for every norm n and utterance b,  gain[n, b, :] = Ws_n cond_b + bs_n  and
+// shift[n, b, :] = Wh_n cond_b + bh_n.  W [norms][dim][E] (scale then shift stacked: [2][norms][dim][E]), cond [B][E].
+__global__ void adanorm_affine_kernel(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ cond,
+                                      float* __restrict__ out, int norms, int B, int D, int E) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // over [2][norms][B][D]
+    if (i >= (long long)2 * norms * B * D) return;
+    const int d = (int)(i % D), b = (int)((i / D) % B), n = (int)((i / ((long long)D * B)) % norms), which = (int)(i / ((long long)D * B * norms));
+    const float* w = W + (((long long)which * norms + n) * D + d) * E;
+    float acc = bias[((long long)which * norms + n) * D + d];
+    for (int e = 0; e < E; ++e) acc = fmaf(w[e], cond[(long long)b * E + e], acc);
+    out[i] = acc;
 }
 
 // head projection output h [tokens, n_fft+2] -> [mag*cos | mag*sin] as hi/lo (Vocos.swift:75-90): mag = min(exp(.), 100)
@@ -179,6 +194,7 @@ struct b2a_vocos {
     int num_sms = 148, kp_embed = 0, kp_spec = 0;
     TcW embed, head, idft;
     DBuf<float> n0_w, n0_b, nf_w, nf_b, win;
+    DBuf<float> ada_w, ada_b, ada_out, cond;     // AdaLayerNorm: [2][1 + layers][dim][E] / [2][1 + layers][dim]; per-call [2][1 + layers][B][dim]
     std::vector<Block> blocks;
     // workspace
     DBuf<float> feats, h, spec, frames, wave;
@@ -192,7 +208,7 @@ struct b2a_vocos {
                   "vocos: dim / intermediate_dim must be multiples of 64 (dim <= 1024)");
         B2A_CHECK(c.n_fft % 2 == 0 && c.n_fft >= 16 && c.hop_length >= 1 && c.hop_length <= c.n_fft, B2A_ERR_INVALID_INPUT, "vocos: bad n_fft / hop_length");
         B2A_CHECK(c.input_kernel_size % 2 == 1 && c.dw_kernel_size % 2 == 1 && c.dw_kernel_size <= 15, B2A_ERR_INVALID_INPUT, "vocos: kernel sizes must be odd");
-        B2A_CHECK(c.adanorm_num_embeddings == 0, B2A_ERR_INVALID_INPUT, "vocos: AdaLayerNorm (bandwidth-conditioned) models are not implemented");
+        B2A_CHECK(c.adanorm_num_embeddings >= 0 && c.adanorm_num_embeddings <= 64, B2A_ERR_INVALID_INPUT, "vocos: adanorm_num_embeddings must be in 0..64");
         require_device(dev);
         B2A_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         B2A_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
@@ -207,7 +223,19 @@ struct b2a_vocos {
             embed.set_bias(tt.f32("backbone.embed.bias", D));
         }
         auto up = [&](DBuf<float>& d, const std::string& name, int n) { std::vector<float> v = tt.f32(name, n); d.upload(v.data(), n); };
-        up(n0_w, "backbone.norm.weight", D); up(n0_b, "backbone.norm.bias", D);
+        const int E = c.adanorm_num_embeddings, norms = 1 + c.num_layers;
+        std::vector<float> aw, ab;
+        if (E > 0) { aw.resize((size_t)2 * norms * D * E); ab.resize((size_t)2 * norms * D); }
+        auto ada = [&](int n, const std::string& p) {      // AdaLayerNorm(numEmbeddings, dim): scale / shift are Linear(E -> dim) (Vocos.swift:17-47)
+            const char* nm[2] = {"scale", "shift"};
+            for (int w = 0; w < 2; ++w) {
+                std::vector<float> W = tt.f32(p + nm[w] + ".weight", (int64_t)D * E), bv = tt.f32(p + nm[w] + ".bias", D);
+                memcpy(&aw[((size_t)w * norms + n) * D * E], W.data(), W.size() * sizeof(float));
+                memcpy(&ab[((size_t)w * norms + n) * D], bv.data(), bv.size() * sizeof(float));
+            }
+        };
+        if (E > 0) ada(0, "backbone.norm.");
+        else { up(n0_w, "backbone.norm.weight", D); up(n0_b, "backbone.norm.bias", D); }
         up(nf_w, "backbone.final_layer_norm.weight", D); up(nf_b, "backbone.final_layer_norm.bias", D);
         blocks.resize(c.num_layers);
         for (int l = 0; l < c.num_layers; ++l) {
@@ -215,11 +243,13 @@ struct b2a_vocos {
             Block& B = blocks[l];
             up(B.dw_w, p + "dwconv.weight", D * c.dw_kernel_size);          // [dim, k, 1]
             up(B.dw_b, p + "dwconv.bias", D);
-            up(B.ln_w, p + "norm.weight", D); up(B.ln_b, p + "norm.bias", D);
+            if (E > 0) ada(1 + l, p + "norm.");
+            else { up(B.ln_w, p + "norm.weight", D); up(B.ln_b, p + "norm.bias", D); }
             B.pw1.build(tt.f32(p + "pwconv1.weight", (int64_t)I * D), I, D); B.pw1.set_bias(tt.f32(p + "pwconv1.bias", I));
             B.pw2.build(tt.f32(p + "pwconv2.weight", (int64_t)D * I), D, I); B.pw2.set_bias(tt.f32(p + "pwconv2.bias", D));
             if (tt.find(p + "gamma")) up(B.gamma, p + "gamma", D);
         }
+        if (E > 0) { ada_w.upload(aw.data(), aw.size()); ada_b.upload(ab.data(), ab.size()); B2A_CUDA(cudaDeviceSynchronize()); }
         head.build(tt.f32("head.out.weight", (int64_t)(N + 2) * D), N + 2, D);
         head.set_bias(tt.f32("head.out.bias", N + 2));
         // windowed inverse real DFT as a matrix: frame[j] = w[j]/N * (Re0 + (-1)^j Re_{N/2} + 2 sum_k (Re_k cos - Im_k sin))
@@ -253,10 +283,26 @@ struct b2a_vocos {
     long long out_len(int L) const { return (long long)(L - 1) * cfg.hop_length; }
 
     // d_feats [B, L, input_channels] fp32 (device) -> d_wave [B, (L-1)*hop]
-    void decode_dev(const float* d_feats, int B, int L, float* d_wave, cudaStream_t s) {
+    // d_cond [B, adanorm_num_embeddings] fp32 (device): the conditioning rows AdaLayerNorm's Linears see (one-hot bandwidth ids in the
+    // reference's use); required iff the model was built with adanorm_num_embeddings > 0 (the reference fatalErrors without it)
+    void decode_dev(const float* d_feats, int B, int L, float* d_wave, cudaStream_t s, const float* d_cond = nullptr) {
         B2A_CHECK(B >= 1 && L >= 2, B2A_ERR_INVALID_INPUT, "vocos decode: need at least 2 frames");
         B2A_CUDA(cudaSetDevice(device));
         const int D = cfg.dim, I = cfg.intermediate_dim, N = cfg.n_fft;
+        const int E = cfg.adanorm_num_embeddings, norms = 1 + cfg.num_layers;
+        B2A_CHECK((E > 0) == (d_cond != nullptr), B2A_ERR_INVALID_INPUT,
+                  E > 0 ? "vocos decode: AdaLayerNorm requires bandwidthId (a conditioning row per utterance)" : "vocos decode: this model takes no conditioning");
+        const float *g0 = n0_w.p, *b0 = n0_b.p;
+        int bs = 0;
+        if (E > 0) {
+            ada_out.alloc((size_t)2 * norms * B * D);
+            const long long n = (long long)2 * norms * B * D;
+            adanorm_affine_kernel<<<(unsigned)cdiv(n, 256), 256, 0, s>>>(ada_w.p, ada_b.p, d_cond, ada_out.p, norms, B, D, E);
+            count_launch();
+            g0 = ada_out.p; b0 = ada_out.p + (size_t)norms * B * D; bs = D;
+        }
+        auto gain = [&](int n, const float* plain) { return E > 0 ? ada_out.p + (size_t)n * B * D : plain; };
+        auto shift = [&](int n, const float* plain) { return E > 0 ? ada_out.p + ((size_t)norms + n) * B * D : plain; };
         const long long T = (long long)B * L, Tp = pad64(T);
         B2A_CHECK(T < (1ll << 30), B2A_ERR_INVALID_INPUT, "vocos decode: too many frames");
         const size_t kmax = (size_t)std::max(std::max(kp_embed, I), std::max(D, kp_spec));
@@ -269,11 +315,13 @@ struct b2a_vocos {
             cg::Args a{}; a.N = (int)T; a.epi = cg::E_STORE_F32; a.x = spec.p; a.ldx = D;      // spec doubles as scratch [T, D]
             cgemm(embed, xa.p, 2 * Tp, a, s);
         }
-        dw_layernorm_kernel<<<(unsigned)T, DL_THREADS, 0, s>>>(spec.p, nullptr, nullptr, n0_w.p, n0_b.p, h.p, nullptr, L, D, 1, 1e-6f);
+        dw_layernorm_kernel<<<(unsigned)T, DL_THREADS, 0, s>>>(spec.p, nullptr, nullptr, g0, b0, h.p, nullptr, L, D, 1, 1e-6f, bs);
         count_launch();
+        int li = 0;
         for (auto& Bk : blocks) {
-            dw_layernorm_kernel<<<(unsigned)T, DL_THREADS, 0, s>>>(h.p, Bk.dw_w.p, Bk.dw_b.p, Bk.ln_w.p, Bk.ln_b.p, nullptr, xa.p, L, D,
-                                                                   cfg.dw_kernel_size, 1e-6f);
+            ++li;
+            dw_layernorm_kernel<<<(unsigned)T, DL_THREADS, 0, s>>>(h.p, Bk.dw_w.p, Bk.dw_b.p, gain(li, Bk.ln_w.p), shift(li, Bk.ln_b.p), nullptr, xa.p, L, D,
+                                                                   cfg.dw_kernel_size, 1e-6f, bs);
             count_launch();
             cg::Args a1{}; a1.N = (int)T; a1.epi = cg::E_STORE_HILO; a1.gelu = 1; a1.hl = xb.p; a1.ldh = I; a1.T = L;
             cgemm(Bk.pw1, xa.p, 2 * Tp, a1, s);
@@ -331,6 +379,23 @@ int32_t b2a_vocos_decode(b2a_vocos* h, const float* feats, int32_t B, int32_t L,
         h->feats.alloc(nin); h->wave.alloc(nout);
         B2A_CUDA(cudaMemcpyAsync(h->feats.p, feats, nin * sizeof(float), cudaMemcpyHostToDevice, s));
         h->decode_dev(h->feats.p, B, L, h->wave.p, s);
+        B2A_CUDA(cudaMemcpyAsync(wave, h->wave.p, nout * sizeof(float), cudaMemcpyDeviceToHost, s));
+        B2A_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+int32_t b2a_vocos_decode_cond(b2a_vocos* h, const float* feats, const float* cond, int32_t B, int32_t L, float* wave) {
+    return guarded([&] {
+        B2A_CHECK(h && feats && wave, B2A_ERR_INVALID_INPUT, "b2a_vocos_decode_cond: null argument");
+        B2A_CHECK(B >= 1 && L >= 2, B2A_ERR_AUDIO_DECODING_FAILED, "b2a_vocos_decode_cond: need at least 2 frames");
+        B2A_CUDA(cudaSetDevice(h->device));
+        cudaStream_t s = h->stream;
+        const int E = h->cfg.adanorm_num_embeddings;
+        const size_t nin = (size_t)B * L * h->cfg.input_channels, nout = (size_t)B * h->out_len(L);
+        h->feats.alloc(nin); h->wave.alloc(nout);
+        B2A_CUDA(cudaMemcpyAsync(h->feats.p, feats, nin * sizeof(float), cudaMemcpyHostToDevice, s));
+        if (cond && E > 0) { h->cond.alloc((size_t)B * E); B2A_CUDA(cudaMemcpyAsync(h->cond.p, cond, (size_t)B * E * sizeof(float), cudaMemcpyHostToDevice, s)); }
+        h->decode_dev(h->feats.p, B, L, h->wave.p, s, (cond && E > 0) ? h->cond.p : (cond ? cond : nullptr));
         B2A_CUDA(cudaMemcpyAsync(wave, h->wave.p, nout * sizeof(float), cudaMemcpyDeviceToHost, s));
         B2A_CUDA(cudaStreamSynchronize(s));
     });

@@ -49,8 +49,12 @@ struct JsonParser {
     explicit JsonParser(const char* s, size_t n) : p(s), end(s + n) {}
     [[noreturn]] void fail(const char* what) { throw Error(B2A_ERR_MODEL_NOT_INITIALIZED, std::string("json: ") + what); }
     void ws() { while (p < end && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) ++p; }
+    int depth = 0;
+    struct Depth { int& d; explicit Depth(int& x) : d(x) { ++d; } ~Depth() { --d; } };
     Json parse() { ws(); Json j = value(); ws(); return j; }
     Json value() {
+        Depth guard(depth);
+        if (depth > 64) fail("nesting deeper than 64 levels");      // a hostile header must not overflow the stack
         ws();
         if (p >= end) fail("unexpected end");
         Json j;
@@ -235,7 +239,16 @@ struct b2a_weights {
             it.name = kv.first;
             it.ndim = (int)sh->arr.size();
             B2A_CHECK(it.ndim <= 4, B2A_ERR_MODEL_NOT_INITIALIZED, "more than 4 dimensions: " + kv.first);
-            for (int i = 0; i < it.ndim; ++i) it.shape[i] = (int64_t)sh->arr[i].num;
+            int64_t total = 1;
+            for (int i = 0; i < it.ndim; ++i) {
+                const double d = sh->arr[i].num;
+                B2A_CHECK(sh->arr[i].kind == Json::Num && d >= 0 && d <= 9.0e15 && d == (double)(int64_t)d, B2A_ERR_MODEL_NOT_INITIALIZED,
+                          "safetensors: shape entries must be non-negative integers: " + it.name);
+                it.shape[i] = (int64_t)d;
+                B2A_CHECK(it.shape[i] == 0 || total <= ((int64_t)1 << 46) / it.shape[i], B2A_ERR_MODEL_NOT_INITIALIZED,
+                          "safetensors: tensor too large: " + it.name);            // numel() cannot overflow below
+                total *= it.shape[i];
+            }
             const size_t o0 = (size_t)off->arr[0].num, o1 = (size_t)off->arr[1].num;
             B2A_CHECK(o0 <= o1 && o1 <= data_len, B2A_ERR_MODEL_NOT_INITIALIZED, "tensor out of bounds: " + kv.first);
             const uint8_t* src = data + o0;
@@ -433,6 +446,7 @@ struct b2a_weights {
             B2A_CHECK(w.dtype == B2A_DTYPE_I32 && w.ndim == 2, B2A_ERR_MODEL_NOT_INITIALIZED, "quantised weight must be uint32 [out, in*bits/32]: " + p);
             const int per = 32 / bits;
             const int64_t rows = w.shape[0], words = w.shape[1], cols = words * per, groups = cols / group_size;
+            B2A_CHECK(cols % group_size == 0, B2A_ERR_MODEL_NOT_INITIALIZED, "quantised weight: columns are not a multiple of group_size: " + p);
             const std::vector<float> sc = as_f32(items[is]), bi = as_f32(items[ib]);
             B2A_CHECK((int64_t)sc.size() == rows * groups && bi.size() == sc.size(), B2A_ERR_MODEL_NOT_INITIALIZED, "bad scales / biases shape: " + p);
             auto o = std::make_shared<std::vector<uint8_t>>((size_t)(rows * cols) * 2);
@@ -629,8 +643,12 @@ int32_t b2a_tts_config_from_json(const char* config_path, int32_t max_batch, int
         c.num_key_value_heads = (int)j.number("num_key_value_heads", c.num_attention_heads);
         c.head_dim = (int)j.number("head_dim", c.num_attention_heads ? c.hidden_size / c.num_attention_heads : 0);
         c.vocab_size = (int)j.number("vocab_size", 0);
-        c.rms_norm_eps = (float)j.number("rms_norm_eps", 1e-5); c.rope_theta = (float)j.number("rope_theta", 500000.0);
+        c.rms_norm_eps = (float)j.number("rms_norm_eps", 1e-5); c.rope_theta = (float)j.number("rope_theta", 10000.0);   // LlamaTTSConfig.swift:25
         c.tie_word_embeddings = (int)j.number("tie_word_embeddings", 1);
+        // decoded by the reference but with no code path here: reject instead of silently computing something else
+        B2A_CHECK(j.number("rope_traditional", 0) == 0, B2A_ERR_INVALID_INPUT, "config.json: rope_traditional = true is not supported");
+        B2A_CHECK(j.number("attention_bias", 0) == 0 && j.number("mlp_bias", 0) == 0, B2A_ERR_INVALID_INPUT,
+                  "config.json: attention_bias / mlp_bias = true are not supported");
         c.rope_factor = 32.f; c.rope_low_freq_factor = 1.f; c.rope_high_freq_factor = 4.f; c.rope_old_context_len = 8192.f;
         if (const Json* rs = j.find("rope_scaling"); rs && rs->kind == Json::Obj) {
             B2A_CHECK(rs->has("factor"), B2A_ERR_MODEL_NOT_INITIALIZED, "rope_scaling must contain 'factor'");

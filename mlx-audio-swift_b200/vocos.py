@@ -18,6 +18,7 @@ class Vocos:
         cfg = _ffi.VocosConfig(input_channels, dim, intermediate_dim, num_layers, n_fft, hop_length, input_kernel_size,
                                dw_kernel_size, adanorm_num_embeddings or 0)
         self.input_channels, self.hop_length, self.n_fft = input_channels, hop_length, n_fft
+        self.adanorm_num_embeddings = adanorm_num_embeddings or 0
         table, keep = _ffi.make_tensor_table(weights)
         self._h = C.c_void_p()
         _ffi.check(_ffi.lib().b2a_vocos_create(device, C.byref(cfg), table, len(weights), C.byref(self._h)))
@@ -31,8 +32,9 @@ class Vocos:
     def stream(self) -> int:
         return int(_ffi.lib().b2a_vocos_stream(self._h) or 0)
 
-    def decode(self, features) -> np.ndarray:
-        """decode(_ features:) (:302-306): [B, L, C] (or [B, C, L], transposed like VocosBackbone.swift:170-175) -> [B, (L-1)*hop]."""
+    def decode(self, features, bandwidth_id=None) -> np.ndarray:
+        """decode(_ features:bandwidthId:) (:302-306): [B, L, C] (or [B, C, L], transposed like VocosBackbone.swift:170-175) -> [B, (L-1)*hop].
+        `bandwidth_id` [B, adanorm_num_embeddings]: the conditioning rows of an AdaLayerNorm model (Vocos.swift:17-47)."""
         x = np.ascontiguousarray(features, dtype=np.float32)
         if x.ndim == 2:
             x = x[None]
@@ -41,7 +43,11 @@ class Vocos:
         B, L, _ = x.shape
         n = int(_ffi.lib().b2a_vocos_output_length(self._h, L))
         out = np.empty((B, n), dtype=np.float32)
-        _ffi.check(_ffi.lib().b2a_vocos_decode(self._h, _ffi.ptr(x), B, L, _ffi.ptr(out)))
+        if bandwidth_id is not None:
+            c = np.ascontiguousarray(bandwidth_id, dtype=np.float32).reshape(B, -1)
+            _ffi.check(_ffi.lib().b2a_vocos_decode_cond(self._h, _ffi.ptr(x), _ffi.ptr(c), B, L, _ffi.ptr(out)))
+        else:
+            _ffi.check(_ffi.lib().b2a_vocos_decode(self._h, _ffi.ptr(x), B, L, _ffi.ptr(out)))
         return out
 
     def decode_audio(self, features) -> np.ndarray:

@@ -163,7 +163,7 @@ def test_simt_fallback_matches_tcgen05_path(b2a, tiny, monkeypatch):
     m2 = b2a.LlamaTTSModel(hf_config(cfg), W, max_batch=4, max_context=64)
     monkeypatch.delenv("B2A_GEMM")
     b = m2(ids)
-    assert rel_err(b, a) < 1e-5
+    assert rel_err(b, a) < 3e-5                                   # the fused-norm step applies rstd behind the GEMM: fp32 rounding differs
     ref = ol.LlamaOracle(cfg, W, round_acts=False).forward(torch.as_tensor(ids)).numpy()
     assert rel_err(b, ref) < 1e-4
 

@@ -62,3 +62,26 @@ def test_decode_vs_committed_golden(b2a):
     assert y.shape == tuple(g["vocos_shape"]) and np.abs(y[:, :64] - g["vocos_first"]).max() < TOL * peak
     yy = y.astype(np.float64).reshape(-1)
     assert np.abs(np.array([yy.mean(), np.abs(yy).mean(), yy.min(), yy.max()]) - g["vocos_stats"]).max() < TOL * peak
+
+
+def test_adalayernorm_model_vs_oracle(b2a):
+    """AdaLayerNorm (Vocos.swift:17-47, VocosBackbone.swift:44-79,178-193): scale / shift are Linears of the bandwidth conditioning row;
+    different rows of a batch may carry different conditioning; no conditioning -> error where the reference fatalErrors."""
+    cfg = ov.VocosConfig(dim=128, intermediate_dim=256, num_layers=2, adanorm_num_embeddings=4)
+    W = ov.init_weights(cfg, 11)
+    assert "backbone.norm.scale.weight" in W and "backbone.norm.weight" not in W and "backbone.final_layer_norm.weight" in W
+    m = b2a.Vocos(cfg.input_channels, cfg.dim, cfg.intermediate_dim, cfg.num_layers, cfg.n_fft, cfg.hop_length, cfg.input_kernel_size,
+                  cfg.dw_kernel_size, adanorm_num_embeddings=4, weights=W)
+    f = np.random.default_rng(2).standard_normal((3, 70, cfg.input_channels)).astype(np.float32)
+    cond = np.eye(4, dtype=np.float32)[[2, 0, 3]]                          # one-hot bandwidth ids, one per utterance
+    y, ref = m.decode(f, bandwidth_id=cond), ov.decode(cfg, W, f, cond)
+    assert y.shape == ref.shape and max_rel_to_peak(y, ref) < TOL, max_rel_to_peak(y, ref)
+    soft = np.random.default_rng(3).random((3, 4)).astype(np.float32)      # any conditioning row, not only one-hot
+    assert max_rel_to_peak(m.decode(f, bandwidth_id=soft), ov.decode(cfg, W, f, soft)) < TOL
+    assert max_rel_to_peak(m.decode(f, bandwidth_id=cond[::-1].copy()), y) > 1e-2      # the conditioning matters
+    with pytest.raises(b2a.AudioGenerationError) as e:
+        m.decode(f)
+    assert e.value.case == "invalidInput"
+    plain = make(b2a, ov.VocosConfig(dim=128, intermediate_dim=256, num_layers=1), ov.init_weights(ov.VocosConfig(dim=128, intermediate_dim=256, num_layers=1), 3))
+    with pytest.raises(b2a.AudioGenerationError):
+        plain.decode(f[:1], bandwidth_id=cond[:1])                         # a LayerNorm model takes no conditioning
