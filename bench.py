@@ -145,10 +145,10 @@ def kv_bytes(cfg, batch, ctx, elem_bytes: int = 2) -> int:
     return 2 * batch * cfg["num_key_value_heads"] * ctx * cfg["head_dim"] * elem_bytes * cfg["num_hidden_layers"]
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum over the 200 launches of ONE decode step (batch 8, context 320), from
+# dram__bytes_read.sum + dram__bytes_write.sum over the 144 launches of ONE decode step (batch 8, context 320), from
 # `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none python tools/profile_step.py 320 3`
 # on the B200 (profiles/r02_decode_step_dram.csv, summary profiles/r02_decode_step_dram.md)
-MEASURED_STEP_DRAM_BYTES = {"context": 320, "batch": 8, "bytes": 7259108096}
+MEASURED_STEP_DRAM_BYTES = {"context": 320, "batch": 8, "bytes": 7244129280}
 
 
 # ------------------------------------------------------------------------------------------------- CPU legs
@@ -482,6 +482,60 @@ def snac_block(m, torch, timer, rank, world, local, codec, steps, warmup):
                          "algorithmic_minimum_bytes": minimum, "frac_vs_algorithmic_minimum": minimum / (ms_dev / steps * 1e-3) / 1e9 / peak}}
 
 
+Q3_ROWS, Q3_FRAMES, Q3_CHUNK = 4, 1024, 64
+
+
+def qwen3_block(m, torch, timer, rank, world, local, steps, warmup):
+    """BASELINE config 5: Qwen3-TTS-0.6B geometry (talker 1024 x 28, code predictor 1024 x 5, 16 code groups; random-init bf16 -- an
+    8-bit checkpoint is expanded to bf16 at load), batch 32 over 8 GPUs = 4 utterances per GPU, 1024 frames each
+    (81.9 s of audio), the codes decoded by the speech-tokenizer decoder (the model's vocoder) in streaming chunks of 64 frames."""
+    import importlib
+    codec = importlib.import_module("mlx_audio_swift_b200.qwen3_tts_codec")
+    tcfg = m.Qwen3TalkerConfig()
+    talker = m.Qwen3TTSTalker.random_init(tcfg, device=local, max_batch=Q3_ROWS, max_context=Q3_FRAMES + 32, std=0.02, seed=77 + rank)
+    dcfg = codec.Qwen3TTSTokenizerDecoderConfig()
+    dec = codec.Qwen3TTSSpeechTokenizerDecoder(dcfg, weights=codec.random_init_weights(dcfg, 5), device=local, max_batch=Q3_ROWS,
+                                                 max_cache_frames=Q3_FRAMES + 8)
+    rng = np.random.default_rng(9 + rank)
+    H = tcfg.hidden_size
+    embeds = (0.05 * rng.standard_normal((Q3_ROWS, 10, H))).astype(np.float32)          # the prompt rows prepareGenerationInputs builds (L = 10)
+    trailing = (0.05 * rng.standard_normal((Q3_ROWS, 24, H))).astype(np.float32)
+    pad = (0.05 * rng.standard_normal(H)).astype(np.float32)
+    P = m.Qwen3GenerateParameters(max_tokens=Q3_FRAMES, temperature=0.9, top_k=50, top_p=1.0, repetition_penalty=1.05, seed=rank, mask_eos=True)
+    stream = torch.cuda.ExternalStream(talker.stream, device=torch.device("cuda", local))
+    stages = {}
+
+    def step():
+        t0 = time.perf_counter()
+        codes, info = talker.generate_codes(embeds, list(trailing), pad, P)
+        t1 = time.perf_counter()
+        c = np.ascontiguousarray(np.stack(codes).transpose(0, 2, 1))                    # [B, 16, frames]
+        dec.reset_streaming_state()
+        n = 0
+        for f0 in range(0, Q3_FRAMES, Q3_CHUNK):
+            n += dec.streaming_step(c[:, :, f0:f0 + Q3_CHUNK]).shape[-1]
+        stages["talker"], stages["decoder"] = t1 - t0, time.perf_counter() - t1
+        assert n == Q3_FRAMES * 1920 and all(len(x) == Q3_FRAMES for x in codes)
+        return info
+
+    ms, launches, infos = timer(step, stream, steps, warmup)           # every call ends synchronised (codes / audio copied to the host)
+    audio = Q3_ROWS * Q3_FRAMES * 1920 / 24000.0 * world
+    frame_ms = float(np.median([i.generate_time for i in infos])) / Q3_FRAMES * 1e3
+    return {"metric": "qwen3tts_0.6b_rtfx_batch4_per_gpu", "unit": UNIT, "value": audio * steps / (ms * 1e-3), "ms_per_step": ms / steps,
+            "config": {"workload": f"Qwen3-TTS-0.6B geometry random-init bf16, {Q3_ROWS} utterances per GPU (batch 32 on 8 GPUs), 10 prompt rows, {Q3_FRAMES} "
+                                   f"frames x 16 code groups each, sampled (T 0.9, top-k 50, rep 1.05, EOS masked), speech-tokenizer decoder in "
+                                   f"{Q3_CHUNK}-frame streaming chunks", "rows_per_gpu": Q3_ROWS},
+            "e2e": {"value": audio * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
+                    "h2d_bytes_per_step": int(embeds.nbytes + trailing.nbytes + pad.nbytes + Q3_ROWS * 16 * Q3_FRAMES * 4),
+                    "d2h_bytes_per_step": int(Q3_ROWS * Q3_FRAMES * (16 * 4 + 1920 * 4)),
+                    "note": "the only entry points are host-buffer calls (b2a_qwen3_talker_generate, b2a_speech_tokenizer_streaming_step): value == e2e"},
+            "gpu_launches": int(launches), "stages_s": dict(stages), "ms_per_frame": frame_ms,
+            "roofline": {"kernel": "one frame = one CUDA graph (talker step + 16 code-predictor passes + 16 sampler launches)", "bound": "hbm",
+                         "achieved": (0.88e9 + 16 * 0.15e9 + 15 * 2 * 2048 * 1024 * 2) / (frame_ms * 1e-3) / 1e9, "peak": measured_peaks()[0], "unit": "GB/s",
+                         "frac": (0.88e9 + 16 * 0.15e9 + 15 * 2 * 2048 * 1024 * 2) / (frame_ms * 1e-3) / 1e9 / measured_peaks()[0], "traffic": None,
+                         "note": "bytes = talker weights once + predictor weights 16 times + 15 heads/embeddings per frame (bf16); the frame is launch-latency bound, not HBM bound"}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -570,6 +624,10 @@ def main():
         torch.cuda.empty_cache()
         secondary["whisper"] = whisper_block(m, torch, timer, rank, world, local, max(3, min(args.steps, 10)), 3)
         secondary["snac"] = snac_block(m, torch, timer, rank, world, local, codec, max(3, min(args.steps, 10)), 3)
+        try:
+            secondary["qwen3"] = qwen3_block(m, torch, timer, rank, world, local, 2, 1)
+        except Exception as e:      # row N1 is the newest path: the headline line must still print
+            secondary["qwen3"] = {"unavailable": repr(e)[:300]}
 
     if rank != 0:
         if dist is not None:
@@ -587,11 +645,12 @@ def main():
         "gpu_launches": int(launches),
         "stages_s": {"prefill": float(np.median([i.prefill_time for i in infos])), "decode": float(np.median([i.generate_time for i in infos])),
                      "codec": float(np.median([i.codec_time for i in infos]))},
-        "roofline": {"kernel": "decode step (CUDA graph: 28 x [rmsnorm, qkv tcgen05 gemm, 2-CTA-cluster attention, o gemm, rmsnorm, "
-                               "gate/up gemm+swiglu, down gemm] + lm-head gemm + sampler); dominant kernel tc_gemm_kernel<16>", "bound": "hbm",
+        "roofline": {"kernel": "decode step (CUDA graph of 144 launches: embed, norm, 28 x [qkv tcgen05 gemm (rstd in the epilogue), 2-CTA-cluster "
+                               "attention, o cluster split-K gemm (+ residual + norm 2), gate/up gemm + swiglu, down cluster split-K gemm (+ residual + "
+                               "next norm)], lm-head gemm, sampler); dominant kernels tc_gemm_kernel<16> / tc_gemm_splitk_kernel", "bound": "hbm",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "traffic_source": "sum of dram__bytes_read.sum + dram__bytes_write.sum over the 200 launches of one step at context 320, batch 8 "
-                                       "(ncu, profiles/r02_decode_step_dram.csv)",
+                     "traffic_source": "sum of dram__bytes_read.sum + dram__bytes_write.sum over the launches of one step at context 320, batch 8 "
+                                       "(ncu, profiles/r02_decode_step_dram.csv / .md)",
                      "algorithmic_bytes_per_step": alg_bytes, "bytes_definition": "SURVEY.md 8(d): every weight once (bf16, tied lm head) + bf16 K/V read at the mean context",
                      "kv_cache_dtype_built": "f32", "built_bytes_per_step": built_bytes,
                      "ms_per_decode_step": step_ms, "ms_per_decode_step_source": "median generate_time / 511 graph replays inside the timed loop",

@@ -1,8 +1,6 @@
 """Host-side mirror of the Qwen3-TTS speech tokenizer's DECODE side
-(Sources/MLXAudioTTS/Models/Qwen3TTS/Qwen3TTSSpeechTokenizer.swift:888-1092) over the C ABI.
-
-EXPERIMENTAL: the CUDA path behind it has been compiled but not yet run on a GPU; its parity
-tests (tests/test_gpu_qwen3_tts_codec.py) are gated behind B2A_EXPERIMENTAL_N1=1."""
+(Sources/MLXAudioTTS/Models/Qwen3TTS/Qwen3TTSSpeechTokenizer.swift:888-1092) over the C ABI (SURVEY.md section 8f row N1;
+parity tests: tests/test_gpu_qwen3_tts_codec.py)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -40,6 +38,82 @@ class Qwen3TTSTokenizerDecoderConfig:
     def from_dict(cls, d: dict) -> "Qwen3TTSTokenizerDecoderConfig":
         known = {f for f in cls.__dataclass_fields__}
         return cls(**{k: v for k, v in d.items() if k in known})
+
+
+def random_init_weights(cfg: "Qwen3TTSTokenizerDecoderConfig", seed: int = 1234, layer_scale: float = 0.01, out_gain: float = 0.02) -> Dict[str, np.ndarray]:
+    """Random-init weights with the reference's key set and MLX layouts (benchmarks; there are no checkpoints here): conv / linear
+    weights N(0, 1 / fan_in), biases N(0, 0.05^2), norm gains 1, SnakeBeta alpha = beta = 0."""
+    rng = np.random.default_rng(seed)
+    W: Dict[str, np.ndarray] = {}
+
+    def rn(shape, s):
+        return (rng.standard_normal(shape) * s).astype(np.float32)
+
+    def conv(prefix, cout, k, cin, bias=True):
+        W[prefix + ".weight"] = rn((cout, k, cin), 1.0 / np.sqrt(k * cin))
+        if bias:
+            W[prefix + ".bias"] = rn((cout,), 0.05)
+
+    def lin(prefix, cout, cin, bias=True):
+        W[prefix + ".weight"] = rn((cout, cin), 1.0 / np.sqrt(cin))
+        if bias:
+            W[prefix + ".bias"] = rn((cout,), 0.05)
+
+    def snake(prefix, c):
+        W[prefix + ".alpha"] = np.zeros(c, np.float32)
+        W[prefix + ".beta"] = np.zeros(c, np.float32)
+
+    half = cfg.codebook_dim // 2
+    for name, n in (("rvq_first", cfg.num_semantic_quantizers), ("rvq_rest", cfg.num_quantizers - cfg.num_semantic_quantizers)):
+        for i in range(n):
+            p = f"quantizer.{name}.vq.layers.{i}.codebook"
+            W[p + ".cluster_usage"] = np.ones(cfg.codebook_size, np.float32)
+            W[p + ".embedding_sum"] = rn((cfg.codebook_size, half), 1.0)
+        conv(f"quantizer.{name}.output_proj", cfg.codebook_dim, 1, half, bias=False)
+    conv("pre_conv.conv", cfg.latent_dim, 3, cfg.codebook_dim)
+    H, hd = cfg.hidden_size, cfg.head_dim
+    lin("pre_transformer.input_proj", H, cfg.latent_dim)
+    lin("pre_transformer.output_proj", cfg.latent_dim, H)
+    W["pre_transformer.norm.weight"] = np.ones(H, np.float32)
+    for i in range(cfg.num_hidden_layers):
+        p = f"pre_transformer.layers.{i}"
+        lin(p + ".self_attn.q_proj", cfg.num_attention_heads * hd, H, bias=cfg.attention_bias)
+        lin(p + ".self_attn.k_proj", cfg.num_key_value_heads * hd, H, bias=cfg.attention_bias)
+        lin(p + ".self_attn.v_proj", cfg.num_key_value_heads * hd, H, bias=cfg.attention_bias)
+        lin(p + ".self_attn.o_proj", H, cfg.num_attention_heads * hd, bias=cfg.attention_bias)
+        lin(p + ".mlp.gate_proj", cfg.intermediate_size, H, bias=False)
+        lin(p + ".mlp.up_proj", cfg.intermediate_size, H, bias=False)
+        lin(p + ".mlp.down_proj", H, cfg.intermediate_size, bias=False)
+        W[p + ".input_layernorm.weight"] = np.ones(H, np.float32)
+        W[p + ".post_attention_layernorm.weight"] = np.ones(H, np.float32)
+        W[p + ".self_attn_layer_scale.scale"] = np.full(H, layer_scale, np.float32)
+        W[p + ".mlp_layer_scale.scale"] = np.full(H, layer_scale, np.float32)
+    L = cfg.latent_dim
+    for i, f in enumerate(cfg.upsampling_ratios):
+        conv(f"upsample.{i}.layers.0.conv", L, f, L)
+        p = f"upsample.{i}.layers.1"
+        conv(p + ".dwconv.conv", L, 7, 1)
+        W[p + ".norm.weight"] = np.ones(L, np.float32)
+        W[p + ".norm.bias"] = np.zeros(L, np.float32)
+        lin(p + ".pwconv1", 4 * L, L)
+        lin(p + ".pwconv2", L, 4 * L)
+        W[p + ".gamma"] = np.full(L, 0.3, np.float32)
+    conv("decoder.0.conv", cfg.decoder_dim, 7, L)
+    for b, r in enumerate(cfg.upsample_rates):
+        cin, cout = cfg.decoder_dim >> b, cfg.decoder_dim >> (b + 1)
+        p = f"decoder.{1 + b}.block"
+        snake(p + ".0", cin)
+        conv(p + ".1.conv", cout, 2 * r, cin)
+        for j in (2, 3, 4):
+            snake(f"{p}.{j}.act1", cout)
+            conv(f"{p}.{j}.conv1.conv", cout, 7, cout)
+            snake(f"{p}.{j}.act2", cout)
+            conv(f"{p}.{j}.conv2.conv", cout, 1, cout)
+    n = len(cfg.upsample_rates)
+    snake(f"decoder.{n + 1}", cfg.decoder_dim >> n)
+    conv(f"decoder.{n + 2}.conv", 1, 7, cfg.decoder_dim >> n)
+    W[f"decoder.{n + 2}.conv.weight"] *= out_gain
+    return W
 
 
 def check_array_shape(shape: Tuple[int, ...]) -> bool:

@@ -1,5 +1,5 @@
 """The implicit-GEMM causal convolution kernel (csrc/implicit_conv.cuh) alone, through b2a_implicit_conv_test, against its numpy
-contract (tests/implicit_conv_model.py).  GATED like the rest of row N1 (B2A_EXPERIMENTAL_N1=1): not yet run on a GPU."""
+contract (tests/implicit_conv_model.py).  Green on the B200 since round 2 (row N1)."""
 import os
 
 import numpy as np
@@ -7,8 +7,7 @@ import pytest
 
 from implicit_conv_model import implicit_conv
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("B2A_EXPERIMENTAL_N1") != "1",
-                                                  reason="experimental N1 path: set B2A_EXPERIMENTAL_N1=1")]
+pytestmark = pytest.mark.gpu
 
 
 def run(b2a, w, x, T, *, dil=1, shift0=0, up=1, bias=None, gamma=None, gelu=False, add=None, twice=False, sa=None, sb=None, Hout=0, want_xo=True, want_hl=True, fp16=0):

@@ -1,5 +1,5 @@
 """The Qwen3-TTS sampler kernel (csrc/qwen3_sampler.cu) through b2a_qwen3_sample_test against the oracle's sampleToken restatement.
-GATED like the rest of row N1 (B2A_EXPERIMENTAL_N1=1): not yet run on a GPU."""
+Green on the B200 since round 2 (row N1); the same kernel is launched per frame by the talker loop (tests/test_gpu_qwen3_talker.py)."""
 import os
 
 import numpy as np
@@ -9,8 +9,7 @@ import torch
 from oracle import qwen3_tts as oq
 from qwen3_sampler_model import filtered_row
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("B2A_EXPERIMENTAL_N1") != "1",
-                                                  reason="experimental N1 path: set B2A_EXPERIMENTAL_N1=1")]
+pytestmark = pytest.mark.gpu
 
 
 def run(b2a, logits, *, T=0.9, top_p=1.0, top_k=50, min_p=0.0, rep=1.0, eos=-1, suppress=(0, 0), seen=None, track=0, seed=1, step=0, want_filtered=True):

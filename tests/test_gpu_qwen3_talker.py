@@ -150,3 +150,37 @@ def test_shipped_geometry_logits_and_greedy_frames_vs_oracle(b2a):
     codes, _ = m.generate_codes(ri.numpy().astype(np.float32), [rt[0].numpy()], rp[0, 0].numpy(), P)
     ref = ot.generate_codes(cfg, W, ri, rt, rp, max_tokens=4, temperature=0.0, repetition_penalty=1.05, stop_on_eos=False).numpy()
     assert np.array_equal(codes[0], ref), (codes[0], ref)
+
+
+def test_text_ids_to_waveform_and_streamed_chunks(b2a, small):
+    """Qwen3TTSModel: prompt rows -> talker / code predictor frames -> speech-tokenizer decoder.  One-shot generate() equals the
+    oracle's decode of the oracle's greedy codes; generate_stream() hands out audio chunks produced from inside the frame loop
+    (b2a_qwen3_talker_generate's on_frame hook -> streaming_step), equal to the oracle's streamed decode of the same chunking."""
+    import importlib
+    from conftest import max_rel_to_peak
+    from oracle import qwen3_tts_codec as oc
+    codec = importlib.import_module("mlx_audio_swift_b200.qwen3_tts_codec")
+    cfg, W, m = small
+    dcfg = oc.mid_config(codebook_size=2048)                      # 4 quantizers = the small talker's 4 code groups
+    DW = oc.init_weights(dcfg, 5)
+    tok = codec.Qwen3TTSSpeechTokenizer(codec.Qwen3TTSTokenizerDecoderConfig.from_dict({k: getattr(dcfg, k) for k in dcfg.__dataclass_fields__}),
+                                        weights={k: v.numpy() for k, v in DW.items()}, decode_upsample_rate=dcfg.total_upsample, max_batch=1)
+    model = b2a.Qwen3TTSModel(m, tok)
+    inp, trail, pad = m.prepare_generation_inputs(CHAT, **TTS, language_id=2160)
+    ri, rt, rp = ot.prepare_generation_inputs(cfg, W, CHAT, **TTS, language_id=2160)
+    P = b2a.Qwen3GenerateParameters(max_tokens=9, temperature=0.0, repetition_penalty=1.05, mask_eos=True)
+    ref_codes = ot.generate_codes(cfg, W, ri, rt, rp, max_tokens=9, temperature=0.0, repetition_penalty=1.05, stop_on_eos=False).numpy()
+    wav = model.generate(inp, trail, pad, P)
+    ref_wav, ref_len = oc.decode(dcfg, DW, ref_codes[None])
+    assert len(wav) == int(ref_len[0]) == 9 * dcfg.total_upsample
+    assert max_rel_to_peak(wav, ref_wav[0, :len(wav)]) < TOL
+    events = list(model.generate_stream(inp, trail, pad, P, streaming_interval=0.32))      # int(0.32 * 12.5) = 4 frames per chunk
+    toks = [v for k, v in events if k == "token"]
+    chunks = [v for k, v in events if k == "audio"]
+    assert toks == ref_codes[:, 0].tolist() and [len(c) for c in chunks] == [4 * dcfg.total_upsample] * 2 + [dcfg.total_upsample]
+    assert events[-1][0] == "info" and events.index(("token", toks[4])) < [i for i, e in enumerate(events) if e[0] == "audio"][1]
+    d = oc.SpeechTokenizerDecoder(dcfg, DW)
+    d.reset_streaming_state()
+    c = ref_codes.T[None]
+    want = np.concatenate([d.streaming_step(c[:, :, a:b])[0, 0].numpy() for a, b in ((0, 4), (4, 8), (8, 9))])
+    assert max_rel_to_peak(np.concatenate(chunks), want) < TOL
