@@ -578,6 +578,14 @@ int32_t b2a_qwen3_talker_generate(b2a_qwen3_talker* h, const float* input_embeds
                                   const float* trailing_text_hidden, const int32_t* n_trailing, int32_t n_trailing_max,
                                   const float* tts_pad_embed, const b2a_qwen3_gen_params* params, int32_t* codes_out,
                                   int32_t* n_frames_out, b2a_gen_info* info, b2a_frame_cb on_frame, void* user);
+/* Loading (Qwen3TTSModel.fromModelDirectory, Qwen3TTS.swift:1136-1175, talker half): config.json's "talker_config" (+ nested
+ * "code_predictor_config", defaults of Qwen3TTSConfig.swift:45-63,268-292) -> the config struct; every *.safetensors of the directory
+ * -> keep "talker.*" and strip the prefix (Qwen3TTSTalker.swift:356-365) -> MLX affine de-quantisation of every layer that carries
+ * ".scales" as config.json's "quantization" block says (:1156-1171; 8-bit group-64 for the shipped 8-bit checkpoints) -> create.     */
+int32_t b2a_qwen3_talker_config_from_json(const char* config_path, int32_t max_batch, int32_t max_context, b2a_qwen3_talker_config* cfg);
+int32_t b2a_weights_sanitize_qwen3_talker(b2a_weights* w, const char* config_path /* nullable: no quantisation */);
+int32_t b2a_qwen3_talker_create_from_directory(const char* model_dir, int32_t device, int32_t max_batch, int32_t max_context,
+                                               b2a_qwen3_talker** out);
 int32_t b2a_qwen3_talker_cancel(b2a_qwen3_talker* h);
 void b2a_qwen3_talker_destroy(b2a_qwen3_talker* h);
 

@@ -227,6 +227,9 @@ SIGNATURES = {
     "b2a_qwen3_talker_forward": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
     "b2a_qwen3_talker_generate": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, _P, _P, C.c_int32, _P, C.POINTER(Qwen3GenParams), _P, _P,
                                               C.POINTER(GenInfo), _P, _P]),
+    "b2a_qwen3_talker_config_from_json": (C.c_int32, [C.c_char_p, C.c_int32, C.c_int32, C.POINTER(Qwen3TalkerConfig)]),
+    "b2a_weights_sanitize_qwen3_talker": (C.c_int32, [_P, C.c_char_p]),
+    "b2a_qwen3_talker_create_from_directory": (C.c_int32, [C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P)]),
     "b2a_qwen3_talker_cancel": (C.c_int32, [_P]),
     "b2a_qwen3_talker_destroy": (None, [_P]),
     "b2a_stt_cancel": (C.c_int32, [_P]),

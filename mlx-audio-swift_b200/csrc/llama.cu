@@ -1033,132 +1033,152 @@ __device__ __forceinline__ float uniform01(unsigned long long seed, unsigned lon
     return (float)(z >> 40) * (1.0f / 16777216.0f);
 }
 
-// Logits processors + sampler, one CTA per row, no atomics (deterministic for a given seed):
+// Logits processors + sampler (deterministic for a given seed, no atomics):
 //   RepetitionContext.process -> EOS mask (bench only) -> argmax | TopPSampler.
-// Top-p = "sample from the smallest top set whose mass reaches top_p".  Implemented as rejection
-// sampling: draw token ~ softmax(l/T) by inverse CDF, accept iff the mass of strictly more probable
-// tokens is < top_p (exactly the nucleus membership test; ties are all kept).  Acceptance probability
-// is >= top_p, so a handful of attempts suffice; after SM_MAX_ATTEMPTS the argmax (always in the
-// nucleus) is returned.
-__global__ void __launch_bounds__(SM_THREADS)
+// Top-p = "sample from the smallest top set whose mass reaches top_p".  Implemented as rejection sampling: draw
+// token ~ softmax(l/T) by the Gumbel-max trick (token = argmax_i l_i/T + g_i, g_i = -log(-log(u_i)), u_i a hash of (seed, row,
+// step, attempt, i): one coalesced pass, no inverse-CDF walk), accept iff the mass of strictly more probable tokens is < top_p
+// (exactly the nucleus membership test; ties are all kept).  The acceptance probability is >= top_p, so a handful of
+// attempts suffice; after SM_MAX_ATTEMPTS the argmax (always in the nucleus) is returned.
+// One thread-block CLUSTER of SM_CLUSTER CTAs per row: every CTA owns a contiguous 1/8 of the vocabulary (19 618 of Orpheus's
+// 156 940 logits: 20 per thread) and the per-pass (max, index) / sums are exchanged through distributed shared memory -- every CTA
+// writes its partial into every peer's slot, one cluster barrier, every CTA reduces the 8 partials in rank order.  (Round 1 ran one
+// CTA per row: 8 of 148 SMs, and the sampling passes were bound by that one SM's issue rate: 104-148 us per launch against 17 us
+// for the greedy pick, 6 % of the decode step.)
+constexpr int SM_CLUSTER = 8;
+struct SampleExchange { float v[2][SM_CLUSTER]; int i[2][SM_CLUSTER]; float s[2][SM_CLUSTER]; };
+
+__global__ void __cluster_dims__(SM_CLUSTER, 1, 1) __launch_bounds__(SM_THREADS)
 sample_kernel(SampleArgs a) {
+    namespace cgr = cooperative_groups;
+    cgr::cluster_group cluster = cgr::this_cluster();
+    const int rank = (int)cluster.block_rank();
     __shared__ float sred[SM_WARPS];
-    __shared__ float wtot[SM_WARPS];
-    __shared__ int s_tok, s_pick;
     __shared__ float s_val[SM_WARPS];
     __shared__ int s_idx[SM_WARPS];
-    const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    __shared__ SampleExchange ex;
+    const int b = blockIdx.x / SM_CLUSTER, t = threadIdx.x, lane = t & 31, warp = t >> 5;
     pdl_wait();                  // NO pdl_trigger(): this kernel writes pos[] (see attn_decode_cluster_kernel)
     float* lg = a.logits + (long long)b * a.V;
-    float* pr = a.probs + (long long)b * a.V;
+    const int chunk = (a.V + SM_CLUSTER - 1) / SM_CLUSTER, i0 = rank * chunk, i1 = min(a.V, i0 + chunk);
     const int nrec = min(a.recent_n[b], a.R);
+    int parity = 0;
+    int tok_final = 0;
+
+    // (value, index) and a sum: block reduce, then all-to-all through distributed shared memory; every CTA ends with the same result
+    auto exchange = [&](float& v, int& i, float& sum) {
+        for (int o = 16; o; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+            if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+        }
+        sum = warp_sum(sum);
+        __syncthreads();
+        if (lane == 0) { s_val[warp] = v; s_idx[warp] = i; sred[warp] = sum; }
+        __syncthreads();
+        if (warp == 0) {
+            float bv = s_val[lane], bs = sred[lane];
+            int bi = s_idx[lane];
+            for (int o = 16; o; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            bs = warp_sum(bs);
+            if (lane < SM_CLUSTER) {             // lane p writes this CTA's partial into CTA p's slot [rank]
+                SampleExchange* peer = cluster.map_shared_rank(&ex, lane);
+                peer->v[parity][rank] = bv; peer->i[parity][rank] = bi; peer->s[parity][rank] = bs;
+            }
+        }
+        cluster.sync();
+        v = ex.v[parity][0]; i = ex.i[parity][0]; sum = ex.s[parity][0];
+#pragma unroll
+        for (int r = 1; r < SM_CLUSTER; ++r) {
+            const float ov = ex.v[parity][r];
+            const int oi = ex.i[parity][r];
+            if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+            sum += ex.s[parity][r];
+        }
+        parity ^= 1;
+    };
 
     if (a.forced == nullptr) {
-        // RepetitionContext.process: once per unique token among the last R
+        // RepetitionContext.process: once per unique token among the last R; every CTA handles the tokens of its own range
         if (a.rep_penalty != 1.0f && t < nrec) {
             const int tok = a.recent[b * a.R + t];
             bool dup = false;
             for (int j = 0; j < t; ++j) dup |= (a.recent[b * a.R + j] == tok);
-            if (!dup && tok >= 0 && tok < a.V) {
+            if (!dup && tok >= i0 && tok < i1) {
                 const float l = lg[tok];
                 lg[tok] = l < 0.f ? l * a.rep_penalty : l / a.rep_penalty;
             }
         }
-        if (a.mask_eos && t == 0 && TOK_END_OF_SPEECH < a.V) lg[TOK_END_OF_SPEECH] = -INFINITY;
+        if (a.mask_eos && t == 0 && TOK_END_OF_SPEECH >= i0 && TOK_END_OF_SPEECH < i1) lg[TOK_END_OF_SPEECH] = -INFINITY;
         __syncthreads();
 
         // max (and argmax, lowest index wins ties)
-        float best = -INFINITY;
+        float best = -INFINITY, dummy = 0.f;
         int bi = 0x7fffffff;
-        for (int i = t; i < a.V; i += SM_THREADS) {
+        for (int i = i0 + t; i < i1; i += SM_THREADS) {
             const float v = lg[i];
             if (v > best) { best = v; bi = i; }
         }
-        for (int o = 16; o; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-        }
-        if (lane == 0) { s_val[warp] = best; s_idx[warp] = bi; }
-        __syncthreads();
-        if (t == 0) {
-            for (int i = 1; i < SM_WARPS; ++i)
-                if (s_val[i] > best || (s_val[i] == best && s_idx[i] < bi)) { best = s_val[i]; bi = s_idx[i]; }
-            s_val[0] = best; s_tok = bi;
-        }
-        __syncthreads();
-        const float mx = s_val[0];
+        exchange(best, bi, dummy);
+        const float mx = best;
+        tok_final = bi;
 
         if (a.temperature > 0.f) {
-            // p = exp((l - max)/T) (unnormalised); each warp owns one contiguous segment of the vocabulary
             const float inv_t = 1.0f / a.temperature;
-            const int seg = ((a.V + SM_WARPS - 1) / SM_WARPS + 31) & ~31;
-            const int s0 = warp * seg, s1 = min(a.V, s0 + seg);
-            float z = 0.f;
-            for (int i = s0 + lane; i < s1; i += 32) {
-                const float e = __expf((lg[i] - mx) * inv_t);
-                pr[i] = e;
-                z += e;
-            }
-            z = warp_sum(z);
-            if (lane == 0) wtot[warp] = z;
-            __syncthreads();
-            float Z = 0.f;
-#pragma unroll
-            for (int w = 0; w < SM_WARPS; ++w) Z += wtot[w];
-            const float target = a.top_p * Z;
             const int step = a.n_gen[b];
-            bool accepted = false;
-            for (int att = 0; att < SM_MAX_ATTEMPTS && !accepted; ++att) {
-                const float r = uniform01(a.seed, (unsigned long long)b, (unsigned long long)step, (unsigned long long)att) * Z;
-                // owning warp: first w with prefix(w+1) > r
-                float run = 0.f;
-                int ow = SM_WARPS - 1;
-                for (int w = 0; w < SM_WARPS; ++w) {
-                    if (run + wtot[w] > r) { ow = w; break; }
-                    run += wtot[w];
-                }
-                if (t == 0) s_pick = -1;
-                __syncthreads();
-                if (warp == ow) {   // cooperative inverse-CDF walk over this warp's segment
-                    int pick = -1, last_pos = -1;
-                    for (int base = s0; base < s1 && pick < 0; base += 32) {
-                        const int i = base + lane;
-                        const float p = i < s1 ? pr[i] : 0.f;
-                        float inc = p;
-#pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            const float n = __shfl_up_sync(0xffffffffu, inc, o);
-                            if (lane >= o) inc += n;
-                        }
-                        const unsigned hit = __ballot_sync(0xffffffffu, p > 0.f && run + inc > r);
-                        const unsigned posm = __ballot_sync(0xffffffffu, p > 0.f);
-                        if (posm) last_pos = base + 31 - __clz(posm);
-                        if (hit) pick = base + __ffs(hit) - 1;
-                        run += __shfl_sync(0xffffffffu, inc, 31);
-                    }
-                    if (pick < 0) pick = last_pos;        // rounding corner: r beyond the last partial sum
-                    if (lane == 0) s_pick = pick;
-                }
-                __syncthreads();
-                const int cand = s_pick;
-                if (cand < 0) continue;
-                if (a.top_p >= 1.0f) { accepted = true; if (t == 0) s_tok = cand; break; }
-                const float pt = pr[cand];
-                float gm = 0.f;
-                for (int i = t; i < a.V; i += SM_THREADS) { const float p = pr[i]; if (p > pt) gm += p; }
-                gm = block_sum_1024(gm, sred);
-                if (gm < target) { accepted = true; if (t == 0) s_tok = cand; }
+            auto gumbel_key = [&](int i, float l, int att) {
+                unsigned long long z = a.seed + 0x9E3779B97F4A7C15ull * ((unsigned long long)b * 1000003ull + (unsigned long long)step * 131ull + (unsigned long long)att + 1ull);
+                z ^= (unsigned long long)(unsigned)i * 0xD6E8FEB86659FD93ull;
+                z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+                z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+                z ^= z >> 31;
+                const float u = ((float)(z >> 40) + 0.5f) * (1.0f / 16777216.0f);      // (0, 1)
+                return l * inv_t - __logf(-__logf(u));
+            };
+            // pass A: Z = sum exp((l - max) / T) and the first draw
+            float z = 0.f, gv = -INFINITY;
+            int gi = 0x7fffffff;
+            for (int i = i0 + t; i < i1; i += SM_THREADS) {
+                const float l = lg[i];
+                z += __expf((l - mx) * inv_t);
+                const float k = l == -INFINITY ? -INFINITY : gumbel_key(i, l, 0);
+                if (k > gv) { gv = k; gi = i; }
             }
-            __syncthreads();
+            exchange(gv, gi, z);
+            const float Z = z;
+            int cand = gi;
+            bool accepted = a.top_p >= 1.0f;
+            for (int att = 0; !accepted; ++att) {
+                // nucleus test: the mass of strictly more probable tokens must be below top_p
+                const float lc = lg[cand];
+                float gm = 0.f, dv = -INFINITY;
+                int di = 0x7fffffff;
+                for (int i = i0 + t; i < i1; i += SM_THREADS) { const float l = lg[i]; if (l > lc) gm += __expf((l - mx) * inv_t); }
+                exchange(dv, di, gm);
+                if (gm < a.top_p * Z) { accepted = true; break; }
+                if (att + 1 >= SM_MAX_ATTEMPTS) { cand = tok_final; break; }      // the argmax is always in the nucleus
+                gv = -INFINITY; gi = 0x7fffffff;
+                float ds = 0.f;
+                for (int i = i0 + t; i < i1; i += SM_THREADS) {
+                    const float l = lg[i];
+                    const float k = l == -INFINITY ? -INFINITY : gumbel_key(i, l, att + 1);
+                    if (k > gv) { gv = k; gi = i; }
+                }
+                exchange(gv, gi, ds);
+                cand = gi;
+            }
+            if (cand >= 0 && cand < a.V) tok_final = cand;
         }
     } else {
-        if (t == 0) s_tok = a.forced[b];
-        __syncthreads();
+        tok_final = a.forced[b];
     }
 
-    if (t == 0) {
-        const int tok = s_tok;
+    if (rank == 0 && t == 0) {
+        const int tok = tok_final;
         a.tokens[b] = tok;
         a.pos[b] += 1;
         const int rn = a.recent_n[b];
@@ -1304,6 +1324,7 @@ struct b2a_tts {
     bool use_batched_prefill = true;
     DBuf<int> tokens, pos, recent, recent_n, out_tokens, n_gen, done, n_active, ids, forced;
     HBuf<int> h_flag;
+    cudaEvent_t ev_poll[2] = {nullptr, nullptr};   // the generate loop's pipelined "rows still active" polls
     // fused-norm decode step (default on the tcgen05 path): o_proj / down_proj run as cluster split-K GEMMs whose leader CTA does the
     // residual add + the next norm's gain + hi/lo split + sum of squares; no stand-alone add_rmsnorm launches (tc_gemm.cuh)
     bool fused = false;
@@ -1328,6 +1349,7 @@ struct b2a_tts {
     ~b2a_tts() {
         if (g_step) cudaGraphExecDestroy(g_step);
         if (g_prefill) cudaGraphExecDestroy(g_prefill);
+        for (auto& e : ev_poll) if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
     }
 
@@ -1927,7 +1949,7 @@ struct b2a_tts {
         B2A_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
         run_layers(B, stream);
         run_lm_head(B, stream);
-        launch_pdl(sample_kernel, dim3(B), dim3(SM_THREADS), 0, stream, sa);
+        launch_pdl(sample_kernel, dim3(B * SM_CLUSTER), dim3(SM_THREADS), 0, stream, sa);
         B2A_CUDA(cudaStreamEndCapture(stream, &g));
         B2A_CUDA(cudaGraphInstantiate(&g_step, g, 0));
         cudaGraphDestroy(g);
@@ -2031,7 +2053,7 @@ static void tts_generate_impl(b2a_tts* h, const int32_t* input_ids, bool ids_on_
     if (h->can_batch_prefill(L)) {
         h->prefill_batched(B, L, s);
         h->run_lm_head_after_prefill(B, s);
-        launch_pdl(sample_kernel, dim3(B), dim3(SM_THREADS), 0, s, sa);
+        launch_pdl(sample_kernel, dim3(B * SM_CLUSTER), dim3(SM_THREADS), 0, s, sa);
         steps = 1;
     } else {
         for (int p = 0; p < L - 1; ++p) {
@@ -2105,6 +2127,13 @@ static void tts_generate_impl(b2a_tts* h, const int32_t* input_ids, bool ids_on_
         B2A_CUDA(cudaMemcpyAsync(h->h_flag.p, h->n_active.p, sizeof(int), cudaMemcpyDeviceToHost, s));
         B2A_CUDA(cudaStreamSynchronize(s));
     }
+    // Without per-token callbacks the host keeps ONE burst of graph launches queued ahead of the burst whose "rows still active"
+    // flag it is waiting for, so the GPU never idles while the host polls (round 1 synchronised after every burst: 5 % of the
+    // loop).  A burst launched after every row has finished only replays steps whose tokens are not recorded; steps never exceed
+    // max_tokens, so the KV cache cannot overflow.
+    const bool pipelined = !on_token && !streaming;
+    if (pipelined && !h->ev_poll[0]) { B2A_CUDA(cudaEventCreateWithFlags(&h->ev_poll[0], cudaEventDisableTiming)); B2A_CUDA(cudaEventCreateWithFlags(&h->ev_poll[1], cudaEventDisableTiming)); }
+    int slot = 0, pending = -1;
     while (steps < MT && !(steps == 1 && h->h_flag.p[0] <= 0)) {
         const int burst = on_token ? 1 : std::min(streaming ? 7 : 16, MT - steps);
         for (int i = 0; i < burst; ++i) {
@@ -2112,6 +2141,17 @@ static void tts_generate_impl(b2a_tts* h, const int32_t* input_ids, bool ids_on_
             count_launch(h->launches_step);
         }
         steps += burst;
+        if (pipelined) {
+            B2A_CUDA(cudaMemcpyAsync(h->h_flag.p + 1 + slot, h->n_active.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+            B2A_CUDA(cudaEventRecord(h->ev_poll[slot], s));
+            if (pending >= 0) {
+                B2A_CUDA(cudaEventSynchronize(h->ev_poll[pending]));
+                if (h->cancel.load()) { cancelled = true; break; }
+                if (h->h_flag.p[1 + pending] <= 0) break;
+            }
+            pending = slot; slot ^= 1;
+            continue;
+        }
         B2A_CUDA(cudaMemcpyAsync(h->h_flag.p, h->n_active.p, sizeof(int), cudaMemcpyDeviceToHost, s));
         B2A_CUDA(cudaStreamSynchronize(s));
         if (on_token) stream_tokens();
@@ -2119,6 +2159,7 @@ static void tts_generate_impl(b2a_tts* h, const int32_t* input_ids, bool ids_on_
         if (h->cancel.load()) { cancelled = true; break; }
         if (h->h_flag.p[0] <= 0) break;
     }
+    if (pipelined) { B2A_CUDA(cudaStreamSynchronize(s)); if (h->cancel.load()) cancelled = true; }
     if (streaming && !cancelled) emit_audio(true);
     const double t2 = now_s();
     B2A_CHECK(!cancelled, B2A_ERR_CANCELLED, "generation cancelled");

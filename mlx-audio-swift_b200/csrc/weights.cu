@@ -466,6 +466,21 @@ struct b2a_weights {
         }
     }
 
+    // ---- Qwen3-TTS talker: Qwen3TTSTalkerForConditionalGeneration.sanitize (Qwen3TTSTalker.swift:356-365) keeps "talker.*" and drops
+    // the prefix; a quantised checkpoint (config "quantization", Qwen3TTS.swift:1156-1171: every layer that carries ".scales") is
+    // expanded to bf16 -- the engine streams bf16 matrices.
+    void sanitize_qwen3_talker(const QuantSpec& spec) {
+        std::vector<WItem> out;
+        for (auto& it : items) {
+            if (it.name.rfind("talker.", 0) != 0) continue;
+            WItem t = it;
+            t.name = it.name.substr(7);
+            out.push_back(std::move(t));
+        }
+        items = std::move(out);
+        dequantize_layers(spec);
+    }
+
     // ---- Qwen3-TTS speech tokenizer, decoder half of Qwen3TTSSpeechTokenizer.sanitize (Qwen3TTSSpeechTokenizer.swift:1094-1440).
     // Output: the keys b2a_speech_tokenizer_create takes (below the "decoder." module) in MLX layouts.  encoder.* (voice-cloning
     // encoder) and speaker-encoder keys are dropped.
@@ -683,6 +698,73 @@ int32_t b2a_tts_create_from_directory(const char* model_dir, int32_t device, int
         w->sanitize_llama(cfg.tie_word_embeddings != 0, parse_quant(read_json_file(dir + "/config.json")));
         const std::vector<b2a_tensor> tab = w->table();
         st = b2a_tts_create(device, &cfg, tab.data(), (int32_t)tab.size(), snac, out);
+        if (st != B2A_OK) throw Error(st, b2a_last_error());
+    });
+}
+
+// config.json -> b2a_qwen3_talker_config: "talker_config" with its nested "code_predictor_config" (Qwen3TTSConfig.swift:45-63,268-292; the
+// same defaults), max_batch / max_context from the caller.
+static b2a_qwen3_talker_config qwen3_talker_config_of(const Json& root, int max_batch, int max_context) {
+    Json empty;
+    empty.kind = Json::Obj;
+    const Json* tj = root.find("talker_config");
+    const Json& t = (tj && tj->kind == Json::Obj) ? *tj : empty;
+    const Json* pj = t.find("code_predictor_config");
+    const Json& p = (pj && pj->kind == Json::Obj) ? *pj : empty;
+    b2a_qwen3_talker_config c{};
+    c.vocab_size = (int)t.number("vocab_size", 3072); c.hidden_size = (int)t.number("hidden_size", 1024);
+    c.intermediate_size = (int)t.number("intermediate_size", 3072); c.num_hidden_layers = (int)t.number("num_hidden_layers", 28);
+    c.num_attention_heads = (int)t.number("num_attention_heads", 16); c.num_key_value_heads = (int)t.number("num_key_value_heads", 8);
+    c.head_dim = (int)t.number("head_dim", 128); c.rms_norm_eps = (float)t.number("rms_norm_eps", 1e-6);
+    c.rope_theta = (float)t.number("rope_theta", 1000000.0); c.num_code_groups = (int)t.number("num_code_groups", 16);
+    c.text_hidden_size = (int)t.number("text_hidden_size", 2048); c.text_vocab_size = (int)t.number("text_vocab_size", 151936);
+    c.codec_eos_token_id = (int)t.number("codec_eos_token_id", 2150);
+    c.cp_vocab_size = (int)p.number("vocab_size", 2048); c.cp_hidden_size = (int)p.number("hidden_size", 1024);
+    c.cp_intermediate_size = (int)p.number("intermediate_size", 3072); c.cp_num_hidden_layers = (int)p.number("num_hidden_layers", 5);
+    c.cp_num_attention_heads = (int)p.number("num_attention_heads", 16); c.cp_num_key_value_heads = (int)p.number("num_key_value_heads", 8);
+    c.cp_head_dim = (int)p.number("head_dim", 128); c.cp_rms_norm_eps = (float)p.number("rms_norm_eps", 1e-6);
+    c.cp_rope_theta = (float)p.number("rope_theta", 1000000.0);
+    B2A_CHECK(t.number("attention_bias", 0) == 0 && p.number("attention_bias", 0) == 0, B2A_ERR_INVALID_INPUT,
+              "qwen3 talker: attention_bias = true is not supported");
+    c.max_batch = max_batch; c.max_context = max_context;
+    return c;
+}
+
+int32_t b2a_qwen3_talker_config_from_json(const char* config_path, int32_t max_batch, int32_t max_context, b2a_qwen3_talker_config* cfg) {
+    return guarded([&] {
+        B2A_CHECK(config_path && cfg, B2A_ERR_INVALID_INPUT, "b2a_qwen3_talker_config_from_json: null argument");
+        const Json j = read_json_file(config_path);
+        B2A_CHECK(j.kind == Json::Obj, B2A_ERR_MODEL_NOT_INITIALIZED, "config.json is not an object");
+        *cfg = qwen3_talker_config_of(j, max_batch, max_context);
+    });
+}
+
+int32_t b2a_weights_sanitize_qwen3_talker(b2a_weights* w, const char* config_path) {
+    return guarded([&] {
+        B2A_CHECK(w, B2A_ERR_INVALID_INPUT, "b2a_weights_sanitize_qwen3_talker: null handle");
+        QuantSpec q;
+        if (config_path && *config_path) q = parse_quant(read_json_file(config_path));
+        w->sanitize_qwen3_talker(q);
+    });
+}
+
+// Qwen3TTSModel.fromModelDirectory (Qwen3TTS.swift:1136-1175), the talker half: config.json + every *.safetensors -> sanitize ->
+// (de)quantise -> create.  The tokenizer, the speaker encoder and the speech tokenizer (b2a_speech_tokenizer_create_from_directory on
+// <dir>/speech_tokenizer) are the caller's.
+int32_t b2a_qwen3_talker_create_from_directory(const char* model_dir, int32_t device, int32_t max_batch, int32_t max_context,
+                                               b2a_qwen3_talker** out) {
+    return guarded([&] {
+        B2A_CHECK(model_dir && out, B2A_ERR_INVALID_INPUT, "b2a_qwen3_talker_create_from_directory: null argument");
+        *out = nullptr;
+        const std::string dir = model_dir;
+        const Json j = read_json_file(dir + "/config.json");
+        B2A_CHECK(j.kind == Json::Obj, B2A_ERR_MODEL_NOT_INITIALIZED, "config.json is not an object");
+        const b2a_qwen3_talker_config cfg = qwen3_talker_config_of(j, max_batch, max_context);
+        std::unique_ptr<b2a_weights> w(new b2a_weights());
+        w->load(dir);
+        w->sanitize_qwen3_talker(parse_quant(j));
+        const std::vector<b2a_tensor> tab = w->table();
+        const int32_t st = b2a_qwen3_talker_create(device, &cfg, tab.data(), (int32_t)tab.size(), out);
         if (st != B2A_OK) throw Error(st, b2a_last_error());
     });
 }

@@ -104,6 +104,28 @@ class Qwen3TTSTalker:
         _ffi.check(_ffi.lib().b2a_qwen3_talker_create_random(device, C.byref(c), std, seed, C.byref(self._h)))
         return self
 
+    @classmethod
+    def from_model_directory(cls, model_dir, device: int = 0, max_batch: int = 8, max_context: int = 2048) -> "Qwen3TTSTalker":
+        """The talker half of Qwen3TTSModel.fromModelDirectory (Qwen3TTS.swift:1136-1175): config.json + every *.safetensors ->
+        sanitize ("talker." prefix) -> MLX affine de-quantisation as config.json's "quantization" says -> weights on the device, all
+        inside the library.  The tokenizer and <dir>/speech_tokenizer (Qwen3TTSSpeechTokenizerDecoder.from_model_directory) stay with
+        the caller."""
+        self = cls.__new__(cls)
+        c = _ffi.Qwen3TalkerConfig()
+        _ffi.check(_ffi.lib().b2a_qwen3_talker_config_from_json(str(model_dir).encode() + b"/config.json", max_batch, max_context, C.byref(c)))
+        cp = Qwen3CodePredictorConfig(vocab_size=c.cp_vocab_size, hidden_size=c.cp_hidden_size, intermediate_size=c.cp_intermediate_size,
+                                      num_hidden_layers=c.cp_num_hidden_layers, num_attention_heads=c.cp_num_attention_heads,
+                                      num_key_value_heads=c.cp_num_key_value_heads, head_dim=c.cp_head_dim, rms_norm_eps=c.cp_rms_norm_eps,
+                                      rope_theta=c.cp_rope_theta, num_code_groups=c.num_code_groups)
+        self.config = Qwen3TalkerConfig(vocab_size=c.vocab_size, hidden_size=c.hidden_size, intermediate_size=c.intermediate_size,
+                                        num_hidden_layers=c.num_hidden_layers, num_attention_heads=c.num_attention_heads,
+                                        num_key_value_heads=c.num_key_value_heads, head_dim=c.head_dim, rms_norm_eps=c.rms_norm_eps,
+                                        rope_theta=c.rope_theta, num_code_groups=c.num_code_groups, text_hidden_size=c.text_hidden_size,
+                                        text_vocab_size=c.text_vocab_size, codec_eos_token_id=c.codec_eos_token_id, code_predictor=cp)
+        self._h = C.c_void_p()
+        _ffi.check(_ffi.lib().b2a_qwen3_talker_create_from_directory(str(model_dir).encode(), device, max_batch, max_context, C.byref(self._h)))
+        return self
+
     @property
     def stream(self) -> int:
         return int(_ffi.lib().b2a_qwen3_talker_stream(self._h) or 0)

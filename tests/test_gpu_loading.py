@@ -100,3 +100,54 @@ def test_llama_from_model_directory_sharded_and_quantised(b2a, tmp_path):
     with pytest.raises(b2a.AudioGenerationError) as e:
         b2a.LlamaTTSModel.from_model_directory(d)
     assert e.value.case == "modelNotInitialized"
+
+
+def test_qwen3_talker_from_model_directory_8bit(b2a, tmp_path):
+    """An 8-bit (group 64) Qwen3-TTS-style directory: "talker."-prefixed keys, one quantised Linear and the quantised codec head,
+    config.json with talker_config / code_predictor_config -> the same logits and greedy frames as the model built from the
+    de-quantised weights."""
+    from oracle import qwen3_tts as ot
+    from test_gpu_qwen3_talker import small_cfg, bf16_weights, device_model, CHAT, TTS
+    cfg = small_cfg()
+    W = bf16_weights(cfg, 9)
+    qnames = ["model.layers.1.mlp.gate_proj", "codec_head", "code_predictor.lm_head.1"]
+    quant, Wd = {}, dict(W)
+    for qn in qnames:
+        w32 = W[qn + ".weight"].to(torch.float32).numpy()
+        words, scales, biases, q = mlx_affine_quantize(w32, 64, 8)
+        quant[qn] = (words, scales, biases)
+        Wd[qn + ".weight"] = torch.from_numpy((np.repeat(scales, 64, axis=1) * q + np.repeat(biases, 64, axis=1)).astype(np.float32)).to(torch.bfloat16).to(torch.float64)
+    ref_model = device_model(b2a, cfg, Wd, max_batch=2, max_context=64)
+    d = tmp_path / "qwen3"
+    d.mkdir()
+    cp = cfg.code_predictor
+    conf = {"model_type": "qwen3_tts", "quantization": {"group_size": 64, "bits": 8},
+            "talker_config": {"vocab_size": cfg.vocab_size, "hidden_size": cfg.hidden_size, "intermediate_size": cfg.intermediate_size,
+                              "num_hidden_layers": cfg.num_hidden_layers, "num_attention_heads": cfg.num_attention_heads,
+                              "num_key_value_heads": cfg.num_key_value_heads, "head_dim": cfg.head_dim, "num_code_groups": cfg.num_code_groups,
+                              "text_hidden_size": cfg.text_hidden_size, "text_vocab_size": cfg.text_vocab_size,
+                              "code_predictor_config": {"vocab_size": cp.vocab_size, "hidden_size": cp.hidden_size, "intermediate_size": cp.intermediate_size,
+                                                        "num_hidden_layers": cp.num_hidden_layers, "num_attention_heads": cp.num_attention_heads,
+                                                        "num_key_value_heads": cp.num_key_value_heads, "head_dim": cp.head_dim,
+                                                        "num_code_groups": cp.num_code_groups}}}
+    (d / "config.json").write_text(json.dumps(conf))
+    plain = {"talker." + k: v.to(torch.bfloat16).contiguous() for k, v in W.items() if k[:-len(".weight")] not in qnames}
+    plain["speaker_encoder.fc.weight"] = torch.ones(2, 2)
+    save_file_torch(plain, str(d / "model.safetensors"))
+    qd = {}
+    for qn, (words, scales, biases) in quant.items():
+        qd["talker." + qn + ".weight"], qd["talker." + qn + ".scales"], qd["talker." + qn + ".biases"] = words.view(np.int32), scales, biases
+    save_file(qd, str(d / "model-quant.safetensors"))
+    m = b2a.Qwen3TTSTalker.from_model_directory(d, max_batch=2, max_context=64)
+    assert m.config.hidden_size == cfg.hidden_size and m.config.code_predictor.num_hidden_layers == cp.num_hidden_layers
+    ri, rt, rp = ot.prepare_generation_inputs(cfg, Wd, CHAT, **TTS, language_id=2160)
+    x = ri.numpy().astype(np.float32)
+    (lg, hid), (rl, rh) = m(x), ref_model(x)
+    assert np.linalg.norm(lg - rl) / np.linalg.norm(rl) < 2e-5 and np.linalg.norm(hid - rh) / np.linalg.norm(rh) < 2e-5
+    P = b2a.Qwen3GenerateParameters(max_tokens=5, temperature=0.0, repetition_penalty=1.05, mask_eos=True)
+    a, _ = m.generate_codes(x, [rt[0].numpy()], rp[0, 0].numpy(), P)
+    b, _ = ref_model.generate_codes(x, [rt[0].numpy()], rp[0, 0].numpy(), P)
+    assert np.array_equal(a[0], b[0])
+    (d / "config.json").write_text("[]")
+    with pytest.raises(b2a.AudioGenerationError):
+        b2a.Qwen3TTSTalker.from_model_directory(d)

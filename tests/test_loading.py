@@ -222,3 +222,31 @@ def test_llama_config_from_json(b2a, tmp_path):
     p.write_text(json.dumps(cfg))
     with pytest.raises(b2a.AudioGenerationError):
         b2a.llama_config_from_json(p)
+
+
+def test_qwen3_talker_config_and_sanitize(b2a, tmp_path):
+    """Qwen3TTSModel.fromModelDirectory's talker half, host side: talker_config / code_predictor_config decoding with the
+    reference's defaults (Qwen3TTSConfig.swift:45-63,268-292), sanitize keeps "talker.*" without the prefix
+    (Qwen3TTSTalker.swift:356-365), 8-bit layers are expanded (Qwen3TTS.swift:1156-1171)."""
+    import ctypes as C
+    f = b2a._ffi
+    (tmp_path / "config.json").write_text(json.dumps({"model_type": "qwen3_tts", "quantization": {"group_size": 64, "bits": 8},
+                                                      "talker_config": {"hidden_size": 512, "num_hidden_layers": 3, "codec_eos_token_id": 2151,
+                                                                        "code_predictor_config": {"num_hidden_layers": 2, "vocab_size": 1024}}}))
+    c = f.Qwen3TalkerConfig()
+    f.check(f.lib().b2a_qwen3_talker_config_from_json(str(tmp_path / "config.json").encode(), 4, 300, C.byref(c)))
+    assert (c.hidden_size, c.num_hidden_layers, c.vocab_size, c.codec_eos_token_id, c.text_vocab_size) == (512, 3, 3072, 2151, 151936)
+    assert (c.cp_num_hidden_layers, c.cp_vocab_size, c.cp_hidden_size, c.num_code_groups, c.max_batch, c.max_context) == (2, 1024, 1024, 16, 4, 300)
+    assert abs(c.rope_theta - 1e6) < 1 and abs(c.rms_norm_eps - 1e-6) < 1e-12 and c.head_dim == 128
+    rng = np.random.default_rng(8)
+    wq = rng.standard_normal((16, 128)).astype(np.float32)
+    words, scales, biases, q = mlx_affine_quantize(wq, 64, 8)
+    save_file({"talker.model.layers.0.mlp.down_proj.weight": words.view(np.int32), "talker.model.layers.0.mlp.down_proj.scales": scales,
+               "talker.model.layers.0.mlp.down_proj.biases": biases, "talker.model.norm.weight": np.ones(4, np.float32),
+               "speaker_encoder.fc.weight": np.ones((2, 2), np.float32)}, str(tmp_path / "model.safetensors"))
+    w = b2a.Weights(tmp_path)
+    f.check(f.lib().b2a_weights_sanitize_qwen3_talker(w._h, str(tmp_path / "config.json").encode()))
+    t = w.tensors()
+    assert set(t) == {"model.layers.0.mlp.down_proj.weight", "model.norm.weight"}
+    ref = (np.repeat(scales, 64, axis=1) * q + np.repeat(biases, 64, axis=1)).astype(np.float32)
+    assert torch.equal(t["model.layers.0.mlp.down_proj.weight"], torch.from_numpy(ref).to(torch.bfloat16))
