@@ -1706,6 +1706,9 @@ struct b2a_tts {
         a.out_f32 = yout; a.out_bf16 = actout; a.M = M; a.N = B; a.K = K;
         a.m_tiles = cdiv(M, tc::BM); a.k_blocks = K / tc::BK;
         a.stages = 6;   // 6 x 18 KB ring: two GEMM CTAs (this kernel's and the next kernel's prefetching one) fit per SM
+        { static const int e_all = getenv("B2A_STAGES") ? atoi(getenv("B2A_STAGES")) : 0, e_gu = getenv("B2A_STAGES_GU") ? atoi(getenv("B2A_STAGES_GU")) : 0;
+          if (e_all > 0) a.stages = e_all;
+          if (op == OP_GU && e_gu > 0) a.stages = e_gu; }
         a.hilo = 1;
         int ctas = num_sms;
         if (op == OP_GU) {
@@ -1759,6 +1762,7 @@ struct b2a_tts {
     void splitk_gemm(const CUtensorMap& tmW, const CUtensorMap& tmX, int M, int K, const float* gain, float* ss, int B, cudaStream_t s) {
         tc::SplitArgs a{};
         a.M = M; a.N = B; a.K = K; a.k_blocks = K / tc::BK; a.stages = 5;
+        { static const int e_sk = getenv("B2A_STAGES_SK") ? atoi(getenv("B2A_STAGES_SK")) : 0; if (e_sk > 0) a.stages = e_sk; }
         a.h = x.p; a.gain = gain; a.xn = xn.p; a.ss = ss;
         a.rstd_ss = nullptr; a.rstd_parts = 0; a.rstd_inv_h = 0.f; a.rstd_eps = 0.f;
         tc::launch_splitk(tmW, tmX, a, cdiv(M, tc::BM), std::max(1, std::min(fused_cluster, a.k_blocks)), s);
