@@ -33,6 +33,21 @@ CUtensorMap make_tmap_bf16(const void* base, long long rows, long long cols, int
     return m;
 }
 
+// 3-D fp16 tensor [d2][d1][d0] (d0 contiguous), box {b0, b1, 1}, 128-byte swizzle (b0 * 2 bytes must be 128): attn_tc.cuh's operands
+CUtensorMap make_tmap_f16_3d(const void* base, long long d0, long long d1, long long d2, int b0, int b1) {
+    B2A_CHECK(b0 * 2 == 128 && d0 % 8 == 0 && ((uintptr_t)base & 15) == 0, B2A_ERR_INVALID_INPUT, "TMA: bad 3-D fp16 tensor");
+    CUtensorMap m;
+    const cuuint64_t dims[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+    const cuuint64_t strides[2] = {(cuuint64_t)d0 * 2, (cuuint64_t)d0 * (cuuint64_t)d1 * 2};
+    const cuuint32_t box[3] = {(cuuint32_t)b0, (cuuint32_t)b1, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B2A_CHECK(r == CUDA_SUCCESS, B2A_ERR_CUDA, "cuTensorMapEncodeTiled (3-D fp16) failed (" + std::to_string((int)r) + ")");
+    return m;
+}
+
 template <int BN>
 void launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Args& a, int ctas, int n_tiles, cudaStream_t s) {
     launch_pdl(tc_gemm_kernel<BN>, dim3(ctas, n_tiles), dim3(THREADS), Smem<BN>::bytes(a.stages), s, tmA, tmB, a);

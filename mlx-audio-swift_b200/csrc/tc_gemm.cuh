@@ -598,6 +598,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 // 2-D bf16 row-major [rows, cols] tensor map with a {64, box_rows} box and 128-byte swizzle
 CUtensorMap make_tmap_bf16(const void* base, long long rows, long long cols, int box_rows);
+CUtensorMap make_tmap_f16_3d(const void* base, long long d0, long long d1, long long d2, int b0, int b1);
 
 template <int BN>
 void launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Args& a, int ctas, int n_tiles, cudaStream_t s);

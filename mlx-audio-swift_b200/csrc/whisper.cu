@@ -12,6 +12,7 @@
 // flash-decoding kernel (bulk async K/V loads, split over keys) for the decoder's self and cross attention.
 #include "common.cuh"
 #include "tc_gemm.cuh"
+#include "attn_tc.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -545,6 +546,10 @@ struct b2a_stt {
     int enc_cap_B = 0;
     DBuf<float> pcm, feats, h1, xe, qkve, kvbuf;
     DBuf<bf16> X1, X2, xne, attne, acte, enc_out;
+    DBuf<__half> fa_q, fa_k, fa_vt;                  // attn_tc.cuh operands: [B*nh][Tp][64] x2, [B*nh][64][Tp]
+    CUtensorMap tm_faq{}, tm_fak{}, tm_fav{};
+    bool attn_tc = true;                             // B2A_WH_ATTN=simt: the fp32 CUDA-core flash kernel (kept as an independent implementation)
+    static constexpr int FA_TP = 1536;               // 1500 keys padded to whole 128-key tiles
     CUtensorMap tmx_X1{}, tmx_X2{}, tmx_xne{}, tmx_attne{}, tmx_acte{}, tmx_encout{};
     // caches
     DBuf<float> self_k, self_v, cross_k, cross_v;
@@ -817,6 +822,17 @@ struct b2a_stt {
         tmx_attne = tc::make_tmap_bf16(attne.p, 2 * T2p, D, 128);
         tmx_acte = tc::make_tmap_bf16(acte.p, 2 * T2p, c.encoder_ffn_dim, 128);
         tmx_encout = tc::make_tmap_bf16(enc_out.p, 2 * T2p, D, 128);
+        {
+            const char* e = getenv("B2A_WH_ATTN");
+            attn_tc = !(e && std::string(e) == "simt");
+            const int nh = c.encoder_attention_heads;
+            const size_t n = (size_t)B * nh * FA_TP * HD;
+            fa_q.alloc(n); fa_k.alloc(n); fa_vt.alloc(n);
+            tm_faq = tc::make_tmap_f16_3d(fa_q.p, HD, FA_TP, (long long)B * nh, 64, fa::BQ);
+            tm_fak = tc::make_tmap_f16_3d(fa_k.p, HD, FA_TP, (long long)B * nh, 64, fa::BKV);
+            tm_fav = tc::make_tmap_f16_3d(fa_vt.p, FA_TP, HD, (long long)B * nh, 64, 64);
+            B2A_CUDA(cudaFuncSetAttribute(fa::mha_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fa::FA_SMEM_BYTES));
+        }
         enc_cap_B = B;
     }
 
@@ -839,8 +855,16 @@ struct b2a_stt {
             EncLayer& L = enc[l];
             ln(L.ln1, xe.p, xne.p, T2, ENC_HALF, l == 0 ? enc_pos.p : nullptr, 1500, s);     // + positions (:150)
             gemm_big(L.qkv, tmx_xne, tc::EPI_STORE, tc::ACT_NONE, qkve.p, nullptr, T2, s);
-            mha_fwd_kernel<<<dim3(cdiv(1500, FA_T), nh, B), FA_THREADS, fa_sm, s>>>(qkve.p, attne.p, 1500, D, 1.0f / sqrtf((float)HD));
-            count_launch();
+            if (attn_tc) {
+                // tcgen05 flash attention (attn_tc.cuh): pack q | k | v as fp16 operands, then one CTA per (128-query tile, head, clip)
+                fa::pack_qkv_f16_kernel<<<dim3(FA_TP / 64, B), 256, 0, s>>>(qkve.p, fa_q.p, fa_k.p, fa_vt.p, 1500, FA_TP, nh, 1.0f / sqrtf((float)HD));
+                fa::Args fa_args{attne.p, 1500, FA_TP, nh, D, ENC_HALF};
+                fa::mha_tc_kernel<<<dim3(FA_TP / fa::BQ, nh, B), fa::FA_THREADS, fa::FA_SMEM_BYTES, s>>>(tm_faq, tm_fak, tm_fav, fa_args);
+                count_launch(2);
+            } else {
+                mha_fwd_kernel<<<dim3(cdiv(1500, FA_T), nh, B), FA_THREADS, fa_sm, s>>>(qkve.p, attne.p, 1500, D, 1.0f / sqrtf((float)HD));
+                count_launch();
+            }
             gemm_big(L.o, tmx_attne, tc::EPI_ADD, tc::ACT_NONE, xe.p, nullptr, T2, s);
             ln(L.ln2, xe.p, xne.p, T2, ENC_HALF, nullptr, 1, s);
             gemm_big(L.fc1, tmx_xne, tc::EPI_STORE_BF16, tc::ACT_GELU, nullptr, acte.p, T2, s);
