@@ -8,8 +8,8 @@
 //   Kh [B*nh][Tp][64] fp16                                                                 -> B operand (K-major: d contiguous)
 //   Vt [B*nh][64][Tp] fp16 (transposed so that keys are contiguous)                        -> B operand of  O = P V
 //   rows / keys >= T are zero padding up to Tp (a multiple of 128)
-// One CTA per (128-query tile, head, clip); 192 threads: warp 0 = TMA producer (2-stage K / V ring), warp 1 = single-thread tcgen05
-// issue + TMEM owner, warps 2-5 = softmax (thread = query row = TMEM lane).  TMEM: S = 128 fp32 columns, O = 64 (256 allocated, so two
+// One CTA per (128-query tile, head, clip); 320 threads: warp 0 = TMA producer (2-stage K / V ring), warp 1 = single-thread tcgen05
+// issue + TMEM owner, warps 2-9 = softmax (a query row = a TMEM lane is shared by two threads, 64 key columns each).  TMEM: S = 128 fp32 columns, O = 64 (256 allocated, so two
 // CTAs share an SM and one's softmax overlaps the other's MMAs).  Two passes over the keys instead of an online softmax: pass 1 only
 // takes the row maxima of S (the QK^T product is cheap on this machine), pass 2 recomputes S, writes P = exp(S - max) as the fp16 A
 // operand (K-major, 128-byte swizzle, written by hand) and accumulates O += P V in TMEM with no rescaling pass over O.
@@ -22,11 +22,11 @@ namespace b2a {
 namespace fa {
 
 constexpr int BQ = 128, BKV = 128, HDIM = 64;
-constexpr int FA_THREADS = 192;
+constexpr int FA_THREADS = 320;                   // producer warp, MMA warp, 8 softmax warps (two per TMEM lane quadrant: 64 key columns each)
 constexpr int Q_BYTES = BQ * HDIM * 2, K_BYTES = BKV * HDIM * 2, V_BYTES = HDIM * BKV * 2, P_BYTES = BQ * BKV * 2;
 constexpr int STAGE_BYTES = K_BYTES + V_BYTES, FA_STAGES = 2;
 constexpr int SMEM_DATA = Q_BYTES + P_BYTES + FA_STAGES * STAGE_BYTES;      // 112 KB
-constexpr size_t FA_SMEM_BYTES = SMEM_DATA + 256 + 768;                      // + barriers + alignment slack: 113 KB, two CTAs per SM
+constexpr size_t FA_SMEM_BYTES = SMEM_DATA + 1280 + 512;                     // + barriers / row exchange + alignment slack: 113.75 KB, two CTAs per SM
 
 struct Args {
     __nv_bfloat16* out;      // [2 * Tp_tokens, d_model] hi/lo tiles of `half` tokens (the out-projection GEMM's B operand)
@@ -73,11 +73,11 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z, bh = b * a.nh + h;
     const int n_kv = a.Tp / BKV, n_it = 2 * n_kv;
     if (warp == 0 && lane == 0) {
-        if (reinterpret_cast<uintptr_t>(smem) + FA_SMEM_BYTES - 768 > reinterpret_cast<uintptr_t>(fa_raw) + FA_SMEM_BYTES) __trap();   // alignment slack exceeded
+        if (reinterpret_cast<uintptr_t>(smem) - reinterpret_cast<uintptr_t>(fa_raw) > 512) __trap();   // alignment slack exceeded
         tc::tma_prefetch_desc(&tmQ); tc::tma_prefetch_desc(&tmK); tc::tma_prefetch_desc(&tmV);
         tc::mbar_init(qfull, 1);
         for (int i = 0; i < FA_STAGES; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
-        tc::mbar_init(sfull, 1); tc::mbar_init(sfree, 4); tc::mbar_init(pready, 4); tc::mbar_init(pfree, 1); tc::mbar_init(ofull, 1);
+        tc::mbar_init(sfull, 1); tc::mbar_init(sfree, 8); tc::mbar_init(pready, 8); tc::mbar_init(pfree, 1); tc::mbar_init(ofull, 1);
         tc::fence_barrier_init();
     }
     if (warp == 1) tc::tmem_alloc<256>(tmem_slot);
@@ -133,16 +133,22 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             }
         }
     } else {
-        const int q = warp & 3, row = q * 32 + lane;
+        const int q = warp & 3, row = q * 32 + lane, ch = (warp - 2) >> 2;      // ch: which 64-column half of every S tile / which half of O
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        float* xch = reinterpret_cast<float*>(tmem_slot + 2);                    // [2][128]: the two halves of a row exchange max / sum here
         float m = -INFINITY, l = 0.f;
         for (int i = 0; i < n_it; ++i) {
             const int j = i % n_kv, pass = i / n_kv;
+            if (i == n_kv) {                                                     // pass 1 done: combine the two half-row maxima
+                xch[ch * BQ + row] = m;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                m = fmaxf(m, xch[(ch ^ 1) * BQ + row]);
+            }
             tc::mbar_wait(sfull, (uint32_t)(i & 1));
             tc::tc_fence_after();
             if (!pass) {
 #pragma unroll 1
-                for (int c = 0; c < BKV / 32; ++c) {
+                for (int c = 2 * ch; c < 2 * ch + 2; ++c) {
                     float v[32];
                     tmem_ld32(tmem_S + lane_off + (uint32_t)(c * 32), v);
                     const int k0 = j * BKV + c * 32;
@@ -155,16 +161,17 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 continue;
             }
             if (j > 0) tc::mbar_wait(pfree, (uint32_t)((j - 1) & 1));          // the previous P V product has read the P tile
+            uint8_t* prow = sP + (size_t)ch * (P_BYTES / 2) + (size_t)row * 128; // this thread's 64 keys = one 128-byte row of panel `ch`
 #pragma unroll 1
-            for (int c = 0; c < BKV / 32; ++c) {
+            for (int c2 = 0; c2 < 2; ++c2) {
                 float v[32];
-                tmem_ld32(tmem_S + lane_off + (uint32_t)(c * 32), v);
-                if (c == BKV / 32 - 1) {                                       // S is in registers: the next Q K^T may overwrite it
+                tmem_ld32(tmem_S + lane_off + (uint32_t)((2 * ch + c2) * 32), v);
+                if (c2 == 1) {                                                  // S is in registers: the next Q K^T may overwrite it
                     tc::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(sfree);
                 }
-                const int k0 = j * BKV + c * 32;
+                const int k0 = j * BKV + (2 * ch + c2) * 32;
                 uint32_t pk[16];
 #pragma unroll
                 for (int e = 0; e < 32; e += 2) {
@@ -175,37 +182,45 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                     pk[e >> 1] = *reinterpret_cast<const uint32_t*>(&hp);
                 }
                 // K-major SWIZZLE_128B A tile: key kk of row r lives in panel kk / 64 at byte r * 128 + (((kk % 64) / 8) ^ (r & 7)) * 16 + (kk % 8) * 2
-                uint8_t* prow = sP + (size_t)((c * 32) / 64) * (P_BYTES / 2) + (size_t)row * 128;
-                const int chunk0 = ((c * 32) % 64) / 8;
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc) {
-                    uint4 val = make_uint4(pk[4 * cc], pk[4 * cc + 1], pk[4 * cc + 2], pk[4 * cc + 3]);
-                    *reinterpret_cast<uint4*>(prow + (size_t)(((chunk0 + cc) ^ (row & 7)) * 16)) = val;
+                    const uint4 val = make_uint4(pk[4 * cc], pk[4 * cc + 1], pk[4 * cc + 2], pk[4 * cc + 3]);
+                    *reinterpret_cast<uint4*>(prow + (size_t)(((4 * c2 + cc) ^ (row & 7)) * 16)) = val;
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy stores -> visible to the tensor core
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(pready);
         }
+        xch[ch * BQ + row] = l;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        l += xch[(ch ^ 1) * BQ + row];
         tc::mbar_wait(ofull, 0);
         tc::tc_fence_after();
         const int qrow = qt * BQ + row;
         const float inv = 1.0f / l;
-#pragma unroll 1
-        for (int c = 0; c < HDIM / 32; ++c) {
+        {
             float v[32];
-            tmem_ld32(tmem_O + lane_off + (uint32_t)(c * 32), v);
+            tmem_ld32(tmem_O + lane_off + (uint32_t)(ch * 32), v);
             if (qrow < a.T) {
                 const long long tok = (long long)b * a.T + qrow;
                 const long long r = (tok / a.half) * 2 * a.half + (tok % a.half);
-                __nv_bfloat16* ph = a.out + r * a.d_model + h * HDIM + c * 32;
+                __nv_bfloat16* ph = a.out + r * a.d_model + h * HDIM + ch * 32;
                 __nv_bfloat16* pl = ph + (long long)a.half * a.d_model;
 #pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    const float o = v[e] * inv;
-                    const __nv_bfloat16 hi = __float2bfloat16_rn(o);
-                    ph[e] = hi;
-                    pl[e] = __float2bfloat16_rn(o - __bfloat162float(hi));
+                for (int e = 0; e < 32; e += 8) {                               // 16-byte stores: 8 bf16 at a time
+                    uint32_t hw[4], lw[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float o0 = v[e + 2 * u] * inv, o1 = v[e + 2 * u + 1] * inv;
+                        const __nv_bfloat16 h0 = __float2bfloat16_rn(o0), h1 = __float2bfloat16_rn(o1);
+                        const __nv_bfloat162 hh = __halves2bfloat162(h0, h1);
+                        const __nv_bfloat162 ll = __halves2bfloat162(__float2bfloat16_rn(o0 - __bfloat162float(h0)), __float2bfloat16_rn(o1 - __bfloat162float(h1)));
+                        hw[u] = *reinterpret_cast<const uint32_t*>(&hh);
+                        lw[u] = *reinterpret_cast<const uint32_t*>(&ll);
+                    }
+                    *reinterpret_cast<uint4*>(ph + e) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                    *reinterpret_cast<uint4*>(pl + e) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                 }
             }
         }
@@ -218,32 +233,29 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     }
 }
 
-// qkv fp32 [B*T, 3 * d_model] (q | k | v) -> Qh (scaled), Kh, Vt.  One CTA per (clip, 64-token tile); V goes through shared memory so
-// that the transposed rows are written 128 bytes at a time.
+// qkv fp32 [B*T, 3 * d_model] (q | k | v) -> Qh (scaled), Kh, Vt.  One CTA per (64-token tile, clip, head); V goes through shared memory
+// so that the transposed rows are written 128 bytes at a time.
 __global__ void __launch_bounds__(256)
 pack_qkv_f16_kernel(const float* __restrict__ qkv, __half* __restrict__ Qh, __half* __restrict__ Kh, __half* __restrict__ Vt, int T, int Tp,
                     int nh, float scale) {
     __shared__ __half sv[64][HDIM + 2];
-    const int b = blockIdx.y, t0 = blockIdx.x * 64, dm = nh * HDIM;
-    for (int h = 0; h < nh; ++h) {
-        for (int i = threadIdx.x; i < 64 * HDIM; i += 256) {
-            const int r = i >> 6, c = i & 63, t = t0 + r;
-            float q = 0.f, k = 0.f, v = 0.f;
-            if (t < T) {
-                const float* src = qkv + ((long long)b * T + t) * 3 * dm + h * HDIM + c;
-                q = src[0] * scale; k = src[dm]; v = src[2 * dm];
-            }
-            const long long o = (((long long)b * nh + h) * Tp + t) * HDIM + c;
-            Qh[o] = __float2half_rn(q);
-            Kh[o] = __float2half_rn(k);
-            sv[r][c] = __float2half_rn(v);
+    const int b = blockIdx.y, h = blockIdx.z, t0 = blockIdx.x * 64, dm = nh * HDIM;
+    for (int i = threadIdx.x; i < 64 * HDIM; i += 256) {
+        const int r = i >> 6, c = i & 63, t = t0 + r;
+        float q = 0.f, k = 0.f, v = 0.f;
+        if (t < T) {
+            const float* src = qkv + ((long long)b * T + t) * 3 * dm + h * HDIM + c;
+            q = src[0] * scale; k = src[dm]; v = src[2 * dm];
         }
-        __syncthreads();
-        for (int i = threadIdx.x; i < 64 * HDIM; i += 256) {
-            const int c = i >> 6, r = i & 63;                   // d = c, token = t0 + r: consecutive threads -> consecutive tokens
-            Vt[(((long long)b * nh + h) * HDIM + c) * Tp + t0 + r] = sv[r][c];
-        }
-        __syncthreads();
+        const long long o = (((long long)b * nh + h) * Tp + t) * HDIM + c;
+        Qh[o] = __float2half_rn(q);
+        Kh[o] = __float2half_rn(k);
+        sv[r][c] = __float2half_rn(v);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * HDIM; i += 256) {
+        const int c = i >> 6, r = i & 63;                       // d = c, token = t0 + r: consecutive threads -> consecutive tokens
+        Vt[(((long long)b * nh + h) * HDIM + c) * Tp + t0 + r] = sv[r][c];
     }
 }
 

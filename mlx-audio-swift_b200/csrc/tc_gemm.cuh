@@ -321,7 +321,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (lane == 0) mbar_arrive(&tempty[acc]);
                 }
                 if (a.bias || a.act) {
-                    const float bv = (a.bias && m_ok) ? a.bias[m] : 0.f;
+                    // a partial K range (stream-K red.add) carries the bias only in the segment that starts the tile
+                    const float bv = (a.bias && m_ok && (whole || seg_begin == (long long)mt * a.k_blocks)) ? a.bias[m] : 0.f;
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         float t = v[j] + bv;

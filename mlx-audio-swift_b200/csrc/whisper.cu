@@ -394,7 +394,7 @@ struct PickArgs {
     const int* begin_suppress; int n_begin;
     const int* suppress; int n_suppress;
     int V, max_tokens, timestamp_begin, eot, mask_eot;
-    float temperature;           // > 0: categorical(logits / T) (WhisperModel.swift:289-290), else argmax
+    float temperature;           // > 0: categorical(logits / T) (WhisperModel.swift:289-290, Gumbel-max draw), else argmax
     unsigned long long seed;
 };
 __device__ __forceinline__ float wh_uniform01(unsigned long long seed, unsigned long long a, unsigned long long b) {
@@ -433,46 +433,45 @@ wh_pick_kernel(PickArgs a) {
     }
     if ((t & 31) == 0) { s_val[t >> 5] = best; s_idx[t >> 5] = bi; }
     __syncthreads();
-    __shared__ float s_max, s_wsum[32];
     __shared__ int s_pick;
     if (t == 0) {
         for (int i = 1; i < 32; ++i)
             if (s_val[i] > best || (s_val[i] == best && s_idx[i] < bi)) { best = s_val[i]; bi = s_idx[i]; }
-        s_max = best; s_pick = bi;
+        s_pick = bi;
     }
     __syncthreads();
     if (a.temperature > 0.f) {
-        // categorical(logits / T): inverse-CDF draw over softmax((l - max) / T).  Thread t owns the contiguous ids
-        // [t*C, (t+1)*C); an exclusive scan of the 1024 chunk sums finds the owning thread, which walks its chunk.
-        // Deterministic for a given (seed, row, step); the distribution is the reference's, the stream of draws is not
-        // (MLX draws Gumbel noise from its own generator).
-        const float mx = s_max, inv_t = 1.0f / a.temperature;
-        const int C = (a.V + 1023) / 1024, i0 = t * C, i1 = min(a.V, i0 + C);
-        float mine = 0.f;
-        for (int i = i0; i < i1; ++i) {
+        // categorical(logits / T) by the Gumbel-max trick: argmax_i (l_i / T - log(-log u_i)), u_i a hash of (seed, clip, step, i).
+        // Deterministic for a given seed and robust to last-bit differences in the logits (an inverse-CDF walk over 51 865 nearly
+        // flat probabilities is not: the stream-K residual GEMMs reorder fp32 sums from run to run).  The distribution is the
+        // reference's, the stream of draws is not (MLX draws its own Gumbel noise).
+        const float inv_t = 1.0f / a.temperature;
+        const unsigned long long base = a.seed + 0x9E3779B97F4A7C15ull * ((unsigned long long)b * 1000003ull + (unsigned long long)a.n_gen[b] + 1ull);
+        float gv = -INFINITY;
+        int gi = 0x7fffffff;
+        for (int i = t; i < a.V; i += 1024) {
             float v = lg[i];
             if (i >= a.timestamp_begin) v += -1e9f;
-            mine += __expf((v - mx) * inv_t);
+            unsigned long long z = base ^ ((unsigned long long)(unsigned)i * 0xD6E8FEB86659FD93ull);
+            z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+            z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+            z ^= z >> 31;
+            const float u = ((float)(z >> 40) + 0.5f) * (1.0f / 16777216.0f);
+            const float k = v * inv_t - __logf(-__logf(u));
+            if (k > gv) { gv = k; gi = i; }
         }
-        float inc = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const float n = __shfl_up_sync(0xffffffffu, inc, o); if ((t & 31) >= o) inc += n; }
-        if ((t & 31) == 31) s_wsum[t >> 5] = inc;
+        for (int o = 16; o; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, gv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, gi, o);
+            if (ov > gv || (ov == gv && oi < gi)) { gv = ov; gi = oi; }
+        }
         __syncthreads();
-        float wbase = 0.f, Z = 0.f;
-        for (int w = 0; w < 32; ++w) { if (w < (t >> 5)) wbase += s_wsum[w]; Z += s_wsum[w]; }
-        const float hi = wbase + inc, lo = hi - mine;
-        const float r = wh_uniform01(a.seed, (unsigned long long)b, (unsigned long long)a.n_gen[b]) * Z;
-        if (mine > 0.f && r >= lo && r < hi) {          // exactly one thread owns r; none (r == Z by rounding) keeps the argmax
-            float run = lo;
-            int pick = -1, last = -1;
-            for (int i = i0; i < i1 && pick < 0; ++i) {
-                float v = lg[i];
-                if (i >= a.timestamp_begin) v += -1e9f;
-                const float e = __expf((v - mx) * inv_t);
-                if (e > 0.f) { last = i; run += e; if (run > r) pick = i; }
-            }
-            s_pick = pick >= 0 ? pick : last;
+        if ((t & 31) == 0) { s_val[t >> 5] = gv; s_idx[t >> 5] = gi; }
+        __syncthreads();
+        if (t == 0) {
+            for (int i = 1; i < 32; ++i)
+                if (s_val[i] > gv || (s_val[i] == gv && s_idx[i] < gi)) { gv = s_val[i]; gi = s_idx[i]; }
+            if (gi >= 0 && gi < a.V) s_pick = gi;
         }
         __syncthreads();
     }
@@ -548,6 +547,7 @@ struct b2a_stt {
     DBuf<bf16> X1, X2, xne, attne, acte, enc_out;
     DBuf<__half> fa_q, fa_k, fa_vt;                  // attn_tc.cuh operands: [B*nh][Tp][64] x2, [B*nh][64][Tp]
     CUtensorMap tm_faq{}, tm_fak{}, tm_fav{};
+    bool split_residual_gemms = true;                // B2A_WH_SPLIT=0: whole-tile CTAs for the decoder's residual GEMMs (round 1)
     bool attn_tc = true;                             // B2A_WH_ATTN=simt: the fp32 CUDA-core flash kernel (kept as an independent implementation)
     static constexpr int FA_TP = 1536;               // 1500 keys padded to whole 128-key tiles
     CUtensorMap tmx_X1{}, tmx_X2{}, tmx_xne{}, tmx_attne{}, tmx_acte{}, tmx_encout{};
@@ -788,7 +788,15 @@ struct b2a_stt {
         a.m_tiles = cdiv(M, tc::BM); a.k_blocks = K / tc::BK; a.stages = 8; a.hilo = 1;
         a.epi_full = epi; a.epi_partial = -1; a.bias = bias; a.act = act;
         a.lo_rows = epi == tc::EPI_STORE_BF16 ? DEC_HALF : 0;
-        tc::launch<32>(tmW, tmX, a, std::min(num_sms, a.m_tiles), 1, s);
+        int ctas = std::min(num_sms, a.m_tiles);
+        if (epi == tc::EPI_ADD && act == tc::ACT_NONE && split_residual_gemms) {
+            // out-proj / cross out-proj / fc2 add into the residual stream: their (m_tile, k_block) units can be dealt to many CTAs
+            // (stream-K), partial tiles red.add straight into x.  M = 512 gives only 4 whole-tile CTAs otherwise, each streaming its
+            // K range alone (fc2: 32 k-blocks, 16 us of a 600 us step made of such kernels).
+            a.epi_partial = tc::EPI_ATOMIC;
+            ctas = (int)std::min<long long>(num_sms, (long long)a.m_tiles * a.k_blocks);
+        }
+        tc::launch<32>(tmW, tmX, a, ctas, 1, s);
     }
     void gemm_step(const Lin& L, const CUtensorMap& tmX, int epi, int act, float* of32, bf16* obf16, int B, cudaStream_t s) {
         gemm_step(L.tm, L.M, L.K, L.has_bias ? L.b.p : nullptr, tmX, epi, act, of32, obf16, B, s);
@@ -825,6 +833,8 @@ struct b2a_stt {
         {
             const char* e = getenv("B2A_WH_ATTN");
             attn_tc = !(e && std::string(e) == "simt");
+            const char* sp = getenv("B2A_WH_SPLIT");
+            split_residual_gemms = !(sp && std::string(sp) == "0");
             const int nh = c.encoder_attention_heads;
             const size_t n = (size_t)B * nh * FA_TP * HD;
             fa_q.alloc(n); fa_k.alloc(n); fa_vt.alloc(n);
@@ -857,7 +867,7 @@ struct b2a_stt {
             gemm_big(L.qkv, tmx_xne, tc::EPI_STORE, tc::ACT_NONE, qkve.p, nullptr, T2, s);
             if (attn_tc) {
                 // tcgen05 flash attention (attn_tc.cuh): pack q | k | v as fp16 operands, then one CTA per (128-query tile, head, clip)
-                fa::pack_qkv_f16_kernel<<<dim3(FA_TP / 64, B), 256, 0, s>>>(qkve.p, fa_q.p, fa_k.p, fa_vt.p, 1500, FA_TP, nh, 1.0f / sqrtf((float)HD));
+                fa::pack_qkv_f16_kernel<<<dim3(FA_TP / 64, B, nh), 256, 0, s>>>(qkve.p, fa_q.p, fa_k.p, fa_vt.p, 1500, FA_TP, nh, 1.0f / sqrtf((float)HD));
                 fa::Args fa_args{attne.p, 1500, FA_TP, nh, D, ENC_HALF};
                 fa::mha_tc_kernel<<<dim3(FA_TP / fa::BQ, nh, B), fa::FA_THREADS, fa::FA_SMEM_BYTES, s>>>(tm_faq, tm_fak, tm_fav, fa_args);
                 count_launch(2);
