@@ -43,6 +43,10 @@ int32_t b2a_tts_debug_trace(b2a_tts* h, int32_t enable, int32_t batch, float* ou
  * (phase-major), taps = n.  layout_out: [rows][taps][kpad] float32, kpad = ceil(in / 64) * 64.                              */
 int32_t b2a_speech_tokenizer_debug_layout(const float* w, int32_t out, int32_t k, int32_t in, int32_t stride, float* layout_out,
                                           int64_t capacity, int32_t* rows, int32_t* taps, int32_t* kpad);
+/* tools/diag_n1_stages.py: stage >= 0 makes later decodes keep a copy of the fp32 activation tensor after that stage (0 = transformer
+ * output before the final norm, 1 + i = upsample layer i, 10 + 4 b = decoder block b after its transposed conv, 11 + 4 b + j = after
+ * its residual unit j); out != null first copies the last kept tensor to the host (capacity in floats, length in *n).            */
+int32_t b2a_speech_tokenizer_debug_stage(b2a_speech_tokenizer* h, int32_t stage, float* out, int64_t capacity, int64_t* n);
 /* tests/test_gpu_qwen3_sampler.py: the Qwen3-TTS in-graph sampler kernel (csrc/qwen3_sampler.cu = sampleToken,
  * Qwen3TTS.swift:1003-1118) on HOST logits [B, V <= 4096]; suppress [lo, hi) except eos; seen = bitmap of the tokens generated
  * so far [B, ceil(V/32)] (nullable; updated when track != 0); tokens_out [B]; filtered_out [B, V] (nullable) = the logits handed

@@ -192,6 +192,7 @@ SIGNATURES = {
                                          C.c_int32, _P, C.c_int32, C.c_uint64, C.c_int32, _P, _P]),
     "b2a_implicit_conv_test": (C.c_int32, [_P, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                           _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int32, C.c_int32, _P, _P]),
+    "b2a_speech_tokenizer_debug_stage": (C.c_int32, [_P, C.c_int32, _P, C.c_int64, _P]),
     "b2a_speech_tokenizer_debug_layout": (C.c_int32, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int64, _P, _P, _P]),
     "b2a_encodec_create": (C.c_int32, [C.c_int32, C.POINTER(EncodecConfig), C.POINTER(Tensor), C.c_int32, C.POINTER(_P)]),
     "b2a_encodec_output_length": (C.c_int64, [_P, C.c_int32, C.c_int32]),

@@ -48,9 +48,16 @@ struct Args {
     __nv_bfloat16* hl;            // planar hi/lo output [2][B][Hout + To][Cout] or null
     int Hout;
     int f16;                      // operands (weights and planes) are fp16 hi/lo pairs instead of bf16 ones: same three products and cost, 22
-                                  // instead of 16 mantissa bits per operand (predicted error of the decoder 6e-5 instead of 3e-4); range 65504
+                                  // instead of 16 mantissa bits per operand (shipped decoder geometry, 6 frames: 2.7e-4 of the peak instead of
+                                  // 7.0e-4); values saturate at 65504
     const float* wscale;          // [M] or null: the accumulator of row m is multiplied by wscale[m] (fp16 operands: weight rows are stored
                                   // times a power of two so that their lo halves are NORMAL fp16 numbers, not subnormals)
+    int seg_kb;                   // k-blocks accumulated per TMEM accumulator before the epilogue warps drain it into registers (0 = all).
+                                  // tcgen05's fp32 accumulation truncates (rounds toward zero): every accumulating MMA shrinks the running
+                                  // sum by ~2^-25 of its value, a multiplicative bias of -1.8e-9 * K on the output (measured,
+                                  // tools/probe_n1_dec0.py: -1.2e-5 at K = 7168, three times the operand-split error, and systematic, so the
+                                  // decoder's later stages amplify it).  Segments of 4 k-blocks (K = 256) added in registers (round to
+                                  // nearest) cap the bias at -4e-7 for 7 % more decoder time (8: -9e-7, 2 %).
     const float* sa;              // SnakeBeta on the hi/lo copy: v + sb * sin^2(sa * v), sa = exp(alpha), sb = 1 / (exp(beta) + 1e-9)
     const float* sb;
 };
@@ -75,6 +82,7 @@ __host__ __device__ constexpr uint32_t make_idesc16(int n, int f16) {
 // v -> hi + lo in the operand format, stored as raw 16-bit words at idx and plane + idx
 __device__ __forceinline__ void put_hilo16(uint16_t* base, long long plane, long long idx, float v, int f16) {
     if (f16) {
+        v = fminf(fmaxf(v, -65504.f), 65504.f);      // saturate instead of producing inf (fp16 range)
         const __half hi = __float2half_rn(v);
         base[idx] = __half_as_ushort(hi);
         base[plane + idx] = __half_as_ushort(__float2half_rn(v - __half2float(hi)));
@@ -141,26 +149,30 @@ implicit_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             const uint32_t idesc_full = make_idesc16(BN, a.f16), idesc_half = make_idesc16(HALF, a.f16);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
+            const int seg = a.seg_kb > 0 ? a.seg_kb : k_blocks;
             for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
-                mbar_wait(&tempty[acc], acc_phase ^ 1);
-                tc_fence_after();
-                const uint32_t d = tmem_base + (uint32_t)(acc * BN);
-                for (int kb = 0; kb < k_blocks; ++kb) {
-                    mbar_wait(&full[stage], phase);
+                for (int kb0 = 0; kb0 < k_blocks; kb0 += seg) {          // one accumulator per segment of the contraction
+                    mbar_wait(&tempty[acc], acc_phase ^ 1);
                     tc_fence_after();
-                    const uint32_t s0 = smem_u32(smem + (size_t)stage * STAGE);
-                    const uint64_t ad = make_smem_desc(s0), a2d = make_smem_desc(s0 + A_BYTES), bd = make_smem_desc(s0 + 2 * A_BYTES);
+                    const uint32_t d = tmem_base + (uint32_t)(acc * BN);
+                    const int kend = min(k_blocks, kb0 + seg);
+                    for (int kb = kb0; kb < kend; ++kb) {
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t s0 = smem_u32(smem + (size_t)stage * STAGE);
+                        const uint64_t ad = make_smem_desc(s0), a2d = make_smem_desc(s0 + A_BYTES), bd = make_smem_desc(s0 + 2 * A_BYTES);
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint64_t off = (uint64_t)(k * UMMA_K * 2 / 16);
-                        umma_bf16(d, ad + off, bd + off, idesc_full, (kb == 0 && k == 0) ? 0u : 1u);   // Wh * [Xh; Xl]
-                        umma_bf16(d, a2d + off, bd + off, idesc_half, 1u);                            // Wl * Xh -> columns [0, 64)
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            const uint64_t off = (uint64_t)(k * UMMA_K * 2 / 16);
+                            umma_bf16(d, ad + off, bd + off, idesc_full, (kb == kb0 && k == 0) ? 0u : 1u);   // Wh * [Xh; Xl]
+                            umma_bf16(d, a2d + off, bd + off, idesc_half, 1u);                              // Wl * Xh -> columns [0, 64)
+                        }
+                        umma_commit(&empty[stage]);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
-                    umma_commit(&empty[stage]);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    umma_commit(&tfull[acc]);
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
-                umma_commit(&tfull[acc]);
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
@@ -192,20 +204,32 @@ implicit_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     xv[j] = (m_ok && tf < a.T) ? a.xo[((long long)b * To + (long long)tf * a.up + rho) * a.Cout + co] : 0.f;
                 }
             }
-            mbar_wait(&tfull[acc], acc_phase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-            float v[16], w[16];
-            tmem_ld16(taddr + c0, v);
-            tmem_ld16(taddr + c0 + HALF, w);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
+            float sum[16];
+            const int seg = a.seg_kb > 0 ? a.seg_kb : k_blocks;
+            for (int kb0 = 0; kb0 < k_blocks; kb0 += seg) {              // drain every segment's accumulator, add in registers (RN)
+                mbar_wait(&tfull[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+                float v[16], w[16];
+                tmem_ld16(taddr + c0, v);
+                tmem_ld16(taddr + c0 + HALF, w);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+                if (kb0 == 0) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) sum[j] = v[j] + w[j];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) sum[j] += v[j] + w[j];
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const int tf = t_first + j;
                 if (tf >= a.T || !m_ok) continue;
-                float val = (v[j] + w[j]) * ws + bias;
+                float val = sum[j] * ws + bias;
                 if (a.bias_twice_t0 && tf == 0) val += bias;
                 if (a.gelu) val = 0.5f * val * (1.0f + erff(val * 0.70710678118654752f));
                 val *= gm;
@@ -218,7 +242,6 @@ implicit_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     put_hilo16(reinterpret_cast<uint16_t*>(a.hl), plane, idx, hv, a.f16);
                 }
             }
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
     tc_fence_before();

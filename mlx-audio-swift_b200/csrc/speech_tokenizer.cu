@@ -343,6 +343,13 @@ final_conv_kernel(const float* __restrict__ x, const float* __restrict__ st, con
 }
 
 // ----------------------------------------------------------------------------------------------- weights
+// k-blocks per accumulation segment of the implicit convolution (ic::Args::seg_kb); B2A_ST_SEG=0 restores one accumulator per tile
+static int seg_kb_default() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("B2A_ST_SEG"); v = e ? std::max(0, atoi(e)) : 4; }
+    return v;
+}
+
 struct IW {                       // implicit-conv weight: [M][taps][cblocks * 64] as bf16 hi / lo, K-major
     DBuf<bf16> hi, lo;
     DBuf<float> bias, rscale;     // rscale[m] (fp16 operands only): 1 / the power of two row m is stored times
@@ -412,7 +419,7 @@ struct b2a_speech_tokenizer {
     cudaStream_t stream = nullptr;
     int num_sms = 148;
     int total_up = 1, D2 = 0, Mqkv = 0;
-    int use_f16 = 0;              // B2A_ST_FP16=1: fp16 hi/lo operands instead of bf16 hi/lo (ic::Args::f16)
+    int use_f16 = 1;              // fp16 hi/lo operand pairs (22 mantissa bits, saturating at 65504); B2A_ST_FP16=0: bf16 pairs (16 bits, fp32 range)
     // weights
     DBuf<float> emb;              // [nq][bins][D2] usage-normalised codebooks
     IW rvq_proj, pre_conv, in_proj, out_proj, dec0;
@@ -432,6 +439,16 @@ struct b2a_speech_tokenizer {
     DBuf<int> d_codes;
     DBuf<bf16> P0, P1;
     DBuf<float> Xh, Xc, Q, wave;
+    // diagnostics (b2a_speech_tokenizer_debug_stage): a copy of the fp32 activation tensor after stage `dbg_stage`
+    int dbg_stage = -1;
+    long long dbg_n = 0;
+    DBuf<float> dbg;
+    void dbg_tap(int stage, const float* src, long long n, cudaStream_t s) {
+        if (stage != dbg_stage) return;
+        dbg.alloc((size_t)n);
+        B2A_CUDA(cudaMemcpyAsync(dbg.p, src, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        dbg_n = n;
+    }
 
     ~b2a_speech_tokenizer() { if (stream) cudaStreamDestroy(stream); }
 
@@ -479,7 +496,7 @@ struct b2a_speech_tokenizer {
                   B2A_ERR_INVALID_INPUT, "speech tokenizer: decoder_dim / 2^blocks must be a multiple of 8 and <= 128");
         B2A_CHECK(c.max_batch >= 1 && c.max_cache_frames >= 1, B2A_ERR_INVALID_INPUT, "speech tokenizer: max_batch / max_cache_frames must be positive");
         require_device(dev);
-        { const char* e = getenv("B2A_ST_FP16"); use_f16 = (e && e[0] == '1') ? 1 : 0; }
+        { const char* e = getenv("B2A_ST_FP16"); use_f16 = (e && e[0] == '0') ? 0 : 1; }
         B2A_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         B2A_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
         B2A_CUDA(cudaFuncSetAttribute(ic::implicit_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ic::SMEM_BYTES));
@@ -651,6 +668,7 @@ struct b2a_speech_tokenizer {
         a.t_tiles = cdiv(a.T, ic::HALF);
         a.bias = W.has_bias ? W.bias.p : nullptr;
         a.f16 = use_f16;
+        a.seg_kb = seg_kb_default();
         a.wscale = use_f16 ? W.rscale.p : nullptr;
         const CUtensorMap tb = make_tmap_planes(in, W.Cin, in_frames, a.B, use_f16);
         const long long tiles = (long long)a.B * a.t_tiles * a.m_tiles;
@@ -732,6 +750,7 @@ struct b2a_speech_tokenizer {
             count_launch();
             { ic::Args a{}; a.B = B; a.T = T; a.xo = Xh.p; a.add = 1; a.gamma = Ly.sc_mlp.p; conv(Ly.down, P1.p, T, a, s); }
         }
+        dbg_tap(0, Xh.p, N * Hd, s);
         rmsnorm_planes_kernel<<<(unsigned)N, RN_THREADS, 0, s>>>(Xh.p, final_norm.p, planes(P0, B, T, Hd), N, Hd, c.rms_norm_eps, use_f16);
         count_launch();
         { ic::Args a{}; a.B = B; a.T = T; a.hl = planes(P1, B, T, L); conv(out_proj, P0.p, T, a, s); }
@@ -750,6 +769,7 @@ struct b2a_speech_tokenizer {
             { ic::Args a{}; a.B = B; a.T = (int)Tc; a.gelu = 1; a.hl = other; conv(U.pw1, cur, Tc, a, s); }
             Hcur = i + 1 < ups.size() ? 0 : st_dec0.H;
             { ic::Args a{}; a.B = B; a.T = (int)Tc; a.xo = Xc.p; a.add = 1; a.gamma = U.gamma.p; a.hl = cur; a.Hout = Hcur; conv(U.pw2, other, Tc, a, s); }
+            dbg_tap(1 + (int)i, Xc.p, (long long)B * Tc * L, s);
         }
         // 5. decoder.0 (k7 causal) with block 0's SnakeBeta fused                            (:641-656)
         carry(cur, st_dec0, B, Tc, s);
@@ -765,6 +785,7 @@ struct b2a_speech_tokenizer {
                 conv(Bk.ct, cur, 1 + Tc, a, s);
             }
             Tc *= Bk.rate;
+            dbg_tap(10 + 4 * (int)b, Xc.p, (long long)B * Tc * Bk.cout, s);
             std::swap(cur, other);
             for (int j = 0; j < 3; ++j) {
                 ResUnit& R = Bk.ru[j];
@@ -774,6 +795,7 @@ struct b2a_speech_tokenizer {
                 if (j < 2) { a.hl = cur; a.Hout = Bk.ru[j + 1].st.H; a.sa = Bk.ru[j + 1].a1.a.p; a.sb = Bk.ru[j + 1].a1.ib.p; }
                 else if (b + 1 < blocks.size()) { a.hl = cur; a.Hout = 1; a.sa = blocks[b + 1].sn.a.p; a.sb = blocks[b + 1].sn.ib.p; }
                 conv(R.c2, other, Tc, a, s);
+                dbg_tap(11 + 4 * (int)b + j, Xc.p, (long long)B * Tc * Bk.cout, s);
             }
         }
         // 7. output SnakeBeta + k7 conv to one channel + clip                                 (:693-731, :946)
@@ -885,6 +907,23 @@ int32_t b2a_speech_tokenizer_chunked_decode(b2a_speech_tokenizer* h, const int32
 
 void b2a_speech_tokenizer_destroy(b2a_speech_tokenizer* h) { delete h; }
 
+// Diagnostics: stage >= 0 makes later decodes keep a copy of the fp32 activation tensor after that stage (0 = transformer output
+// before the final norm, 1 + i = upsample layer i, 10 + 4 b = decoder block b after its transposed conv, 11 + 4 b + j = after residual
+// unit j); out != null copies the last kept tensor to the host (capacity in floats) and returns its length in *n.
+int32_t b2a_speech_tokenizer_debug_stage(b2a_speech_tokenizer* h, int32_t stage, float* out, int64_t capacity, int64_t* n) {
+    return guarded([&] {
+        B2A_CHECK(h, B2A_ERR_INVALID_INPUT, "b2a_speech_tokenizer_debug_stage: null handle");
+        B2A_CUDA(cudaSetDevice(h->device));
+        if (out) {
+            B2A_CHECK(n && h->dbg_n <= capacity, B2A_ERR_INVALID_INPUT, "b2a_speech_tokenizer_debug_stage: output buffer too small");
+            B2A_CUDA(cudaStreamSynchronize(h->stream));
+            B2A_CUDA(cudaMemcpy(out, h->dbg.p, (size_t)h->dbg_n * sizeof(float), cudaMemcpyDeviceToHost));
+            *n = h->dbg_n;
+        }
+        h->dbg_stage = stage;
+    });
+}
+
 // Host-only: the GEMM weight matrix the implicit convolution reads, from an MLX-layout [out, k, in] weight.
 // stride == 0: plain causal conv (rows = out, taps = k); stride > 0: transposed conv with k = n * stride (rows = stride * out
 // phase-major, taps = n).  layout_out receives [rows][taps][ceil(in / 64) * 64] fp32 (capacity in floats).
@@ -931,6 +970,7 @@ int32_t b2a_implicit_conv_test(const float* w, int32_t M, int32_t taps, int32_t 
         ic::Args a{};
         a.M = M; a.m_tiles = cdiv(M, tc::BM); a.taps = taps; a.cblocks = W.cblocks; a.dil = dil; a.shift0 = shift0;
         a.B = B; a.T = T; a.t_tiles = cdiv(T, ic::HALF); a.Cout = Cout; a.up = up; a.gelu = gelu; a.add = add; a.bias_twice_t0 = bias_twice_t0; a.Hout = Hout; a.f16 = fp16;
+        a.seg_kb = seg_kb_default();
         a.wscale = fp16 ? W.rscale.p : nullptr;
         if (bias) { dbias.upload(bias, Cout); a.bias = dbias.p; }
         if (gamma) { dgamma.upload(gamma, Cout); a.gamma = dgamma.p; }

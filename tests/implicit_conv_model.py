@@ -38,7 +38,7 @@ def implicit_conv(Wg, cin, X, T, *, dil=1, shift0=0, up=1, bias=None, gamma=None
             hl[:, Hout + fo, :] = hv
 
 
-OPERAND = "bf16"          # "fp16": what Args::f16 / B2A_ST_FP16=1 selects
+OPERAND = "bf16"          # "fp16": what Args::f16 selects (the decoder default; B2A_ST_FP16=0 = bf16)
 
 
 def _bf16(x):

@@ -89,7 +89,7 @@ def test_gelu_gamma_residual(b2a):
 
 
 def test_fp16_operand_pairs(b2a):
-    """Same contract with fp16 hi/lo operands (Args::f16, B2A_ST_FP16=1): 22 mantissa bits per operand instead of 16."""
+    """Same contract with fp16 hi/lo operands (Args::f16, the decoder default; B2A_ST_FP16=0 selects bf16 pairs): 22 mantissa bits per operand instead of 16."""
     rng = np.random.default_rng(9)
     w = rng.standard_normal((192, 7, 96)) / np.sqrt(7 * 96)
     x = rng.standard_normal((2, 54 + 130, 96)) * 3.0

@@ -101,7 +101,34 @@ def bench_encodec():
                       "note": "fp32 implicit-GEMM convs + persistent wavefront LSTM (T + 1 grid barriers)"}))
 
 
+def bench_speech_tokenizer():
+    """Qwen3-TTS speech-tokenizer decoder, shipped geometry, 4 rows x 16 streaming chunks of 64 code frames (bench.py's qwen3 block)."""
+    import importlib
+    import os
+    codec = importlib.import_module("mlx_audio_swift_b200.qwen3_tts_codec")
+    cfg = codec.Qwen3TTSTokenizerDecoderConfig()
+    B, frames, chunk = 4, 1024, 64
+    dec = codec.Qwen3TTSSpeechTokenizerDecoder(cfg, weights=codec.random_init_weights(cfg, 5), max_batch=B, max_cache_frames=frames + 8)
+    codes = np.random.default_rng(1).integers(0, cfg.codebook_size, (B, cfg.num_quantizers, frames)).astype(np.int32)
+
+    def run():
+        dec.reset_streaming_state()
+        for f0 in range(0, frames, chunk):
+            dec.streaming_step(codes[:, :, f0:f0 + chunk])
+
+    for _ in range(2):
+        run()
+    t0 = time.perf_counter()
+    n = 3
+    for _ in range(n):
+        run()
+    ms = (time.perf_counter() - t0) / n * 1e3                    # every streaming_step ends synchronised (waveform copied to the host)
+    print(json.dumps({"stage": "speech_tokenizer_decode", "workload": f"{B} rows x {frames} code frames in {chunk}-frame streaming chunks -> {B} x {frames * 1920 / 24000:.1f} s",
+                      "ms": ms, "x_realtime": B * frames * 1920 / 24000 / (ms * 1e-3),
+                      "operands": "fp16 pairs" if os.environ.get("B2A_ST_FP16", "1") != "0" else "bf16 pairs", "seg_kb": os.environ.get("B2A_ST_SEG", "default")}))
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["mel", "snac", "whisper", "encodec"]
     for w in which:
-        {"mel": bench_mel, "snac": bench_snac, "whisper": bench_whisper, "encodec": bench_encodec}[w]()
+        {"mel": bench_mel, "snac": bench_snac, "whisper": bench_whisper, "encodec": bench_encodec, "speech_tokenizer": bench_speech_tokenizer}[w]()

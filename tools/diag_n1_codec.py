@@ -24,7 +24,7 @@ def run(name, cfg, T, seed=1):
     up = cfg.total_upsample
     e = np.abs(y - ref) / np.abs(ref).max()
     per = [float(e[f * up:(f + 1) * up].max()) for f in range(T)]
-    print(f"fp16={os.environ.get('B2A_ST_FP16', '0')} {name:24s} T={T} max {e.max():.2e} per-frame {['%.1e' % p for p in per]}", flush=True)
+    print(f"fp16={os.environ.get('B2A_ST_FP16', '1')} {name:24s} T={T} max {e.max():.2e} per-frame {['%.1e' % p for p in per]}", flush=True)
 
 
 D = oc.TokenizerDecoderConfig
