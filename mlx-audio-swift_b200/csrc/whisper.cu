@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <type_traits>
 #include <cmath>
 #include <cstdlib>
 
@@ -215,31 +216,34 @@ mha_fwd_kernel(const float* __restrict__ qkv, bf16* __restrict__ out, int T, int
     }
 }
 
-// cross K/V: token-major projection [B*T, 2d] -> head-major caches [B][nh][T][64]   (WhisperLayers.swift:217-234)
-__global__ void kv_relayout_kernel(const float* __restrict__ kv, float* __restrict__ kc, float* __restrict__ vc, int T, int d,
+// cross K/V: token-major projection [B*T, 2d] -> head-major fp16 caches [B][nh][T][64]   (WhisperLayers.swift:217-234).  The
+// cross-attention of a decode step reads all of it (16 x 8 x 1500 x 64 x 2 tensors x 6 layers = 590 MB per step in fp32, the largest
+// single item of the step): fp16 halves that.  Same operand precision as the encoder attention (attn_tc.cuh), fp32 accumulation.
+__global__ void kv_relayout_kernel(const float* __restrict__ kv, __half* __restrict__ kc, __half* __restrict__ vc, int T, int d,
                                    int nh) {
     const long long tok = blockIdx.x;
     const int b = (int)(tok / T), t = (int)(tok - (long long)b * T);
     for (int i = threadIdx.x; i < d; i += blockDim.x) {
         const int h = i / HD, c = i - h * HD;
         const long long dst = (((long long)b * nh + h) * T + t) * HD + c;
-        kc[dst] = kv[tok * 2 * d + i];
-        vc[dst] = kv[tok * 2 * d + d + i];
+        kc[dst] = __float2half_rn(kv[tok * 2 * d + i]);
+        vc[dst] = __float2half_rn(kv[tok * 2 * d + d + i]);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Decoder attention, one query per (row, head): flash-decoding over 128-key splits, K/V fetched with one
-// cp.async.bulk each.  APPEND: self-attention -- the new key/value (from the fused q|k|v row) is written at
-// position pos[b] first.  Otherwise cross-attention over n_keys fixed keys.
+// Decoder attention, one query per (row, head): flash-decoding over key splits, K/V fetched with one
+// cp.async.bulk each.  APPEND: self-attention over the fp32 cache, 64 keys per CTA -- the new key/value (from the
+// fused q|k|v row) is written at position pos[b] first.  Otherwise cross-attention over n_keys fixed fp16 keys,
+// 128 per CTA (the same 16 KB per tensor in flight).  Two threads per key.
 // ------------------------------------------------------------------------------------------------
-constexpr int DA_CAP = 64, DA_THREADS = 128;   // 2 threads per key
+constexpr int DA_CAP = 64, DA_CAP_CROSS = 128;
 struct DecAttnArgs {
     const float* q;        // [B, ldq] fp32, head h at column q_off + h*64
     const float* kv_new;   // APPEND: [B, ldq] fp32, key at k_off + h*64, value at v_off + h*64
     const int* pos;        // [B]
-    float* kcache;         // [B][nh][max_t][64]
-    float* vcache;
+    void* kcache;          // [B][nh][max_t][64]  fp32 (APPEND) / fp16 (cross)
+    void* vcache;
     bf16* out;             // [2*DEC_HALF, d] hi/lo
     float* part_o;         // [B][nh][S][64]
     float* part_ml;        // [B][nh][S][2]
@@ -249,37 +253,59 @@ struct DecAttnArgs {
 };
 
 template <bool APPEND>
-__global__ void __launch_bounds__(DA_THREADS)
+__global__ void __launch_bounds__(APPEND ? 2 * DA_CAP : 2 * DA_CAP_CROSS)
 mha_decode_kernel(DecAttnArgs a) {
-    __shared__ __align__(16) float sK[DA_CAP * HD];
-    __shared__ __align__(16) float sV[DA_CAP * HD];
+    using CT = typename std::conditional<APPEND, float, __half>::type;
+    constexpr int CAP = APPEND ? DA_CAP : DA_CAP_CROSS, THREADS = 2 * CAP, NSL = THREADS / HD;
+    __shared__ __align__(16) CT sK[CAP * HD];
+    __shared__ __align__(16) CT sV[CAP * HD];
     __shared__ __align__(16) float sq[HD];
-    __shared__ float sc[DA_CAP];
-    __shared__ float spo[2][HD];
-    __shared__ float red[DA_THREADS / 32];
+    __shared__ float sc[CAP];
+    __shared__ float spo[NSL][HD];
+    __shared__ float red[THREADS / 32];
     __shared__ float stat[2];
     __shared__ int s_last;
     __shared__ __align__(8) uint64_t bar;
     const int h = blockIdx.x, b = blockIdx.y, s = blockIdx.z, tid = threadIdx.x;
     pdl_trigger();
+    if (!APPEND) {
+        // the cross keys / values and the split geometry do not depend on the previous kernel: start the copy before waiting for it
+        const int t0 = s * CAP, nk = min(t0 + CAP, a.n_keys) - t0;
+        if (tid == 0 && nk > 0) {
+            const CT* kc = reinterpret_cast<const CT*>(a.kcache) + (((long long)b * a.nh + h) * a.max_t) * HD;
+            const CT* vc = reinterpret_cast<const CT*>(a.vcache) + (((long long)b * a.nh + h) * a.max_t) * HD;
+            tc::mbar_init(&bar, 1);
+            tc::fence_barrier_init();
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            const uint32_t bytes = (uint32_t)nk * HD * sizeof(CT);
+            tc::mbar_arrive_expect_tx(&bar, 2 * bytes);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(tc::smem_u32(sK)), "l"(kc + (long long)t0 * HD), "r"(bytes), "r"(tc::smem_u32(&bar)) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(tc::smem_u32(sV)), "l"(vc + (long long)t0 * HD), "r"(bytes), "r"(tc::smem_u32(&bar)) : "memory");
+        }
+    }
     pdl_wait();
     const int p = a.pos[b];
-    if (p < 0) return;
+    if (p < 0) {                            // inactive row: the CTA must not retire with a bulk copy into its shared memory in flight
+        if (!APPEND && tid == 0 && min(s * CAP + CAP, a.n_keys) - s * CAP > 0) tc::mbar_wait(&bar, 0);
+        return;
+    }
     const int n_total = APPEND ? p + 1 : a.n_keys;
     if (APPEND && p >= a.max_t) return;
-    const int S_eff = (n_total + DA_CAP - 1) / DA_CAP;
+    const int S_eff = (n_total + CAP - 1) / CAP;
     if (s >= S_eff) return;
-    const int t0 = s * DA_CAP, t1 = min(t0 + DA_CAP, n_total), nk = t1 - t0;
+    const int t0 = s * CAP, t1 = min(t0 + CAP, n_total), nk = t1 - t0;
     const bool has_new = APPEND && s == S_eff - 1;
     const int n_load = has_new ? nk - 1 : nk;
-    float* kc = a.kcache + (((long long)b * a.nh + h) * a.max_t) * HD;
-    float* vc = a.vcache + (((long long)b * a.nh + h) * a.max_t) * HD;
-    if (tid == 0) {
+    CT* kc = reinterpret_cast<CT*>(a.kcache) + (((long long)b * a.nh + h) * a.max_t) * HD;
+    CT* vc = reinterpret_cast<CT*>(a.vcache) + (((long long)b * a.nh + h) * a.max_t) * HD;
+    if (APPEND && tid == 0) {
         tc::mbar_init(&bar, 1);
         tc::fence_barrier_init();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         if (n_load > 0) {
-            const uint32_t bytes = (uint32_t)n_load * HD * 4;
+            const uint32_t bytes = (uint32_t)n_load * HD * sizeof(CT);
             tc::mbar_arrive_expect_tx(&bar, 2 * bytes);
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          ::"r"(tc::smem_u32(sK)), "l"(kc + (long long)t0 * HD), "r"(bytes), "r"(tc::smem_u32(&bar)) : "memory");
@@ -291,30 +317,44 @@ mha_decode_kernel(DecAttnArgs a) {
     }
     if (tid < HD) {
         sq[tid] = a.q[(long long)b * a.ldq + a.q_off + h * HD + tid];
-        if (has_new) {
+        if (APPEND && has_new) {
             const float k = a.kv_new[(long long)b * a.ldq + a.k_off + h * HD + tid];
-            kc[(long long)p * HD + tid] = k;
-            sK[(p - t0) * HD + tid] = k;
+            reinterpret_cast<float*>(kc)[(long long)p * HD + tid] = k;
+            reinterpret_cast<float*>(sK)[(p - t0) * HD + tid] = k;
         }
-    } else if (has_new) {
+    } else if (APPEND && has_new) {
         const int dd = tid - HD;
         const float v = a.kv_new[(long long)b * a.ldq + a.v_off + h * HD + dd];
-        vc[(long long)p * HD + dd] = v;
-        sV[(p - t0) * HD + dd] = v;
+        reinterpret_cast<float*>(vc)[(long long)p * HD + dd] = v;
+        reinterpret_cast<float*>(sV)[(p - t0) * HD + dd] = v;
     }
     __syncthreads();
     tc::mbar_wait(&bar, 0);
-    // scores: 2 threads per key (32 dims each), bank-rotated float4 columns
+    // scores: 2 threads per key (32 dims each), bank-rotated 16-byte columns
     const int key = tid >> 1, part = tid & 1;
     float acc = 0.f;
     if (key < nk) {
-        const float4* kr = reinterpret_cast<const float4*>(sK + key * HD);
+        if (APPEND) {
+            const float4* kr = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(sK) + key * HD);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int d4 = part + 2 * ((j + key) & 7);
-            const float4 kf = kr[d4];
-            const float4 qf = reinterpret_cast<const float4*>(sq)[d4];
-            acc = fmaf(qf.x, kf.x, acc); acc = fmaf(qf.y, kf.y, acc); acc = fmaf(qf.z, kf.z, acc); acc = fmaf(qf.w, kf.w, acc);
+            for (int j = 0; j < 8; ++j) {
+                const int d4 = part + 2 * ((j + key) & 7);
+                const float4 kf = kr[d4];
+                const float4 qf = reinterpret_cast<const float4*>(sq)[d4];
+                acc = fmaf(qf.x, kf.x, acc); acc = fmaf(qf.y, kf.y, acc); acc = fmaf(qf.z, kf.z, acc); acc = fmaf(qf.w, kf.w, acc);
+            }
+        } else {
+            const uint4* kr = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(sK) + key * HD);   // 8 x 16 bytes per key
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int g = part + 2 * ((j + key) & 3);         // 8 dims; four consecutive keys x two parts hit the eight 16-byte groups
+                const uint4 kk = kr[g];
+                const __half2* k2 = reinterpret_cast<const __half2*>(&kk);
+                const float4 q0 = reinterpret_cast<const float4*>(sq)[2 * g], q1 = reinterpret_cast<const float4*>(sq)[2 * g + 1];
+                const float2 f0 = __half22float2(k2[0]), f1 = __half22float2(k2[1]), f2 = __half22float2(k2[2]), f3 = __half22float2(k2[3]);
+                acc = fmaf(q0.x, f0.x, acc); acc = fmaf(q0.y, f0.y, acc); acc = fmaf(q0.z, f1.x, acc); acc = fmaf(q0.w, f1.y, acc);
+                acc = fmaf(q1.x, f2.x, acc); acc = fmaf(q1.y, f2.y, acc); acc = fmaf(q1.z, f3.x, acc); acc = fmaf(q1.w, f3.y, acc);
+            }
         }
     }
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
@@ -325,7 +365,7 @@ mha_decode_kernel(DecAttnArgs a) {
     __syncthreads();
     if (tid == 0) {
         float mm = red[0];
-        for (int i = 1; i < DA_THREADS / 32; ++i) mm = fmaxf(mm, red[i]);
+        for (int i = 1; i < THREADS / 32; ++i) mm = fmaxf(mm, red[i]);
         stat[0] = mm;
     }
     __syncthreads();
@@ -337,17 +377,25 @@ mha_decode_kernel(DecAttnArgs a) {
     __syncthreads();
     if (tid == 0) {
         float sum = 0.f;
-        for (int i = 0; i < DA_THREADS / 32; ++i) sum += red[i];
+        for (int i = 0; i < THREADS / 32; ++i) sum += red[i];
         stat[1] = sum;
     }
-    // PV: thread = (key parity, dim)
+    // PV: thread = (key residue mod NSL, dim)
     const int sl = tid >> 6, dd = tid & 63;
     float o = 0.f;
-    for (int t = sl; t < nk; t += 2) o = fmaf(sc[t], sV[t * HD + dd], o);
+    for (int t = sl; t < nk; t += NSL) {
+        const float vv = APPEND ? reinterpret_cast<const float*>(sV)[t * HD + dd] : __half2float(reinterpret_cast<const __half*>(sV)[t * HD + dd]);
+        o = fmaf(sc[t], vv, o);
+    }
     spo[sl][dd] = o;
     __syncthreads();
     const long long pbase = ((long long)b * a.nh + h) * a.S + s;
-    if (tid < HD) a.part_o[pbase * HD + tid] = spo[0][tid] + spo[1][tid];
+    if (tid < HD) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < NSL; ++i) t += spo[i][tid];
+        a.part_o[pbase * HD + tid] = t;
+    }
     if (tid == 0) { a.part_ml[pbase * 2] = stat[0]; a.part_ml[pbase * 2 + 1] = stat[1]; }
     __threadfence();
     __syncthreads();
@@ -552,7 +600,8 @@ struct b2a_stt {
     static constexpr int FA_TP = 1536;               // 1500 keys padded to whole 128-key tiles
     CUtensorMap tmx_X1{}, tmx_X2{}, tmx_xne{}, tmx_attne{}, tmx_acte{}, tmx_encout{};
     // caches
-    DBuf<float> self_k, self_v, cross_k, cross_v;
+    DBuf<float> self_k, self_v;
+    DBuf<__half> cross_k, cross_v;      // fp16 (kv_relayout_kernel)
     // decoder step state
     DBuf<float> x, qkv, cq, logits, part_o, part_ml;
     DBuf<bf16> xn, attn, act;
@@ -644,7 +693,7 @@ struct b2a_stt {
         tmx_attn = tc::make_tmap_bf16(attn.p, R, D, 32);
         tmx_act = tc::make_tmap_bf16(act.p, R, c.decoder_ffn_dim, 32);
         da_splits_self = cdiv(c.max_target_positions, DA_CAP);
-        da_splits_cross = cdiv(c.max_source_positions, DA_CAP);
+        da_splits_cross = cdiv(c.max_source_positions, DA_CAP_CROSS);
         const int S = std::max(da_splits_self, da_splits_cross);
         part_o.alloc((size_t)B * nh * S * HD); part_ml.alloc((size_t)B * nh * S * 2);
         counters.alloc((size_t)B * nh);
@@ -893,13 +942,13 @@ struct b2a_stt {
     }
 
     // ---- decoder step ----------------------------------------------------------------------------------------
-    void dec_attn(bool append, const float* q, int ldq, int q_off, const float* kvn, int k_off, int v_off, float* kc, float* vc,
+    void dec_attn(bool append, const float* q, int ldq, int q_off, const float* kvn, int k_off, int v_off, void* kc, void* vc,
                   int max_t, int n_keys, int S, int B, cudaStream_t s) {
         DecAttnArgs a{q, kvn, pos.p, kc, vc, attn.p, part_o.p, part_ml.p, counters.p, ldq, q_off, k_off, v_off,
                       cfg.decoder_attention_heads, max_t, n_keys, S, d(), 1.0f / sqrtf((float)HD)};
         const dim3 grid(cfg.decoder_attention_heads, B, S);
-        if (append) launch_pdl(mha_decode_kernel<true>, grid, dim3(DA_THREADS), 0, s, a);
-        else launch_pdl(mha_decode_kernel<false>, grid, dim3(DA_THREADS), 0, s, a);
+        if (append) launch_pdl(mha_decode_kernel<true>, grid, dim3(2 * DA_CAP), 0, s, a);
+        else launch_pdl(mha_decode_kernel<false>, grid, dim3(2 * DA_CAP_CROSS), 0, s, a);
     }
 
     void run_layers(int B, cudaStream_t s) {
