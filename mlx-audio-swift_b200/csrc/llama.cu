@@ -1314,6 +1314,8 @@ struct b2a_tts {
     bool use_tc = true;
     int num_sms = 148;
     std::vector<CUtensorMap> tm_qkv, tm_o, tm_gu, tm_down;
+    std::vector<CUtensorMap> tm_gu_dec;     // gate/up with gu_tile_rows-row boxes for the decode step (tc::Args::tile_rows)
+    int gu_tile_rows = 0;
     CUtensorMap tm_lm{}, tmx_xn{}, tmx_attn{}, tmx_act{};
     // batched prefill workspace (sized for the largest B*L seen so far)
     DBuf<float> xp, yp, qkvp;
@@ -1516,6 +1518,15 @@ struct b2a_tts {
                 tm_qkv.push_back(tc::make_tmap_bf16(L.wqkv.p, NQ + 2 * NKV, H, tc::BM));
                 tm_o.push_back(tc::make_tmap_bf16(L.wo.p, H, NQ, tc::BM));
                 tm_gu.push_back(tc::make_tmap_bf16(L.wgu.p, 2 * I, H, tc::BM));
+                {   // decode step: when 128-row tiles would leave more than a quarter of the SMs idle (Qwen3-TTS: 6144 rows = 48 tiles), use
+                    // as many m-tiles as SMs (rows per tile a multiple of 8): frame 3.47 -> 3.38 ms.  Orpheus (128 tiles on 148 SMs) measured
+                    // no gain from 147 tiles of 112 rows (1.796 vs 1.812 ms per step) and keeps 128.  B2A_GU_ROWS overrides.
+                    static const int e_rows = getenv("B2A_GU_ROWS") ? atoi(getenv("B2A_GU_ROWS")) : 0;
+                    int rows = e_rows > 0 ? e_rows : (cdiv(2 * I, tc::BM) * 4 >= num_sms * 3 ? tc::BM : cdiv(cdiv(2 * I, num_sms), 8) * 8);
+                    rows = std::max(8, std::min(tc::BM, rows / 8 * 8));
+                    gu_tile_rows = rows;
+                    tm_gu_dec.push_back(tc::make_tmap_bf16(L.wgu.p, 2 * I, H, rows));
+                }
                 tm_down.push_back(tc::make_tmap_bf16(L.wdown.p, H, I, tc::BM));
             }
             if (lm_head) tm_lm = tc::make_tmap_bf16(lm_head, c.vocab_size, H, tc::BM);
@@ -1713,6 +1724,7 @@ struct b2a_tts {
         int ctas = num_sms;
         if (op == OP_GU) {
             a.ldo = M / 2; a.epi_full = tc::EPI_SWIGLU; a.epi_partial = -1; a.lo_rows = LO_ROW;
+            a.tile_rows = gu_tile_rows; a.m_tiles = cdiv(M, gu_tile_rows);      // tmW is tm_gu_dec[layer]
             ctas = std::min(num_sms, a.m_tiles);
         } else if (op == OP_LM) {
             a.ldo = M; a.epi_full = tc::EPI_STORE; a.epi_partial = -1; a.lo_rows = 0;
@@ -1738,7 +1750,7 @@ struct b2a_tts {
                 else gemv_nb(op, L->wo.p, attn.p, y.p, nullptr, H, NQ, s);
                 break;
             case OP_GU:
-                if (use_tc) tc_gemm(tm_gu[layer], tmx_xn, op, nullptr, act.p, B, 2 * I, H, s, pf_of(L2_GU, layer));
+                if (use_tc) tc_gemm(tm_gu_dec[layer], tmx_xn, op, nullptr, act.p, B, 2 * I, H, s, pf_of(L2_GU, layer));
                 else gemv_nb(op, L->wgu.p, xn.p, nullptr, act.p, 2 * I, H, s);
                 break;
             case OP_DOWN:
@@ -1786,7 +1798,7 @@ struct b2a_tts {
                         spec.qk_norm ? Lw.qnorm.p : nullptr, spec.qk_norm ? Lw.knorm.p : nullptr, cfg.rms_norm_eps, 1};
             attn_launch(aa, B, s);
             splitk_gemm(tm_o[l], tmx_attn, H, NQ, Lw.ln2.p, ss_a.p, B, s);
-            tc_gemm(tm_gu[l], tmx_xn, OP_GU, nullptr, act.p, B, 2 * I, H, s, L2Prefetch{nullptr, 0}, ss_a.p);
+            tc_gemm(tm_gu_dec[l], tmx_xn, OP_GU, nullptr, act.p, B, 2 * I, H, s, L2Prefetch{nullptr, 0}, ss_a.p);
             splitk_gemm(tm_down[l], tmx_act, H, I, l + 1 < L ? layers[l + 1].ln1.p : final_ln.p, ss_b.p, B, s);
         }
     }

@@ -36,6 +36,10 @@ struct Args {
                              // j + BN/2 of the accumulator are summed, giving fp32-activation accuracy for free
     const float* bias;       // nullable [M]: added to every output column before the activation
     int act;                 // ACT_NONE | ACT_GELU (exact erf GELU, WhisperLayers.swift:101)
+    int tile_rows;           // whole-tile mode (epi_partial < 0) only: weight rows per m-tile when != 0 (a multiple of 8, <= 128; tmA's box must
+                             // have this many rows).  16384 gate/up rows are 128 tiles of 128 -- 20 of the 148 SMs idle and every CTA streams
+                             // 128 rows; 147 tiles of 112 rows use all SMs with 12.5 % fewer bytes per CTA.  The MMA still multiplies 128
+                             // shared-memory rows; rows past tile_rows are stale and their accumulator rows are never stored.
     const void* pf_ptr;      // optional L2 prefetch of a later GEMM's weights (issued by the epilogue warps at kernel start)
     long long pf_bytes;
     const float* rstd_ss;    // nullable [rstd_parts, 8]: the X rows are UN-normalised (h * gain); every accumulator column t is
@@ -158,6 +162,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.y * BN;
+    const int TR = a.tile_rows > 0 ? a.tile_rows : BM;                  // weight rows per m-tile
+    const uint32_t stage_tx = (uint32_t)(TR * BK * 2 + S::B_BYTES);     // bytes the two TMA loads of a stage deliver
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: let the next kernel's prologue start
 
     if (warp == 0 && lane == 0) {
@@ -192,8 +198,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int i = 0; i < npre; ++i) {
                 const long long u = u0 + i;
                 const int mt = (int)(u / a.k_blocks), kb = (int)(u - (long long)mt * a.k_blocks);
-                mbar_arrive_expect_tx(&full[i], S::STAGE);
-                tma_load_2d(smem + (size_t)i * S::STAGE, &tmA, &full[i], kb * BK, mt * BM);
+                mbar_arrive_expect_tx(&full[i], stage_tx);
+                tma_load_2d(smem + (size_t)i * S::STAGE, &tmA, &full[i], kb * BK, mt * TR);
             }
             asm volatile("griddepcontrol.wait;" ::: "memory");
             for (int i = 0; i < npre; ++i) {
@@ -207,8 +213,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int mt = (int)(u / a.k_blocks), kb = (int)(u - (long long)mt * a.k_blocks);
                 mbar_wait(&empty[stage], phase ^ 1);
                 uint8_t* sa = smem + (size_t)stage * S::STAGE;
-                mbar_arrive_expect_tx(&full[stage], S::STAGE);
-                tma_load_2d(sa, &tmA, &full[stage], kb * BK, mt * BM);
+                mbar_arrive_expect_tx(&full[stage], stage_tx);
+                tma_load_2d(sa, &tmA, &full[stage], kb * BK, mt * TR);
                 tma_load_2d(sa + S::A_BYTES, &tmB, &full[stage], kb * BK, n0);
                 if (++stage == a.stages) { stage = 0; phase ^= 1; }
             }
@@ -285,13 +291,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int epi = whole ? a.epi_full : a.epi_partial;
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
-            const int m = mt * BM + q * 32 + lane;
+            const int m = mt * TR + q * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
             constexpr int HALF = BN / 2;
             constexpr int CH = (BN == 16) ? 8 : 16;            // token columns handled per iteration
             const int n_cols = a.hilo ? HALF : BN;              // hilo: column j of the hi half pairs with j + HALF
             const int ntok0 = a.hilo ? (int)blockIdx.y * HALF : n0;
-            const bool m_ok = m < a.M;
+            const bool m_ok = m < a.M && q * 32 + lane < TR;
             const int cstep = (BN == 16 && !a.hilo) ? 16 : CH;
             for (int c0 = 0; c0 < n_cols; c0 += cstep) {
                 float v[16];
