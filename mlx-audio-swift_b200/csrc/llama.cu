@@ -1314,6 +1314,12 @@ struct b2a_tts {
     bool use_tc = true;
     int num_sms = 148;
     std::vector<CUtensorMap> tm_qkv, tm_o, tm_gu, tm_down;
+    // weight rows per m-tile for a whole-tile GEMM of M rows (tc::Args::tile_rows): 128 unless that leaves > 1/4 of the SMs idle
+    static int pick_tile_rows(int M, int sms) {
+        if (cdiv(M, tc::BM) * 4 >= sms * 3) return tc::BM;
+        return std::max(8, std::min(tc::BM, cdiv(cdiv(M, sms), 8) * 8));
+    }
+    int lm_tile_rows = 128, head_rows_now = 0;   // head_rows_now: tile rows of the map passed to the current OP_LM launch (0 = lm_tile_rows)
     std::vector<CUtensorMap> tm_gu_dec;     // gate/up with gu_tile_rows-row boxes for the decode step (tc::Args::tile_rows)
     int gu_tile_rows = 0;
     CUtensorMap tm_lm{}, tmx_xn{}, tmx_attn{}, tmx_act{};
@@ -1529,7 +1535,8 @@ struct b2a_tts {
                 }
                 tm_down.push_back(tc::make_tmap_bf16(L.wdown.p, H, I, tc::BM));
             }
-            if (lm_head) tm_lm = tc::make_tmap_bf16(lm_head, c.vocab_size, H, tc::BM);
+            lm_tile_rows = pick_tile_rows(c.vocab_size, num_sms);
+            if (lm_head) tm_lm = tc::make_tmap_bf16(lm_head, c.vocab_size, H, lm_tile_rows);
             tmx_xn = tc::make_tmap_bf16(xn.p, R16, H, 16);
             tmx_attn = tc::make_tmap_bf16(attn.p, R16, NQ, 16);
             tmx_act = tc::make_tmap_bf16(act.p, R16, I, 16);
@@ -1728,6 +1735,7 @@ struct b2a_tts {
             ctas = std::min(num_sms, a.m_tiles);
         } else if (op == OP_LM) {
             a.ldo = M; a.epi_full = tc::EPI_STORE; a.epi_partial = -1; a.lo_rows = 0;
+            a.tile_rows = head_rows_now > 0 ? head_rows_now : lm_tile_rows; a.m_tiles = cdiv(M, a.tile_rows);
             ctas = std::min(num_sms, a.m_tiles);
         } else {   // qkv / o / down: stream-K, partial tiles accumulate into the zeroed fp32 output
             a.ldo = M; a.epi_full = tc::EPI_STORE; a.epi_partial = tc::EPI_ATOMIC; a.lo_rows = 0;
@@ -1857,10 +1865,12 @@ struct b2a_tts {
         gemm(OP_LM, -1, B, s);
     }
     // a head the caller owns (row N1: the code predictor's 15 lm heads): logits_out[b, :M] = W[M, H] * normed hidden
-    void run_head(const CUtensorMap& tmW, const bf16* W, int M, float* logits_out, int B, cudaStream_t s) {
+    void run_head(const CUtensorMap& tmW, const bf16* W, int M, float* logits_out, int B, cudaStream_t s, int tile_rows = 0) {
+        head_rows_now = tile_rows;              // tmW's box rows (0: this stack's own lm_tile_rows)
         if (use_tc) tc_gemm(tmW, tmx_xn, OP_LM, logits_out, nullptr, B, M, cfg.hidden_size, s, L2Prefetch{nullptr, 0},
                             (fused && !trace_on) ? ss_b.p : nullptr);
         else gemv_nb(OP_LM, W, xn.p, logits_out, nullptr, M, cfg.hidden_size, s);
+        head_rows_now = 0;
     }
     // logits are [8, V] row-major.
 
@@ -2596,6 +2606,7 @@ struct b2a_qwen3_talker {
     DBuf<float> fc1_b, fc2_b;
     std::vector<DBuf<bf16>> cp_emb, cp_head;
     std::vector<CUtensorMap> tm_cp_head;
+    int cp_head_rows = 128;
     DBuf<const bf16*> cp_emb_ptrs;
     DBuf<float> x_in, hid, px, trailing, pad, embeds, tmp_a, tmp_b;
     DBuf<int> codes, out_codes, n_frames, done, n_active, row_frame, n_trailing, ids;
@@ -2664,7 +2675,8 @@ struct b2a_qwen3_talker {
         cp_emb_ptrs.upload(ptrs.data(), ptrs.size());
         if (pred->use_tc) {
             tm_cp_head.clear();
-            for (auto& hd : cp_head) tm_cp_head.push_back(tc::make_tmap_bf16(hd.p, cfg.cp_vocab_size, Hh, tc::BM));
+            cp_head_rows = b2a_tts::pick_tile_rows(cfg.cp_vocab_size, pred->num_sms);
+            for (auto& hd : cp_head) tm_cp_head.push_back(tc::make_tmap_bf16(hd.p, cfg.cp_vocab_size, Hh, cp_head_rows));
         } else tm_cp_head.resize(cp_head.size());
         talker->x_ext = x_in.p; talker->normed_out = hid.p;
         pred->x_ext = px.p;
@@ -2773,7 +2785,7 @@ struct b2a_qwen3_talker {
             else launch_pdl(q3_gather_kernel, dim3(B), dim3(256), 0, s, (const bf16*)cp_emb[k - 1].p, cfg.cp_vocab_size, (const int*)codes.p, G(), k, px.p, H(), pred->pos.p, k + 1);
             pred->run_layers(B, s);
             pred->run_final_norm(B, s);
-            pred->run_head(tm_cp_head[k], cp_head[k].p, cfg.cp_vocab_size, pred->logits.p, B, s);
+            pred->run_head(tm_cp_head[k], cp_head[k].p, cfg.cp_vocab_size, pred->logits.p, B, s, cp_head_rows);
             q3s::Args a = sampler_args(p, false, k + 1);
             a.tokens = codes.p + (k + 1); a.tokens_stride = G();
             q3s::sample_kernel<<<B, q3s::THREADS, 0, s>>>(a);
