@@ -562,6 +562,8 @@ struct Lin {
     DBuf<bf16> w;
     DBuf<float> b;
     CUtensorMap tm{};
+    CUtensorMap tm_step{};    // decode-step GEMMs that own whole m-tiles: boxes of step_rows weight rows (tc::Args::tile_rows)
+    int step_rows = 0;        // 0: tm / 128-row tiles
     int M = 0, K = 0;
     bool has_bias = false;
 };
@@ -631,6 +633,14 @@ struct b2a_stt {
         B2A_CUDA(cudaMemset(L.b.p, 0, M * sizeof(float)));
         L.tm = tc::make_tmap_bf16(L.w.p, M, K, tc::BM);
     }
+    // A decode-step GEMM that cannot split K (bias / GELU epilogue) runs on M / 128 CTAs -- 12, 4 and 16 for q|k|v, the cross query and
+    // fc1 of Whisper-base.  Tiles of fewer weight rows (a multiple of 8) spread the same rows over up to one CTA per SM.
+    void make_step_map(Lin& L) {
+        static const bool off = getenv("B2A_WH_ROWS") && atoi(getenv("B2A_WH_ROWS")) == 128;
+        if (off || cdiv(L.M, tc::BM) * 4 >= num_sms * 3) return;
+        L.step_rows = std::max(8, std::min(tc::BM, cdiv(cdiv(L.M, num_sms), 8) * 8));
+        L.tm_step = tc::make_tmap_bf16(L.w.p, L.M, L.K, L.step_rows);
+    }
 
     void check_config() {
         const b2a_whisper_config& c = cfg;
@@ -669,6 +679,7 @@ struct b2a_stt {
         for (auto& L : dec) {
             make_lin(L.qkv, 3 * D, D); make_lin(L.o, D, D); make_lin(L.cq, D, D); make_lin(L.ckv, 2 * D, D); make_lin(L.co, D, D);
             make_lin(L.fc1, c.decoder_ffn_dim, D); make_lin(L.fc2, D, c.decoder_ffn_dim);
+            make_step_map(L.qkv); make_step_map(L.cq); make_step_map(L.fc1);
             mk_ln(L.ln1); mk_ln(L.ln2); mk_ln(L.ln3);
         }
         mk_ln(enc_ln); mk_ln(dec_ln);
@@ -831,10 +842,11 @@ struct b2a_stt {
     }
     // decoder step: B <= 16 rows as hi/lo in one 32-column tile, whole tiles per CTA
     void gemm_step(const CUtensorMap& tmW, int M, int K, const float* bias, const CUtensorMap& tmX, int epi, int act,
-                   float* of32, bf16* obf16, int B, cudaStream_t s) {
+                   float* of32, bf16* obf16, int B, cudaStream_t s, int tile_rows = 0) {
         tc::Args a{};
         a.out_f32 = of32; a.out_bf16 = obf16; a.M = M; a.N = B; a.K = K; a.ldo = M;
-        a.m_tiles = cdiv(M, tc::BM); a.k_blocks = K / tc::BK; a.stages = 8; a.hilo = 1;
+        a.tile_rows = tile_rows;
+        a.m_tiles = cdiv(M, tile_rows > 0 ? tile_rows : tc::BM); a.k_blocks = K / tc::BK; a.stages = 8; a.hilo = 1;
         a.epi_full = epi; a.epi_partial = -1; a.bias = bias; a.act = act;
         a.lo_rows = epi == tc::EPI_STORE_BF16 ? DEC_HALF : 0;
         int ctas = std::min(num_sms, a.m_tiles);
@@ -848,7 +860,9 @@ struct b2a_stt {
         tc::launch<32>(tmW, tmX, a, ctas, 1, s);
     }
     void gemm_step(const Lin& L, const CUtensorMap& tmX, int epi, int act, float* of32, bf16* obf16, int B, cudaStream_t s) {
-        gemm_step(L.tm, L.M, L.K, L.has_bias ? L.b.p : nullptr, tmX, epi, act, of32, obf16, B, s);
+        const bool whole = !(epi == tc::EPI_ADD && act == tc::ACT_NONE && split_residual_gemms);
+        if (whole && L.step_rows > 0) gemm_step(L.tm_step, L.M, L.K, L.has_bias ? L.b.p : nullptr, tmX, epi, act, of32, obf16, B, s, L.step_rows);
+        else gemm_step(L.tm, L.M, L.K, L.has_bias ? L.b.p : nullptr, tmX, epi, act, of32, obf16, B, s);
     }
     void ln(const LNp& l, float* xrows, bf16* out, long long rows, int half, const float* addend, int add_mod, cudaStream_t s) {
         launch_pdl(layernorm_hilo_kernel, dim3((unsigned)rows), dim3(LN_THREADS), 0, s, xrows, (const float*)l.w.p, (const float*)l.b.p, out, d(),
