@@ -1701,7 +1701,10 @@ struct b2a_tts {
             case L2_NORM1: if (l2pf_mask & 1) return L2Prefetch{L.wqkv.p, b_qkv}; break;                 // norm1 -> QKV
             case L2_ATTN:
                 if ((l2pf_mask & 2) && (l2pf_mask & 4)) return L2Prefetch{L.wo.p, b_o};                   // attn -> O (GU by the O GEMM)
-                if (l2pf_mask & 2) return L2Prefetch{L.wgu.p, b_gu};                                      // attn -> GU
+                if (l2pf_mask & 2) {                                                                      // attn -> GU (first B2A_L2PF_GU_MB MB)
+                    static const long long cap = getenv("B2A_L2PF_GU_MB") ? atoll(getenv("B2A_L2PF_GU_MB")) << 20 : (1ll << 40);
+                    return L2Prefetch{L.wgu.p, std::min(b_gu, cap)};
+                }
                 if (l2pf_mask & 4) return L2Prefetch{L.wo.p, b_o};
                 break;
             case L2_QKV: if (l2pf_mask & 8) return L2Prefetch{L.wo.p, b_o}; break;                        // QKV GEMM -> O
@@ -1800,13 +1803,13 @@ struct b2a_tts {
         const size_t kv_layer = (size_t)cfg.max_batch * nkv * cfg.max_context * HD;
         for (int l = 0; l < L; ++l) {
             LayerW& Lw = layers[l];
-            tc_gemm(tm_qkv[l], tmx_xn, OP_QKV, qkv.p, nullptr, B, NQ + 2 * NKV, H, s, L2Prefetch{nullptr, 0}, ss_b.p);
+            tc_gemm(tm_qkv[l], tmx_xn, OP_QKV, qkv.p, nullptr, B, NQ + 2 * NKV, H, s, pf_of(L2_QKV, l), ss_b.p);
             AttnArgs aa{qkv.p, pos.p, freqs.p, kcache.p + l * kv_layer, vcache.p + l * kv_layer, attn.p, part_o.p, part_ml.p,
-                        at_counters.p, nq, nkv, cfg.max_context, at_splits, 1.0f / sqrtf((float)HD), L2Prefetch{nullptr, 0},
+                        at_counters.p, nq, nkv, cfg.max_context, at_splits, 1.0f / sqrtf((float)HD), pf_of(L2_ATTN, l),
                         spec.qk_norm ? Lw.qnorm.p : nullptr, spec.qk_norm ? Lw.knorm.p : nullptr, cfg.rms_norm_eps, 1};
             attn_launch(aa, B, s);
             splitk_gemm(tm_o[l], tmx_attn, H, NQ, Lw.ln2.p, ss_a.p, B, s);
-            tc_gemm(tm_gu_dec[l], tmx_xn, OP_GU, nullptr, act.p, B, 2 * I, H, s, L2Prefetch{nullptr, 0}, ss_a.p);
+            tc_gemm(tm_gu_dec[l], tmx_xn, OP_GU, nullptr, act.p, B, 2 * I, H, s, pf_of(L2_GU, l), ss_a.p);
             splitk_gemm(tm_down[l], tmx_act, H, I, l + 1 < L ? layers[l + 1].ln1.p : final_ln.p, ss_b.p, B, s);
         }
     }

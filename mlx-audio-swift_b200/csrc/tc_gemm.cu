@@ -50,7 +50,7 @@ CUtensorMap make_tmap_f16_3d(const void* base, long long d0, long long d1, long 
 
 template <int BN>
 void launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Args& a, int ctas, int n_tiles, cudaStream_t s) {
-    launch_pdl(tc_gemm_kernel<BN>, dim3(ctas, n_tiles), dim3(THREADS), Smem<BN>::bytes(a.stages), s, tmA, tmB, a);
+    launch_pdl(tc_gemm_kernel<BN>, dim3(ctas, n_tiles), dim3(Cfg<BN>::NTHREADS), Smem<BN>::bytes(a.stages), s, tmA, tmB, a);
 }
 template void launch<16>(const CUtensorMap&, const CUtensorMap&, const Args&, int, int, cudaStream_t);
 template void launch<32>(const CUtensorMap&, const CUtensorMap&, const Args&, int, int, cudaStream_t);

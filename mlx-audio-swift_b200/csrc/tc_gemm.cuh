@@ -140,6 +140,15 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
+// Epilogue warps per CTA.  The 128-column tile (prefill / Whisper encoder: 64 tokens as hi/lo pairs) gave each of 4 epilogue warps
+// 32 rows x 128 columns to read from TMEM, add, activate and store -- ~5 us per tile against 1.1 us of MMA, so the whole kernel ran at
+// the epilogue's pace (tensor pipe 22 % active).  16 warps split the columns four ways (the same fix conv_gemm.cuh needed).
+template <int BN>
+struct Cfg {
+    static constexpr int EPI_WARPS = BN >= 128 ? 16 : 4;
+    static constexpr int NTHREADS = 64 + 32 * EPI_WARPS;
+};
+
 template <int BN>
 struct Smem {
     static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE = A_BYTES + B_BYTES;
@@ -149,7 +158,7 @@ struct Smem {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(THREADS, 2)
+__global__ void __launch_bounds__(Cfg<BN>::NTHREADS, Cfg<BN>::EPI_WARPS > 4 ? 1 : 2)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Args a) {
     using S = Smem<BN>;
     extern __shared__ uint8_t smem_raw[];
@@ -170,7 +179,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         for (int i = 0; i < a.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], Cfg<BN>::EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<S::TMEM_COLS>(tmem_slot);
@@ -253,13 +262,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else {
         if (a.pf_ptr) {
             constexpr long long CH = 8192;
-            const long long w = (long long)blockIdx.x * 128 + (threadIdx.x - 64), nw = (long long)gridDim.x * 128;
+            constexpr int NE = 32 * Cfg<BN>::EPI_WARPS;
+            const long long w = (long long)blockIdx.x * NE + (threadIdx.x - 64), nw = (long long)gridDim.x * NE;
             for (long long off = w * CH; off < a.pf_bytes; off += nw * CH) {
                 const unsigned n = (unsigned)(a.pf_bytes - off < CH ? ((a.pf_bytes - off) & ~15ll) : CH);
                 if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"((const char*)a.pf_ptr + off), "r"(n) : "memory");
             }
         }
         const int q = warp & 3;                           // TMEM lane quadrant this warp may access
+        constexpr int NCG = Cfg<BN>::EPI_WARPS / 4;       // column groups: warps 2 + 4 g .. 5 + 4 g take every NCG-th column chunk
+        const int cg = (warp - 2) >> 2;
         int acc = 0; uint32_t acc_phase = 0;
         long long u = u0;
         float rstd[8];
@@ -299,7 +311,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int ntok0 = a.hilo ? (int)blockIdx.y * HALF : n0;
             const bool m_ok = m < a.M && q * 32 + lane < TR;
             const int cstep = (BN == 16 && !a.hilo) ? 16 : CH;
-            for (int c0 = 0; c0 < n_cols; c0 += cstep) {
+            for (int c0 = cg * cstep; c0 < n_cols; c0 += cstep * NCG) {
                 float v[16];
                 if (BN == 16) {
                     tmem_ld16(taddr, v);                         // all 16 columns: [0,8) hi, [8,16) lo
@@ -321,7 +333,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
                 const int jn = (BN == 16 && !a.hilo) ? 16 : CH;
-                if (c0 + jn >= n_cols) {                         // last TMEM read of this accumulator: hand it back early
+                if (c0 + cstep * NCG >= n_cols) {                // this warp's last TMEM read of the accumulator: hand it back early
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty[acc]);
