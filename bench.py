@@ -80,7 +80,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "400"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             return
         self.thr = threading.Thread(target=self._read, daemon=True)
@@ -647,6 +647,9 @@ def main():
         "gpu_launches": int(launches),
         "stages_s": {"prefill": float(np.median([i.prefill_time for i in infos])), "decode": float(np.median([i.generate_time for i in infos])),
                      "codec": float(np.median([i.codec_time for i in infos]))},
+        # host-clock prefill + decode + codec of every timed step: a host-side stall between or inside steps shows up as an outlier here
+        # (ms_per_step is the CUDA-event time of all steps / steps and includes such stalls)
+        "steps_host_s": [float(i.prefill_time + i.generate_time + i.codec_time) for i in infos],
         "roofline": {"kernel": "decode step (CUDA graph of 144 launches: embed, norm, 28 x [qkv tcgen05 gemm (rstd in the epilogue), 2-CTA-cluster "
                                "attention, o cluster split-K gemm (+ residual + norm 2), gate/up gemm + swiglu, down cluster split-K gemm (+ residual + "
                                "next norm)], lm-head gemm, sampler); dominant kernels tc_gemm_kernel<16> / tc_gemm_splitk_kernel", "bound": "hbm",
