@@ -26,7 +26,10 @@ constexpr int FA_THREADS = 320;                   // producer warp, MMA warp, 8 
 constexpr int Q_BYTES = BQ * HDIM * 2, K_BYTES = BKV * HDIM * 2, V_BYTES = HDIM * BKV * 2, P_BYTES = BQ * BKV * 2;
 constexpr int STAGE_BYTES = K_BYTES + V_BYTES, FA_STAGES = 2;
 constexpr int SMEM_DATA = Q_BYTES + P_BYTES + FA_STAGES * STAGE_BYTES;      // 112 KB
-constexpr size_t FA_SMEM_BYTES = SMEM_DATA + 1280 + 512;                     // + barriers / row exchange + alignment slack: 113.75 KB, two CTAs per SM
+// + barriers + alignment slack = 112.75 KB.  Two CTAs per SM need 2 x (dynamic + 1 KB reserved) <= 228 KB, i.e. <= 113 KB each: the first
+// version carried its 1 KB max / sum exchange array next to the barriers (113.75 KB) and ran ONE CTA per SM (ncu: 15.6 % occupancy) --
+// the exchange now aliases the head of the P tile, which is idle at both moments it is needed.
+constexpr size_t FA_SMEM_BYTES = SMEM_DATA + 256 + 512;
 
 struct Args {
     __nv_bfloat16* out;      // [2 * Tp_tokens, d_model] hi/lo tiles of `half` tokens (the out-projection GEMM's B operand)
@@ -135,7 +138,7 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     } else {
         const int q = warp & 3, row = q * 32 + lane, ch = (warp - 2) >> 2;      // ch: which 64-column half of every S tile / which half of O
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-        float* xch = reinterpret_cast<float*>(tmem_slot + 2);                    // [2][128]: the two halves of a row exchange max / sum here
+        float* xch = reinterpret_cast<float*>(sP);                               // [2][128]: the two halves of a row exchange max / sum here (P tile idle)
         float m = -INFINITY, l = 0.f;
         for (int i = 0; i < n_it; ++i) {
             const int j = i % n_kv, pass = i / n_kv;
@@ -143,6 +146,7 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 xch[ch * BQ + row] = m;
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 m = fmaxf(m, xch[(ch ^ 1) * BQ + row]);
+                asm volatile("bar.sync 1, 256;" ::: "memory");                   // nobody writes P over the exchange before everybody has read it
             }
             tc::mbar_wait(sfull, (uint32_t)(i & 1));
             tc::tc_fence_after();
@@ -192,11 +196,11 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(pready);
         }
+        tc::mbar_wait(ofull, 0);                                                 // every P V product has completed: the P tile is free
+        tc::tc_fence_after();
         xch[ch * BQ + row] = l;
         asm volatile("bar.sync 1, 256;" ::: "memory");
         l += xch[(ch ^ 1) * BQ + row];
-        tc::mbar_wait(ofull, 0);
-        tc::tc_fence_after();
         const int qrow = qt * BQ + row;
         const float inv = 1.0f / l;
         {

@@ -905,6 +905,7 @@ struct b2a_stt {
             tm_fak = tc::make_tmap_f16_3d(fa_k.p, HD, FA_TP, (long long)B * nh, 64, fa::BKV);
             tm_fav = tc::make_tmap_f16_3d(fa_vt.p, FA_TP, HD, (long long)B * nh, 64, 64);
             B2A_CUDA(cudaFuncSetAttribute(fa::mha_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fa::FA_SMEM_BYTES));
+            B2A_CUDA(cudaFuncSetAttribute(fa::mha_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));   // two CTAs per SM
         }
         enc_cap_B = B;
     }
