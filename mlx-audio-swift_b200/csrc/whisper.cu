@@ -96,6 +96,67 @@ layernorm_hilo_kernel(float* __restrict__ x, const float* __restrict__ w, const 
     }
 }
 
+// Same LayerNorm for many rows (the encoder: 24000 rows of 512): one WARP per row, 8 rows per CTA, float4 loads and 8-byte hi / lo
+// stores, no shared memory.  The one-CTA-per-row kernel above moved 98 MB in 75 us (1.3 TB/s); d <= 1024 and d % 128 == 0.
+constexpr int LNW_ROWS = 8, LNW_MAXV = 8;            // float4 per lane
+__global__ void __launch_bounds__(LNW_ROWS * 32)
+layernorm_hilo_rows_kernel(float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, bf16* __restrict__ out,
+                           long long rows, int d, int half, const float* __restrict__ addend, int add_mod) {
+    pdl_trigger();
+    pdl_wait();
+    const long long row = (long long)blockIdx.x * LNW_ROWS + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31, nv = d / 128;           // float4 per lane: element index (lane + 32 j) * 4
+    if (row >= rows) return;
+    float4* xr = reinterpret_cast<float4*>(x + row * d);
+    float4 v[LNW_MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < LNW_MAXV; ++j) {
+        if (j < nv) {
+            float4 t = xr[lane + 32 * j];
+            if (addend) {
+                const float4 ad = reinterpret_cast<const float4*>(addend + (row % add_mod) * d)[lane + 32 * j];
+                t.x += ad.x; t.y += ad.y; t.z += ad.z; t.w += ad.w;
+                xr[lane + 32 * j] = t;
+            }
+            v[j] = t;
+            s += (t.x + t.y) + (t.z + t.w);
+        }
+    }
+    s = wsum(s);
+    const float mean = s / (float)d;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < LNW_MAXV; ++j) {
+        if (j < nv) {
+            const float c0 = v[j].x - mean, c1 = v[j].y - mean, c2 = v[j].z - mean, c3 = v[j].w - mean;
+            q += (c0 * c0 + c1 * c1) + (c2 * c2 + c3 * c3);
+        }
+    }
+    q = wsum(q);
+    const float r = rsqrtf(q / (float)d + 1e-5f);
+    const long long orow = (row / half) * 2 * half + (row % half);
+    uint2* oh = reinterpret_cast<uint2*>(out + orow * d);
+    uint2* ol = reinterpret_cast<uint2*>(out + (orow + half) * d);
+#pragma unroll
+    for (int j = 0; j < LNW_MAXV; ++j) {
+        if (j < nv) {
+            const float4 g = reinterpret_cast<const float4*>(w)[lane + 32 * j], bb = reinterpret_cast<const float4*>(b)[lane + 32 * j];
+            const float y[4] = {(v[j].x - mean) * r * g.x + bb.x, (v[j].y - mean) * r * g.y + bb.y, (v[j].z - mean) * r * g.z + bb.z,
+                                (v[j].w - mean) * r * g.w + bb.w};
+            unsigned short hs[4], ls[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const bf16 hi = __float2bfloat16_rn(y[e]);
+                hs[e] = __bfloat16_as_ushort(hi);
+                ls[e] = __bfloat16_as_ushort(__float2bfloat16_rn(y[e] - __bfloat162float(hi)));
+            }
+            oh[lane + 32 * j] = make_uint2((unsigned)hs[0] | ((unsigned)hs[1] << 16), (unsigned)hs[2] | ((unsigned)hs[3] << 16));
+            ol[lane + 32 * j] = make_uint2((unsigned)ls[0] | ((unsigned)ls[1] << 16), (unsigned)ls[2] | ((unsigned)ls[3] << 16));
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Conv stem as GEMMs: im2col writes [x[t*stride-1] | x[t*stride] | x[t*stride+1]] (zero padded) as hi/lo rows.
 // in: [B, Tin, C] fp32 (NLC).  out: [2 * Tp, Kp] bf16, Kp >= 3C (extra columns zero).
@@ -865,6 +926,11 @@ struct b2a_stt {
         else gemm_step(L.tm, L.M, L.K, L.has_bias ? L.b.p : nullptr, tmX, epi, act, of32, obf16, B, s);
     }
     void ln(const LNp& l, float* xrows, bf16* out, long long rows, int half, const float* addend, int add_mod, cudaStream_t s) {
+        if (rows >= 1024 && d() % 128 == 0 && d() <= 128 * LNW_MAXV) {
+            launch_pdl(layernorm_hilo_rows_kernel, dim3((unsigned)cdiv(rows, (long long)LNW_ROWS)), dim3(LNW_ROWS * 32), 0, s, xrows, (const float*)l.w.p,
+                       (const float*)l.b.p, out, rows, d(), half, addend, add_mod);
+            return;
+        }
         launch_pdl(layernorm_hilo_kernel, dim3((unsigned)rows), dim3(LN_THREADS), 0, s, xrows, (const float*)l.w.p, (const float*)l.b.p, out, d(),
                    half, addend, add_mod);
     }
