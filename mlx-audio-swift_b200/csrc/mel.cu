@@ -7,7 +7,8 @@
 // Data layout in HBM: PCM float32 [B, n] (read once, coalesced, staged per CTA in shared memory),
 // log-mel float32 [B, F, n_mels] (written once by kernel 1, clamped in place by kernel 2).
 // The 400-point real DFT is done as a 20x20 Cooley-Tukey split in shared memory (two passes of
-// 20-point DFTs with a twiddle in between, exploiting conjugate symmetry of the real input);
+// 20-point DFTs with a twiddle in between, exploiting conjugate symmetry of the real input; every
+// 20-point transform is a folded real-input DFT, real_dft20: 10 FMAs per output);
 // the filterbank is applied in its sparse (contiguous-support) form.
 #include "common.cuh"
 
@@ -77,6 +78,32 @@ __device__ constexpr float S20[20] = {-0.f, -0.309017003f, -0.587785244f, -0.809
                                       -0.587785244f, -0.309017003f, -1.22464685e-16f, 0.309017003f, 0.587785244f, 0.809017003f,
                                       0.95105654f, 1.f, 0.95105654f, 0.809017003f, 0.587785244f, 0.309017003f};
 
+// Forward 20-point DFT of a REAL sequence, outputs k = 0..10, with the input folded twice (x[n] +- x[20-n], then n <-> 10-n, whose
+// cosine / sine differ by the sign (-1)^k): 10 FMAs per output instead of 40.  Fully unrolled: every twiddle is an immediate.
+//   re[k] = x0 + (-1)^k x10 + a5 cos(pi k / 2) + sum_{n=1..4} (a[n] + (-1)^k a[10-n]) cos(2 pi n k / 20),    a[n] = x[n] + x[20-n]
+//   im[k] =                   d5 S20[5k]       + sum_{n=1..4} (d[n] - (-1)^k d[10-n]) S20[n k],              d[n] = x[n] - x[20-n]
+__device__ __forceinline__ void real_dft20(const float (&x)[R], float (&re)[K1N], float (&im)[K1N]) {
+    float a[10], d[10];
+#pragma unroll
+    for (int n = 1; n < 10; ++n) { a[n] = x[n] + x[R - n]; d[n] = x[n] - x[R - n]; }
+    float ee[5], eo[5], de[5], dd[5];
+#pragma unroll
+    for (int n = 1; n < 5; ++n) { ee[n] = a[n] + a[10 - n]; eo[n] = a[n] - a[10 - n]; de[n] = d[n] - d[10 - n]; dd[n] = d[n] + d[10 - n]; }
+    const float b_even = x[0] + x[10], b_odd = x[0] - x[10];
+#pragma unroll
+    for (int k = 0; k < K1N; ++k) {
+        const bool ev = (k & 1) == 0;
+        float r = fmaf(a[5], C20[(5 * k) % R], ev ? b_even : b_odd);
+        float i = d[5] * S20[(5 * k) % R];
+#pragma unroll
+        for (int n = 1; n < 5; ++n) {
+            r = fmaf(ev ? ee[n] : eo[n], C20[(n * k) % R], r);
+            i = fmaf(ev ? de[n] : dd[n], S20[(n * k) % R], i);
+        }
+        re[k] = r; im[k] = i;
+    }
+}
+
 struct MelTables {          // device pointers, owned by MelCore
     const float* window;    // [400]
     const float2* tw20;     // [20]  exp(-2*pi*i*j/20)
@@ -102,8 +129,8 @@ mel_log_kernel(const float* __restrict__ pcm, long long pcm_stride, long long n_
                float* __restrict__ max_buf) {
     __shared__ float s_x[(FR - 1) * 160 + NFFT + 8 + (FR - 1) * 96];  // sized for hop <= 256
     __shared__ float s_win[NFFT];
-    __shared__ float2 s_tw400[NFFT];
-    __shared__ float2 s_y[FR][K1N][R];
+    __shared__ float2 s_tw[K1N][R];                 // tw400[n2 * k1] as [k1][n2]: the 20 threads of a frame read consecutive entries
+    __shared__ float2 s_y[FR][K1N][R + 1];          // + 1: the rows k1 of pass 2's readers fall into different banks
     __shared__ float s_p[FR][NBINS + 3];
     __shared__ float s_red[MEL_THREADS / 32];
 
@@ -113,7 +140,8 @@ mel_log_kernel(const float* __restrict__ pcm, long long pcm_stride, long long n_
     const int tid = threadIdx.x;
     const float* sig = pcm + (long long)b * pcm_stride;
 
-    for (int i = tid; i < NFFT; i += MEL_THREADS) { s_win[i] = tb.window[i]; s_tw400[i] = tb.tw400[i]; }
+    for (int i = tid; i < NFFT; i += MEL_THREADS) s_win[i] = tb.window[i];
+    for (int i = tid; i < K1N * R; i += MEL_THREADS) s_tw[i / R][i % R] = tb.tw400[(i % R) * (i / R)];
     const int span = (nf - 1) * hop + NFFT;
     const long long base = (long long)f0 * hop;
     for (int i = tid; i < span; i += MEL_THREADS) {
@@ -139,16 +167,12 @@ mel_log_kernel(const float* __restrict__ pcm, long long pcm_stride, long long n_
         float xr[R];
 #pragma unroll
         for (int n1 = 0; n1 < R; ++n1) xr[n1] = x[R * n1] * s_win[R * n1 + n2];
+        float re[K1N], im[K1N];
+        real_dft20(xr, re, im);
 #pragma unroll
         for (int k1 = 0; k1 < K1N; ++k1) {
-            float re = 0.f, im = 0.f;
-#pragma unroll
-            for (int n1 = 0; n1 < R; ++n1) {
-                re = fmaf(xr[n1], C20[(n1 * k1) % R], re);
-                im = fmaf(xr[n1], S20[(n1 * k1) % R], im);
-            }
-            const float2 w = s_tw400[n2 * k1];
-            s_y[f][k1][n2] = make_float2(re * w.x - im * w.y, re * w.y + im * w.x);
+            const float2 w = s_tw[k1][n2];
+            s_y[f][k1][n2] = make_float2(re[k1] * w.x - im[k1] * w.y, re[k1] * w.y + im[k1] * w.x);
         }
     }
     __syncthreads();
@@ -164,15 +188,13 @@ mel_log_kernel(const float* __restrict__ pcm, long long pcm_stride, long long n_
         float yr[R], yi[R];
 #pragma unroll
         for (int n2 = 0; n2 < R; ++n2) { const float2 v = y[n2]; yr[n2] = v.x; yi[n2] = sgn * v.y; }
+        // DFT(yr + i yi) = DFT(yr) + i DFT(yi): two real-input transforms
+        float ra[K1N], ia[K1N], rb[K1N], ib[K1N];
+        real_dft20(yr, ra, ia);
+        real_dft20(yi, rb, ib);
 #pragma unroll
         for (int kk = 0; kk < K1N; ++kk) {
-            float re = 0.f, im = 0.f;
-#pragma unroll
-            for (int n2 = 0; n2 < R; ++n2) {
-                const float c = C20[(n2 * kk) % R], sn = S20[(n2 * kk) % R];
-                re = fmaf(yr[n2], c, re); re = fmaf(-yi[n2], sn, re);
-                im = fmaf(yr[n2], sn, im); im = fmaf(yi[n2], c, im);
-            }
+            const float re = ra[kk] - ib[kk], im = ia[kk] + rb[kk];
             const int k2 = mirror ? kk - 1 : kk;
             const int k = k1 + R * k2;
             if (k2 >= 0 && k < NBINS) s_p[f][k] = re * re + im * im;
