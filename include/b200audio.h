@@ -442,6 +442,54 @@ int32_t b2a_stt_transcribe_long(b2a_stt* h, const float* pcm, int64_t n_samples,
 int32_t b2a_stt_cancel(b2a_stt* h);
 void b2a_stt_destroy(b2a_stt* h);
 
+/* ---- the streaming STT session around the model ------------------------------------------------------
+ * Sources/MLXAudioSTT/Streaming/StreamingInferenceSession.swift:589-950 (the core that drives `any STTGenerationModel` through
+ * streamingDecodeTokenIds(audio:config:confirmedTokenIds:)) and StreamingTypes.swift:36-92 (StreamingConfig, DelayPreset), at the token
+ * level: the host keeps the tokenizer, the text de-duplication of the window overlap and the AsyncStream of TranscriptionEvents; it calls
+ * feed() from feedAudio(samples:) and stop() from stop(), passing its own clock (Date().timeIntervalSinceReferenceDate).
+ *   feed : samples join the pending buffer.  A whole window (window_s) pending -> it is frozen (the buffer keeps its last
+ *          window_overlap_s), decoded once without a prefix, and its tokens become completed window n (kind 2); confirmed / provisional
+ *          tokens are cleared.  Otherwise, with >= 0.5 s pending and max(0.2, decode_interval_s) since the last pass, the whole pending
+ *          buffer is decoded with the confirmed tokens as a forced decoder prefix (kind 1) and promoteTokens runs: a provisional
+ *          position keeps its first-seen time and gains an agreement while it repeats the previous pass; the longest prefix older than
+ *          delay_ms AND agreed on by min_agreement_passes passes moves to the confirmed list.  At most one decode pass per call.
+ *   stop : what is pending is decoded as a last window; left-over provisional tokens are confirmed (kind 3).
+ * Decode passes run synchronously on the model's stream (the reference detaches a Task and drops feeds that arrive while one runs).  */
+typedef struct b2a_stt_stream_config {
+    double decode_interval_s;     /* StreamingConfig.decodeIntervalSeconds, 1.0 */
+    double window_s;              /* 8.0: the reference freezes 8 s windows */
+    double window_overlap_s;      /* encoderWindowOverlapSeconds, 1.0 */
+    int32_t delay_ms;             /* DelayPreset.delayMs: realtime 200, agent 480 (default), subtitle 2400 */
+    int32_t min_agreement_passes; /* minAgreementPasses, 2 */
+    int32_t max_tokens_per_pass;  /* maxTokensPerPass, 512 (clamped to what the decoder context leaves after the prefix) */
+    int32_t sample_rate;          /* 16000 */
+} b2a_stt_stream_config;
+
+typedef struct b2a_stt_stream_update {
+    int32_t kind;                 /* 0 nothing ran, 1 partial pass, 2 window finalised, 3 ended */
+    int32_t promoted;             /* tokens moved provisional -> confirmed by this pass */
+    int32_t completed_windows;    /* finalised windows so far (their tokens: b2a_stt_session_tokens(which = 0, window)) */
+    int32_t n_confirmed;          /* confirmed tokens of the current (pending) window */
+    int32_t n_provisional;
+    double total_audio_s;         /* StreamingStats.totalAudioSeconds */
+    double pass_encode_time;      /* of the pass this call ran (0 when none) */
+    double pass_decode_time;
+} b2a_stt_stream_update;
+
+/* A host-side decoder (the reference accepts `any STTGenerationModel`, :162): writes the continuation AFTER `prefix` for `pcm`. */
+typedef int32_t (*b2a_stt_decode_cb)(void* user, const float* pcm, int64_t n_samples, const int32_t* prefix, int32_t n_prefix,
+                                     int32_t* tokens_out, int32_t capacity, int32_t* n_tokens_out);
+
+typedef struct b2a_stt_session b2a_stt_session;
+/* params: the decode parameters of every pass (prompt / suppress lists are copied; max_tokens is replaced by max_tokens_per_pass) */
+int32_t b2a_stt_session_create(b2a_stt* model, const b2a_stt_params* params, const b2a_stt_stream_config* config, b2a_stt_session** out);
+int32_t b2a_stt_session_create_with_decoder(b2a_stt_decode_cb decode, void* user, const b2a_stt_stream_config* config, b2a_stt_session** out);
+int32_t b2a_stt_session_feed(b2a_stt_session* s, const float* pcm, int64_t n_samples, double now_s, b2a_stt_stream_update* update);
+int32_t b2a_stt_session_stop(b2a_stt_session* s, double now_s, b2a_stt_stream_update* update);
+/* which: 0 = completed window `window`, 1 = confirmed, 2 = provisional; *n_out = the list's length (written even when capacity is short) */
+int32_t b2a_stt_session_tokens(b2a_stt_session* s, int32_t which, int32_t window, int32_t* tokens_out, int32_t capacity, int32_t* n_out);
+void b2a_stt_session_destroy(b2a_stt_session* s);
+
 /* ------------------------------------------------------------------ Qwen3-TTS speech-tokenizer decoder
  * Replaces Qwen3TTSSpeechTokenizerDecoder and the decode entry points of Qwen3TTSSpeechTokenizer
  * (Sources/MLXAudioTTS/Models/Qwen3TTS/Qwen3TTSSpeechTokenizer.swift):

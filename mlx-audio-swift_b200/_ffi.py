@@ -118,6 +118,19 @@ class SttInfo(C.Structure):
 
 TOKEN_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int32, C.c_int32, C.c_int32)
 AUDIO_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int32, C.POINTER(C.c_float), C.c_int64, C.c_int32)
+STT_DECODE_CB = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.POINTER(C.c_float), C.c_int64, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32),
+                            C.c_int32, C.POINTER(C.c_int32))
+
+
+class SttStreamConfig(C.Structure):
+    _fields_ = [("decode_interval_s", C.c_double), ("window_s", C.c_double), ("window_overlap_s", C.c_double), ("delay_ms", C.c_int32),
+                ("min_agreement_passes", C.c_int32), ("max_tokens_per_pass", C.c_int32), ("sample_rate", C.c_int32)]
+
+
+class SttStreamUpdate(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("promoted", C.c_int32), ("completed_windows", C.c_int32), ("n_confirmed", C.c_int32),
+                ("n_provisional", C.c_int32), ("total_audio_s", C.c_double), ("pass_encode_time", C.c_double), ("pass_decode_time", C.c_double)]
+
 
 # name -> (restype, argtypes); every symbol include/b200audio.h and include/b200audio_internal.h declare
 _P = C.c_void_p
@@ -233,6 +246,12 @@ SIGNATURES = {
     "b2a_qwen3_talker_create_from_directory": (C.c_int32, [C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P)]),
     "b2a_qwen3_talker_cancel": (C.c_int32, [_P]),
     "b2a_qwen3_talker_destroy": (None, [_P]),
+    "b2a_stt_session_create": (C.c_int32, [_P, C.POINTER(SttParams), C.POINTER(SttStreamConfig), C.POINTER(_P)]),
+    "b2a_stt_session_create_with_decoder": (C.c_int32, [STT_DECODE_CB, _P, C.POINTER(SttStreamConfig), C.POINTER(_P)]),
+    "b2a_stt_session_feed": (C.c_int32, [_P, _P, C.c_int64, C.c_double, C.POINTER(SttStreamUpdate)]),
+    "b2a_stt_session_stop": (C.c_int32, [_P, C.c_double, C.POINTER(SttStreamUpdate)]),
+    "b2a_stt_session_tokens": (C.c_int32, [_P, C.c_int32, C.c_int32, _P, C.c_int32, C.POINTER(C.c_int32)]),
+    "b2a_stt_session_destroy": (None, [_P]),
     "b2a_stt_cancel": (C.c_int32, [_P]),
     "b2a_stt_destroy": (None, [_P]),
 }

@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <memory>
 #include <type_traits>
 #include <cmath>
 #include <cstdlib>
@@ -1290,5 +1291,187 @@ int32_t b2a_stt_cancel(b2a_stt* h) {
 }
 
 void b2a_stt_destroy(b2a_stt* h) { delete h; }
+
+// ------------------------------------------------------------------------------------------------
+// Streaming session: StreamingInferenceSession.swift:589-950 at the token level, host logic around the model's
+// transcribe pass (or a host decoder).  See include/b200audio.h for the contract; oracle/stt_streaming.py is the checker.
+// ------------------------------------------------------------------------------------------------
+}  // extern "C"
+
+struct b2a_stt_session {
+    b2a_stt* model = nullptr;
+    b2a_stt_decode_cb cb = nullptr;
+    void* user = nullptr;
+    b2a_stt_stream_config cfg{};
+    b2a_stt_params sp{};
+    std::vector<int32_t> prompt, begin_suppress, suppress;
+    long long window = 0, overlap = 0;
+    std::vector<float> pending;
+    long long total = 0;
+    bool has_last = false, active = true;
+    double last_decode = 0.0, pass_enc = 0.0, pass_dec = 0.0;
+    std::vector<std::vector<int32_t>> completed;
+    std::vector<int32_t> confirmed, provisional;
+    std::vector<double> first_seen;
+    std::vector<int> agreement;
+
+    void init(const b2a_stt_stream_config* c) {
+        cfg = b2a_stt_stream_config{1.0, 8.0, 1.0, 480, 2, 512, 16000};
+        if (c) cfg = *c;
+        B2A_CHECK(cfg.sample_rate > 0 && cfg.window_s > 0 && cfg.window_overlap_s >= 0 && cfg.decode_interval_s >= 0 && cfg.delay_ms >= 0 &&
+                      cfg.max_tokens_per_pass >= 1, B2A_ERR_INVALID_INPUT, "stt session: bad stream config");
+        window = (long long)(cfg.sample_rate * cfg.window_s);
+        B2A_CHECK(window >= 1, B2A_ERR_INVALID_INPUT, "stt session: window shorter than one sample");
+        overlap = std::max<long long>(0, std::min<long long>(llround(cfg.window_overlap_s * cfg.sample_rate), std::max<long long>(0, window - 1)));   // :578-584
+    }
+    // continuation after `prefix` for `n` samples
+    std::vector<int32_t> decode(const float* pcm, long long n, const std::vector<int32_t>& prefix) {
+        pass_enc = pass_dec = 0.0;
+        std::vector<int32_t> out((size_t)std::max(1, cfg.max_tokens_per_pass));
+        int32_t got = 0;
+        if (cb) {
+            const int32_t rc = cb(user, pcm, n, prefix.data(), (int32_t)prefix.size(), out.data(), (int32_t)out.size(), &got);
+            B2A_CHECK(rc == 0, B2A_ERR_GENERATION_FAILED, "stt session: the host decoder failed");
+        } else {
+            if (n <= 200) return {};                                              // shorter than the front end accepts: nothing to say yet
+            std::vector<int32_t> pr = prompt;
+            pr.insert(pr.end(), prefix.begin(), prefix.end());
+            if ((int)pr.size() + 1 >= model->cfg.max_target_positions) return {};   // the prefix has filled the decoder context
+            b2a_stt_params p = sp;
+            p.prompt_ids = pr.data(); p.n_prompt = (int32_t)pr.size();
+            p.begin_suppress = begin_suppress.data(); p.n_begin_suppress = (int32_t)begin_suppress.size();
+            p.suppress = suppress.data(); p.n_suppress = (int32_t)suppress.size();
+            p.max_tokens = cfg.max_tokens_per_pass;
+            b2a_stt_info info{};
+            stt_transcribe_impl(model, pcm, false, 1, n, &p, out.data(), &got, &info);
+            pass_enc = info.encode_time; pass_dec = info.decode_time;
+        }
+        out.resize((size_t)std::max(0, std::min<int32_t>(got, (int32_t)out.size())));
+        return out;
+    }
+    void finalize(const float* pcm, long long n) {                                // finalizeWindow :727-748
+        completed.push_back(decode(pcm, n, {}));
+        confirmed.clear(); provisional.clear(); first_seen.clear(); agreement.clear();
+    }
+    int promote(const std::vector<int32_t>& fresh, double now) {                  // promoteTokens :750-829
+        const double delay = cfg.delay_ms / 1000.0;
+        size_t match = 0;
+        while (match < provisional.size() && match < fresh.size() && provisional[match] == fresh[match]) ++match;
+        std::vector<double> seen(fresh.size());
+        std::vector<int> agree(fresh.size());
+        for (size_t i = 0; i < fresh.size(); ++i) {
+            if (i < match) {
+                seen[i] = i < first_seen.size() ? first_seen[i] : now;
+                agree[i] = std::max(1, (i < agreement.size() ? agreement[i] : 1) + 1);
+            } else {
+                seen[i] = now; agree[i] = 1;
+            }
+        }
+        const int need = std::max(1, cfg.min_agreement_passes);
+        size_t n_promote = 0;
+        for (size_t i = 0; i < fresh.size(); ++i) {
+            if (now - seen[i] >= delay && agree[i] >= need) n_promote = i + 1;
+            else break;
+        }
+        confirmed.insert(confirmed.end(), fresh.begin(), fresh.begin() + n_promote);
+        provisional.assign(fresh.begin() + n_promote, fresh.end());
+        first_seen.assign(seen.begin() + n_promote, seen.end());
+        agreement.assign(agree.begin() + n_promote, agree.end());
+        return (int)n_promote;
+    }
+    void fill(b2a_stt_stream_update* u, int kind, int promoted) const {
+        if (!u) return;
+        u->kind = kind; u->promoted = promoted; u->completed_windows = (int32_t)completed.size();
+        u->n_confirmed = (int32_t)confirmed.size(); u->n_provisional = (int32_t)provisional.size();
+        u->total_audio_s = (double)total / cfg.sample_rate;
+        u->pass_encode_time = kind ? pass_enc : 0.0; u->pass_decode_time = kind ? pass_dec : 0.0;
+    }
+};
+
+extern "C" {
+
+int32_t b2a_stt_session_create(b2a_stt* model, const b2a_stt_params* params, const b2a_stt_stream_config* config, b2a_stt_session** out) {
+    return guarded([&] {
+        B2A_CHECK(out, B2A_ERR_INVALID_INPUT, "b2a_stt_session_create: null out");
+        *out = nullptr;
+        B2A_CHECK(model && params && params->prompt_ids && params->n_prompt >= 1, B2A_ERR_INVALID_INPUT, "b2a_stt_session_create: model and decode parameters needed");
+        std::unique_ptr<b2a_stt_session> s(new b2a_stt_session());
+        s->init(config);
+        B2A_CHECK(s->cfg.sample_rate == 16000 && s->window <= 480000, B2A_ERR_INVALID_INPUT, "b2a_stt_session_create: Whisper needs 16 kHz and windows of at most 30 s");
+        s->model = model; s->sp = *params;
+        s->prompt.assign(params->prompt_ids, params->prompt_ids + params->n_prompt);
+        if (params->n_begin_suppress > 0) s->begin_suppress.assign(params->begin_suppress, params->begin_suppress + params->n_begin_suppress);
+        if (params->n_suppress > 0) s->suppress.assign(params->suppress, params->suppress + params->n_suppress);
+        *out = s.release();
+    });
+}
+
+int32_t b2a_stt_session_create_with_decoder(b2a_stt_decode_cb decode, void* user, const b2a_stt_stream_config* config, b2a_stt_session** out) {
+    return guarded([&] {
+        B2A_CHECK(out, B2A_ERR_INVALID_INPUT, "b2a_stt_session_create_with_decoder: null out");
+        *out = nullptr;
+        B2A_CHECK(decode, B2A_ERR_INVALID_INPUT, "b2a_stt_session_create_with_decoder: null decoder");
+        std::unique_ptr<b2a_stt_session> s(new b2a_stt_session());
+        s->init(config);
+        s->cb = decode; s->user = user;
+        *out = s.release();
+    });
+}
+
+int32_t b2a_stt_session_feed(b2a_stt_session* s, const float* pcm, int64_t n, double now, b2a_stt_stream_update* u) {
+    return guarded([&] {
+        B2A_CHECK(s && (pcm || n == 0) && n >= 0, B2A_ERR_INVALID_INPUT, "b2a_stt_session_feed: bad argument");
+        if (!s->active) { s->fill(u, 0, 0); return; }
+        s->pending.insert(s->pending.end(), pcm, pcm + n);
+        s->total += n;
+        if ((long long)s->pending.size() >= s->window) {                           // a whole window: freeze it (:600-616)
+            std::vector<float> win(s->pending.begin(), s->pending.begin() + s->window);
+            s->pending.erase(s->pending.begin(), s->pending.begin() + std::max<long long>(0, s->window - s->overlap));
+            s->has_last = true; s->last_decode = now;
+            s->finalize(win.data(), (long long)win.size());
+            s->fill(u, 2, 0);
+            return;
+        }
+        if ((long long)s->pending.size() < s->cfg.sample_rate / 2) { s->fill(u, 0, 0); return; }
+        if (s->has_last && now - s->last_decode < std::max(0.2, s->cfg.decode_interval_s)) { s->fill(u, 0, 0); return; }
+        s->has_last = true; s->last_decode = now;
+        const std::vector<int32_t> fresh = s->decode(s->pending.data(), (long long)s->pending.size(), s->confirmed);
+        const int promoted = s->promote(fresh, now);
+        s->fill(u, 1, promoted);
+    });
+}
+
+int32_t b2a_stt_session_stop(b2a_stt_session* s, double now, b2a_stt_stream_update* u) {
+    (void)now;
+    return guarded([&] {
+        B2A_CHECK(s, B2A_ERR_INVALID_INPUT, "b2a_stt_session_stop: null session");
+        if (!s->active) { s->fill(u, 0, 0); return; }
+        s->active = false;
+        s->pass_enc = s->pass_dec = 0.0;
+        if (!s->pending.empty()) s->finalize(s->pending.data(), (long long)s->pending.size());
+        s->confirmed.insert(s->confirmed.end(), s->provisional.begin(), s->provisional.end());
+        s->provisional.clear(); s->first_seen.clear(); s->agreement.clear();
+        s->pending.clear();
+        s->fill(u, 3, 0);
+    });
+}
+
+int32_t b2a_stt_session_tokens(b2a_stt_session* s, int32_t which, int32_t window, int32_t* out, int32_t cap, int32_t* n_out) {
+    return guarded([&] {
+        B2A_CHECK(s && n_out && (out || cap == 0) && cap >= 0, B2A_ERR_INVALID_INPUT, "b2a_stt_session_tokens: bad argument");
+        const std::vector<int32_t>* v = nullptr;
+        if (which == 0) {
+            B2A_CHECK(window >= 0 && window < (int32_t)s->completed.size(), B2A_ERR_INVALID_INPUT, "b2a_stt_session_tokens: no such completed window");
+            v = &s->completed[(size_t)window];
+        } else if (which == 1) v = &s->confirmed;
+        else if (which == 2) v = &s->provisional;
+        B2A_CHECK(v, B2A_ERR_INVALID_INPUT, "b2a_stt_session_tokens: which must be 0, 1 or 2");
+        *n_out = (int32_t)v->size();
+        const size_t m = std::min<size_t>(v->size(), (size_t)cap);
+        if (m) memcpy(out, v->data(), m * sizeof(int32_t));
+    });
+}
+
+void b2a_stt_session_destroy(b2a_stt_session* s) { delete s; }
 
 }  // extern "C"

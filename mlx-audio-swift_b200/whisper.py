@@ -4,6 +4,7 @@ with the host (`WhisperTokenizer`); `generate` returns token ids plus the STTOut
 from __future__ import annotations
 
 import ctypes as C
+import time
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence
 
@@ -230,3 +231,91 @@ class WhisperModel:
                 self._h = C.c_void_p()
         except Exception:
             pass
+
+
+# ------------------------------------------------------------------------------------------------ streaming session (row N3)
+@dataclass
+class StreamingConfig:
+    """StreamingConfig (StreamingTypes.swift:36-92), the fields the generic session core reads."""
+    decode_interval_seconds: float = 1.0
+    window_seconds: float = 8.0
+    encoder_window_overlap_seconds: float = 1.0
+    delay_ms: int = 480                      # DelayPreset.agent; realtime 200, subtitle 2400
+    min_agreement_passes: int = 2
+    max_tokens_per_pass: int = 512
+    sample_rate: int = 16000
+
+    def _c(self) -> "_ffi.SttStreamConfig":
+        return _ffi.SttStreamConfig(self.decode_interval_seconds, self.window_seconds, self.encoder_window_overlap_seconds, self.delay_ms,
+                                    self.min_agreement_passes, self.max_tokens_per_pass, self.sample_rate)
+
+
+@dataclass
+class StreamingUpdate:
+    kind: str                                # "none" | "partial" | "final_window" | "ended"
+    promoted: int
+    completed: List[List[int]]
+    confirmed: List[int]
+    provisional: List[int]
+    total_audio_seconds: float
+    pass_encode_time: float
+    pass_decode_time: float
+
+
+class StreamingInferenceSession:
+    """StreamingInferenceSession(model:config:) for `any STTGenerationModel` (StreamingInferenceSession.swift:162, core :589-950) at the
+    token level: `feed_audio(samples, now)` / `stop(now)` return what the reference would turn into TranscriptionEvents.  `model` is a
+    WhisperModel, or `decoder(audio, prefix) -> continuation` for a host-side model."""
+
+    _KINDS = ("none", "partial", "final_window", "ended")
+
+    def __init__(self, model=None, config: Optional[StreamingConfig] = None, generation_parameters: Optional[STTGenerateParameters] = None,
+                 decoder=None):
+        self._h = C.c_void_p()
+        cfg = (config or StreamingConfig())._c()
+        self._keep = None
+        if decoder is not None:
+            def _cb(user, pcm, n, prefix, n_prefix, out, cap, n_out):
+                try:
+                    toks = list(decoder(np.ctypeslib.as_array(pcm, shape=(n,)).copy() if n else np.zeros(0, np.float32),
+                                        [int(prefix[i]) for i in range(n_prefix)]))[:cap]
+                    for i, t in enumerate(toks):
+                        out[i] = int(t)
+                    n_out[0] = len(toks)
+                    return 0
+                except Exception:      # the C side reports generationFailed
+                    return 1
+            self._keep = _ffi.STT_DECODE_CB(_cb)
+            _ffi.check(_ffi.lib().b2a_stt_session_create_with_decoder(self._keep, None, C.byref(cfg), C.byref(self._h)))
+        else:
+            p = generation_parameters or model.default_generation_parameters
+            sp, keep = model._params(p)
+            _ffi.check(_ffi.lib().b2a_stt_session_create(model._h, C.byref(sp), C.byref(cfg), C.byref(self._h)))
+            self._model = model            # the session borrows the model handle
+
+    def _tokens(self, which: int, window: int = 0) -> List[int]:
+        n = C.c_int32(0)
+        _ffi.check(_ffi.lib().b2a_stt_session_tokens(self._h, which, window, None, 0, C.byref(n)))
+        buf = np.zeros(max(1, n.value), dtype=np.int32)
+        _ffi.check(_ffi.lib().b2a_stt_session_tokens(self._h, which, window, _ffi.ptr(buf), len(buf), C.byref(n)))
+        return buf[:n.value].tolist()
+
+    def _update(self, u) -> StreamingUpdate:
+        return StreamingUpdate(self._KINDS[u.kind], u.promoted, [self._tokens(0, w) for w in range(u.completed_windows)], self._tokens(1),
+                               self._tokens(2), u.total_audio_s, u.pass_encode_time, u.pass_decode_time)
+
+    def feed_audio(self, samples, now: Optional[float] = None) -> StreamingUpdate:
+        x = np.ascontiguousarray(samples, dtype=np.float32).reshape(-1)
+        u = _ffi.SttStreamUpdate()
+        _ffi.check(_ffi.lib().b2a_stt_session_feed(self._h, _ffi.ptr(x) if len(x) else None, len(x), time.monotonic() if now is None else float(now), C.byref(u)))
+        return self._update(u)
+
+    def stop(self, now: Optional[float] = None) -> StreamingUpdate:
+        u = _ffi.SttStreamUpdate()
+        _ffi.check(_ffi.lib().b2a_stt_session_stop(self._h, time.monotonic() if now is None else float(now), C.byref(u)))
+        return self._update(u)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            _ffi.lib().b2a_stt_session_destroy(self._h)
+            self._h = None
