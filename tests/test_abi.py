@@ -100,3 +100,31 @@ def test_bench_cpu_arm_thread_budget():
     import bench
     n = bench.usable_cpus()
     assert 1 <= n <= (os.cpu_count() or 1) and n <= len(os.sched_getaffinity(0))
+
+
+def test_bench_workload_accounting():
+    """The numbers bench.py's line is built from: BASELINE.md's audio per utterance, SURVEY.md 8(d)'s bytes per decode step, the
+    prompt that makes parseOutput crop like a real checkpoint, and the sharding of the two scaling modes."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+    import bench
+    from oracle import llama
+    assert bench.frames_per_utterance() == 73 and abs(bench.audio_seconds_per_utterance() - 73 * 2048 / 24000.0) < 1e-12     # 6.229 s
+    ids = bench.make_prompts(0)
+    assert ids.shape == (8, 64) and (ids[:, 0] == 128259).all() and (ids[:, -1] == 128257).all()
+    # parseOutput on prompt + 512 generated code tokens keeps exactly the 73 whole frames after the last START_OF_SPEECH
+    gen = [128266 + (i % 7) * 4096 + 5 for i in range(512)]
+    rows = llama.parse_output(np.asarray([ids[0].tolist() + gen]))
+    assert len(rows) == 1 and len(rows[0]) == 73 * 7
+    layers = llama.codes_from_code_list(rows[0])
+    assert [int(c.shape[1]) for c in layers] == [73, 146, 292]
+    cfg = bench.ORPHEUS
+    H, I, V, L = 3072, 8192, 156940, 28
+    per_layer = (24 + 16) * 128 * H + H * 24 * 128 + 3 * I * H
+    assert bench.weight_bytes(cfg) == 2 * (L * per_layer + V * H)                       # every matrix once + the tied head, bf16
+    assert bench.kv_bytes(cfg, 8, 320, 2) == 2 * 8 * 8 * 320 * 128 * 2 * 28             # bf16 K and V at the loop's mean context
+    assert bench.kv_bytes(cfg, 8, 320, 4) == 2 * bench.kv_bytes(cfg, 8, 320, 2)
+    assert abs((bench.weight_bytes(cfg) + bench.kv_bytes(cfg, 8, 320, 2)) / 1e9 - 6.895) < 1e-3
+    assert bench.bench_config(cfg, 4, "weak")["global_batch"] == 32 and bench.bench_config(cfg, 4, "strong")["global_batch"] == 8
+    assert bench.bench_config(cfg, 8, "strong")["rows_per_gpu"] == 1
